@@ -1,0 +1,165 @@
+/*
+ * waves_b200.h -- C ABI of the B200-native Waves.jl acoustic RK4 hot path.
+ *
+ * Drop-in boundary.  The reference (gladisor/Waves.jl) has no FFI:
+ * the seam is Julia dispatch on
+ *     (env::WaveEnv)(action)                      src/env.jl:91-121      (B1)
+ *     (iter::Integrator)(ui, tspan, θ)            src/dynamics.jl:37-53  (B2)
+ *     runge_kutta(f,u,t,θ,dt) / dyn(x,t,θ)        src/dynamics.jl:9-16, :179-188 (B3)
+ * Each entry point below names the reference interface it replaces.  A Julia `ccall`
+ * shim (waves.jl_b200/julia/WavesB200.jl) and the Python ctypes mirror
+ * (waves.jl_b200/) both bind exactly these symbols.
+ *
+ * Conventions
+ *  - Plain C types only; every pointer may be a HOST or a DEVICE pointer (the library
+ *    asks the CUDA runtime which) unless stated otherwise.  The caller owns all buffers
+ *    it passes; the handle owns all device memory and streams it creates.
+ *  - Layout is the reference's column-major (nx, ny, field[, frame]) == C-order
+ *    [frame][field][ny][nx], x fastest, fields tot{U,Vx,Vy,Psix,Psiy,Omega}, inc{...}
+ *    (src/dynamics.jl:152-157,185-187).
+ *  - Every function returns 0 on success, non-zero on failure; waves_last_error()
+ *    returns a thread-local message.  Nothing throws across the ABI.  There is NO CPU
+ *    fallback: without a CUDA device waves_create fails.
+ *  - A handle is not thread-safe.  Calls that write caller buffers synchronise before
+ *    returning; everything else is asynchronous on the handle's stream.
+ */
+#ifndef WAVES_B200_H
+#define WAVES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WAVES_B200_VERSION 100 /* 0.1.0 */
+#define WAVES_FIELDS 12
+#define WAVES_HALO 4 /* ghost rows per side of a slab: one per RK4 stage */
+
+typedef struct waves_handle waves_handle;
+
+/* integrate/step modes */
+#define WAVES_MODE_FUSED 0 /* one fused kernel per RK4 step (the product path) */
+#define WAVES_MODE_EXACT 1 /* per-stage kernels in the reference's exact float32 evaluation order */
+
+/* adjoint modes (src/dynamics.jl:97-118) */
+#define WAVES_ADJ_EXACT 0  /* exact discrete adjoint  lambda_i = a_i + (I+J_i^T) lambda_{i+1} */
+#define WAVES_ADJ_COMPAT 1 /* the reference loop as written (one extra step-vjp) */
+
+/*
+ * Mirrors AcousticDynamics(dim, c0, pml_width, pml_scale) (src/dynamics.jl:141-149)
+ * plus the WaveEnv keyword arguments that reach the integrator (src/env.jl:37-50).
+ */
+typedef struct waves_config {
+    int32_t nx, ny;     /* local grid points; the reference needs nx == ny_global (σy = σx', src/dynamics.jl:162) */
+    int32_t n_env;      /* independent environments held by this handle (>= 1) */
+    int32_t device;     /* CUDA device ordinal */
+    float c0;           /* ambient wave speed, dyn.c0 */
+    float dt;           /* iter.dt */
+    float pml_width;    /* used only when sigma == NULL */
+    float pml_scale;    /* used only when sigma == NULL */
+    const float *x;     /* HOST, nx values: dim.x (src/dims.jl:56-60) */
+    const float *y;     /* HOST, ny_global values: dim.y */
+    const float *sigma; /* HOST, optional nx values: dyn.pml[:,1]; NULL -> build_pml (src/pml.jl:21-29) from x */
+    const float *grad8; /* HOST, optional 8 values: rows of dyn.grad = first(3) central(2) last(3);
+                           NULL -> gradient(x) (src/operators.jl:10-22) */
+    float d_omega;      /* get_dx(dim)*get_dy(dim) (src/env.jl:108); <= 0 -> computed from x, y */
+    /* slab decomposition of ONE large grid along y (dim 2): this handle owns global rows
+       [row0, row0+ny) of ny_global.  Single-device use: ny_global = ny, row0 = 0. */
+    int32_t ny_global;
+    int32_t row0;
+    uint32_t flags;     /* reserved, 0 */
+} waves_config;
+
+int waves_version(void);
+const char *waves_last_error(void);
+
+/* AcousticDynamics + Integrator + WaveEnv state allocation (src/dynamics.jl:141-149, src/env.jl:52-66). */
+int waves_create(const waves_config *cfg, waves_handle **out);
+int waves_destroy(waves_handle *h);
+int waves_sync(waves_handle *h);
+
+/* env.wave[:,:,:,end] <- u12 / -> u12 : (12, ny, nx) floats (src/env.jl:102,116). env = -1: all envs, contiguous. */
+int waves_set_state(waves_handle *h, int env, const float *u12);
+int waves_get_state(waves_handle *h, int env, float *u12);
+
+/* θ[2] = F: Source / RandomPosGaussianSource (src/sources.jl:10-23,25-69): f(t) = shape .* sin(2π t freq).
+ * shape (ny, nx) plane; shape == NULL -> NoSource (src/sources.jl:7-8). */
+int waves_set_source(waves_handle *h, int env, const float *shape, float freq);
+
+/* θ[1] = C: t -> speed(DesignInterpolator(initial, final, ti, tf)(t), grid, c0)
+ * (src/env.jl:96-99, src/designs.jl:99-116, 274-292).  cyl0/cyl1: HOST (ncyl,4) rows {x, y, r, c}
+ * of the stacked cylinders (Cloak: config then core, src/designs.jl:228) at ti and tf.
+ * ncyl == 0 -> NoDesign: scalar c0 (src/designs.jl:63). */
+int waves_set_design(waves_handle *h, int env, int ncyl, const float *cyl0, const float *cyl1, float ti, float tf);
+
+/* θ[1] = C: t -> a fixed speed plane c (ny, nx) (generic C closure frozen in time). NULL clears it. */
+int waves_set_speed_field(waves_handle *h, int env, const float *c);
+
+/* dyn(x, t, θ) (src/dynamics.jl:179-188) on the current state of `env`: du12 (12, ny, nx). EXACT order. */
+int waves_rhs(waves_handle *h, int env, float t, float *du12);
+
+/* u <- u + runge_kutta(dyn, u, t, θ, dt) for every env (src/dynamics.jl:9-16, :40-42). */
+int waves_step(waves_handle *h, float t, int mode);
+
+/*
+ * (iter::Integrator)(ui, tspan, θ) (src/dynamics.jl:37-53) fused with the energy metric of
+ * (env::WaveEnv)(action) (src/env.jl:104-114), for every env of the handle.
+ *   tspan        HOST, steps+1 times (build_tspan, src/dynamics.jl:5-7); step i uses tspan[i]
+ *   energy       nullable, (n_env, steps+1, 3) floats {tot, inc, sc}; frame 0 is the initial state
+ *   save_steps   HOST, nsave ascending step indices in [0, steps]; frames (n_env, nsave, 12, ny, nx)
+ *                (env.wave = frames 80,90,100: src/env.jl:116)
+ *   u_tot_traj / u_inc_traj  nullable (n_env, steps+1, ny, nx): the full U trajectories that
+ *                (env::WaveEnv)(action) returns for rendering (src/env.jl:120, src/plot.jl:25)
+ * The state of the handle is left at the last step.
+ */
+int waves_integrate(waves_handle *h, const float *tspan, int steps, int mode, float *energy, const int32_t *save_steps,
+                    int nsave, float *frames, float *u_tot_traj, float *u_inc_traj);
+
+/* tot/inc/sc energy of the current state (src/env.jl:104-111): e3 (n_env, 3). */
+int waves_energy(waves_handle *h, float *e3);
+
+/* ---- slab decomposition (one process per GPU) ----------------------------------- */
+/* Device pointers + sizes of the rows a neighbour needs / provides after every RK4 step:
+ * send_lo/send_hi: the first/last WAVES_HALO owned rows; recv_lo/recv_hi: the ghost rows.
+ * Each region is n_env*12 row blocks of WAVES_HALO*pitch floats, strided by plane_stride floats. */
+typedef struct waves_halo_desc {
+    float *send_lo, *send_hi, *recv_lo, *recv_hi; /* NULL where there is no neighbour */
+    int64_t plane_stride;                          /* floats between consecutive field planes */
+    int32_t n_planes;                              /* n_env*12 */
+    int32_t block_floats;                          /* WAVES_HALO * pitch */
+    int32_t pitch;                                 /* floats per row in device memory */
+} waves_halo_desc;
+int waves_halo_describe(waves_handle *h, waves_halo_desc *out);
+/* Pack the send rows into two contiguous device buffers / unpack received ghost rows.
+ * Buffers are n_planes*block_floats floats each (device). NULL skips that side. */
+int waves_halo_pack(waves_handle *h, float *lo_buf, float *hi_buf);
+int waves_halo_unpack(waves_handle *h, const float *lo_buf, const float *hi_buf);
+/* CUDA stream (cudaStream_t) the handle launches on, so the caller can order NCCL calls with it. */
+void *waves_stream(waves_handle *h);
+
+/* ---- host-side builders restating reference constructors (used by the Python mirror and tests) --- */
+/* collect(range(start, stop, n)) for Float32 endpoints, src/dims.jl:56-60 (Float64 interpolation, one rounding). */
+int waves_range_f32(float start, float stop, int n, float *out);
+/* build_pml(::TwoDim) 1-D profile, src/pml.jl:21-29 */
+int waves_build_pml_profile(const float *x, int n, float width, float scale, float *out);
+/* gradient(x) rows first(3) central(2) last(3), src/operators.jl:10-22 */
+int waves_build_gradient8(const float *x, int n, float *out8);
+/* build_normal(grid, mu, sigma, a), src/utils.jl:12-18: out (ny, nx) */
+int waves_build_normal(const float *x, int nx, const float *y, int ny, int n, const float *mu_xy, const float *sigma,
+                       const float *a, float *out);
+/* get_dx(dim) = mean(diff(x)), src/dims.jl:126 */
+float waves_mean_diff(const float *x, int n);
+
+/* ---- introspection for benchmarks -------------------------------------------------------- */
+/* number of kernel launches issued by this handle so far */
+int64_t waves_launch_count(waves_handle *h);
+/* average device time (ms) of the fused step kernel launches since the last reset, measured with
+ * CUDA events on the handle's stream when profiling is on (waves_profile(h, 1)). */
+int waves_profile(waves_handle *h, int on);
+int waves_profile_read(waves_handle *h, double *fused_ms_total, int64_t *fused_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVES_B200_H */

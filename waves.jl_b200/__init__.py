@@ -1,0 +1,15 @@
+"""waves.jl_b200 -- B200-native drop-in for the Waves.jl acoustic RK4 hot path.
+
+The computation lives in csrc/ (hand-written sm_100a CUDA behind the C ABI of include/waves_b200.h);
+this package is the host-side mirror of the reference's call surface for that path.
+"""
+from . import _lib
+from ._lib import WavesError, build
+from .engine import MODE_EXACT, MODE_FUSED, Engine
+from .env import AcousticDynamics, Integrator, WaveEnv
+from .host import (AIR, WATER, Cloak, Cylinders, DesignInterpolator, DesignSpace, NoSource, RandomPosGaussianSource,
+                   Source, TwoDim, build_action_space, build_gradient, build_grid, build_normal, build_pml,
+                   build_radii_design_space, build_triple_ring_design_space, build_tspan, build_wave, get_dx, get_dy,
+                   hexagon_ring, julia_range)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,290 @@
+// Per-stage CUDA kernels that evaluate the reference's dynamics in its EXACT float32 evaluation
+// order (compiled with -fmad=false: Julia never contracts a*b+c).  They serve WAVES_MODE_EXACT,
+// waves_rhs (B3 parity, src/dynamics.jl:179-188) and the energy metric (src/env.jl:104-114), and are
+// the on-device cross-check of the fused kernel.  sm_100a only.
+#include "waves_internal.h"
+
+namespace {
+
+// ---- stage table: RK4 stage times (src/dynamics.jl:10-13) and source factors (src/sources.jl:68) ---
+__global__ void k_stage_table(const float *__restrict__ tspan, int steps, const EnvParams *__restrict__ env,
+                              int n_env, float dt, float hdt, float *__restrict__ table) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= steps * n_env) return;
+    int e = idx / steps, n = idx - e * steps;
+    float t = tspan[n];
+    float ts[3] = {t, t + hdt, t + dt};
+    float *row = table + (size_t)idx * STAGE_ROW;
+    const float two_pi = 2.0f * 3.14159274101257324f;  // 2.0f0 * Float32(π)
+    for (int s = 0; s < 3; ++s) {
+        row[s] = ts[s];
+        float arg = (two_pi * ts[s]) * env[e].freq;
+        // Julia's sin(::Float32) is the rounding of an accurate double evaluation
+        row[3 + s] = env[e].has_source ? (float)sin((double)arg) : 0.0f;
+    }
+    row[6] = 0.f;
+    row[7] = 0.f;
+}
+
+// DesignInterpolator(t) for one scalar parameter (src/designs.jl:287-292, :45-49)
+__device__ __forceinline__ float interp_param(float p0, float p1, float ti, float tf, float t) {
+    float dt = tf - ti;
+    dt = dt > 0.0f ? dt : 1.0f;
+    float inv = 1.0f / dt;
+    float tc = fminf(fmaxf(t, ti), tf);
+    float s = tc - ti;
+    float dy = p1 + (p0 * -1.0f);
+    float slope = dy * inv;
+    return p0 + (slope * s);
+}
+
+// speed(design(t), grid, c0)^2 (src/designs.jl:99-116) -> b2 plane of each env
+__global__ void k_speed2(GridP gp, const EnvParams *__restrict__ env, const float *__restrict__ cyl0,
+                         const float *__restrict__ cyl1, int cyl_cap, const float *__restrict__ cplane, int env0,
+                         const float *__restrict__ table, int steps, int step, int stage, float *__restrict__ b2) {
+    extern __shared__ float cur[];  // [ncyl][4]
+    int e = env0 + blockIdx.z;
+    const EnvParams ep = env[e];
+    float t = table[((size_t)e * steps + step) * STAGE_ROW + (stage == 0 ? 0 : (stage == 3 ? 2 : 1))];
+    for (int k = threadIdx.y * blockDim.x + threadIdx.x; k < 4 * ep.ncyl; k += blockDim.x * blockDim.y) {
+        size_t o = (size_t)e * cyl_cap * 4 + k;
+        cur[k] = interp_param(cyl0[o], cyl1[o], ep.ti, ep.tf, t);
+    }
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int jl = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= gp.nx || jl >= gp.ny_alloc) return;
+    size_t q = (size_t)e * gp.plane + (size_t)jl * gp.nxp + i;
+    if (ep.has_cplane) {
+        float c = cplane[q];
+        b2[q] = c * c;
+        return;
+    }
+    int g = gp.grow0 + jl;
+    float xs = gp.x[i], ys = gp.y[min(max(g, 0), gp.ny_global - 1)];
+    int cnt = 0;
+    float cd = 0.0f;
+    for (int k = 0; k < ep.ncyl; ++k) {
+        float ddx = xs - cur[4 * k], ddy = ys - cur[4 * k + 1];
+        float r2 = cur[4 * k + 2] * cur[4 * k + 2];
+        float d2 = (ddx * ddx) + (ddy * ddy);
+        bool m = d2 < r2;
+        cnt += m;
+        cd = cd + (m ? 1.0f : 0.0f) * cur[4 * k + 3];
+    }
+    float c = ((cnt == 0 ? 1.0f : 0.0f) * gp.c0) + cd;
+    b2[q] = c * c;
+}
+
+struct Plane {
+    const float *p;
+    const float *sh;  // source shape plane or nullptr
+    float s;          // source factor
+    __device__ __forceinline__ float at(long long q) const { return sh ? (p[q] + (sh[q] * s)) : p[q]; }
+};
+
+// ∇*u along x (src/operators.jl:45), SparseMatrixCSC accumulation order
+__device__ __forceinline__ float d_x(const GridP &gp, const Plane &pl, long long row, int i) {
+    int n = gp.nx;
+    if (i == 0)
+        return ((gp.g_first[0] * pl.at(row)) + (gp.g_first[1] * pl.at(row + 1))) + (gp.g_first[2] * pl.at(row + 2));
+    if (i == n - 1)
+        return ((gp.g_last[0] * pl.at(row + n - 3)) + (gp.g_last[1] * pl.at(row + n - 2))) +
+               (gp.g_last[2] * pl.at(row + n - 1));
+    return (gp.g_central[0] * pl.at(row + i - 1)) + (gp.g_central[1] * pl.at(row + i + 1));
+}
+
+// (∇*u')' along y (src/operators.jl:46); g = global row, jl = local row
+__device__ __forceinline__ float d_y(const GridP &gp, const Plane &pl, long long base, int jl, int g, int i) {
+    long long P = gp.nxp;
+    if (g == 0)
+        return ((gp.g_first[0] * pl.at(base + jl * P + i)) + (gp.g_first[1] * pl.at(base + (jl + 1) * P + i))) +
+               (gp.g_first[2] * pl.at(base + (jl + 2) * P + i));
+    if (g == gp.ny_global - 1)
+        return ((gp.g_last[0] * pl.at(base + (jl - 2) * P + i)) + (gp.g_last[1] * pl.at(base + (jl - 1) * P + i))) +
+               (gp.g_last[2] * pl.at(base + jl * P + i));
+    int jm = max(jl - 1, 0), jp = min(jl + 1, gp.ny_alloc - 1);  // clamped only in never-consumed ghost rows
+    return (gp.g_central[0] * pl.at(base + jm * P + i)) + (gp.g_central[1] * pl.at(base + jp * P + i));
+}
+
+// acoustic_dynamics for both wavefields (src/dynamics.jl:151-188); blockIdx.z = env*2 + wavefield
+__global__ void __launch_bounds__(256)
+k_rhs_exact(GridP gp, const EnvParams *__restrict__ env, int env0, const float *__restrict__ u, float *__restrict__ kout,
+            const float *__restrict__ b2, const float *__restrict__ shape, const float *__restrict__ table, int steps,
+            int step, int stage) {
+    int e = env0 + (blockIdx.z >> 1), w = blockIdx.z & 1;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int jl = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= gp.nx || jl >= gp.ny_alloc) return;
+    int g = gp.grow0 + jl;
+    if (g < 0 || g >= gp.ny_global) return;
+    const EnvParams ep = env[e];
+    const long long P = gp.plane;
+    const float *x = u + (long long)e * gp.env_stride + (long long)w * 6 * P;
+    float *k = kout + (long long)e * gp.env_stride + (long long)w * 6 * P;
+    float sf = table[((size_t)e * steps + step) * STAGE_ROW + 3 + (stage == 0 ? 0 : (stage == 3 ? 2 : 1))];
+    const float *sh = shape + (long long)e * P;
+    Plane pU{x, nullptr, 0.f}, pUf{x, sh, sf}, pVx{x + P, nullptr, 0.f}, pVy{x + 2 * P, nullptr, 0.f};
+    if (!ep.has_source) pUf.sh = nullptr;  // U .+ 0.0f0
+    long long row = (long long)jl * gp.nxp, q = row + i;
+    float b = (w == 0 && (ep.ncyl > 0 || ep.has_cplane)) ? b2[(long long)e * P + q] : gp.b0;
+    float sx = gp.sigma[i], sy = gp.sigma[g];
+    bool border = (i == 0) || (i == gp.nx - 1) || (g == 0) || (g == gp.ny_global - 1);
+    float bc = border ? 0.0f : 1.0f;  // build_dirichlet (src/dims.jl:117-124)
+    float U = pU.at(q), Vx = pVx.at(q), Vy = pVy.at(q);
+    float Px = x[3 * P + q], Py = x[4 * P + q], Om = x[5 * P + q];
+    float Vxx = d_x(gp, pVx, row, i);
+    float Vyy = d_y(gp, pVy, 0, jl, g, i);
+    float Ux = d_x(gp, pUf, row, i);
+    float Uy = d_y(gp, pUf, 0, jl, g, i);
+    float dU = ((((b * (Vxx + Vyy)) + Px) + Py) - ((sx + sy) * U)) - Om;
+    k[q] = bc * dU;
+    k[P + q] = Ux - (sx * Vx);
+    k[2 * P + q] = Uy - (sy * Vy);
+    k[3 * P + q] = (b * sx) * Vyy;
+    k[4 * P + q] = (b * sy) * Vxx;
+    k[5 * P + q] = (sx * sy) * U;
+}
+
+// runge_kutta accumulation (src/dynamics.jl:10-15): k1 .+ 2*k2 .+ 2*k3 .+ k4 left to right; y = u .+ (a*k)
+__global__ void k_rk_update(long long n, int stage, float a, const float *__restrict__ u, const float *__restrict__ k,
+                            float *__restrict__ acc, float *__restrict__ ys) {
+    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    float kk = k[q];
+    if (stage == 0)
+        acc[q] = kk;
+    else if (stage == 3)
+        acc[q] = acc[q] + kk;
+    else
+        acc[q] = acc[q] + 2.0f * kk;
+    if (stage < 3) ys[q] = u[q] + a * kk;
+}
+
+// du = 1/6f0 * (...); return du * dt; u' = u .+ du  (src/dynamics.jl:14-15,41)
+__global__ void k_rk_final(long long n, float dt, const float *__restrict__ u, const float *__restrict__ acc,
+                           float *__restrict__ out) {
+    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const float sixth = 1.0f / 6.0f;
+    float du = sixth * acc[q];
+    out[q] = u[q] + du * dt;
+}
+
+// Energy metric (src/env.jl:104-111): Σ u_tot², Σ u_inc², Σ (u_tot-u_inc)² over owned rows, f64 accumulation.
+__global__ void __launch_bounds__(256) k_energy_partial(GridP gp, const float *__restrict__ u, double *__restrict__ part) {
+    int e = blockIdx.y;
+    const float *ut = u + (long long)e * gp.env_stride, *ui = ut + 6 * gp.plane;
+    double st = 0, si = 0, ss = 0;
+    long long cells = (long long)gp.ny_own * gp.nx;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x) {
+        int j = (int)(c / gp.nx), i = (int)(c - (long long)j * gp.nx);
+        long long q = (long long)(j + gp.ny_own0) * gp.nxp + i;
+        float a = ut[q], b = ui[q], d = a - b;
+        st += (double)a * (double)a;
+        si += (double)b * (double)b;
+        ss += (double)d * (double)d;
+    }
+    __shared__ double sm[3][8];
+    for (int o = 16; o > 0; o >>= 1) {
+        st += __shfl_down_sync(0xffffffffu, st, o);
+        si += __shfl_down_sync(0xffffffffu, si, o);
+        ss += __shfl_down_sync(0xffffffffu, ss, o);
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        sm[0][w] = st;
+        sm[1][w] = si;
+        sm[2][w] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0;
+        for (int k = 0; k < 8; ++k) s += sm[threadIdx.x][k];
+        part[((size_t)e * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = s;
+    }
+}
+
+__global__ void k_energy_final(const double *__restrict__ part, int nblk, float d_omega, float *__restrict__ e3,
+                               int env_stride3) {
+    int e = blockIdx.x;
+    if (threadIdx.x < 3) {
+        double s = 0;
+        for (int k = 0; k < nblk; ++k) s += part[((size_t)e * nblk + k) * 3 + threadIdx.x];
+        e3[(size_t)e * env_stride3 + threadIdx.x] = (float)s * d_omega;
+    }
+}
+
+// Halo pack/unpack for slab decomposition: WAVES_HALO rows x nxp floats per field plane.
+__global__ void k_halo_copy(GridP gp, float *__restrict__ u, float *__restrict__ lo, float *__restrict__ hi, int unpack) {
+    int blk = WAVES_HALO * gp.nxp;
+    long long total = (long long)gp.n_env * 12 * blk;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        long long pl = q / blk;
+        int r = (int)(q - pl * blk);
+        float *base = u + pl * gp.plane;
+        if (!unpack) {
+            if (lo) lo[q] = base[(long long)gp.ny_own0 * gp.nxp + r];
+            if (hi) hi[q] = base[(long long)(gp.ny_own0 + gp.ny_own - WAVES_HALO) * gp.nxp + r];
+        } else {
+            if (lo) base[(long long)(gp.ny_own0 - WAVES_HALO) * gp.nxp + r] = lo[q];
+            if (hi) base[(long long)(gp.ny_own0 + gp.ny_own) * gp.nxp + r] = hi[q];
+        }
+    }
+}
+
+}  // namespace
+
+void launch_stage_table(waves_handle *h, const float *d_tspan, int steps, float *d_table) {
+    int n = steps * h->gp.n_env;
+    k_stage_table<<<(n + 127) / 128, 128, 0, h->stream>>>(d_tspan, steps, h->d_env, h->gp.n_env, h->gp.dt, h->gp.hdt,
+                                                           d_table);
+    h->launches++;
+}
+
+void launch_speed2(waves_handle *h, int env0, int nenv, const float *d_table, int steps, int step, int stage,
+                   float *b2) {
+    dim3 blk(32, 8), grd((h->gp.nx + 31) / 32, (h->gp.ny_alloc + 7) / 8, nenv);
+    size_t sm = sizeof(float) * 4 * (size_t)(h->cyl_cap > 0 ? h->cyl_cap : 1);
+    k_speed2<<<grd, blk, sm, h->stream>>>(h->gp, h->d_env, h->d_cyl0, h->d_cyl1, h->cyl_cap, h->cplane, env0, d_table,
+                                          steps, step, stage, b2);
+    h->launches++;
+}
+
+void launch_rhs_exact(waves_handle *h, int env0, int nenv, const float *u_in, float *k_out, const float *d_table,
+                      int steps, int step, int stage) {
+    dim3 blk(32, 8), grd((h->gp.nx + 31) / 32, (h->gp.ny_alloc + 7) / 8, nenv * 2);
+    k_rhs_exact<<<grd, blk, 0, h->stream>>>(h->gp, h->d_env, env0, u_in, k_out, h->b2, h->shape, d_table, steps, step,
+                                            stage);
+    h->launches++;
+}
+
+void launch_rk_update(waves_handle *h, int stage, const float *u, const float *k, float *acc, float *ys) {
+    long long n = h->gp.env_stride * h->gp.n_env;
+    float a = stage == 2 ? h->gp.dt : h->gp.hdt;
+    k_rk_update<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, stage, a, u, k, acc, ys);
+    h->launches++;
+}
+
+void launch_rk_final(waves_handle *h, const float *u_in, const float *acc, float *u_out) {
+    long long n = h->gp.env_stride * h->gp.n_env;
+    k_rk_final<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, h->gp.dt, u_in, acc, u_out);
+    h->launches++;
+}
+
+void launch_energy(waves_handle *h, const float *u, float *d_e3, int env_stride3) {
+    dim3 grd(h->epart_blocks, h->gp.n_env);
+    k_energy_partial<<<grd, 256, 0, h->stream>>>(h->gp, u, h->d_epart);
+    k_energy_final<<<h->gp.n_env, 32, 0, h->stream>>>(h->d_epart, h->epart_blocks, h->d_omega, d_e3, env_stride3);
+    h->launches += 2;
+}
+
+void launch_pack_halo(waves_handle *h, const float *u, float *lo, float *hi) {
+    k_halo_copy<<<h->sm_count * 4, 256, 0, h->stream>>>(h->gp, const_cast<float *>(u), lo, hi, 0);
+    h->launches++;
+}
+
+void launch_unpack_halo(waves_handle *h, float *u, const float *lo, const float *hi) {
+    k_halo_copy<<<h->sm_count * 4, 256, 0, h->stream>>>(h->gp, u, const_cast<float *>(lo), const_cast<float *>(hi), 1);
+    h->launches++;
+}

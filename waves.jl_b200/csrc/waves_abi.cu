@@ -1,0 +1,633 @@
+// C ABI of the B200-native Waves.jl hot path (include/waves_b200.h): handle management, host-side
+// restatements of the reference constructors, and the orchestration of (iter::Integrator)(ui,tspan,θ)
+// + the WaveEnv energy metric.  No CPU compute path exists: everything runs on the CUDA device.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "waves_internal.h"
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#define CU_TRY(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define CHECK_H(h)                                   \
+    do {                                             \
+        if (!(h)) return fail("null waves_handle");  \
+        CU_TRY(cudaSetDevice((h)->device));          \
+    } while (0)
+
+int waves_set_error(const char *msg) { return fail("%s", msg); }
+
+extern "C" int waves_version(void) { return WAVES_B200_VERSION; }
+extern "C" const char *waves_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// Host builders (reference constructors restated in float32, same evaluation order)
+// ---------------------------------------------------------------------------------------------
+extern "C" int waves_range_f32(float start, float stop, int n, float *out) {
+    if (n < 1 || !out) return fail("waves_range_f32: bad arguments");
+    if (n == 1) {
+        out[0] = start;
+        return 0;
+    }
+    // Julia evaluates Float32 ranges in Float64 and rounds each element once (src/dims.jl:56-60)
+    double a = start, b = stop;
+    for (int i = 0; i < n; ++i) out[i] = (float)((((double)(n - 1 - i)) * a + ((double)i) * b) / (double)(n - 1));
+    out[0] = start;
+    out[n - 1] = stop;
+    return 0;
+}
+
+extern "C" int waves_build_pml_profile(const float *x, int n, float width, float scale, float *out) {
+    // src/pml.jl:21-29
+    if (n < 1 || !x || !out) return fail("waves_build_pml_profile: bad arguments");
+    float start = fabsf(x[0]) - width;
+    float mn = INFINITY;
+    for (int i = 0; i < n; ++i) {
+        float ax = fabsf(x[i]);
+        if (ax > start && ax < mn) mn = ax;
+    }
+    for (int i = 0; i < n; ++i) {
+        float ax = fabsf(x[i]);
+        float v = 0.0f;
+        if (ax > start) v = (ax - mn) / width;
+        float cube = (v * v) * v;
+        out[i] = cube * scale;
+    }
+    return 0;
+}
+
+extern "C" int waves_build_gradient8(const float *x, int n, float *o) {
+    // src/operators.jl:10-22: each coefficient is one float32 division by (2Δ)
+    if (n < 3 || !x || !o) return fail("waves_build_gradient8: need n >= 3");
+    float delta = (x[n - 1] - x[0]) / (float)(n - 1);
+    float two = 2.0f * delta;
+    const float f[3] = {-3.0f, 4.0f, -1.0f}, c[2] = {-1.0f, 1.0f}, l[3] = {1.0f, -4.0f, 3.0f};
+    for (int k = 0; k < 3; ++k) o[k] = f[k] / two;
+    for (int k = 0; k < 2; ++k) o[3 + k] = c[k] / two;
+    for (int k = 0; k < 3; ++k) o[5 + k] = l[k] / two;
+    return 0;
+}
+
+extern "C" int waves_build_normal(const float *x, int nx, const float *y, int ny, int n, const float *mu,
+                                  const float *sigma, const float *a, float *out) {
+    // src/utils.jl:12-18
+    if (!x || !y || !mu || !sigma || !a || !out) return fail("waves_build_normal: null argument");
+    const float two_pi = 2.0f * 3.14159274101257324f;
+    for (size_t q = 0; q < (size_t)nx * ny; ++q) out[q] = 0.0f;
+    for (int k = 0; k < n; ++k) {
+        float s2 = sigma[k] * sigma[k];
+        float coef = 1.0f / (two_pi * s2);
+        float den = 2.0f * s2;
+        float ca = coef * a[k];
+        for (int j = 0; j < ny; ++j) {
+            float dy = y[j] - mu[2 * k + 1];
+            float dy2 = dy * dy;
+            for (int i = 0; i < nx; ++i) {
+                float dx = x[i] - mu[2 * k];
+                float r2 = (dx * dx) + dy2;
+                float e = (float)exp((double)((-r2) / den));
+                float fk = ca * e;
+                size_t q = (size_t)j * nx + i;
+                out[q] = k == 0 ? fk : out[q] + fk;
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" float waves_mean_diff(const float *x, int n) {
+    // Flux.mean(diff(x)) (src/dims.jl:126): float32 differences, pairwise-summed in the reference;
+    // accumulated in double here (agrees to <= 1 ulp)
+    double s = 0;
+    for (int i = 0; i + 1 < n; ++i) s += (double)(float)(x[i + 1] - x[i]);
+    return (float)((float)s / (float)(n - 1));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Handle
+// ---------------------------------------------------------------------------------------------
+static void free_handle(waves_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    float **bufs[] = {&h->u[0], &h->u[1], &h->k,      &h->ys,     &h->acc,    &h->b2,     &h->shape,  &h->cplane,
+                      &h->d_x,  &h->d_y,  &h->d_sigma, &h->d_cyl0, &h->d_cyl1, &h->d_tspan, &h->d_stage, &h->d_energy};
+    for (auto b : bufs)
+        if (*b) cudaFree(*b);
+    if (h->d_env) cudaFree(h->d_env);
+    if (h->d_epart) cudaFree(h->d_epart);
+    fused_release(h);
+    free(h->h_env);
+    free(h->h_cyl0);
+    free(h->h_cyl1);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int waves_create(const waves_config *cfg, waves_handle **out) {
+    if (!cfg || !out) return fail("waves_create: null argument");
+    *out = nullptr;
+    int ny_global = cfg->ny_global > 0 ? cfg->ny_global : cfg->ny;
+    if (cfg->nx < 32 || cfg->ny < 8) return fail("waves_create: need nx >= 32 and ny >= 8 (got %d x %d)", cfg->nx, cfg->ny);
+    if (cfg->nx != ny_global)
+        return fail("waves_create: nx (%d) must equal ny_global (%d): the reference takes sigma_y = sigma_x' "
+                    "(src/dynamics.jl:162)", cfg->nx, ny_global);
+    if (cfg->n_env < 1) return fail("waves_create: n_env must be >= 1");
+    if (!cfg->x || !cfg->y) return fail("waves_create: x and y grids are required");
+    if (cfg->row0 < 0 || cfg->row0 + cfg->ny > ny_global) return fail("waves_create: slab rows out of range");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail("waves_create: no CUDA device (%s); this library has no CPU path",
+                    ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("waves_create: device %d out of range (%d)", cfg->device, ndev);
+    CU_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail("waves_create: needs an sm_100a device (Blackwell B200); found sm_%d%d", prop.major, prop.minor);
+
+    waves_handle *h = new waves_handle();
+    memset(h, 0, sizeof(*h));
+    h->device = cfg->device;
+    h->sm_count = prop.multiProcessorCount;
+    GridP &gp = h->gp;
+    gp.nx = cfg->nx;
+    gp.nxp = (cfg->nx + 3) & ~3;
+    int gtop = cfg->row0 > 0 ? WAVES_HALO : 0;
+    int gbot = cfg->row0 + cfg->ny < ny_global ? WAVES_HALO : 0;
+    gp.ny_own0 = gtop;
+    gp.ny_own = cfg->ny;
+    gp.ny_alloc = cfg->ny + gtop + gbot;
+    gp.ny_global = ny_global;
+    gp.grow0 = cfg->row0 - gtop;
+    gp.n_env = cfg->n_env;
+    gp.plane = (long long)gp.ny_alloc * gp.nxp;
+    gp.env_stride = 12 * gp.plane;
+    gp.c0 = cfg->c0;
+    gp.b0 = cfg->c0 * cfg->c0;
+    gp.dt = cfg->dt;
+    gp.hdt = 0.5f * cfg->dt;
+
+    std::vector<float> sig(cfg->nx), g8(8);
+    if (cfg->sigma)
+        memcpy(sig.data(), cfg->sigma, sizeof(float) * cfg->nx);
+    else if (waves_build_pml_profile(cfg->x, cfg->nx, cfg->pml_width, cfg->pml_scale, sig.data()))
+        return 1;
+    if (cfg->grad8)
+        memcpy(g8.data(), cfg->grad8, sizeof(float) * 8);
+    else if (waves_build_gradient8(cfg->x, cfg->nx, g8.data()))
+        return 1;
+    memcpy(gp.g_first, g8.data(), 12);
+    memcpy(gp.g_central, g8.data() + 3, 8);
+    memcpy(gp.g_last, g8.data() + 5, 12);
+    h->d_omega = cfg->d_omega > 0 ? cfg->d_omega
+                                  : (float)(waves_mean_diff(cfg->x, cfg->nx) * waves_mean_diff(cfg->y, ny_global));
+
+#define ALLOC(ptr, count)                                                                     \
+    do {                                                                                      \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), sizeof(*(ptr)) * (size_t)(count));       \
+        if (e_ != cudaSuccess) {                                                              \
+            free_handle(h);                                                                   \
+            return fail("cudaMalloc(%s, %zu B): %s", #ptr, sizeof(*(ptr)) * (size_t)(count), cudaGetErrorString(e_)); \
+        }                                                                                     \
+        cudaMemset((ptr), 0, sizeof(*(ptr)) * (size_t)(count));                               \
+    } while (0)
+
+    cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    size_t state = (size_t)gp.env_stride * gp.n_env;
+    ALLOC(h->u[0], state);
+    ALLOC(h->u[1], state);
+    ALLOC(h->shape, (size_t)gp.plane * gp.n_env);
+    ALLOC(h->d_x, gp.nx);
+    ALLOC(h->d_y, ny_global);
+    ALLOC(h->d_sigma, gp.nx);
+    ALLOC(h->d_env, gp.n_env);
+    h->cyl_cap = 32;
+    ALLOC(h->d_cyl0, (size_t)gp.n_env * h->cyl_cap * 4);
+    ALLOC(h->d_cyl1, (size_t)gp.n_env * h->cyl_cap * 4);
+    h->h_cyl0 = (float *)calloc((size_t)gp.n_env * h->cyl_cap * 4, sizeof(float));
+    h->h_cyl1 = (float *)calloc((size_t)gp.n_env * h->cyl_cap * 4, sizeof(float));
+    h->h_env = (EnvParams *)calloc(gp.n_env, sizeof(EnvParams));
+    h->epart_blocks = 64;
+    ALLOC(h->d_epart, (size_t)gp.n_env * h->epart_blocks * 3);
+    cudaMemcpy(h->d_x, cfg->x, sizeof(float) * gp.nx, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_y, cfg->y, sizeof(float) * ny_global, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_sigma, sig.data(), sizeof(float) * gp.nx, cudaMemcpyHostToDevice);
+    gp.x = h->d_x;
+    gp.y = h->d_y;
+    gp.sigma = h->d_sigma;
+    h->env_dirty = true;
+    h->cyl_dirty = true;
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    if (fused_prepare(h)) {
+        free_handle(h);
+        return 1;  // message set by fused_prepare
+    }
+    ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) {
+        free_handle(h);
+        return fail("waves_create: %s", cudaGetErrorString(ce));
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int waves_destroy(waves_handle *h) {
+    free_handle(h);
+    return 0;
+}
+
+extern "C" int waves_sync(waves_handle *h) {
+    CHECK_H(h);
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" void *waves_stream(waves_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+static int flush_params(waves_handle *h) {
+    if (h->env_dirty) {
+        CU_TRY(cudaMemcpyAsync(h->d_env, h->h_env, sizeof(EnvParams) * h->gp.n_env, cudaMemcpyHostToDevice, h->stream));
+        h->env_dirty = false;
+    }
+    if (h->cyl_dirty) {
+        size_t n = sizeof(float) * 4 * (size_t)h->cyl_cap * h->gp.n_env;
+        CU_TRY(cudaMemcpyAsync(h->d_cyl0, h->h_cyl0, n, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(cudaMemcpyAsync(h->d_cyl1, h->h_cyl1, n, cudaMemcpyHostToDevice, h->stream));
+        h->cyl_dirty = false;
+    }
+    return 0;
+}
+
+// copy a dense (rows, nx) block <-> the pitched owned rows of one field plane
+static int copy_plane(waves_handle *h, float *dev_plane, const float *src, float *dst, int planes) {
+    const GridP &gp = h->gp;
+    for (int p = 0; p < planes; ++p) {
+        float *d = dev_plane + (size_t)p * gp.plane + (size_t)gp.ny_own0 * gp.nxp;
+        if (src)
+            CU_TRY(cudaMemcpy2DAsync(d, sizeof(float) * gp.nxp, src + (size_t)p * gp.ny_own * gp.nx, sizeof(float) * gp.nx,
+                                     sizeof(float) * gp.nx, gp.ny_own, cudaMemcpyDefault, h->stream));
+        else
+            CU_TRY(cudaMemcpy2DAsync(dst + (size_t)p * gp.ny_own * gp.nx, sizeof(float) * gp.nx, d, sizeof(float) * gp.nxp,
+                                     sizeof(float) * gp.nx, gp.ny_own, cudaMemcpyDefault, h->stream));
+    }
+    return 0;
+}
+
+static int copy_planes_fast(waves_handle *h, float *dev_plane, const float *src, float *dst, int planes) {
+    // without ghost rows consecutive planes are consecutive rows: one 2-D copy
+    const GridP &gp = h->gp;
+    if (gp.ny_alloc != gp.ny_own) return copy_plane(h, dev_plane, src, dst, planes);
+    size_t rows = (size_t)planes * gp.ny_own;
+    if (src)
+        CU_TRY(cudaMemcpy2DAsync(dev_plane, sizeof(float) * gp.nxp, src, sizeof(float) * gp.nx, sizeof(float) * gp.nx, rows,
+                                 cudaMemcpyDefault, h->stream));
+    else
+        CU_TRY(cudaMemcpy2DAsync(dst, sizeof(float) * gp.nx, dev_plane, sizeof(float) * gp.nxp, sizeof(float) * gp.nx, rows,
+                                 cudaMemcpyDefault, h->stream));
+    return 0;
+}
+
+extern "C" int waves_set_state(waves_handle *h, int env, const float *u12) {
+    CHECK_H(h);
+    if (!u12) return fail("waves_set_state: null buffer");
+    const GridP &gp = h->gp;
+    if (env >= gp.n_env) return fail("waves_set_state: env %d out of range", env);
+    int e0 = env < 0 ? 0 : env, e1 = env < 0 ? gp.n_env : env + 1;
+    size_t per_env = (size_t)12 * gp.ny_own * gp.nx;
+    for (int e = e0; e < e1; ++e)
+        if (copy_planes_fast(h, h->u[h->cur] + (size_t)e * gp.env_stride, u12 + (size_t)(e - e0) * per_env, nullptr, 12))
+            return 1;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int waves_get_state(waves_handle *h, int env, float *u12) {
+    CHECK_H(h);
+    if (!u12) return fail("waves_get_state: null buffer");
+    const GridP &gp = h->gp;
+    if (env >= gp.n_env) return fail("waves_get_state: env %d out of range", env);
+    int e0 = env < 0 ? 0 : env, e1 = env < 0 ? gp.n_env : env + 1;
+    size_t per_env = (size_t)12 * gp.ny_own * gp.nx;
+    for (int e = e0; e < e1; ++e)
+        if (copy_planes_fast(h, h->u[h->cur] + (size_t)e * gp.env_stride, nullptr, u12 + (size_t)(e - e0) * per_env, 12))
+            return 1;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int waves_set_source(waves_handle *h, int env, const float *shape, float freq) {
+    CHECK_H(h);
+    const GridP &gp = h->gp;
+    if (env >= gp.n_env) return fail("waves_set_source: env %d out of range", env);
+    int e0 = env < 0 ? 0 : env, e1 = env < 0 ? gp.n_env : env + 1;
+    for (int e = e0; e < e1; ++e) {
+        EnvParams &ep = h->h_env[e];
+        float *d = h->shape + (size_t)e * gp.plane;
+        if (!shape) {
+            CU_TRY(cudaMemsetAsync(d, 0, sizeof(float) * gp.plane, h->stream));
+            ep.has_source = 0;
+            ep.freq = 0.f;
+            ep.src_j0 = ep.src_j1 = ep.src_i0 = ep.src_i1 = 0;
+        } else {
+            // the same plane is broadcast to every env when env < 0
+            if (copy_plane(h, d, shape, nullptr, 1)) return 1;
+            ep.has_source = 1;
+            ep.freq = freq;
+            int bb[4];
+            if (source_bbox(h, e, bb)) return 1;
+            ep.src_i0 = bb[0];
+            ep.src_i1 = bb[1];
+            ep.src_j0 = bb[2];
+            ep.src_j1 = bb[3];
+        }
+    }
+    h->env_dirty = true;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int waves_set_design(waves_handle *h, int env, int ncyl, const float *cyl0, const float *cyl1, float ti,
+                                float tf) {
+    CHECK_H(h);
+    const GridP &gp = h->gp;
+    if (env >= gp.n_env) return fail("waves_set_design: env %d out of range", env);
+    if (ncyl < 0 || (ncyl > 0 && (!cyl0 || !cyl1))) return fail("waves_set_design: bad cylinder arguments");
+    if (ncyl > h->cyl_cap) {
+        int cap = h->cyl_cap;
+        while (cap < ncyl) cap *= 2;
+        float *n0 = (float *)calloc((size_t)gp.n_env * cap * 4, sizeof(float));
+        float *n1 = (float *)calloc((size_t)gp.n_env * cap * 4, sizeof(float));
+        for (int e = 0; e < gp.n_env; ++e) {
+            memcpy(n0 + (size_t)e * cap * 4, h->h_cyl0 + (size_t)e * h->cyl_cap * 4, sizeof(float) * 4 * h->cyl_cap);
+            memcpy(n1 + (size_t)e * cap * 4, h->h_cyl1 + (size_t)e * h->cyl_cap * 4, sizeof(float) * 4 * h->cyl_cap);
+        }
+        free(h->h_cyl0);
+        free(h->h_cyl1);
+        h->h_cyl0 = n0;
+        h->h_cyl1 = n1;
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_cyl0);
+        cudaFree(h->d_cyl1);
+        CU_TRY(cudaMalloc((void **)&h->d_cyl0, sizeof(float) * 4 * (size_t)cap * gp.n_env));
+        CU_TRY(cudaMalloc((void **)&h->d_cyl1, sizeof(float) * 4 * (size_t)cap * gp.n_env));
+        h->cyl_cap = cap;
+    }
+    int e0 = env < 0 ? 0 : env, e1 = env < 0 ? gp.n_env : env + 1;
+    for (int e = e0; e < e1; ++e) {
+        EnvParams &ep = h->h_env[e];
+        ep.ncyl = ncyl;
+        ep.ti = ti;
+        ep.tf = tf;
+        if (ncyl > 0) {
+            memcpy(h->h_cyl0 + (size_t)e * h->cyl_cap * 4, cyl0, sizeof(float) * 4 * ncyl);
+            memcpy(h->h_cyl1 + (size_t)e * h->cyl_cap * 4, cyl1, sizeof(float) * 4 * ncyl);
+        }
+    }
+    h->env_dirty = true;
+    h->cyl_dirty = true;
+    return 0;
+}
+
+extern "C" int waves_set_speed_field(waves_handle *h, int env, const float *c) {
+    CHECK_H(h);
+    const GridP &gp = h->gp;
+    if (env >= gp.n_env) return fail("waves_set_speed_field: env %d out of range", env);
+    int e0 = env < 0 ? 0 : env, e1 = env < 0 ? gp.n_env : env + 1;
+    if (c && !h->cplane) {
+        CU_TRY(cudaMalloc((void **)&h->cplane, sizeof(float) * (size_t)gp.plane * gp.n_env));
+        CU_TRY(cudaMemsetAsync(h->cplane, 0, sizeof(float) * (size_t)gp.plane * gp.n_env, h->stream));
+    }
+    for (int e = e0; e < e1; ++e) {
+        h->h_env[e].has_cplane = c ? 1 : 0;
+        if (c && copy_plane(h, h->cplane + (size_t)e * gp.plane, c, nullptr, 1)) return 1;
+    }
+    h->env_dirty = true;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int ensure_exact_scratch(waves_handle *h) {
+    size_t state = (size_t)h->gp.env_stride * h->gp.n_env;
+    if (!h->k) CU_TRY(cudaMalloc((void **)&h->k, sizeof(float) * state));
+    if (!h->ys) CU_TRY(cudaMalloc((void **)&h->ys, sizeof(float) * state));
+    if (!h->acc) CU_TRY(cudaMalloc((void **)&h->acc, sizeof(float) * state));
+    if (!h->b2) CU_TRY(cudaMalloc((void **)&h->b2, sizeof(float) * (size_t)h->gp.plane * h->gp.n_env));
+    return 0;
+}
+
+static int ensure_stage(waves_handle *h, int steps) {
+    if (steps + 1 > h->stage_cap) {
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        if (h->d_tspan) cudaFree(h->d_tspan);
+        if (h->d_stage) cudaFree(h->d_stage);
+        h->stage_cap = steps + 1 < 128 ? 128 : steps + 1;
+        CU_TRY(cudaMalloc((void **)&h->d_tspan, sizeof(float) * h->stage_cap));
+        CU_TRY(cudaMalloc((void **)&h->d_stage, sizeof(float) * STAGE_ROW * (size_t)h->stage_cap * h->gp.n_env));
+    }
+    return 0;
+}
+
+static bool any_speed_plane(const waves_handle *h) {
+    for (int e = 0; e < h->gp.n_env; ++e)
+        if (h->h_env[e].ncyl > 0 || h->h_env[e].has_cplane) return true;
+    return false;
+}
+
+// one RK4 step in the reference's exact order: 4 x (speed -> rhs -> accumulate), then the update
+static int step_exact(waves_handle *h, int steps, int step) {
+    if (ensure_exact_scratch(h)) return 1;
+    const bool sp = any_speed_plane(h);
+    float *u = h->u[h->cur];
+    for (int s = 0; s < 4; ++s) {
+        const float *in = s == 0 ? u : h->ys;
+        if (sp) launch_speed2(h, 0, h->gp.n_env, h->d_stage, steps, step, s, h->b2);
+        launch_rhs_exact(h, 0, h->gp.n_env, in, h->k, h->d_stage, steps, step, s);
+        launch_rk_update(h, s, u, h->k, h->acc, h->ys);
+    }
+    launch_rk_final(h, u, h->acc, u);
+    return 0;
+}
+
+static int step_any(waves_handle *h, int steps, int step, int mode, float *d_e3) {
+    if (mode == WAVES_MODE_EXACT) {
+        if (step_exact(h, steps, step)) return 1;
+        if (d_e3) launch_energy(h, h->u[h->cur], d_e3, 3 * (steps + 1));
+        return 0;
+    }
+    if (mode != WAVES_MODE_FUSED) return fail("unknown mode %d", mode);
+    return launch_fused_step(h, h->d_stage, steps, step, d_e3);
+}
+
+extern "C" int waves_rhs(waves_handle *h, int env, float t, float *du12) {
+    CHECK_H(h);
+    if (env < 0 || env >= h->gp.n_env || !du12) return fail("waves_rhs: bad arguments");
+    if (ensure_exact_scratch(h) || ensure_stage(h, 1) || flush_params(h)) return 1;
+    CU_TRY(cudaMemcpyAsync(h->d_tspan, &t, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    launch_stage_table(h, h->d_tspan, 1, h->d_stage);
+    const EnvParams &ep = h->h_env[env];
+    if (ep.ncyl > 0 || ep.has_cplane) launch_speed2(h, env, 1, h->d_stage, 1, 0, 0, h->b2);
+    launch_rhs_exact(h, env, 1, h->u[h->cur], h->k, h->d_stage, 1, 0, 0);
+    if (copy_planes_fast(h, h->k + (size_t)env * h->gp.env_stride, nullptr, du12, 12)) return 1;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int waves_step(waves_handle *h, float t, int mode) {
+    CHECK_H(h);
+    if (ensure_stage(h, 1) || flush_params(h)) return 1;
+    CU_TRY(cudaMemcpyAsync(h->d_tspan, &t, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    launch_stage_table(h, h->d_tspan, 1, h->d_stage);
+    if (step_any(h, 1, 0, mode, nullptr)) return 1;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int waves_energy(waves_handle *h, float *e3) {
+    CHECK_H(h);
+    if (!e3) return fail("waves_energy: null buffer");
+    if (h->energy_cap < 1) {
+        CU_TRY(cudaMalloc((void **)&h->d_energy, sizeof(float) * 3 * 128 * (size_t)h->gp.n_env));
+        h->energy_cap = 128;
+    }
+    launch_energy(h, h->u[h->cur], h->d_energy, 3);
+    CU_TRY(cudaMemcpyAsync(e3, h->d_energy, sizeof(float) * 3 * h->gp.n_env, cudaMemcpyDefault, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, int mode, float *energy,
+                               const int32_t *save_steps, int nsave, float *frames, float *u_tot_traj,
+                               float *u_inc_traj) {
+    CHECK_H(h);
+    const GridP &gp = h->gp;
+    if (!tspan || steps < 1) return fail("waves_integrate: need tspan with steps >= 1");
+    if (nsave > 0 && (!save_steps || !frames)) return fail("waves_integrate: save_steps/frames missing");
+    for (int i = 0; i < nsave; ++i)
+        if (save_steps[i] < 0 || save_steps[i] > steps || (i > 0 && save_steps[i] <= save_steps[i - 1]))
+            return fail("waves_integrate: save_steps must be ascending within [0, steps]");
+    if (ensure_stage(h, steps) || flush_params(h)) return 1;
+    if (energy && h->energy_cap < steps + 1) {
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        if (h->d_energy) cudaFree(h->d_energy);
+        h->energy_cap = steps + 1 < 128 ? 128 : steps + 1;
+        CU_TRY(cudaMalloc((void **)&h->d_energy, sizeof(float) * 3 * (size_t)h->energy_cap * gp.n_env));
+    }
+    CU_TRY(cudaMemcpyAsync(h->d_tspan, tspan, sizeof(float) * (steps + 1), cudaMemcpyDefault, h->stream));
+    launch_stage_table(h, h->d_tspan, steps, h->d_stage);
+
+    const size_t frame_elems = (size_t)12 * gp.ny_own * gp.nx, plane_elems = (size_t)gp.ny_own * gp.nx;
+    int isave = 0;
+    auto emit = [&](int frame) -> int {
+        const float *u = h->u[h->cur];
+        if (isave < nsave && save_steps[isave] == frame) {
+            for (int e = 0; e < gp.n_env; ++e)
+                if (copy_planes_fast(h, const_cast<float *>(u) + (size_t)e * gp.env_stride, nullptr,
+                                     frames + ((size_t)e * nsave + isave) * frame_elems, 12))
+                    return 1;
+            ++isave;
+        }
+        for (int e = 0; e < gp.n_env; ++e) {
+            float *base = const_cast<float *>(u) + (size_t)e * gp.env_stride;
+            if (u_tot_traj && copy_plane(h, base, nullptr, u_tot_traj + ((size_t)e * (steps + 1) + frame) * plane_elems, 1))
+                return 1;
+            if (u_inc_traj &&
+                copy_plane(h, base + 6 * gp.plane, nullptr, u_inc_traj + ((size_t)e * (steps + 1) + frame) * plane_elems, 1))
+                return 1;
+        }
+        return 0;
+    };
+
+    if (energy) launch_energy(h, h->u[h->cur], h->d_energy, 3 * (steps + 1));
+    if (emit(0)) return 1;
+    for (int n = 0; n < steps; ++n) {
+        float *d_e3 = energy ? h->d_energy + 3 * (size_t)(n + 1) : nullptr;
+        if (step_any(h, steps, n, mode, d_e3)) return 1;
+        if (emit(n + 1)) return 1;
+    }
+    if (energy)
+        CU_TRY(cudaMemcpyAsync(energy, h->d_energy, sizeof(float) * 3 * (size_t)(steps + 1) * gp.n_env, cudaMemcpyDefault,
+                               h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- slab halo plumbing ----------------------------------------------------------------------
+extern "C" int waves_halo_describe(waves_handle *h, waves_halo_desc *o) {
+    CHECK_H(h);
+    if (!o) return fail("waves_halo_describe: null");
+    const GridP &gp = h->gp;
+    float *u = h->u[h->cur];
+    bool lo = gp.ny_own0 > 0, hi = gp.ny_alloc > gp.ny_own0 + gp.ny_own;
+    o->send_lo = lo ? u + (size_t)gp.ny_own0 * gp.nxp : nullptr;
+    o->recv_lo = lo ? u + (size_t)(gp.ny_own0 - WAVES_HALO) * gp.nxp : nullptr;
+    o->send_hi = hi ? u + (size_t)(gp.ny_own0 + gp.ny_own - WAVES_HALO) * gp.nxp : nullptr;
+    o->recv_hi = hi ? u + (size_t)(gp.ny_own0 + gp.ny_own) * gp.nxp : nullptr;
+    o->plane_stride = gp.plane;
+    o->n_planes = gp.n_env * 12;
+    o->block_floats = WAVES_HALO * gp.nxp;
+    o->pitch = gp.nxp;
+    return 0;
+}
+
+extern "C" int waves_halo_pack(waves_handle *h, float *lo_buf, float *hi_buf) {
+    CHECK_H(h);
+    const GridP &gp = h->gp;
+    if (gp.ny_own0 == 0) lo_buf = nullptr;
+    if (gp.ny_alloc == gp.ny_own0 + gp.ny_own) hi_buf = nullptr;
+    if (lo_buf || hi_buf) launch_pack_halo(h, h->u[h->cur], lo_buf, hi_buf);
+    return 0;
+}
+
+extern "C" int waves_halo_unpack(waves_handle *h, const float *lo_buf, const float *hi_buf) {
+    CHECK_H(h);
+    const GridP &gp = h->gp;
+    if (gp.ny_own0 == 0) lo_buf = nullptr;
+    if (gp.ny_alloc == gp.ny_own0 + gp.ny_own) hi_buf = nullptr;
+    if (lo_buf || hi_buf) launch_unpack_halo(h, h->u[h->cur], lo_buf, hi_buf);
+    return 0;
+}
+
+// ---- introspection ---------------------------------------------------------------------------
+extern "C" int64_t waves_launch_count(waves_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int waves_profile(waves_handle *h, int on) {
+    CHECK_H(h);
+    h->profile = on;
+    h->fused_ms = 0;
+    h->fused_launches = 0;
+    return 0;
+}
+
+extern "C" int waves_profile_read(waves_handle *h, double *ms, int64_t *n) {
+    CHECK_H(h);
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (ms) *ms = h->fused_ms;
+    if (n) *n = h->fused_launches;
+    return 0;
+}

@@ -1,0 +1,98 @@
+// Internal declarations shared by the C-ABI host code and the CUDA kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/waves_b200.h"
+
+// Per-environment parameters of θ = [C, F] (src/env.jl:96-102), device-resident.
+struct EnvParams {
+    int ncyl;        // 0 -> NoDesign
+    int has_source;  // 0 -> NoSource
+    int has_cplane;  // 1 -> fixed speed plane overrides the design
+    float ti, tf;    // DesignInterpolator window (src/designs.jl:274-279)
+    float freq;      // source frequency (src/sources.jl:12,35)
+    int src_j0, src_j1;  // local row range [j0, j1) where the source shape is non-zero
+    int src_i0, src_i1;  // column range where the source shape is non-zero
+};
+
+// Geometry + constants passed by value to every kernel.
+struct GridP {
+    int nx;         // grid points along x (contiguous)
+    int nxp;        // row pitch in floats (nx rounded up to a multiple of 4)
+    int ny_alloc;   // rows held in device memory (owned + ghost)
+    int ny_own0;    // first owned local row (== number of ghost rows on top)
+    int ny_own;     // owned rows
+    int ny_global;  // rows of the whole grid
+    int grow0;      // global row index of local row 0
+    int n_env;
+    long long plane;       // floats per field plane  (ny_alloc * nxp)
+    long long env_stride;  // floats per environment  (12 * plane)
+    float g_first[3], g_central[2], g_last[3];  // rows of the gradient matrix (src/operators.jl:10-22)
+    float c0, b0;   // ambient speed and c0*c0
+    float dt, hdt;  // dt and 0.5f*dt
+    const float *x, *y, *sigma;  // device: dim.x (nx), dim.y (ny_global), pml profile (max(nx, ny_global))
+};
+
+// One row of the per-(env, step) stage table: times and source factors of the RK4 stages.
+// [0..2] = t, t+dt/2, t+dt ; [3..5] = sin(2π t f) at those times ; [6..7] pad
+#define STAGE_ROW 8
+
+struct waves_handle {
+    GridP gp;
+    int device;
+    cudaStream_t stream;
+    float *u[2];  // ping-pong state [n_env][12][ny_alloc][nxp]
+    int cur;
+    float *k, *ys, *acc;  // exact-mode scratch, lazily allocated
+    float *b2;            // exact-mode c^2 plane per env [n_env][plane], lazily allocated
+    float *shape;         // [n_env][plane] source shape (zeros when NoSource)
+    float *cplane;        // [n_env][plane] fixed speed plane, lazily allocated
+    float *d_x, *d_y, *d_sigma;
+    EnvParams *h_env, *d_env;
+    bool env_dirty;
+    float *d_cyl0, *d_cyl1;  // [n_env][cyl_cap][4]
+    float *h_cyl0, *h_cyl1;
+    int cyl_cap;
+    bool cyl_dirty;
+    float *d_tspan;
+    float *d_stage;
+    int stage_cap;  // steps capacity of d_tspan / d_stage
+    double *d_epart;
+    int epart_blocks;
+    float *d_energy;
+    int energy_cap;  // frames capacity
+    float d_omega;
+    CUtensorMap map_u[2];  // TMA descriptors over the two state buffers
+    CUtensorMap map_shape;
+    bool maps_ready;
+    int64_t launches;
+    int profile;
+    double fused_ms;
+    int64_t fused_launches;
+    cudaEvent_t ev0, ev1;
+    int fused_smem;
+    int sm_count;
+    void *plan;  // FusedPlan (kernels_fused.cu)
+};
+
+// ---- kernels_exact.cu ----
+void launch_stage_table(waves_handle *h, const float *d_tspan, int steps, float *d_table);
+void launch_speed2(waves_handle *h, int env0, int nenv, const float *d_table, int steps, int step, int stage,
+                   float *b2);
+void launch_rhs_exact(waves_handle *h, int env0, int nenv, const float *u_in, float *k_out, const float *d_table,
+                      int steps, int step, int stage);
+void launch_rk_update(waves_handle *h, int stage, const float *u, const float *k, float *acc, float *ys);
+void launch_rk_final(waves_handle *h, const float *u_in, const float *acc, float *u_out);
+void launch_energy(waves_handle *h, const float *u, float *d_e3, int frame_stride3);
+void launch_pack_halo(waves_handle *h, const float *u, float *lo, float *hi);
+void launch_unpack_halo(waves_handle *h, float *u, const float *lo, const float *hi);
+
+// ---- kernels_fused.cu ----
+int fused_prepare(waves_handle *h);  // work items, tensor maps, smem attribute; 0 on success
+void fused_release(waves_handle *h);
+int fused_item_counts(waves_handle *h, int *n_int, int *n_gen);
+int source_bbox(waves_handle *h, int env, int *bbox4);
+int waves_set_error(const char *msg);  // sets the thread-local message, returns 1
+int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step, float *d_e3 /*nullable*/);

@@ -1,0 +1,144 @@
+"""Thin object wrapper over the C ABI handle (include/waves_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+F32 = np.float32
+MODE_FUSED, MODE_EXACT = 0, 1
+
+
+def _ptr(a):
+    """Raw address of a NumPy array (host) or a torch tensor (host or CUDA); None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.dtype in (np.float32, np.int32) and a.flags["C_CONTIGUOUS"], "need a contiguous float32/int32 array"
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(int(a))
+
+
+class Engine:
+    """One waves_handle: `n_env` independent environments (or one slab of a large grid) on one GPU."""
+
+    def __init__(self, x, y, c0, dt, pml_width=2.0, pml_scale=20000.0, n_env=1, device=0, sigma=None, grad8=None,
+                 d_omega=0.0, ny_local=None, row0=0):
+        self._x = np.ascontiguousarray(x, F32)
+        self._y = np.ascontiguousarray(y, F32)
+        self._sigma = None if sigma is None else np.ascontiguousarray(sigma, F32)
+        self._grad8 = None if grad8 is None else np.ascontiguousarray(grad8, F32)
+        self.nx, self.ny_global = len(self._x), len(self._y)
+        self.ny = int(ny_local) if ny_local is not None else self.ny_global
+        self.n_env, self.device = int(n_env), int(device)
+        cfg = _lib.WavesConfig(
+            nx=self.nx, ny=self.ny, n_env=self.n_env, device=self.device, c0=float(c0), dt=float(dt),
+            pml_width=float(pml_width), pml_scale=float(pml_scale), x=self._x.ctypes.data_as(_lib.fp),
+            y=self._y.ctypes.data_as(_lib.fp),
+            sigma=None if self._sigma is None else self._sigma.ctypes.data_as(_lib.fp),
+            grad8=None if self._grad8 is None else self._grad8.ctypes.data_as(_lib.fp),
+            d_omega=float(d_omega), ny_global=self.ny_global, row0=int(row0), flags=0)
+        h = C.c_void_p()
+        check(_lib.lib().waves_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().waves_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # state -------------------------------------------------------------------
+    def set_state(self, u12, env=-1):
+        check(_lib.lib().waves_set_state(self._h, env, _ptr(u12)))
+
+    def get_state(self, env=-1, out=None):
+        n = self.n_env if env < 0 else 1
+        if out is None:
+            out = np.empty((n, 12, self.ny, self.nx), dtype=F32)
+        check(_lib.lib().waves_get_state(self._h, env, _ptr(out)))
+        return out if env < 0 else (out[0] if isinstance(out, np.ndarray) and out.ndim == 4 else out)
+
+    # θ = [C, F] --------------------------------------------------------------
+    def set_source(self, shape, freq, env=-1):
+        check(_lib.lib().waves_set_source(self._h, env, _ptr(shape), C.c_float(freq)))
+
+    def set_design(self, cyl0, cyl1, ti, tf, env=-1):
+        if cyl0 is None:
+            check(_lib.lib().waves_set_design(self._h, env, 0, None, None, C.c_float(0), C.c_float(0)))
+            return
+        a, b = np.ascontiguousarray(cyl0, F32), np.ascontiguousarray(cyl1, F32)
+        assert a.shape == b.shape and a.shape[1] == 4
+        check(_lib.lib().waves_set_design(self._h, env, a.shape[0], a.ctypes.data_as(_lib.fp), b.ctypes.data_as(_lib.fp),
+                                          C.c_float(ti), C.c_float(tf)))
+
+    def set_speed_field(self, c, env=-1):
+        check(_lib.lib().waves_set_speed_field(self._h, env, _ptr(c)))
+
+    # dynamics ----------------------------------------------------------------
+    def rhs(self, t, env=0):
+        out = np.empty((12, self.ny, self.nx), dtype=F32)
+        check(_lib.lib().waves_rhs(self._h, env, C.c_float(t), _ptr(out)))
+        return out
+
+    def step(self, t, mode=MODE_FUSED):
+        check(_lib.lib().waves_step(self._h, C.c_float(t), mode))
+
+    def integrate(self, tspan, mode=MODE_FUSED, energy=True, save_steps=(), frames=None, u_tot=None, u_inc=None):
+        """(iter::Integrator)(ui, tspan, θ) + energy metric.  Returns (energy (n_env, steps+1, 3) | None, frames | None)."""
+        ts = np.ascontiguousarray(tspan, F32)
+        steps = len(ts) - 1
+        en = np.empty((self.n_env, steps + 1, 3), dtype=F32) if energy is True else (energy if energy is not False else None)
+        ss = np.ascontiguousarray(save_steps, np.int32)
+        if len(ss) and frames is None:
+            frames = np.empty((self.n_env, len(ss), 12, self.ny, self.nx), dtype=F32)
+        check(_lib.lib().waves_integrate(self._h, ts.ctypes.data_as(_lib.fp), steps, mode, _ptr(en),
+                                         ss.ctypes.data_as(_lib.ip) if len(ss) else None, len(ss), _ptr(frames),
+                                         _ptr(u_tot), _ptr(u_inc)))
+        return en, frames
+
+    def energy(self):
+        out = np.empty((self.n_env, 3), dtype=F32)
+        check(_lib.lib().waves_energy(self._h, _ptr(out)))
+        return out
+
+    def sync(self):
+        check(_lib.lib().waves_sync(self._h))
+
+    # slab plumbing -----------------------------------------------------------
+    def halo_describe(self):
+        d = _lib.HaloDesc()
+        check(_lib.lib().waves_halo_describe(self._h, C.byref(d)))
+        return d
+
+    def halo_pack(self, lo, hi):
+        check(_lib.lib().waves_halo_pack(self._h, _ptr(lo), _ptr(hi)))
+
+    def halo_unpack(self, lo, hi):
+        check(_lib.lib().waves_halo_unpack(self._h, _ptr(lo), _ptr(hi)))
+
+    def stream(self) -> int:
+        return int(_lib.lib().waves_stream(self._h) or 0)
+
+    # introspection -----------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(_lib.lib().waves_launch_count(self._h))
+
+    def profile(self, on: bool):
+        check(_lib.lib().waves_profile(self._h, int(on)))
+
+    def profile_read(self):
+        ms, n = C.c_double(0), C.c_int64(0)
+        check(_lib.lib().waves_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
