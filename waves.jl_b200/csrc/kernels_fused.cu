@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -59,6 +60,7 @@ struct FusedArgs {
     float *epart;  // [n_env][n_items_total][3] or nullptr
     int epart_stride;  // items per env in epart (all kernels of a step share one buffer)
     int epart_off;     // offset of this kernel's items
+    int dbg;           // developer bisecting flags (WAVES_DEBUG_FLAGS)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -451,7 +453,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, c
     // 1. prefetch row r + PF into the slot that row r + PF - RING vacated (all its readers finished >= 1 step ago)
     __syncwarp();
     const int rp = r + PF;
-    if (c.lane == 0 && rp >= c.la && rp < c.lb) {
+    if (c.lane == 0 && rp >= c.la && rp < c.lb && !(A.dbg & 2)) {
         const int slot = (rp - c.la) & (RING - 1);
         const uint32_t bar = c.bar0 + slot * 8, dst = smem_u32(c.ring + slot * SLOT_F);
         const bool s = src_row(c, rp);
@@ -462,7 +464,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, c
     // 2. arrival of row r: stage-0 windows
     if (r >= c.la && r < c.lb) {
         const int rel = r - c.la;
-        mbar_wait(c.bar0 + (rel & (RING - 1)) * 8, (rel >> 3) & 1);
+        if (!(A.dbg & 2)) mbar_wait(c.bar0 + (rel & (RING - 1)) * 8, (rel >> 3) & 1);
         const float *ur = ring_row(c, r);
         const float shv = sh_at(c, r);
         constexpr int s0 = PH & 3;
@@ -474,6 +476,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, c
     }
     // 3. the four stages, each one row behind the previous
     const int jlo = c.la + 1, jhi = c.lb - 2;  // rows with both y-neighbours loaded
+    if (A.dbg & 1) return;
     if (r - 1 >= jlo && r - 1 <= jhi) stage<GENERAL, 1, PH>(c, A, ep, e, R, r - 1);
     if (r - 2 >= jlo && r - 2 <= jhi) stage<GENERAL, 2, PH>(c, A, ep, e, R, r - 2);
     if (r - 3 >= jlo && r - 3 <= jhi) stage<GENERAL, 3, PH>(c, A, ep, e, R, r - 3);
@@ -512,10 +515,10 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     c.valid_lane = lane >= item.vlo && lane < item.vhi;
     c.is_first_col = c.col == 0;
     c.is_last_col = c.col == gp.nx - 1;
-    c.xb = (item.x0 == 0) || (item.x0 + 32 == gp.nx);
+    c.xb = (item.x0 == 0) || (item.x0 + 32 >= gp.nx);
     c.bcm = (c.is_first_col || c.is_last_col) ? 0.0f : 1.0f;
-    c.xs = gp.x[c.col];
-    c.sx = GENERAL ? gp.sigma[c.col] : 0.0f;
+    c.xs = gp.x[min(c.col, gp.nx - 1)];  // lanes past the last column (nx % 4 != 0) are never valid
+    c.sx = GENERAL ? gp.sigma[min(c.col, gp.nx - 1)] : 0.0f;
     c.kd = gp.g_central[1];
     c.dt = gp.dt;
     c.hdt = gp.hdt;
@@ -532,7 +535,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     c.src_j0 = ep.src_j0;
     c.src_j1 = ep.src_j1;
 
-    if (lane == 0) {
+    if (lane == 0 && !(A.dbg & 8)) {
         for (int s = 0; s < RING; ++s) mbar_init(c.bar0 + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -540,8 +543,8 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     __syncwarp();
     // cull the design's cylinders against this warp's window, at the three stage times (src/designs.jl:287-292)
     c.nact = 0;
-    if (ep.ncyl > 0) {
-        const float xlo = gp.x[item.x0], xhi = gp.x[item.x0 + 31];
+    if (ep.ncyl > 0 && !(A.dbg & 4)) {
+        const float xlo = gp.x[item.x0], xhi = gp.x[min(item.x0 + 31, gp.nx - 1)];
         const float ylo = gp.y[min(max(gp.grow0 + item.la, 0), gp.ny_global - 1)];
         const float yhi = gp.y[min(max(gp.grow0 + item.lb - 1, 0), gp.ny_global - 1)];
         int n = 0;
@@ -728,26 +731,22 @@ int fused_prepare(waves_handle *h) {
     if (!clean) z0 = z1 = 0;  // unusual profile: everything general
 
     // --- columns: output ranges [olo, ohi) ---
+    // MEASURED ON B200: cp.async.bulk.tensor (tiled) raises "illegal instruction" unless the innermost
+    // coordinate is 16-byte aligned, so every window starts at a multiple of 4 columns (scripts/dbg/tma_ring.cu).
     struct Col { int olo, ohi, x0; bool interior; };
     std::vector<Col> cols;
-    auto add_cols = [&](int a, int b, bool interior) {
-        // split [a,b) into strips of <= 24 output columns (28 when touching a domain edge)
+    auto add_cols = [&](int a, int b, bool interior) {  // a is a multiple of 4
         int o = a;
         while (o < b) {
-            int w = 24;
-            if (o == 0) w = 28;
-            int hi = o + w < b ? o + w : b;
-            if (gp.nx - hi < 4 && hi != gp.nx) hi = b;  // do not leave a sliver that cannot hold its halo
-            int x0 = o - 4;
-            if (x0 < 0) x0 = 0;
-            if (x0 + 32 > gp.nx) x0 = gp.nx - 32;
-            // ensure the window covers hi + 4 (or the domain edge)
-            while (hi - x0 > ((x0 + 32 == gp.nx) ? 32 : 28)) --hi;
+            const int x0 = o == 0 ? 0 : o - 4;
+            int hi = x0 + 28;  // 24 owned columns + 4 halo (28 at the left domain edge)
+            if (hi > b) hi = b;
             cols.push_back({o, hi, x0, interior});
             o = hi;
         }
     };
-    int ci0 = z0 + 4, ci1 = z1 - 4;  // interior output columns need their 4-column halo inside the zero zone
+    // interior output columns keep their 4-column halo inside the zero-sigma zone
+    int ci0 = (z0 + 4 + 3) & ~3, ci1 = (z1 - 4) & ~3;
     if (ci1 - ci0 < 24) {
         add_cols(0, gp.nx, false);
     } else {
@@ -880,8 +879,11 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     A.out = h->u[h->cur ^ 1];
     A.epart = d_e3 ? p->d_epart : nullptr;
     A.epart_stride = p->n_int + p->n_gen;
+    static const int dbg_flags = getenv("WAVES_DEBUG_FLAGS") ? atoi(getenv("WAVES_DEBUG_FLAGS")) : 0;
+    A.dbg = dbg_flags;
+    static const int dbg_skip = getenv("WAVES_DEBUG_SKIP") ? atoi(getenv("WAVES_DEBUG_SKIP")) : 0;  // developer bisecting aid
     if (h->profile) cudaEventRecord(h->ev0, h->stream);
-    if (p->n_int > 0) {
+    if (p->n_int > 0 && !(dbg_skip & 1)) {
         A.items = p->d_items_int;
         A.n_items = p->n_int;
         A.epart_off = 0;
@@ -890,7 +892,7 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
                                                                                                           h->map_shape);
         h->launches++;
     }
-    if (p->n_gen > 0) {
+    if (p->n_gen > 0 && !(dbg_skip & 2)) {
         A.items = p->d_items_gen;
         A.n_items = p->n_gen;
         A.epart_off = p->n_int;
