@@ -32,15 +32,29 @@
 
 namespace {
 
-constexpr int RING = 8;       // ring slots (rows) per warp
-constexpr int PF = 2;         // TMA prefetch distance in rows
-constexpr int SLOT_F = 13 * 32;  // floats per ring slot: 12 fields + source shape
-constexpr int CYL_CAP = 12;   // culled cylinders kept per warp
-constexpr int BSET_F = 24 * 32;  // border-row state per warp (floats)
-constexpr int WARPS = 4;      // warps per CTA (independent work items)
+constexpr int RING = 8;      // ring slots (rows) per warp
+constexpr int PF = 2;        // TMA prefetch distance in rows
+constexpr int CYL_CAP = 12;  // culled cylinders kept per warp
+constexpr int WARPS = 4;     // warps per CTA (independent work items)
+
+// Per-variant layout.  The interior variant marches BOTH wavefields in one warp (it needs both for
+// the scattered energy and has registers to spare); the general variant (PML strips, domain borders)
+// carries twice the state per wavefield, so each warp takes ONE wavefield.
+template <bool GENERAL>
+struct Cfg {
+    static constexpr int NW = GENERAL ? 1 : 2;   // wavefields per warp
+    static constexpr int NF = 6 * NW;            // state fields per ring slot (TMA box depth)
+    static constexpr int F_SH = NF;              // source shape row
+    static constexpr int F_B = NF + 1;           // c^2 at the 3 stage times (tot wavefield)
+    static constexpr int F_P = NF + 4;           // interior only: Psix + Psiy - Omega per wavefield
+    static constexpr int SLOT_ROWS = GENERAL ? NF + 4 : NF + 6;
+    static constexpr int SLOT_F = SLOT_ROWS * 32;  // floats per ring slot
+    static constexpr int BSET_F = GENERAL ? 12 * 32 : 0;  // border-row state (general only)
+    static constexpr int WARP_BYTES = ((RING * SLOT_F * 4 + BSET_F * 4 + CYL_CAP * 12 * 4 + RING * 8) + 127) & ~127;
+};
 
 struct Item {
-    int x0;        // first column of the 32-lane window
+    int x0;        // first column of the 32-lane window (multiple of 4: TMA needs 16-byte aligned boxes)
     int vlo, vhi;  // lanes [vlo, vhi) own output columns
     int j0, j1;    // output local rows [j0, j1)
     int la, lb;    // loaded local rows [la, lb)
@@ -57,7 +71,7 @@ struct FusedArgs {
     float *out;
     const Item *items;
     int n_items;
-    float *epart;  // [n_env][n_items_total][3] or nullptr
+    float *epart;      // [n_env][epart_stride][3] or nullptr
     int epart_stride;  // items per env in epart (all kernels of a step share one buffer)
     int epart_off;     // offset of this kernel's items
     int dbg;           // developer bisecting flags (WAVES_DEBUG_FLAGS)
@@ -106,66 +120,88 @@ __device__ __forceinline__ float interp_param(float p0, float p1, float ti, floa
 
 struct WarpCtx {
     // geometry
-    int lane, col, x0, la, lb, j0, j1;
-    bool valid_lane, xb, top, bot, is_first_col, is_last_col;
+    int lane, col, x0, la, lb;
+    int js0;           // first row the regular stages may store
+    unsigned jsn;      // rows [js0, js0+jsn) are stored by this lane (0 for halo lanes)
+    int jb0;           // first owned row (border routine)
+    unsigned jbn;      // owned rows for this lane incl. border rows (0 for halo lanes)
+    float *out_e;      // output state of this env (+ wavefield offset in the general variant)
+    unsigned plane;    // floats per field plane
+    unsigned nxp;
+    bool xb, top, bot, is_first_col, is_last_col;
+    bool is_tot;  // general variant: this warp carries the total wavefield (speed field applies)
+    int w0;       // general variant: wavefield index (plane offset w0*6)
     float xs, sx, bcm;
     // step constants
     float kd, dt, hdt, b0;
     float sf[3];  // source factor at t, t+dt/2, t+dt
     // smem
-    float *ring;   // [RING][13][32]
-    float *bset;   // [24][32]
-    float *cyl;    // [CYL_CAP][3][4]
-    uint32_t bar0; // smem address of mbarrier 0
-    int nact;      // active cylinders (-1: overflow, use the slow loop)
-    // source
-    bool src_cols;
-    int src_j0, src_j1;
+    float *ring;    // [RING][SLOT_ROWS][32]
+    float *bset;    // border-row state
+    float *cyl;     // [CYL_CAP][3][4]
+    uint32_t bar0;  // smem address of mbarrier 0
+    int nact;       // culled cylinders (0: none touch this window, -1: list overflow -> slow loop)
+    // source: rows [src_j0, src_j0+src_n) of this window carry a non-zero shape (src_n == 0: none)
+    int src_j0;
+    unsigned src_n;
     // global
     const float *ys_g, *sig_g;
     int grow0, ny_global;
 };
 
-__device__ __forceinline__ int ring_slot(const WarpCtx &c, int j) { return (j - c.la) & (RING - 1); }
-__device__ __forceinline__ const float *ring_row(const WarpCtx &c, int j) { return c.ring + ring_slot(c, j) * SLOT_F + c.lane; }
-__device__ __forceinline__ bool src_row(const WarpCtx &c, int j) { return c.src_cols && j >= c.src_j0 && j < c.src_j1; }
-__device__ __forceinline__ float sh_at(const WarpCtx &c, int j) { return src_row(c, j) ? ring_row(c, j)[12 * 32] : 0.0f; }
+__device__ __forceinline__ bool src_row(const WarpCtx &c, int j) { return (unsigned)(j - c.src_j0) < c.src_n; }
 
-// c(x,y,t)^2 for this lane at local row j and stage-time index tau (src/designs.jl:99-116), exact order
-__device__ __forceinline__ float speed2(const WarpCtx &c, const FusedArgs &A, const EnvParams &ep, int e, int j, int tau) {
-    if (c.nact == 0) return c.b0;
-    float yv = c.ys_g[min(max(c.grow0 + j, 0), c.ny_global - 1)];
+// c(x,y,t)^2 with every cylinder (list overflow), exact order of src/designs.jl:99-116
+__device__ __noinline__ float speed2_slow(float xs, float yv, const float *cyl0, const float *cyl1, int ncyl, float ti, float tf,
+                                          float t, float c0) {
     int cnt = 0;
     float cd = 0.0f;
-    if (c.nact > 0) {
-        for (int a = 0; a < c.nact; ++a) {
-            const float4 p = *reinterpret_cast<const float4 *>(c.cyl + (a * 3 + tau) * 4);  // px, py, r2, c
-            float dy = __fsub_rn(yv, p.y);
-            float dy2 = __fmul_rn(dy, dy);
-            if (dy2 >= p.z) continue;  // warp-uniform: the row misses this cylinder
-            float dx = __fsub_rn(c.xs, p.x);
-            float d2 = __fadd_rn(__fmul_rn(dx, dx), dy2);
-            bool m = d2 < p.z;
-            cnt += m;
-            cd = __fadd_rn(cd, m ? p.w : 0.0f);
-        }
-    } else {  // overflow of the per-warp list: evaluate every cylinder
-        float t = A.table[((size_t)e * A.steps + A.step) * STAGE_ROW + tau];
-        for (int k = 0; k < ep.ncyl; ++k) {
-            size_t o = ((size_t)e * A.cyl_cap + k) * 4;
-            float px = interp_param(A.cyl0[o], A.cyl1[o], ep.ti, ep.tf, t);
-            float py = interp_param(A.cyl0[o + 1], A.cyl1[o + 1], ep.ti, ep.tf, t);
-            float r = interp_param(A.cyl0[o + 2], A.cyl1[o + 2], ep.ti, ep.tf, t);
-            float cc = interp_param(A.cyl0[o + 3], A.cyl1[o + 3], ep.ti, ep.tf, t);
-            float dx = __fsub_rn(c.xs, px), dy = __fsub_rn(yv, py);
-            float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-            bool m = d2 < __fmul_rn(r, r);
-            cnt += m;
-            cd = __fadd_rn(cd, m ? cc : 0.0f);
-        }
+    for (int k = 0; k < ncyl; ++k) {
+        float px = interp_param(cyl0[4 * k], cyl1[4 * k], ti, tf, t);
+        float py = interp_param(cyl0[4 * k + 1], cyl1[4 * k + 1], ti, tf, t);
+        float r = interp_param(cyl0[4 * k + 2], cyl1[4 * k + 2], ti, tf, t);
+        float cc = interp_param(cyl0[4 * k + 3], cyl1[4 * k + 3], ti, tf, t);
+        float dx = __fsub_rn(xs, px), dy = __fsub_rn(yv, py);
+        float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        bool m = d2 < __fmul_rn(r, r);
+        cnt += m;
+        cd = __fadd_rn(cd, m ? cc : 0.0f);
     }
-    float cv = __fadd_rn(cnt == 0 ? A.gp.c0 : 0.0f, cd);
+    float cv = __fadd_rn(cnt == 0 ? c0 : 0.0f, cd);
     return __fmul_rn(cv, cv);
+}
+
+// speed(design(t), grid, c0)^2 of local row j at the three stage times -> dst[0], dst[32], dst[64]
+// (src/designs.jl:99-116: strict '<', speeds of overlapping cylinders add, ambient where none).
+__device__ __forceinline__ void speed_row(const WarpCtx &c, const FusedArgs &A, const EnvParams &ep, int e, int j, float *dst) {
+    const float yv = c.ys_g[min(max(c.grow0 + j, 0), c.ny_global - 1)];
+#pragma unroll 1
+    for (int tau = 0; tau < 3; ++tau) {
+        float b;
+        if (c.nact > 0) {
+            int cnt = 0;
+            float cd = 0.0f;
+#pragma unroll 1
+            for (int a = 0; a < c.nact; ++a) {
+                const float4 p = *reinterpret_cast<const float4 *>(c.cyl + (a * 3 + tau) * 4);  // px, py, r^2, c
+                float dy = __fsub_rn(yv, p.y);
+                float dy2 = __fmul_rn(dy, dy);
+                if (dy2 >= p.z) continue;  // warp-uniform: the row misses this cylinder
+                float dx = __fsub_rn(c.xs, p.x);
+                float d2 = __fadd_rn(__fmul_rn(dx, dx), dy2);
+                bool m = d2 < p.z;
+                cnt += m;
+                cd = __fadd_rn(cd, m ? p.w : 0.0f);
+            }
+            float cv = __fadd_rn(cnt == 0 ? A.gp.c0 : 0.0f, cd);
+            b = __fmul_rn(cv, cv);
+        } else {
+            const float t = A.table[((size_t)e * A.steps + A.step) * STAGE_ROW + tau];
+            const size_t o = (size_t)e * A.cyl_cap * 4;
+            b = speed2_slow(c.xs, yv, A.cyl0 + o, A.cyl1 + o, ep.ncyl, ep.ti, ep.tf, t, A.gp.c0);
+        }
+        dst[tau * 32] = b;
+    }
 }
 
 // d/dx across lanes: central (src/operators.jl:5) or the one-sided border rows (:3-4) on the domain's edge columns
@@ -186,133 +222,119 @@ __device__ __forceinline__ float ddx(const WarpCtx &c, const GridP &gp, float v)
 // Register state of one warp: rotating windows indexed [stage][wavefield][row & 3]
 template <bool GENERAL>
 struct Regs {
-    float Uf[4][2][4];  // U + f of stage state y_s (s = 0: the loaded row)
-    float Vy[4][2][4];
-    float Vx[4][2][4];  // s = 1..3
-    float aU[2][4], aVx[2][4], aVy[2][4];  // k1 + 2k2 + 2k3 accumulators
+    static constexpr int NW = Cfg<GENERAL>::NW;
+    float Uf[4][NW][4];  // U + f of stage state y_s (s = 0: the loaded row)
+    float Vy[4][NW][4];
+    float Vx[4][NW][4];  // s = 1..3
+    float aU[NW][4], aVx[NW][4], aVy[NW][4];  // k1 + 2k2 + 2k3 accumulators
     // GENERAL only
-    float Uc[4][2][4], Px[4][2][4], Py[4][2][4], Om[4][2][4];
-    float aPx[2][4], aPy[2][4], aOm[2][4];
+    float Uc[4][NW][4], Px[4][NW][4], Py[4][NW][4], Om[4][NW][4];
+    float aPx[NW][4], aPy[NW][4], aOm[NW][4];
     float e_tot, e_inc, e_sc;
 };
 
-// Border-row state kept in shared memory (per warp): index = field * 32 + lane
-// fields: for wf w (0,1): base = w*12: 0 Vx, 1 Uc, 2 Px, 3 Py, 4 Om, 5 aU, 6 aVx, 7 aVy, 8 aPx, 9 aPy, 10 aOm, 11 spare
+// Border-row state kept in shared memory (general variant, per warp): index = field * 32 + lane
 enum { B_VX = 0, B_UC, B_PX, B_PY, B_OM, B_AU, B_AVX, B_AVY, B_APX, B_APY, B_AOM };
 
-// One RK stage on a domain-border row (global row 0 or ny-1).  v3[w][0..2] / f3[w][0..2] hold
-// Vy and U+f of the previous stage state on the three rows the one-sided stencil spans, border row
-// first for TOP (rows 0,1,2) and last for BOT (rows L-2,L-1,L).  Returns the new Uf / Vy of the border row.
-__device__ __noinline__ void border_row_stage(const WarpCtx c, const FusedArgs &A, const EnvParams ep, int e, int S,
-                                              bool top, int jb, const float (*f3)[3], const float (*v3)[3],
-                                              float *uf_out, float *vy_out, float *e3) {
-    const GridP &gp = A.gp;
-    const float *g = top ? gp.g_first : gp.g_last;
-    const float *ur = ring_row(c, jb);
-    const float sy = c.sig_g[c.grow0 + jb];
-    const float sx = c.sx;
-    const float a = (S == 3) ? c.dt : c.hdt;
-    const int tau = (S == 1) ? 0 : (S == 4 ? 2 : 1);
-    const float shv = sh_at(c, jb);
-    const float sf_next = (S == 1 || S == 2) ? c.sf[1] : c.sf[2];
-    const float btot = speed2(c, A, ep, e, jb, tau);
-    float outU[2];
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-        float *bs = c.bset + w * 12 * 32 + c.lane;
-        const float *uw = ur + w * 6 * 32;
-        const float uU = uw[0], uVx = uw[32], uVy = uw[64], uPx = uw[96], uPy = uw[128], uOm = uw[160];
-        const float b = (w == 0) ? btot : c.b0;
-        const int ib = top ? 0 : 2;  // position of the border row in f3/v3
-        float ufC = f3[w][ib], vyC = v3[w][ib];
-        float vxC = (S == 1) ? uVx : bs[B_VX * 32];
-        float uC = (S == 1) ? uU : bs[B_UC * 32];
-        float px = (S == 1) ? uPx : bs[B_PX * 32];
-        float py = (S == 1) ? uPy : bs[B_PY * 32];
-        float om = (S == 1) ? uOm : bs[B_OM * 32];
-        float Ux = ddx<true>(c, gp, ufC);
-        float Vxx = ddx<true>(c, gp, vxC);
-        float Uy = ((g[0] * f3[w][0]) + (g[1] * f3[w][1])) + (g[2] * f3[w][2]);
-        float Vyy = ((g[0] * v3[w][0]) + (g[1] * v3[w][1])) + (g[2] * v3[w][2]);
-        // bc == 0 on a border row (src/dims.jl:117-124): dU = 0
-        float kU = 0.0f;
-        float kVx = Ux - sx * vxC;
-        float kVy = Uy - sy * vyC;
-        float kPx = (b * sx) * Vyy;
-        float kPy = (b * sy) * Vxx;
-        float kOm = (sx * sy) * uC;
-        if (S < 4) {
-            float Us = uU + a * kU;
-            uf_out[w] = Us + shv * sf_next;
-            vy_out[w] = uVy + a * kVy;
-            bs[B_VX * 32] = uVx + a * kVx;
-            bs[B_UC * 32] = Us;
-            bs[B_PX * 32] = uPx + a * kPx;
-            bs[B_PY * 32] = uPy + a * kPy;
-            bs[B_OM * 32] = uOm + a * kOm;
-            if (S == 1) {
-                bs[B_AU * 32] = kU;
-                bs[B_AVX * 32] = kVx;
-                bs[B_AVY * 32] = kVy;
-                bs[B_APX * 32] = kPx;
-                bs[B_APY * 32] = kPy;
-                bs[B_AOM * 32] = kOm;
-            } else {
-                bs[B_AU * 32] += 2.0f * kU;
-                bs[B_AVX * 32] += 2.0f * kVx;
-                bs[B_AVY * 32] += 2.0f * kVy;
-                bs[B_APX * 32] += 2.0f * kPx;
-                bs[B_APY * 32] += 2.0f * kPy;
-                bs[B_AOM * 32] += 2.0f * kOm;
-            }
-        } else {
-            const float sixth = 1.0f / 6.0f;
-            float oU = uU + (sixth * (bs[B_AU * 32] + kU)) * c.dt;
-            float oVx = uVx + (sixth * (bs[B_AVX * 32] + kVx)) * c.dt;
-            float oVy = uVy + (sixth * (bs[B_AVY * 32] + kVy)) * c.dt;
-            float oPx = uPx + (sixth * (bs[B_APX * 32] + kPx)) * c.dt;
-            float oPy = uPy + (sixth * (bs[B_APY * 32] + kPy)) * c.dt;
-            float oOm = uOm + (sixth * (bs[B_AOM * 32] + kOm)) * c.dt;
-            outU[w] = oU;
-            if (c.valid_lane && jb >= c.j0 && jb < c.j1) {
-                float *o = A.out + (long long)e * gp.env_stride + (long long)w * 6 * gp.plane + (long long)jb * gp.nxp + c.col;
-                o[0] = oU;
-                o[gp.plane] = oVx;
-                o[2 * gp.plane] = oVy;
-                o[3 * gp.plane] = oPx;
-                o[4 * gp.plane] = oPy;
-                o[5 * gp.plane] = oOm;
-            }
-        }
-    }
-    if (S == 4 && c.valid_lane && jb >= c.j0 && jb < c.j1) {
-        float d = outU[0] - outU[1];
-        e3[0] += outU[0] * outU[0];
-        e3[1] += outU[1] * outU[1];
-        e3[2] += d * d;
-    }
-    __syncwarp();
+// Arguments of border_row_stage, built at the (rare) call site so the hot path's state stays in registers.
+struct BorderArgs {
+    const float *ur;   // ring row of the border row (+ lane)
+    float *bs;         // border-row state (+ lane)
+    float *out;        // output address of field 0 at (border row, this column); nullptr: do not store
+    unsigned plane;
+    float sx, sy, kd, dt, a, b, shv, sf_next;
+    float g0, g1, g2;  // one-sided stencil row (src/operators.jl:3-4)
+    float f0, f1, f2, v0, v1, v2;
+    int S;
+    bool top, xb, first_col, last_col;
+    float gf0, gf1, gf2, gl0, gl1, gl2;  // x-direction one-sided rows
+};
+
+__device__ __forceinline__ float ddx_b(const BorderArgs &B, float v) {
+    float e1 = __shfl_down_sync(0xffffffffu, v, 1), w1 = __shfl_up_sync(0xffffffffu, v, 1);
+    float e2 = __shfl_down_sync(0xffffffffu, v, 2), w2 = __shfl_up_sync(0xffffffffu, v, 2);
+    float d = B.kd * (e1 - w1);
+    if (B.first_col) d = ((B.gf0 * v) + (B.gf1 * e1)) + (B.gf2 * e2);
+    if (B.last_col) d = ((B.gl0 * w2) + (B.gl1 * w1)) + (B.gl2 * v);
+    return d;
 }
 
-// One RK stage S (1..4) on interior row j = r - S, for both wavefields.  PH = r & 3.
+// One RK stage on a domain-border row (global row 0 or ny-1) of this warp's wavefield.  f0..f2 / v0..v2 hold
+// U+f and Vy of the previous stage state on the three rows the one-sided stencil spans (ascending rows);
+// the border row is the first for TOP and the last for BOT.  Returns the new Uf / Vy of the border row.
+__device__ __noinline__ float2 border_row_stage(const BorderArgs B) {
+    const float *ur = B.ur;
+    float *bs = B.bs;
+    const int S = B.S;
+    const float uU = ur[0], uVx = ur[32], uVy = ur[64], uPx = ur[96], uPy = ur[128], uOm = ur[160];
+    const float ufC = B.top ? B.f0 : B.f2, vyC = B.top ? B.v0 : B.v2;
+    const float vxC = (S == 1) ? uVx : bs[B_VX * 32];
+    const float uC = (S == 1) ? uU : bs[B_UC * 32];
+    const float Ux = ddx_b(B, ufC);
+    const float Vxx = ddx_b(B, vxC);
+    const float Uy = ((B.g0 * B.f0) + (B.g1 * B.f1)) + (B.g2 * B.f2);
+    const float Vyy = ((B.g0 * B.v0) + (B.g1 * B.v1)) + (B.g2 * B.v2);
+    // bc == 0 on a border row (src/dims.jl:117-124): dU = 0
+    const float kU = 0.0f;
+    const float kVx = Ux - B.sx * vxC;
+    const float kVy = Uy - B.sy * vyC;
+    const float kPx = (B.b * B.sx) * Vyy;
+    const float kPy = (B.b * B.sy) * Vxx;
+    const float kOm = (B.sx * B.sy) * uC;
+    float2 ret = make_float2(0.f, 0.f);
+    if (S < 4) {
+        const float Us = uU + B.a * kU;
+        ret.x = Us + B.shv * B.sf_next;
+        ret.y = uVy + B.a * kVy;
+        bs[B_VX * 32] = uVx + B.a * kVx;
+        bs[B_UC * 32] = Us;
+        bs[B_PX * 32] = uPx + B.a * kPx;
+        bs[B_PY * 32] = uPy + B.a * kPy;
+        bs[B_OM * 32] = uOm + B.a * kOm;
+        const float m = (S == 1) ? 0.0f : 1.0f, w = (S == 1) ? 1.0f : 2.0f;
+        bs[B_AU * 32] = m * bs[B_AU * 32] + w * kU;
+        bs[B_AVX * 32] = m * bs[B_AVX * 32] + w * kVx;
+        bs[B_AVY * 32] = m * bs[B_AVY * 32] + w * kVy;
+        bs[B_APX * 32] = m * bs[B_APX * 32] + w * kPx;
+        bs[B_APY * 32] = m * bs[B_APY * 32] + w * kPy;
+        bs[B_AOM * 32] = m * bs[B_AOM * 32] + w * kOm;
+    } else if (B.out) {
+        const float sixth = 1.0f / 6.0f;
+        float *o = B.out;
+        o[0] = uU + (sixth * (bs[B_AU * 32] + kU)) * B.dt;
+        o[B.plane] = uVx + (sixth * (bs[B_AVX * 32] + kVx)) * B.dt;
+        o[2 * (size_t)B.plane] = uVy + (sixth * (bs[B_AVY * 32] + kVy)) * B.dt;
+        o[3 * (size_t)B.plane] = uPx + (sixth * (bs[B_APX * 32] + kPx)) * B.dt;
+        o[4 * (size_t)B.plane] = uPy + (sixth * (bs[B_APY * 32] + kPy)) * B.dt;
+        o[5 * (size_t)B.plane] = uOm + (sixth * (bs[B_AOM * 32] + kOm)) * B.dt;
+    }
+    __syncwarp();
+    return ret;
+}
+
+// One RK stage S (1..4) on row j = r - S.  PH = r & 3.  Runs unguarded on every row: rows whose inputs are
+// not loaded yet (warm-up / drain) produce values that no stored cell depends on, and stores are predicated.
 template <bool GENERAL, int S, int PH>
-__device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, const EnvParams &ep, int e, Regs<GENERAL> &R, int j) {
+__device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, int e, Regs<GENERAL> &R, int j) {
+    using C = Cfg<GENERAL>;
     const GridP &gp = A.gp;
     constexpr int sc = (PH - S + 8) & 3, sm = (sc + 3) & 3, sp = (sc + 1) & 3;  // slots of rows j, j-1, j+1
-    const float *ur = ring_row(c, j);
+    const float *ur = c.ring + ((j - c.la) & (RING - 1)) * C::SLOT_F + c.lane;
     const float a = (S == 3) ? c.dt : c.hdt;
     constexpr int tau = (S == 1) ? 0 : (S == 4 ? 2 : 1);
-    const float sy = GENERAL ? c.sig_g[c.grow0 + j] : 0.0f;
+    const float sy = GENERAL ? c.sig_g[min(max(c.grow0 + j, 0), c.ny_global - 1)] : 0.0f;
     const float sx = c.sx;
-    const float shv = (S < 4) ? sh_at(c, j) : 0.0f;
+    const float shv = (S < 4 && src_row(c, j)) ? ur[C::F_SH * 32] : 0.0f;
     const float sf_next = (S == 1 || S == 2) ? c.sf[1] : c.sf[2];
-    const float btot = speed2(c, A, ep, e, j, tau);
-    float outU[2];
+    const float btot = (c.nact != 0) ? ur[(C::F_B + tau) * 32] : c.b0;
+    const bool st = (unsigned)(j - c.js0) < c.jsn;  // this lane stores row j
+    float outU[C::NW];
 #pragma unroll
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < C::NW; ++w) {
         const float *uw = ur + w * 6 * 32;
         const float uU = uw[0], uVx = uw[32], uVy = uw[64];
-        const float b = (w == 0) ? btot : c.b0;
+        const bool tot = GENERAL ? c.is_tot : (w == 0);
+        const float b = tot ? btot : c.b0;
         const float ufC = R.Uf[S - 1][w][sc];
         const float vxC = (S == 1) ? uVx : R.Vx[S - 1][w][sc];
         const float Ux = ddx<GENERAL>(c, gp, ufC);
@@ -337,9 +359,8 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
             kPy = (b * sy) * Vxx;
             kOm = (sx * sy) * uC;
         } else {
-            // sigma == 0 in the whole window: Psi, Omega never change within the step
-            const float P = (uw[96] + uw[128]) - uw[160];
-            kU = (b * (Vxx + Vyy)) + P;
+            // sigma == 0 in the whole window: Psi, Omega never change within the step; P was formed on arrival
+            kU = (b * (Vxx + Vyy)) + ur[(C::F_P + w) * 32];
             kVx = Ux;
             kVy = Uy;
         }
@@ -378,71 +399,80 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
             const float oU = uU + (sixth * (R.aU[w][sc] + kU)) * c.dt;
             const float oVx = uVx + (sixth * (R.aVx[w][sc] + kVx)) * c.dt;
             const float oVy = uVy + (sixth * (R.aVy[w][sc] + kVy)) * c.dt;
-            float oPx, oPy, oOm;
-            if (GENERAL) {
-                oPx = uPx + (sixth * (R.aPx[w][sc] + kPx)) * c.dt;
-                oPy = uPy + (sixth * (R.aPy[w][sc] + kPy)) * c.dt;
-                oOm = uOm + (sixth * (R.aOm[w][sc] + kOm)) * c.dt;
-            } else {
-                oPx = uw[96];
-                oPy = uw[128];
-                oOm = uw[160];
-            }
             outU[w] = oU;
-            if (c.valid_lane && j >= c.j0 && j < c.j1) {
-                float *o = A.out + (long long)e * gp.env_stride + (long long)w * 6 * gp.plane + (long long)j * gp.nxp + c.col;
+            if (st) {
+                float *o = c.out_e + (unsigned)(w * 6) * c.plane + (unsigned)j * c.nxp;
                 o[0] = oU;
-                o[gp.plane] = oVx;
-                o[2 * gp.plane] = oVy;
-                o[3 * gp.plane] = oPx;
-                o[4 * gp.plane] = oPy;
-                o[5 * gp.plane] = oOm;
+                o[c.plane] = oVx;
+                o[2u * c.plane] = oVy;
+                if (GENERAL) {  // interior: Psi/Omega were passed through on arrival
+                    o[3u * c.plane] = uPx + (sixth * (R.aPx[w][sc] + kPx)) * c.dt;
+                    o[4u * c.plane] = uPy + (sixth * (R.aPy[w][sc] + kPy)) * c.dt;
+                    o[5u * c.plane] = uOm + (sixth * (R.aOm[w][sc] + kOm)) * c.dt;
+                }
             }
         }
     }
-    if (S == 4 && c.valid_lane && j >= c.j0 && j < c.j1) {
-        const float d = outU[0] - outU[1];
+    if (!GENERAL && S == 4 && st) {
+        const float d = outU[0] - outU[C::NW - 1];
         R.e_tot += outU[0] * outU[0];
-        R.e_inc += outU[1] * outU[1];
+        R.e_inc += outU[C::NW - 1] * outU[C::NW - 1];
         R.e_sc += d * d;
     }
     if (GENERAL) {
         // domain-border rows ride along with their inward neighbour (see file header)
-        const bool do_top = c.top && j == 1, do_bot = c.bot && j == c.lb - 2;
+        const bool do_top = c.top && j == c.la + 1, do_bot = c.bot && j == c.lb - 2;
         if (do_top || do_bot) {
-            float f3[2][3], v3[2][3], ufo[2], vyo[2], e3[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                f3[w][0] = R.Uf[S - 1][w][sm];
-                f3[w][1] = R.Uf[S - 1][w][sc];
-                f3[w][2] = R.Uf[S - 1][w][sp];
-                v3[w][0] = R.Vy[S - 1][w][sm];
-                v3[w][1] = R.Vy[S - 1][w][sc];
-                v3[w][2] = R.Vy[S - 1][w][sp];
-            }
-            if (do_top) {
-                border_row_stage(c, A, ep, e, S, true, c.la, f3, v3, ufo, vyo, e3);
+            BorderArgs B;
+            B.f0 = R.Uf[S - 1][0][sm];
+            B.f1 = R.Uf[S - 1][0][sc];
+            B.f2 = R.Uf[S - 1][0][sp];
+            B.v0 = R.Vy[S - 1][0][sm];
+            B.v1 = R.Vy[S - 1][0][sc];
+            B.v2 = R.Vy[S - 1][0][sp];
+            B.bs = c.bset + c.lane;
+            B.plane = c.plane;
+            B.sx = sx;
+            B.kd = c.kd;
+            B.dt = c.dt;
+            B.a = a;
+            B.sf_next = sf_next;
+            B.S = S;
+            B.xb = c.xb;
+            B.first_col = c.is_first_col;
+            B.last_col = c.is_last_col;
+            B.gf0 = gp.g_first[0];
+            B.gf1 = gp.g_first[1];
+            B.gf2 = gp.g_first[2];
+            B.gl0 = gp.g_last[0];
+            B.gl1 = gp.g_last[1];
+            B.gl2 = gp.g_last[2];
+#pragma unroll 1
+            for (int side = 0; side < 2; ++side) {
+                const bool top = side == 0;
+                if (top ? !do_top : !do_bot) continue;
+                const int jb = top ? c.la : c.lb - 1;
+                const float *ub = c.ring + ((jb - c.la) & (RING - 1)) * C::SLOT_F + c.lane;
+                B.ur = ub;
+                B.top = top;
+                B.g0 = top ? gp.g_first[0] : gp.g_last[0];
+                B.g1 = top ? gp.g_first[1] : gp.g_last[1];
+                B.g2 = top ? gp.g_first[2] : gp.g_last[2];
+                B.sy = c.sig_g[c.grow0 + jb];
+                B.shv = src_row(c, jb) ? ub[C::F_SH * 32] : 0.0f;
+                B.b = (c.is_tot && c.nact != 0) ? ub[(C::F_B + tau) * 32] : c.b0;
+                B.out = ((unsigned)(jb - c.jb0) < c.jbn) ? c.out_e + (unsigned)jb * c.nxp : nullptr;
+                const float2 o = border_row_stage(B);
                 if (S < 4) {
-#pragma unroll
-                    for (int w = 0; w < 2; ++w) {
-                        R.Uf[S][w][sm] = ufo[w];
-                        R.Vy[S][w][sm] = vyo[w];
+                    if (top) {
+                        R.Uf[S][0][sm] = o.x;
+                        R.Vy[S][0][sm] = o.y;
+                    } else {
+                        R.Uf[S][0][sp] = o.x;
+                        R.Vy[S][0][sp] = o.y;
                     }
                 }
             }
-            if (do_bot) {
-                border_row_stage(c, A, ep, e, S, false, c.lb - 1, f3, v3, ufo, vyo, e3);
-                if (S < 4) {
-#pragma unroll
-                    for (int w = 0; w < 2; ++w) {
-                        R.Uf[S][w][sp] = ufo[w];
-                        R.Vy[S][w][sp] = vyo[w];
-                    }
-                }
-            }
-            R.e_tot += e3[0];
-            R.e_inc += e3[1];
-            R.e_sc += e3[2];
         }
     }
 }
@@ -450,69 +480,99 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
 template <bool GENERAL, int PH>
 __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, const EnvParams &ep, int e, Regs<GENERAL> &R, int r,
                                          const CUtensorMap *map_u, const CUtensorMap *map_sh) {
+    using C = Cfg<GENERAL>;
     // 1. prefetch row r + PF into the slot that row r + PF - RING vacated (all its readers finished >= 1 step ago)
     __syncwarp();
     const int rp = r + PF;
     if (c.lane == 0 && rp >= c.la && rp < c.lb && !(A.dbg & 2)) {
         const int slot = (rp - c.la) & (RING - 1);
-        const uint32_t bar = c.bar0 + slot * 8, dst = smem_u32(c.ring + slot * SLOT_F);
+        const uint32_t bar = c.bar0 + slot * 8, dst = smem_u32(c.ring + slot * C::SLOT_F);
         const bool s = src_row(c, rp);
-        mbar_expect_tx(bar, 12 * 128 + (s ? 128 : 0));
-        tma_load_3d(dst, map_u, c.x0, rp, e * 12, bar);
-        if (s) tma_load_3d(dst + 12 * 128, map_sh, c.x0, rp, e, bar);
+        mbar_expect_tx(bar, C::NF * 128 + (s ? 128 : 0));
+        tma_load_3d(dst, map_u, c.x0, rp, e * 12 + c.w0 * 6, bar);
+        if (s) tma_load_3d(dst + C::F_SH * 128, map_sh, c.x0, rp, e, bar);
     }
-    // 2. arrival of row r: stage-0 windows
+    // 2. arrival of row r: stage-0 windows, speed field of the row, interior pass-through of Psi/Omega
     if (r >= c.la && r < c.lb) {
         const int rel = r - c.la;
         if (!(A.dbg & 2)) mbar_wait(c.bar0 + (rel & (RING - 1)) * 8, (rel >> 3) & 1);
-        const float *ur = ring_row(c, r);
-        const float shv = sh_at(c, r);
+        float *ur = c.ring + (rel & (RING - 1)) * C::SLOT_F + c.lane;
+        const float shv = src_row(c, r) ? ur[C::F_SH * 32] : 0.0f;
         constexpr int s0 = PH & 3;
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
+        for (int w = 0; w < C::NW; ++w) {
             R.Uf[0][w][s0] = ur[w * 6 * 32] + shv * c.sf[0];
             R.Vy[0][w][s0] = ur[w * 6 * 32 + 64];
         }
+        if (c.nact != 0) speed_row(c, A, ep, e, r, ur + C::F_B * 32);
+        if (!GENERAL) {
+            const bool st = (unsigned)(r - c.js0) < c.jsn;
+#pragma unroll
+            for (int w = 0; w < C::NW; ++w) {
+                const float px = ur[(w * 6 + 3) * 32], py = ur[(w * 6 + 4) * 32], om = ur[(w * 6 + 5) * 32];
+                ur[(C::F_P + w) * 32] = (px + py) - om;
+                if (st) {
+                    float *o = c.out_e + (unsigned)(w * 6 + 3) * c.plane + (unsigned)r * c.nxp;
+                    o[0] = px;
+                    o[c.plane] = py;
+                    o[2u * c.plane] = om;
+                }
+            }
+        }
     }
-    // 3. the four stages, each one row behind the previous
-    const int jlo = c.la + 1, jhi = c.lb - 2;  // rows with both y-neighbours loaded
     if (A.dbg & 1) return;
-    if (r - 1 >= jlo && r - 1 <= jhi) stage<GENERAL, 1, PH>(c, A, ep, e, R, r - 1);
-    if (r - 2 >= jlo && r - 2 <= jhi) stage<GENERAL, 2, PH>(c, A, ep, e, R, r - 2);
-    if (r - 3 >= jlo && r - 3 <= jhi) stage<GENERAL, 3, PH>(c, A, ep, e, R, r - 3);
-    if (r - 4 >= jlo && r - 4 <= jhi) stage<GENERAL, 4, PH>(c, A, ep, e, R, r - 4);
+    // 3. the four stages, each one row behind the previous
+    // (rows below la + 1 run unguarded: whatever they compute is overwritten before any stored cell reads it;
+    //  rows above lb - 2 must not run: they would clobber the border row's window slots)
+    const int jhi = c.lb - 2;
+    if (r - 1 <= jhi) stage<GENERAL, 1, PH>(c, A, e, R, r - 1);
+    if (r - 2 <= jhi) stage<GENERAL, 2, PH>(c, A, e, R, r - 2);
+    if (r - 3 <= jhi) stage<GENERAL, 3, PH>(c, A, e, R, r - 3);
+    if (r - 4 <= jhi) stage<GENERAL, 4, PH>(c, A, e, R, r - 4);
 }
 
 template <bool GENERAL>
-__global__ void __launch_bounds__(WARPS * 32, GENERAL ? 2 : 3)
+__global__ void __launch_bounds__(WARPS * 32, 3)
 k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_sh) {
+    using C = Cfg<GENERAL>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * WARPS + warp;
+    long long gw = (long long)blockIdx.x * WARPS + warp;
+    const int w0 = GENERAL ? (int)(gw & 1) : 0;  // general: two warps (tot, inc) per item
+    if (GENERAL) gw >>= 1;
     const int e = (int)(gw / A.n_items), it = (int)(gw - (long long)e * A.n_items);
     if (e >= A.gp.n_env) return;
     const GridP &gp = A.gp;
     const Item item = A.items[it];
     const EnvParams ep = A.env[e];
 
-    // per-warp shared memory carve-up
-    constexpr int WARP_BYTES = RING * SLOT_F * 4 + BSET_F * 4 + CYL_CAP * 12 * 4 + RING * 8;
-    unsigned char *wbase = smem_raw + (size_t)warp * ((WARP_BYTES + 127) & ~127);
+    float *wbase = reinterpret_cast<float *>(smem_raw + (size_t)warp * C::WARP_BYTES);
     WarpCtx c;
-    c.ring = reinterpret_cast<float *>(wbase);
-    c.bset = c.ring + RING * SLOT_F;
-    c.cyl = c.bset + BSET_F;
-    c.bar0 = smem_u32(c.cyl + CYL_CAP * 12);
+    c.ring = wbase;
+    c.bset = wbase + RING * C::SLOT_F;
+    c.cyl = wbase + RING * C::SLOT_F + C::BSET_F;
+    c.bar0 = smem_u32(wbase + RING * C::SLOT_F + C::BSET_F + CYL_CAP * 12);
     c.lane = lane;
+    c.w0 = w0;
+    c.is_tot = w0 == 0;
     c.x0 = item.x0;
     c.col = item.x0 + lane;
     c.la = item.la;
     c.lb = item.lb;
-    c.j0 = item.j0;
-    c.j1 = item.j1;
     c.top = item.top;
     c.bot = item.bot;
-    c.valid_lane = lane >= item.vlo && lane < item.vhi;
+    const bool valid_lane = lane >= item.vlo && lane < item.vhi;
+    {
+        // regular stages store rows that have both y-neighbours loaded; border rows belong to border_row_stage
+        const int js0 = max(item.j0, item.la + 1), js1 = min(item.j1, item.lb - 1);
+        c.js0 = js0;
+        c.jsn = (valid_lane && js1 > js0) ? (unsigned)(js1 - js0) : 0u;
+        c.jb0 = item.j0;
+        c.jbn = valid_lane ? (unsigned)(item.j1 - item.j0) : 0u;
+    }
+    c.plane = (unsigned)gp.plane;
+    c.nxp = (unsigned)gp.nxp;
+    c.out_e = A.out + (long long)e * gp.env_stride + (long long)w0 * 6 * gp.plane + min(c.col, gp.nx - 1);
     c.is_first_col = c.col == 0;
     c.is_last_col = c.col == gp.nx - 1;
     c.xb = (item.x0 == 0) || (item.x0 + 32 >= gp.nx);
@@ -531,9 +591,11 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     c.sf[0] = trow[3];
     c.sf[1] = trow[4];
     c.sf[2] = trow[5];
-    c.src_cols = ep.has_source && item.x0 < ep.src_i1 && item.x0 + 32 > ep.src_i0;
-    c.src_j0 = ep.src_j0;
-    c.src_j1 = ep.src_j1;
+    {
+        const bool src_cols = ep.has_source && item.x0 < ep.src_i1 && item.x0 + 32 > ep.src_i0;
+        c.src_j0 = ep.src_j0;
+        c.src_n = (src_cols && ep.src_j1 > ep.src_j0) ? (unsigned)(ep.src_j1 - ep.src_j0) : 0u;
+    }
 
     if (lane == 0 && !(A.dbg & 8)) {
         for (int s = 0; s < RING; ++s) mbar_init(c.bar0 + s * 8, 1);
@@ -541,9 +603,10 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
+
     // cull the design's cylinders against this warp's window, at the three stage times (src/designs.jl:287-292)
     c.nact = 0;
-    if (ep.ncyl > 0 && !(A.dbg & 4)) {
+    if (ep.ncyl > 0 && (!GENERAL || c.is_tot) && !(A.dbg & 4)) {
         const float xlo = gp.x[item.x0], xhi = gp.x[min(item.x0 + 31, gp.nx - 1)];
         const float ylo = gp.y[min(max(gp.grow0 + item.la, 0), gp.ny_global - 1)];
         const float yhi = gp.y[min(max(gp.grow0 + item.lb - 1, 0), gp.ny_global - 1)];
@@ -587,11 +650,11 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
 
     Regs<GENERAL> R;
     R.e_tot = R.e_inc = R.e_sc = 0.0f;
-    // zero-init windows so never-consumed warm-up lanes hold finite values
+    // zero-init windows so never-consumed warm-up values are finite
 #pragma unroll
     for (int s = 0; s < 4; ++s)
 #pragma unroll
-        for (int w = 0; w < 2; ++w)
+        for (int w = 0; w < C::NW; ++w)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 R.Uf[s][w][q] = 0.f;
@@ -603,7 +666,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
                 R.Om[s][w][q] = 0.f;
             }
 #pragma unroll
-    for (int w = 0; w < 2; ++w)
+    for (int w = 0; w < C::NW; ++w)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             R.aU[w][q] = R.aVx[w][q] = R.aVy[w][q] = 0.f;
@@ -611,6 +674,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
         }
 
     const int r_begin = (c.la - PF) & ~3, r_end = c.lb + 4;  // the first PF steps only prefetch
+#pragma unroll 1
     for (int r = r_begin; r < r_end; r += 4) {
         row_step<GENERAL, 0>(c, A, ep, e, R, r, &map_u, &map_sh);
         row_step<GENERAL, 1>(c, A, ep, e, R, r + 1, &map_u, &map_sh);
@@ -618,7 +682,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
         row_step<GENERAL, 3>(c, A, ep, e, R, r + 3, &map_u, &map_sh);
     }
 
-    if (A.epart) {
+    if (!GENERAL && A.epart) {
         float et = R.e_tot, ei = R.e_inc, es = R.e_sc;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -632,6 +696,39 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
             p[1] = ei;
             p[2] = es;
         }
+    }
+}
+
+// Energy partials of the output cells owned by the general items (PML strips / borders): one warp per item,
+// reading the freshly written U_tot / U_inc rows (src/env.jl:104-111).
+__global__ void __launch_bounds__(128) k_energy_items(GridP gp, const float *__restrict__ u, const Item *__restrict__ items, int n_items,
+                                                      float *__restrict__ epart, int epart_stride, int epart_off) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int e = (int)(gw / n_items), it = (int)(gw - (long long)e * n_items);
+    if (e >= gp.n_env) return;
+    const Item item = items[it];
+    const float *ut = u + (long long)e * gp.env_stride, *ui = ut + 6 * gp.plane;
+    float et = 0.f, ei = 0.f, es = 0.f;
+    if (lane >= item.vlo && lane < item.vhi) {
+        for (int j = item.j0; j < item.j1; ++j) {
+            const long long q = (long long)j * gp.nxp + item.x0 + lane;
+            const float a = ut[q], b = ui[q], d = a - b;
+            et += a * a;
+            ei += b * b;
+            es += d * d;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        et += __shfl_down_sync(0xffffffffu, et, o);
+        ei += __shfl_down_sync(0xffffffffu, ei, o);
+        es += __shfl_down_sync(0xffffffffu, es, o);
+    }
+    if (lane == 0) {
+        float *p = epart + ((size_t)e * epart_stride + epart_off + it) * 3;
+        p[0] = et;
+        p[1] = ei;
+        p[2] = es;
     }
 }
 
@@ -675,7 +772,7 @@ struct FusedPlan {
     int n_int = 0, n_gen = 0;
     float *d_epart = nullptr;
     int *d_bb = nullptr;
-    int smem_bytes = 0;
+    int smem_int = 0, smem_gen = 0;
 };
 
 FusedPlan *plan_of(waves_handle *h, bool create) {
@@ -688,6 +785,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_map(PFN_encodeTiled enc, CUtensorMap *m, float *base, const GridP &gp, int planes, int box_planes) {
+    // box = 32 columns x 1 row x box_planes field planes
     cuuint64_t dims[3] = {(cuuint64_t)gp.nx, (cuuint64_t)gp.ny_alloc, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)gp.nxp * 4, (cuuint64_t)gp.plane * 4};
     cuuint32_t box[3] = {32, 1, (cuuint32_t)box_planes};
@@ -813,16 +911,16 @@ int fused_prepare(waves_handle *h) {
     cudaMalloc((void **)&p->d_epart, sizeof(float) * 3 * (size_t)(ii.size() + gg.size()) * gp.n_env);
     cudaMalloc((void **)&p->d_bb, sizeof(int) * 4);
 
-    constexpr int WARP_BYTES = RING * SLOT_F * 4 + BSET_F * 4 + CYL_CAP * 12 * 4 + RING * 8;
-    p->smem_bytes = WARPS * ((WARP_BYTES + 127) & ~127);
-    cudaError_t ce = cudaFuncSetAttribute(k_fused_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes);
+    p->smem_gen = WARPS * Cfg<true>::WARP_BYTES;
+    p->smem_int = WARPS * Cfg<false>::WARP_BYTES;
+    cudaError_t ce = cudaFuncSetAttribute(k_fused_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_gen);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_int);
     if (ce != cudaSuccess) {
         char buf[256];
         snprintf(buf, sizeof(buf), "fused_prepare: cudaFuncSetAttribute: %s (was the library built for sm_100a?)", cudaGetErrorString(ce));
         return waves_set_error(buf);
     }
-    h->fused_smem = p->smem_bytes;
+    h->fused_smem = p->smem_int;
 
     // TMA descriptors
     void *fn = nullptr;
@@ -833,6 +931,8 @@ int fused_prepare(waves_handle *h) {
     int r0 = make_map(enc, &h->map_u[0], h->u[0], gp, 12 * gp.n_env, 12);
     int r1 = make_map(enc, &h->map_u[1], h->u[1], gp, 12 * gp.n_env, 12);
     int r2 = make_map(enc, &h->map_shape, h->shape, gp, gp.n_env, 1);
+    r0 |= make_map(enc, &h->map_u6[0], h->u[0], gp, 12 * gp.n_env, 6);
+    r1 |= make_map(enc, &h->map_u6[1], h->u[1], gp, 12 * gp.n_env, 6);
     if (r0 || r1 || r2) {
         char buf[256];
         snprintf(buf, sizeof(buf), "fused_prepare: cuTensorMapEncodeTiled failed (%d %d %d)", r0, r1, r2);
@@ -888,18 +988,24 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
         A.n_items = p->n_int;
         A.epart_off = 0;
         long long warps = (long long)p->n_int * h->gp.n_env;
-        k_fused_step<false><<<(unsigned)((warps + WARPS - 1) / WARPS), WARPS * 32, p->smem_bytes, h->stream>>>(A, h->map_u[h->cur],
-                                                                                                          h->map_shape);
+        k_fused_step<false><<<(unsigned)((warps + WARPS - 1) / WARPS), WARPS * 32, p->smem_int, h->stream>>>(A, h->map_u[h->cur],
+                                                                                                        h->map_shape);
         h->launches++;
     }
     if (p->n_gen > 0 && !(dbg_skip & 2)) {
         A.items = p->d_items_gen;
         A.n_items = p->n_gen;
         A.epart_off = p->n_int;
-        long long warps = (long long)p->n_gen * h->gp.n_env;
-        k_fused_step<true><<<(unsigned)((warps + WARPS - 1) / WARPS), WARPS * 32, p->smem_bytes, h->stream>>>(A, h->map_u[h->cur],
-                                                                                                         h->map_shape);
+        long long warps = 2LL * p->n_gen * h->gp.n_env;  // one warp per wavefield
+        k_fused_step<true><<<(unsigned)((warps + WARPS - 1) / WARPS), WARPS * 32, p->smem_gen, h->stream>>>(A, h->map_u6[h->cur],
+                                                                                                       h->map_shape);
         h->launches++;
+        if (d_e3) {
+            long long ew = (long long)p->n_gen * h->gp.n_env;
+            k_energy_items<<<(unsigned)((ew + 3) / 4), 128, 0, h->stream>>>(h->gp, A.out, p->d_items_gen, p->n_gen, p->d_epart,
+                                                                            A.epart_stride, p->n_int);
+            h->launches++;
+        }
     }
     if (h->profile) {
         cudaEventRecord(h->ev1, h->stream);
