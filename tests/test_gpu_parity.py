@@ -1,0 +1,306 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the
+oracle on the same seeded inputs, the committed golden fixtures, and size-independent properties at the
+BASELINE sizes.  Tolerance (BASELINE.json north_star): relative L2 <= 1e-4 on fields and energy traces;
+WAVES_MODE_EXACT is additionally required to be BIT-EXACT with the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import waves_b200 as wb
+from oracle import c_oracle as co
+from oracle import waves_oracle as wo
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+TOL = 1e-4        # stated tolerance
+TIGHT = 2e-5      # what the fused kernel actually delivers (FMA contraction + reassociated stencils)
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / (np.linalg.norm(b.astype(np.float64)) + 1e-300))
+
+
+def table(cyl):
+    return np.ascontiguousarray(np.concatenate([cyl.pos, cyl.r[:, None], cyl.c[:, None]], axis=1), F32)
+
+
+def make_engine(dim, dyn, n_env=1, dO=None):
+    dO = F32(wo.get_dx(dim) * wo.get_dy(dim)) if dO is None else dO
+    return wb.Engine(dim.x, dim.y, dyn.c0, 1e-5, n_env=n_env, sigma=dyn.pml, grad8=co.grad8(dyn.grad), d_omega=float(dO))
+
+
+def load_small(golden_dir):
+    g = np.load(os.path.join(golden_dir, "small_design_96.npz"))
+    dim = wo.TwoDim.make(g["grid_size"], int(g["n"]))
+    dyn = wo.AcousticDynamics.make(dim, g["c0"], g["pml_width"], g["pml_scale"])
+    return g, dim, dyn
+
+
+@pytest.mark.parametrize("mode", [wb.MODE_EXACT, wb.MODE_FUSED])
+def test_golden_small(golden_dir, mode):
+    g, dim, dyn = load_small(golden_dir)
+    eng = make_engine(dim, dyn, dO=g["dOmega"])
+    ts = g["tspan"]
+    eng.set_state(g["u0"][None])
+    eng.set_source(g["shape"], float(g["freq"]))
+    eng.set_design(g["cyl0"], g["cyl1"], ts[0], ts[-1])
+    k = eng.rhs(g["rhs_t"])
+    assert np.array_equal(k, g["rhs"]), "dyn(x,t,θ) must be bit-exact"
+    en, fr = eng.integrate(ts, mode, energy=True, save_steps=[1, len(ts) - 1])
+    final = eng.get_state(0)
+    if mode == wb.MODE_EXACT:
+        assert np.array_equal(fr[0, 0], g["step1"]) and np.array_equal(final, g["final"])
+        assert np.allclose(en[0], g["energy"], rtol=1e-6, atol=0)
+    else:
+        assert rel(fr[0, 0], g["step1"]) < TIGHT and rel(final, g["final"]) < TIGHT
+        for f in range(12):
+            assert rel(final[f], g["final"][f]) < TOL, f"field {f}"
+        assert np.abs(en[0] - g["energy"]).max() / g["energy"].max() < TIGHT
+    assert np.array_equal(fr[0, 1], final)
+    eng.close()
+
+
+def test_golden_config1_fused(golden_dir):
+    """BASELINE config 1: TwoDim(15,700), Gaussian source, no design, 100 steps."""
+    g = np.load(os.path.join(golden_dir, "config1_700.npz"))
+    dim = wb.TwoDim(15.0, 700)
+    assert np.array_equal(dim.x, g["x"])
+    eng = wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 2.0, 20000.0, d_omega=float(g["dOmega"]))
+    shape = wb.build_normal(dim, [[-10.0, 0.0]], [0.3], [1.0])
+    assert np.array_equal(shape[350], g["shape_row350"])
+    eng.set_source(shape, 1000.0)
+    en, fr = eng.integrate(g["tspan"], wb.MODE_FUSED, energy=True, save_steps=[1, 10, 100])
+    for i, s in enumerate((1, 10, 100)):
+        got, want = fr[0, i][:, g["probe_j"], g["probe_i"]], g[f"probes_{s}"]
+        assert rel(got, want) < TIGHT   # (plain field sums cancel to rounding noise: only the bit-exact oracle test pins them)
+    e, ge = en[0], g["energy"]
+    assert rel(e[:, 0], ge[:, 0]) < TIGHT and rel(e[:, 1], ge[:, 1]) < TIGHT
+    # no design: both wavefields see identical inputs -> bitwise equal, scattered energy exactly 0
+    final = fr[0, 2]
+    assert np.array_equal(final[:6], final[6:]) and np.all(e[:, 2] == 0)
+    eng.close()
+
+
+@pytest.mark.parametrize("n,gs,pw,dt", [(33, 1.0, 0.3, 5e-6), (70, 2.0, 0.5, 1e-5), (100, 3.0, 0.0, 1e-5), (257, 6.0, 1.0, 1e-5)])
+def test_ragged_sizes_vs_oracle(n, gs, pw, dt):
+    """Edge cases: nx not a multiple of 4 / of the 24-column strip, tiny grids, pml_width = 0."""
+    dim = wo.TwoDim.make(gs, n)
+    dyn = wo.AcousticDynamics.make(dim, wo.WATER, pw if pw > 0 else 0.5, 20000.0 if pw > 0 else 0.0)
+    rng = np.random.default_rng(n)
+    u0 = (rng.standard_normal((12, n, n)) * 1e-3).astype(F32)
+    shape = wo.build_normal(wo.build_grid(dim), np.array([[-0.3 * gs, 0.1 * gs]]), np.array([0.08 * gs]), np.array([1.0]))
+    pos = np.array([[0.2 * gs, 0.0], [0.35 * gs, 0.1 * gs], [-0.1 * gs, -0.4 * gs]], F32)
+    d0 = wo.Cylinders(pos, np.array([0.15, 0.1, 0.2]) * gs, [1032.0, 1032.0, 2120.0])
+    d1 = wo.Cylinders(pos, np.array([0.2, 0.08, 0.12]) * gs, [1032.0, 1032.0, 2120.0])
+    ts = wo.build_tspan(F32(2e-4), F32(dt), 12)
+    dO = F32(wo.get_dx(dim) * wo.get_dy(dim))
+    ref, ren, _ = co.integrate(dyn, u0, ts, dt, dO, d0, d1, ts[0], ts[-1], shape=shape, freq=1000.0)
+    for mode in (wb.MODE_EXACT, wb.MODE_FUSED):
+        eng = wb.Engine(dim.x, dim.y, dyn.c0, dt, sigma=dyn.pml, grad8=co.grad8(dyn.grad), d_omega=float(dO))
+        eng.set_state(u0[None])
+        eng.set_source(shape, 1000.0)
+        eng.set_design(table(d0), table(d1), ts[0], ts[-1])
+        en, _ = eng.integrate(ts, mode)
+        got = eng.get_state(0)
+        if mode == wb.MODE_EXACT:
+            assert np.array_equal(got, ref)
+        else:
+            assert rel(got, ref) < TIGHT
+            for f in range(12):
+                assert rel(got[f], ref[f]) < TOL
+        assert np.abs(en[0] - ren).max() / ren.max() < TIGHT
+        eng.close()
+
+
+def test_batch_of_independent_envs():
+    """config 3 in miniature: every env has its own state, design and source; no cross-talk."""
+    n, E = 96, 5
+    dim = wo.TwoDim.make(3.0, n)
+    dyn = wo.AcousticDynamics.make(dim, wo.WATER, 0.6, 20000.0)
+    grid = wo.build_grid(dim)
+    dO = F32(wo.get_dx(dim) * wo.get_dy(dim))
+    ts = wo.build_tspan(F32(1e-4), F32(1e-5), 15)
+    eng = make_engine(dim, dyn, n_env=E)
+    refs = []
+    for e in range(E):
+        rng = np.random.default_rng(100 + e)
+        u0 = (rng.standard_normal((12, n, n)) * 1e-3).astype(F32)
+        shape = wo.build_normal(grid, rng.uniform(-1.5, 1.5, (1, 2)), np.array([0.15]), np.array([1.0]))
+        pos = rng.uniform(-1.2, 1.2, (4, 2)).astype(F32)
+        d0 = wo.Cylinders(pos, rng.uniform(0.2, 0.5, 4), [1032.0] * 4)
+        d1 = wo.Cylinders(pos, rng.uniform(0.2, 0.5, 4), [1032.0] * 4)
+        eng.set_state(u0[None], env=e)
+        if e == 2:   # one env without source, one without design
+            eng.set_source(None, 0.0, env=e)
+            shape = None
+        else:
+            eng.set_source(shape, 900.0 + 50 * e, env=e)
+        if e == 3:
+            eng.set_design(None, None, 0, 0, env=e)
+            d0 = d1 = None
+        else:
+            eng.set_design(table(d0), table(d1), ts[0], ts[-1], env=e)
+        refs.append(co.integrate(dyn, u0, ts, 1e-5, dO, d0, d1, ts[0], ts[-1], shape=shape, freq=900.0 + 50 * e))
+    en, _ = eng.integrate(ts, wb.MODE_FUSED)
+    got = eng.get_state(-1)
+    for e in range(E):
+        assert rel(got[e], refs[e][0]) < TIGHT, f"env {e}"
+        assert np.abs(en[e] - refs[e][1]).max() / refs[e][1].max() < TIGHT
+    eng.close()
+
+
+def test_waveenv_mirror_matches_oracle_env():
+    """(env::WaveEnv)(action) (src/env.jl:91-121): signal, kept frames, design and time bookkeeping."""
+    n = 128
+    dimo, dimg = wo.TwoDim.make(15.0, n), wb.TwoDim(15.0, n)
+    dso, dsg = wo.build_triple_ring_design_space(), wb.build_triple_ring_design_space()
+    rng = np.random.default_rng(2)
+    d_init = dsg.rand(rng)
+    shape = wb.build_normal(dimg, [[-6.0, 1.0]], [0.8], [1.0])
+    envg = wb.WaveEnv(dimg, design_space=dsg, source=wb.Source(shape, 1000.0), dt=2e-5, integration_steps=30, actions=3)
+    envg.design = d_init
+    envo = wo.WaveEnv(dimo, dso, wo.Source(shape, F32(1000.0)), dt=2e-5, integration_steps=30, actions=3,
+                      design=wo.Cloak(wo.Cylinders(d_init.config.pos, d_init.config.r, d_init.config.c),
+                                      wo.Cylinders(d_init.core.pos, d_init.core.r, d_init.core.c)))
+    sig_g, sig_o = [], []
+    while not envg.is_terminated():
+        act = envg.action_space().rand(rng)
+        tg, _, ut, ui = envg(act, return_frames=True)
+        to, _, uto, uio = envo(wo.Cylinders(act.pos, act.r, act.c))
+        assert np.array_equal(tg, to)
+        assert rel(ut, uto) < TIGHT and rel(ui, uio) < TIGHT
+        assert rel(envg.wave, envo.wave) < TIGHT
+        sig_g.append(envg.signal)
+        sig_o.append(envo.signal)
+    assert envo.is_terminated() and envg.time_step == envo.time_step == 90
+    sg, so = wo.flatten_repeated_last_dim(np.stack(sig_g)), wo.flatten_repeated_last_dim(np.stack(sig_o))
+    assert sg.shape == (91, 3) and rel(sg, so) < TIGHT
+    assert so[-1, 2] > 0, "the pulse must have reached the scatterers"
+    assert abs(float(envg.reward()) - float(envo.reward())) <= 1e-4 * abs(float(envo.reward()))
+
+
+def test_integrator_mirror_returns_reference_shape():
+    dim = wb.TwoDim(5.0, 128)
+    it = wb.Integrator(wb.AcousticDynamics(dim, wb.WATER, 1.0, 0.0), 1e-5)
+    wave = wb.build_wave(dim, 12)
+    ic = wb.build_normal(dim, [[0.0, 0.0]], [0.3], [1.0])
+    wave[0] = ic
+    wave[6] = ic
+    ts = it.build_tspan(0.0, 20)
+    sol = it(wave, ts, (None, wb.NoSource()))       # scripts/pml.jl:6-18
+    assert sol.shape == (21, 12, 128, 128) and np.array_equal(sol[0], wave)
+    assert np.array_equal(sol[:, :6], sol[:, 6:])
+
+
+# ---- BASELINE-size properties (700^2), independent of any oracle run --------------------------
+def _engine700(n_env=1):
+    dim = wb.TwoDim(15.0, 700)
+    return dim, wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 2.0, 20000.0, n_env=n_env)
+
+
+def test_full_size_linearity_and_fused_vs_exact():
+    """Without a source the step is linear: scaling the state by 2 scales the result by exactly 2 (bitwise);
+    and the fused kernel agrees with the exact per-stage kernels at full size."""
+    dim, eng = _engine700(2)
+    ds = wb.build_triple_ring_design_space()
+    rng = np.random.default_rng(11)
+    d0 = ds.rand(rng)
+    d1 = ds(d0, wb.build_action_space(d0, 0.25).rand(rng))
+    u0 = (rng.standard_normal((12, 700, 700)) * 1e-3).astype(F32)
+    ts = wb.build_tspan(0.0, 1e-5, 6)
+    eng.set_design(d0.table(), d1.table(), ts[0], ts[-1])
+    eng.set_state(u0[None], env=0)
+    eng.set_state((2 * u0)[None], env=1)
+    eng.integrate(ts, wb.MODE_FUSED, energy=False)
+    a = eng.get_state(-1)
+    assert np.array_equal(2 * a[0], a[1])
+    eng.set_state(u0[None], env=0)
+    eng.set_state(u0[None], env=1)
+    eng.integrate(ts, wb.MODE_EXACT, energy=False)
+    b = eng.get_state(0)
+    assert rel(a[0], b) < TIGHT
+    eng.close()
+
+
+def test_full_size_transpose_symmetry():
+    dim, eng = _engine700(2)
+    ic = wb.build_normal(dim, [[3.0, -5.0]], [0.4], [1.0])
+    u = np.zeros((2, 12, 700, 700), F32)
+    u[0, 0] = u[0, 6] = ic
+    u[1, 0] = u[1, 6] = ic.T
+    eng.set_state(u)
+    en, _ = eng.integrate(wb.build_tspan(0.0, 1e-5, 40), wb.MODE_FUSED)
+    out = eng.get_state(-1)
+    perm = [0, 2, 1, 4, 3, 5]
+    bt = np.stack([out[1, p].T for p in perm])
+    assert rel(out[0, :6], bt) < TIGHT and np.allclose(en[0], en[1], rtol=1e-5)
+    eng.close()
+
+
+def test_pml_absorbs_and_walls_reflect():
+    """scripts/pml.jl: free pulse, energy kept with pml_scale = 0, absorbed with the PML on."""
+    dim = wb.TwoDim(5.0, 160)
+    ic = wb.build_normal(dim, [[0.7, -0.4]], [0.3], [1.0])
+    u = np.zeros((1, 12, 160, 160), F32)
+    u[0, 0] = u[0, 6] = ic
+    ts = wb.build_tspan(0.0, 1e-5, 700)
+    ends = []
+    for scale in (0.0, 20000.0):
+        eng = wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 1.0, scale)
+        eng.set_state(u)
+        en, _ = eng.integrate(ts, wb.MODE_FUSED)
+        assert np.all(np.isfinite(en))
+        ends.append((en[0, 0, 0], en[0, -1, 0]))
+        eng.close()
+    assert ends[1][1] < 0.02 * ends[1][0] and ends[0][1] > 10 * ends[1][1]
+
+
+def test_speed_plane_and_error_behaviour():
+    n = 64
+    dim = wo.TwoDim.make(2.0, n)
+    dyn = wo.AcousticDynamics.make(dim, wo.WATER, 0.4, 20000.0)
+    rng = np.random.default_rng(9)
+    u0 = (rng.standard_normal((12, n, n)) * 1e-3).astype(F32)
+    cpl = (1531.0 - 400.0 * np.exp(-((wo.build_grid(dim)[0]) ** 2 + (wo.build_grid(dim)[1]) ** 2))).astype(F32)
+    ts = wo.build_tspan(F32(0.0), F32(1e-5), 5)
+    dO = F32(wo.get_dx(dim) * wo.get_dy(dim))
+    ref, _, _ = co.integrate(dyn, u0, ts, 1e-5, dO, cplane=cpl)
+    eng = make_engine(dim, dyn)
+    eng.set_state(u0[None])
+    eng.set_speed_field(cpl)
+    eng.integrate(ts, wb.MODE_EXACT, energy=False)
+    assert np.array_equal(eng.get_state(0), ref)
+    with pytest.raises(wb.WavesError, match="speed plane"):
+        eng.integrate(ts, wb.MODE_FUSED, energy=False)
+    with pytest.raises(wb.WavesError):
+        eng.integrate(ts, 7, energy=False)
+    with pytest.raises(wb.WavesError, match="ascending"):
+        eng.set_speed_field(None)
+        eng.integrate(ts, wb.MODE_FUSED, energy=False, save_steps=[3, 2])
+    with pytest.raises(wb.WavesError, match="out of range"):
+        eng.set_state(u0[None], env=4)
+    eng.close()
+    with pytest.raises(wb.WavesError, match="sigma_y"):
+        wb.Engine(dim.x, dim.y[:-1], 1531.0, 1e-5)
+
+
+def test_many_cylinders_overflow_path():
+    """More cylinders under one warp window than its culled list holds (slow exact loop)."""
+    n = 96
+    dim = wo.TwoDim.make(3.0, n)
+    dyn = wo.AcousticDynamics.make(dim, wo.WATER, 0.6, 20000.0)
+    rng = np.random.default_rng(21)
+    pos = rng.uniform(-0.8, 0.8, (40, 2)).astype(F32)
+    d0 = wo.Cylinders(pos, rng.uniform(0.1, 0.4, 40), rng.uniform(900, 1400, 40))
+    d1 = wo.Cylinders(pos, rng.uniform(0.1, 0.4, 40), d0.c)
+    u0 = (rng.standard_normal((12, n, n)) * 1e-3).astype(F32)
+    ts = wo.build_tspan(F32(0.0), F32(1e-5), 6)
+    dO = F32(wo.get_dx(dim) * wo.get_dy(dim))
+    ref, ren, _ = co.integrate(dyn, u0, ts, 1e-5, dO, d0, d1, ts[0], ts[-1])
+    eng = make_engine(dim, dyn)
+    eng.set_state(u0[None])
+    eng.set_design(table(d0), table(d1), ts[0], ts[-1])
+    en, _ = eng.integrate(ts, wb.MODE_FUSED)
+    assert rel(eng.get_state(0), ref) < TIGHT
+    eng.close()

@@ -1,0 +1,94 @@
+"""CPU-only tests of the product's host side: the C ABI library loads and exports every symbol the header
+declares, its host-side restatements of the reference constructors agree with the oracle, the Python
+mirror of the reference types behaves like the oracle's, and the product fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import waves_b200 as wb
+from oracle import c_oracle as co
+from oracle import waves_oracle as wo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+F32 = np.float32
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "waves_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(waves_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = C.CDLL(wb._lib.SO_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/waves_b200.h but not exported"
+    assert declared == set(wb._lib.SYMBOLS), "ctypes binding and header disagree"
+    assert wb._lib.lib().waves_version() == 100
+
+
+def test_no_oracle_in_product():
+    """The product must never import or link the oracle (test infrastructure only)."""
+    pkg = os.path.join(ROOT, "waves.jl_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".jl")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in txt.lower().replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu():
+    dim = wb.TwoDim(15.0, 64)
+    with pytest.raises(wb.WavesError, match="no CUDA device|no CPU path"):
+        wb.Engine(dim.x, dim.y, 1531.0, 1e-5)
+
+
+@pytest.mark.parametrize("gs,n", [(15.0, 700), (5.0, 512), (3.0, 96), (2.0, 33)])
+def test_host_builders_match_oracle(gs, n):
+    d = wb.TwoDim(gs, n)
+    o = wo.TwoDim.make(gs, n)
+    assert np.array_equal(d.x, o.x) and np.array_equal(d.y, o.y)
+    assert np.array_equal(wb.build_pml(d, 2.0 if gs > 4 else 0.5, 20000.0), wo.build_pml_profile(o.x, 2.0 if gs > 4 else 0.5, 20000.0))
+    assert np.array_equal(wb.build_gradient(d), co.grad8(wo.build_gradient(o.x)))
+    assert abs(float(wb.get_dx(d)) - float(wo.get_dx(o))) <= 2e-7 * float(wo.get_dx(o))
+    mu, sg, a = np.array([[-0.4 * gs, 0.1 * gs], [0.2, -0.3]]), np.array([0.3, 0.2]), np.array([1.0, 0.5])
+    assert np.array_equal(wb.build_normal(d, mu, sg, a), wo.build_normal(wo.build_grid(o), mu, sg, a))
+
+
+def test_tspan_matches_oracle():
+    for ts, steps in [(0, 100), (100, 100), (1900, 100), (37, 13)]:
+        ti = F32(F32(ts) * F32(1e-5))
+        assert np.array_equal(wb.build_tspan(ti, 1e-5, steps), wo.build_tspan(ti, 1e-5, steps))
+
+
+def test_design_types_match_oracle():
+    a, b = wb.build_triple_ring_design_space(), wo.build_triple_ring_design_space()
+    assert np.array_equal(a.low.table(), np.concatenate([b.low.all_cylinders().pos, b.low.all_cylinders().r[:, None],
+                                                         b.low.all_cylinders().c[:, None]], 1))
+    ra, rb = np.random.default_rng(5), np.random.default_rng(5)
+    da = a.rand(ra)
+    # the oracle samples radii only; the mirror follows rand(::DesignSpace{Cylinders}) and draws pos, r, c
+    db = wo.Cloak(wo.Cylinders(da.config.pos, da.config.r, da.config.c), wo.Cylinders(da.core.pos, da.core.r, da.core.c))
+    act = wb.build_action_space(da, 0.25).rand(ra)
+    acto = wo.Cylinders(act.pos, act.r, act.c)
+    na, nb = a(da, act), b(db, acto)
+    assert np.array_equal(na.table()[:, 2], nb.all_cylinders().r)
+    ia, ib = wb.DesignInterpolator(da, na, F32(0.001), F32(0.002)), wo.DesignInterpolator(db, nb, F32(0.001), F32(0.002))
+    for t in (0.0005, 0.001, 0.00137, 0.002, 0.003):
+        assert np.array_equal(ia(F32(t)).table()[:, 2], ib(F32(t)).all_cylinders().r)
+
+
+def test_random_pos_gaussian_source_in_bounds():
+    d = wb.TwoDim(15.0, 128)
+    s = wb.RandomPosGaussianSource(d, [[-10.0, -10.0]], [[-10.0, 10.0]], [0.3], [1.0], 1000.0, rng=np.random.default_rng(3))
+    assert s.mu[0, 0] == -10 and -10 <= s.mu[0, 1] <= 10 and s.shape.shape == (128, 128)
