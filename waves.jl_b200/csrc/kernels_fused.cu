@@ -35,22 +35,29 @@ namespace {
 constexpr int RING = 8;      // ring slots (rows) per warp
 constexpr int PF = 2;        // TMA prefetch distance in rows
 constexpr int CYL_CAP = 12;  // culled cylinders kept per warp
-constexpr int WARPS = 4;     // warps per CTA (independent work items)
+constexpr int WARPS = 1;     // warps per CTA: one, so every item-derived value is provably CTA-uniform
 
 // Per-variant layout.  The interior variant marches BOTH wavefields in one warp (it needs both for
 // the scattered energy and has registers to spare); the general variant (PML strips, domain borders)
 // carries twice the state per wavefield, so each warp takes ONE wavefield.
+// Ring slot rows (32 floats each): [0, NF) state fields written by TMA, NF: source shape written by TMA,
+// then rows written by the warp itself on arrival: F_BK..+2 = kd*c^2 at the three stage times,
+// F_SHV = source shape or 0, F_P.. = Psix+Psiy-Omega per wavefield (interior only).
 template <bool GENERAL>
 struct Cfg {
-    static constexpr int NW = GENERAL ? 1 : 2;   // wavefields per warp
-    static constexpr int NF = 6 * NW;            // state fields per ring slot (TMA box depth)
-    static constexpr int F_SH = NF;              // source shape row
-    static constexpr int F_B = NF + 1;           // c^2 at the 3 stage times (tot wavefield)
-    static constexpr int F_P = NF + 4;           // interior only: Psix + Psiy - Omega per wavefield
-    static constexpr int SLOT_ROWS = GENERAL ? NF + 4 : NF + 6;
-    static constexpr int SLOT_F = SLOT_ROWS * 32;  // floats per ring slot
-    static constexpr int BSET_F = GENERAL ? 12 * 32 : 0;  // border-row state (general only)
-    static constexpr int WARP_BYTES = ((RING * SLOT_F * 4 + BSET_F * 4 + CYL_CAP * 12 * 4 + RING * 8) + 127) & ~127;
+    static constexpr int NW = GENERAL ? 1 : 2;
+    static constexpr int NF = 6 * NW;
+    static constexpr int F_SH = NF;
+    static constexpr int F_BK = NF + 1;
+    static constexpr int F_SHV = NF + 4;
+    static constexpr int F_P = NF + 5;
+    static constexpr int SLOT_ROWS = GENERAL ? NF + 5 : NF + 7;
+    static constexpr int SLOT_F = SLOT_ROWS * 32;
+    static constexpr int BSET_F = GENERAL ? 20 * 32 : 0;  // border-row state + call scratch (general only)
+    static constexpr int RING_F = RING * SLOT_F;
+    static constexpr int CYL_OFF = RING_F + BSET_F;
+    static constexpr int BAR_OFF = CYL_OFF + CYL_CAP * 12;
+    static constexpr int WARP_F = ((BAR_OFF + RING * 2) + 31) & ~31;  // floats per warp (128-byte multiple)
 };
 
 struct Item {
@@ -75,7 +82,14 @@ struct FusedArgs {
     int epart_stride;  // items per env in epart (all kernels of a step share one buffer)
     int epart_off;     // offset of this kernel's items
     int dbg;           // developer bisecting flags (WAVES_DEBUG_FLAGS)
+    // host-computed step constants: read straight from the constant bank as FFMA operands
+    float kd, b0kd;             // 1/(2Δ) and c0^2/(2Δ)
+    float akd_h, akd_f, dt6kd;  // (dt/2)kd, dt*kd, (dt/6)kd
+    float hdt, dt, dt6;
+    unsigned plane, nxp;
 };
+
+extern __shared__ __align__(128) float smf[];  // all shared memory, indexed with 32-bit arithmetic
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -118,42 +132,32 @@ __device__ __forceinline__ float interp_param(float p0, float p1, float ti, floa
     return __fadd_rn(p0, __fmul_rn(slope, s));
 }
 
+// Per-warp context.  Everything here is either warp-uniform or a per-lane constant of the whole march.
 struct WarpCtx {
-    // geometry
-    int lane, col, x0, la, lb;
+    int lane, wb;      // lane, first float of this warp's shared memory
+    int x0, la, lb;
     int js0;           // first row the regular stages may store
     unsigned jsn;      // rows [js0, js0+jsn) are stored by this lane (0 for halo lanes)
-    int jb0;           // first owned row (border routine)
-    unsigned jbn;      // owned rows for this lane incl. border rows (0 for halo lanes)
-    float *out_e;      // output state of this env (+ wavefield offset in the general variant)
-    unsigned plane;    // floats per field plane
-    unsigned nxp;
-    bool xb, top, bot, is_first_col, is_last_col;
-    bool is_tot;  // general variant: this warp carries the total wavefield (speed field applies)
-    int w0;       // general variant: wavefield index (plane offset w0*6)
+    float *out_e;      // output state of this env at this lane's column (+ wavefield offset in the general variant)
+    bool xb, top, bot, is_first_col, is_last_col, is_tot;
+    int w0;
     float xs, sx, bcm;
-    // step constants
-    float kd, dt, hdt, b0;
-    float sf[3];  // source factor at t, t+dt/2, t+dt
-    // smem
-    float *ring;    // [RING][SLOT_ROWS][32]
-    float *bset;    // border-row state
-    float *cyl;     // [CYL_CAP][3][4]
-    uint32_t bar0;  // smem address of mbarrier 0
-    int nact;       // culled cylinders (0: none touch this window, -1: list overflow -> slow loop)
-    // source: rows [src_j0, src_j0+src_n) of this window carry a non-zero shape (src_n == 0: none)
+    float sf[3];       // source factor at t, t+dt/2, t+dt
+    uint32_t bar0, ring_sa;  // shared-window addresses of mbarrier 0 and of the ring
+    int nact;          // culled cylinders (0: none touch this window, -1: list overflow -> slow loop)
     int src_j0;
-    unsigned src_n;
-    // global
-    const float *ys_g, *sig_g;
-    int grow0, ny_global;
+    unsigned src_n;    // rows [src_j0, src_j0+src_n) of this window carry a non-zero source shape
 };
 
 __device__ __forceinline__ bool src_row(const WarpCtx &c, int j) { return (unsigned)(j - c.src_j0) < c.src_n; }
 
 // c(x,y,t)^2 with every cylinder (list overflow), exact order of src/designs.jl:99-116
-__device__ __noinline__ float speed2_slow(float xs, float yv, const float *cyl0, const float *cyl1, int ncyl, float ti, float tf,
-                                          float t, float c0) {
+__device__ __noinline__ float speed2_slow(const FusedArgs &A, int e, int tau, float xs, float yv) {
+    const EnvParams ep = A.env[e];
+    const float *cyl0 = A.cyl0 + (size_t)e * A.cyl_cap * 4, *cyl1 = A.cyl1 + (size_t)e * A.cyl_cap * 4;
+    const int ncyl = ep.ncyl;
+    const float ti = ep.ti, tf = ep.tf, c0 = A.gp.c0;
+    const float t = A.table[((size_t)e * A.steps + A.step) * STAGE_ROW + tau];
     int cnt = 0;
     float cd = 0.0f;
     for (int k = 0; k < ncyl; ++k) {
@@ -171,10 +175,12 @@ __device__ __noinline__ float speed2_slow(float xs, float yv, const float *cyl0,
     return __fmul_rn(cv, cv);
 }
 
-// speed(design(t), grid, c0)^2 of local row j at the three stage times -> dst[0], dst[32], dst[64]
+// kd * speed(design(t), grid, c0)^2 of local row j at the three stage times -> smf[dst + tau*32]
 // (src/designs.jl:99-116: strict '<', speeds of overlapping cylinders add, ambient where none).
-__device__ __forceinline__ void speed_row(const WarpCtx &c, const FusedArgs &A, const EnvParams &ep, int e, int j, float *dst) {
-    const float yv = c.ys_g[min(max(c.grow0 + j, 0), c.ny_global - 1)];
+template <bool GENERAL>
+__device__ __forceinline__ void speed_row(const WarpCtx &c, const FusedArgs &A, int e, int j, int dst) {
+    using C = Cfg<GENERAL>;
+    const float yv = A.gp.y[min(max(A.gp.grow0 + j, 0), A.gp.ny_global - 1)];
 #pragma unroll 1
     for (int tau = 0; tau < 3; ++tau) {
         float b;
@@ -183,7 +189,7 @@ __device__ __forceinline__ void speed_row(const WarpCtx &c, const FusedArgs &A, 
             float cd = 0.0f;
 #pragma unroll 1
             for (int a = 0; a < c.nact; ++a) {
-                const float4 p = *reinterpret_cast<const float4 *>(c.cyl + (a * 3 + tau) * 4);  // px, py, r^2, c
+                const float4 p = *reinterpret_cast<const float4 *>(&smf[c.wb + C::CYL_OFF + (a * 3 + tau) * 4]);  // px, py, r^2, c
                 float dy = __fsub_rn(yv, p.y);
                 float dy2 = __fmul_rn(dy, dy);
                 if (dy2 >= p.z) continue;  // warp-uniform: the row misses this cylinder
@@ -196,27 +202,10 @@ __device__ __forceinline__ void speed_row(const WarpCtx &c, const FusedArgs &A, 
             float cv = __fadd_rn(cnt == 0 ? A.gp.c0 : 0.0f, cd);
             b = __fmul_rn(cv, cv);
         } else {
-            const float t = A.table[((size_t)e * A.steps + A.step) * STAGE_ROW + tau];
-            const size_t o = (size_t)e * A.cyl_cap * 4;
-            b = speed2_slow(c.xs, yv, A.cyl0 + o, A.cyl1 + o, ep.ncyl, ep.ti, ep.tf, t, A.gp.c0);
+            b = speed2_slow(A, e, tau, c.xs, yv);
         }
-        dst[tau * 32] = b;
+        smf[dst + tau * 32] = b * A.kd;
     }
-}
-
-// d/dx across lanes: central (src/operators.jl:5) or the one-sided border rows (:3-4) on the domain's edge columns
-template <bool GENERAL>
-__device__ __forceinline__ float ddx(const WarpCtx &c, const GridP &gp, float v) {
-    float e1 = __shfl_down_sync(0xffffffffu, v, 1), w1 = __shfl_up_sync(0xffffffffu, v, 1);
-    float d = c.kd * (e1 - w1);
-    if (GENERAL) {
-        if (c.xb) {
-            float e2 = __shfl_down_sync(0xffffffffu, v, 2), w2 = __shfl_up_sync(0xffffffffu, v, 2);
-            if (c.is_first_col) d = ((gp.g_first[0] * v) + (gp.g_first[1] * e1)) + (gp.g_first[2] * e2);
-            if (c.is_last_col) d = ((gp.g_last[0] * w2) + (gp.g_last[1] * w1)) + (gp.g_last[2] * v);
-        }
-    }
-    return d;
 }
 
 // Register state of one warp: rotating windows indexed [stage][wavefield][row & 3]
@@ -226,251 +215,245 @@ struct Regs {
     float Uf[4][NW][4];  // U + f of stage state y_s (s = 0: the loaded row)
     float Vy[4][NW][4];
     float Vx[4][NW][4];  // s = 1..3
-    float aU[NW][4], aVx[NW][4], aVy[NW][4];  // k1 + 2k2 + 2k3 accumulators
+    float aU[NW][4], aVx[NW][4], aVy[NW][4];  // k1 + 2k2 + 2k3 accumulators (aVx, aVy: un-scaled differences)
     // GENERAL only
     float Uc[4][NW][4], Px[4][NW][4], Py[4][NW][4], Om[4][NW][4];
     float aPx[NW][4], aPy[NW][4], aOm[NW][4];
     float e_tot, e_inc, e_sc;
 };
 
-// Border-row state kept in shared memory (general variant, per warp): index = field * 32 + lane
-enum { B_VX = 0, B_UC, B_PX, B_PY, B_OM, B_AU, B_AVX, B_AVY, B_APX, B_APY, B_AOM };
+// Border-row state kept in shared memory (general variant, per warp): row index * 32 + lane
+enum { B_VX = 0, B_UC, B_PX, B_PY, B_OM, B_AU, B_AVX, B_AVY, B_APX, B_APY, B_AOM, B_F0 = 12, B_F1, B_F2, B_V0, B_V1, B_V2 };
 
-// Arguments of border_row_stage, built at the (rare) call site so the hot path's state stays in registers.
-struct BorderArgs {
-    const float *ur;   // ring row of the border row (+ lane)
-    float *bs;         // border-row state (+ lane)
-    float *out;        // output address of field 0 at (border row, this column); nullptr: do not store
-    unsigned plane;
-    float sx, sy, kd, dt, a, b, shv, sf_next;
-    float g0, g1, g2;  // one-sided stencil row (src/operators.jl:3-4)
-    float f0, f1, f2, v0, v1, v2;
-    int S;
-    bool top, xb, first_col, last_col;
-    float gf0, gf1, gf2, gl0, gl1, gl2;  // x-direction one-sided rows
-};
-
-__device__ __forceinline__ float ddx_b(const BorderArgs &B, float v) {
-    float e1 = __shfl_down_sync(0xffffffffu, v, 1), w1 = __shfl_up_sync(0xffffffffu, v, 1);
-    float e2 = __shfl_down_sync(0xffffffffu, v, 2), w2 = __shfl_up_sync(0xffffffffu, v, 2);
-    float d = B.kd * (e1 - w1);
-    if (B.first_col) d = ((B.gf0 * v) + (B.gf1 * e1)) + (B.gf2 * e2);
-    if (B.last_col) d = ((B.gl0 * w2) + (B.gl1 * w1)) + (B.gl2 * v);
-    return d;
-}
-
-// One RK stage on a domain-border row (global row 0 or ny-1) of this warp's wavefield.  f0..f2 / v0..v2 hold
-// U+f and Vy of the previous stage state on the three rows the one-sided stencil spans (ascending rows);
-// the border row is the first for TOP and the last for BOT.  Returns the new Uf / Vy of the border row.
-__device__ __noinline__ float2 border_row_stage(const BorderArgs B) {
-    const float *ur = B.ur;
-    float *bs = B.bs;
-    const int S = B.S;
-    const float uU = ur[0], uVx = ur[32], uVy = ur[64], uPx = ur[96], uPy = ur[128], uOm = ur[160];
-    const float ufC = B.top ? B.f0 : B.f2, vyC = B.top ? B.v0 : B.v2;
-    const float vxC = (S == 1) ? uVx : bs[B_VX * 32];
-    const float uC = (S == 1) ? uU : bs[B_UC * 32];
-    const float Ux = ddx_b(B, ufC);
-    const float Vxx = ddx_b(B, vxC);
-    const float Uy = ((B.g0 * B.f0) + (B.g1 * B.f1)) + (B.g2 * B.f2);
-    const float Vyy = ((B.g0 * B.v0) + (B.g1 * B.v1)) + (B.g2 * B.v2);
+// One RK stage on a domain-border row (global row 0 or ny-1) of this warp's wavefield.  The caller left
+// U+f and Vy of the previous stage state on the three rows the one-sided stencil spans (ascending rows)
+// in the border scratch B_F0..B_V2; everything else is re-derived here (rare path, kept out of line and
+// out of the hot path's registers).  Returns the new (Uf, Vy) of the border row.
+__device__ __noinline__ float2 border_row_stage(const FusedArgs &A, int e, int it, int w0, int S, bool top, int nact) {
+    using C = Cfg<true>;
+    const GridP &gp = A.gp;
+    const int lane = threadIdx.x & 31, wb = (threadIdx.x >> 5) * C::WARP_F;
+    const Item item = A.items[it];
+    const int jb = top ? item.la : item.lb - 1;
+    const int col = item.x0 + lane;
+    const int uri = wb + ((jb - item.la) & (RING - 1)) * C::SLOT_F + lane;
+    const int bsi = wb + C::RING_F + lane;
+    const float *g = top ? gp.g_first : gp.g_last;
+    const float kd = gp.g_central[1];
+    const float sx = gp.sigma[min(col, gp.nx - 1)], sy = gp.sigma[gp.grow0 + jb];
+    const float a = (S == 3) ? gp.dt : gp.hdt;
+    const int tau = (S == 1) ? 0 : (S == 4 ? 2 : 1);
+    const float *trow = A.table + ((size_t)e * A.steps + A.step) * STAGE_ROW;
+    const float sf_next = (S == 1 || S == 2) ? trow[4] : trow[5];
+    const float shv = smf[uri + C::F_SHV * 32];
+    const float b = (w0 == 0 && nact != 0) ? smf[uri + (C::F_BK + tau) * 32] / kd : gp.b0;
+    const float uU = smf[uri], uVx = smf[uri + 32], uVy = smf[uri + 64], uPx = smf[uri + 96], uPy = smf[uri + 128], uOm = smf[uri + 160];
+    const float f0 = smf[bsi + B_F0 * 32], f1 = smf[bsi + B_F1 * 32], f2 = smf[bsi + B_F2 * 32];
+    const float v0 = smf[bsi + B_V0 * 32], v1 = smf[bsi + B_V1 * 32], v2 = smf[bsi + B_V2 * 32];
+    const float ufC = top ? f0 : f2, vyC = top ? v0 : v2;
+    const float vxC = (S == 1) ? uVx : smf[bsi + B_VX * 32];
+    const float uC = (S == 1) ? uU : smf[bsi + B_UC * 32];
+    auto ddx = [&](float v) {
+        float e1 = __shfl_down_sync(0xffffffffu, v, 1), w1 = __shfl_up_sync(0xffffffffu, v, 1);
+        float e2 = __shfl_down_sync(0xffffffffu, v, 2), w2 = __shfl_up_sync(0xffffffffu, v, 2);
+        float d = kd * (e1 - w1);
+        if (col == 0) d = ((gp.g_first[0] * v) + (gp.g_first[1] * e1)) + (gp.g_first[2] * e2);
+        if (col == gp.nx - 1) d = ((gp.g_last[0] * w2) + (gp.g_last[1] * w1)) + (gp.g_last[2] * v);
+        return d;
+    };
+    const float Ux = ddx(ufC), Vxx = ddx(vxC);
+    const float Uy = ((g[0] * f0) + (g[1] * f1)) + (g[2] * f2);
+    const float Vyy = ((g[0] * v0) + (g[1] * v1)) + (g[2] * v2);
     // bc == 0 on a border row (src/dims.jl:117-124): dU = 0
     const float kU = 0.0f;
-    const float kVx = Ux - B.sx * vxC;
-    const float kVy = Uy - B.sy * vyC;
-    const float kPx = (B.b * B.sx) * Vyy;
-    const float kPy = (B.b * B.sy) * Vxx;
-    const float kOm = (B.sx * B.sy) * uC;
+    const float kVx = Ux - sx * vxC, kVy = Uy - sy * vyC;
+    const float kPx = (b * sx) * Vyy, kPy = (b * sy) * Vxx, kOm = (sx * sy) * uC;
     float2 ret = make_float2(0.f, 0.f);
     if (S < 4) {
-        const float Us = uU + B.a * kU;
-        ret.x = Us + B.shv * B.sf_next;
-        ret.y = uVy + B.a * kVy;
-        bs[B_VX * 32] = uVx + B.a * kVx;
-        bs[B_UC * 32] = Us;
-        bs[B_PX * 32] = uPx + B.a * kPx;
-        bs[B_PY * 32] = uPy + B.a * kPy;
-        bs[B_OM * 32] = uOm + B.a * kOm;
+        const float Us = uU + a * kU;
+        ret.x = Us + shv * sf_next;
+        ret.y = uVy + a * kVy;
+        smf[bsi + B_VX * 32] = uVx + a * kVx;
+        smf[bsi + B_UC * 32] = Us;
+        smf[bsi + B_PX * 32] = uPx + a * kPx;
+        smf[bsi + B_PY * 32] = uPy + a * kPy;
+        smf[bsi + B_OM * 32] = uOm + a * kOm;
         const float m = (S == 1) ? 0.0f : 1.0f, w = (S == 1) ? 1.0f : 2.0f;
-        bs[B_AU * 32] = m * bs[B_AU * 32] + w * kU;
-        bs[B_AVX * 32] = m * bs[B_AVX * 32] + w * kVx;
-        bs[B_AVY * 32] = m * bs[B_AVY * 32] + w * kVy;
-        bs[B_APX * 32] = m * bs[B_APX * 32] + w * kPx;
-        bs[B_APY * 32] = m * bs[B_APY * 32] + w * kPy;
-        bs[B_AOM * 32] = m * bs[B_AOM * 32] + w * kOm;
-    } else if (B.out) {
+        smf[bsi + B_AU * 32] = m * smf[bsi + B_AU * 32] + w * kU;
+        smf[bsi + B_AVX * 32] = m * smf[bsi + B_AVX * 32] + w * kVx;
+        smf[bsi + B_AVY * 32] = m * smf[bsi + B_AVY * 32] + w * kVy;
+        smf[bsi + B_APX * 32] = m * smf[bsi + B_APX * 32] + w * kPx;
+        smf[bsi + B_APY * 32] = m * smf[bsi + B_APY * 32] + w * kPy;
+        smf[bsi + B_AOM * 32] = m * smf[bsi + B_AOM * 32] + w * kOm;
+    } else if (lane >= item.vlo && lane < item.vhi && jb >= item.j0 && jb < item.j1) {
         const float sixth = 1.0f / 6.0f;
-        float *o = B.out;
-        o[0] = uU + (sixth * (bs[B_AU * 32] + kU)) * B.dt;
-        o[B.plane] = uVx + (sixth * (bs[B_AVX * 32] + kVx)) * B.dt;
-        o[2 * (size_t)B.plane] = uVy + (sixth * (bs[B_AVY * 32] + kVy)) * B.dt;
-        o[3 * (size_t)B.plane] = uPx + (sixth * (bs[B_APX * 32] + kPx)) * B.dt;
-        o[4 * (size_t)B.plane] = uPy + (sixth * (bs[B_APY * 32] + kPy)) * B.dt;
-        o[5 * (size_t)B.plane] = uOm + (sixth * (bs[B_AOM * 32] + kOm)) * B.dt;
+        float *o = A.out + (long long)e * gp.env_stride + (long long)w0 * 6 * gp.plane + (long long)jb * gp.nxp + col;
+        o[0] = uU + (sixth * (smf[bsi + B_AU * 32] + kU)) * gp.dt;
+        o[gp.plane] = uVx + (sixth * (smf[bsi + B_AVX * 32] + kVx)) * gp.dt;
+        o[2 * gp.plane] = uVy + (sixth * (smf[bsi + B_AVY * 32] + kVy)) * gp.dt;
+        o[3 * gp.plane] = uPx + (sixth * (smf[bsi + B_APX * 32] + kPx)) * gp.dt;
+        o[4 * gp.plane] = uPy + (sixth * (smf[bsi + B_APY * 32] + kPy)) * gp.dt;
+        o[5 * gp.plane] = uOm + (sixth * (smf[bsi + B_AOM * 32] + kOm)) * gp.dt;
     }
     __syncwarp();
     return ret;
 }
 
-// One RK stage S (1..4) on row j = r - S.  PH = r & 3.  Runs unguarded on every row: rows whose inputs are
-// not loaded yet (warm-up / drain) produce values that no stored cell depends on, and stores are predicated.
+// One RK stage S (1..4) on row j = r - S.  PH = r & 3.  Rows whose inputs are not loaded yet (warm-up)
+// produce values that no stored cell depends on, and stores are predicated.
+// Derivatives are kept un-scaled (differences); the 1/(2Δ) factor is folded into the coefficients.
 template <bool GENERAL, int S, int PH>
-__device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, int e, Regs<GENERAL> &R, int j) {
+__device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, int e, int it, Regs<GENERAL> &R, int j) {
     using C = Cfg<GENERAL>;
-    const GridP &gp = A.gp;
     constexpr int sc = (PH - S + 8) & 3, sm = (sc + 3) & 3, sp = (sc + 1) & 3;  // slots of rows j, j-1, j+1
-    const float *ur = c.ring + ((j - c.la) & (RING - 1)) * C::SLOT_F + c.lane;
-    const float a = (S == 3) ? c.dt : c.hdt;
+    const int uri = c.wb + ((j - c.la) & (RING - 1)) * C::SLOT_F + c.lane;
+    const float a = (S == 3) ? A.dt : A.hdt;
+    const float akd = (S == 3) ? A.akd_f : A.akd_h;
     constexpr int tau = (S == 1) ? 0 : (S == 4 ? 2 : 1);
-    const float sy = GENERAL ? c.sig_g[min(max(c.grow0 + j, 0), c.ny_global - 1)] : 0.0f;
-    const float sx = c.sx;
-    const float shv = (S < 4 && src_row(c, j)) ? ur[C::F_SH * 32] : 0.0f;
+    const float shv = (S < 4) ? smf[uri + C::F_SHV * 32] : 0.0f;
     const float sf_next = (S == 1 || S == 2) ? c.sf[1] : c.sf[2];
-    const float btot = (c.nact != 0) ? ur[(C::F_B + tau) * 32] : c.b0;
-    const bool st = (unsigned)(j - c.js0) < c.jsn;  // this lane stores row j
+    const float bk_tot = smf[uri + (C::F_BK + tau) * 32];  // kd * c^2 (written on arrival)
+    const bool st = (unsigned)(j - c.js0) < c.jsn;         // this lane stores row j
     float outU[C::NW];
+    if (!GENERAL) {
 #pragma unroll
-    for (int w = 0; w < C::NW; ++w) {
-        const float *uw = ur + w * 6 * 32;
-        const float uU = uw[0], uVx = uw[32], uVy = uw[64];
-        const bool tot = GENERAL ? c.is_tot : (w == 0);
-        const float b = tot ? btot : c.b0;
-        const float ufC = R.Uf[S - 1][w][sc];
-        const float vxC = (S == 1) ? uVx : R.Vx[S - 1][w][sc];
-        const float Ux = ddx<GENERAL>(c, gp, ufC);
-        const float Vxx = ddx<GENERAL>(c, gp, vxC);
-        const float Uy = c.kd * (R.Uf[S - 1][w][sp] - R.Uf[S - 1][w][sm]);
-        const float Vyy = c.kd * (R.Vy[S - 1][w][sp] - R.Vy[S - 1][w][sm]);
-        float kU, kVx, kVy, kPx = 0.f, kPy = 0.f, kOm = 0.f;
-        float uPx = 0.f, uPy = 0.f, uOm = 0.f;
-        if (GENERAL) {
-            uPx = uw[96];
-            uPy = uw[128];
-            uOm = uw[160];
-            const float vyC = R.Vy[S - 1][w][sc];
-            const float uC = (S == 1) ? uU : R.Uc[S - 1][w][sc];
-            const float px = (S == 1) ? uPx : R.Px[S - 1][w][sc];
-            const float py = (S == 1) ? uPy : R.Py[S - 1][w][sc];
-            const float om = (S == 1) ? uOm : R.Om[S - 1][w][sc];
-            kU = c.bcm * (((((b * (Vxx + Vyy)) + px) + py) - ((sx + sy) * uC)) - om);
-            kVx = Ux - sx * vxC;
-            kVy = Uy - sy * vyC;
-            kPx = (b * sx) * Vyy;
-            kPy = (b * sy) * Vxx;
-            kOm = (sx * sy) * uC;
-        } else {
+        for (int w = 0; w < C::NW; ++w) {
+            const int uw = uri + w * 6 * 32;
+            const float uU = smf[uw], uVx = smf[uw + 32], uVy = smf[uw + 64];
+            const float bk = (w == 0) ? bk_tot : A.b0kd;
+            const float ufC = R.Uf[S - 1][w][sc];
+            const float vxC = (S == 1) ? uVx : R.Vx[S - 1][w][sc];
+            const float dUx = __shfl_down_sync(0xffffffffu, ufC, 1) - __shfl_up_sync(0xffffffffu, ufC, 1);
+            const float dVx = __shfl_down_sync(0xffffffffu, vxC, 1) - __shfl_up_sync(0xffffffffu, vxC, 1);
+            const float dUy = R.Uf[S - 1][w][sp] - R.Uf[S - 1][w][sm];
+            const float dVy = R.Vy[S - 1][w][sp] - R.Vy[S - 1][w][sm];
             // sigma == 0 in the whole window: Psi, Omega never change within the step; P was formed on arrival
-            kU = (b * (Vxx + Vyy)) + ur[(C::F_P + w) * 32];
-            kVx = Ux;
-            kVy = Uy;
-        }
-        if (S < 4) {
-            const float Us = uU + a * kU;
-            R.Uf[S][w][sc] = Us + shv * sf_next;
-            R.Vx[S][w][sc] = uVx + a * kVx;
-            R.Vy[S][w][sc] = uVy + a * kVy;
-            if (GENERAL) {
-                R.Uc[S][w][sc] = Us;
-                R.Px[S][w][sc] = uPx + a * kPx;
-                R.Py[S][w][sc] = uPy + a * kPy;
-                R.Om[S][w][sc] = uOm + a * kOm;
-            }
-            if (S == 1) {
-                R.aU[w][sc] = kU;
-                R.aVx[w][sc] = kVx;
-                R.aVy[w][sc] = kVy;
-                if (GENERAL) {
-                    R.aPx[w][sc] = kPx;
-                    R.aPy[w][sc] = kPy;
-                    R.aOm[w][sc] = kOm;
+            const float kU = bk * (dVx + dVy) + smf[uri + (C::F_P + w) * 32];
+            if (S < 4) {
+                const float Us = uU + a * kU;
+                R.Uf[S][w][sc] = Us + shv * sf_next;
+                R.Vx[S][w][sc] = uVx + akd * dUx;
+                R.Vy[S][w][sc] = uVy + akd * dUy;
+                if (S == 1) {
+                    R.aU[w][sc] = kU;
+                    R.aVx[w][sc] = dUx;
+                    R.aVy[w][sc] = dUy;
+                } else {
+                    R.aU[w][sc] += 2.0f * kU;
+                    R.aVx[w][sc] += 2.0f * dUx;
+                    R.aVy[w][sc] += 2.0f * dUy;
                 }
             } else {
-                R.aU[w][sc] += 2.0f * kU;
-                R.aVx[w][sc] += 2.0f * kVx;
-                R.aVy[w][sc] += 2.0f * kVy;
-                if (GENERAL) {
-                    R.aPx[w][sc] += 2.0f * kPx;
-                    R.aPy[w][sc] += 2.0f * kPy;
-                    R.aOm[w][sc] += 2.0f * kOm;
-                }
-            }
-        } else {
-            const float sixth = 1.0f / 6.0f;
-            const float oU = uU + (sixth * (R.aU[w][sc] + kU)) * c.dt;
-            const float oVx = uVx + (sixth * (R.aVx[w][sc] + kVx)) * c.dt;
-            const float oVy = uVy + (sixth * (R.aVy[w][sc] + kVy)) * c.dt;
-            outU[w] = oU;
-            if (st) {
-                float *o = c.out_e + (unsigned)(w * 6) * c.plane + (unsigned)j * c.nxp;
-                o[0] = oU;
-                o[c.plane] = oVx;
-                o[2u * c.plane] = oVy;
-                if (GENERAL) {  // interior: Psi/Omega were passed through on arrival
-                    o[3u * c.plane] = uPx + (sixth * (R.aPx[w][sc] + kPx)) * c.dt;
-                    o[4u * c.plane] = uPy + (sixth * (R.aPy[w][sc] + kPy)) * c.dt;
-                    o[5u * c.plane] = uOm + (sixth * (R.aOm[w][sc] + kOm)) * c.dt;
+                const float oU = uU + A.dt6 * (R.aU[w][sc] + kU);
+                outU[w] = oU;
+                if (st) {
+                    float *o = c.out_e + (unsigned)(w * 6) * A.plane + (unsigned)j * A.nxp;
+                    o[0] = oU;
+                    o[A.plane] = uVx + A.dt6kd * (R.aVx[w][sc] + dUx);
+                    o[2u * A.plane] = uVy + A.dt6kd * (R.aVy[w][sc] + dUy);
                 }
             }
         }
-    }
-    if (!GENERAL && S == 4 && st) {
-        const float d = outU[0] - outU[C::NW - 1];
-        R.e_tot += outU[0] * outU[0];
-        R.e_inc += outU[C::NW - 1] * outU[C::NW - 1];
-        R.e_sc += d * d;
-    }
-    if (GENERAL) {
+        if (S == 4 && st) {
+            const float d = outU[0] - outU[C::NW - 1];
+            R.e_tot += outU[0] * outU[0];
+            R.e_inc += outU[C::NW - 1] * outU[C::NW - 1];
+            R.e_sc += d * d;
+        }
+    } else {
+        const GridP &gp = A.gp;
+        const float sy = gp.sigma[min(max(A.gp.grow0 + j, 0), A.gp.ny_global - 1)];
+        const float sx = c.sx;
+        const float uU = smf[uri], uVx = smf[uri + 32], uVy = smf[uri + 64], uPx = smf[uri + 96], uPy = smf[uri + 128], uOm = smf[uri + 160];
+        const float bk = c.is_tot ? bk_tot : A.b0kd;
+        const float ufC = R.Uf[S - 1][0][sc];
+        const float vxC = (S == 1) ? uVx : R.Vx[S - 1][0][sc];
+        const float vyC = R.Vy[S - 1][0][sc];
+        const float uC = (S == 1) ? uU : R.Uc[S - 1][0][sc];
+        const float px = (S == 1) ? uPx : R.Px[S - 1][0][sc];
+        const float py = (S == 1) ? uPy : R.Py[S - 1][0][sc];
+        const float om = (S == 1) ? uOm : R.Om[S - 1][0][sc];
+        // un-scaled x-differences (one-sided 3-point rows on the domain's edge columns, pre-divided by kd)
+        float e1 = __shfl_down_sync(0xffffffffu, ufC, 1), w1 = __shfl_up_sync(0xffffffffu, ufC, 1);
+        float dUx = e1 - w1;
+        float e1v = __shfl_down_sync(0xffffffffu, vxC, 1), w1v = __shfl_up_sync(0xffffffffu, vxC, 1);
+        float dVx = e1v - w1v;
+        if (c.xb) {
+            const float e2 = __shfl_down_sync(0xffffffffu, ufC, 2), w2 = __shfl_up_sync(0xffffffffu, ufC, 2);
+            const float e2v = __shfl_down_sync(0xffffffffu, vxC, 2), w2v = __shfl_up_sync(0xffffffffu, vxC, 2);
+            const float ik = 1.0f / A.kd;
+            if (c.is_first_col) {
+                dUx = (((gp.g_first[0] * ufC) + (gp.g_first[1] * e1)) + (gp.g_first[2] * e2)) * ik;
+                dVx = (((gp.g_first[0] * vxC) + (gp.g_first[1] * e1v)) + (gp.g_first[2] * e2v)) * ik;
+            }
+            if (c.is_last_col) {
+                dUx = (((gp.g_last[0] * w2) + (gp.g_last[1] * w1)) + (gp.g_last[2] * ufC)) * ik;
+                dVx = (((gp.g_last[0] * w2v) + (gp.g_last[1] * w1v)) + (gp.g_last[2] * vxC)) * ik;
+            }
+        }
+        const float dUy = R.Uf[S - 1][0][sp] - R.Uf[S - 1][0][sm];
+        const float dVy = R.Vy[S - 1][0][sp] - R.Vy[S - 1][0][sm];
+        const float kU = c.bcm * ((((bk * (dVx + dVy) + px) + py) - (sx + sy) * uC) - om);
+        const float kVx = A.kd * dUx - sx * vxC;
+        const float kVy = A.kd * dUy - sy * vyC;
+        const float kPx = (bk * sx) * dVy;
+        const float kPy = (bk * sy) * dVx;
+        const float kOm = (sx * sy) * uC;
+        if (S < 4) {
+            const float Us = uU + a * kU;
+            R.Uf[S][0][sc] = Us + shv * sf_next;
+            R.Vx[S][0][sc] = uVx + a * kVx;
+            R.Vy[S][0][sc] = uVy + a * kVy;
+            R.Uc[S][0][sc] = Us;
+            R.Px[S][0][sc] = uPx + a * kPx;
+            R.Py[S][0][sc] = uPy + a * kPy;
+            R.Om[S][0][sc] = uOm + a * kOm;
+            if (S == 1) {
+                R.aU[0][sc] = kU;
+                R.aVx[0][sc] = kVx;
+                R.aVy[0][sc] = kVy;
+                R.aPx[0][sc] = kPx;
+                R.aPy[0][sc] = kPy;
+                R.aOm[0][sc] = kOm;
+            } else {
+                R.aU[0][sc] += 2.0f * kU;
+                R.aVx[0][sc] += 2.0f * kVx;
+                R.aVy[0][sc] += 2.0f * kVy;
+                R.aPx[0][sc] += 2.0f * kPx;
+                R.aPy[0][sc] += 2.0f * kPy;
+                R.aOm[0][sc] += 2.0f * kOm;
+            }
+        } else if (st) {
+            float *o = c.out_e + (unsigned)j * A.nxp;
+            o[0] = uU + A.dt6 * (R.aU[0][sc] + kU);
+            o[A.plane] = uVx + A.dt6 * (R.aVx[0][sc] + kVx);
+            o[2u * A.plane] = uVy + A.dt6 * (R.aVy[0][sc] + kVy);
+            o[3u * A.plane] = uPx + A.dt6 * (R.aPx[0][sc] + kPx);
+            o[4u * A.plane] = uPy + A.dt6 * (R.aPy[0][sc] + kPy);
+            o[5u * A.plane] = uOm + A.dt6 * (R.aOm[0][sc] + kOm);
+        }
         // domain-border rows ride along with their inward neighbour (see file header)
         const bool do_top = c.top && j == c.la + 1, do_bot = c.bot && j == c.lb - 2;
         if (do_top || do_bot) {
-            BorderArgs B;
-            B.f0 = R.Uf[S - 1][0][sm];
-            B.f1 = R.Uf[S - 1][0][sc];
-            B.f2 = R.Uf[S - 1][0][sp];
-            B.v0 = R.Vy[S - 1][0][sm];
-            B.v1 = R.Vy[S - 1][0][sc];
-            B.v2 = R.Vy[S - 1][0][sp];
-            B.bs = c.bset + c.lane;
-            B.plane = c.plane;
-            B.sx = sx;
-            B.kd = c.kd;
-            B.dt = c.dt;
-            B.a = a;
-            B.sf_next = sf_next;
-            B.S = S;
-            B.xb = c.xb;
-            B.first_col = c.is_first_col;
-            B.last_col = c.is_last_col;
-            B.gf0 = gp.g_first[0];
-            B.gf1 = gp.g_first[1];
-            B.gf2 = gp.g_first[2];
-            B.gl0 = gp.g_last[0];
-            B.gl1 = gp.g_last[1];
-            B.gl2 = gp.g_last[2];
-#pragma unroll 1
-            for (int side = 0; side < 2; ++side) {
-                const bool top = side == 0;
-                if (top ? !do_top : !do_bot) continue;
-                const int jb = top ? c.la : c.lb - 1;
-                const float *ub = c.ring + ((jb - c.la) & (RING - 1)) * C::SLOT_F + c.lane;
-                B.ur = ub;
-                B.top = top;
-                B.g0 = top ? gp.g_first[0] : gp.g_last[0];
-                B.g1 = top ? gp.g_first[1] : gp.g_last[1];
-                B.g2 = top ? gp.g_first[2] : gp.g_last[2];
-                B.sy = c.sig_g[c.grow0 + jb];
-                B.shv = src_row(c, jb) ? ub[C::F_SH * 32] : 0.0f;
-                B.b = (c.is_tot && c.nact != 0) ? ub[(C::F_B + tau) * 32] : c.b0;
-                B.out = ((unsigned)(jb - c.jb0) < c.jbn) ? c.out_e + (unsigned)jb * c.nxp : nullptr;
-                const float2 o = border_row_stage(B);
+            const int bsi = c.wb + C::RING_F + c.lane;
+            smf[bsi + B_F0 * 32] = R.Uf[S - 1][0][sm];
+            smf[bsi + B_F1 * 32] = R.Uf[S - 1][0][sc];
+            smf[bsi + B_F2 * 32] = R.Uf[S - 1][0][sp];
+            smf[bsi + B_V0 * 32] = R.Vy[S - 1][0][sm];
+            smf[bsi + B_V1 * 32] = R.Vy[S - 1][0][sc];
+            smf[bsi + B_V2 * 32] = R.Vy[S - 1][0][sp];
+            if (do_top) {
+                const float2 o = border_row_stage(A, e, it, c.w0, S, true, c.nact);
                 if (S < 4) {
-                    if (top) {
-                        R.Uf[S][0][sm] = o.x;
-                        R.Vy[S][0][sm] = o.y;
-                    } else {
-                        R.Uf[S][0][sp] = o.x;
-                        R.Vy[S][0][sp] = o.y;
-                    }
+                    R.Uf[S][0][sm] = o.x;
+                    R.Vy[S][0][sm] = o.y;
+                }
+            }
+            if (do_bot) {
+                const float2 o = border_row_stage(A, e, it, c.w0, S, false, c.nact);
+                if (S < 4) {
+                    R.Uf[S][0][sp] = o.x;
+                    R.Vy[S][0][sp] = o.y;
                 }
             }
         }
@@ -478,7 +461,7 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, int 
 }
 
 template <bool GENERAL, int PH>
-__device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, const EnvParams &ep, int e, Regs<GENERAL> &R, int r,
+__device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, int e, int it, Regs<GENERAL> &R, int r,
                                          const CUtensorMap *map_u, const CUtensorMap *map_sh) {
     using C = Cfg<GENERAL>;
     // 1. prefetch row r + PF into the slot that row r + PF - RING vacated (all its readers finished >= 1 step ago)
@@ -486,7 +469,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, c
     const int rp = r + PF;
     if (c.lane == 0 && rp >= c.la && rp < c.lb && !(A.dbg & 2)) {
         const int slot = (rp - c.la) & (RING - 1);
-        const uint32_t bar = c.bar0 + slot * 8, dst = smem_u32(c.ring + slot * C::SLOT_F);
+        const uint32_t bar = c.bar0 + slot * 8, dst = c.ring_sa + slot * (C::SLOT_F * 4);
         const bool s = src_row(c, rp);
         mbar_expect_tx(bar, C::NF * 128 + (s ? 128 : 0));
         tma_load_3d(dst, map_u, c.x0, rp, e * 12 + c.w0 * 6, bar);
@@ -496,46 +479,59 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, c
     if (r >= c.la && r < c.lb) {
         const int rel = r - c.la;
         if (!(A.dbg & 2)) mbar_wait(c.bar0 + (rel & (RING - 1)) * 8, (rel >> 3) & 1);
-        float *ur = c.ring + (rel & (RING - 1)) * C::SLOT_F + c.lane;
-        const float shv = src_row(c, r) ? ur[C::F_SH * 32] : 0.0f;
+        const int uri = c.wb + (rel & (RING - 1)) * C::SLOT_F + c.lane;
+        const float shv = src_row(c, r) ? smf[uri + C::F_SH * 32] : 0.0f;
+        smf[uri + C::F_SHV * 32] = shv;
         constexpr int s0 = PH & 3;
 #pragma unroll
         for (int w = 0; w < C::NW; ++w) {
-            R.Uf[0][w][s0] = ur[w * 6 * 32] + shv * c.sf[0];
-            R.Vy[0][w][s0] = ur[w * 6 * 32 + 64];
+            R.Uf[0][w][s0] = smf[uri + w * 6 * 32] + shv * c.sf[0];
+            R.Vy[0][w][s0] = smf[uri + w * 6 * 32 + 64];
         }
-        if (c.nact != 0) speed_row(c, A, ep, e, r, ur + C::F_B * 32);
+        if (c.nact != 0) {
+            speed_row<GENERAL>(c, A, e, r, uri + C::F_BK * 32);
+        } else {
+            smf[uri + C::F_BK * 32] = A.b0kd;
+            smf[uri + (C::F_BK + 1) * 32] = A.b0kd;
+            smf[uri + (C::F_BK + 2) * 32] = A.b0kd;
+        }
         if (!GENERAL) {
             const bool st = (unsigned)(r - c.js0) < c.jsn;
 #pragma unroll
             for (int w = 0; w < C::NW; ++w) {
-                const float px = ur[(w * 6 + 3) * 32], py = ur[(w * 6 + 4) * 32], om = ur[(w * 6 + 5) * 32];
-                ur[(C::F_P + w) * 32] = (px + py) - om;
+                const float px = smf[uri + (w * 6 + 3) * 32], py = smf[uri + (w * 6 + 4) * 32], om = smf[uri + (w * 6 + 5) * 32];
+                smf[uri + (C::F_P + w) * 32] = (px + py) - om;
                 if (st) {
-                    float *o = c.out_e + (unsigned)(w * 6 + 3) * c.plane + (unsigned)r * c.nxp;
+                    float *o = c.out_e + (unsigned)(w * 6 + 3) * A.plane + (unsigned)r * A.nxp;
                     o[0] = px;
-                    o[c.plane] = py;
-                    o[2u * c.plane] = om;
+                    o[A.plane] = py;
+                    o[2u * A.plane] = om;
                 }
             }
         }
     }
     if (A.dbg & 1) return;
-    // 3. the four stages, each one row behind the previous
-    // (rows below la + 1 run unguarded: whatever they compute is overwritten before any stored cell reads it;
-    //  rows above lb - 2 must not run: they would clobber the border row's window slots)
-    const int jhi = c.lb - 2;
-    if (r - 1 <= jhi) stage<GENERAL, 1, PH>(c, A, e, R, r - 1);
-    if (r - 2 <= jhi) stage<GENERAL, 2, PH>(c, A, e, R, r - 2);
-    if (r - 3 <= jhi) stage<GENERAL, 3, PH>(c, A, e, R, r - 3);
-    if (r - 4 <= jhi) stage<GENERAL, 4, PH>(c, A, e, R, r - 4);
+    // 3. the four stages, each one row behind the previous.  Rows below la + 1 run unguarded (whatever they
+    //    compute is overwritten before a stored cell reads it).  In the general variant rows above lb - 2
+    //    must not run: they would clobber the border row's window slots.
+    if (GENERAL) {
+        const int jhi = c.lb - 2;
+        if (r - 1 <= jhi) stage<GENERAL, 1, PH>(c, A, e, it, R, r - 1);
+        if (r - 2 <= jhi) stage<GENERAL, 2, PH>(c, A, e, it, R, r - 2);
+        if (r - 3 <= jhi) stage<GENERAL, 3, PH>(c, A, e, it, R, r - 3);
+        if (r - 4 <= jhi) stage<GENERAL, 4, PH>(c, A, e, it, R, r - 4);
+    } else {
+        stage<GENERAL, 1, PH>(c, A, e, it, R, r - 1);
+        stage<GENERAL, 2, PH>(c, A, e, it, R, r - 2);
+        stage<GENERAL, 3, PH>(c, A, e, it, R, r - 3);
+        stage<GENERAL, 4, PH>(c, A, e, it, R, r - 4);
+    }
 }
 
 template <bool GENERAL>
-__global__ void __launch_bounds__(WARPS * 32, 3)
+__global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
 k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_sh) {
     using C = Cfg<GENERAL>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long gw = (long long)blockIdx.x * WARPS + warp;
     const int w0 = GENERAL ? (int)(gw & 1) : 0;  // general: two warps (tot, inc) per item
@@ -546,47 +542,33 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     const Item item = A.items[it];
     const EnvParams ep = A.env[e];
 
-    float *wbase = reinterpret_cast<float *>(smem_raw + (size_t)warp * C::WARP_BYTES);
     WarpCtx c;
-    c.ring = wbase;
-    c.bset = wbase + RING * C::SLOT_F;
-    c.cyl = wbase + RING * C::SLOT_F + C::BSET_F;
-    c.bar0 = smem_u32(wbase + RING * C::SLOT_F + C::BSET_F + CYL_CAP * 12);
     c.lane = lane;
+    c.wb = warp * C::WARP_F;
+    c.ring_sa = smem_u32(&smf[c.wb]);
+    c.bar0 = smem_u32(&smf[c.wb + C::BAR_OFF]);
     c.w0 = w0;
     c.is_tot = w0 == 0;
     c.x0 = item.x0;
-    c.col = item.x0 + lane;
     c.la = item.la;
     c.lb = item.lb;
     c.top = item.top;
     c.bot = item.bot;
+    const int col = item.x0 + lane;
     const bool valid_lane = lane >= item.vlo && lane < item.vhi;
     {
         // regular stages store rows that have both y-neighbours loaded; border rows belong to border_row_stage
         const int js0 = max(item.j0, item.la + 1), js1 = min(item.j1, item.lb - 1);
         c.js0 = js0;
         c.jsn = (valid_lane && js1 > js0) ? (unsigned)(js1 - js0) : 0u;
-        c.jb0 = item.j0;
-        c.jbn = valid_lane ? (unsigned)(item.j1 - item.j0) : 0u;
     }
-    c.plane = (unsigned)gp.plane;
-    c.nxp = (unsigned)gp.nxp;
-    c.out_e = A.out + (long long)e * gp.env_stride + (long long)w0 * 6 * gp.plane + min(c.col, gp.nx - 1);
-    c.is_first_col = c.col == 0;
-    c.is_last_col = c.col == gp.nx - 1;
+    c.out_e = A.out + (long long)e * gp.env_stride + (long long)w0 * 6 * gp.plane + min(col, gp.nx - 1);
+    c.is_first_col = col == 0;
+    c.is_last_col = col == gp.nx - 1;
     c.xb = (item.x0 == 0) || (item.x0 + 32 >= gp.nx);
     c.bcm = (c.is_first_col || c.is_last_col) ? 0.0f : 1.0f;
-    c.xs = gp.x[min(c.col, gp.nx - 1)];  // lanes past the last column (nx % 4 != 0) are never valid
-    c.sx = GENERAL ? gp.sigma[min(c.col, gp.nx - 1)] : 0.0f;
-    c.kd = gp.g_central[1];
-    c.dt = gp.dt;
-    c.hdt = gp.hdt;
-    c.b0 = gp.b0;
-    c.ys_g = gp.y;
-    c.sig_g = gp.sigma;
-    c.grow0 = gp.grow0;
-    c.ny_global = gp.ny_global;
+    c.xs = gp.x[min(col, gp.nx - 1)];  // lanes past the last column (nx % 4 != 0) are never valid
+    c.sx = GENERAL ? gp.sigma[min(col, gp.nx - 1)] : 0.0f;
     const float *trow = A.table + ((size_t)e * A.steps + A.step) * STAGE_ROW;
     c.sf[0] = trow[3];
     c.sf[1] = trow[4];
@@ -640,7 +622,8 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
             if (hit && pos < CYL_CAP) {
 #pragma unroll
                 for (int tau = 0; tau < 3; ++tau)
-                    *reinterpret_cast<float4 *>(c.cyl + (pos * 3 + tau) * 4) = make_float4(P[tau][0], P[tau][1], P[tau][2], P[tau][3]);
+                    *reinterpret_cast<float4 *>(&smf[c.wb + C::CYL_OFF + (pos * 3 + tau) * 4]) =
+                        make_float4(P[tau][0], P[tau][1], P[tau][2], P[tau][3]);
             }
             n += __popc(bal);
         }
@@ -676,10 +659,10 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     const int r_begin = (c.la - PF) & ~3, r_end = c.lb + 4;  // the first PF steps only prefetch
 #pragma unroll 1
     for (int r = r_begin; r < r_end; r += 4) {
-        row_step<GENERAL, 0>(c, A, ep, e, R, r, &map_u, &map_sh);
-        row_step<GENERAL, 1>(c, A, ep, e, R, r + 1, &map_u, &map_sh);
-        row_step<GENERAL, 2>(c, A, ep, e, R, r + 2, &map_u, &map_sh);
-        row_step<GENERAL, 3>(c, A, ep, e, R, r + 3, &map_u, &map_sh);
+        row_step<GENERAL, 0>(c, A, e, it, R, r, &map_u, &map_sh);
+        row_step<GENERAL, 1>(c, A, e, it, R, r + 1, &map_u, &map_sh);
+        row_step<GENERAL, 2>(c, A, e, it, R, r + 2, &map_u, &map_sh);
+        row_step<GENERAL, 3>(c, A, e, it, R, r + 3, &map_u, &map_sh);
     }
 
     if (!GENERAL && A.epart) {
@@ -911,8 +894,8 @@ int fused_prepare(waves_handle *h) {
     cudaMalloc((void **)&p->d_epart, sizeof(float) * 3 * (size_t)(ii.size() + gg.size()) * gp.n_env);
     cudaMalloc((void **)&p->d_bb, sizeof(int) * 4);
 
-    p->smem_gen = WARPS * Cfg<true>::WARP_BYTES;
-    p->smem_int = WARPS * Cfg<false>::WARP_BYTES;
+    p->smem_gen = WARPS * Cfg<true>::WARP_F * 4;
+    p->smem_int = WARPS * Cfg<false>::WARP_F * 4;
     cudaError_t ce = cudaFuncSetAttribute(k_fused_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_gen);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_int);
     if (ce != cudaSuccess) {
@@ -979,6 +962,16 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     A.out = h->u[h->cur ^ 1];
     A.epart = d_e3 ? p->d_epart : nullptr;
     A.epart_stride = p->n_int + p->n_gen;
+    A.kd = h->gp.g_central[1];
+    A.b0kd = h->gp.b0 * A.kd;
+    A.dt = h->gp.dt;
+    A.hdt = h->gp.hdt;
+    A.dt6 = h->gp.dt * (1.0f / 6.0f);
+    A.akd_h = A.hdt * A.kd;
+    A.akd_f = A.dt * A.kd;
+    A.dt6kd = A.dt6 * A.kd;
+    A.plane = (unsigned)h->gp.plane;
+    A.nxp = (unsigned)h->gp.nxp;
     static const int dbg_flags = getenv("WAVES_DEBUG_FLAGS") ? atoi(getenv("WAVES_DEBUG_FLAGS")) : 0;
     A.dbg = dbg_flags;
     static const int dbg_skip = getenv("WAVES_DEBUG_SKIP") ? atoi(getenv("WAVES_DEBUG_SKIP")) : 0;  // developer bisecting aid
