@@ -26,6 +26,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "waves_internal.h"
@@ -40,24 +41,30 @@ constexpr int WARPS = 1;     // warps per CTA: one, so every item-derived value 
 // Per-variant layout.  The interior variant marches BOTH wavefields in one warp (it needs both for
 // the scattered energy and has registers to spare); the general variant (PML strips, domain borders)
 // carries twice the state per wavefield, so each warp takes ONE wavefield.
-// Ring slot rows (32 floats each): [0, NF) state fields written by TMA, NF: source shape written by TMA,
-// then rows written by the warp itself on arrival: F_BK..+2 = kd*c^2 at the three stage times,
-// F_SHV = source shape or 0, F_P.. = Psix+Psiy-Omega per wavefield (interior only).
+// Ring slot rows (32 floats each): [0, NF) state fields written by TMA, row NF: source shape written by TMA
+// (only for rows inside the source's bounding box).  On arrival the warp rewrites some rows IN PLACE
+// (generic-proxy writes followed by fence.proxy.async before the slot's next TMA):
+//   F_SHV (= the shape row): shape or 0;
+//   interior: Psix rows -> P = Psix+Psiy-Omega (Psi/Omega are passed through to the output on arrival),
+//             Psiy_tot, Omega_tot, Psiy_inc rows -> kd*c^2 at the three stage times;
+//   general:  three extra rows hold kd*c^2 (all six fields stay live through the four stages).
 template <bool GENERAL>
 struct Cfg {
     static constexpr int NW = GENERAL ? 1 : 2;
     static constexpr int NF = 6 * NW;
     static constexpr int F_SH = NF;
-    static constexpr int F_BK = NF + 1;
-    static constexpr int F_SHV = NF + 4;
-    static constexpr int F_P = NF + 5;
-    static constexpr int SLOT_ROWS = GENERAL ? NF + 5 : NF + 7;
+    static constexpr int F_SHV = NF;
+    static constexpr int SLOT_ROWS = GENERAL ? NF + 4 : NF + 1;
     static constexpr int SLOT_F = SLOT_ROWS * 32;
     static constexpr int BSET_F = GENERAL ? 20 * 32 : 0;  // border-row state + call scratch (general only)
     static constexpr int RING_F = RING * SLOT_F;
     static constexpr int CYL_OFF = RING_F + BSET_F;
     static constexpr int BAR_OFF = CYL_OFF + CYL_CAP * 12;
     static constexpr int WARP_F = ((BAR_OFF + RING * 2) + 31) & ~31;  // floats per warp (128-byte multiple)
+    // row holding kd*c^2 at stage-time index tau
+    __host__ __device__ static constexpr int f_bk(int tau) { return GENERAL ? NF + 1 + tau : (tau == 0 ? 4 : (tau == 1 ? 5 : 10)); }
+    // interior: row holding P of wavefield w
+    __host__ __device__ static constexpr int f_p(int w) { return w * 6 + 3; }
 };
 
 struct Item {
@@ -178,7 +185,7 @@ __device__ __noinline__ float speed2_slow(const FusedArgs &A, int e, int tau, fl
 // kd * speed(design(t), grid, c0)^2 of local row j at the three stage times -> smf[dst + tau*32]
 // (src/designs.jl:99-116: strict '<', speeds of overlapping cylinders add, ambient where none).
 template <bool GENERAL>
-__device__ __forceinline__ void speed_row(const WarpCtx &c, const FusedArgs &A, int e, int j, int dst) {
+__device__ __forceinline__ void speed_row(const WarpCtx &c, const FusedArgs &A, int e, int j, int uri) {
     using C = Cfg<GENERAL>;
     const float yv = A.gp.y[min(max(A.gp.grow0 + j, 0), A.gp.ny_global - 1)];
 #pragma unroll 1
@@ -204,7 +211,39 @@ __device__ __forceinline__ void speed_row(const WarpCtx &c, const FusedArgs &A, 
         } else {
             b = speed2_slow(A, e, tau, c.xs, yv);
         }
-        smf[dst + tau * 32] = b * A.kd;
+        smf[uri + (tau == 0 ? C::f_bk(0) : (tau == 1 ? C::f_bk(1) : C::f_bk(2))) * 32] = b * A.kd;
+    }
+}
+
+// Out-of-line copy for the general variant (keeps its instruction footprint inside the I-cache)
+__device__ __noinline__ void speed_row_general(const FusedArgs &A, int e, int it, int j, int uri, int nact) {
+    using C = Cfg<true>;
+    const int lane = threadIdx.x & 31, wb = (threadIdx.x >> 5) * C::WARP_F;
+    const int col = A.items[it].x0 + lane;
+    const float xs = A.gp.x[min(col, A.gp.nx - 1)];
+    const float yv = A.gp.y[min(max(A.gp.grow0 + j, 0), A.gp.ny_global - 1)];
+    for (int tau = 0; tau < 3; ++tau) {
+        float b;
+        if (nact > 0) {
+            int cnt = 0;
+            float cd = 0.0f;
+            for (int a = 0; a < nact; ++a) {
+                const float4 p = *reinterpret_cast<const float4 *>(&smf[wb + C::CYL_OFF + (a * 3 + tau) * 4]);
+                float dy = __fsub_rn(yv, p.y);
+                float dy2 = __fmul_rn(dy, dy);
+                if (dy2 >= p.z) continue;
+                float dx = __fsub_rn(xs, p.x);
+                float d2 = __fadd_rn(__fmul_rn(dx, dx), dy2);
+                bool m = d2 < p.z;
+                cnt += m;
+                cd = __fadd_rn(cd, m ? p.w : 0.0f);
+            }
+            float cv = __fadd_rn(cnt == 0 ? A.gp.c0 : 0.0f, cd);
+            b = __fmul_rn(cv, cv);
+        } else {
+            b = speed2_slow(A, e, tau, xs, yv);
+        }
+        smf[uri + C::f_bk(tau) * 32] = b * A.kd;
     }
 }
 
@@ -246,7 +285,7 @@ __device__ __noinline__ float2 border_row_stage(const FusedArgs &A, int e, int i
     const float *trow = A.table + ((size_t)e * A.steps + A.step) * STAGE_ROW;
     const float sf_next = (S == 1 || S == 2) ? trow[4] : trow[5];
     const float shv = smf[uri + C::F_SHV * 32];
-    const float b = (w0 == 0 && nact != 0) ? smf[uri + (C::F_BK + tau) * 32] / kd : gp.b0;
+    const float b = (w0 == 0 && nact != 0) ? smf[uri + C::f_bk(tau) * 32] / kd : gp.b0;
     const float uU = smf[uri], uVx = smf[uri + 32], uVy = smf[uri + 64], uPx = smf[uri + 96], uPy = smf[uri + 128], uOm = smf[uri + 160];
     const float f0 = smf[bsi + B_F0 * 32], f1 = smf[bsi + B_F1 * 32], f2 = smf[bsi + B_F2 * 32];
     const float v0 = smf[bsi + B_V0 * 32], v1 = smf[bsi + B_V1 * 32], v2 = smf[bsi + B_V2 * 32];
@@ -312,7 +351,7 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, int 
     constexpr int tau = (S == 1) ? 0 : (S == 4 ? 2 : 1);
     const float shv = (S < 4) ? smf[uri + C::F_SHV * 32] : 0.0f;
     const float sf_next = (S == 1 || S == 2) ? c.sf[1] : c.sf[2];
-    const float bk_tot = smf[uri + (C::F_BK + tau) * 32];  // kd * c^2 (written on arrival)
+    const float bk_tot = smf[uri + C::f_bk(tau) * 32];  // kd * c^2 (written on arrival)
     const bool st = (unsigned)(j - c.js0) < c.jsn;         // this lane stores row j
     float outU[C::NW];
     if (!GENERAL) {
@@ -328,7 +367,7 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, int 
             const float dUy = R.Uf[S - 1][w][sp] - R.Uf[S - 1][w][sm];
             const float dVy = R.Vy[S - 1][w][sp] - R.Vy[S - 1][w][sm];
             // sigma == 0 in the whole window: Psi, Omega never change within the step; P was formed on arrival
-            const float kU = bk * (dVx + dVy) + smf[uri + (C::F_P + w) * 32];
+            const float kU = bk * (dVx + dVy) + smf[uri + C::f_p(w) * 32];
             if (S < 4) {
                 const float Us = uU + a * kU;
                 R.Uf[S][w][sc] = Us + shv * sf_next;
@@ -379,16 +418,17 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, int 
         float e1v = __shfl_down_sync(0xffffffffu, vxC, 1), w1v = __shfl_up_sync(0xffffffffu, vxC, 1);
         float dVx = e1v - w1v;
         if (c.xb) {
+            // one-sided 3-point rows on the domain's edge columns (src/operators.jl:3-4); relative to 1/(2Δ) the
+            // coefficients are (-3, 4, -1) and (1, -4, 3)
             const float e2 = __shfl_down_sync(0xffffffffu, ufC, 2), w2 = __shfl_up_sync(0xffffffffu, ufC, 2);
             const float e2v = __shfl_down_sync(0xffffffffu, vxC, 2), w2v = __shfl_up_sync(0xffffffffu, vxC, 2);
-            const float ik = 1.0f / A.kd;
             if (c.is_first_col) {
-                dUx = (((gp.g_first[0] * ufC) + (gp.g_first[1] * e1)) + (gp.g_first[2] * e2)) * ik;
-                dVx = (((gp.g_first[0] * vxC) + (gp.g_first[1] * e1v)) + (gp.g_first[2] * e2v)) * ik;
+                dUx = (4.0f * e1 - 3.0f * ufC) - e2;
+                dVx = (4.0f * e1v - 3.0f * vxC) - e2v;
             }
             if (c.is_last_col) {
-                dUx = (((gp.g_last[0] * w2) + (gp.g_last[1] * w1)) + (gp.g_last[2] * ufC)) * ik;
-                dVx = (((gp.g_last[0] * w2v) + (gp.g_last[1] * w1v)) + (gp.g_last[2] * vxC)) * ik;
+                dUx = (3.0f * ufC - 4.0f * w1) + w2;
+                dVx = (3.0f * vxC - 4.0f * w1v) + w2v;
             }
         }
         const float dUy = R.Uf[S - 1][0][sp] - R.Uf[S - 1][0][sm];
@@ -488,19 +528,13 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
             R.Uf[0][w][s0] = smf[uri + w * 6 * 32] + shv * c.sf[0];
             R.Vy[0][w][s0] = smf[uri + w * 6 * 32 + 64];
         }
-        if (c.nact != 0) {
-            speed_row<GENERAL>(c, A, e, r, uri + C::F_BK * 32);
-        } else {
-            smf[uri + C::F_BK * 32] = A.b0kd;
-            smf[uri + (C::F_BK + 1) * 32] = A.b0kd;
-            smf[uri + (C::F_BK + 2) * 32] = A.b0kd;
-        }
+        float pP[C::NW];
         if (!GENERAL) {
             const bool st = (unsigned)(r - c.js0) < c.jsn;
 #pragma unroll
             for (int w = 0; w < C::NW; ++w) {
                 const float px = smf[uri + (w * 6 + 3) * 32], py = smf[uri + (w * 6 + 4) * 32], om = smf[uri + (w * 6 + 5) * 32];
-                smf[uri + (C::F_P + w) * 32] = (px + py) - om;
+                pP[w] = (px + py) - om;
                 if (st) {
                     float *o = c.out_e + (unsigned)(w * 6 + 3) * A.plane + (unsigned)r * A.nxp;
                     o[0] = px;
@@ -508,7 +542,21 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
                     o[2u * A.plane] = om;
                 }
             }
+#pragma unroll
+            for (int w = 0; w < C::NW; ++w) smf[uri + C::f_p(w) * 32] = pP[w];
         }
+        if (c.nact != 0) {
+            if (GENERAL)
+                speed_row_general(A, e, it, r, uri, c.nact);
+            else
+                speed_row<GENERAL>(c, A, e, r, uri);
+        } else {
+            smf[uri + C::f_bk(0) * 32] = A.b0kd;
+            smf[uri + C::f_bk(1) * 32] = A.b0kd;
+            smf[uri + C::f_bk(2) * 32] = A.b0kd;
+        }
+        // the rows rewritten above are TMA targets again RING rows later: order the generic writes before it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (A.dbg & 1) return;
     // 3. the four stages, each one row behind the previous.  Rows below la + 1 run unguarded (whatever they
@@ -821,6 +869,7 @@ int fused_prepare(waves_handle *h) {
         while (o < b) {
             const int x0 = o == 0 ? 0 : o - 4;
             int hi = x0 + 28;  // 24 owned columns + 4 halo (28 at the left domain edge)
+            if (x0 + 32 >= gp.nx) hi = gp.nx;  // the window reaches the right domain edge: no halo needed there
             if (hi > b) hi = b;
             cols.push_back({o, hi, x0, interior});
             o = hi;
@@ -848,7 +897,8 @@ int fused_prepare(waves_handle *h) {
     int ri0 = z0 + 4 - gp.grow0, ri1 = z1 - 4 - gp.grow0;
     if (ri0 < own0) ri0 = own0;
     if (ri1 > own1) ri1 = own1;
-    const int SEG = 64;  // rows per slab
+    // rows per slab: tall slabs amortise the 8 warm-up rows, but keep >= ~8 waves of warps in flight
+    const int SEG = std::max(48, std::min(192, (int)((long long)gp.ny_own * (long long)cols.size() * gp.n_env / 14000)));
     auto add_rows = [&](int a, int b, bool interior) {
         if (b <= a) return;
         int n = (b - a + SEG - 1) / SEG;
