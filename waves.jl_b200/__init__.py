@@ -7,6 +7,7 @@ from . import _lib
 from ._lib import WavesError, build
 from .engine import MODE_EXACT, MODE_FUSED, Engine
 from .env import AcousticDynamics, Integrator, WaveEnv
+from .parallel import HaloExchanger, SlabEngine, shard_envs, slab_rows
 from .host import (AIR, WATER, Cloak, Cylinders, DesignInterpolator, DesignSpace, NoSource, RandomPosGaussianSource,
                    Source, TwoDim, build_action_space, build_gradient, build_grid, build_normal, build_pml,
                    build_radii_design_space, build_triple_ring_design_space, build_tspan, build_wave, get_dx, get_dy,

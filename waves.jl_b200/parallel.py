@@ -1,0 +1,125 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), two partitionings.
+
+ * batches of independent environments: contiguous blocks of environments per rank, NO data-path collective;
+ * one large grid: 1-D slab decomposition along y (dim 2, the strided dimension, so every slab stays
+   x-contiguous) with a nearest-neighbour exchange of WAVES_HALO = 4 rows x 12 fields after every RK4 step
+   (one ghost row per RK stage; the fused kernel recomputes the 4-row halo instead of exchanging per stage).
+
+torch.distributed is only the transport (NCCL over NVLink on GPUs, gloo in the CPU tests); the compute is
+the CUDA library.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+HALO = 4  # WAVES_HALO in include/waves_b200.h
+
+
+def shard_envs(n_env_total: int, rank: int, world: int):
+    """Contiguous block of environment indices owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(int(n_env_total), int(world))
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+def slab_rows(ny: int, rank: int, world: int):
+    """(row0, n_rows) of the slab of a grid with `ny` rows owned by `rank`; every slab needs >= 2*HALO rows."""
+    base, rem = divmod(int(ny), int(world))
+    if base < 2 * HALO:
+        raise ValueError(f"{ny} rows over {world} ranks leaves slabs thinner than {2 * HALO} rows")
+    row0 = rank * base + min(rank, rem)
+    return row0, base + (1 if rank < rem else 0)
+
+
+class HaloExchanger:
+    """Exchanges the boundary rows of neighbouring slabs.
+
+    `pack(lo, hi)` / `unpack(lo, hi)` are the engine's halo kernels (waves_halo_pack / waves_halo_unpack);
+    `lo`/`hi` are torch tensors living wherever the transport wants them (CUDA for NCCL, CPU for gloo).
+    Rank r sends its first owned rows to r-1 (they become r-1's upper ghost rows) and its last owned rows
+    to r+1, non-periodically.
+    """
+
+    def __init__(self, rank: int, world: int, n_floats: int, device, group=None):
+        import torch
+        self.rank, self.world, self.group = rank, world, group
+        self.has_lo, self.has_hi = rank > 0, rank < world - 1
+        mk = lambda on: torch.empty(n_floats if on else 0, dtype=torch.float32, device=device)
+        self.send_lo, self.recv_lo = mk(self.has_lo), mk(self.has_lo)
+        self.send_hi, self.recv_hi = mk(self.has_hi), mk(self.has_hi)
+
+    def exchange(self, pack, unpack):
+        import torch.distributed as dist
+        pack(self.send_lo if self.has_lo else None, self.send_hi if self.has_hi else None)
+        ops = []
+        if self.has_lo:
+            ops += [dist.P2POp(dist.isend, self.send_lo, self.rank - 1, self.group),
+                    dist.P2POp(dist.irecv, self.recv_lo, self.rank - 1, self.group)]
+        if self.has_hi:
+            ops += [dist.P2POp(dist.isend, self.send_hi, self.rank + 1, self.group),
+                    dist.P2POp(dist.irecv, self.recv_hi, self.rank + 1, self.group)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        unpack(self.recv_lo if self.has_lo else None, self.recv_hi if self.has_hi else None)
+
+
+class SlabEngine:
+    """One rank's slab of a single large grid (BASELINE config 4).  Requires an initialised process group."""
+
+    def __init__(self, x, y, c0, dt, pml_width, pml_scale, device, rank=None, world=None):
+        import torch
+        import torch.distributed as dist
+
+        from .engine import Engine
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.row0, self.ny = slab_rows(len(y), self.rank, self.world)
+        self.engine = Engine(x, y, c0, dt, pml_width, pml_scale, n_env=1, device=device, ny_local=self.ny, row0=self.row0)
+        d = self.engine.halo_describe()
+        self.stream = torch.cuda.ExternalStream(self.engine.stream(), device=device)
+        self.halo = HaloExchanger(self.rank, self.world, d.n_planes * d.block_floats, torch.device("cuda", device))
+        self._torch = torch
+
+    def exchange(self):
+        with self._torch.cuda.stream(self.stream):   # NCCL ordered with the engine's own stream
+            self.halo.exchange(self.engine.halo_pack, self.engine.halo_unpack)
+
+    def set_state_global(self, u12_global):
+        """Scatter: every rank takes its rows of a (12, ny_global, nx) array, then ghost rows are exchanged."""
+        self.engine.set_state(np.ascontiguousarray(u12_global[:, self.row0:self.row0 + self.ny])[None])
+        self.exchange()
+
+    def set_source_global(self, shape_global, freq):
+        self.engine.set_source(np.ascontiguousarray(shape_global[self.row0:self.row0 + self.ny]) if shape_global is not None else None, freq)
+
+    def integrate(self, tspan, mode=0, energy=True):
+        """RK4 steps with one halo exchange per step; returns the global (steps+1, 3) energy trace (all ranks)."""
+        import torch.distributed as dist
+        torch = self._torch
+        steps = len(tspan) - 1
+        en = np.zeros((steps + 1, 3), dtype=np.float64)
+        if energy:
+            en[0] = self.engine.energy()[0]
+        for n in range(steps):
+            self.engine.step(float(tspan[n]), mode)
+            self.exchange()
+            if energy:
+                en[n + 1] = self.engine.energy()[0]
+        self.engine.sync()
+        if energy:
+            t = torch.from_numpy(en).to(f"cuda:{self.engine.device}")
+            dist.all_reduce(t)
+            en = t.cpu().numpy()
+        return en.astype(np.float32) if energy else None
+
+    def gather_state(self):
+        """All ranks receive the full (12, ny_global, nx) state (test/diagnostic helper)."""
+        import torch.distributed as dist
+        local = self.engine.get_state(0)
+        parts = [None] * self.world
+        dist.all_gather_object(parts, local)
+        return np.concatenate(parts, axis=1)
+
+    def close(self):
+        self.engine.close()
