@@ -84,7 +84,9 @@ int waves_set_state(waves_handle *h, int env, const float *u12);
 int waves_get_state(waves_handle *h, int env, float *u12);
 
 /* θ[2] = F: Source / RandomPosGaussianSource (src/sources.jl:10-23,25-69): f(t) = shape .* sin(2π t freq).
- * shape (ny, nx) plane; shape == NULL -> NoSource (src/sources.jl:7-8). */
+ * shape (ny, nx) plane; shape == NULL -> NoSource (src/sources.jl:7-8).
+ * Slab handles (ny < ny_global) pass their rows INCLUDING the WAVES_HALO ghost rows that exist on each
+ * interior side: global rows [row0 - ghosts_above, row0 + ny + ghosts_below). */
 int waves_set_source(waves_handle *h, int env, const float *shape, float freq);
 
 /* θ[1] = C: t -> speed(DesignInterpolator(initial, final, ti, tf)(t), grid, c0)
@@ -93,7 +95,8 @@ int waves_set_source(waves_handle *h, int env, const float *shape, float freq);
  * ncyl == 0 -> NoDesign: scalar c0 (src/designs.jl:63). */
 int waves_set_design(waves_handle *h, int env, int ncyl, const float *cyl0, const float *cyl1, float ti, float tf);
 
-/* θ[1] = C: t -> a fixed speed plane c (ny, nx) (generic C closure frozen in time). NULL clears it. */
+/* θ[1] = C: t -> a fixed speed plane c (ny, nx) (generic C closure frozen in time). NULL clears it.
+ * Slab handles pass ghost rows too, like waves_set_source. */
 int waves_set_speed_field(waves_handle *h, int env, const float *c);
 
 /* dyn(x, t, θ) (src/dynamics.jl:179-188) on the current state of `env`: du12 (12, ny, nx). EXACT order. */

@@ -64,6 +64,7 @@ def test_slab_decomposition_matches_single_gpu(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][-1]
     res = eval(line[len("RESULT "):])
+    print(res)
     for mode, (bitwise, maxd, erel) in res.items():
-        assert bitwise, f"mode {mode}: slab run differs from single GPU (max |d| = {maxd})"
+        assert bitwise, f"mode {mode}: slab run differs from single GPU (max |d| = {maxd}): {res}"
         assert erel < 1e-6

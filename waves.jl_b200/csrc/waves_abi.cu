@@ -295,6 +295,14 @@ static int copy_plane(waves_handle *h, float *dev_plane, const float *src, float
     return 0;
 }
 
+// copy a dense (ny_alloc, nx) block (owned + ghost rows) into one pitched field plane
+static int copy_plane_with_ghosts(waves_handle *h, float *dev_plane, const float *src) {
+    const GridP &gp = h->gp;
+    CU_TRY(cudaMemcpy2DAsync(dev_plane, sizeof(float) * gp.nxp, src, sizeof(float) * gp.nx, sizeof(float) * gp.nx, gp.ny_alloc,
+                             cudaMemcpyDefault, h->stream));
+    return 0;
+}
+
 static int copy_planes_fast(waves_handle *h, float *dev_plane, const float *src, float *dst, int planes) {
     // without ghost rows consecutive planes are consecutive rows: one 2-D copy
     const GridP &gp = h->gp;
@@ -352,7 +360,7 @@ extern "C" int waves_set_source(waves_handle *h, int env, const float *shape, fl
             ep.src_j0 = ep.src_j1 = ep.src_i0 = ep.src_i1 = 0;
         } else {
             // the same plane is broadcast to every env when env < 0
-            if (copy_plane(h, d, shape, nullptr, 1)) return 1;
+            if (copy_plane_with_ghosts(h, d, shape)) return 1;
             ep.has_source = 1;
             ep.freq = freq;
             int bb[4];
@@ -421,7 +429,7 @@ extern "C" int waves_set_speed_field(waves_handle *h, int env, const float *c) {
     }
     for (int e = e0; e < e1; ++e) {
         h->h_env[e].has_cplane = c ? 1 : 0;
-        if (c && copy_plane(h, h->cplane + (size_t)e * gp.plane, c, nullptr, 1)) return 1;
+        if (c && copy_plane_with_ghosts(h, h->cplane + (size_t)e * gp.plane, c)) return 1;
     }
     h->env_dirty = true;
     CU_TRY(cudaStreamSynchronize(h->stream));

@@ -91,7 +91,13 @@ class SlabEngine:
         self.exchange()
 
     def set_source_global(self, shape_global, freq):
-        self.engine.set_source(np.ascontiguousarray(shape_global[self.row0:self.row0 + self.ny]) if shape_global is not None else None, freq)
+        """Every rank takes its rows of the (ny_global, nx) shape INCLUDING the ghost rows of its slab."""
+        if shape_global is None:
+            self.engine.set_source(None, freq)
+            return
+        lo = self.row0 - (HALO if self.rank > 0 else 0)
+        hi = self.row0 + self.ny + (HALO if self.rank < self.world - 1 else 0)
+        self.engine.set_source(np.ascontiguousarray(shape_global[lo:hi]), freq)
 
     def integrate(self, tspan, mode=0, energy=True):
         """RK4 steps with one halo exchange per step; returns the global (steps+1, 3) energy trace (all ranks)."""
