@@ -1,0 +1,167 @@
+# WavesB200.jl -- thin `ccall` shim that puts libwaves_b200.so (include/waves_b200.h) behind the
+# reference's own call surface:
+#     (env::WaveEnv)(action)                  src/env.jl:91-121      (seam B1)
+#     (iter::Integrator)(ui, tspan, θ)        src/dynamics.jl:37-53  (seam B2)
+#
+# STATUS: UNVERIFIED.  Julia is not installed in the build image or on the GPU boxes, so this file has
+# never been executed; it is written against the C ABI that the Python ctypes mirror exercises
+# symbol for symbol (waves.jl_b200/_lib.py, tests/test_gpu_parity.py).  See INTEGRATION.md.
+#
+# Usage inside the reference repo:
+#     include("path/to/WavesB200.jl"); using .WavesB200
+#     benv = WavesB200.B200Env(env; lib = "/path/to/libwaves_b200.so", device = 0)
+#     while !is_terminated(env); benv(policy(env)); end       # instead of env(policy(env))
+module WavesB200
+
+using Waves
+using Waves: TwoDim, WaveEnv, Integrator, AcousticDynamics, DesignInterpolator, AbstractDesign, NoDesign,
+             Cylinders, Cloak, AbstractScatterers, NoSource, build_tspan, get_dx, get_dy, stack
+using SparseArrays
+
+const MODE_FUSED = Cint(0)
+const MODE_EXACT = Cint(1)
+
+# struct waves_config (include/waves_b200.h) -- field order and types must match exactly
+struct WavesConfig
+    nx::Int32; ny::Int32; n_env::Int32; device::Int32
+    c0::Float32; dt::Float32; pml_width::Float32; pml_scale::Float32
+    x::Ptr{Float32}; y::Ptr{Float32}; sigma::Ptr{Float32}; grad8::Ptr{Float32}
+    d_omega::Float32; ny_global::Int32; row0::Int32; flags::UInt32
+end
+
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    lib::String
+end
+
+function check(h_lib::String, rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:waves_last_error, h_lib), Cstring, ()))
+    error("waves_b200: " * msg)
+end
+
+# rows of dyn.grad (src/operators.jl:10-22): first(3) central(2) last(3)
+function grad8(grad::AbstractMatrix{Float32})
+    g = Matrix(grad)   # tiny: only the three distinct rows are read
+    n = size(g, 1)
+    return Float32[g[1, 1], g[1, 2], g[1, 3], g[2, 1], g[2, 3], g[n, n-2], g[n, n-1], g[n, n]]
+end
+
+"""cylinder table (ncyl, 4) rows {x, y, r, c}, row-major, of the stacked design (src/designs.jl:133-138, :228)"""
+cyl_table(c::Cylinders) = Matrix{Float32}(permutedims(hcat(c.pos, c.r, c.c)))      # 4 x ncyl column-major == (ncyl,4) row-major
+cyl_table(d::AbstractScatterers) = cyl_table(d.cylinders)
+cyl_table(d::Cloak) = cyl_table(stack(d.config.cylinders, d.core))
+
+function create(dyn::AcousticDynamics{TwoDim}, dt::Float32; lib::String, device::Integer = 0, n_env::Integer = 1)
+    dim = dyn.dim
+    x, y = Vector{Float32}(dim.x), Vector{Float32}(dim.y)
+    sigma = Vector{Float32}(dyn.pml[:, 1])
+    g8 = grad8(dyn.grad)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve x y sigma g8 begin
+        cfg = Ref(WavesConfig(length(x), length(y), n_env, device, dyn.c0, dt, 0f0, 0f0,
+                              pointer(x), pointer(y), pointer(sigma), pointer(g8),
+                              get_dx(dim) * get_dy(dim), length(y), 0, 0))
+        check(lib, ccall((:waves_create, lib), Cint, (Ref{WavesConfig}, Ref{Ptr{Cvoid}}), cfg, out))
+    end
+    h = Handle(out[], lib)
+    finalizer(h -> (h.ptr != C_NULL && ccall((:waves_destroy, h.lib), Cint, (Ptr{Cvoid},), h.ptr); h.ptr = C_NULL), h)
+    return h
+end
+
+set_state!(h::Handle, u12::Array{Float32, 3}, env::Integer = -1) =
+    check(h.lib, ccall((:waves_set_state, h.lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), h.ptr, env, u12))
+
+function get_state(h::Handle, nx, ny, env::Integer = 0)
+    u = Array{Float32}(undef, nx, ny, 12)
+    check(h.lib, ccall((:waves_get_state, h.lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), h.ptr, env, u))
+    return u
+end
+
+set_source!(h::Handle, ::NoSource, env::Integer = -1) =
+    check(h.lib, ccall((:waves_set_source, h.lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Cfloat), h.ptr, env, C_NULL, 0f0))
+set_source!(h::Handle, src, env::Integer = -1) =   # Source / RandomPosGaussianSource: fields shape, freq
+    check(h.lib, ccall((:waves_set_source, h.lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Cfloat), h.ptr, env, Array{Float32}(src.shape), src.freq))
+
+set_design!(h::Handle, ::Nothing, env::Integer = -1) =
+    check(h.lib, ccall((:waves_set_design, h.lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Cfloat, Cfloat), h.ptr, env, 0, C_NULL, C_NULL, 0f0, 0f0))
+function set_design!(h::Handle, interp::DesignInterpolator, env::Integer = -1)
+    interp.initial isa NoDesign && return set_design!(h, nothing, env)
+    a, b = cyl_table(interp.initial), cyl_table(interp.final)
+    check(h.lib, ccall((:waves_set_design, h.lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Cfloat, Cfloat),
+                       h.ptr, env, size(a, 2), a, b, interp.ti, interp.tf))
+end
+
+"""
+    integrate!(h, tspan; save_steps, frames, energy, mode)
+
+(iter::Integrator)(ui, tspan, θ) + the energy metric (src/dynamics.jl:37-53, src/env.jl:104-114) for the
+handle's environments.  Returns `(energy::Matrix{Float32} (3, steps+1), frames::Array{Float32,4} (nx,ny,12,nsave))`
+for a single-environment handle.
+"""
+function integrate!(h::Handle, tspan::Vector{Float32}, nx::Int, ny::Int; save_steps::Vector{Int32} = Int32[],
+                    mode::Cint = MODE_FUSED, u_tot = C_NULL, u_inc = C_NULL)
+    steps = length(tspan) - 1
+    energy = Array{Float32}(undef, 3, steps + 1)                  # column-major (3, steps+1) == C (steps+1, 3)
+    frames = Array{Float32}(undef, nx, ny, 12, length(save_steps))
+    check(h.lib, ccall((:waves_integrate, h.lib), Cint,
+                       (Ptr{Cvoid}, Ptr{Float32}, Cint, Cint, Ptr{Float32}, Ptr{Int32}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+                       h.ptr, tspan, steps, mode, energy, save_steps, length(save_steps), frames, u_tot, u_inc))
+    return energy, frames
+end
+
+# ---- seam B2: (iter::Integrator)(ui, tspan, θ) for the parameterised θ the environment builds -------------
+"""Drop-in for `iter(ui, tspan, [C, F])` when C is the design interpolation of `(env::WaveEnv)(action)`
+(src/env.jl:96-99): pass the DesignInterpolator (or `nothing` for a constant c0) instead of the closure."""
+function integrate(iter::Integrator, h::Handle, ui::Array{Float32, 3}, tspan::Vector{Float32}, interp, source)
+    nx, ny = size(ui, 1), size(ui, 2)
+    set_state!(h, ui)
+    set_design!(h, interp)
+    set_source!(h, source)
+    steps = length(tspan) - 1
+    _, frames = integrate!(h, tspan, nx, ny; save_steps = Int32.(0:steps))
+    return frames                                                  # (nx, ny, 12, steps+1) like cat(ui, ...; dims = 4)
+end
+
+# ---- seam B1: (env::WaveEnv)(action) ------------------------------------------------------------------------
+mutable struct B200Env
+    env::WaveEnv
+    h::Handle
+    return_frames::Bool          # also return the full u_tot/u_inc trajectories (only render! needs them)
+end
+
+function B200Env(env::WaveEnv; lib::String, device::Integer = 0, return_frames::Bool = false)
+    h = create(env.iter.dynamics, env.dt; lib = lib, device = device)
+    set_state!(h, Array{Float32}(env.wave[:, :, :, end]))
+    set_source!(h, env.source)
+    return B200Env(env, h, return_frames)
+end
+
+const FRAMESKIP = 10   # src/env.jl:90
+
+function (b::B200Env)(action::AbstractDesign)
+    env = b.env
+    tspan = build_tspan(env)                                       # src/env.jl:92
+    ti = time(env)
+    next_design = env.design_space(env.design, action)             # src/env.jl:96
+    interp = DesignInterpolator(env.design, next_design, ti, tspan[end])
+    set_design!(b.h, interp)
+    nx, ny = size(env.dim)
+    n = env.integration_steps
+    u_tot = b.return_frames ? Array{Float32}(undef, nx, ny, n + 1) : C_NULL
+    u_inc = b.return_frames ? Array{Float32}(undef, nx, ny, n + 1) : C_NULL
+    energy, frames = integrate!(b.h, tspan, nx, ny; save_steps = Int32[n - 2FRAMESKIP, n - FRAMESKIP, n], u_tot = u_tot, u_inc = u_inc)
+    env.signal = permutedims(energy)                               # (steps+1, 3)  src/env.jl:114
+    env.design = next_design
+    env.wave = frames                                              # frames 81, 91, 101  src/env.jl:116
+    env.time_step += n
+    return tspan, interp, (b.return_frames ? u_tot : nothing), (b.return_frames ? u_inc : nothing)
+end
+
+"""Call after `reset!(env)` (src/env.jl:81-88): pushes the zeroed wave and the re-drawn source to the device."""
+function sync_reset!(b::B200Env)
+    set_state!(b.h, Array{Float32}(b.env.wave[:, :, :, end]))
+    set_source!(b.h, b.env.source)
+end
+
+end # module
