@@ -2,22 +2,30 @@
 // runge_kutta step (src/dynamics.jl:9-16) -- 4 evaluations of acoustic_dynamics for the total and the
 // incident wavefield (src/dynamics.jl:151-188), the design speed field (src/designs.jl:99-116) at the
 // three distinct stage times, the Gaussian*sine source (src/sources.jl:67-69), PML and Dirichlet mask,
-// the RK4 combination, and the energy metric of the new frame (src/env.jl:104-111).
+// the RK4 combination, and the energy metric (src/env.jl:104-111) of the frame it reads.
 //
 // Design:
-//  * work item = one WARP = a strip of 32 columns marched along y through a slab of rows;
-//    lane <-> column, so d/dy neighbours live in the lane's own registers and d/dx neighbours come
-//    from warp shuffles.  No block-level synchronisation exists in the kernel.
+//  * work item = one WARP = a strip of 64 columns of ONE wavefield marched along y through a slab of
+//    rows; lane <-> a PAIR of adjacent columns held as float2, so the arithmetic is packed f32x2
+//    (FFMA2/FADD2/FMUL2: one issue slot per two cells), shared memory is read with LDS.64, global
+//    memory written with STG.64, d/dy neighbours live in the lane's own registers and d/dx needs ONE
+//    shuffle per column pair and direction.  No block-level synchronisation exists in the kernel.
 //  * temporal blocking: the 4 RK stages are software-pipelined along y (stage s works one row behind
 //    stage s-1), so a row of state is read from HBM once and written once per step (96 B/cell-update).
-//    The 4-column / 4-row halo per side is recomputed redundantly (24 valid of 32 lanes).
-//  * rows are fetched by TMA (cp.async.bulk.tensor.3d, box 32 x 1 x 12 fields) into a per-warp
-//    shared-memory ring, two rows ahead, completion tracked by mbarriers; out-of-range columns/rows
-//    are zero-filled by the TMA unit.
+//    The 4-column / 4-row halo per side is recomputed redundantly (56 owned of 64 columns).
+//  * rows are fetched by TMA (cp.async.bulk.tensor.3d, box 64 x 1 x 7|6 field planes) into a per-warp
+//    shared-memory ring, PF rows ahead, completion tracked by mbarriers; out-of-range columns/rows
+//    are zero-filled by the TMA unit.  The warp of the total field also receives the U plane of the
+//    incident field (7th plane of its box) and accumulates the three energies of the rows it owns.
 //  * rotating register windows are indexed by (row & 3) with the row loop unrolled by 4, so all
 //    window indices are compile-time constants (no register moves).
-//  * domain-border rows (one-sided 3-point stencils, src/operators.jl:3-4) are processed together
-//    with their inward neighbour by a small out-of-line routine that keeps its state in shared memory.
+//  * the ring slot, mbarrier and output addresses of all rows a loop body touches are compile-time
+//    offsets from two loop-carried bases (the loop is unrolled by 4, the ring holds 8 rows).
+//  * domain-border rows (one-sided 3-point stencils, src/operators.jl:3-4): an item that touches the
+//    first row of the domain marches UPWARDS, one that touches the last row marches downwards, so the
+//    border row is always the last row of the march; when a stage has produced it, the row beyond it is
+//    filled with the quadratic extrapolation 3 v[n-1] - 3 v[n-2] + v[n-3], which turns the central
+//    difference of the next stage into the reference's one-sided stencil (v[n-3] - 4 v[n-2] + 3 v[n-1]).
 //  * GENERAL=false is the lean interior variant (sigma == 0 everywhere in the warp's window): Psi/Omega
 //    pass through unchanged; GENERAL=true handles PML strips and domain borders.
 #include <cuda.h>
@@ -34,45 +42,40 @@
 namespace {
 
 constexpr int RING = 8;      // ring slots (rows) per warp
-constexpr int PF = 2;        // TMA prefetch distance in rows
+constexpr int PF = 3;        // TMA prefetch distance in rows (PF + 5 <= RING)
 constexpr int CYL_CAP = 12;  // culled cylinders kept per warp
-constexpr int WARPS = 1;     // warps per CTA: one, so every item-derived value is provably CTA-uniform
+constexpr int LW = 64;       // columns per warp window (two per lane)
+constexpr int OWN_W = LW - 8;  // owned columns of a full window (4-column halo per side)
 
-// Per-variant layout.  The interior variant marches BOTH wavefields in one warp (it needs both for
-// the scattered energy and has registers to spare); the general variant (PML strips, domain borders)
-// carries twice the state per wavefield, so each warp takes ONE wavefield.
-// Ring slot rows (32 floats each): [0, NF) state fields written by TMA, row NF: source shape written by TMA
-// (only for rows inside the source's bounding box).  On arrival the warp rewrites some rows IN PLACE
-// (generic-proxy writes followed by fence.proxy.async before the slot's next TMA):
-//   F_SHV (= the shape row): shape or 0;
-//   interior: Psix rows -> P = Psix+Psiy-Omega (Psi/Omega are passed through to the output on arrival),
-//             Psiy_tot, Omega_tot, Psiy_inc rows -> kd*c^2 at the three stage times;
-//   general:  three extra rows hold kd*c^2 (all six fields stay live through the four stages).
+// Ring slot rows (LW floats each).  Rows [0, 6): the six fields of the warp's wavefield, written by TMA;
+// row 6: U of the incident field (total-field warps only; consumed on arrival by the energy metric);
+// row 7: source shape (TMA, only for rows inside the source's bounding box).
+// On arrival the warp rewrites some rows IN PLACE (generic-proxy writes followed by fence.proxy.async
+// before the slot's next TMA):
+//   interior: Psix row -> P = Psix+Psiy-Omega (Psi/Omega are passed through to the output on arrival);
+//             Psiy, Omega, U_inc rows -> kd*c^2 at the three stage times (only where a cylinder is near);
+//   general:  rows 6, 8, 9 hold kd*c^2 (all six fields stay live through the four stages).
 template <bool GENERAL>
 struct Cfg {
-    static constexpr int NW = GENERAL ? 1 : 2;
-    static constexpr int NF = 6 * NW;
-    static constexpr int F_SH = NF;
-    static constexpr int F_SHV = NF;
-    static constexpr int SLOT_ROWS = GENERAL ? NF + 4 : NF + 1;
-    static constexpr int SLOT_F = SLOT_ROWS * 32;
-    static constexpr int BSET_F = GENERAL ? 20 * 32 : 0;  // border-row state + call scratch (general only)
+    static constexpr int ROW_UI = 6;
+    static constexpr int ROW_SH = 7;
+    static constexpr int ROW_P = 3;
+    static constexpr int SLOT_ROWS = GENERAL ? 10 : 8;
+    static constexpr int SLOT_F = SLOT_ROWS * LW;
     static constexpr int RING_F = RING * SLOT_F;
-    static constexpr int CYL_OFF = RING_F + BSET_F;
+    static constexpr int CYL_OFF = RING_F;
     static constexpr int BAR_OFF = CYL_OFF + CYL_CAP * 12;
     static constexpr int WARP_F = ((BAR_OFF + RING * 2) + 31) & ~31;  // floats per warp (128-byte multiple)
     // row holding kd*c^2 at stage-time index tau
-    __host__ __device__ static constexpr int f_bk(int tau) { return GENERAL ? NF + 1 + tau : (tau == 0 ? 4 : (tau == 1 ? 5 : 10)); }
-    // interior: row holding P of wavefield w
-    __host__ __device__ static constexpr int f_p(int w) { return w * 6 + 3; }
+    __host__ __device__ static constexpr int f_bk(int tau) { return GENERAL ? (tau == 0 ? 6 : 7 + tau) : 4 + tau; }
 };
 
 struct Item {
-    int x0;        // first column of the 32-lane window (multiple of 4: TMA needs 16-byte aligned boxes)
-    int vlo, vhi;  // lanes [vlo, vhi) own output columns
+    int x0;        // first column of the 64-column window (multiple of 4: TMA needs 16-byte aligned boxes)
+    int vlo, vhi;  // columns [x0 + vlo, x0 + vhi) are owned (both even unless vhi reaches an odd nx)
     int j0, j1;    // output local rows [j0, j1)
     int la, lb;    // loaded local rows [la, lb)
-    int top, bot;  // window touches the domain's first / last row
+    int top, bot;  // window touches the domain's first / last row (never both: the host splits such row ranges)
 };
 
 struct FusedArgs {
@@ -89,6 +92,7 @@ struct FusedArgs {
     int epart_stride;  // items per env in epart (all kernels of a step share one buffer)
     int epart_off;     // offset of this kernel's items
     int dbg;           // developer bisecting flags (WAVES_DEBUG_FLAGS)
+    int cull;          // 0: skip the cylinder cull (no environment has a design)
     // host-computed step constants: read straight from the constant bank as FFMA operands
     float kd, b0kd;             // 1/(2Δ) and c0^2/(2Δ)
     float akd_h, akd_f, dt6kd;  // (dt/2)kd, dt*kd, (dt/6)kd
@@ -97,6 +101,20 @@ struct FusedArgs {
 };
 
 extern __shared__ __align__(128) float smf[];  // all shared memory, indexed with 32-bit arithmetic
+
+// ---- packed f32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2) ----------------------------------
+typedef float2 f2;
+__device__ __forceinline__ f2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ f2 bc2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ f2 operator+(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 operator-(f2 a, f2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ f2 operator*(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 operator*(float s, f2 a) { return __fmul2_rn(a, make_float2(s, s)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }             // a*b + c
+__device__ __forceinline__ f2 fma2(float s, f2 b, f2 c) { return __ffma2_rn(make_float2(s, s), b, c); }  // s*b + c
+__device__ __forceinline__ f2 lds2(int i) { return *reinterpret_cast<const f2 *>(&smf[i]); }
+__device__ __forceinline__ void sts2(int i, f2 v) { *reinterpret_cast<f2 *>(&smf[i]) = v; }
+__device__ __forceinline__ void stg2(float *p, f2 v) { *reinterpret_cast<f2 *>(p) = v; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -107,7 +125,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
+    uint32_t done, spins = 0;
     do {
         asm volatile(
             "{\n"
@@ -118,6 +136,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
+        // a TMA row that never lands is a bug: fail loudly (sticky launch error) instead of hanging the GPU
+        if (!done && ++spins > (1u << 22)) __trap();
     } while (!done);
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
@@ -140,23 +160,26 @@ __device__ __forceinline__ float interp_param(float p0, float p1, float ti, floa
 }
 
 // Per-warp context.  Everything here is either warp-uniform or a per-lane constant of the whole march.
+// Rows are addressed in MARCH order: march row m <-> local row jbase + dir * m, m in [0, nm).
 struct WarpCtx {
-    int lane, wb;      // lane, first float of this warp's shared memory
-    int x0, la, lb;
-    int js0;           // first row the regular stages may store
-    unsigned jsn;      // rows [js0, js0+jsn) are stored by this lane (0 for halo lanes)
-    float *out_e;      // output state of this env at this lane's column (+ wavefield offset in the general variant)
-    bool xb, top, bot, is_first_col, is_last_col, is_tot;
+    int lane2;         // 2 * lane: float offset of this lane's column pair inside a slot row
+    int x0;
+    int nm;            // loaded rows
+    int jbase, dir;    // local row of march row 0; +1 (marching down) or -1 (marching up)
+    int mo0;           // first owned march row
+    unsigned mon;      // march rows [mo0, mo0+mon) are owned (stored, counted in the energy) by this lane; 0 for halo lanes
+    int nlast;         // stages process march rows < nlast (nm when the march ends on a domain border row)
+    bool border;       // the last march row is the domain's first / last row
+    float *out_e;      // output state of this env / wavefield at this lane's column pair
+    int rowstep;       // dir * nxp: floats between consecutive march rows
+    bool xb, first_x, last_x, last_y, is_tot, use_bk, want_e, src_win;
     int w0;
-    float xs, sx, bcm;
+    f2 xs, sx, sxd, bcm;
+    float dirf, kdd;   // dir as float, kd * dir
     float sf[3];       // source factor at t, t+dt/2, t+dt
     uint32_t bar0, ring_sa;  // shared-window addresses of mbarrier 0 and of the ring
     int nact;          // culled cylinders (0: none touch this window, -1: list overflow -> slow loop)
-    int src_j0;
-    unsigned src_n;    // rows [src_j0, src_j0+src_n) of this window carry a non-zero source shape
 };
-
-__device__ __forceinline__ bool src_row(const WarpCtx &c, int j) { return (unsigned)(j - c.src_j0) < c.src_n; }
 
 // c(x,y,t)^2 with every cylinder (list overflow), exact order of src/designs.jl:99-116
 __device__ __noinline__ float speed2_slow(const FusedArgs &A, int e, int tau, float xs, float yv) {
@@ -182,408 +205,277 @@ __device__ __noinline__ float speed2_slow(const FusedArgs &A, int e, int tau, fl
     return __fmul_rn(cv, cv);
 }
 
-// kd * speed(design(t), grid, c0)^2 of local row j at the three stage times -> smf[dst + tau*32]
+// kd * speed(design(t), grid, c0)^2 of local row j at the three stage times -> slot rows f_bk(tau)
 // (src/designs.jl:99-116: strict '<', speeds of overlapping cylinders add, ambient where none).
+// Out of line: it runs once per row of the windows a cylinder touches and keeps the march's code small.
+// uri = float index of this lane's pair in row 0 of the slot.
 template <bool GENERAL>
-__device__ __forceinline__ void speed_row(const WarpCtx &c, const FusedArgs &A, int e, int j, int uri) {
+__device__ __noinline__ void speed_row(const FusedArgs &A, int e, int j, int uri, int nact, f2 xs) {
     using C = Cfg<GENERAL>;
     const float yv = A.gp.y[min(max(A.gp.grow0 + j, 0), A.gp.ny_global - 1)];
-#pragma unroll 1
     for (int tau = 0; tau < 3; ++tau) {
-        float b;
-        if (c.nact > 0) {
-            int cnt = 0;
-            float cd = 0.0f;
-#pragma unroll 1
-            for (int a = 0; a < c.nact; ++a) {
-                const float4 p = *reinterpret_cast<const float4 *>(&smf[c.wb + C::CYL_OFF + (a * 3 + tau) * 4]);  // px, py, r^2, c
-                float dy = __fsub_rn(yv, p.y);
-                float dy2 = __fmul_rn(dy, dy);
-                if (dy2 >= p.z) continue;  // warp-uniform: the row misses this cylinder
-                float dx = __fsub_rn(c.xs, p.x);
-                float d2 = __fadd_rn(__fmul_rn(dx, dx), dy2);
-                bool m = d2 < p.z;
-                cnt += m;
-                cd = __fadd_rn(cd, m ? p.w : 0.0f);
-            }
-            float cv = __fadd_rn(cnt == 0 ? A.gp.c0 : 0.0f, cd);
-            b = __fmul_rn(cv, cv);
-        } else {
-            b = speed2_slow(A, e, tau, c.xs, yv);
-        }
-        smf[uri + (tau == 0 ? C::f_bk(0) : (tau == 1 ? C::f_bk(1) : C::f_bk(2))) * 32] = b * A.kd;
-    }
-}
-
-// Out-of-line copy for the general variant (keeps its instruction footprint inside the I-cache)
-__device__ __noinline__ void speed_row_general(const FusedArgs &A, int e, int it, int j, int uri, int nact) {
-    using C = Cfg<true>;
-    const int lane = threadIdx.x & 31, wb = (threadIdx.x >> 5) * C::WARP_F;
-    const int col = A.items[it].x0 + lane;
-    const float xs = A.gp.x[min(col, A.gp.nx - 1)];
-    const float yv = A.gp.y[min(max(A.gp.grow0 + j, 0), A.gp.ny_global - 1)];
-    for (int tau = 0; tau < 3; ++tau) {
-        float b;
+        f2 b;
         if (nact > 0) {
-            int cnt = 0;
-            float cd = 0.0f;
+            int cnt0 = 0, cnt1 = 0;
+            float cd0 = 0.0f, cd1 = 0.0f;
             for (int a = 0; a < nact; ++a) {
-                const float4 p = *reinterpret_cast<const float4 *>(&smf[wb + C::CYL_OFF + (a * 3 + tau) * 4]);
-                float dy = __fsub_rn(yv, p.y);
-                float dy2 = __fmul_rn(dy, dy);
-                if (dy2 >= p.z) continue;
-                float dx = __fsub_rn(xs, p.x);
-                float d2 = __fadd_rn(__fmul_rn(dx, dx), dy2);
-                bool m = d2 < p.z;
-                cnt += m;
-                cd = __fadd_rn(cd, m ? p.w : 0.0f);
+                const float4 p = *reinterpret_cast<const float4 *>(&smf[C::CYL_OFF + (a * 3 + tau) * 4]);  // px, py, r^2, c
+                const float dy = __fsub_rn(yv, p.y);
+                const float dy2 = __fmul_rn(dy, dy);
+                if (dy2 >= p.z) continue;  // warp-uniform: the row misses this cylinder
+                const float dx0 = __fsub_rn(xs.x, p.x), dx1 = __fsub_rn(xs.y, p.x);
+                const bool m0 = __fadd_rn(__fmul_rn(dx0, dx0), dy2) < p.z, m1 = __fadd_rn(__fmul_rn(dx1, dx1), dy2) < p.z;
+                cnt0 += m0;
+                cnt1 += m1;
+                cd0 = __fadd_rn(cd0, m0 ? p.w : 0.0f);
+                cd1 = __fadd_rn(cd1, m1 ? p.w : 0.0f);
             }
-            float cv = __fadd_rn(cnt == 0 ? A.gp.c0 : 0.0f, cd);
-            b = __fmul_rn(cv, cv);
+            const float cv0 = __fadd_rn(cnt0 == 0 ? A.gp.c0 : 0.0f, cd0), cv1 = __fadd_rn(cnt1 == 0 ? A.gp.c0 : 0.0f, cd1);
+            b = mk2(__fmul_rn(cv0, cv0), __fmul_rn(cv1, cv1));
         } else {
-            b = speed2_slow(A, e, tau, xs, yv);
+            b = mk2(speed2_slow(A, e, tau, xs.x, yv), speed2_slow(A, e, tau, xs.y, yv));
         }
-        smf[uri + C::f_bk(tau) * 32] = b * A.kd;
+        sts2(uri + (tau == 0 ? C::f_bk(0) : (tau == 1 ? C::f_bk(1) : C::f_bk(2))) * LW, A.kd * b);
     }
 }
 
-// Register state of one warp: rotating windows indexed [stage][wavefield][row & 3]
+// Register state of one warp: rotating windows indexed [stage][march row & 3], one column pair per lane
 template <bool GENERAL>
 struct Regs {
-    static constexpr int NW = Cfg<GENERAL>::NW;
-    float Uf[4][NW][4];  // U + f of stage state y_s (s = 0: the loaded row)
-    float Vy[4][NW][4];
-    float Vx[4][NW][4];  // s = 1..3
-    float aU[NW][4], aVx[NW][4], aVy[NW][4];  // k1 + 2k2 + 2k3 accumulators (aVx, aVy: un-scaled differences)
+    f2 Uf[4][4];  // U + f of stage state y_s (s = 0: the loaded row)
+    f2 Vy[4][4];
+    f2 Vx[4][4];  // s = 1..3
+    f2 aU[4], aVx[4], aVy[4];  // k1 + 2k2 + 2k3 accumulators (interior: aVx, aVy hold un-scaled differences)
     // GENERAL only
-    float Uc[4][NW][4], Px[4][NW][4], Py[4][NW][4], Om[4][NW][4];
-    float aPx[NW][4], aPy[NW][4], aOm[NW][4];
-    float e_tot, e_inc, e_sc;
+    f2 Px[4][4], Py[4][4], Om[4][4];
+    f2 aPx[4], aPy[4], aOm[4];
+    float sy[4];  // sigma_y of the rows in flight
+    f2 e_tot, e_inc, e_sc;
 };
 
-// Border-row state kept in shared memory (general variant, per warp): row index * 32 + lane
-enum { B_VX = 0, B_UC, B_PX, B_PY, B_OM, B_AU, B_AVX, B_AVY, B_APX, B_APY, B_AOM, B_F0 = 12, B_F1, B_F2, B_V0, B_V1, B_V2 };
-
-// One RK stage on a domain-border row (global row 0 or ny-1) of this warp's wavefield.  The caller left
-// U+f and Vy of the previous stage state on the three rows the one-sided stencil spans (ascending rows)
-// in the border scratch B_F0..B_V2; everything else is re-derived here (rare path, kept out of line and
-// out of the hot path's registers).  Returns the new (Uf, Vy) of the border row.
-__device__ __noinline__ float2 border_row_stage(const FusedArgs &A, int e, int it, int w0, int S, bool top, int nact) {
-    using C = Cfg<true>;
-    const GridP &gp = A.gp;
-    const int lane = threadIdx.x & 31, wb = (threadIdx.x >> 5) * C::WARP_F;
-    const Item item = A.items[it];
-    const int jb = top ? item.la : item.lb - 1;
-    const int col = item.x0 + lane;
-    const int uri = wb + ((jb - item.la) & (RING - 1)) * C::SLOT_F + lane;
-    const int bsi = wb + C::RING_F + lane;
-    const float *g = top ? gp.g_first : gp.g_last;
-    const float kd = gp.g_central[1];
-    const float sx = gp.sigma[min(col, gp.nx - 1)], sy = gp.sigma[gp.grow0 + jb];
-    const float a = (S == 3) ? gp.dt : gp.hdt;
-    const int tau = (S == 1) ? 0 : (S == 4 ? 2 : 1);
-    const float *trow = A.table + ((size_t)e * A.steps + A.step) * STAGE_ROW;
-    const float sf_next = (S == 1 || S == 2) ? trow[4] : trow[5];
-    const float shv = smf[uri + C::F_SHV * 32];
-    const float b = (w0 == 0 && nact != 0) ? smf[uri + C::f_bk(tau) * 32] / kd : gp.b0;
-    const float uU = smf[uri], uVx = smf[uri + 32], uVy = smf[uri + 64], uPx = smf[uri + 96], uPy = smf[uri + 128], uOm = smf[uri + 160];
-    const float f0 = smf[bsi + B_F0 * 32], f1 = smf[bsi + B_F1 * 32], f2 = smf[bsi + B_F2 * 32];
-    const float v0 = smf[bsi + B_V0 * 32], v1 = smf[bsi + B_V1 * 32], v2 = smf[bsi + B_V2 * 32];
-    const float ufC = top ? f0 : f2, vyC = top ? v0 : v2;
-    const float vxC = (S == 1) ? uVx : smf[bsi + B_VX * 32];
-    const float uC = (S == 1) ? uU : smf[bsi + B_UC * 32];
-    auto ddx = [&](float v) {
-        float e1 = __shfl_down_sync(0xffffffffu, v, 1), w1 = __shfl_up_sync(0xffffffffu, v, 1);
-        float e2 = __shfl_down_sync(0xffffffffu, v, 2), w2 = __shfl_up_sync(0xffffffffu, v, 2);
-        float d = kd * (e1 - w1);
-        if (col == 0) d = ((gp.g_first[0] * v) + (gp.g_first[1] * e1)) + (gp.g_first[2] * e2);
-        if (col == gp.nx - 1) d = ((gp.g_last[0] * w2) + (gp.g_last[1] * w1)) + (gp.g_last[2] * v);
-        return d;
-    };
-    const float Ux = ddx(ufC), Vxx = ddx(vxC);
-    const float Uy = ((g[0] * f0) + (g[1] * f1)) + (g[2] * f2);
-    const float Vyy = ((g[0] * v0) + (g[1] * v1)) + (g[2] * v2);
-    // bc == 0 on a border row (src/dims.jl:117-124): dU = 0
-    const float kU = 0.0f;
-    const float kVx = Ux - sx * vxC, kVy = Uy - sy * vyC;
-    const float kPx = (b * sx) * Vyy, kPy = (b * sy) * Vxx, kOm = (sx * sy) * uC;
-    float2 ret = make_float2(0.f, 0.f);
-    if (S < 4) {
-        const float Us = uU + a * kU;
-        ret.x = Us + shv * sf_next;
-        ret.y = uVy + a * kVy;
-        smf[bsi + B_VX * 32] = uVx + a * kVx;
-        smf[bsi + B_UC * 32] = Us;
-        smf[bsi + B_PX * 32] = uPx + a * kPx;
-        smf[bsi + B_PY * 32] = uPy + a * kPy;
-        smf[bsi + B_OM * 32] = uOm + a * kOm;
-        const float m = (S == 1) ? 0.0f : 1.0f, w = (S == 1) ? 1.0f : 2.0f;
-        smf[bsi + B_AU * 32] = m * smf[bsi + B_AU * 32] + w * kU;
-        smf[bsi + B_AVX * 32] = m * smf[bsi + B_AVX * 32] + w * kVx;
-        smf[bsi + B_AVY * 32] = m * smf[bsi + B_AVY * 32] + w * kVy;
-        smf[bsi + B_APX * 32] = m * smf[bsi + B_APX * 32] + w * kPx;
-        smf[bsi + B_APY * 32] = m * smf[bsi + B_APY * 32] + w * kPy;
-        smf[bsi + B_AOM * 32] = m * smf[bsi + B_AOM * 32] + w * kOm;
-    } else if (lane >= item.vlo && lane < item.vhi && jb >= item.j0 && jb < item.j1) {
-        const float sixth = 1.0f / 6.0f;
-        float *o = A.out + (long long)e * gp.env_stride + (long long)w0 * 6 * gp.plane + (long long)jb * gp.nxp + col;
-        o[0] = uU + (sixth * (smf[bsi + B_AU * 32] + kU)) * gp.dt;
-        o[gp.plane] = uVx + (sixth * (smf[bsi + B_AVX * 32] + kVx)) * gp.dt;
-        o[2 * gp.plane] = uVy + (sixth * (smf[bsi + B_AVY * 32] + kVy)) * gp.dt;
-        o[3 * gp.plane] = uPx + (sixth * (smf[bsi + B_APX * 32] + kPx)) * gp.dt;
-        o[4 * gp.plane] = uPy + (sixth * (smf[bsi + B_APY * 32] + kPy)) * gp.dt;
-        o[5 * gp.plane] = uOm + (sixth * (smf[bsi + B_AOM * 32] + kOm)) * gp.dt;
+// un-scaled d/dx (times 2Δ) of a column-pair value; interior columns only
+__device__ __forceinline__ f2 ddx_int(f2 v) {
+    const float e = __shfl_down_sync(0xffffffffu, v.x, 1), w = __shfl_up_sync(0xffffffffu, v.y, 1);
+    return mk2(v.y - w, e - v.x);
+}
+// same, with the one-sided 3-point rows on the domain's edge columns (src/operators.jl:3-4); relative to
+// 1/(2Δ) their coefficients are (-3, 4, -1) and (1, -4, 3)
+__device__ __forceinline__ f2 ddx_gen(const WarpCtx &c, f2 v) {
+    const float e = __shfl_down_sync(0xffffffffu, v.x, 1), w = __shfl_up_sync(0xffffffffu, v.y, 1);
+    f2 d = mk2(v.y - w, e - v.x);
+    if (c.xb) {  // warp-uniform
+        const float w2 = __shfl_up_sync(0xffffffffu, v.x, 1);
+        if (c.first_x) d.x = (4.0f * v.y - 3.0f * v.x) - e;
+        if (c.last_y) d.y = (3.0f * v.y - 4.0f * v.x) + w;
+        if (c.last_x) d.x = (3.0f * v.x - 4.0f * w) + w2;
     }
-    __syncwarp();
-    return ret;
+    return d;
+}
+// value of the row beyond a domain border row that makes the central difference one-sided (see file header)
+__device__ __forceinline__ f2 ghost_row(f2 v1, f2 v2, f2 v3) { return fma2(3.0f, v1 - v2, v3); }
+
+// Loop-carried addressing of one 4-row loop body: the ring half that holds march rows rb..rb+3 and the
+// other half (rows rb-4..rb-1 and, for the prefetch, rb+4..rb+7).  All are float indices into smf / byte
+// addresses in the shared window INCLUDING this lane's column-pair offset where applicable.
+struct Body {
+    int cur, oth;            // float index of slot 0 of the current / other half + 2 * lane
+    uint32_t bar_c, bar_o;   // mbarrier of slot 0 of the current / other half
+    uint32_t ring_c, ring_o; // byte address of slot 0 of the current / other half (TMA destination)
+    uint32_t par;            // mbarrier phase parity of the rows arriving in this body
+    unsigned orow;           // float offset (row * nxp) of march row rb - 4 in the output planes
+};
+
+// float index of this lane's pair in row 0 of the slot that holds march row rb + PH + D (D in [-4, 3])
+template <bool GENERAL, int PH, int D>
+__device__ __forceinline__ int slot_of(const Body &b) {
+    constexpr int q = PH + D;
+    static_assert(q >= -4 && q < 8, "slot offset out of range");
+    return (q >= 0 && q < 4) ? b.cur + q * Cfg<GENERAL>::SLOT_F : b.oth + (q < 0 ? q + 4 : q - 4) * Cfg<GENERAL>::SLOT_F;
 }
 
-// One RK stage S (1..4) on row j = r - S.  PH = r & 3.  Rows whose inputs are not loaded yet (warm-up)
+// One RK stage S (1..4) on march row m = r - S.  PH = r & 3.  Rows whose inputs are not loaded yet (warm-up)
 // produce values that no stored cell depends on, and stores are predicated.
 // Derivatives are kept un-scaled (differences); the 1/(2Δ) factor is folded into the coefficients.
 template <bool GENERAL, int S, int PH>
-__device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, int e, int it, Regs<GENERAL> &R, int j) {
+__device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, const Body &b, Regs<GENERAL> &R, int m) {
     using C = Cfg<GENERAL>;
-    constexpr int sc = (PH - S + 8) & 3, sm = (sc + 3) & 3, sp = (sc + 1) & 3;  // slots of rows j, j-1, j+1
-    const int uri = c.wb + ((j - c.la) & (RING - 1)) * C::SLOT_F + c.lane;
+    constexpr int sc = (PH - S + 8) & 3, sm = (sc + 3) & 3, sp = (sc + 1) & 3, s2 = (sc + 2) & 3;  // rows m, m-1, m+1, m-2
+    const int uri = slot_of<GENERAL, PH, -S>(b);
     const float a = (S == 3) ? A.dt : A.hdt;
     const float akd = (S == 3) ? A.akd_f : A.akd_h;
     constexpr int tau = (S == 1) ? 0 : (S == 4 ? 2 : 1);
-    const float shv = (S < 4) ? smf[uri + C::F_SHV * 32] : 0.0f;
     const float sf_next = (S == 1 || S == 2) ? c.sf[1] : c.sf[2];
-    const float bk_tot = smf[uri + C::f_bk(tau) * 32];  // kd * c^2 (written on arrival)
-    const bool st = (unsigned)(j - c.js0) < c.jsn;         // this lane stores row j
-    float outU[C::NW];
+    const f2 bk = c.use_bk ? lds2(uri + C::f_bk(tau) * LW) : bc2(A.b0kd);  // kd * c^2 (written on arrival)
+    const f2 uU = lds2(uri), uVx = lds2(uri + LW), uVy = lds2(uri + 2 * LW);
+    const f2 ufC = R.Uf[S - 1][sc];
+    const f2 vxC = (S == 1) ? uVx : R.Vx[S - 1][sc];
+    const f2 dUy = R.Uf[S - 1][sp] - R.Uf[S - 1][sm];  // in march order
+    const f2 dVy = R.Vy[S - 1][sp] - R.Vy[S - 1][sm];
     if (!GENERAL) {
-#pragma unroll
-        for (int w = 0; w < C::NW; ++w) {
-            const int uw = uri + w * 6 * 32;
-            const float uU = smf[uw], uVx = smf[uw + 32], uVy = smf[uw + 64];
-            const float bk = (w == 0) ? bk_tot : A.b0kd;
-            const float ufC = R.Uf[S - 1][w][sc];
-            const float vxC = (S == 1) ? uVx : R.Vx[S - 1][w][sc];
-            const float dUx = __shfl_down_sync(0xffffffffu, ufC, 1) - __shfl_up_sync(0xffffffffu, ufC, 1);
-            const float dVx = __shfl_down_sync(0xffffffffu, vxC, 1) - __shfl_up_sync(0xffffffffu, vxC, 1);
-            const float dUy = R.Uf[S - 1][w][sp] - R.Uf[S - 1][w][sm];
-            const float dVy = R.Vy[S - 1][w][sp] - R.Vy[S - 1][w][sm];
-            // sigma == 0 in the whole window: Psi, Omega never change within the step; P was formed on arrival
-            const float kU = bk * (dVx + dVy) + smf[uri + C::f_p(w) * 32];
-            if (S < 4) {
-                const float Us = uU + a * kU;
-                R.Uf[S][w][sc] = Us + shv * sf_next;
-                R.Vx[S][w][sc] = uVx + akd * dUx;
-                R.Vy[S][w][sc] = uVy + akd * dUy;
-                if (S == 1) {
-                    R.aU[w][sc] = kU;
-                    R.aVx[w][sc] = dUx;
-                    R.aVy[w][sc] = dUy;
-                } else {
-                    R.aU[w][sc] += 2.0f * kU;
-                    R.aVx[w][sc] += 2.0f * dUx;
-                    R.aVy[w][sc] += 2.0f * dUy;
-                }
+        const f2 dUx = ddx_int(ufC), dVx = ddx_int(vxC);
+        // sigma == 0 in the whole window: Psi, Omega never change within the step; P was formed on arrival
+        const f2 kU = fma2(bk, dVx + dVy, lds2(uri + C::ROW_P * LW));
+        if (S < 4) {
+            R.Uf[S][sc] = fma2(sf_next, lds2(uri + C::ROW_SH * LW), fma2(a, kU, uU));
+            R.Vx[S][sc] = fma2(akd, dUx, uVx);
+            R.Vy[S][sc] = fma2(akd, dUy, uVy);
+            if (S == 1) {
+                R.aU[sc] = kU;
+                R.aVx[sc] = dUx;
+                R.aVy[sc] = dUy;
             } else {
-                const float oU = uU + A.dt6 * (R.aU[w][sc] + kU);
-                outU[w] = oU;
-                if (st) {
-                    float *o = c.out_e + (unsigned)(w * 6) * A.plane + (unsigned)j * A.nxp;
-                    o[0] = oU;
-                    o[A.plane] = uVx + A.dt6kd * (R.aVx[w][sc] + dUx);
-                    o[2u * A.plane] = uVy + A.dt6kd * (R.aVy[w][sc] + dUy);
-                }
+                R.aU[sc] = fma2(2.0f, kU, R.aU[sc]);
+                R.aVx[sc] = fma2(2.0f, dUx, R.aVx[sc]);
+                R.aVy[sc] = fma2(2.0f, dUy, R.aVy[sc]);
             }
-        }
-        if (S == 4 && st) {
-            const float d = outU[0] - outU[C::NW - 1];
-            R.e_tot += outU[0] * outU[0];
-            R.e_inc += outU[C::NW - 1] * outU[C::NW - 1];
-            R.e_sc += d * d;
+        } else if ((unsigned)(m - c.mo0) < c.mon) {
+            float *o = c.out_e + (b.orow + (unsigned)(PH * c.rowstep));
+            stg2(o, fma2(A.dt6, R.aU[sc] + kU, uU));
+            stg2(o + A.plane, fma2(A.dt6kd, R.aVx[sc] + dUx, uVx));
+            stg2(o + 2u * A.plane, fma2(A.dt6kd, R.aVy[sc] + dUy, uVy));
         }
     } else {
-        const GridP &gp = A.gp;
-        const float sy = gp.sigma[min(max(A.gp.grow0 + j, 0), A.gp.ny_global - 1)];
-        const float sx = c.sx;
-        const float uU = smf[uri], uVx = smf[uri + 32], uVy = smf[uri + 64], uPx = smf[uri + 96], uPy = smf[uri + 128], uOm = smf[uri + 160];
-        const float bk = c.is_tot ? bk_tot : A.b0kd;
-        const float ufC = R.Uf[S - 1][0][sc];
-        const float vxC = (S == 1) ? uVx : R.Vx[S - 1][0][sc];
-        const float vyC = R.Vy[S - 1][0][sc];
-        const float uC = (S == 1) ? uU : R.Uc[S - 1][0][sc];
-        const float px = (S == 1) ? uPx : R.Px[S - 1][0][sc];
-        const float py = (S == 1) ? uPy : R.Py[S - 1][0][sc];
-        const float om = (S == 1) ? uOm : R.Om[S - 1][0][sc];
-        // un-scaled x-differences (one-sided 3-point rows on the domain's edge columns, pre-divided by kd)
-        float e1 = __shfl_down_sync(0xffffffffu, ufC, 1), w1 = __shfl_up_sync(0xffffffffu, ufC, 1);
-        float dUx = e1 - w1;
-        float e1v = __shfl_down_sync(0xffffffffu, vxC, 1), w1v = __shfl_up_sync(0xffffffffu, vxC, 1);
-        float dVx = e1v - w1v;
-        if (c.xb) {
-            // one-sided 3-point rows on the domain's edge columns (src/operators.jl:3-4); relative to 1/(2Δ) the
-            // coefficients are (-3, 4, -1) and (1, -4, 3)
-            const float e2 = __shfl_down_sync(0xffffffffu, ufC, 2), w2 = __shfl_up_sync(0xffffffffu, ufC, 2);
-            const float e2v = __shfl_down_sync(0xffffffffu, vxC, 2), w2v = __shfl_up_sync(0xffffffffu, vxC, 2);
-            if (c.is_first_col) {
-                dUx = (4.0f * e1 - 3.0f * ufC) - e2;
-                dVx = (4.0f * e1v - 3.0f * vxC) - e2v;
-            }
-            if (c.is_last_col) {
-                dUx = (3.0f * ufC - 4.0f * w1) + w2;
-                dVx = (3.0f * vxC - 4.0f * w1v) + w2v;
-            }
-        }
-        const float dUy = R.Uf[S - 1][0][sp] - R.Uf[S - 1][0][sm];
-        const float dVy = R.Vy[S - 1][0][sp] - R.Vy[S - 1][0][sm];
-        const float kU = c.bcm * ((((bk * (dVx + dVy) + px) + py) - (sx + sy) * uC) - om);
-        const float kVx = A.kd * dUx - sx * vxC;
-        const float kVy = A.kd * dUy - sy * vyC;
-        const float kPx = (bk * sx) * dVy;
-        const float kPy = (bk * sy) * dVx;
-        const float kOm = (sx * sy) * uC;
+        const float sy = R.sy[sc];
+        const f2 sx = c.sx;
+        const f2 uPx = lds2(uri + 3 * LW), uPy = lds2(uri + 4 * LW), uOm = lds2(uri + 5 * LW);
+        const f2 vyC = R.Vy[S - 1][sc];
+        const f2 px = (S == 1) ? uPx : R.Px[S - 1][sc];
+        const f2 py = (S == 1) ? uPy : R.Py[S - 1][sc];
+        const f2 om = (S == 1) ? uOm : R.Om[S - 1][sc];
+        // U of the stage state without the source term (differs from U + f only inside the source's columns)
+        const float sf_cur = (S == 1) ? c.sf[0] : ((S == 4) ? c.sf[2] : c.sf[1]);
+        const f2 uC = (S == 1) ? uU : (c.src_win ? fma2(-sf_cur, lds2(uri + C::ROW_SH * LW), ufC) : ufC);
+        const f2 dUx = ddx_gen(c, ufC), dVx = ddx_gen(c, vxC);
+        const bool brow = c.border && m == c.nm - 1;  // warp-uniform: this is the domain's first / last row
+        // dU = bc * [b (Vxx + Vyy) + Psix + Psiy - (sx + sy) U - Omega]      (src/dynamics.jl:169)
+        const f2 ssum = sx + bc2(sy);
+        const f2 dsum = fma2(c.dirf, dVy, dVx);
+        f2 kU = c.bcm * (((fma2(bk, dsum, px) + py) - ssum * uC) - om);
+        if (brow) kU = bc2(0.0f);  // bc == 0 on the border rows (src/dims.jl:117-124)
+        const f2 kVx = A.kd * dUx - sx * vxC;
+        const f2 kVy = c.kdd * dUy - sy * vyC;
+        const f2 kPx = (bk * c.sxd) * dVy;
+        const f2 kPy = (sy * bk) * dVx;
+        const f2 kOm = (sy * sx) * uC;
         if (S < 4) {
-            const float Us = uU + a * kU;
-            R.Uf[S][0][sc] = Us + shv * sf_next;
-            R.Vx[S][0][sc] = uVx + a * kVx;
-            R.Vy[S][0][sc] = uVy + a * kVy;
-            R.Uc[S][0][sc] = Us;
-            R.Px[S][0][sc] = uPx + a * kPx;
-            R.Py[S][0][sc] = uPy + a * kPy;
-            R.Om[S][0][sc] = uOm + a * kOm;
+            R.Uf[S][sc] = fma2(sf_next, lds2(uri + C::ROW_SH * LW), fma2(a, kU, uU));
+            R.Vx[S][sc] = fma2(a, kVx, uVx);
+            R.Vy[S][sc] = fma2(a, kVy, uVy);
+            R.Px[S][sc] = fma2(a, kPx, uPx);
+            R.Py[S][sc] = fma2(a, kPy, uPy);
+            R.Om[S][sc] = fma2(a, kOm, uOm);
             if (S == 1) {
-                R.aU[0][sc] = kU;
-                R.aVx[0][sc] = kVx;
-                R.aVy[0][sc] = kVy;
-                R.aPx[0][sc] = kPx;
-                R.aPy[0][sc] = kPy;
-                R.aOm[0][sc] = kOm;
+                R.aU[sc] = kU;
+                R.aVx[sc] = kVx;
+                R.aVy[sc] = kVy;
+                R.aPx[sc] = kPx;
+                R.aPy[sc] = kPy;
+                R.aOm[sc] = kOm;
             } else {
-                R.aU[0][sc] += 2.0f * kU;
-                R.aVx[0][sc] += 2.0f * kVx;
-                R.aVy[0][sc] += 2.0f * kVy;
-                R.aPx[0][sc] += 2.0f * kPx;
-                R.aPy[0][sc] += 2.0f * kPy;
-                R.aOm[0][sc] += 2.0f * kOm;
+                R.aU[sc] = fma2(2.0f, kU, R.aU[sc]);
+                R.aVx[sc] = fma2(2.0f, kVx, R.aVx[sc]);
+                R.aVy[sc] = fma2(2.0f, kVy, R.aVy[sc]);
+                R.aPx[sc] = fma2(2.0f, kPx, R.aPx[sc]);
+                R.aPy[sc] = fma2(2.0f, kPy, R.aPy[sc]);
+                R.aOm[sc] = fma2(2.0f, kOm, R.aOm[sc]);
             }
-        } else if (st) {
-            float *o = c.out_e + (unsigned)j * A.nxp;
-            o[0] = uU + A.dt6 * (R.aU[0][sc] + kU);
-            o[A.plane] = uVx + A.dt6 * (R.aVx[0][sc] + kVx);
-            o[2u * A.plane] = uVy + A.dt6 * (R.aVy[0][sc] + kVy);
-            o[3u * A.plane] = uPx + A.dt6 * (R.aPx[0][sc] + kPx);
-            o[4u * A.plane] = uPy + A.dt6 * (R.aPy[0][sc] + kPy);
-            o[5u * A.plane] = uOm + A.dt6 * (R.aOm[0][sc] + kOm);
-        }
-        // domain-border rows ride along with their inward neighbour (see file header)
-        const bool do_top = c.top && j == c.la + 1, do_bot = c.bot && j == c.lb - 2;
-        if (do_top || do_bot) {
-            const int bsi = c.wb + C::RING_F + c.lane;
-            smf[bsi + B_F0 * 32] = R.Uf[S - 1][0][sm];
-            smf[bsi + B_F1 * 32] = R.Uf[S - 1][0][sc];
-            smf[bsi + B_F2 * 32] = R.Uf[S - 1][0][sp];
-            smf[bsi + B_V0 * 32] = R.Vy[S - 1][0][sm];
-            smf[bsi + B_V1 * 32] = R.Vy[S - 1][0][sc];
-            smf[bsi + B_V2 * 32] = R.Vy[S - 1][0][sp];
-            if (do_top) {
-                const float2 o = border_row_stage(A, e, it, c.w0, S, true, c.nact);
-                if (S < 4) {
-                    R.Uf[S][0][sm] = o.x;
-                    R.Vy[S][0][sm] = o.y;
-                }
+            if (brow) {
+                R.Uf[S][sp] = ghost_row(R.Uf[S][sc], R.Uf[S][sm], R.Uf[S][s2]);
+                R.Vy[S][sp] = ghost_row(R.Vy[S][sc], R.Vy[S][sm], R.Vy[S][s2]);
             }
-            if (do_bot) {
-                const float2 o = border_row_stage(A, e, it, c.w0, S, false, c.nact);
-                if (S < 4) {
-                    R.Uf[S][0][sp] = o.x;
-                    R.Vy[S][0][sp] = o.y;
-                }
-            }
+        } else if ((unsigned)(m - c.mo0) < c.mon) {
+            float *o = c.out_e + (b.orow + (unsigned)(PH * c.rowstep));
+            stg2(o, fma2(A.dt6, R.aU[sc] + kU, uU));
+            stg2(o + A.plane, fma2(A.dt6, R.aVx[sc] + kVx, uVx));
+            stg2(o + 2u * A.plane, fma2(A.dt6, R.aVy[sc] + kVy, uVy));
+            stg2(o + 3u * A.plane, fma2(A.dt6, R.aPx[sc] + kPx, uPx));
+            stg2(o + 4u * A.plane, fma2(A.dt6, R.aPy[sc] + kPy, uPy));
+            stg2(o + 5u * A.plane, fma2(A.dt6, R.aOm[sc] + kOm, uOm));
         }
     }
 }
 
 template <bool GENERAL, int PH>
-__device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, int e, int it, Regs<GENERAL> &R, int r,
+__device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, int e, const Body &b, Regs<GENERAL> &R, int r,
                                          const CUtensorMap *map_u, const CUtensorMap *map_sh) {
     using C = Cfg<GENERAL>;
-    // 1. prefetch row r + PF into the slot that row r + PF - RING vacated (all its readers finished >= 1 step ago)
+    // 1. prefetch march row r + PF into the slot that row r + PF - RING vacated (all its readers finished >= 1 step ago)
     __syncwarp();
-    const int rp = r + PF;
-    if (c.lane == 0 && rp >= c.la && rp < c.lb && !(A.dbg & 2)) {
-        const int slot = (rp - c.la) & (RING - 1);
-        const uint32_t bar = c.bar0 + slot * 8, dst = c.ring_sa + slot * (C::SLOT_F * 4);
-        const bool s = src_row(c, rp);
-        mbar_expect_tx(bar, C::NF * 128 + (s ? 128 : 0));
-        tma_load_3d(dst, map_u, c.x0, rp, e * 12 + c.w0 * 6, bar);
-        if (s) tma_load_3d(dst + C::F_SH * 128, map_sh, c.x0, rp, e, bar);
+    {
+        const int rp = r + PF;
+        if (c.lane2 == 0 && rp >= 0 && rp < c.nm) {
+            constexpr int q = PH + PF;
+            const uint32_t bar = (q < 4 ? b.bar_c + q * 8 : b.bar_o + (q - 4) * 8);
+            const uint32_t dst = (q < 4 ? b.ring_c + q * (C::SLOT_F * 4) : b.ring_o + (q - 4) * (C::SLOT_F * 4));
+            const int jp = c.jbase + c.dir * rp;
+            mbar_expect_tx(bar, ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0)) * (LW * 4));
+            tma_load_3d(dst, map_u, c.x0, jp, e * 12 + c.w0 * 6, bar);
+            if (c.src_win) tma_load_3d(dst + C::ROW_SH * (LW * 4), map_sh, c.x0, jp, e, bar);
+        }
     }
-    // 2. arrival of row r: stage-0 windows, speed field of the row, interior pass-through of Psi/Omega
-    if (r >= c.la && r < c.lb) {
-        const int rel = r - c.la;
-        if (!(A.dbg & 2)) mbar_wait(c.bar0 + (rel & (RING - 1)) * 8, (rel >> 3) & 1);
-        const int uri = c.wb + (rel & (RING - 1)) * C::SLOT_F + c.lane;
-        const float shv = src_row(c, r) ? smf[uri + C::F_SH * 32] : 0.0f;
-        smf[uri + C::F_SHV * 32] = shv;
-        constexpr int s0 = PH & 3;
-#pragma unroll
-        for (int w = 0; w < C::NW; ++w) {
-            R.Uf[0][w][s0] = smf[uri + w * 6 * 32] + shv * c.sf[0];
-            R.Vy[0][w][s0] = smf[uri + w * 6 * 32 + 64];
+    // 2. arrival of march row r: stage-0 windows, energy of the owned rows, interior pass-through of Psi/Omega,
+    //    speed field of the row
+    if (r >= 0 && r < c.nm) {
+        mbar_wait(b.bar_c + PH * 8, b.par);
+        const int uri = b.cur + PH * C::SLOT_F;
+        constexpr int s0 = PH & 3, sm = (s0 + 3) & 3, s2 = (s0 + 2) & 3, sp = (s0 + 1) & 3;
+        const f2 U = lds2(uri);
+        R.Uf[0][s0] = fma2(c.sf[0], lds2(uri + C::ROW_SH * LW), U);
+        R.Vy[0][s0] = lds2(uri + 2 * LW);
+        const bool own = (unsigned)(r - c.mo0) < c.mon;
+        if (c.want_e && own) {  // energy of the frame being read (src/env.jl:104-111)
+            const f2 Ui = lds2(uri + C::ROW_UI * LW), d = U - Ui;
+            R.e_tot = fma2(U, U, R.e_tot);
+            R.e_inc = fma2(Ui, Ui, R.e_inc);
+            R.e_sc = fma2(d, d, R.e_sc);
         }
-        float pP[C::NW];
         if (!GENERAL) {
-            const bool st = (unsigned)(r - c.js0) < c.jsn;
-#pragma unroll
-            for (int w = 0; w < C::NW; ++w) {
-                const float px = smf[uri + (w * 6 + 3) * 32], py = smf[uri + (w * 6 + 4) * 32], om = smf[uri + (w * 6 + 5) * 32];
-                pP[w] = (px + py) - om;
-                if (st) {
-                    float *o = c.out_e + (unsigned)(w * 6 + 3) * A.plane + (unsigned)r * A.nxp;
-                    o[0] = px;
-                    o[A.plane] = py;
-                    o[2u * A.plane] = om;
-                }
+            const f2 px = lds2(uri + 3 * LW), py = lds2(uri + 4 * LW), om = lds2(uri + 5 * LW);
+            if (own) {
+                float *o = c.out_e + (b.orow + (unsigned)((PH + 4) * c.rowstep) + 3u * A.plane);
+                stg2(o, px);
+                stg2(o + A.plane, py);
+                stg2(o + 2u * A.plane, om);
             }
-#pragma unroll
-            for (int w = 0; w < C::NW; ++w) smf[uri + C::f_p(w) * 32] = pP[w];
-        }
-        if (c.nact != 0) {
-            if (GENERAL)
-                speed_row_general(A, e, it, r, uri, c.nact);
-            else
-                speed_row<GENERAL>(c, A, e, r, uri);
+            sts2(uri + C::ROW_P * LW, (px + py) - om);
         } else {
-            smf[uri + C::f_bk(0) * 32] = A.b0kd;
-            smf[uri + C::f_bk(1) * 32] = A.b0kd;
-            smf[uri + C::f_bk(2) * 32] = A.b0kd;
+            if (c.border && r == c.nm - 1) {  // ghost row beyond the domain border for the stage-0 windows
+                R.Uf[0][sp] = ghost_row(R.Uf[0][s0], R.Uf[0][sm], R.Uf[0][s2]);
+                R.Vy[0][sp] = ghost_row(R.Vy[0][s0], R.Vy[0][sm], R.Vy[0][s2]);
+            }
         }
+        if (c.use_bk) speed_row<GENERAL>(A, e, c.jbase + c.dir * r, uri, c.nact, c.xs);
         // the rows rewritten above are TMA targets again RING rows later: order the generic writes before it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (A.dbg & 1) return;
-    // 3. the four stages, each one row behind the previous.  Rows below la + 1 run unguarded (whatever they
-    //    compute is overwritten before a stored cell reads it).  In the general variant rows above lb - 2
-    //    must not run: they would clobber the border row's window slots.
+    // 3. the four stages, each one row behind the previous.  Rows below 1 run unguarded (whatever they
+    //    compute is overwritten before a stored cell reads it).  In the general variant rows beyond a domain
+    //    border row must not run: they would clobber the ghost rows.
     if (GENERAL) {
-        const int jhi = c.lb - 2;
-        if (r - 1 <= jhi) stage<GENERAL, 1, PH>(c, A, e, it, R, r - 1);
-        if (r - 2 <= jhi) stage<GENERAL, 2, PH>(c, A, e, it, R, r - 2);
-        if (r - 3 <= jhi) stage<GENERAL, 3, PH>(c, A, e, it, R, r - 3);
-        if (r - 4 <= jhi) stage<GENERAL, 4, PH>(c, A, e, it, R, r - 4);
+        if (r - 1 < c.nlast) stage<GENERAL, 1, PH>(c, A, b, R, r - 1);
+        if (r - 2 < c.nlast) stage<GENERAL, 2, PH>(c, A, b, R, r - 2);
+        if (r - 3 < c.nlast) stage<GENERAL, 3, PH>(c, A, b, R, r - 3);
+        if (r - 4 < c.nlast) stage<GENERAL, 4, PH>(c, A, b, R, r - 4);
+        // sigma_y of march row r: first used by stage 1 in the next iteration (its slot was row r - 4's until now)
+        R.sy[PH & 3] = A.gp.sigma[min(max(A.gp.grow0 + c.jbase + c.dir * r, 0), A.gp.ny_global - 1)];
     } else {
-        stage<GENERAL, 1, PH>(c, A, e, it, R, r - 1);
-        stage<GENERAL, 2, PH>(c, A, e, it, R, r - 2);
-        stage<GENERAL, 3, PH>(c, A, e, it, R, r - 3);
-        stage<GENERAL, 4, PH>(c, A, e, it, R, r - 4);
+        stage<GENERAL, 1, PH>(c, A, b, R, r - 1);
+        stage<GENERAL, 2, PH>(c, A, b, R, r - 2);
+        stage<GENERAL, 3, PH>(c, A, b, R, r - 3);
+        stage<GENERAL, 4, PH>(c, A, b, R, r - 4);
     }
 }
 
 template <bool GENERAL>
-__global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
-k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_sh) {
+__global__ void __launch_bounds__(32, GENERAL ? 8 : 12)
+k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtensorMap map_u7, const __grid_constant__ CUtensorMap map_u6,
+             const __grid_constant__ CUtensorMap map_sh) {
     using C = Cfg<GENERAL>;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    long long gw = (long long)blockIdx.x * WARPS + warp;
-    const int w0 = GENERAL ? (int)(gw & 1) : 0;  // general: two warps (tot, inc) per item
-    if (GENERAL) gw >>= 1;
+    const int lane = threadIdx.x & 31;
+    // one warp per CTA: every item-derived value below is provably CTA-uniform (uniform datapath)
+    long long gw = blockIdx.x;
+    const int w0 = (int)(gw & 1);  // two warps (tot, inc) per item, adjacent block indices -> co-scheduled
+    gw >>= 1;
     const int e = (int)(gw / A.n_items), it = (int)(gw - (long long)e * A.n_items);
     if (e >= A.gp.n_env) return;
     const GridP &gp = A.gp;
@@ -591,55 +483,58 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     const EnvParams ep = A.env[e];
 
     WarpCtx c;
-    c.lane = lane;
-    c.wb = warp * C::WARP_F;
-    c.ring_sa = smem_u32(&smf[c.wb]);
-    c.bar0 = smem_u32(&smf[c.wb + C::BAR_OFF]);
+    c.lane2 = 2 * lane;
+    c.ring_sa = smem_u32(&smf[0]);
+    c.bar0 = smem_u32(&smf[C::BAR_OFF]);
     c.w0 = w0;
     c.is_tot = w0 == 0;
+    c.want_e = c.is_tot && A.epart != nullptr;
     c.x0 = item.x0;
-    c.la = item.la;
-    c.lb = item.lb;
-    c.top = item.top;
-    c.bot = item.bot;
-    const int col = item.x0 + lane;
-    const bool valid_lane = lane >= item.vlo && lane < item.vhi;
-    {
-        // regular stages store rows that have both y-neighbours loaded; border rows belong to border_row_stage
-        const int js0 = max(item.j0, item.la + 1), js1 = min(item.j1, item.lb - 1);
-        c.js0 = js0;
-        c.jsn = (valid_lane && js1 > js0) ? (unsigned)(js1 - js0) : 0u;
-    }
-    c.out_e = A.out + (long long)e * gp.env_stride + (long long)w0 * 6 * gp.plane + min(col, gp.nx - 1);
-    c.is_first_col = col == 0;
-    c.is_last_col = col == gp.nx - 1;
-    c.xb = (item.x0 == 0) || (item.x0 + 32 >= gp.nx);
-    c.bcm = (c.is_first_col || c.is_last_col) ? 0.0f : 1.0f;
-    c.xs = gp.x[min(col, gp.nx - 1)];  // lanes past the last column (nx % 4 != 0) are never valid
-    c.sx = GENERAL ? gp.sigma[min(col, gp.nx - 1)] : 0.0f;
+    c.nm = item.lb - item.la;
+    c.dir = (GENERAL && item.top) ? -1 : 1;
+    c.dirf = (float)c.dir;
+    c.kdd = A.kd * c.dirf;
+    c.jbase = c.dir > 0 ? item.la : item.lb - 1;
+    c.border = GENERAL && (item.top || item.bot);
+    c.nlast = c.border ? c.nm : 0x7fffffff;
+    c.rowstep = c.dir * (int)A.nxp;
+    const int colA = item.x0 + 2 * lane, colB = colA + 1;
+    const bool valid_lane = 2 * lane >= item.vlo && 2 * lane < item.vhi;
+    c.mo0 = c.dir > 0 ? item.j0 - item.la : item.lb - item.j1;
+    c.mon = valid_lane ? (unsigned)(item.j1 - item.j0) : 0u;
+    c.out_e = A.out + (long long)e * gp.env_stride + (long long)w0 * 6 * gp.plane + min(colA, gp.nxp - 2);
+    c.first_x = colA == 0;
+    c.last_x = colA == gp.nx - 1;
+    c.last_y = colB == gp.nx - 1;
+    c.xb = (item.x0 == 0) || (item.x0 + LW >= gp.nx);
+    c.bcm = mk2((c.first_x || c.last_x) ? 0.0f : 1.0f, c.last_y ? 0.0f : 1.0f);
+    c.xs = mk2(gp.x[min(colA, gp.nx - 1)], gp.x[min(colB, gp.nx - 1)]);  // columns past nx are never owned
+    c.sx = GENERAL ? mk2(gp.sigma[min(colA, gp.nx - 1)], gp.sigma[min(colB, gp.nx - 1)]) : bc2(0.0f);
+    c.sxd = c.dirf * c.sx;
     const float *trow = A.table + ((size_t)e * A.steps + A.step) * STAGE_ROW;
     c.sf[0] = trow[3];
     c.sf[1] = trow[4];
     c.sf[2] = trow[5];
-    {
-        const bool src_cols = ep.has_source && item.x0 < ep.src_i1 && item.x0 + 32 > ep.src_i0;
-        c.src_j0 = ep.src_j0;
-        c.src_n = (src_cols && ep.src_j1 > ep.src_j0) ? (unsigned)(ep.src_j1 - ep.src_j0) : 0u;
-    }
+    // the source shape row rides along for every row of the windows that overlap the source's columns; the
+    // other windows keep a zero row
+    c.src_win = ep.has_source && item.x0 < ep.src_i1 && item.x0 + LW > ep.src_i0 && ep.src_j1 > ep.src_j0;
 
-    if (lane == 0 && !(A.dbg & 8)) {
+    if (lane == 0) {
         for (int s = 0; s < RING; ++s) mbar_init(c.bar0 + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (!c.src_win)
+        for (int s = 0; s < RING; ++s) sts2(s * C::SLOT_F + C::ROW_SH * LW + c.lane2, bc2(0.0f));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
 
     // cull the design's cylinders against this warp's window, at the three stage times (src/designs.jl:287-292)
     c.nact = 0;
-    if (ep.ncyl > 0 && (!GENERAL || c.is_tot) && !(A.dbg & 4)) {
-        const float xlo = gp.x[item.x0], xhi = gp.x[min(item.x0 + 31, gp.nx - 1)];
-        const float ylo = gp.y[min(max(gp.grow0 + item.la, 0), gp.ny_global - 1)];
-        const float yhi = gp.y[min(max(gp.grow0 + item.lb - 1, 0), gp.ny_global - 1)];
+    if (A.cull && ep.ncyl > 0 && c.is_tot) {
+        const float xlo = gp.x[item.x0], xhi = gp.x[min(item.x0 + LW - 1, gp.nx - 1)];
+        const float ya = gp.y[min(max(gp.grow0 + item.la, 0), gp.ny_global - 1)];
+        const float yb = gp.y[min(max(gp.grow0 + item.lb - 1, 0), gp.ny_global - 1)];
+        const float ylo = fminf(ya, yb), yhi = fmaxf(ya, yb);
         int n = 0;
         for (int k0 = 0; k0 < ep.ncyl; k0 += 32) {
             const int k = k0 + lane;
@@ -670,7 +565,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
             if (hit && pos < CYL_CAP) {
 #pragma unroll
                 for (int tau = 0; tau < 3; ++tau)
-                    *reinterpret_cast<float4 *>(&smf[c.wb + C::CYL_OFF + (pos * 3 + tau) * 4]) =
+                    *reinterpret_cast<float4 *>(&smf[C::CYL_OFF + (pos * 3 + tau) * 4]) =
                         make_float4(P[tau][0], P[tau][1], P[tau][2], P[tau][3]);
             }
             n += __popc(bal);
@@ -678,43 +573,50 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
         c.nact = n <= CYL_CAP ? n : -1;
         __syncwarp();
     }
+    c.use_bk = c.nact != 0;
 
     Regs<GENERAL> R;
-    R.e_tot = R.e_inc = R.e_sc = 0.0f;
+    R.e_tot = R.e_inc = R.e_sc = bc2(0.0f);
     // zero-init windows so never-consumed warm-up values are finite
 #pragma unroll
     for (int s = 0; s < 4; ++s)
 #pragma unroll
-        for (int w = 0; w < C::NW; ++w)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                R.Uf[s][w][q] = 0.f;
-                R.Vy[s][w][q] = 0.f;
-                R.Vx[s][w][q] = 0.f;
-                R.Uc[s][w][q] = 0.f;
-                R.Px[s][w][q] = 0.f;
-                R.Py[s][w][q] = 0.f;
-                R.Om[s][w][q] = 0.f;
-            }
-#pragma unroll
-    for (int w = 0; w < C::NW; ++w)
-#pragma unroll
         for (int q = 0; q < 4; ++q) {
-            R.aU[w][q] = R.aVx[w][q] = R.aVy[w][q] = 0.f;
-            R.aPx[w][q] = R.aPy[w][q] = R.aOm[w][q] = 0.f;
+            R.Uf[s][q] = R.Vy[s][q] = R.Vx[s][q] = bc2(0.f);
+            R.Px[s][q] = R.Py[s][q] = R.Om[s][q] = bc2(0.f);
         }
-
-    const int r_begin = (c.la - PF) & ~3, r_end = c.lb + 4;  // the first PF steps only prefetch
-#pragma unroll 1
-    for (int r = r_begin; r < r_end; r += 4) {
-        row_step<GENERAL, 0>(c, A, e, it, R, r, &map_u, &map_sh);
-        row_step<GENERAL, 1>(c, A, e, it, R, r + 1, &map_u, &map_sh);
-        row_step<GENERAL, 2>(c, A, e, it, R, r + 2, &map_u, &map_sh);
-        row_step<GENERAL, 3>(c, A, e, it, R, r + 3, &map_u, &map_sh);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        R.aU[q] = R.aVx[q] = R.aVy[q] = bc2(0.f);
+        R.aPx[q] = R.aPy[q] = R.aOm[q] = bc2(0.f);
+        R.sy[q] = 0.f;
     }
 
-    if (!GENERAL && A.epart) {
-        float et = R.e_tot, ei = R.e_inc, es = R.e_sc;
+    const CUtensorMap *map_u = c.is_tot ? &map_u7 : &map_u6;
+    // march rows rb .. rb+3 per loop body; the body starting at -4 only prefetches and warms up.  March row m
+    // lives in ring slot m & 7, so a body's rows fill one half of the ring.
+    Body b;
+    const int nbody = (c.nm + 4 + 3) / 4 + 1;  // bodies -4, 0, 4, ... covering arrivals up to nm-1 and the 4 drain rows
+    b.orow = (unsigned)((c.jbase - 8 * c.dir) * (int)A.nxp);  // march row -8 (body -4 stores rows rb-4 .. rb-1: none owned)
+#pragma unroll 1
+    for (int k = 0; k < nbody; ++k) {
+        const int rb = 4 * k - 4, half = (k + 1) & 1;
+        b.cur = half * 4 * C::SLOT_F + c.lane2;
+        b.oth = (half ^ 1) * 4 * C::SLOT_F + c.lane2;
+        b.bar_c = c.bar0 + half * 32;
+        b.bar_o = c.bar0 + (half ^ 1) * 32;
+        b.ring_c = c.ring_sa + half * (4 * C::SLOT_F * 4);
+        b.ring_o = c.ring_sa + (half ^ 1) * (4 * C::SLOT_F * 4);
+        b.par = ((k - 1) >> 1) & 1;  // march row m is use number m >> 3 of its slot
+        row_step<GENERAL, 0>(c, A, e, b, R, rb, map_u, &map_sh);
+        row_step<GENERAL, 1>(c, A, e, b, R, rb + 1, map_u, &map_sh);
+        row_step<GENERAL, 2>(c, A, e, b, R, rb + 2, map_u, &map_sh);
+        row_step<GENERAL, 3>(c, A, e, b, R, rb + 3, map_u, &map_sh);
+        b.orow += (unsigned)(4 * c.rowstep);
+    }
+
+    if (c.want_e) {
+        float et = R.e_tot.x + R.e_tot.y, ei = R.e_inc.x + R.e_inc.y, es = R.e_sc.x + R.e_sc.y;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             et += __shfl_down_sync(0xffffffffu, et, o);
@@ -727,39 +629,6 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
             p[1] = ei;
             p[2] = es;
         }
-    }
-}
-
-// Energy partials of the output cells owned by the general items (PML strips / borders): one warp per item,
-// reading the freshly written U_tot / U_inc rows (src/env.jl:104-111).
-__global__ void __launch_bounds__(128) k_energy_items(GridP gp, const float *__restrict__ u, const Item *__restrict__ items, int n_items,
-                                                      float *__restrict__ epart, int epart_stride, int epart_off) {
-    const int lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int e = (int)(gw / n_items), it = (int)(gw - (long long)e * n_items);
-    if (e >= gp.n_env) return;
-    const Item item = items[it];
-    const float *ut = u + (long long)e * gp.env_stride, *ui = ut + 6 * gp.plane;
-    float et = 0.f, ei = 0.f, es = 0.f;
-    if (lane >= item.vlo && lane < item.vhi) {
-        for (int j = item.j0; j < item.j1; ++j) {
-            const long long q = (long long)j * gp.nxp + item.x0 + lane;
-            const float a = ut[q], b = ui[q], d = a - b;
-            et += a * a;
-            ei += b * b;
-            es += d * d;
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        et += __shfl_down_sync(0xffffffffu, et, o);
-        ei += __shfl_down_sync(0xffffffffu, ei, o);
-        es += __shfl_down_sync(0xffffffffu, es, o);
-    }
-    if (lane == 0) {
-        float *p = epart + ((size_t)e * epart_stride + epart_off + it) * 3;
-        p[0] = et;
-        p[1] = ei;
-        p[2] = es;
     }
 }
 
@@ -816,10 +685,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_map(PFN_encodeTiled enc, CUtensorMap *m, float *base, const GridP &gp, int planes, int box_planes) {
-    // box = 32 columns x 1 row x box_planes field planes
+    // box = LW columns x 1 row x box_planes field planes
     cuuint64_t dims[3] = {(cuuint64_t)gp.nx, (cuuint64_t)gp.ny_alloc, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)gp.nxp * 4, (cuuint64_t)gp.plane * 4};
-    cuuint32_t box[3] = {32, 1, (cuuint32_t)box_planes};
+    cuuint32_t box[3] = {(cuuint32_t)LW, 1, (cuuint32_t)box_planes};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -862,21 +731,22 @@ int fused_prepare(waves_handle *h) {
     // --- columns: output ranges [olo, ohi) ---
     // MEASURED ON B200: cp.async.bulk.tensor (tiled) raises "illegal instruction" unless the innermost
     // coordinate is 16-byte aligned, so every window starts at a multiple of 4 columns (scripts/dbg/tma_ring.cu).
+    // Owned ranges start at multiples of 8 columns where possible so neighbouring strips split on 32-byte sectors.
     struct Col { int olo, ohi, x0; bool interior; };
     std::vector<Col> cols;
     auto add_cols = [&](int a, int b, bool interior) {  // a is a multiple of 4
         int o = a;
         while (o < b) {
             const int x0 = o == 0 ? 0 : o - 4;
-            int hi = x0 + 28;  // 24 owned columns + 4 halo (28 at the left domain edge)
-            if (x0 + 32 >= gp.nx) hi = gp.nx;  // the window reaches the right domain edge: no halo needed there
+            int hi = o + OWN_W;  // 56 owned columns + 4 halo columns per side
+            if (x0 + LW >= gp.nx) hi = gp.nx;  // the window reaches the right domain edge: no halo needed there
             if (hi > b) hi = b;
             cols.push_back({o, hi, x0, interior});
             o = hi;
         }
     };
     // interior output columns keep their 4-column halo inside the zero-sigma zone
-    int ci0 = (z0 + 4 + 3) & ~3, ci1 = (z1 - 4) & ~3;
+    int ci0 = (z0 + 4 + 7) & ~7, ci1 = (z1 - 4) & ~3;
     if (ci1 - ci0 < 24) {
         add_cols(0, gp.nx, false);
     } else {
@@ -885,8 +755,8 @@ int fused_prepare(waves_handle *h) {
         add_cols(ci1, gp.nx, false);
     }
     for (auto &cc : cols) {
-        // interior strips must have the whole 32-lane window inside the zero zone
-        if (cc.interior && !(cc.x0 >= z0 && cc.x0 + 32 <= z1)) cc.interior = false;
+        // interior strips must have the whole 64-column window inside the zero zone
+        if (cc.interior && !(cc.x0 >= z0 && cc.x0 + LW <= z1)) cc.interior = false;
     }
 
     // --- rows: output ranges in local rows ---
@@ -898,10 +768,12 @@ int fused_prepare(waves_handle *h) {
     if (ri0 < own0) ri0 = own0;
     if (ri1 > own1) ri1 = own1;
     // rows per slab: tall slabs amortise the 8 warm-up rows, but keep >= ~8 waves of warps in flight
-    const int SEG = std::max(48, std::min(192, (int)((long long)gp.ny_own * (long long)cols.size() * gp.n_env / 14000)));
+    const int SEG = std::max(48, std::min(192, (int)(2LL * gp.ny_own * (long long)cols.size() * gp.n_env / 14000)));
     auto add_rows = [&](int a, int b, bool interior) {
         if (b <= a) return;
         int n = (b - a + SEG - 1) / SEG;
+        // an item may touch only ONE of the domain's first / last rows (it marches towards it)
+        if (gp.grow0 + a < 4 && gp.grow0 + b > gp.ny_global - 4 && n < 2) n = 2;
         for (int k = 0; k < n; ++k) {
             int lo = a + (int)((long long)(b - a) * k / n), hi = a + (int)((long long)(b - a) * (k + 1) / n);
             rows.push_back({lo, hi, interior});
@@ -944,8 +816,8 @@ int fused_prepare(waves_handle *h) {
     cudaMalloc((void **)&p->d_epart, sizeof(float) * 3 * (size_t)(ii.size() + gg.size()) * gp.n_env);
     cudaMalloc((void **)&p->d_bb, sizeof(int) * 4);
 
-    p->smem_gen = WARPS * Cfg<true>::WARP_F * 4;
-    p->smem_int = WARPS * Cfg<false>::WARP_F * 4;
+    p->smem_gen = Cfg<true>::WARP_F * 4;
+    p->smem_int = Cfg<false>::WARP_F * 4;
     cudaError_t ce = cudaFuncSetAttribute(k_fused_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_gen);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_int);
     if (ce != cudaSuccess) {
@@ -961,8 +833,8 @@ int fused_prepare(waves_handle *h) {
     ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (ce != cudaSuccess || !fn) return waves_set_error("fused_prepare: cuTensorMapEncodeTiled entry point not found");
     PFN_encodeTiled enc = (PFN_encodeTiled)fn;
-    int r0 = make_map(enc, &h->map_u[0], h->u[0], gp, 12 * gp.n_env, 12);
-    int r1 = make_map(enc, &h->map_u[1], h->u[1], gp, 12 * gp.n_env, 12);
+    int r0 = make_map(enc, &h->map_u[0], h->u[0], gp, 12 * gp.n_env, 7);  // total field + U of the incident field
+    int r1 = make_map(enc, &h->map_u[1], h->u[1], gp, 12 * gp.n_env, 7);
     int r2 = make_map(enc, &h->map_shape, h->shape, gp, gp.n_env, 1);
     r0 |= make_map(enc, &h->map_u6[0], h->u[0], gp, 12 * gp.n_env, 6);
     r1 |= make_map(enc, &h->map_u6[1], h->u[1], gp, 12 * gp.n_env, 6);
@@ -994,6 +866,7 @@ int fused_item_counts(waves_handle *h, int *n_int, int *n_gen) {
     return 0;
 }
 
+// d_e3 (nullable) receives the energies of the state the step READS (frame `step`), not of the one it writes.
 int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step, float *d_e3) {
     FusedPlan *p = plan_of(h, false);
     if (!p || !h->maps_ready) return waves_set_error("fused step: handle not prepared");
@@ -1024,31 +897,25 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     A.nxp = (unsigned)h->gp.nxp;
     static const int dbg_flags = getenv("WAVES_DEBUG_FLAGS") ? atoi(getenv("WAVES_DEBUG_FLAGS")) : 0;
     A.dbg = dbg_flags;
+    A.cull = (dbg_flags & 4) ? 0 : 1;
     static const int dbg_skip = getenv("WAVES_DEBUG_SKIP") ? atoi(getenv("WAVES_DEBUG_SKIP")) : 0;  // developer bisecting aid
     if (h->profile) cudaEventRecord(h->ev0, h->stream);
+    // two warps (= CTAs) per item and environment: the total and the incident wavefield
     if (p->n_int > 0 && !(dbg_skip & 1)) {
         A.items = p->d_items_int;
         A.n_items = p->n_int;
         A.epart_off = 0;
-        long long warps = (long long)p->n_int * h->gp.n_env;
-        k_fused_step<false><<<(unsigned)((warps + WARPS - 1) / WARPS), WARPS * 32, p->smem_int, h->stream>>>(A, h->map_u[h->cur],
-                                                                                                        h->map_shape);
+        const long long warps = 2LL * p->n_int * h->gp.n_env;
+        k_fused_step<false><<<(unsigned)warps, 32, p->smem_int, h->stream>>>(A, h->map_u[h->cur], h->map_u6[h->cur], h->map_shape);
         h->launches++;
     }
     if (p->n_gen > 0 && !(dbg_skip & 2)) {
         A.items = p->d_items_gen;
         A.n_items = p->n_gen;
         A.epart_off = p->n_int;
-        long long warps = 2LL * p->n_gen * h->gp.n_env;  // one warp per wavefield
-        k_fused_step<true><<<(unsigned)((warps + WARPS - 1) / WARPS), WARPS * 32, p->smem_gen, h->stream>>>(A, h->map_u6[h->cur],
-                                                                                                       h->map_shape);
+        const long long warps = 2LL * p->n_gen * h->gp.n_env;
+        k_fused_step<true><<<(unsigned)warps, 32, p->smem_gen, h->stream>>>(A, h->map_u[h->cur], h->map_u6[h->cur], h->map_shape);
         h->launches++;
-        if (d_e3) {
-            long long ew = (long long)p->n_gen * h->gp.n_env;
-            k_energy_items<<<(unsigned)((ew + 3) / 4), 128, 0, h->stream>>>(h->gp, A.out, p->d_items_gen, p->n_gen, p->d_epart,
-                                                                            A.epart_stride, p->n_int);
-            h->launches++;
-        }
     }
     if (h->profile) {
         cudaEventRecord(h->ev1, h->stream);

@@ -148,7 +148,8 @@ extern "C" int waves_create(const waves_config *cfg, waves_handle **out) {
     if (!cfg || !out) return fail("waves_create: null argument");
     *out = nullptr;
     int ny_global = cfg->ny_global > 0 ? cfg->ny_global : cfg->ny;
-    if (cfg->nx < 32 || cfg->ny < 8) return fail("waves_create: need nx >= 32 and ny >= 8 (got %d x %d)", cfg->nx, cfg->ny);
+    if (cfg->nx < 32 || cfg->ny < 8 || ny_global < 16)
+        return fail("waves_create: need nx >= 32, ny >= 8 and ny_global >= 16 (got %d x %d of %d)", cfg->nx, cfg->ny, ny_global);
     if (cfg->nx != ny_global)
         return fail("waves_create: nx (%d) must equal ny_global (%d): the reference takes sigma_y = sigma_x' "
                     "(src/dynamics.jl:162)", cfg->nx, ny_global);
@@ -570,13 +571,18 @@ extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, i
         return 0;
     };
 
-    if (energy) launch_energy(h, h->u[h->cur], h->d_energy, 3 * (steps + 1));
+    // The fused kernel reports the energies of the frame it READS (they ride on the row arrival), so frame n
+    // comes out of step n and the last frame needs one stand-alone reduction; the exact path reports the frame
+    // it wrote.
+    const bool fused = mode == WAVES_MODE_FUSED;
+    if (energy && !fused) launch_energy(h, h->u[h->cur], h->d_energy, 3 * (steps + 1));
     if (emit(0)) return 1;
     for (int n = 0; n < steps; ++n) {
-        float *d_e3 = energy ? h->d_energy + 3 * (size_t)(n + 1) : nullptr;
+        float *d_e3 = energy ? h->d_energy + 3 * (size_t)(fused ? n : n + 1) : nullptr;
         if (step_any(h, steps, n, mode, d_e3)) return 1;
         if (emit(n + 1)) return 1;
     }
+    if (energy && fused) launch_energy(h, h->u[h->cur], h->d_energy + 3 * (size_t)steps, 3 * (steps + 1));
     if (energy)
         CU_TRY(cudaMemcpyAsync(energy, h->d_energy, sizeof(float) * 3 * (size_t)(steps + 1) * gp.n_env, cudaMemcpyDefault,
                                h->stream));

@@ -64,8 +64,8 @@ struct waves_handle {
     float *d_energy;
     int energy_cap;  // frames capacity
     float d_omega;
-    CUtensorMap map_u[2];   // TMA descriptors over the two state buffers, box = 32 x 1 x 12 planes
-    CUtensorMap map_u6[2];  // same tensors, box = 32 x 1 x 6 planes (one wavefield)
+    CUtensorMap map_u[2];   // TMA descriptors over the two state buffers, box = 64 x 1 x 7 planes (total field + U_inc)
+    CUtensorMap map_u6[2];  // same tensors, box = 64 x 1 x 6 planes (one wavefield)
     CUtensorMap map_shape;
     bool maps_ready;
     int64_t launches;
