@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libwaves_b200.so")
+# WAVES_B200_LIB selects another build of the same ABI (scripts/tune_build.sh); there is still no CPU fallback
+SO_PATH = os.environ.get("WAVES_B200_LIB") or os.path.join(_HERE, "libwaves_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 fp = C.POINTER(C.c_float)

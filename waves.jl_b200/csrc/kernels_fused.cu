@@ -26,8 +26,8 @@
 //    border row is always the last row of the march; when a stage has produced it, the row beyond it is
 //    filled with the quadratic extrapolation 3 v[n-1] - 3 v[n-2] + v[n-3], which turns the central
 //    difference of the next stage into the reference's one-sided stencil (v[n-3] - 4 v[n-2] + 3 v[n-1]).
-//  * GENERAL=false is the lean interior variant (sigma == 0 everywhere in the warp's window): Psi/Omega
-//    pass through unchanged; GENERAL=true handles PML strips and domain borders.
+//  * four variants (template V): interior (sigma == 0 in the warp's window: Psi/Omega pass through), left-right
+//    PML strips (only Psix evolves), top-bottom PML strips (only Psiy evolves), corners (everything).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -41,33 +41,54 @@
 
 namespace {
 
+// Build-time tuning switches (defaults are the measured best; scripts/tune_build.sh builds the alternatives)
+#ifndef WV_P_REGS
+#define WV_P_REGS 1   // V = 0: keep P = Psix + Psiy - Omega of the rows in flight in registers instead of shared memory
+#endif
+#ifndef WV_TMA_CTA
+#define WV_TMA_CTA 1  // cp.async.bulk.tensor destination state space: 1 = shared::cta, 0 = shared::cluster
+#endif
+#ifndef WV_PFL2
+#define WV_PFL2 0     // L2 prefetch distance in rows (0: none)
+#endif
+#ifndef WV_OCC_STRIP
+#define WV_OCC_STRIP 8  // resident warps per SM the PML-strip variants are compiled for (8: 255 registers, 12: 168)
+#endif
 constexpr int RING = 8;      // ring slots (rows) per warp
 constexpr int PF = 3;        // TMA prefetch distance in rows (PF + 5 <= RING)
+constexpr int PFL2 = WV_PFL2;  // L2 prefetch distance in rows (cp.async.bulk.prefetch.tensor)
 constexpr int CYL_CAP = 12;  // culled cylinders kept per warp
 constexpr int LW = 64;       // columns per warp window (two per lane)
 constexpr int OWN_W = LW - 8;  // owned columns of a full window (4-column halo per side)
 
+// Kernel variants.  V = SX | SY << 1:
+//   SX: the window's columns may have sigma_x != 0 or include the domain's first / last column
+//   SY: the window's rows may have sigma_y != 0 or include the domain's first / last row
+// V = 0 is the interior (sigma == 0 in the whole window: Psix, Psiy, Omega never change and only pass through);
+// V = 1 / 2 are the left-right / top-bottom PML strips (only Psix / Psiy evolves besides U, Vx, Vy; the other
+// two auxiliary fields pass through); V = 3 are the corners (all six fields evolve).
+//
 // Ring slot rows (LW floats each).  Rows [0, 6): the six fields of the warp's wavefield, written by TMA;
 // row 6: U of the incident field (total-field warps only; consumed on arrival by the energy metric);
-// row 7: source shape (TMA, only for rows inside the source's bounding box).
+// row 7: source shape (TMA, only in windows that overlap the source's columns; zero otherwise).
 // On arrival the warp rewrites some rows IN PLACE (generic-proxy writes followed by fence.proxy.async
 // before the slot's next TMA):
-//   interior: Psix row -> P = Psix+Psiy-Omega (Psi/Omega are passed through to the output on arrival);
-//             Psiy, Omega, U_inc rows -> kd*c^2 at the three stage times (only where a cylinder is near);
-//   general:  rows 6, 8, 9 hold kd*c^2 (all six fields stay live through the four stages).
-template <bool GENERAL>
+//   ROW_P: the constant part of dU, P = sum of the pass-through fields (Psix + Psiy - Omega for V = 0);
+//   rows f_bk(0..2): kd*c^2 at the three stage times (only where a cylinder is near).
+template <int V>
 struct Cfg {
+    static constexpr bool SX = (V & 1) != 0, SY = (V & 2) != 0;
     static constexpr int ROW_UI = 6;
     static constexpr int ROW_SH = 7;
-    static constexpr int ROW_P = 3;
-    static constexpr int SLOT_ROWS = GENERAL ? 10 : 8;
+    static constexpr int ROW_P = SX ? 4 : 3;  // V = 1: Psiy row; V = 0, 2: Psix row; V = 3: unused
+    static constexpr int SLOT_ROWS = V == 0 ? 8 : 10;
     static constexpr int SLOT_F = SLOT_ROWS * LW;
     static constexpr int RING_F = RING * SLOT_F;
     static constexpr int CYL_OFF = RING_F;
     static constexpr int BAR_OFF = CYL_OFF + CYL_CAP * 12;
     static constexpr int WARP_F = ((BAR_OFF + RING * 2) + 31) & ~31;  // floats per warp (128-byte multiple)
     // row holding kd*c^2 at stage-time index tau
-    __host__ __device__ static constexpr int f_bk(int tau) { return GENERAL ? (tau == 0 ? 6 : 7 + tau) : 4 + tau; }
+    __host__ __device__ static constexpr int f_bk(int tau) { return V != 0 ? (tau == 0 ? 6 : 7 + tau) : 4 + tau; }
 };
 
 struct Item {
@@ -76,6 +97,7 @@ struct Item {
     int j0, j1;    // output local rows [j0, j1)
     int la, lb;    // loaded local rows [la, lb)
     int top, bot;  // window touches the domain's first / last row (never both: the host splits such row ranges)
+    int cls;       // kernel variant V
 };
 
 struct FusedArgs {
@@ -142,9 +164,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
     asm volatile(
+#if WV_TMA_CTA
+        "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+#else
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+#endif
         "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
+}
+// HBM -> L2 only: keeps more bytes in flight than the shared-memory ring could hold
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // DesignInterpolator(t) for one parameter, exact float32 order (src/designs.jl:287-292)
@@ -205,51 +235,54 @@ __device__ __noinline__ float speed2_slow(const FusedArgs &A, int e, int tau, fl
     return __fmul_rn(cv, cv);
 }
 
-// kd * speed(design(t), grid, c0)^2 of local row j at the three stage times -> slot rows f_bk(tau)
+// kd * speed(design(t), grid, c0)^2 of one row (y coordinate yv) at the three stage times -> slot rows f_bk(tau)
 // (src/designs.jl:99-116: strict '<', speeds of overlapping cylinders add, ambient where none).
-// Out of line: it runs once per row of the windows a cylinder touches and keeps the march's code small.
+// Out of line: it runs once per row of the windows a cylinder touches and keeps the march's code small; every
+// operand comes by value so no kernel parameter is re-read through a generic pointer.
 // uri = float index of this lane's pair in row 0 of the slot.
-template <bool GENERAL>
-__device__ __noinline__ void speed_row(const FusedArgs &A, int e, int j, int uri, int nact, f2 xs) {
-    using C = Cfg<GENERAL>;
-    const float yv = A.gp.y[min(max(A.gp.grow0 + j, 0), A.gp.ny_global - 1)];
+template <int V>
+__device__ __noinline__ void speed_row(int uri, int nact, f2 xs, float yv, float c0, float kd) {
+    using C = Cfg<V>;
+#pragma unroll 1
     for (int tau = 0; tau < 3; ++tau) {
-        f2 b;
-        if (nact > 0) {
-            int cnt0 = 0, cnt1 = 0;
-            float cd0 = 0.0f, cd1 = 0.0f;
-            for (int a = 0; a < nact; ++a) {
-                const float4 p = *reinterpret_cast<const float4 *>(&smf[C::CYL_OFF + (a * 3 + tau) * 4]);  // px, py, r^2, c
-                const float dy = __fsub_rn(yv, p.y);
-                const float dy2 = __fmul_rn(dy, dy);
-                if (dy2 >= p.z) continue;  // warp-uniform: the row misses this cylinder
-                const float dx0 = __fsub_rn(xs.x, p.x), dx1 = __fsub_rn(xs.y, p.x);
-                const bool m0 = __fadd_rn(__fmul_rn(dx0, dx0), dy2) < p.z, m1 = __fadd_rn(__fmul_rn(dx1, dx1), dy2) < p.z;
-                cnt0 += m0;
-                cnt1 += m1;
-                cd0 = __fadd_rn(cd0, m0 ? p.w : 0.0f);
-                cd1 = __fadd_rn(cd1, m1 ? p.w : 0.0f);
-            }
-            const float cv0 = __fadd_rn(cnt0 == 0 ? A.gp.c0 : 0.0f, cd0), cv1 = __fadd_rn(cnt1 == 0 ? A.gp.c0 : 0.0f, cd1);
-            b = mk2(__fmul_rn(cv0, cv0), __fmul_rn(cv1, cv1));
-        } else {
-            b = mk2(speed2_slow(A, e, tau, xs.x, yv), speed2_slow(A, e, tau, xs.y, yv));
+        int cnt0 = 0, cnt1 = 0;
+        float cd0 = 0.0f, cd1 = 0.0f;
+#pragma unroll 1
+        for (int a = 0; a < nact; ++a) {
+            const float4 p = *reinterpret_cast<const float4 *>(&smf[C::CYL_OFF + (a * 3 + tau) * 4]);  // px, py, r^2, c
+            const float dy = __fsub_rn(yv, p.y);
+            const float dy2 = __fmul_rn(dy, dy);
+            if (dy2 >= p.z) continue;  // warp-uniform: the row misses this cylinder
+            const float dx0 = __fsub_rn(xs.x, p.x), dx1 = __fsub_rn(xs.y, p.x);
+            const bool m0 = __fadd_rn(__fmul_rn(dx0, dx0), dy2) < p.z, m1 = __fadd_rn(__fmul_rn(dx1, dx1), dy2) < p.z;
+            cnt0 += m0;
+            cnt1 += m1;
+            cd0 = __fadd_rn(cd0, m0 ? p.w : 0.0f);
+            cd1 = __fadd_rn(cd1, m1 ? p.w : 0.0f);
         }
-        sts2(uri + (tau == 0 ? C::f_bk(0) : (tau == 1 ? C::f_bk(1) : C::f_bk(2))) * LW, A.kd * b);
+        const float cv0 = __fadd_rn(cnt0 == 0 ? c0 : 0.0f, cd0), cv1 = __fadd_rn(cnt1 == 0 ? c0 : 0.0f, cd1);
+        sts2(uri + (tau == 0 ? C::f_bk(0) : (tau == 1 ? C::f_bk(1) : C::f_bk(2))) * LW, kd * mk2(__fmul_rn(cv0, cv0), __fmul_rn(cv1, cv1)));
     }
+}
+// same with every cylinder of the design (the culled list overflowed)
+template <int V>
+__device__ __noinline__ void speed_row_slow(const FusedArgs &A, int e, int uri, f2 xs, float yv) {
+    using C = Cfg<V>;
+    for (int tau = 0; tau < 3; ++tau)
+        sts2(uri + (tau == 0 ? C::f_bk(0) : (tau == 1 ? C::f_bk(1) : C::f_bk(2))) * LW,
+             A.kd * mk2(speed2_slow(A, e, tau, xs.x, yv), speed2_slow(A, e, tau, xs.y, yv)));
 }
 
 // Register state of one warp: rotating windows indexed [stage][march row & 3], one column pair per lane
-template <bool GENERAL>
 struct Regs {
     f2 Uf[4][4];  // U + f of stage state y_s (s = 0: the loaded row)
     f2 Vy[4][4];
     f2 Vx[4][4];  // s = 1..3
-    f2 aU[4], aVx[4], aVy[4];  // k1 + 2k2 + 2k3 accumulators (interior: aVx, aVy hold un-scaled differences)
-    // GENERAL only
-    f2 Px[4][4], Py[4][4], Om[4][4];
+    f2 aU[4], aVx[4], aVy[4];  // k1 + 2k2 + 2k3 accumulators (V = 0: aVx, aVy hold un-scaled differences)
+    f2 Px[4][4], Py[4][4], Om[4][4];  // SX / SY / SX && SY only
     f2 aPx[4], aPy[4], aOm[4];
-    float sy[4];  // sigma_y of the rows in flight
+    float sy[4];  // sigma_y of the rows in flight (SY only)
+    f2 P[4];      // V = 0: Psix + Psiy - Omega of the rows in flight
     f2 e_tot, e_inc, e_sc;
 };
 
@@ -286,21 +319,22 @@ struct Body {
 };
 
 // float index of this lane's pair in row 0 of the slot that holds march row rb + PH + D (D in [-4, 3])
-template <bool GENERAL, int PH, int D>
+template <int V, int PH, int D>
 __device__ __forceinline__ int slot_of(const Body &b) {
     constexpr int q = PH + D;
     static_assert(q >= -4 && q < 8, "slot offset out of range");
-    return (q >= 0 && q < 4) ? b.cur + q * Cfg<GENERAL>::SLOT_F : b.oth + (q < 0 ? q + 4 : q - 4) * Cfg<GENERAL>::SLOT_F;
+    return (q >= 0 && q < 4) ? b.cur + q * Cfg<V>::SLOT_F : b.oth + (q < 0 ? q + 4 : q - 4) * Cfg<V>::SLOT_F;
 }
 
 // One RK stage S (1..4) on march row m = r - S.  PH = r & 3.  Rows whose inputs are not loaded yet (warm-up)
 // produce values that no stored cell depends on, and stores are predicated.
 // Derivatives are kept un-scaled (differences); the 1/(2Δ) factor is folded into the coefficients.
-template <bool GENERAL, int S, int PH>
-__device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, const Body &b, Regs<GENERAL> &R, int m) {
-    using C = Cfg<GENERAL>;
+template <int V, int S, int PH>
+__device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, const Body &b, Regs &R, int m) {
+    using C = Cfg<V>;
+    constexpr bool SX = C::SX, SY = C::SY;
     constexpr int sc = (PH - S + 8) & 3, sm = (sc + 3) & 3, sp = (sc + 1) & 3, s2 = (sc + 2) & 3;  // rows m, m-1, m+1, m-2
-    const int uri = slot_of<GENERAL, PH, -S>(b);
+    const int uri = slot_of<V, PH, -S>(b);
     const float a = (S == 3) ? A.dt : A.hdt;
     const float akd = (S == 3) ? A.akd_f : A.akd_h;
     constexpr int tau = (S == 1) ? 0 : (S == 4 ? 2 : 1);
@@ -311,10 +345,11 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
     const f2 vxC = (S == 1) ? uVx : R.Vx[S - 1][sc];
     const f2 dUy = R.Uf[S - 1][sp] - R.Uf[S - 1][sm];  // in march order
     const f2 dVy = R.Vy[S - 1][sp] - R.Vy[S - 1][sm];
-    if (!GENERAL) {
+    const bool st = (unsigned)(m - c.mo0) < c.mon;  // this lane stores march row m
+    if (V == 0) {
         const f2 dUx = ddx_int(ufC), dVx = ddx_int(vxC);
         // sigma == 0 in the whole window: Psi, Omega never change within the step; P was formed on arrival
-        const f2 kU = fma2(bk, dVx + dVy, lds2(uri + C::ROW_P * LW));
+        const f2 kU = fma2(bk, dVx + dVy, WV_P_REGS ? R.P[sc] : lds2(uri + C::ROW_P * LW));
         if (S < 4) {
             R.Uf[S][sc] = fma2(sf_next, lds2(uri + C::ROW_SH * LW), fma2(a, kU, uU));
             R.Vx[S][sc] = fma2(akd, dUx, uVx);
@@ -328,77 +363,91 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
                 R.aVx[sc] = fma2(2.0f, dUx, R.aVx[sc]);
                 R.aVy[sc] = fma2(2.0f, dUy, R.aVy[sc]);
             }
-        } else if ((unsigned)(m - c.mo0) < c.mon) {
+        } else if (st) {
             float *o = c.out_e + (b.orow + (unsigned)(PH * c.rowstep));
             stg2(o, fma2(A.dt6, R.aU[sc] + kU, uU));
             stg2(o + A.plane, fma2(A.dt6kd, R.aVx[sc] + dUx, uVx));
             stg2(o + 2u * A.plane, fma2(A.dt6kd, R.aVy[sc] + dUy, uVy));
         }
     } else {
-        const float sy = R.sy[sc];
+        // dU  = bc * [b (Vxx + Vyy) + Psix + Psiy - (sx + sy) U - Omega]      (src/dynamics.jl:169-176)
+        // dVx = Ux - sx Vx; dVy = Uy - sy Vy; dPsix = b sx Vyy; dPsiy = b sy Vxx; dOmega = sx sy U
+        // with sx == 0 (no SX) or sy == 0 (no SY) the matching auxiliary fields are constant: their sum sits in ROW_P.
         const f2 sx = c.sx;
-        const f2 uPx = lds2(uri + 3 * LW), uPy = lds2(uri + 4 * LW), uOm = lds2(uri + 5 * LW);
-        const f2 vyC = R.Vy[S - 1][sc];
-        const f2 px = (S == 1) ? uPx : R.Px[S - 1][sc];
-        const f2 py = (S == 1) ? uPy : R.Py[S - 1][sc];
-        const f2 om = (S == 1) ? uOm : R.Om[S - 1][sc];
+        const float sy = SY ? R.sy[sc] : 0.0f;
         // U of the stage state without the source term (differs from U + f only inside the source's columns)
         const float sf_cur = (S == 1) ? c.sf[0] : ((S == 4) ? c.sf[2] : c.sf[1]);
         const f2 uC = (S == 1) ? uU : (c.src_win ? fma2(-sf_cur, lds2(uri + C::ROW_SH * LW), ufC) : ufC);
-        const f2 dUx = ddx_gen(c, ufC), dVx = ddx_gen(c, vxC);
-        const bool brow = c.border && m == c.nm - 1;  // warp-uniform: this is the domain's first / last row
-        // dU = bc * [b (Vxx + Vyy) + Psix + Psiy - (sx + sy) U - Omega]      (src/dynamics.jl:169)
-        const f2 ssum = sx + bc2(sy);
-        const f2 dsum = fma2(c.dirf, dVy, dVx);
-        f2 kU = c.bcm * (((fma2(bk, dsum, px) + py) - ssum * uC) - om);
+        const f2 dUx = SX ? ddx_gen(c, ufC) : ddx_int(ufC), dVx = SX ? ddx_gen(c, vxC) : ddx_int(vxC);
+        const bool brow = SY && c.border && m == c.nm - 1;  // warp-uniform: this is the domain's first / last row
+        const f2 dsum = SY ? fma2(c.dirf, dVy, dVx) : dVx + dVy;
+        f2 acc, uPx, uPy, uOm, px, py, om;
+        if (V == 3) {
+            uPx = lds2(uri + 3 * LW), uPy = lds2(uri + 4 * LW), uOm = lds2(uri + 5 * LW);
+            px = (S == 1) ? uPx : R.Px[S - 1][sc];
+            py = (S == 1) ? uPy : R.Py[S - 1][sc];
+            om = (S == 1) ? uOm : R.Om[S - 1][sc];
+            acc = ((fma2(bk, dsum, px) + py) - (sx + bc2(sy)) * uC) - om;
+        } else if (V == 1) {
+            uPx = lds2(uri + 3 * LW);
+            px = (S == 1) ? uPx : R.Px[S - 1][sc];
+            acc = (fma2(bk, dsum, px) + lds2(uri + C::ROW_P * LW)) - sx * uC;
+        } else {
+            uPy = lds2(uri + 4 * LW);
+            py = (S == 1) ? uPy : R.Py[S - 1][sc];
+            acc = (fma2(bk, dsum, py) + lds2(uri + C::ROW_P * LW)) - sy * uC;
+        }
+        f2 kU = SX ? c.bcm * acc : acc;
         if (brow) kU = bc2(0.0f);  // bc == 0 on the border rows (src/dims.jl:117-124)
-        const f2 kVx = A.kd * dUx - sx * vxC;
-        const f2 kVy = c.kdd * dUy - sy * vyC;
-        const f2 kPx = (bk * c.sxd) * dVy;
-        const f2 kPy = (sy * bk) * dVx;
-        const f2 kOm = (sy * sx) * uC;
+        const f2 kVx = SX ? A.kd * dUx - sx * vxC : A.kd * dUx;
+        const f2 kVy = SY ? c.kdd * dUy - sy * R.Vy[S - 1][sc] : A.kd * dUy;
+        f2 kPx, kPy, kOm;
+        if (SX) kPx = (bk * c.sxd) * dVy;
+        if (SY) kPy = (sy * bk) * dVx;
+        if (V == 3) kOm = (sy * sx) * uC;
         if (S < 4) {
             R.Uf[S][sc] = fma2(sf_next, lds2(uri + C::ROW_SH * LW), fma2(a, kU, uU));
             R.Vx[S][sc] = fma2(a, kVx, uVx);
             R.Vy[S][sc] = fma2(a, kVy, uVy);
-            R.Px[S][sc] = fma2(a, kPx, uPx);
-            R.Py[S][sc] = fma2(a, kPy, uPy);
-            R.Om[S][sc] = fma2(a, kOm, uOm);
+            if (SX) R.Px[S][sc] = fma2(a, kPx, uPx);
+            if (SY) R.Py[S][sc] = fma2(a, kPy, uPy);
+            if (V == 3) R.Om[S][sc] = fma2(a, kOm, uOm);
             if (S == 1) {
                 R.aU[sc] = kU;
                 R.aVx[sc] = kVx;
                 R.aVy[sc] = kVy;
-                R.aPx[sc] = kPx;
-                R.aPy[sc] = kPy;
-                R.aOm[sc] = kOm;
+                if (SX) R.aPx[sc] = kPx;
+                if (SY) R.aPy[sc] = kPy;
+                if (V == 3) R.aOm[sc] = kOm;
             } else {
                 R.aU[sc] = fma2(2.0f, kU, R.aU[sc]);
                 R.aVx[sc] = fma2(2.0f, kVx, R.aVx[sc]);
                 R.aVy[sc] = fma2(2.0f, kVy, R.aVy[sc]);
-                R.aPx[sc] = fma2(2.0f, kPx, R.aPx[sc]);
-                R.aPy[sc] = fma2(2.0f, kPy, R.aPy[sc]);
-                R.aOm[sc] = fma2(2.0f, kOm, R.aOm[sc]);
+                if (SX) R.aPx[sc] = fma2(2.0f, kPx, R.aPx[sc]);
+                if (SY) R.aPy[sc] = fma2(2.0f, kPy, R.aPy[sc]);
+                if (V == 3) R.aOm[sc] = fma2(2.0f, kOm, R.aOm[sc]);
             }
             if (brow) {
                 R.Uf[S][sp] = ghost_row(R.Uf[S][sc], R.Uf[S][sm], R.Uf[S][s2]);
                 R.Vy[S][sp] = ghost_row(R.Vy[S][sc], R.Vy[S][sm], R.Vy[S][s2]);
             }
-        } else if ((unsigned)(m - c.mo0) < c.mon) {
+        } else if (st) {
             float *o = c.out_e + (b.orow + (unsigned)(PH * c.rowstep));
             stg2(o, fma2(A.dt6, R.aU[sc] + kU, uU));
             stg2(o + A.plane, fma2(A.dt6, R.aVx[sc] + kVx, uVx));
             stg2(o + 2u * A.plane, fma2(A.dt6, R.aVy[sc] + kVy, uVy));
-            stg2(o + 3u * A.plane, fma2(A.dt6, R.aPx[sc] + kPx, uPx));
-            stg2(o + 4u * A.plane, fma2(A.dt6, R.aPy[sc] + kPy, uPy));
-            stg2(o + 5u * A.plane, fma2(A.dt6, R.aOm[sc] + kOm, uOm));
+            if (SX) stg2(o + 3u * A.plane, fma2(A.dt6, R.aPx[sc] + kPx, uPx));
+            if (SY) stg2(o + 4u * A.plane, fma2(A.dt6, R.aPy[sc] + kPy, uPy));
+            if (V == 3) stg2(o + 5u * A.plane, fma2(A.dt6, R.aOm[sc] + kOm, uOm));
         }
     }
 }
 
-template <bool GENERAL, int PH>
-__device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, int e, const Body &b, Regs<GENERAL> &R, int r,
+template <int V, int PH>
+__device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, int e, const Body &b, Regs &R, int r,
                                          const CUtensorMap *map_u, const CUtensorMap *map_sh) {
-    using C = Cfg<GENERAL>;
+    using C = Cfg<V>;
+    constexpr bool SX = C::SX, SY = C::SY;
     // 1. prefetch march row r + PF into the slot that row r + PF - RING vacated (all its readers finished >= 1 step ago)
     __syncwarp();
     {
@@ -412,9 +461,13 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
             tma_load_3d(dst, map_u, c.x0, jp, e * 12 + c.w0 * 6, bar);
             if (c.src_win) tma_load_3d(dst + C::ROW_SH * (LW * 4), map_sh, c.x0, jp, e, bar);
         }
+        if (PFL2 > 0) {
+            const int rl = r + PFL2;
+            if (c.lane2 == 0 && rl < c.nm) tma_prefetch_l2_3d(map_u, c.x0, c.jbase + c.dir * rl, e * 12 + c.w0 * 6);
+        }
     }
-    // 2. arrival of march row r: stage-0 windows, energy of the owned rows, interior pass-through of Psi/Omega,
-    //    speed field of the row
+    // 2. arrival of march row r: stage-0 windows, energy of the owned rows, pass-through of the constant
+    //    auxiliary fields, speed field of the row
     if (r >= 0 && r < c.nm) {
         mbar_wait(b.bar_c + PH * 8, b.par);
         const int uri = b.cur + PH * C::SLOT_F;
@@ -429,48 +482,68 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
             R.e_inc = fma2(Ui, Ui, R.e_inc);
             R.e_sc = fma2(d, d, R.e_sc);
         }
-        if (!GENERAL) {
-            const f2 px = lds2(uri + 3 * LW), py = lds2(uri + 4 * LW), om = lds2(uri + 5 * LW);
-            if (own) {
-                float *o = c.out_e + (b.orow + (unsigned)((PH + 4) * c.rowstep) + 3u * A.plane);
-                stg2(o, px);
-                stg2(o + A.plane, py);
-                stg2(o + 2u * A.plane, om);
+        if (V != 3) {
+            // fields that stay constant in this window: copy them to the output, keep their sum for dU
+            float *o = c.out_e + (b.orow + (unsigned)((PH + 4) * c.rowstep));
+            const f2 om = lds2(uri + 5 * LW);
+            f2 P;
+            if (V == 0) {
+                const f2 px = lds2(uri + 3 * LW), py = lds2(uri + 4 * LW);
+                if (own) stg2(o + 3u * A.plane, px), stg2(o + 4u * A.plane, py);
+                P = (px + py) - om;
+            } else if (V == 1) {
+                const f2 py = lds2(uri + 4 * LW);
+                if (own) stg2(o + 4u * A.plane, py);
+                P = py - om;
+            } else {
+                const f2 px = lds2(uri + 3 * LW);
+                if (own) stg2(o + 3u * A.plane, px);
+                P = px - om;
             }
-            sts2(uri + C::ROW_P * LW, (px + py) - om);
-        } else {
-            if (c.border && r == c.nm - 1) {  // ghost row beyond the domain border for the stage-0 windows
-                R.Uf[0][sp] = ghost_row(R.Uf[0][s0], R.Uf[0][sm], R.Uf[0][s2]);
-                R.Vy[0][sp] = ghost_row(R.Vy[0][s0], R.Vy[0][sm], R.Vy[0][s2]);
-            }
+            if (own) stg2(o + 5u * A.plane, om);
+            if (V == 0 && WV_P_REGS)
+                R.P[s0] = P;
+            else
+                sts2(uri + C::ROW_P * LW, P);
         }
-        if (c.use_bk) speed_row<GENERAL>(A, e, c.jbase + c.dir * r, uri, c.nact, c.xs);
+        if (SY && c.border && r == c.nm - 1) {  // ghost row beyond the domain border for the stage-0 windows
+            R.Uf[0][sp] = ghost_row(R.Uf[0][s0], R.Uf[0][sm], R.Uf[0][s2]);
+            R.Vy[0][sp] = ghost_row(R.Vy[0][s0], R.Vy[0][sm], R.Vy[0][s2]);
+        }
+        if (c.use_bk) {
+            const float yv = A.gp.y[min(max(A.gp.grow0 + c.jbase + c.dir * r, 0), A.gp.ny_global - 1)];
+            if (c.nact > 0)
+                speed_row<V>(uri, c.nact, c.xs, yv, A.gp.c0, A.kd);
+            else
+                speed_row_slow<V>(A, e, uri, c.xs, yv);
+        }
         // the rows rewritten above are TMA targets again RING rows later: order the generic writes before it
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (V != 0 || !WV_P_REGS || c.use_bk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     // 3. the four stages, each one row behind the previous.  Rows below 1 run unguarded (whatever they
-    //    compute is overwritten before a stored cell reads it).  In the general variant rows beyond a domain
-    //    border row must not run: they would clobber the ghost rows.
-    if (GENERAL) {
-        if (r - 1 < c.nlast) stage<GENERAL, 1, PH>(c, A, b, R, r - 1);
-        if (r - 2 < c.nlast) stage<GENERAL, 2, PH>(c, A, b, R, r - 2);
-        if (r - 3 < c.nlast) stage<GENERAL, 3, PH>(c, A, b, R, r - 3);
-        if (r - 4 < c.nlast) stage<GENERAL, 4, PH>(c, A, b, R, r - 4);
+    //    compute is overwritten before a stored cell reads it).  Rows beyond a domain border row must not
+    //    run: they would clobber the ghost rows.
+    if (SY) {
+        if (r - 1 < c.nlast) stage<V, 1, PH>(c, A, b, R, r - 1);
+        if (r - 2 < c.nlast) stage<V, 2, PH>(c, A, b, R, r - 2);
+        if (r - 3 < c.nlast) stage<V, 3, PH>(c, A, b, R, r - 3);
+        if (r - 4 < c.nlast) stage<V, 4, PH>(c, A, b, R, r - 4);
         // sigma_y of march row r: first used by stage 1 in the next iteration (its slot was row r - 4's until now)
         R.sy[PH & 3] = A.gp.sigma[min(max(A.gp.grow0 + c.jbase + c.dir * r, 0), A.gp.ny_global - 1)];
     } else {
-        stage<GENERAL, 1, PH>(c, A, b, R, r - 1);
-        stage<GENERAL, 2, PH>(c, A, b, R, r - 2);
-        stage<GENERAL, 3, PH>(c, A, b, R, r - 3);
-        stage<GENERAL, 4, PH>(c, A, b, R, r - 4);
+        stage<V, 1, PH>(c, A, b, R, r - 1);
+        stage<V, 2, PH>(c, A, b, R, r - 2);
+        stage<V, 3, PH>(c, A, b, R, r - 3);
+        stage<V, 4, PH>(c, A, b, R, r - 4);
     }
 }
 
-template <bool GENERAL>
-__global__ void __launch_bounds__(32, GENERAL ? 8 : 12)
+template <int V>
+__global__ void __launch_bounds__(32, V == 3 ? 8 : (V == 0 ? 12 : WV_OCC_STRIP))
 k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtensorMap map_u7, const __grid_constant__ CUtensorMap map_u6,
              const __grid_constant__ CUtensorMap map_sh) {
-    using C = Cfg<GENERAL>;
+    using C = Cfg<V>;
+    constexpr bool SX = C::SX, SY = C::SY;
     const int lane = threadIdx.x & 31;
     // one warp per CTA: every item-derived value below is provably CTA-uniform (uniform datapath)
     long long gw = blockIdx.x;
@@ -491,11 +564,11 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     c.want_e = c.is_tot && A.epart != nullptr;
     c.x0 = item.x0;
     c.nm = item.lb - item.la;
-    c.dir = (GENERAL && item.top) ? -1 : 1;
+    c.dir = (SY && item.top) ? -1 : 1;
     c.dirf = (float)c.dir;
     c.kdd = A.kd * c.dirf;
     c.jbase = c.dir > 0 ? item.la : item.lb - 1;
-    c.border = GENERAL && (item.top || item.bot);
+    c.border = SY && (item.top || item.bot);
     c.nlast = c.border ? c.nm : 0x7fffffff;
     c.rowstep = c.dir * (int)A.nxp;
     const int colA = item.x0 + 2 * lane, colB = colA + 1;
@@ -509,7 +582,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     c.xb = (item.x0 == 0) || (item.x0 + LW >= gp.nx);
     c.bcm = mk2((c.first_x || c.last_x) ? 0.0f : 1.0f, c.last_y ? 0.0f : 1.0f);
     c.xs = mk2(gp.x[min(colA, gp.nx - 1)], gp.x[min(colB, gp.nx - 1)]);  // columns past nx are never owned
-    c.sx = GENERAL ? mk2(gp.sigma[min(colA, gp.nx - 1)], gp.sigma[min(colB, gp.nx - 1)]) : bc2(0.0f);
+    c.sx = SX ? mk2(gp.sigma[min(colA, gp.nx - 1)], gp.sigma[min(colB, gp.nx - 1)]) : bc2(0.0f);
     c.sxd = c.dirf * c.sx;
     const float *trow = A.table + ((size_t)e * A.steps + A.step) * STAGE_ROW;
     c.sf[0] = trow[3];
@@ -575,7 +648,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     }
     c.use_bk = c.nact != 0;
 
-    Regs<GENERAL> R;
+    Regs R;
     R.e_tot = R.e_inc = R.e_sc = bc2(0.0f);
     // zero-init windows so never-consumed warm-up values are finite
 #pragma unroll
@@ -608,10 +681,10 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
         b.ring_c = c.ring_sa + half * (4 * C::SLOT_F * 4);
         b.ring_o = c.ring_sa + (half ^ 1) * (4 * C::SLOT_F * 4);
         b.par = ((k - 1) >> 1) & 1;  // march row m is use number m >> 3 of its slot
-        row_step<GENERAL, 0>(c, A, e, b, R, rb, map_u, &map_sh);
-        row_step<GENERAL, 1>(c, A, e, b, R, rb + 1, map_u, &map_sh);
-        row_step<GENERAL, 2>(c, A, e, b, R, rb + 2, map_u, &map_sh);
-        row_step<GENERAL, 3>(c, A, e, b, R, rb + 3, map_u, &map_sh);
+        row_step<V, 0>(c, A, e, b, R, rb, map_u, &map_sh);
+        row_step<V, 1>(c, A, e, b, R, rb + 1, map_u, &map_sh);
+        row_step<V, 2>(c, A, e, b, R, rb + 2, map_u, &map_sh);
+        row_step<V, 3>(c, A, e, b, R, rb + 3, map_u, &map_sh);
         b.orow += (unsigned)(4 * c.rowstep);
     }
 
@@ -668,11 +741,13 @@ __global__ void k_bbox(GridP gp, const float *__restrict__ shape, int *__restric
 
 // ---- host side -------------------------------------------------------------------------------
 struct FusedPlan {
-    Item *d_items_int = nullptr, *d_items_gen = nullptr;
-    int n_int = 0, n_gen = 0;
+    Item *d_items = nullptr;  // sorted by kernel variant
+    int off[5] = {0, 0, 0, 0, 0};  // items of variant v: [off[v], off[v+1])
     float *d_epart = nullptr;
     int *d_bb = nullptr;
-    int smem_int = 0, smem_gen = 0;
+    int smem[4] = {0, 0, 0, 0};
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // the PML variants run beside the interior kernel
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 };
 
 FusedPlan *plan_of(waves_handle *h, bool create) {
@@ -787,7 +862,7 @@ int fused_prepare(waves_handle *h) {
         add_rows(ri1, own1, false);
     }
 
-    std::vector<Item> ii, gg;
+    std::vector<Item> cls[4];
     for (auto &rr : rows)
         for (auto &cc : cols) {
             Item it;
@@ -800,32 +875,42 @@ int fused_prepare(waves_handle *h) {
             it.lb = rr.j1 + 4 > gp.ny_alloc ? gp.ny_alloc : rr.j1 + 4;
             it.top = (gp.grow0 + it.la == 0) ? 1 : 0;
             it.bot = (gp.grow0 + it.lb == gp.ny_global) ? 1 : 0;
-            bool interior = cc.interior && rr.interior && !it.top && !it.bot;
-            // rows la..lb-1 must also be inside the zero zone
-            if (interior && !(gp.grow0 + it.la >= z0 && gp.grow0 + it.lb <= z1)) interior = false;
-            (interior ? ii : gg).push_back(it);
+            // rows la..lb-1 must be inside the zero-sigma zone and away from the domain's first / last row
+            bool rows_clean = rr.interior && !it.top && !it.bot && gp.grow0 + it.la >= z0 && gp.grow0 + it.lb <= z1;
+            it.cls = (cc.interior ? 0 : 1) | (rows_clean ? 0 : 2);
+            cls[it.cls].push_back(it);
         }
-    p->n_int = (int)ii.size();
-    p->n_gen = (int)gg.size();
-    if (p->d_items_int) cudaFree(p->d_items_int);
-    if (p->d_items_gen) cudaFree(p->d_items_gen);
-    cudaMalloc((void **)&p->d_items_int, sizeof(Item) * (ii.size() + 1));
-    cudaMalloc((void **)&p->d_items_gen, sizeof(Item) * (gg.size() + 1));
-    cudaMemcpy(p->d_items_int, ii.data(), sizeof(Item) * ii.size(), cudaMemcpyHostToDevice);
-    cudaMemcpy(p->d_items_gen, gg.data(), sizeof(Item) * gg.size(), cudaMemcpyHostToDevice);
-    cudaMalloc((void **)&p->d_epart, sizeof(float) * 3 * (size_t)(ii.size() + gg.size()) * gp.n_env);
+    std::vector<Item> all;
+    for (int v = 0; v < 4; ++v) {
+        p->off[v] = (int)all.size();
+        all.insert(all.end(), cls[v].begin(), cls[v].end());
+    }
+    p->off[4] = (int)all.size();
+    if (p->d_items) cudaFree(p->d_items);
+    cudaMalloc((void **)&p->d_items, sizeof(Item) * (all.size() + 1));
+    cudaMemcpy(p->d_items, all.data(), sizeof(Item) * all.size(), cudaMemcpyHostToDevice);
+    cudaMalloc((void **)&p->d_epart, sizeof(float) * 3 * all.size() * gp.n_env);
     cudaMalloc((void **)&p->d_bb, sizeof(int) * 4);
+    for (int k = 0; k < 3; ++k) {
+        cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&p->ev_join[k], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
 
-    p->smem_gen = Cfg<true>::WARP_F * 4;
-    p->smem_int = Cfg<false>::WARP_F * 4;
-    cudaError_t ce = cudaFuncSetAttribute(k_fused_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_gen);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_int);
+    p->smem[0] = Cfg<0>::WARP_F * 4;
+    p->smem[1] = Cfg<1>::WARP_F * 4;
+    p->smem[2] = Cfg<2>::WARP_F * 4;
+    p->smem[3] = Cfg<3>::WARP_F * 4;
+    cudaError_t ce = cudaFuncSetAttribute(k_fused_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[0]);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[1]);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[2]);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[3]);
     if (ce != cudaSuccess) {
         char buf[256];
         snprintf(buf, sizeof(buf), "fused_prepare: cudaFuncSetAttribute: %s (was the library built for sm_100a?)", cudaGetErrorString(ce));
         return waves_set_error(buf);
     }
-    h->fused_smem = p->smem_int;
+    h->fused_smem = p->smem[0];
 
     // TMA descriptors
     void *fn = nullptr;
@@ -850,10 +935,14 @@ int fused_prepare(waves_handle *h) {
 void fused_release(waves_handle *h) {
     FusedPlan *p = static_cast<FusedPlan *>(h->plan);
     if (!p) return;
-    if (p->d_items_int) cudaFree(p->d_items_int);
-    if (p->d_items_gen) cudaFree(p->d_items_gen);
+    if (p->d_items) cudaFree(p->d_items);
     if (p->d_epart) cudaFree(p->d_epart);
     if (p->d_bb) cudaFree(p->d_bb);
+    for (int k = 0; k < 3; ++k) {
+        if (p->side[k]) cudaStreamDestroy(p->side[k]);
+        if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]);
+    }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     delete p;
     h->plan = nullptr;
 }
@@ -861,8 +950,8 @@ void fused_release(waves_handle *h) {
 int fused_item_counts(waves_handle *h, int *n_int, int *n_gen) {
     FusedPlan *p = plan_of(h, false);
     if (!p) return 1;
-    *n_int = p->n_int;
-    *n_gen = p->n_gen;
+    *n_int = p->off[1] - p->off[0];
+    *n_gen = p->off[4] - p->off[1];
     return 0;
 }
 
@@ -884,7 +973,7 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     A.step = step;
     A.out = h->u[h->cur ^ 1];
     A.epart = d_e3 ? p->d_epart : nullptr;
-    A.epart_stride = p->n_int + p->n_gen;
+    A.epart_stride = p->off[4];
     A.kd = h->gp.g_central[1];
     A.b0kd = h->gp.b0 * A.kd;
     A.dt = h->gp.dt;
@@ -900,22 +989,30 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     A.cull = (dbg_flags & 4) ? 0 : 1;
     static const int dbg_skip = getenv("WAVES_DEBUG_SKIP") ? atoi(getenv("WAVES_DEBUG_SKIP")) : 0;  // developer bisecting aid
     if (h->profile) cudaEventRecord(h->ev0, h->stream);
-    // two warps (= CTAs) per item and environment: the total and the incident wavefield
-    if (p->n_int > 0 && !(dbg_skip & 1)) {
-        A.items = p->d_items_int;
-        A.n_items = p->n_int;
-        A.epart_off = 0;
-        const long long warps = 2LL * p->n_int * h->gp.n_env;
-        k_fused_step<false><<<(unsigned)warps, 32, p->smem_int, h->stream>>>(A, h->map_u[h->cur], h->map_u6[h->cur], h->map_shape);
+    // two warps (= CTAs) per item and environment: the total and the incident wavefield.  The PML variants are
+    // launched on side streams (fork / join with events) so their CTAs fill the tail of the interior kernel.
+    A.items = p->d_items;
+    const bool fork = !(dbg_flags & 16);
+    if (fork) cudaEventRecord(p->ev_fork, h->stream);
+    for (int v = 3; v >= 0; --v) {
+        const int n = p->off[v + 1] - p->off[v];
+        if (n == 0 || ((dbg_skip >> v) & 1)) continue;
+        A.n_items = n;
+        A.epart_off = p->off[v];
+        A.items = p->d_items + p->off[v];
+        const unsigned grid = (unsigned)(2LL * n * h->gp.n_env);
+        cudaStream_t st = (v == 0 || !fork) ? h->stream : p->side[v - 1];
+        if (st != h->stream) cudaStreamWaitEvent(st, p->ev_fork, 0);
+        const CUtensorMap &m7 = h->map_u[h->cur], &m6 = h->map_u6[h->cur];
+        if (v == 0) k_fused_step<0><<<grid, 32, p->smem[0], st>>>(A, m7, m6, h->map_shape);
+        if (v == 1) k_fused_step<1><<<grid, 32, p->smem[1], st>>>(A, m7, m6, h->map_shape);
+        if (v == 2) k_fused_step<2><<<grid, 32, p->smem[2], st>>>(A, m7, m6, h->map_shape);
+        if (v == 3) k_fused_step<3><<<grid, 32, p->smem[3], st>>>(A, m7, m6, h->map_shape);
         h->launches++;
-    }
-    if (p->n_gen > 0 && !(dbg_skip & 2)) {
-        A.items = p->d_items_gen;
-        A.n_items = p->n_gen;
-        A.epart_off = p->n_int;
-        const long long warps = 2LL * p->n_gen * h->gp.n_env;
-        k_fused_step<true><<<(unsigned)warps, 32, p->smem_gen, h->stream>>>(A, h->map_u[h->cur], h->map_u6[h->cur], h->map_shape);
-        h->launches++;
+        if (st != h->stream) {
+            cudaEventRecord(p->ev_join[v - 1], st);
+            cudaStreamWaitEvent(h->stream, p->ev_join[v - 1], 0);
+        }
     }
     if (h->profile) {
         cudaEventRecord(h->ev1, h->stream);
@@ -926,7 +1023,7 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
         h->fused_launches++;
     }
     if (d_e3) {
-        k_energy_reduce<<<h->gp.n_env, 256, 0, h->stream>>>(p->d_epart, p->n_int + p->n_gen, h->d_omega, d_e3, 3 * (steps + 1));
+        k_energy_reduce<<<h->gp.n_env, 256, 0, h->stream>>>(p->d_epart, p->off[4], h->d_omega, d_e3, 3 * (steps + 1));
         h->launches++;
     }
     h->cur ^= 1;
