@@ -119,6 +119,22 @@ int waves_step(waves_handle *h, float t, int mode);
 int waves_integrate(waves_handle *h, const float *tspan, int steps, int mode, float *energy, const int32_t *save_steps,
                     int nsave, float *frames, float *u_tot_traj, float *u_inc_traj);
 
+/*
+ * rrule(::Integrator, z0, t, θ) + adjoint_sensitivity (src/dynamics.jl:97-128) for the 2-D dynamics: runs the forward
+ * integration from the handle's current state (storing all steps+1 states on the device, like the reference), then the
+ * reverse sweep.  The loss is
+ *     L = sum_i sum_k w_energy[i][k] * E_k(z_i)  +  <dL_dzN, z_N>          E = {tot, inc, sc} of src/env.jl:104-111
+ *   w_energy   HOST, nullable, (steps+1, 3)           dL_dzN   nullable, (n_env, 12, ny, nx) extra cotangent of the last state
+ *   dL_dz0     out, (n_env, 12, ny, nx)               dL_dc    out, nullable, (n_env, ny, nx): sensitivity to the speed
+ *              plane of the total field (a time-constant perturbation, accumulated over every RK stage; the hard cylinder
+ *              mask of src/designs.jl:99-104 has no derivative, so no design-parameter gradient exists in the reference)
+ *   loss       out, nullable, HOST (n_env): the energy part of L
+ *   fwd_mode   WAVES_MODE_FUSED / WAVES_MODE_EXACT for the forward pass;  adj_mode  WAVES_ADJ_EXACT / WAVES_ADJ_COMPAT
+ * Not available on slab handles.
+ */
+int waves_adjoint(waves_handle *h, const float *tspan, int steps, int fwd_mode, int adj_mode, const float *w_energy,
+                  const float *dL_dzN, float *dL_dz0, float *dL_dc, float *loss);
+
 /* tot/inc/sc energy of the current state (src/env.jl:104-111): e3 (n_env, 3). */
 int waves_energy(waves_handle *h, float *e3);
 

@@ -9,6 +9,6 @@ NV="/usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a
 while [ $# -ge 2 ]; do
   tag=$1; flags=$2; shift 2
   $NV $flags -Xptxas -v -c -o $OUT/fused_$tag.o kernels_fused.cu 2> $OUT/fused_$tag.ptxas.log
-  $NV -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libwaves_b200_$tag.so kernels_exact.o $OUT/fused_$tag.o waves_abi.o -lcudart_static -lpthread -ldl -lrt
+  $NV -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libwaves_b200_$tag.so kernels_exact.o kernels_adjoint.o $OUT/fused_$tag.o waves_abi.o -lcudart_static -lpthread -ldl -lrt
   echo "$tag: $(grep -E 'Used [0-9]+ registers' $OUT/fused_$tag.ptxas.log | head -4 | sed 's/ptxas info    : Used //; s/ registers.*//' | tr '\n' ' ')"
 done

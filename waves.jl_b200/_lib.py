@@ -52,6 +52,8 @@ SYMBOLS = {
     "waves_integrate": (C.c_int, [C.c_void_p, fp, C.c_int, C.c_int, C.c_void_p, ip, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
     "waves_energy": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "waves_adjoint": (C.c_int, [C.c_void_p, fp, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
     "waves_halo_describe": (C.c_int, [C.c_void_p, C.POINTER(HaloDesc)]),
     "waves_halo_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "waves_halo_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,0 +1,124 @@
+// Reverse pass of the integrator: adjoint_sensitivity / rrule(::Integrator) (src/dynamics.jl:97-128) for the 2-D
+// AcousticDynamics (src/dynamics.jl:151-188).  One kernel applies the TRANSPOSED right-hand side
+//   (J^T λ)_U  = -(σx+σy) m λU + Dx^T λVx + Dy^T λVy + σxσy λΩ          m = Dirichlet mask (src/dims.jl:117-124)
+//   (J^T λ)_Vx = Dx^T[b (m λU + σy λΨy)] - σx λVx
+//   (J^T λ)_Vy = Dy^T[b (m λU + σx λΨx)] - σy λVy
+//   (J^T λ)_Ψx = (J^T λ)_Ψy = m λU ;  (J^T λ)_Ω = -m λU
+// and accumulates the sensitivity to the speed plane of the total field,
+//   dL/dc += 2 c [ m λU (DxVx + DyVy) + σx λΨx DyVy + σy λΨy DxVx ]      (derivatives of the forward stage state),
+// where D is the 3-band matrix of src/operators.jl:10-22 with its one-sided first / last rows and D^T its transpose.
+// The step-level reverse of runge_kutta (src/dynamics.jl:9-16) is orchestrated in waves_abi.cu (waves_adjoint).
+// Checked in tests/test_gpu_adjoint.py against an independent autodiff of the forward program.  sm_100a only.
+#include "waves_internal.h"
+
+namespace {
+
+// coefficient of v[r] in (D^T v)[i]: D[r][i]
+struct Band {
+    float gf[3], gc[2], gl[3];
+    int n;
+    // sum over rows r of D[r][i] * v(r), v given by a callable on the row index
+    template <class F>
+    __device__ __forceinline__ float transposed(int i, F v) const {
+        float acc = 0.0f;
+        if (i + 1 <= n - 2) acc += gc[0] * v(i + 1);          // interior row r = i+1 holds gc[0] on column r-1
+        if (i - 1 >= 1) acc += gc[1] * v(i - 1);              // interior row r = i-1 holds gc[1] on column r+1
+        if (i <= 2) acc += gf[i] * v(0);                      // first row: columns 0,1,2
+        if (i >= n - 3) acc += gl[i - (n - 3)] * v(n - 1);    // last row: columns n-3,n-2,n-1
+        return acc;
+    }
+    template <class F>
+    __device__ __forceinline__ float forward(int i, F v) const {
+        if (i == 0) return gf[0] * v(0) + gf[1] * v(1) + gf[2] * v(2);
+        if (i == n - 1) return gl[0] * v(n - 3) + gl[1] * v(n - 2) + gl[2] * v(n - 1);
+        return gc[0] * v(i - 1) + gc[1] * v(i + 1);
+    }
+};
+
+// blockIdx.z = env * 2 + wavefield.  lam, y, out: [n_env][12][plane]; b2: [n_env][plane] or nullptr (scalar c0^2);
+// gcacc: [n_env][plane] or nullptr.
+__global__ void __launch_bounds__(256)
+k_rhs_transposed(GridP gp, const float *__restrict__ lam, const float *__restrict__ y, const float *__restrict__ b2,
+                 float *__restrict__ out, float *__restrict__ gcacc) {
+    const int e = blockIdx.z >> 1, w = blockIdx.z & 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= gp.nx || j >= gp.ny_own) return;
+    const long long P = gp.plane;
+    const int nxp = gp.nxp, nx = gp.nx, ny = gp.ny_global;
+    const float *L = lam + (long long)e * gp.env_stride + (long long)w * 6 * P;
+    float *O = out + (long long)e * gp.env_stride + (long long)w * 6 * P;
+    const float *bpl = (w == 0 && b2) ? b2 + (long long)e * P : nullptr;
+    Band bx{{gp.g_first[0], gp.g_first[1], gp.g_first[2]}, {gp.g_central[0], gp.g_central[1]}, {gp.g_last[0], gp.g_last[1], gp.g_last[2]}, nx};
+    Band by = bx;
+    by.n = ny;
+    auto mask = [&](int ii, int jj) { return (ii == 0 || ii == nx - 1 || jj == 0 || jj == ny - 1) ? 0.0f : 1.0f; };
+    auto bval = [&](int ii, int jj) { return bpl ? bpl[(long long)jj * nxp + ii] : gp.b0; };
+    auto at = [&](int f, int ii, int jj) { return L[(long long)f * P + (long long)jj * nxp + ii]; };
+    const float sx = gp.sigma[i], sy = gp.sigma[j];
+    const long long q = (long long)j * nxp + i;
+    const float lU = L[q], lVx = L[P + q], lVy = L[2 * P + q], lPx = L[3 * P + q], lPy = L[4 * P + q], lOm = L[5 * P + q];
+    const float mU = mask(i, j) * lU;
+    // Dx^T along i (row j fixed), Dy^T along j (column i fixed)
+    const float dxT_lVx = bx.transposed(i, [&](int r) { return at(1, r, j); });
+    const float dyT_lVy = by.transposed(j, [&](int r) { return at(2, i, r); });
+    const float dxT_qx = bx.transposed(i, [&](int r) { return bval(r, j) * (mask(r, j) * at(0, r, j) + sy * at(4, r, j)); });
+    const float dyT_qy = by.transposed(j, [&](int r) { return bval(i, r) * (mask(i, r) * at(0, i, r) + sx * at(3, i, r)); });
+    O[q] = -(sx + sy) * mU + dxT_lVx + dyT_lVy + (sx * sy) * lOm;
+    O[P + q] = dxT_qx - sx * lVx;
+    O[2 * P + q] = dyT_qy - sy * lVy;
+    O[3 * P + q] = mU;
+    O[4 * P + q] = mU;
+    O[5 * P + q] = -mU;
+    if (w == 0 && gcacc) {
+        const float *Y = y + (long long)e * gp.env_stride;
+        const float Vxx = bx.forward(i, [&](int r) { return Y[P + (long long)j * nxp + r]; });
+        const float Vyy = by.forward(j, [&](int r) { return Y[2 * P + (long long)r * nxp + i]; });
+        const float gb = mU * (Vxx + Vyy) + (sx * lPx) * Vyy + (sy * lPy) * Vxx;
+        const float b = bval(i, j);
+        gcacc[(long long)e * P + q] += 2.0f * sqrtf(b) * gb;
+    }
+}
+
+// out = a*x + b*y + c*z (y, z nullable); elementwise over the whole state
+__global__ void k_lin3(long long n, float *__restrict__ out, float a, const float *__restrict__ x, float b, const float *__restrict__ y,
+                       float c, const float *__restrict__ z) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    float v = a * x[q];
+    if (y) v += b * y[q];
+    if (z) v += c * z[q];
+    out[q] = v;
+}
+
+// w += dL/dz_i of the energy-weighted loss sum_k w3[k] E_k (src/env.jl:104-111): only the two U planes are touched
+__global__ void k_energy_cotangent(GridP gp, const float *__restrict__ z, float *__restrict__ w, float w_tot, float w_inc, float w_sc,
+                                   float d_omega) {
+    const int e = blockIdx.z;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= gp.nx || j >= gp.ny_own) return;
+    const long long q = (long long)e * gp.env_stride + (long long)j * gp.nxp + i;
+    const float ut = z[q], ui = z[q + 6 * gp.plane], d = ut - ui;
+    const float two = 2.0f * d_omega;
+    w[q] += two * (w_tot * ut + w_sc * d);
+    w[q + 6 * gp.plane] += two * (w_inc * ui - w_sc * d);
+}
+
+}  // namespace
+
+void launch_rhs_transposed(waves_handle *h, const float *lam, const float *y, const float *b2, float *out, float *gcacc) {
+    dim3 blk(32, 8), grd((h->gp.nx + 31) / 32, (h->gp.ny_own + 7) / 8, h->gp.n_env * 2);
+    k_rhs_transposed<<<grd, blk, 0, h->stream>>>(h->gp, lam, y, b2, out, gcacc);
+    h->launches++;
+}
+
+void launch_lin3(waves_handle *h, float *out, float a, const float *x, float b, const float *y, float c, const float *z) {
+    const long long n = h->gp.env_stride * h->gp.n_env;
+    k_lin3<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, out, a, x, b, y, c, z);
+    h->launches++;
+}
+
+void launch_energy_cotangent(waves_handle *h, const float *z, float *w, const float *w3) {
+    dim3 blk(32, 8), grd((h->gp.nx + 31) / 32, (h->gp.ny_own + 7) / 8, h->gp.n_env);
+    k_energy_cotangent<<<grd, blk, 0, h->stream>>>(h->gp, z, w, w3[0], w3[1], w3[2], h->d_omega);
+    h->launches++;
+}

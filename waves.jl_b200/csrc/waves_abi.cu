@@ -128,6 +128,9 @@ static void free_handle(waves_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int k = 0; k < 9; ++k)
+        if (h->adj[k]) cudaFree(h->adj[k]);
+    if (h->traj) cudaFree(h->traj);
     float **bufs[] = {&h->u[0], &h->u[1], &h->k,      &h->ys,     &h->acc,    &h->b2,     &h->shape,  &h->cplane,
                       &h->d_x,  &h->d_y,  &h->d_sigma, &h->d_cyl0, &h->d_cyl1, &h->d_tspan, &h->d_stage, &h->d_energy};
     for (auto b : bufs)
@@ -586,6 +589,147 @@ extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, i
     if (energy)
         CU_TRY(cudaMemcpyAsync(energy, h->d_energy, sizeof(float) * 3 * (size_t)(steps + 1) * gp.n_env, cudaMemcpyDefault,
                                h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+
+// ---- reverse pass -----------------------------------------------------------------------------
+extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int fwd_mode, int adj_mode,
+                             const float *w_energy, const float *dL_dzN, float *dL_dz0, float *dL_dc, float *loss) {
+    CHECK_H(h);
+    const GridP &gp = h->gp;
+    if (!tspan || steps < 1 || !dL_dz0) return fail("waves_adjoint: need tspan, steps >= 1 and dL_dz0");
+    if (gp.ny_own != gp.ny_global) return fail("waves_adjoint: not available on slab handles");
+    if (adj_mode != WAVES_ADJ_EXACT && adj_mode != WAVES_ADJ_COMPAT) return fail("waves_adjoint: unknown adjoint mode %d", adj_mode);
+    const size_t state = (size_t)gp.env_stride * gp.n_env, planes = (size_t)gp.plane * gp.n_env;
+    // scratch: 0 w, 1 wsum, 2 lk, 3 ly, 4 y1, 5 y2, 6 y3 (state-sized); 7: three b^2 planes; 8: dL/dc
+    for (int k = 0; k < 7; ++k)
+        if (!h->adj[k]) CU_TRY(cudaMalloc((void **)&h->adj[k], sizeof(float) * state));
+    if (!h->adj[7]) CU_TRY(cudaMalloc((void **)&h->adj[7], sizeof(float) * 3 * planes));
+    if (!h->adj[8]) CU_TRY(cudaMalloc((void **)&h->adj[8], sizeof(float) * planes));
+    if (h->traj_cap < steps + 1) {
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        if (h->traj) cudaFree(h->traj);
+        h->traj = nullptr;
+        h->traj_cap = 0;
+        cudaError_t ce = cudaMalloc((void **)&h->traj, sizeof(float) * state * (size_t)(steps + 1));
+        if (ce != cudaSuccess)
+            return fail("waves_adjoint: cannot store %d states of %.1f MB on the device (%s)", steps + 1, state * 4e-6,
+                        cudaGetErrorString(ce));
+        h->traj_cap = steps + 1;
+    }
+    float *W = h->adj[0], *WS = h->adj[1], *LK = h->adj[2], *LY = h->adj[3];
+    float *Y[3] = {h->adj[4], h->adj[5], h->adj[6]};
+    float *B2[3] = {h->adj[7], h->adj[7] + planes, h->adj[7] + 2 * planes};
+    float *GC = h->adj[8];
+    if (ensure_exact_scratch(h)) return 1;
+
+    // ---- forward: (iter::Integrator)(z0, t, θ), every state kept (src/dynamics.jl:121) ----
+    // the stage table gets steps+1 rows: the reference's loop also pulls back through a step taken at t_N
+    const int rows = steps + 1;
+    if (ensure_stage(h, rows + 1) || flush_params(h)) return 1;
+    if (h->energy_cap < rows) {
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        if (h->d_energy) cudaFree(h->d_energy);
+        h->energy_cap = rows < 128 ? 128 : rows;
+        CU_TRY(cudaMalloc((void **)&h->d_energy, sizeof(float) * 3 * (size_t)h->energy_cap * gp.n_env));
+    }
+    {
+        std::vector<float> ts(rows + 1);
+        memcpy(ts.data(), tspan, sizeof(float) * rows);
+        ts[rows] = tspan[steps];
+        CU_TRY(cudaMemcpyAsync(h->d_tspan, ts.data(), sizeof(float) * rows, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+    }
+    launch_stage_table(h, h->d_tspan, rows, h->d_stage);
+    CU_TRY(cudaMemcpyAsync(h->traj, h->u[h->cur], sizeof(float) * state, cudaMemcpyDeviceToDevice, h->stream));
+    for (int n = 0; n < steps; ++n) {
+        if (step_any(h, rows, n, fwd_mode, nullptr)) return 1;
+        CU_TRY(cudaMemcpyAsync(h->traj + (size_t)(n + 1) * state, h->u[h->cur], sizeof(float) * state, cudaMemcpyDeviceToDevice,
+                               h->stream));
+    }
+    if (loss) {
+        std::vector<float> e3((size_t)3 * gp.n_env);
+        for (int e = 0; e < gp.n_env; ++e) loss[e] = 0.0f;
+        std::vector<double> acc(gp.n_env, 0.0);
+        for (int i = 0; i <= steps && w_energy; ++i) {
+            const float *w3 = w_energy + 3 * i;
+            if (w3[0] == 0.0f && w3[1] == 0.0f && w3[2] == 0.0f) continue;
+            launch_energy(h, h->traj + (size_t)i * state, h->d_energy, 3);
+            CU_TRY(cudaMemcpyAsync(e3.data(), h->d_energy, sizeof(float) * 3 * gp.n_env, cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            for (int e = 0; e < gp.n_env; ++e)
+                acc[e] += (double)w3[0] * e3[3 * e] + (double)w3[1] * e3[3 * e + 1] + (double)w3[2] * e3[3 * e + 2];
+        }
+        for (int e = 0; e < gp.n_env; ++e) loss[e] = (float)acc[e];
+    }
+
+    // ---- reverse sweep ----
+    const bool sp = any_speed_plane(h);
+    const float dt = gp.dt, hdt = gp.hdt, s6 = dt / 6.0f, s3 = dt / 3.0f;
+    CU_TRY(cudaMemsetAsync(GC, 0, sizeof(float) * planes, h->stream));
+    CU_TRY(cudaMemsetAsync(W, 0, sizeof(float) * state, h->stream));
+    auto add_cotangent = [&](int i) -> int {  // W += a_i
+        if (w_energy) {
+            const float *w3 = w_energy + 3 * i;
+            if (w3[0] != 0.0f || w3[1] != 0.0f || w3[2] != 0.0f) launch_energy_cotangent(h, h->traj + (size_t)i * state, W, w3);
+        }
+        if (i == steps && dL_dzN) {
+            // LK <- the caller's cotangent in the pitched layout, W += LK
+            CU_TRY(cudaMemsetAsync(LK, 0, sizeof(float) * state, h->stream));
+            for (int e = 0; e < gp.n_env; ++e)
+                if (copy_planes_fast(h, LK + (size_t)e * gp.env_stride, dL_dzN + (size_t)e * 12 * gp.ny_own * gp.nx, nullptr, 12))
+                    return 1;
+            launch_lin3(h, W, 1.0f, W, 1.0f, LK, 0.0f, nullptr);
+        }
+        return 0;
+    };
+    // W <- W + J_step(z_i, t_i)^T W, dL/dc accumulated: the pullback of one runge_kutta call (src/dynamics.jl:105-107)
+    auto step_vjp = [&](int i) {
+        const float *z = h->traj + (size_t)i * state;
+        if (sp)
+            for (int tau = 0; tau < 3; ++tau) launch_speed2(h, 0, gp.n_env, h->d_stage, rows, i, tau == 0 ? 0 : (tau == 1 ? 1 : 3), B2[tau]);
+        float *saved_b2 = h->b2;
+        // forward stage states y1, y2, y3 (k4 is not needed)
+        for (int s = 0; s < 3; ++s) {
+            h->b2 = B2[s == 0 ? 0 : 1];
+            launch_rhs_exact(h, 0, gp.n_env, s == 0 ? z : Y[s - 1], h->k, h->d_stage, rows, i, s);
+            launch_lin3(h, Y[s], 1.0f, z, s == 2 ? dt : hdt, h->k, 0.0f, nullptr);
+        }
+        h->b2 = saved_b2;
+        const float *b0 = sp ? B2[0] : nullptr, *b1 = sp ? B2[1] : nullptr, *b2p = sp ? B2[2] : nullptr;
+        float *gc = dL_dc ? GC : nullptr;
+        launch_lin3(h, LK, s6, W, 0.0f, nullptr, 0.0f, nullptr);
+        launch_rhs_transposed(h, LK, Y[2], b2p, LY, gc);          // λ_y3 = J4^T λ_k4
+        launch_lin3(h, WS, 1.0f, W, 1.0f, LY, 0.0f, nullptr);
+        launch_lin3(h, LK, s3, W, dt, LY, 0.0f, nullptr);         // λ_k3 = dt/3 w + dt λ_y3
+        launch_rhs_transposed(h, LK, Y[1], b1, LY, gc);           // λ_y2 = J3^T λ_k3
+        launch_lin3(h, WS, 1.0f, WS, 1.0f, LY, 0.0f, nullptr);
+        launch_lin3(h, LK, s3, W, hdt, LY, 0.0f, nullptr);        // λ_k2 = dt/3 w + dt/2 λ_y2
+        launch_rhs_transposed(h, LK, Y[0], b1, LY, gc);           // λ_y1 = J2^T λ_k2
+        launch_lin3(h, WS, 1.0f, WS, 1.0f, LY, 0.0f, nullptr);
+        launch_lin3(h, LK, s6, W, hdt, LY, 0.0f, nullptr);        // λ_k1 = dt/6 w + dt/2 λ_y1
+        launch_rhs_transposed(h, LK, z, b0, LY, gc);              // λ_z = J1^T λ_k1
+        launch_lin3(h, W, 1.0f, WS, 1.0f, LY, 0.0f, nullptr);
+    };
+    if (adj_mode == WAVES_ADJ_EXACT) {
+        if (add_cotangent(steps)) return 1;            // λ_N = a_N
+        for (int i = steps - 1; i >= 0; --i) {         // λ_i = a_i + (I + J_i^T) λ_{i+1}
+            step_vjp(i);
+            if (add_cotangent(i)) return 1;
+        }
+    } else {
+        for (int i = steps; i >= 0; --i) {             // the loop as written: acc = (I + J_i^T)(acc + a_i), i = N..0
+            if (add_cotangent(i)) return 1;
+            step_vjp(i);
+        }
+    }
+    for (int e = 0; e < gp.n_env; ++e) {
+        if (copy_planes_fast(h, W + (size_t)e * gp.env_stride, nullptr, dL_dz0 + (size_t)e * 12 * gp.ny_own * gp.nx, 12)) return 1;
+        if (dL_dc && copy_planes_fast(h, GC + (size_t)e * gp.plane, nullptr, dL_dc + (size_t)e * gp.ny_own * gp.nx, 1)) return 1;
+    }
     CU_TRY(cudaStreamSynchronize(h->stream));
     CU_TRY(cudaGetLastError());
     return 0;

@@ -49,6 +49,9 @@ struct waves_handle {
     float *b2;            // exact-mode c^2 plane per env [n_env][plane], lazily allocated
     float *shape;         // [n_env][plane] source shape (zeros when NoSource)
     float *cplane;        // [n_env][plane] fixed speed plane, lazily allocated
+    float *adj[9];        // adjoint scratch: w, wsum, lk, ly, y1, y2, y3 (state-sized), b2 planes x3 (one block), dL/dc
+    float *traj;          // stored forward trajectory [(steps+1)][state]
+    long long traj_cap;   // frames
     float *d_x, *d_y, *d_sigma;
     EnvParams *h_env, *d_env;
     bool env_dirty;
@@ -89,6 +92,11 @@ void launch_rk_final(waves_handle *h, const float *u_in, const float *acc, float
 void launch_energy(waves_handle *h, const float *u, float *d_e3, int frame_stride3);
 void launch_pack_halo(waves_handle *h, const float *u, float *lo, float *hi);
 void launch_unpack_halo(waves_handle *h, float *u, const float *lo, const float *hi);
+
+// ---- kernels_adjoint.cu ----
+void launch_rhs_transposed(waves_handle *h, const float *lam, const float *y, const float *b2, float *out, float *gcacc);
+void launch_lin3(waves_handle *h, float *out, float a, const float *x, float b, const float *y, float c, const float *z);
+void launch_energy_cotangent(waves_handle *h, const float *z, float *w, const float *w3 /*host, 3 weights*/);
 
 // ---- kernels_fused.cu ----
 int fused_prepare(waves_handle *h);  // work items, tensor maps, smem attribute; 0 on success

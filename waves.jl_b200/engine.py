@@ -10,6 +10,7 @@ from ._lib import check
 
 F32 = np.float32
 MODE_FUSED, MODE_EXACT = 0, 1
+ADJ_EXACT, ADJ_COMPAT = 0, 1
 
 
 def _ptr(a):
@@ -107,6 +108,21 @@ class Engine:
                                          ss.ctypes.data_as(_lib.ip) if len(ss) else None, len(ss), _ptr(frames),
                                          _ptr(u_tot), _ptr(u_inc)))
         return en, frames
+
+    def adjoint(self, tspan, w_energy=None, dL_dzN=None, fwd_mode=MODE_FUSED, adj_mode=ADJ_EXACT, want_dc=True):
+        """rrule(::Integrator) + adjoint_sensitivity (src/dynamics.jl:97-128) from the current state.
+        Returns (loss (n_env,), dL/dz0 (n_env,12,ny,nx), dL/dc (n_env,ny,nx) | None)."""
+        ts = np.ascontiguousarray(tspan, F32)
+        steps = len(ts) - 1
+        we = None if w_energy is None else np.ascontiguousarray(w_energy, F32)
+        assert we is None or we.shape == (steps + 1, 3)
+        an = None if dL_dzN is None else np.ascontiguousarray(dL_dzN, F32)
+        gz = np.empty((self.n_env, 12, self.ny, self.nx), dtype=F32)
+        gc = np.empty((self.n_env, self.ny, self.nx), dtype=F32) if want_dc else None
+        loss = np.zeros(self.n_env, dtype=F32)
+        check(_lib.lib().waves_adjoint(self._h, ts.ctypes.data_as(_lib.fp), steps, fwd_mode, adj_mode, _ptr(we), _ptr(an),
+                                       _ptr(gz), _ptr(gc), _ptr(loss)))
+        return loss, gz, gc
 
     def energy(self):
         out = np.empty((self.n_env, 3), dtype=F32)

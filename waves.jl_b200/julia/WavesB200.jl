@@ -110,6 +110,25 @@ function integrate!(h::Handle, tspan::Vector{Float32}, nx::Int, ny::Int; save_st
     return energy, frames
 end
 
+"""
+    adjoint!(h, tspan, nx, ny; w_energy, dL_dzN, fwd_mode, adj_mode)
+
+rrule(::Integrator, z0, t, θ) + adjoint_sensitivity (src/dynamics.jl:97-128) from the handle's current state for the
+loss  L = Σᵢ Σₖ w_energy[k, i] Eₖ(zᵢ) + ⟨dL_dzN, z_N⟩.  `adj_mode = 0` is the exact discrete adjoint, `1` the reference
+loop as written.  Returns `(loss, ∂L/∂z0 (nx,ny,12), ∂L/∂c (nx,ny))` for a single-environment handle.
+"""
+function adjoint!(h::Handle, tspan::Vector{Float32}, nx::Int, ny::Int; w_energy = C_NULL, dL_dzN = C_NULL,
+                  fwd_mode::Cint = MODE_FUSED, adj_mode::Cint = Cint(0))
+    steps = length(tspan) - 1
+    gz = Array{Float32}(undef, nx, ny, 12)
+    gc = Array{Float32}(undef, nx, ny)
+    loss = zeros(Float32, 1)
+    check(h.lib, ccall((:waves_adjoint, h.lib), Cint,
+                       (Ptr{Cvoid}, Ptr{Float32}, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+                       h.ptr, tspan, steps, fwd_mode, adj_mode, w_energy, dL_dzN, gz, gc, loss))   # w_energy: (3, steps+1) column-major
+    return loss[1], gz, gc
+end
+
 # ---- seam B2: (iter::Integrator)(ui, tspan, θ) for the parameterised θ the environment builds -------------
 """Drop-in for `iter(ui, tspan, [C, F])` when C is the design interpolation of `(env::WaveEnv)(action)`
 (src/env.jl:96-99): pass the DesignInterpolator (or `nothing` for a constant c0) instead of the closure."""
