@@ -207,7 +207,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_fused_step<interior> + k_fused_step<general> (one RK4 step of the whole batch)",
+                         "kernel": "k_fused_step<V=0..3> launch set (interior + PML strips + corners): one RK4 step of the whole batch",
                          "launch_us": round(per_launch_s * 1e6, 1)},
             "clocks": clocks,
         }
