@@ -85,7 +85,7 @@ struct Cfg {
     static constexpr int SLOT_F = SLOT_ROWS * LW;
     static constexpr int RING_F = RING * SLOT_F;
     static constexpr int CYL_OFF = RING_F;
-    static constexpr int BAR_OFF = CYL_OFF + CYL_CAP * 12;
+    static constexpr int BAR_OFF = CYL_OFF + CYL_CAP * 16;  // per culled cylinder: (px, py, r^2, c) x 3 stage times + (y_mid, reach^2, -, -)
     static constexpr int WARP_F = ((BAR_OFF + RING * 2) + 31) & ~31;  // floats per warp (128-byte multiple)
     // row holding kd*c^2 at stage-time index tau
     __host__ __device__ static constexpr int f_bk(int tau) { return V != 0 ? (tau == 0 ? 6 : 7 + tau) : 4 + tau; }
@@ -162,14 +162,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!done && ++spins > (1u << 22)) __trap();
     } while (!done);
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+// One elected lane arms the mbarrier with `bytes` and issues the TMA load(s) of a row: the state planes and, when
+// `with_shape`, the source-shape row.  Every operand is warp-uniform; the whole warp executes this (no divergence).
+__device__ __forceinline__ void tma_issue_row(uint32_t bar, uint32_t bytes, uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                              bool with_shape, uint32_t dst_sh, const CUtensorMap *map_sh, int e) {
     asm volatile(
+        "{\n"
+        ".reg .pred pe, ps;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.and.b32 ps, %9, 0, pe;\n"
+        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
 #if WV_TMA_CTA
-        "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "@pe cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%2], [%3, {%4, %5, %6}], [%0];\n"
+        "@ps cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%7], [%8, {%4, %5, %10}], [%0];\n"
 #else
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3, {%4, %5, %6}], [%0];\n"
+        "@ps cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%7], [%8, {%4, %5, %10}], [%0];\n"
 #endif
-        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        "}\n" ::"r"(bar),
+        "r"(bytes), "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(dst_sh), "l"(map_sh), "r"((int)with_shape), "r"(e)
         : "memory");
 }
 // HBM -> L2 only: keeps more bytes in flight than the shared-memory ring could hold
@@ -209,6 +220,8 @@ struct WarpCtx {
     float sf[3];       // source factor at t, t+dt/2, t+dt
     uint32_t bar0, ring_sa;  // shared-window addresses of mbarrier 0 and of the ring
     int nact;          // culled cylinders (0: none touch this window, -1: list overflow -> slow loop)
+    uint32_t tx_bytes; // bytes one row's TMA loads deliver
+    float cyl_ylo, cyl_yhi;  // rows with y outside (cyl_ylo, cyl_yhi) are not touched by any culled cylinder
 };
 
 // c(x,y,t)^2 with every cylinder (list overflow), exact order of src/designs.jl:99-116
@@ -243,25 +256,31 @@ __device__ __noinline__ float speed2_slow(const FusedArgs &A, int e, int tau, fl
 template <int V>
 __device__ __noinline__ void speed_row(int uri, int nact, f2 xs, float yv, float c0, float kd) {
     using C = Cfg<V>;
+    int cnt0[3] = {0, 0, 0}, cnt1[3] = {0, 0, 0};
+    float cd0[3] = {0.f, 0.f, 0.f}, cd1[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int tau = 0; tau < 3; ++tau) {
-        int cnt0 = 0, cnt1 = 0;
-        float cd0 = 0.0f, cd1 = 0.0f;
-#pragma unroll 1
-        for (int a = 0; a < nact; ++a) {
-            const float4 p = *reinterpret_cast<const float4 *>(&smf[C::CYL_OFF + (a * 3 + tau) * 4]);  // px, py, r^2, c
+    for (int a = 0; a < nact; ++a) {
+        // meta: (y_mid, reach^2): rows farther than `reach` from y_mid miss the cylinder at all three stage times
+        const float2 meta = *reinterpret_cast<const float2 *>(&smf[C::CYL_OFF + a * 16 + 12]);
+        const float dm = yv - meta.x;
+        if (dm * dm >= meta.y) continue;  // warp-uniform
+#pragma unroll
+        for (int tau = 0; tau < 3; ++tau) {
+            const float4 p = *reinterpret_cast<const float4 *>(&smf[C::CYL_OFF + a * 16 + tau * 4]);  // px, py, r^2, c
             const float dy = __fsub_rn(yv, p.y);
             const float dy2 = __fmul_rn(dy, dy);
-            if (dy2 >= p.z) continue;  // warp-uniform: the row misses this cylinder
             const float dx0 = __fsub_rn(xs.x, p.x), dx1 = __fsub_rn(xs.y, p.x);
             const bool m0 = __fadd_rn(__fmul_rn(dx0, dx0), dy2) < p.z, m1 = __fadd_rn(__fmul_rn(dx1, dx1), dy2) < p.z;
-            cnt0 += m0;
-            cnt1 += m1;
-            cd0 = __fadd_rn(cd0, m0 ? p.w : 0.0f);
-            cd1 = __fadd_rn(cd1, m1 ? p.w : 0.0f);
+            cnt0[tau] += m0;
+            cnt1[tau] += m1;
+            cd0[tau] = __fadd_rn(cd0[tau], m0 ? p.w : 0.0f);  // adding 0.0f to a non-negative sum is exact
+            cd1[tau] = __fadd_rn(cd1[tau], m1 ? p.w : 0.0f);
         }
-        const float cv0 = __fadd_rn(cnt0 == 0 ? c0 : 0.0f, cd0), cv1 = __fadd_rn(cnt1 == 0 ? c0 : 0.0f, cd1);
-        sts2(uri + (tau == 0 ? C::f_bk(0) : (tau == 1 ? C::f_bk(1) : C::f_bk(2))) * LW, kd * mk2(__fmul_rn(cv0, cv0), __fmul_rn(cv1, cv1)));
+    }
+#pragma unroll
+    for (int tau = 0; tau < 3; ++tau) {
+        const float cv0 = __fadd_rn(cnt0[tau] == 0 ? c0 : 0.0f, cd0[tau]), cv1 = __fadd_rn(cnt1[tau] == 0 ? c0 : 0.0f, cd1[tau]);
+        sts2(uri + C::f_bk(tau) * LW, kd * mk2(__fmul_rn(cv0, cv0), __fmul_rn(cv1, cv1)));
     }
 }
 // same with every cylinder of the design (the culled list overflowed)
@@ -315,7 +334,7 @@ struct Body {
     uint32_t bar_c, bar_o;   // mbarrier of slot 0 of the current / other half
     uint32_t ring_c, ring_o; // byte address of slot 0 of the current / other half (TMA destination)
     uint32_t par;            // mbarrier phase parity of the rows arriving in this body
-    unsigned orow;           // float offset (row * nxp) of march row rb - 4 in the output planes
+    float *po;               // this lane's column pair of the output U plane at march row rb - 4 (stage 4 of row rb stores there)
 };
 
 // float index of this lane's pair in row 0 of the slot that holds march row rb + PH + D (D in [-4, 3])
@@ -364,7 +383,7 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
                 R.aVy[sc] = fma2(2.0f, dUy, R.aVy[sc]);
             }
         } else if (st) {
-            float *o = c.out_e + (b.orow + (unsigned)(PH * c.rowstep));
+            float *o = b.po + PH * c.rowstep;
             stg2(o, fma2(A.dt6, R.aU[sc] + kU, uU));
             stg2(o + A.plane, fma2(A.dt6kd, R.aVx[sc] + dUx, uVx));
             stg2(o + 2u * A.plane, fma2(A.dt6kd, R.aVy[sc] + dUy, uVy));
@@ -432,7 +451,7 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
                 R.Vy[S][sp] = ghost_row(R.Vy[S][sc], R.Vy[S][sm], R.Vy[S][s2]);
             }
         } else if (st) {
-            float *o = c.out_e + (b.orow + (unsigned)(PH * c.rowstep));
+            float *o = b.po + PH * c.rowstep;
             stg2(o, fma2(A.dt6, R.aU[sc] + kU, uU));
             stg2(o + A.plane, fma2(A.dt6, R.aVx[sc] + kVx, uVx));
             stg2(o + 2u * A.plane, fma2(A.dt6, R.aVy[sc] + kVy, uVy));
@@ -452,14 +471,12 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
     __syncwarp();
     {
         const int rp = r + PF;
-        if (c.lane2 == 0 && rp >= 0 && rp < c.nm) {
+        if (rp >= 0 && rp < c.nm) {  // warp-uniform
             constexpr int q = PH + PF;
             const uint32_t bar = (q < 4 ? b.bar_c + q * 8 : b.bar_o + (q - 4) * 8);
             const uint32_t dst = (q < 4 ? b.ring_c + q * (C::SLOT_F * 4) : b.ring_o + (q - 4) * (C::SLOT_F * 4));
-            const int jp = c.jbase + c.dir * rp;
-            mbar_expect_tx(bar, ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0)) * (LW * 4));
-            tma_load_3d(dst, map_u, c.x0, jp, e * 12 + c.w0 * 6, bar);
-            if (c.src_win) tma_load_3d(dst + C::ROW_SH * (LW * 4), map_sh, c.x0, jp, e, bar);
+            tma_issue_row(bar, c.tx_bytes, dst, map_u, c.x0, c.jbase + c.dir * rp, e * 12 + c.w0 * 6, c.src_win,
+                          dst + C::ROW_SH * (LW * 4), map_sh, e);
         }
         if (PFL2 > 0) {
             const int rl = r + PFL2;
@@ -484,7 +501,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
         }
         if (V != 3) {
             // fields that stay constant in this window: copy them to the output, keep their sum for dU
-            float *o = c.out_e + (b.orow + (unsigned)((PH + 4) * c.rowstep));
+            float *o = b.po + (PH + 4) * c.rowstep;
             const f2 om = lds2(uri + 5 * LW);
             f2 P;
             if (V == 0) {
@@ -512,10 +529,15 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
         }
         if (c.use_bk) {
             const float yv = A.gp.y[min(max(A.gp.grow0 + c.jbase + c.dir * r, 0), A.gp.ny_global - 1)];
-            if (c.nact > 0)
-                speed_row<V>(uri, c.nact, c.xs, yv, A.gp.c0, A.kd);
-            else
+            if (c.nact < 0) {
                 speed_row_slow<V>(A, e, uri, c.xs, yv);
+            } else if (yv > c.cyl_ylo && yv < c.cyl_yhi) {
+                speed_row<V>(uri, c.nact, c.xs, yv, A.gp.c0, A.kd);
+            } else {  // ambient speed on the whole row
+                sts2(uri + C::f_bk(0) * LW, bc2(A.b0kd));
+                sts2(uri + C::f_bk(1) * LW, bc2(A.b0kd));
+                sts2(uri + C::f_bk(2) * LW, bc2(A.b0kd));
+            }
         }
         // the rows rewritten above are TMA targets again RING rows later: order the generic writes before it
         if (V != 0 || !WV_P_REGS || c.use_bk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -592,6 +614,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     // other windows keep a zero row
     c.src_win = ep.has_source && item.x0 < ep.src_i1 && item.x0 + LW > ep.src_i0 && ep.src_j1 > ep.src_j0;
 
+    c.tx_bytes = ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0)) * (LW * 4);
     if (lane == 0) {
         for (int s = 0; s < RING; ++s) mbar_init(c.bar0 + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -609,10 +632,12 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
         const float yb = gp.y[min(max(gp.grow0 + item.lb - 1, 0), gp.ny_global - 1)];
         const float ylo = fminf(ya, yb), yhi = fmaxf(ya, yb);
         int n = 0;
+        float ylo_all = 1e30f, yhi_all = -1e30f;
         for (int k0 = 0; k0 < ep.ncyl; k0 += 32) {
             const int k = k0 + lane;
             float P[3][4];
             bool hit = false;
+            float mrg = 0.f, pymin_ = 0.f, pymax_ = 0.f;
             if (k < ep.ncyl) {
                 const size_t o = ((size_t)e * A.cyl_cap + k) * 4;
                 float rmax = 0.f, pxmin = 1e30f, pxmax = -1e30f, pymin = 1e30f, pymax = -1e30f;
@@ -630,20 +655,35 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
                     pymin = fminf(pymin, P[tau][1]);
                     pymax = fmaxf(pymax, P[tau][1]);
                 }
-                const float m = rmax * 1.0001f + 1e-6f;
-                hit = (pxmax + m >= xlo) && (pxmin - m <= xhi) && (pymax + m >= ylo) && (pymin - m <= yhi);
+                mrg = rmax * 1.0001f + 1e-6f;
+                pymin_ = pymin;
+                pymax_ = pymax;
+                hit = (pxmax + mrg >= xlo) && (pxmin - mrg <= xhi) && (pymax + mrg >= ylo) && (pymin - mrg <= yhi);
             }
             const unsigned bal = __ballot_sync(0xffffffffu, hit);
             const int pos = n + __popc(bal & ((1u << lane) - 1));
             if (hit && pos < CYL_CAP) {
 #pragma unroll
                 for (int tau = 0; tau < 3; ++tau)
-                    *reinterpret_cast<float4 *>(&smf[C::CYL_OFF + (pos * 3 + tau) * 4]) =
+                    *reinterpret_cast<float4 *>(&smf[C::CYL_OFF + pos * 16 + tau * 4]) =
                         make_float4(P[tau][0], P[tau][1], P[tau][2], P[tau][3]);
+                const float reach = 0.5f * (pymax_ - pymin_) + mrg;
+                *reinterpret_cast<float4 *>(&smf[C::CYL_OFF + pos * 16 + 12]) = make_float4(0.5f * (pymax_ + pymin_), reach * reach, 0.f, 0.f);
+            }
+            if (hit) {
+                ylo_all = fminf(ylo_all, pymin_ - mrg);
+                yhi_all = fmaxf(yhi_all, pymax_ + mrg);
             }
             n += __popc(bal);
         }
         c.nact = n <= CYL_CAP ? n : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ylo_all = fminf(ylo_all, __shfl_xor_sync(0xffffffffu, ylo_all, o));
+            yhi_all = fmaxf(yhi_all, __shfl_xor_sync(0xffffffffu, yhi_all, o));
+        }
+        c.cyl_ylo = ylo_all;
+        c.cyl_yhi = yhi_all;
         __syncwarp();
     }
     c.use_bk = c.nact != 0;
@@ -670,7 +710,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     // lives in ring slot m & 7, so a body's rows fill one half of the ring.
     Body b;
     const int nbody = (c.nm + 4 + 3) / 4 + 1;  // bodies -4, 0, 4, ... covering arrivals up to nm-1 and the 4 drain rows
-    b.orow = (unsigned)((c.jbase - 8 * c.dir) * (int)A.nxp);  // march row -8 (body -4 stores rows rb-4 .. rb-1: none owned)
+    b.po = c.out_e + (long long)(c.jbase - 8 * c.dir) * (int)A.nxp;  // march row -8 (the body at -4 stores rows -8 .. -5: none owned)
 #pragma unroll 1
     for (int k = 0; k < nbody; ++k) {
         const int rb = 4 * k - 4, half = (k + 1) & 1;
@@ -685,7 +725,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
         row_step<V, 1>(c, A, e, b, R, rb + 1, map_u, &map_sh);
         row_step<V, 2>(c, A, e, b, R, rb + 2, map_u, &map_sh);
         row_step<V, 3>(c, A, e, b, R, rb + 3, map_u, &map_sh);
-        b.orow += (unsigned)(4 * c.rowstep);
+        b.po += 4 * c.rowstep;
     }
 
     if (c.want_e) {
@@ -812,8 +852,10 @@ int fused_prepare(waves_handle *h) {
     auto add_cols = [&](int a, int b, bool interior) {  // a is a multiple of 4
         int o = a;
         while (o < b) {
-            const int x0 = o == 0 ? 0 : o - 4;
-            int hi = o + OWN_W;  // 56 owned columns + 4 halo columns per side
+            int x0 = o == 0 ? 0 : o - 4;
+            // the last interior window is pulled back so that it stays inside the zero-sigma zone (it owns fewer columns)
+            if (interior && x0 + LW > z1 && ((z1 - LW) & ~3) >= z0) x0 = (z1 - LW) & ~3;
+            int hi = x0 + LW - 4;  // 4 halo columns on the right (and on the left unless the window starts at column 0)
             if (x0 + LW >= gp.nx) hi = gp.nx;  // the window reaches the right domain edge: no halo needed there
             if (hi > b) hi = b;
             cols.push_back({o, hi, x0, interior});
@@ -821,7 +863,7 @@ int fused_prepare(waves_handle *h) {
         }
     };
     // interior output columns keep their 4-column halo inside the zero-sigma zone
-    int ci0 = (z0 + 4 + 7) & ~7, ci1 = (z1 - 4) & ~3;
+    int ci0 = (z0 + 4 + 3) & ~3, ci1 = (z1 - 4) & ~3;
     if (ci1 - ci0 < 24) {
         add_cols(0, gp.nx, false);
     } else {
