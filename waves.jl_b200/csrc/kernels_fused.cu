@@ -54,8 +54,14 @@ namespace {
 #ifndef WV_OCC_STRIP
 #define WV_OCC_STRIP 8  // resident warps per SM the PML-strip variants are compiled for (8: 255 registers, 12: 168)
 #endif
-constexpr int RING = 8;      // ring slots (rows) per warp
-constexpr int PF = 3;        // TMA prefetch distance in rows (PF + 5 <= RING)
+#ifndef WV_SP0
+#define WV_SP0 1      // interior variant: rows between consecutive RK stages of the software pipeline (1 or 2; measured: 2 at
+                      // 8 warps/SM equals 1 at 12 warps/SM)
+#endif
+#ifndef WV_SP1
+#define WV_SP1 1      // same for the left / right PML strips
+#endif
+constexpr int PF = 3;        // TMA prefetch distance in rows
 constexpr int PFL2 = WV_PFL2;  // L2 prefetch distance in rows (cp.async.bulk.prefetch.tensor)
 constexpr int CYL_CAP = 12;  // culled cylinders kept per warp
 constexpr int LW = 64;       // columns per warp window (two per lane)
@@ -78,6 +84,13 @@ constexpr int OWN_W = LW - 8;  // owned columns of a full window (4-column halo 
 template <int V>
 struct Cfg {
     static constexpr bool SX = (V & 1) != 0, SY = (V & 2) != 0;
+    // Stage spacing: stage s works SP rows behind stage s-1.  With SP = 1 the stages of one loop iteration form a
+    // dependent chain (stage s needs the row stage s-1 just produced); with SP = 2 they are independent, which
+    // gives each warp four interleavable chains at the price of a deeper ring and more live registers.
+    static constexpr int SP = (V == 0) ? WV_SP0 : (V == 1 ? WV_SP1 : 1);
+    static constexpr int NG = SP == 1 ? 2 : 3;   // ring groups of 4 rows: rows r + PF .. r - 4 SP must stay resident
+    static constexpr int RING = 4 * NG;
+    static constexpr bool P_REGS = (V == 0) && WV_P_REGS && SP == 1;
     static constexpr int ROW_UI = 6;
     static constexpr int ROW_SH = 7;
     static constexpr int ROW_P = SX ? 4 : 3;  // V = 1: Psiy row; V = 0, 2: Psix row; V = 3: unused
@@ -87,6 +100,8 @@ struct Cfg {
     static constexpr int CYL_OFF = RING_F;
     static constexpr int BAR_OFF = CYL_OFF + CYL_CAP * 16;  // per culled cylinder: (px, py, r^2, c) x 3 stage times + (y_mid, reach^2, -, -)
     static constexpr int WARP_F = ((BAR_OFF + RING * 2) + 31) & ~31;  // floats per warp (128-byte multiple)
+    static_assert(PF + 4 * SP + 1 <= RING, "ring too shallow");
+    static_assert(!(SY && SP != 1), "the sigma_y window and the ghost rows assume SP == 1");
     // row holding kd*c^2 at stage-time index tau
     __host__ __device__ static constexpr int f_bk(int tau) { return V != 0 ? (tau == 0 ? 6 : 7 + tau) : 4 + tau; }
 };
@@ -297,9 +312,9 @@ struct Regs {
     f2 Uf[4][4];  // U + f of stage state y_s (s = 0: the loaded row)
     f2 Vy[4][4];
     f2 Vx[4][4];  // s = 1..3
-    f2 aU[4], aVx[4], aVy[4];  // k1 + 2k2 + 2k3 accumulators (V = 0: aVx, aVy hold un-scaled differences)
+    f2 aU[4][4], aVx[4][4], aVy[4][4];  // [s]: k1 + .. + w_s k_s after stage s (V = 0: aVx, aVy hold un-scaled differences)
     f2 Px[4][4], Py[4][4], Om[4][4];  // SX / SY / SX && SY only
-    f2 aPx[4], aPy[4], aOm[4];
+    f2 aPx[4][4], aPy[4][4], aOm[4][4];
     float sy[4];  // sigma_y of the rows in flight (SY only)
     f2 P[4];      // V = 0: Psix + Psiy - Omega of the rows in flight
     f2 e_tot, e_inc, e_sc;
@@ -326,37 +341,47 @@ __device__ __forceinline__ f2 ddx_gen(const WarpCtx &c, f2 v) {
 // value of the row beyond a domain border row that makes the central difference one-sided (see file header)
 __device__ __forceinline__ f2 ghost_row(f2 v1, f2 v2, f2 v3) { return fma2(3.0f, v1 - v2, v3); }
 
-// Loop-carried addressing of one 4-row loop body: the ring half that holds march rows rb..rb+3 and the
-// other half (rows rb-4..rb-1 and, for the prefetch, rb+4..rb+7).  All are float indices into smf / byte
-// addresses in the shared window INCLUDING this lane's column-pair offset where applicable.
+// Loop-carried addressing of one 4-row loop body.  The ring holds NG groups of 4 rows; march row m lives in slot
+// m mod (4 NG).  g[0] is the group of rows rb..rb+3, g[1] of rb-4..rb-1, g[2] of rb-8..rb-5; the group after the
+// current one (prefetch target) is the oldest.  Float indices into smf include this lane's column-pair offset.
 struct Body {
-    int cur, oth;            // float index of slot 0 of the current / other half + 2 * lane
-    uint32_t bar_c, bar_o;   // mbarrier of slot 0 of the current / other half
-    uint32_t ring_c, ring_o; // byte address of slot 0 of the current / other half (TMA destination)
-    uint32_t par;            // mbarrier phase parity of the rows arriving in this body
-    float *po;               // this lane's column pair of the output U plane at march row rb - 4 (stage 4 of row rb stores there)
+    int g[3];          // float index of slot 0 of each group + 2 * lane
+    uint32_t bar[3];   // mbarrier of slot 0 of each group
+    uint32_t par;      // mbarrier phase parity of the rows arriving in this body
+    float *po;         // this lane's column pair of the output U plane at the march row stage 4 of row rb works on
 };
 
-// float index of this lane's pair in row 0 of the slot that holds march row rb + PH + D (D in [-4, 3])
+// float index of this lane's pair in row 0 of the slot that holds march row rb + PH + D (D in [-8, 3])
 template <int V, int PH, int D>
 __device__ __forceinline__ int slot_of(const Body &b) {
+    using C = Cfg<V>;
     constexpr int q = PH + D;
-    static_assert(q >= -4 && q < 8, "slot offset out of range");
-    return (q >= 0 && q < 4) ? b.cur + q * Cfg<V>::SLOT_F : b.oth + (q < 0 ? q + 4 : q - 4) * Cfg<V>::SLOT_F;
+    static_assert(q >= -4 * (C::NG - 1) && q < 8, "slot offset out of range");
+    return q >= 4 ? b.g[C::NG - 1] + (q - 4) * C::SLOT_F
+                  : (q >= 0 ? b.g[0] + q * C::SLOT_F : (q >= -4 ? b.g[1] + (q + 4) * C::SLOT_F : b.g[2] + (q + 8) * C::SLOT_F));
+}
+template <int V, int PH, int D>
+__device__ __forceinline__ uint32_t bar_of(const Body &b) {
+    using C = Cfg<V>;
+    constexpr int q = PH + D;
+    return q >= 4 ? b.bar[C::NG - 1] + (q - 4) * 8 : (q >= 0 ? b.bar[0] + q * 8 : (q >= -4 ? b.bar[1] + (q + 4) * 8 : b.bar[2] + (q + 8) * 8));
 }
 
-// One RK stage S (1..4) on march row m = r - S.  PH = r & 3.  Rows whose inputs are not loaded yet (warm-up)
+// One RK stage S (1..4) on march row m = r - S * SP.  PH = r & 3.  Rows whose inputs are not loaded yet (warm-up)
 // produce values that no stored cell depends on, and stores are predicated.
 // Derivatives are kept un-scaled (differences); the 1/(2Δ) factor is folded into the coefficients.
 template <int V, int S, int PH>
 __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, const Body &b, Regs &R, int m) {
     using C = Cfg<V>;
     constexpr bool SX = C::SX, SY = C::SY;
-    constexpr int sc = (PH - S + 8) & 3, sm = (sc + 3) & 3, sp = (sc + 1) & 3, s2 = (sc + 2) & 3;  // rows m, m-1, m+1, m-2
-    const int uri = slot_of<V, PH, -S>(b);
+    constexpr int sc = (PH - S * C::SP + 16) & 3, sm = (sc + 3) & 3, sp = (sc + 1) & 3, s2 = (sc + 2) & 3;  // rows m, m-1, m+1, m-2
+    const int uri = slot_of<V, PH, -S * C::SP>(b);
     const float a = (S == 3) ? A.dt : A.hdt;
     const float akd = (S == 3) ? A.akd_f : A.akd_h;
     constexpr int tau = (S == 1) ? 0 : (S == 4 ? 2 : 1);
+    // accumulator level read / written by this stage: in place with SP == 1, one level per stage otherwise (a row's
+    // accumulator outlives the 4-slot window when the stages are 2 rows apart)
+    constexpr int ar = C::SP == 1 ? 0 : S - 1, aw = C::SP == 1 ? 0 : S;
     const float sf_next = (S == 1 || S == 2) ? c.sf[1] : c.sf[2];
     const f2 bk = c.use_bk ? lds2(uri + C::f_bk(tau) * LW) : bc2(A.b0kd);  // kd * c^2 (written on arrival)
     const f2 uU = lds2(uri), uVx = lds2(uri + LW), uVy = lds2(uri + 2 * LW);
@@ -368,25 +393,25 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
     if (V == 0) {
         const f2 dUx = ddx_int(ufC), dVx = ddx_int(vxC);
         // sigma == 0 in the whole window: Psi, Omega never change within the step; P was formed on arrival
-        const f2 kU = fma2(bk, dVx + dVy, WV_P_REGS ? R.P[sc] : lds2(uri + C::ROW_P * LW));
+        const f2 kU = fma2(bk, dVx + dVy, C::P_REGS ? R.P[sc] : lds2(uri + C::ROW_P * LW));
         if (S < 4) {
             R.Uf[S][sc] = fma2(sf_next, lds2(uri + C::ROW_SH * LW), fma2(a, kU, uU));
             R.Vx[S][sc] = fma2(akd, dUx, uVx);
             R.Vy[S][sc] = fma2(akd, dUy, uVy);
             if (S == 1) {
-                R.aU[sc] = kU;
-                R.aVx[sc] = dUx;
-                R.aVy[sc] = dUy;
+                R.aU[aw][sc] = kU;
+                R.aVx[aw][sc] = dUx;
+                R.aVy[aw][sc] = dUy;
             } else {
-                R.aU[sc] = fma2(2.0f, kU, R.aU[sc]);
-                R.aVx[sc] = fma2(2.0f, dUx, R.aVx[sc]);
-                R.aVy[sc] = fma2(2.0f, dUy, R.aVy[sc]);
+                R.aU[aw][sc] = fma2(2.0f, kU, R.aU[ar][sc]);
+                R.aVx[aw][sc] = fma2(2.0f, dUx, R.aVx[ar][sc]);
+                R.aVy[aw][sc] = fma2(2.0f, dUy, R.aVy[ar][sc]);
             }
         } else if (st) {
             float *o = b.po + PH * c.rowstep;
-            stg2(o, fma2(A.dt6, R.aU[sc] + kU, uU));
-            stg2(o + A.plane, fma2(A.dt6kd, R.aVx[sc] + dUx, uVx));
-            stg2(o + 2u * A.plane, fma2(A.dt6kd, R.aVy[sc] + dUy, uVy));
+            stg2(o, fma2(A.dt6, R.aU[ar][sc] + kU, uU));
+            stg2(o + A.plane, fma2(A.dt6kd, R.aVx[ar][sc] + dUx, uVx));
+            stg2(o + 2u * A.plane, fma2(A.dt6kd, R.aVy[ar][sc] + dUy, uVy));
         }
     } else {
         // dU  = bc * [b (Vxx + Vyy) + Psix + Psiy - (sx + sy) U - Omega]      (src/dynamics.jl:169-176)
@@ -432,19 +457,19 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
             if (SY) R.Py[S][sc] = fma2(a, kPy, uPy);
             if (V == 3) R.Om[S][sc] = fma2(a, kOm, uOm);
             if (S == 1) {
-                R.aU[sc] = kU;
-                R.aVx[sc] = kVx;
-                R.aVy[sc] = kVy;
-                if (SX) R.aPx[sc] = kPx;
-                if (SY) R.aPy[sc] = kPy;
-                if (V == 3) R.aOm[sc] = kOm;
+                R.aU[aw][sc] = kU;
+                R.aVx[aw][sc] = kVx;
+                R.aVy[aw][sc] = kVy;
+                if (SX) R.aPx[aw][sc] = kPx;
+                if (SY) R.aPy[aw][sc] = kPy;
+                if (V == 3) R.aOm[aw][sc] = kOm;
             } else {
-                R.aU[sc] = fma2(2.0f, kU, R.aU[sc]);
-                R.aVx[sc] = fma2(2.0f, kVx, R.aVx[sc]);
-                R.aVy[sc] = fma2(2.0f, kVy, R.aVy[sc]);
-                if (SX) R.aPx[sc] = fma2(2.0f, kPx, R.aPx[sc]);
-                if (SY) R.aPy[sc] = fma2(2.0f, kPy, R.aPy[sc]);
-                if (V == 3) R.aOm[sc] = fma2(2.0f, kOm, R.aOm[sc]);
+                R.aU[aw][sc] = fma2(2.0f, kU, R.aU[ar][sc]);
+                R.aVx[aw][sc] = fma2(2.0f, kVx, R.aVx[ar][sc]);
+                R.aVy[aw][sc] = fma2(2.0f, kVy, R.aVy[ar][sc]);
+                if (SX) R.aPx[aw][sc] = fma2(2.0f, kPx, R.aPx[ar][sc]);
+                if (SY) R.aPy[aw][sc] = fma2(2.0f, kPy, R.aPy[ar][sc]);
+                if (V == 3) R.aOm[aw][sc] = fma2(2.0f, kOm, R.aOm[ar][sc]);
             }
             if (brow) {
                 R.Uf[S][sp] = ghost_row(R.Uf[S][sc], R.Uf[S][sm], R.Uf[S][s2]);
@@ -452,12 +477,12 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
             }
         } else if (st) {
             float *o = b.po + PH * c.rowstep;
-            stg2(o, fma2(A.dt6, R.aU[sc] + kU, uU));
-            stg2(o + A.plane, fma2(A.dt6, R.aVx[sc] + kVx, uVx));
-            stg2(o + 2u * A.plane, fma2(A.dt6, R.aVy[sc] + kVy, uVy));
-            if (SX) stg2(o + 3u * A.plane, fma2(A.dt6, R.aPx[sc] + kPx, uPx));
-            if (SY) stg2(o + 4u * A.plane, fma2(A.dt6, R.aPy[sc] + kPy, uPy));
-            if (V == 3) stg2(o + 5u * A.plane, fma2(A.dt6, R.aOm[sc] + kOm, uOm));
+            stg2(o, fma2(A.dt6, R.aU[ar][sc] + kU, uU));
+            stg2(o + A.plane, fma2(A.dt6, R.aVx[ar][sc] + kVx, uVx));
+            stg2(o + 2u * A.plane, fma2(A.dt6, R.aVy[ar][sc] + kVy, uVy));
+            if (SX) stg2(o + 3u * A.plane, fma2(A.dt6, R.aPx[ar][sc] + kPx, uPx));
+            if (SY) stg2(o + 4u * A.plane, fma2(A.dt6, R.aPy[ar][sc] + kPy, uPy));
+            if (V == 3) stg2(o + 5u * A.plane, fma2(A.dt6, R.aOm[ar][sc] + kOm, uOm));
         }
     }
 }
@@ -472,9 +497,8 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
     {
         const int rp = r + PF;
         if (rp >= 0 && rp < c.nm) {  // warp-uniform
-            constexpr int q = PH + PF;
-            const uint32_t bar = (q < 4 ? b.bar_c + q * 8 : b.bar_o + (q - 4) * 8);
-            const uint32_t dst = (q < 4 ? b.ring_c + q * (C::SLOT_F * 4) : b.ring_o + (q - 4) * (C::SLOT_F * 4));
+            const uint32_t bar = bar_of<V, PH, PF>(b);
+            const uint32_t dst = c.ring_sa + 4u * (uint32_t)(slot_of<V, PH, PF>(b) - c.lane2);
             tma_issue_row(bar, c.tx_bytes, dst, map_u, c.x0, c.jbase + c.dir * rp, e * 12 + c.w0 * 6, c.src_win,
                           dst + C::ROW_SH * (LW * 4), map_sh, e);
         }
@@ -486,8 +510,8 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
     // 2. arrival of march row r: stage-0 windows, energy of the owned rows, pass-through of the constant
     //    auxiliary fields, speed field of the row
     if (r >= 0 && r < c.nm) {
-        mbar_wait(b.bar_c + PH * 8, b.par);
-        const int uri = b.cur + PH * C::SLOT_F;
+        mbar_wait(b.bar[0] + PH * 8, b.par);
+        const int uri = b.g[0] + PH * C::SLOT_F;
         constexpr int s0 = PH & 3, sm = (s0 + 3) & 3, s2 = (s0 + 2) & 3, sp = (s0 + 1) & 3;
         const f2 U = lds2(uri);
         R.Uf[0][s0] = fma2(c.sf[0], lds2(uri + C::ROW_SH * LW), U);
@@ -501,7 +525,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
         }
         if (V != 3) {
             // fields that stay constant in this window: copy them to the output, keep their sum for dU
-            float *o = b.po + (PH + 4) * c.rowstep;
+            float *o = b.po + (PH + 4 * C::SP) * c.rowstep;
             const f2 om = lds2(uri + 5 * LW);
             f2 P;
             if (V == 0) {
@@ -518,7 +542,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
                 P = px - om;
             }
             if (own) stg2(o + 5u * A.plane, om);
-            if (V == 0 && WV_P_REGS)
+            if (C::P_REGS)
                 R.P[s0] = P;
             else
                 sts2(uri + C::ROW_P * LW, P);
@@ -540,7 +564,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
             }
         }
         // the rows rewritten above are TMA targets again RING rows later: order the generic writes before it
-        if (V != 0 || !WV_P_REGS || c.use_bk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (!C::P_REGS || c.use_bk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     // 3. the four stages, each one row behind the previous.  Rows below 1 run unguarded (whatever they
     //    compute is overwritten before a stored cell reads it).  Rows beyond a domain border row must not
@@ -553,15 +577,15 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
         // sigma_y of march row r: first used by stage 1 in the next iteration (its slot was row r - 4's until now)
         R.sy[PH & 3] = A.gp.sigma[min(max(A.gp.grow0 + c.jbase + c.dir * r, 0), A.gp.ny_global - 1)];
     } else {
-        stage<V, 1, PH>(c, A, b, R, r - 1);
-        stage<V, 2, PH>(c, A, b, R, r - 2);
-        stage<V, 3, PH>(c, A, b, R, r - 3);
-        stage<V, 4, PH>(c, A, b, R, r - 4);
+        stage<V, 1, PH>(c, A, b, R, r - 1 * C::SP);
+        stage<V, 2, PH>(c, A, b, R, r - 2 * C::SP);
+        stage<V, 3, PH>(c, A, b, R, r - 3 * C::SP);
+        stage<V, 4, PH>(c, A, b, R, r - 4 * C::SP);
     }
 }
 
 template <int V>
-__global__ void __launch_bounds__(32, V == 3 ? 8 : (V == 0 ? 12 : WV_OCC_STRIP))
+__global__ void __launch_bounds__(32, V == 3 ? 8 : (V == 0 ? (WV_SP0 == 1 ? 12 : 8) : WV_OCC_STRIP))
 k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtensorMap map_u7, const __grid_constant__ CUtensorMap map_u6,
              const __grid_constant__ CUtensorMap map_sh) {
     using C = Cfg<V>;
@@ -616,11 +640,11 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
 
     c.tx_bytes = ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0)) * (LW * 4);
     if (lane == 0) {
-        for (int s = 0; s < RING; ++s) mbar_init(c.bar0 + s * 8, 1);
+        for (int s = 0; s < C::RING; ++s) mbar_init(c.bar0 + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (!c.src_win)
-        for (int s = 0; s < RING; ++s) sts2(s * C::SLOT_F + C::ROW_SH * LW + c.lane2, bc2(0.0f));
+        for (int s = 0; s < C::RING; ++s) sts2(s * C::SLOT_F + C::ROW_SH * LW + c.lane2, bc2(0.0f));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
 
@@ -699,33 +723,45 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
             R.Px[s][q] = R.Py[s][q] = R.Om[s][q] = bc2(0.f);
         }
 #pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            R.aU[s][q] = R.aVx[s][q] = R.aVy[s][q] = bc2(0.f);
+            R.aPx[s][q] = R.aPy[s][q] = R.aOm[s][q] = bc2(0.f);
+        }
+#pragma unroll
     for (int q = 0; q < 4; ++q) {
-        R.aU[q] = R.aVx[q] = R.aVy[q] = bc2(0.f);
-        R.aPx[q] = R.aPy[q] = R.aOm[q] = bc2(0.f);
         R.sy[q] = 0.f;
+        R.P[q] = bc2(0.f);
     }
 
     const CUtensorMap *map_u = c.is_tot ? &map_u7 : &map_u6;
     // march rows rb .. rb+3 per loop body; the body starting at -4 only prefetches and warms up.  March row m
-    // lives in ring slot m & 7, so a body's rows fill one half of the ring.
+    // lives in ring slot m mod RING, so a body's rows fill one group of the ring.
     Body b;
-    const int nbody = (c.nm + 4 + 3) / 4 + 1;  // bodies -4, 0, 4, ... covering arrivals up to nm-1 and the 4 drain rows
-    b.po = c.out_e + (long long)(c.jbase - 8 * c.dir) * (int)A.nxp;  // march row -8 (the body at -4 stores rows -8 .. -5: none owned)
+    const int nbody = (c.nm + 4 * C::SP + 4 + 3) / 4;  // bodies -4, 0, 4, ... covering arrivals up to nm-1 and the 4 SP drain rows
+    b.po = c.out_e + (long long)(c.jbase - (4 + 4 * C::SP) * c.dir) * (int)A.nxp;  // the body at -4 stores rows that are never owned
+    int grp = C::NG - 1;  // group of body k = (k - 1) mod NG
+    b.par = 1;            // rows of body k are use number (k - 1) div NG of their slots
 #pragma unroll 1
     for (int k = 0; k < nbody; ++k) {
-        const int rb = 4 * k - 4, half = (k + 1) & 1;
-        b.cur = half * 4 * C::SLOT_F + c.lane2;
-        b.oth = (half ^ 1) * 4 * C::SLOT_F + c.lane2;
-        b.bar_c = c.bar0 + half * 32;
-        b.bar_o = c.bar0 + (half ^ 1) * 32;
-        b.ring_c = c.ring_sa + half * (4 * C::SLOT_F * 4);
-        b.ring_o = c.ring_sa + (half ^ 1) * (4 * C::SLOT_F * 4);
-        b.par = ((k - 1) >> 1) & 1;  // march row m is use number m >> 3 of its slot
+        const int rb = 4 * k - 4;
+#pragma unroll
+        for (int d = 0; d < C::NG; ++d) {
+            int gd = grp - d;
+            gd += gd < 0 ? C::NG : 0;
+            b.g[d] = gd * 4 * C::SLOT_F + c.lane2;
+            b.bar[d] = c.bar0 + gd * 32;
+        }
         row_step<V, 0>(c, A, e, b, R, rb, map_u, &map_sh);
         row_step<V, 1>(c, A, e, b, R, rb + 1, map_u, &map_sh);
         row_step<V, 2>(c, A, e, b, R, rb + 2, map_u, &map_sh);
         row_step<V, 3>(c, A, e, b, R, rb + 3, map_u, &map_sh);
         b.po += 4 * c.rowstep;
+        if (++grp == C::NG) {
+            grp = 0;
+            b.par ^= 1;
+        }
     }
 
     if (c.want_e) {
@@ -939,7 +975,7 @@ int fused_prepare(waves_handle *h) {
     }
     cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
 
-    p->smem[0] = Cfg<0>::WARP_F * 4;
+    p->smem[0] = Cfg<0>::WARP_F * 4;  // (ring depth depends on the variant's stage spacing)
     p->smem[1] = Cfg<1>::WARP_F * 4;
     p->smem[2] = Cfg<2>::WARP_F * 4;
     p->smem[3] = Cfg<3>::WARP_F * 4;
