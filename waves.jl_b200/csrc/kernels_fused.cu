@@ -130,6 +130,7 @@ struct FusedArgs {
     int epart_off;     // offset of this kernel's items
     int dbg;           // developer bisecting flags (WAVES_DEBUG_FLAGS)
     int cull;          // 0: skip the cylinder cull (no environment has a design)
+    int skip_aux;      // 1: the output buffer already holds the auxiliary fields that are constant in a window (see launch_fused_step)
     // host-computed step constants: read straight from the constant bank as FFMA operands
     float kd, b0kd;             // 1/(2Δ) and c0^2/(2Δ)
     float akd_h, akd_f, dt6kd;  // (dt/2)kd, dt*kd, (dt/6)kd
@@ -517,6 +518,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
         R.Uf[0][s0] = fma2(c.sf[0], lds2(uri + C::ROW_SH * LW), U);
         R.Vy[0][s0] = lds2(uri + 2 * LW);
         const bool own = (unsigned)(r - c.mo0) < c.mon;
+        const bool copy_aux = own && !A.skip_aux;
         if (c.want_e && own) {  // energy of the frame being read (src/env.jl:104-111)
             const f2 Ui = lds2(uri + C::ROW_UI * LW), d = U - Ui;
             R.e_tot = fma2(U, U, R.e_tot);
@@ -530,18 +532,18 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
             f2 P;
             if (V == 0) {
                 const f2 px = lds2(uri + 3 * LW), py = lds2(uri + 4 * LW);
-                if (own) stg2(o + 3u * A.plane, px), stg2(o + 4u * A.plane, py);
+                if (copy_aux) stg2(o + 3u * A.plane, px), stg2(o + 4u * A.plane, py);
                 P = (px + py) - om;
             } else if (V == 1) {
                 const f2 py = lds2(uri + 4 * LW);
-                if (own) stg2(o + 4u * A.plane, py);
+                if (copy_aux) stg2(o + 4u * A.plane, py);
                 P = py - om;
             } else {
                 const f2 px = lds2(uri + 3 * LW);
-                if (own) stg2(o + 3u * A.plane, px);
+                if (copy_aux) stg2(o + 3u * A.plane, px);
                 P = px - om;
             }
-            if (own) stg2(o + 5u * A.plane, om);
+            if (copy_aux) stg2(o + 5u * A.plane, om);
             if (C::P_REGS)
                 R.P[s0] = P;
             else
@@ -1065,6 +1067,10 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     static const int dbg_flags = getenv("WAVES_DEBUG_FLAGS") ? atoi(getenv("WAVES_DEBUG_FLAGS")) : 0;
     A.dbg = dbg_flags;
     A.cull = (dbg_flags & 4) ? 0 : 1;
+    // Where sigma_x (sigma_y) is zero, Psix/Psiy/Omega (the fields whose RHS carries that factor, src/dynamics.jl:172-174) never
+    // change, whatever their values: once one fused step has copied them, BOTH ping-pong buffers hold them and the copy is
+    // skipped until something else writes the state (waves_set_state, halo unpack: aux_synced is cleared there).
+    A.skip_aux = (h->aux_synced >= 1 && !(dbg_flags & 64)) ? 1 : 0;
     static const int dbg_skip = getenv("WAVES_DEBUG_SKIP") ? atoi(getenv("WAVES_DEBUG_SKIP")) : 0;  // developer bisecting aid
     if (h->profile) cudaEventRecord(h->ev0, h->stream);
     // two warps (= CTAs) per item and environment: the total and the incident wavefield.  The PML variants are
@@ -1105,6 +1111,7 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
         h->launches++;
     }
     h->cur ^= 1;
+    h->aux_synced = 1;
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) {
         char buf[256];

@@ -331,6 +331,7 @@ extern "C" int waves_set_state(waves_handle *h, int env, const float *u12) {
     for (int e = e0; e < e1; ++e)
         if (copy_planes_fast(h, h->u[h->cur] + (size_t)e * gp.env_stride, u12 + (size_t)(e - e0) * per_env, nullptr, 12))
             return 1;
+    h->aux_synced = 0;
     CU_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -768,6 +769,7 @@ extern "C" int waves_halo_unpack(waves_handle *h, const float *lo_buf, const flo
     if (gp.ny_own0 == 0) lo_buf = nullptr;
     if (gp.ny_alloc == gp.ny_own0 + gp.ny_own) hi_buf = nullptr;
     if (lo_buf || hi_buf) launch_unpack_halo(h, h->u[h->cur], lo_buf, hi_buf);
+    h->aux_synced = 0;
     return 0;
 }
 

@@ -45,6 +45,7 @@ struct waves_handle {
     cudaStream_t stream;
     float *u[2];  // ping-pong state [n_env][12][ny_alloc][nxp]
     int cur;
+    int aux_synced;       // 1: a fused step ran since the state was last written from outside: both buffers hold the constant fields
     float *k, *ys, *acc;  // exact-mode scratch, lazily allocated
     float *b2;            // exact-mode c^2 plane per env [n_env][plane], lazily allocated
     float *shape;         // [n_env][plane] source shape (zeros when NoSource)
