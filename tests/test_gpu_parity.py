@@ -304,3 +304,32 @@ def test_many_cylinders_overflow_path():
     en, _ = eng.integrate(ts, wb.MODE_FUSED)
     assert rel(eng.get_state(0), ref) < TIGHT
     eng.close()
+
+
+def test_constant_auxiliary_fields_shortcut_is_invalidated_by_state_writes(golden_dir):
+    """Where sigma is zero, Psi/Omega never change: the fused path stops copying them (and reads their sum from its own
+    plane) after the first step.  Writing a new state must invalidate that: run A, then B with different auxiliary fields on
+    the SAME handle, each against the exact per-stage kernels."""
+    g, dim, dyn = load_small(golden_dir)
+    ts = g["tspan"][:13]
+    rng = np.random.default_rng(11)
+    states = [g["u0"], (rng.standard_normal(g["u0"].shape) * 2e-3).astype(F32)]
+    fused, exact = make_engine(dim, dyn, dO=g["dOmega"]), make_engine(dim, dyn, dO=g["dOmega"])
+    for eng in (fused, exact):
+        eng.set_source(g["shape"], float(g["freq"]))
+        eng.set_design(g["cyl0"], g["cyl1"], ts[0], ts[-1])
+    for u0 in states:
+        fused.set_state(u0[None])
+        exact.set_state(u0[None])
+        ef, _ = fused.integrate(ts, wb.MODE_FUSED)
+        ee, _ = exact.integrate(ts, wb.MODE_EXACT)
+        a, b = fused.get_state(0), exact.get_state(0)
+        for f in range(12):
+            assert rel(a[f], b[f]) < TIGHT, f"field {f}"
+        assert np.abs(ef - ee).max() / ee.max() < TIGHT
+        # single steps after an integration keep working on the shortcut path too
+        fused.step(float(ts[-1]))
+        exact.step(float(ts[-1]), wb.MODE_EXACT)
+        assert rel(fused.get_state(0), exact.get_state(0)) < TIGHT
+    fused.close()
+    exact.close()

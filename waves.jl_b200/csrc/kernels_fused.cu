@@ -71,6 +71,8 @@ constexpr int OWN_W = LW - 8;  // owned columns of a full window (4-column halo 
 //   SX: the window's columns may have sigma_x != 0 or include the domain's first / last column
 //   SY: the window's rows may have sigma_y != 0 or include the domain's first / last row
 // V = 0 is the interior (sigma == 0 in the whole window: Psix, Psiy, Omega never change and only pass through);
+// V = 4 is the LEAN interior: once a V = 0 step has stored P = Psix + Psiy - Omega of every interior cell in its own
+// plane and both state buffers hold the (constant) auxiliary fields, only U, Vx, Vy and P are read and U, Vx, Vy written;
 // V = 1 / 2 are the left-right / top-bottom PML strips (only Psix / Psiy evolves besides U, Vx, Vy; the other
 // two auxiliary fields pass through); V = 3 are the corners (all six fields evolve).
 //
@@ -84,17 +86,18 @@ constexpr int OWN_W = LW - 8;  // owned columns of a full window (4-column halo 
 template <int V>
 struct Cfg {
     static constexpr bool SX = (V & 1) != 0, SY = (V & 2) != 0;
+    static constexpr bool INT = (V == 0 || V == 4), LEAN = (V == 4);
     // Stage spacing: stage s works SP rows behind stage s-1.  With SP = 1 the stages of one loop iteration form a
     // dependent chain (stage s needs the row stage s-1 just produced); with SP = 2 they are independent, which
     // gives each warp four interleavable chains at the price of a deeper ring and more live registers.
-    static constexpr int SP = (V == 0) ? WV_SP0 : (V == 1 ? WV_SP1 : 1);
+    static constexpr int SP = INT ? WV_SP0 : (V == 1 ? WV_SP1 : 1);
     static constexpr int NG = SP == 1 ? 2 : 3;   // ring groups of 4 rows: rows r + PF .. r - 4 SP must stay resident
     static constexpr int RING = 4 * NG;
-    static constexpr bool P_REGS = (V == 0) && WV_P_REGS && SP == 1;
-    static constexpr int ROW_UI = 6;
-    static constexpr int ROW_SH = 7;
+    static constexpr bool P_REGS = INT && WV_P_REGS && SP == 1;
+    static constexpr int ROW_UI = LEAN ? 4 : 6;
+    static constexpr int ROW_SH = LEAN ? 5 : 7;
     static constexpr int ROW_P = SX ? 4 : 3;  // V = 1: Psiy row; V = 0, 2: Psix row; V = 3: unused
-    static constexpr int SLOT_ROWS = V == 0 ? 8 : 10;
+    static constexpr int SLOT_ROWS = INT ? 8 : 10;
     static constexpr int SLOT_F = SLOT_ROWS * LW;
     static constexpr int RING_F = RING * SLOT_F;
     static constexpr int CYL_OFF = RING_F;
@@ -103,7 +106,9 @@ struct Cfg {
     static_assert(PF + 4 * SP + 1 <= RING, "ring too shallow");
     static_assert(!(SY && SP != 1), "the sigma_y window and the ghost rows assume SP == 1");
     // row holding kd*c^2 at stage-time index tau
-    __host__ __device__ static constexpr int f_bk(int tau) { return V != 0 ? (tau == 0 ? 6 : 7 + tau) : 4 + tau; }
+    __host__ __device__ static constexpr int f_bk(int tau) {
+        return LEAN ? (tau == 0 ? 4 : 5 + tau) : (INT ? 4 + tau : (tau == 0 ? 6 : 7 + tau));
+    }
 };
 
 struct Item {
@@ -130,6 +135,7 @@ struct FusedArgs {
     int epart_off;     // offset of this kernel's items
     int dbg;           // developer bisecting flags (WAVES_DEBUG_FLAGS)
     int cull;          // 0: skip the cylinder cull (no environment has a design)
+    float *pconst;     // [n_env][2][plane]: P of the interior cells (written by V = 0 when skip_aux == 0, read by V = 4)
     int skip_aux;      // 1: the output buffer already holds the auxiliary fields that are constant in a window (see launch_fused_step)
     // host-computed step constants: read straight from the constant bank as FFMA operands
     float kd, b0kd;             // 1/(2Δ) and c0^2/(2Δ)
@@ -199,6 +205,30 @@ __device__ __forceinline__ void tma_issue_row(uint32_t bar, uint32_t bytes, uint
         "r"(bytes), "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(dst_sh), "l"(map_sh), "r"((int)with_shape), "r"(e)
         : "memory");
 }
+// Lean interior: U, Vx, Vy (box of 3 planes), the P plane, U of the incident field for total-field warps, the shape row.
+__device__ __forceinline__ void tma_issue_row_lean(uint32_t bar, uint32_t bytes, uint32_t dst, const CUtensorMap *map3, const CUtensorMap *map1,
+                                                   const CUtensorMap *mapp, const CUtensorMap *map_sh, int c0, int c1, int pl_u, int pl_p,
+                                                   int pl_ui, int e, bool with_ui, bool with_shape, uint32_t row_bytes) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pu, ps;\n"
+        ".reg .b32 d3, d4, d5;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.and.b32 pu, %11, 0, pe;\n"
+        "setp.ne.and.b32 ps, %12, 0, pe;\n"
+        "mad.lo.u32 d3, %13, 3, %2;\n"
+        "add.u32 d4, d3, %13;\n"
+        "add.u32 d5, d4, %13;\n"
+        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+        "@pe cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%2], [%3, {%7, %8, %9}], [%0];\n"
+        "@pe cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [d3], [%5, {%7, %8, %10}], [%0];\n"
+        "@pu cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [d4], [%4, {%7, %8, %14}], [%0];\n"
+        "@ps cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [d5], [%6, {%7, %8, %15}], [%0];\n"
+        "}\n" ::"r"(bar),
+        "r"(bytes), "r"(dst), "l"(map3), "l"(map1), "l"(mapp), "l"(map_sh), "r"(c0), "r"(c1), "r"(pl_u), "r"(pl_p), "r"((int)with_ui),
+        "r"((int)with_shape), "r"(row_bytes), "r"(pl_ui), "r"(e)
+        : "memory");
+}
 // HBM -> L2 only: keeps more bytes in flight than the shared-memory ring could hold
 __device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap *map, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -228,8 +258,9 @@ struct WarpCtx {
     int nlast;         // stages process march rows < nlast (nm when the march ends on a domain border row)
     bool border;       // the last march row is the domain's first / last row
     float *out_e;      // output state of this env / wavefield at this lane's column pair
+    float *pc_e;       // same position in the P plane of this env / wavefield
     int rowstep;       // dir * nxp: floats between consecutive march rows
-    bool xb, first_x, last_x, last_y, is_tot, use_bk, want_e, src_win;
+    bool xb, first_x, last_x, last_y, is_tot, use_bk, want_e, src_win, in_dom;
     int w0;
     f2 xs, sx, sxd, bcm;
     float dirf, kdd;   // dir as float, kd * dir
@@ -391,7 +422,7 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
     const f2 dUy = R.Uf[S - 1][sp] - R.Uf[S - 1][sm];  // in march order
     const f2 dVy = R.Vy[S - 1][sp] - R.Vy[S - 1][sm];
     const bool st = (unsigned)(m - c.mo0) < c.mon;  // this lane stores march row m
-    if (V == 0) {
+    if (C::INT) {
         const f2 dUx = ddx_int(ufC), dVx = ddx_int(vxC);
         // sigma == 0 in the whole window: Psi, Omega never change within the step; P was formed on arrival
         const f2 kU = fma2(bk, dVx + dVy, C::P_REGS ? R.P[sc] : lds2(uri + C::ROW_P * LW));
@@ -490,7 +521,8 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
 
 template <int V, int PH>
 __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, int e, const Body &b, Regs &R, int r,
-                                         const CUtensorMap *map_u, const CUtensorMap *map_sh) {
+                                         const CUtensorMap *map_u, const CUtensorMap *map_b, const CUtensorMap *map_c,
+                                         const CUtensorMap *map_sh) {
     using C = Cfg<V>;
     constexpr bool SX = C::SX, SY = C::SY;
     // 1. prefetch march row r + PF into the slot that row r + PF - RING vacated (all its readers finished >= 1 step ago)
@@ -500,8 +532,12 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
         if (rp >= 0 && rp < c.nm) {  // warp-uniform
             const uint32_t bar = bar_of<V, PH, PF>(b);
             const uint32_t dst = c.ring_sa + 4u * (uint32_t)(slot_of<V, PH, PF>(b) - c.lane2);
-            tma_issue_row(bar, c.tx_bytes, dst, map_u, c.x0, c.jbase + c.dir * rp, e * 12 + c.w0 * 6, c.src_win,
-                          dst + C::ROW_SH * (LW * 4), map_sh, e);
+            if (C::LEAN)
+                tma_issue_row_lean(bar, c.tx_bytes, dst, map_u, map_b, map_c, map_sh, c.x0, c.jbase + c.dir * rp, e * 12 + c.w0 * 6,
+                                   e * 2 + c.w0, e * 12 + 6, e, c.is_tot, c.src_win, LW * 4);
+            else
+                tma_issue_row(bar, c.tx_bytes, dst, map_u, c.x0, c.jbase + c.dir * rp, e * 12 + c.w0 * 6, c.src_win,
+                              dst + C::ROW_SH * (LW * 4), map_sh, e);
         }
         if (PFL2 > 0) {
             const int rl = r + PFL2;
@@ -525,7 +561,9 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
             R.e_inc = fma2(Ui, Ui, R.e_inc);
             R.e_sc = fma2(d, d, R.e_sc);
         }
-        if (V != 3) {
+        if (C::LEAN) {
+            if (C::P_REGS) R.P[s0] = lds2(uri + C::ROW_P * LW);
+        } else if (V != 3) {
             // fields that stay constant in this window: copy them to the output, keep their sum for dU
             float *o = b.po + (PH + 4 * C::SP) * c.rowstep;
             const f2 om = lds2(uri + 5 * LW);
@@ -534,6 +572,9 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
                 const f2 px = lds2(uri + 3 * LW), py = lds2(uri + 4 * LW);
                 if (copy_aux) stg2(o + 3u * A.plane, px), stg2(o + 4u * A.plane, py);
                 P = (px + py) - om;
+                // feeds the lean interior variant of the next steps; halo cells too (they are interior windows' inputs, and
+                // every writer of a cell stores the same value)
+                if (!A.skip_aux && c.in_dom) stg2(c.pc_e + (o - c.out_e), P);
             } else if (V == 1) {
                 const f2 py = lds2(uri + 4 * LW);
                 if (copy_aux) stg2(o + 4u * A.plane, py);
@@ -566,7 +607,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
             }
         }
         // the rows rewritten above are TMA targets again RING rows later: order the generic writes before it
-        if (!C::P_REGS || c.use_bk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if ((!C::P_REGS && !C::LEAN) || c.use_bk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     // 3. the four stages, each one row behind the previous.  Rows below 1 run unguarded (whatever they
     //    compute is overwritten before a stored cell reads it).  Rows beyond a domain border row must not
@@ -587,9 +628,11 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
 }
 
 template <int V>
-__global__ void __launch_bounds__(32, V == 3 ? 8 : (V == 0 ? (WV_SP0 == 1 ? 12 : 8) : WV_OCC_STRIP))
+__global__ void __launch_bounds__(32, V == 3 ? 8 : ((V == 0 || V == 4) ? (WV_SP0 == 1 ? 12 : 8) : WV_OCC_STRIP))
 k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtensorMap map_u7, const __grid_constant__ CUtensorMap map_u6,
-             const __grid_constant__ CUtensorMap map_sh) {
+             const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_sh) {
+    // full variants: map_u7 / map_u6 = boxes of 7 / 6 state planes; lean interior: map_u7 = box of 3 planes, map_u6 = box of 1 plane,
+    // map_c = the P planes
     using C = Cfg<V>;
     constexpr bool SX = C::SX, SY = C::SY;
     const int lane = threadIdx.x & 31;
@@ -624,6 +667,8 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     c.mo0 = c.dir > 0 ? item.j0 - item.la : item.lb - item.j1;
     c.mon = valid_lane ? (unsigned)(item.j1 - item.j0) : 0u;
     c.out_e = A.out + (long long)e * gp.env_stride + (long long)w0 * 6 * gp.plane + min(colA, gp.nxp - 2);
+    c.pc_e = A.pconst + ((long long)e * 2 + w0) * gp.plane + min(colA, gp.nxp - 2);
+    c.in_dom = colA < gp.nx;
     c.first_x = colA == 0;
     c.last_x = colA == gp.nx - 1;
     c.last_y = colB == gp.nx - 1;
@@ -640,7 +685,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     // other windows keep a zero row
     c.src_win = ep.has_source && item.x0 < ep.src_i1 && item.x0 + LW > ep.src_i0 && ep.src_j1 > ep.src_j0;
 
-    c.tx_bytes = ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0)) * (LW * 4);
+    c.tx_bytes = (C::LEAN ? (4 + (c.is_tot ? 1 : 0) + (c.src_win ? 1 : 0)) : ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0))) * (LW * 4);
     if (lane == 0) {
         for (int s = 0; s < C::RING; ++s) mbar_init(c.bar0 + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -737,7 +782,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
         R.P[q] = bc2(0.f);
     }
 
-    const CUtensorMap *map_u = c.is_tot ? &map_u7 : &map_u6;
+    const CUtensorMap *map_u = (C::LEAN || c.is_tot) ? &map_u7 : &map_u6;
     // march rows rb .. rb+3 per loop body; the body starting at -4 only prefetches and warms up.  March row m
     // lives in ring slot m mod RING, so a body's rows fill one group of the ring.
     Body b;
@@ -755,10 +800,10 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
             b.g[d] = gd * 4 * C::SLOT_F + c.lane2;
             b.bar[d] = c.bar0 + gd * 32;
         }
-        row_step<V, 0>(c, A, e, b, R, rb, map_u, &map_sh);
-        row_step<V, 1>(c, A, e, b, R, rb + 1, map_u, &map_sh);
-        row_step<V, 2>(c, A, e, b, R, rb + 2, map_u, &map_sh);
-        row_step<V, 3>(c, A, e, b, R, rb + 3, map_u, &map_sh);
+        row_step<V, 0>(c, A, e, b, R, rb, map_u, &map_u6, &map_c, &map_sh);
+        row_step<V, 1>(c, A, e, b, R, rb + 1, map_u, &map_u6, &map_c, &map_sh);
+        row_step<V, 2>(c, A, e, b, R, rb + 2, map_u, &map_u6, &map_c, &map_sh);
+        row_step<V, 3>(c, A, e, b, R, rb + 3, map_u, &map_u6, &map_c, &map_sh);
         b.po += 4 * c.rowstep;
         if (++grp == C::NG) {
             grp = 0;
@@ -823,7 +868,7 @@ struct FusedPlan {
     int off[5] = {0, 0, 0, 0, 0};  // items of variant v: [off[v], off[v+1])
     float *d_epart = nullptr;
     int *d_bb = nullptr;
-    int smem[4] = {0, 0, 0, 0};
+    int smem[5] = {0, 0, 0, 0, 0};
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // the PML variants run beside the interior kernel
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 };
@@ -981,10 +1026,12 @@ int fused_prepare(waves_handle *h) {
     p->smem[1] = Cfg<1>::WARP_F * 4;
     p->smem[2] = Cfg<2>::WARP_F * 4;
     p->smem[3] = Cfg<3>::WARP_F * 4;
+    p->smem[4] = Cfg<4>::WARP_F * 4;
     cudaError_t ce = cudaFuncSetAttribute(k_fused_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[0]);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[1]);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[2]);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[3]);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[4]);
     if (ce != cudaSuccess) {
         char buf[256];
         snprintf(buf, sizeof(buf), "fused_prepare: cudaFuncSetAttribute: %s (was the library built for sm_100a?)", cudaGetErrorString(ce));
@@ -1001,6 +1048,9 @@ int fused_prepare(waves_handle *h) {
     int r0 = make_map(enc, &h->map_u[0], h->u[0], gp, 12 * gp.n_env, 7);  // total field + U of the incident field
     int r1 = make_map(enc, &h->map_u[1], h->u[1], gp, 12 * gp.n_env, 7);
     int r2 = make_map(enc, &h->map_shape, h->shape, gp, gp.n_env, 1);
+    r0 |= make_map(enc, &h->map_u3[0], h->u[0], gp, 12 * gp.n_env, 3) | make_map(enc, &h->map_u1[0], h->u[0], gp, 12 * gp.n_env, 1);
+    r1 |= make_map(enc, &h->map_u3[1], h->u[1], gp, 12 * gp.n_env, 3) | make_map(enc, &h->map_u1[1], h->u[1], gp, 12 * gp.n_env, 1);
+    r2 |= make_map(enc, &h->map_p, h->pconst, gp, 2 * gp.n_env, 1);
     r0 |= make_map(enc, &h->map_u6[0], h->u[0], gp, 12 * gp.n_env, 6);
     r1 |= make_map(enc, &h->map_u6[1], h->u[1], gp, 12 * gp.n_env, 6);
     if (r0 || r1 || r2) {
@@ -1071,6 +1121,8 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     // change, whatever their values: once one fused step has copied them, BOTH ping-pong buffers hold them and the copy is
     // skipped until something else writes the state (waves_set_state, halo unpack: aux_synced is cleared there).
     A.skip_aux = (h->aux_synced >= 1 && !(dbg_flags & 64)) ? 1 : 0;
+    A.pconst = h->pconst;
+    const bool lean = A.skip_aux && !(dbg_flags & 128);
     static const int dbg_skip = getenv("WAVES_DEBUG_SKIP") ? atoi(getenv("WAVES_DEBUG_SKIP")) : 0;  // developer bisecting aid
     if (h->profile) cudaEventRecord(h->ev0, h->stream);
     // two warps (= CTAs) per item and environment: the total and the incident wavefield.  The PML variants are
@@ -1088,10 +1140,11 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
         cudaStream_t st = (v == 0 || !fork) ? h->stream : p->side[v - 1];
         if (st != h->stream) cudaStreamWaitEvent(st, p->ev_fork, 0);
         const CUtensorMap &m7 = h->map_u[h->cur], &m6 = h->map_u6[h->cur];
-        if (v == 0) k_fused_step<0><<<grid, 32, p->smem[0], st>>>(A, m7, m6, h->map_shape);
-        if (v == 1) k_fused_step<1><<<grid, 32, p->smem[1], st>>>(A, m7, m6, h->map_shape);
-        if (v == 2) k_fused_step<2><<<grid, 32, p->smem[2], st>>>(A, m7, m6, h->map_shape);
-        if (v == 3) k_fused_step<3><<<grid, 32, p->smem[3], st>>>(A, m7, m6, h->map_shape);
+        if (v == 0 && lean) k_fused_step<4><<<grid, 32, p->smem[4], st>>>(A, h->map_u3[h->cur], h->map_u1[h->cur], h->map_p, h->map_shape);
+        if (v == 0 && !lean) k_fused_step<0><<<grid, 32, p->smem[0], st>>>(A, m7, m6, h->map_p, h->map_shape);
+        if (v == 1) k_fused_step<1><<<grid, 32, p->smem[1], st>>>(A, m7, m6, h->map_p, h->map_shape);
+        if (v == 2) k_fused_step<2><<<grid, 32, p->smem[2], st>>>(A, m7, m6, h->map_p, h->map_shape);
+        if (v == 3) k_fused_step<3><<<grid, 32, p->smem[3], st>>>(A, m7, m6, h->map_p, h->map_shape);
         h->launches++;
         if (st != h->stream) {
             cudaEventRecord(p->ev_join[v - 1], st);

@@ -131,6 +131,7 @@ static void free_handle(waves_handle *h) {
     for (int k = 0; k < 9; ++k)
         if (h->adj[k]) cudaFree(h->adj[k]);
     if (h->traj) cudaFree(h->traj);
+    if (h->pconst) cudaFree(h->pconst);
     float **bufs[] = {&h->u[0], &h->u[1], &h->k,      &h->ys,     &h->acc,    &h->b2,     &h->shape,  &h->cplane,
                       &h->d_x,  &h->d_y,  &h->d_sigma, &h->d_cyl0, &h->d_cyl1, &h->d_tspan, &h->d_stage, &h->d_energy};
     for (auto b : bufs)
@@ -222,6 +223,7 @@ extern "C" int waves_create(const waves_config *cfg, waves_handle **out) {
     ALLOC(h->u[0], state);
     ALLOC(h->u[1], state);
     ALLOC(h->shape, (size_t)gp.plane * gp.n_env);
+    ALLOC(h->pconst, (size_t)gp.plane * gp.n_env * 2);
     ALLOC(h->d_x, gp.nx);
     ALLOC(h->d_y, ny_global);
     ALLOC(h->d_sigma, gp.nx);

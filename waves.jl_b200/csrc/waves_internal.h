@@ -50,6 +50,7 @@ struct waves_handle {
     float *b2;            // exact-mode c^2 plane per env [n_env][plane], lazily allocated
     float *shape;         // [n_env][plane] source shape (zeros when NoSource)
     float *cplane;        // [n_env][plane] fixed speed plane, lazily allocated
+    float *pconst;        // [n_env][2][plane]: Psix + Psiy - Omega of the interior cells of both wavefields (kernels_fused.cu)
     float *adj[9];        // adjoint scratch: w, wsum, lk, ly, y1, y2, y3 (state-sized), b2 planes x3 (one block), dL/dc
     float *traj;          // stored forward trajectory [(steps+1)][state]
     long long traj_cap;   // frames
@@ -70,6 +71,9 @@ struct waves_handle {
     float d_omega;
     CUtensorMap map_u[2];   // TMA descriptors over the two state buffers, box = 64 x 1 x 7 planes (total field + U_inc)
     CUtensorMap map_u6[2];  // same tensors, box = 64 x 1 x 6 planes (one wavefield)
+    CUtensorMap map_u3[2];  // box = 64 x 1 x 3 planes (U, Vx, Vy of one wavefield: the lean interior variant)
+    CUtensorMap map_u1[2];  // box = 64 x 1 x 1 plane
+    CUtensorMap map_p;      // the P planes, box = 64 x 1 x 1
     CUtensorMap map_shape;
     bool maps_ready;
     int64_t launches;
