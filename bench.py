@@ -207,7 +207,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_fused_step<V=0..3> launch set (interior + PML strips + corners): one RK4 step of the whole batch",
+                         "kernel": "k_fused_step<V> launch set (lean interior V=4 + PML strips V=1,2 + corners V=3): one RK4 step of the whole batch",
+                         "traffic_note": "ncu dram bytes of one steady-state launch set (profiles/); below the 96 B/cell-update the metric counts because auxiliary fields that are constant in a window are not re-copied",
                          "launch_us": round(per_launch_s * 1e6, 1)},
             "clocks": clocks,
         }
