@@ -96,8 +96,10 @@ struct Cfg {
     static constexpr bool P_REGS = INT && WV_P_REGS && SP == 1;
     static constexpr int ROW_UI = LEAN ? 4 : 6;
     static constexpr int ROW_SH = LEAN ? 5 : 7;
-    static constexpr int ROW_P = SX ? 4 : 3;  // V = 1: Psiy row; V = 0, 2: Psix row; V = 3: unused
-    static constexpr int SLOT_ROWS = INT ? 8 : 10;
+    // V = 0: the Psix row (only when P is not kept in registers); V = 4: the TMA-loaded P row; V = 1, 2: a row no TMA load
+    // ever writes, so storing P needs no cross-proxy fence
+    static constexpr int ROW_P = INT ? 3 : 8;
+    static constexpr int SLOT_ROWS = INT ? 8 : 11;
     static constexpr int SLOT_F = SLOT_ROWS * LW;
     static constexpr int RING_F = RING * SLOT_F;
     static constexpr int CYL_OFF = RING_F;
@@ -107,7 +109,7 @@ struct Cfg {
     static_assert(!(SY && SP != 1), "the sigma_y window and the ghost rows assume SP == 1");
     // row holding kd*c^2 at stage-time index tau
     __host__ __device__ static constexpr int f_bk(int tau) {
-        return LEAN ? (tau == 0 ? 4 : 5 + tau) : (INT ? 4 + tau : (tau == 0 ? 6 : 7 + tau));
+        return LEAN ? (tau == 0 ? 4 : 5 + tau) : (INT ? 4 + tau : (tau == 0 ? 6 : 8 + tau));
     }
 };
 
@@ -205,28 +207,33 @@ __device__ __forceinline__ void tma_issue_row(uint32_t bar, uint32_t bytes, uint
         "r"(bytes), "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(dst_sh), "l"(map_sh), "r"((int)with_shape), "r"(e)
         : "memory");
 }
-// Lean interior: U, Vx, Vy (box of 3 planes), the P plane, U of the incident field for total-field warps, the shape row.
-__device__ __forceinline__ void tma_issue_row_lean(uint32_t bar, uint32_t bytes, uint32_t dst, const CUtensorMap *map3, const CUtensorMap *map1,
-                                                   const CUtensorMap *mapp, const CUtensorMap *map_sh, int c0, int c1, int pl_u, int pl_p,
-                                                   int pl_ui, int e, bool with_ui, bool with_shape, uint32_t row_bytes) {
+// One elected lane issues one TMA load that completes on an already armed mbarrier (uniform operands, whole warp executes).
+__device__ __forceinline__ void tma_issue_one(uint32_t bar, uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2) {
     asm volatile(
         "{\n"
-        ".reg .pred pe, pu, ps;\n"
-        ".reg .b32 d3, d4, d5;\n"
+        ".reg .pred pe;\n"
         "elect.sync _|pe, 0xffffffff;\n"
-        "setp.ne.and.b32 pu, %11, 0, pe;\n"
-        "setp.ne.and.b32 ps, %12, 0, pe;\n"
-        "mad.lo.u32 d3, %13, 3, %2;\n"
-        "add.u32 d4, d3, %13;\n"
-        "add.u32 d5, d4, %13;\n"
-        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
-        "@pe cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%2], [%3, {%7, %8, %9}], [%0];\n"
-        "@pe cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [d3], [%5, {%7, %8, %10}], [%0];\n"
-        "@pu cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [d4], [%4, {%7, %8, %14}], [%0];\n"
-        "@ps cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [d5], [%6, {%7, %8, %15}], [%0];\n"
+        "@pe cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%1], [%2, {%3, %4, %5}], [%0];\n"
         "}\n" ::"r"(bar),
-        "r"(bytes), "r"(dst), "l"(map3), "l"(map1), "l"(mapp), "l"(map_sh), "r"(c0), "r"(c1), "r"(pl_u), "r"(pl_p), "r"((int)with_ui),
-        "r"((int)with_shape), "r"(row_bytes), "r"(pl_ui), "r"(e)
+        "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// Lean interior: arm the mbarrier, load U, Vx, Vy (box of 3 planes) and the P plane.  U of the incident field (total-field
+// warps that accumulate the energies) and the shape row follow as separate loads under warp-uniform branches, so their
+// operands are only marshalled where they are needed.
+__device__ __forceinline__ void tma_issue_row_lean(uint32_t bar, uint32_t bytes, uint32_t dst, const CUtensorMap *map3, const CUtensorMap *mapp,
+                                                   int c0, int c1, int pl_u, int pl_p, uint32_t row_bytes) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        ".reg .b32 d3;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "mad.lo.u32 d3, %9, 3, %2;\n"
+        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+        "@pe cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%2], [%3, {%5, %6, %7}], [%0];\n"
+        "@pe cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [d3], [%4, {%5, %6, %8}], [%0];\n"
+        "}\n" ::"r"(bar),
+        "r"(bytes), "r"(dst), "l"(map3), "l"(mapp), "r"(c0), "r"(c1), "r"(pl_u), "r"(pl_p), "r"(row_bytes)
         : "memory");
 }
 // HBM -> L2 only: keeps more bytes in flight than the shared-memory ring could hold
@@ -532,9 +539,12 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
         if (rp >= 0 && rp < c.nm) {  // warp-uniform
             const uint32_t bar = bar_of<V, PH, PF>(b);
             const uint32_t dst = c.ring_sa + 4u * (uint32_t)(slot_of<V, PH, PF>(b) - c.lane2);
-            if (C::LEAN)
-                tma_issue_row_lean(bar, c.tx_bytes, dst, map_u, map_b, map_c, map_sh, c.x0, c.jbase + c.dir * rp, e * 12 + c.w0 * 6,
-                                   e * 2 + c.w0, e * 12 + 6, e, c.is_tot, c.src_win, LW * 4);
+            if (C::LEAN) {
+                const int jp = c.jbase + c.dir * rp;
+                tma_issue_row_lean(bar, c.tx_bytes, dst, map_u, map_c, c.x0, jp, e * 12 + c.w0 * 6, e * 2 + c.w0, LW * 4);
+                if (c.want_e) tma_issue_one(bar, dst + C::ROW_UI * (LW * 4), map_b, c.x0, jp, e * 12 + 6);
+                if (c.src_win) tma_issue_one(bar, dst + C::ROW_SH * (LW * 4), map_sh, c.x0, jp, e);
+            }
             else
                 tma_issue_row(bar, c.tx_bytes, dst, map_u, c.x0, c.jbase + c.dir * rp, e * 12 + c.w0 * 6, c.src_win,
                               dst + C::ROW_SH * (LW * 4), map_sh, e);
@@ -607,7 +617,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
             }
         }
         // the rows rewritten above are TMA targets again RING rows later: order the generic writes before it
-        if ((!C::P_REGS && !C::LEAN) || c.use_bk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if ((C::INT && !C::P_REGS && !C::LEAN) || c.use_bk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     // 3. the four stages, each one row behind the previous.  Rows below 1 run unguarded (whatever they
     //    compute is overwritten before a stored cell reads it).  Rows beyond a domain border row must not
@@ -685,7 +695,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     // other windows keep a zero row
     c.src_win = ep.has_source && item.x0 < ep.src_i1 && item.x0 + LW > ep.src_i0 && ep.src_j1 > ep.src_j0;
 
-    c.tx_bytes = (C::LEAN ? (4 + (c.is_tot ? 1 : 0) + (c.src_win ? 1 : 0)) : ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0))) * (LW * 4);
+    c.tx_bytes = (C::LEAN ? (4 + (c.want_e ? 1 : 0) + (c.src_win ? 1 : 0)) : ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0))) * (LW * 4);
     if (lane == 0) {
         for (int s = 0; s < C::RING; ++s) mbar_init(c.bar0 + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -967,8 +977,9 @@ int fused_prepare(waves_handle *h) {
     int ri0 = z0 + 4 - gp.grow0, ri1 = z1 - 4 - gp.grow0;
     if (ri0 < own0) ri0 = own0;
     if (ri1 > own1) ri1 = own1;
-    // rows per slab: tall slabs amortise the 8 warm-up rows, but keep >= ~8 waves of warps in flight
-    const int SEG = std::max(48, std::min(192, (int)(2LL * gp.ny_own * (long long)cols.size() * gp.n_env / 14000)));
+    // rows per slab: tall slabs amortise the 8 halo + 8 fill/drain rows, but keep >= ~8 waves of warps in flight; a single
+    // environment is latency-bound by the march length, so short slabs (more, redundant, warps) win there
+    const int SEG = std::max(16, std::min(192, (int)(2LL * gp.ny_own * (long long)cols.size() * gp.n_env / 14000)));
     auto add_rows = [&](int a, int b, bool interior) {
         if (b <= a) return;
         int n = (b - a + SEG - 1) / SEG;
