@@ -151,7 +151,9 @@ typedef struct waves_halo_desc {
 } waves_halo_desc;
 int waves_halo_describe(waves_handle *h, waves_halo_desc *out);
 /* Pack the send rows into two contiguous device buffers / unpack received ghost rows.
- * Buffers are n_planes*block_floats floats each (device). NULL skips that side. */
+ * Buffers are n_planes*block_floats floats each (device). NULL skips that side.
+ * The ghost rows must come from the neighbouring slab of the SAME global state (after waves_set_state on one rank every
+ * rank must set its state too): the fused path caches fields that are constant where sigma is zero. */
 int waves_halo_pack(waves_handle *h, float *lo_buf, float *hi_buf);
 int waves_halo_unpack(waves_handle *h, const float *lo_buf, const float *hi_buf);
 /* CUDA stream (cudaStream_t) the handle launches on, so the caller can order NCCL calls with it. */

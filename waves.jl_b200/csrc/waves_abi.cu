@@ -771,7 +771,9 @@ extern "C" int waves_halo_unpack(waves_handle *h, const float *lo_buf, const flo
     if (gp.ny_own0 == 0) lo_buf = nullptr;
     if (gp.ny_alloc == gp.ny_own0 + gp.ny_own) hi_buf = nullptr;
     if (lo_buf || hi_buf) launch_unpack_halo(h, h->u[h->cur], lo_buf, hi_buf);
-    h->aux_synced = 0;
+    // aux_synced is NOT cleared: the auxiliary fields a window treats as constant are constant in the neighbour's rows too
+    // (same sigma profile), so every exchange delivers the same ghost values for them; new initial conditions arrive through
+    // waves_set_state on every rank, which clears the flag.
     return 0;
 }
 
