@@ -92,3 +92,18 @@ def test_random_pos_gaussian_source_in_bounds():
     d = wb.TwoDim(15.0, 128)
     s = wb.RandomPosGaussianSource(d, [[-10.0, -10.0]], [[-10.0, 10.0]], [0.3], [1.0], 1000.0, rng=np.random.default_rng(3))
     assert s.mu[0, 0] == -10 and -10 <= s.mu[0, 1] <= 10 and s.shape.shape == (128, 128)
+
+
+def test_bench_reference_arm_prints_contract_json():
+    """bench.py --impl reference: the CPU restatement timed on bounded samples; must print ONE JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-rk4-steps", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-800:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config",
+              "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0

@@ -35,47 +35,58 @@ struct Band {
     }
 };
 
-// blockIdx.z = env * 2 + wavefield.  lam, y, out: [n_env][12][plane]; b2: [n_env][plane] or nullptr (scalar c0^2);
-// gcacc: [n_env][plane] or nullptr.
+// blockIdx.z = env * 2 + wavefield.  The cotangent is formed on the fly as lam = a * w + b * lyp (lyp nullable): the step-level
+// reverse (waves_adjoint) never materialises it.  w, lyp, y, out, ws: [n_env][12][plane]; b2: [n_env][plane] or nullptr
+// (scalar c0^2); gcacc: [n_env][plane] or nullptr.  Besides out = J^T lam the kernel keeps the running sum of the step:
+// ws = (first ? w : ws) + out.  out must not alias lyp (neighbouring cells read it).
 __global__ void __launch_bounds__(256)
-k_rhs_transposed(GridP gp, const float *__restrict__ lam, const float *__restrict__ y, const float *__restrict__ b2,
-                 float *__restrict__ out, float *__restrict__ gcacc) {
-    const int e = blockIdx.z >> 1, w = blockIdx.z & 1;
+k_rhs_transposed(GridP gp, float a, const float *__restrict__ w, float b, const float *__restrict__ lyp, const float *__restrict__ y,
+                 const float *__restrict__ b2, float *__restrict__ out, float *__restrict__ ws, int first, float *__restrict__ gcacc) {
+    const int e = blockIdx.z >> 1, wf = blockIdx.z & 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= gp.nx || j >= gp.ny_own) return;
     const long long P = gp.plane;
     const int nxp = gp.nxp, nx = gp.nx, ny = gp.ny_global;
-    const float *L = lam + (long long)e * gp.env_stride + (long long)w * 6 * P;
-    float *O = out + (long long)e * gp.env_stride + (long long)w * 6 * P;
-    const float *bpl = (w == 0 && b2) ? b2 + (long long)e * P : nullptr;
+    const long long base = (long long)e * gp.env_stride + (long long)wf * 6 * P;
+    const float *W = w + base, *LP = lyp ? lyp + base : nullptr;
+    float *O = out + base, *WS = ws + base;
+    const float *bpl = (wf == 0 && b2) ? b2 + (long long)e * P : nullptr;
     Band bx{{gp.g_first[0], gp.g_first[1], gp.g_first[2]}, {gp.g_central[0], gp.g_central[1]}, {gp.g_last[0], gp.g_last[1], gp.g_last[2]}, nx};
     Band by = bx;
     by.n = ny;
     auto mask = [&](int ii, int jj) { return (ii == 0 || ii == nx - 1 || jj == 0 || jj == ny - 1) ? 0.0f : 1.0f; };
     auto bval = [&](int ii, int jj) { return bpl ? bpl[(long long)jj * nxp + ii] : gp.b0; };
-    auto at = [&](int f, int ii, int jj) { return L[(long long)f * P + (long long)jj * nxp + ii]; };
+    auto at = [&](int f, int ii, int jj) {
+        const long long q = (long long)f * P + (long long)jj * nxp + ii;
+        return LP ? a * W[q] + b * LP[q] : a * W[q];
+    };
     const float sx = gp.sigma[i], sy = gp.sigma[j];
     const long long q = (long long)j * nxp + i;
-    const float lU = L[q], lVx = L[P + q], lVy = L[2 * P + q], lPx = L[3 * P + q], lPy = L[4 * P + q], lOm = L[5 * P + q];
+    const float lU = at(0, i, j), lVx = at(1, i, j), lVy = at(2, i, j), lPx = at(3, i, j), lPy = at(4, i, j), lOm = at(5, i, j);
     const float mU = mask(i, j) * lU;
     // Dx^T along i (row j fixed), Dy^T along j (column i fixed)
     const float dxT_lVx = bx.transposed(i, [&](int r) { return at(1, r, j); });
     const float dyT_lVy = by.transposed(j, [&](int r) { return at(2, i, r); });
     const float dxT_qx = bx.transposed(i, [&](int r) { return bval(r, j) * (mask(r, j) * at(0, r, j) + sy * at(4, r, j)); });
     const float dyT_qy = by.transposed(j, [&](int r) { return bval(i, r) * (mask(i, r) * at(0, i, r) + sx * at(3, i, r)); });
-    O[q] = -(sx + sy) * mU + dxT_lVx + dyT_lVy + (sx * sy) * lOm;
-    O[P + q] = dxT_qx - sx * lVx;
-    O[2 * P + q] = dyT_qy - sy * lVy;
-    O[3 * P + q] = mU;
-    O[4 * P + q] = mU;
-    O[5 * P + q] = -mU;
-    if (w == 0 && gcacc) {
+    float o[6];
+    o[0] = -(sx + sy) * mU + dxT_lVx + dyT_lVy + (sx * sy) * lOm;
+    o[1] = dxT_qx - sx * lVx;
+    o[2] = dyT_qy - sy * lVy;
+    o[3] = mU;
+    o[4] = mU;
+    o[5] = -mU;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        O[f * P + q] = o[f];
+        WS[f * P + q] = (first ? W[f * P + q] : WS[f * P + q]) + o[f];
+    }
+    if (wf == 0 && gcacc) {
         const float *Y = y + (long long)e * gp.env_stride;
         const float Vxx = bx.forward(i, [&](int r) { return Y[P + (long long)j * nxp + r]; });
         const float Vyy = by.forward(j, [&](int r) { return Y[2 * P + (long long)r * nxp + i]; });
         const float gb = mU * (Vxx + Vyy) + (sx * lPx) * Vyy + (sy * lPy) * Vxx;
-        const float b = bval(i, j);
-        gcacc[(long long)e * P + q] += 2.0f * sqrtf(b) * gb;
+        gcacc[(long long)e * P + q] += 2.0f * sqrtf(bval(i, j)) * gb;
     }
 }
 
@@ -105,9 +116,10 @@ __global__ void k_energy_cotangent(GridP gp, const float *__restrict__ z, float 
 
 }  // namespace
 
-void launch_rhs_transposed(waves_handle *h, const float *lam, const float *y, const float *b2, float *out, float *gcacc) {
+void launch_rhs_transposed(waves_handle *h, float a, const float *w, float b, const float *lyp, const float *y, const float *b2,
+                           float *out, float *ws, int first, float *gcacc) {
     dim3 blk(32, 8), grd((h->gp.nx + 31) / 32, (h->gp.ny_own + 7) / 8, h->gp.n_env * 2);
-    k_rhs_transposed<<<grd, blk, 0, h->stream>>>(h->gp, lam, y, b2, out, gcacc);
+    k_rhs_transposed<<<grd, blk, 0, h->stream>>>(h->gp, a, w, b, lyp, y, b2, out, ws, first, gcacc);
     h->launches++;
 }
 

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <utility>
 #include <vector>
 
 #include "waves_internal.h"
@@ -623,7 +624,7 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
                         cudaGetErrorString(ce));
         h->traj_cap = steps + 1;
     }
-    float *W = h->adj[0], *WS = h->adj[1], *LK = h->adj[2], *LY = h->adj[3];
+    float *W = h->adj[0], *WS = h->adj[1], *LK = h->adj[2], *LY = h->adj[3];  // W / WS swap roles after every step
     float *Y[3] = {h->adj[4], h->adj[5], h->adj[6]};
     float *B2[3] = {h->adj[7], h->adj[7] + planes, h->adj[7] + 2 * planes};
     float *GC = h->adj[8];
@@ -704,18 +705,13 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
         h->b2 = saved_b2;
         const float *b0 = sp ? B2[0] : nullptr, *b1 = sp ? B2[1] : nullptr, *b2p = sp ? B2[2] : nullptr;
         float *gc = dL_dc ? GC : nullptr;
-        launch_lin3(h, LK, s6, W, 0.0f, nullptr, 0.0f, nullptr);
-        launch_rhs_transposed(h, LK, Y[2], b2p, LY, gc);          // λ_y3 = J4^T λ_k4
-        launch_lin3(h, WS, 1.0f, W, 1.0f, LY, 0.0f, nullptr);
-        launch_lin3(h, LK, s3, W, dt, LY, 0.0f, nullptr);         // λ_k3 = dt/3 w + dt λ_y3
-        launch_rhs_transposed(h, LK, Y[1], b1, LY, gc);           // λ_y2 = J3^T λ_k3
-        launch_lin3(h, WS, 1.0f, WS, 1.0f, LY, 0.0f, nullptr);
-        launch_lin3(h, LK, s3, W, hdt, LY, 0.0f, nullptr);        // λ_k2 = dt/3 w + dt/2 λ_y2
-        launch_rhs_transposed(h, LK, Y[0], b1, LY, gc);           // λ_y1 = J2^T λ_k2
-        launch_lin3(h, WS, 1.0f, WS, 1.0f, LY, 0.0f, nullptr);
-        launch_lin3(h, LK, s6, W, hdt, LY, 0.0f, nullptr);        // λ_k1 = dt/6 w + dt/2 λ_y1
-        launch_rhs_transposed(h, LK, z, b0, LY, gc);              // λ_z = J1^T λ_k1
-        launch_lin3(h, W, 1.0f, WS, 1.0f, LY, 0.0f, nullptr);
+        // each launch forms its cotangent on the fly (a w + b λ_y of the previous stage), returns λ_y = J^T(.) and keeps the
+        // running sum WS = w + λ_y3 + λ_y2 + λ_y1 + λ_z; LK / LY alternate as the λ_y buffers
+        launch_rhs_transposed(h, s6, W, 0.0f, nullptr, Y[2], b2p, LY, WS, 1, gc);  // λ_k4 = dt/6 w           -> λ_y3 = J4^T λ_k4
+        launch_rhs_transposed(h, s3, W, dt, LY, Y[1], b1, LK, WS, 0, gc);          // λ_k3 = dt/3 w + dt λ_y3   -> λ_y2
+        launch_rhs_transposed(h, s3, W, hdt, LK, Y[0], b1, LY, WS, 0, gc);         // λ_k2 = dt/3 w + dt/2 λ_y2 -> λ_y1
+        launch_rhs_transposed(h, s6, W, hdt, LY, z, b0, LK, WS, 0, gc);            // λ_k1 = dt/6 w + dt/2 λ_y1 -> λ_z
+        std::swap(W, WS);                                                          // w <- w + J_step^T w
     };
     if (adj_mode == WAVES_ADJ_EXACT) {
         if (add_cotangent(steps)) return 1;            // λ_N = a_N

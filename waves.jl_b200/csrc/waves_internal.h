@@ -99,7 +99,8 @@ void launch_pack_halo(waves_handle *h, const float *u, float *lo, float *hi);
 void launch_unpack_halo(waves_handle *h, float *u, const float *lo, const float *hi);
 
 // ---- kernels_adjoint.cu ----
-void launch_rhs_transposed(waves_handle *h, const float *lam, const float *y, const float *b2, float *out, float *gcacc);
+void launch_rhs_transposed(waves_handle *h, float a, const float *w, float b, const float *lyp, const float *y, const float *b2,
+                           float *out, float *ws, int first, float *gcacc);
 void launch_lin3(waves_handle *h, float *out, float a, const float *x, float b, const float *y, float c, const float *z);
 void launch_energy_cotangent(waves_handle *h, const float *z, float *w, const float *w3 /*host, 3 weights*/);
 
