@@ -267,7 +267,7 @@ struct WarpCtx {
     float *out_e;      // output state of this env / wavefield at this lane's column pair
     float *pc_e;       // same position in the P plane of this env / wavefield
     int rowstep;       // dir * nxp: floats between consecutive march rows
-    bool xb, first_x, last_x, last_y, is_tot, use_bk, want_e, src_win, in_dom;
+    bool xleft, xright, need_w2, first_x, last_x, last_y, is_tot, use_bk, want_e, src_win, in_dom;
     int w0;
     f2 xs, sx, sxd, bcm;
     float dirf, kdd;   // dir as float, kd * dir
@@ -369,11 +369,16 @@ __device__ __forceinline__ f2 ddx_int(f2 v) {
 __device__ __forceinline__ f2 ddx_gen(const WarpCtx &c, f2 v) {
     const float e = __shfl_down_sync(0xffffffffu, v.x, 1), w = __shfl_up_sync(0xffffffffu, v.y, 1);
     f2 d = mk2(v.y - w, e - v.x);
-    if (c.xb) {  // warp-uniform
-        const float w2 = __shfl_up_sync(0xffffffffu, v.x, 1);
+    // warp-uniform: a window holds the domain's first column, its last one, both (narrow grids) or neither
+    if (c.xleft) {
         if (c.first_x) d.x = (4.0f * v.y - 3.0f * v.x) - e;
+    }
+    if (c.xright) {
         if (c.last_y) d.y = (3.0f * v.y - 4.0f * v.x) + w;
-        if (c.last_x) d.x = (3.0f * v.x - 4.0f * w) + w2;
+        if (c.need_w2) {  // the last column is the first of its pair (odd nx)
+            const float w2 = __shfl_up_sync(0xffffffffu, v.x, 1);
+            if (c.last_x) d.x = (3.0f * v.x - 4.0f * w) + w2;
+        }
     }
     return d;
 }
@@ -682,7 +687,9 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     c.first_x = colA == 0;
     c.last_x = colA == gp.nx - 1;
     c.last_y = colB == gp.nx - 1;
-    c.xb = (item.x0 == 0) || (item.x0 + LW >= gp.nx);
+    c.xleft = item.x0 == 0;
+    c.xright = item.x0 + LW >= gp.nx;
+    c.need_w2 = ((gp.nx - 1 - item.x0) & 1) == 0;
     c.bcm = mk2((c.first_x || c.last_x) ? 0.0f : 1.0f, c.last_y ? 0.0f : 1.0f);
     c.xs = mk2(gp.x[min(colA, gp.nx - 1)], gp.x[min(colB, gp.nx - 1)]);  // columns past nx are never owned
     c.sx = SX ? mk2(gp.sigma[min(colA, gp.nx - 1)], gp.sigma[min(colB, gp.nx - 1)]) : bc2(0.0f);
@@ -979,7 +986,9 @@ int fused_prepare(waves_handle *h) {
     if (ri1 > own1) ri1 = own1;
     // rows per slab: tall slabs amortise the 8 halo + 8 fill/drain rows, but keep >= ~8 waves of warps in flight; a single
     // environment is latency-bound by the march length, so short slabs (more, redundant, warps) win there
-    const int SEG = std::max(16, std::min(192, (int)(2LL * gp.ny_own * (long long)cols.size() * gp.n_env / 14000)));
+    static const int seg_cap = getenv("WAVES_DEBUG_SEGCAP") ? atoi(getenv("WAVES_DEBUG_SEGCAP")) : 192;  // developer tuning aid
+    static const int seg_div = getenv("WAVES_DEBUG_SEGDIV") ? atoi(getenv("WAVES_DEBUG_SEGDIV")) : 14000;
+    const int SEG = std::max(16, std::min(seg_cap, (int)(2LL * gp.ny_own * (long long)cols.size() * gp.n_env / seg_div)));
     auto add_rows = [&](int a, int b, bool interior) {
         if (b <= a) return;
         int n = (b - a + SEG - 1) / SEG;
