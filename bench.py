@@ -126,8 +126,7 @@ def run_ours(args):
     time_step = [0]
 
     def bind_designs(ts):
-        for e in range(E):
-            eng.set_design(hd[e, 0], hd[e, 1], ts[0], ts[-1], env=e)
+        eng.set_design_batch(hd[:, 0], hd[:, 1], ts[0], ts[-1])
 
     def one_step(e2e):
         """One env(action) for the whole batch.  e2e: host design tables in, energy signal out, frames kept on device."""

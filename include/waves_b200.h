@@ -41,6 +41,7 @@ typedef struct waves_handle waves_handle;
 /* integrate/step modes */
 #define WAVES_MODE_FUSED 0 /* one fused kernel per RK4 step (the product path) */
 #define WAVES_MODE_EXACT 1 /* per-stage kernels in the reference's exact float32 evaluation order */
+#define WAVES_STEP_ASYNC 0x100 /* OR into the mode of waves_step: return without synchronising the handle's stream */
 
 /* adjoint modes (src/dynamics.jl:97-118) */
 #define WAVES_ADJ_EXACT 0  /* exact discrete adjoint  lambda_i = a_i + (I+J_i^T) lambda_{i+1} */
@@ -94,6 +95,10 @@ int waves_set_source(waves_handle *h, int env, const float *shape, float freq);
  * of the stacked cylinders (Cloak: config then core, src/designs.jl:228) at ti and tf.
  * ncyl == 0 -> NoDesign: scalar c0 (src/designs.jl:63). */
 int waves_set_design(waves_handle *h, int env, int ncyl, const float *cyl0, const float *cyl1, float ti, float tf);
+
+/* Same for every environment of the handle in one call: cyl0 / cyl1 are HOST (n_env, ncyl, 4) blocks (one DesignInterpolator
+ * per environment over a common [ti, tf]: a batch of WaveEnv stepping in lockstep). */
+int waves_set_design_batch(waves_handle *h, int ncyl, const float *cyl0, const float *cyl1, float ti, float tf);
 
 /* θ[1] = C: t -> a fixed speed plane c (ny, nx) (generic C closure frozen in time). NULL clears it.
  * Slab handles pass ghost rows too, like waves_set_source. */

@@ -40,7 +40,7 @@ stream = torch.cuda.ExternalStream(eng.stream(), device=local)
 
 def run(k):
     for i in range(k):
-        eng.step(float(ts[i % steps]), wb.MODE_FUSED)
+        eng.step(float(ts[i % steps]), wb.MODE_FUSED | wb.STEP_ASYNC)
         if world > 1:
             slab.exchange()
 

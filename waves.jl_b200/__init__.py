@@ -5,7 +5,7 @@ this package is the host-side mirror of the reference's call surface for that pa
 """
 from . import _lib
 from ._lib import WavesError, build
-from .engine import ADJ_COMPAT, ADJ_EXACT, MODE_EXACT, MODE_FUSED, Engine
+from .engine import ADJ_COMPAT, ADJ_EXACT, MODE_EXACT, MODE_FUSED, STEP_ASYNC, Engine
 from .env import AcousticDynamics, Integrator, WaveEnv
 from .parallel import HaloExchanger, SlabEngine, shard_envs, slab_rows
 from .host import (AIR, WATER, Cloak, Cylinders, DesignInterpolator, DesignSpace, NoSource, RandomPosGaussianSource,

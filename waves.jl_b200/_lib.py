@@ -46,6 +46,7 @@ SYMBOLS = {
     "waves_get_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "waves_set_source": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float]),
     "waves_set_design": (C.c_int, [C.c_void_p, C.c_int, C.c_int, fp, fp, C.c_float, C.c_float]),
+    "waves_set_design_batch": (C.c_int, [C.c_void_p, C.c_int, fp, fp, C.c_float, C.c_float]),
     "waves_set_speed_field": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "waves_rhs": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "waves_step": (C.c_int, [C.c_void_p, C.c_float, C.c_int]),

@@ -426,6 +426,15 @@ extern "C" int waves_set_design(waves_handle *h, int env, int ncyl, const float 
     return 0;
 }
 
+extern "C" int waves_set_design_batch(waves_handle *h, int ncyl, const float *cyl0, const float *cyl1, float ti, float tf) {
+    CHECK_H(h);
+    if (ncyl < 0 || (ncyl > 0 && (!cyl0 || !cyl1))) return fail("waves_set_design_batch: bad cylinder arguments");
+    for (int e = 0; e < h->gp.n_env; ++e)
+        if (waves_set_design(h, e, ncyl, cyl0 ? cyl0 + (size_t)e * ncyl * 4 : nullptr, cyl1 ? cyl1 + (size_t)e * ncyl * 4 : nullptr, ti, tf))
+            return 1;
+    return 0;
+}
+
 extern "C" int waves_set_speed_field(waves_handle *h, int env, const float *c) {
     CHECK_H(h);
     const GridP &gp = h->gp;
@@ -516,8 +525,8 @@ extern "C" int waves_step(waves_handle *h, float t, int mode) {
     if (ensure_stage(h, 1) || flush_params(h)) return 1;
     CU_TRY(cudaMemcpyAsync(h->d_tspan, &t, sizeof(float), cudaMemcpyHostToDevice, h->stream));
     launch_stage_table(h, h->d_tspan, 1, h->d_stage);
-    if (step_any(h, 1, 0, mode, nullptr)) return 1;
-    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (step_any(h, 1, 0, mode & ~WAVES_STEP_ASYNC, nullptr)) return 1;
+    if (!(mode & WAVES_STEP_ASYNC)) CU_TRY(cudaStreamSynchronize(h->stream));
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -561,10 +570,16 @@ extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, i
     auto emit = [&](int frame) -> int {
         const float *u = h->u[h->cur];
         if (isave < nsave && save_steps[isave] == frame) {
-            for (int e = 0; e < gp.n_env; ++e)
-                if (copy_planes_fast(h, const_cast<float *>(u) + (size_t)e * gp.env_stride, nullptr,
-                                     frames + ((size_t)e * nsave + isave) * frame_elems, 12))
-                    return 1;
+            if (gp.nxp == gp.nx && gp.ny_alloc == gp.ny_own) {
+                // dense planes: one strided copy moves this frame of every environment
+                CU_TRY(cudaMemcpy2DAsync(frames + (size_t)isave * frame_elems, sizeof(float) * frame_elems * nsave, u,
+                                         sizeof(float) * gp.env_stride, sizeof(float) * frame_elems, gp.n_env, cudaMemcpyDefault, h->stream));
+            } else {
+                for (int e = 0; e < gp.n_env; ++e)
+                    if (copy_planes_fast(h, const_cast<float *>(u) + (size_t)e * gp.env_stride, nullptr,
+                                         frames + ((size_t)e * nsave + isave) * frame_elems, 12))
+                        return 1;
+            }
             ++isave;
         }
         for (int e = 0; e < gp.n_env; ++e) {

@@ -10,6 +10,7 @@ from ._lib import check
 
 F32 = np.float32
 MODE_FUSED, MODE_EXACT = 0, 1
+STEP_ASYNC = 0x100
 ADJ_EXACT, ADJ_COMPAT = 0, 1
 
 
@@ -83,6 +84,13 @@ class Engine:
         assert a.shape == b.shape and a.shape[1] == 4
         check(_lib.lib().waves_set_design(self._h, env, a.shape[0], a.ctypes.data_as(_lib.fp), b.ctypes.data_as(_lib.fp),
                                           C.c_float(ti), C.c_float(tf)))
+
+    def set_design_batch(self, cyl0, cyl1, ti, tf):
+        """One DesignInterpolator per environment over a common [ti, tf]: cyl0 / cyl1 are (n_env, ncyl, 4)."""
+        a, b = np.ascontiguousarray(cyl0, F32), np.ascontiguousarray(cyl1, F32)
+        assert a.shape == b.shape and a.shape[0] == self.n_env and a.shape[2] == 4
+        check(_lib.lib().waves_set_design_batch(self._h, a.shape[1], a.ctypes.data_as(_lib.fp), b.ctypes.data_as(_lib.fp),
+                                                C.c_float(ti), C.c_float(tf)))
 
     def set_speed_field(self, c, env=-1):
         check(_lib.lib().waves_set_speed_field(self._h, env, _ptr(c)))

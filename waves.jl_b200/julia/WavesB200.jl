@@ -92,6 +92,11 @@ function set_design!(h::Handle, interp::DesignInterpolator, env::Integer = -1)
                        h.ptr, env, size(a, 2), a, b, interp.ti, interp.tf))
 end
 
+"""One DesignInterpolator per environment of a batch handle over a common [ti, tf]: `a`, `b` are (4, ncyl, n_env) arrays."""
+set_design_batch!(h::Handle, a::Array{Float32, 3}, b::Array{Float32, 3}, ti::Float32, tf::Float32) =
+    check(h.lib, ccall((:waves_set_design_batch, h.lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{Float32}, Cfloat, Cfloat),
+                       h.ptr, size(a, 2), a, b, ti, tf))
+
 """
     integrate!(h, tspan; save_steps, frames, energy, mode)
 

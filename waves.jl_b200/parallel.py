@@ -107,8 +107,9 @@ class SlabEngine:
         en = np.zeros((steps + 1, 3), dtype=np.float64)
         if energy:
             en[0] = self.engine.energy()[0]
+        from .engine import STEP_ASYNC
         for n in range(steps):
-            self.engine.step(float(tspan[n]), mode)
+            self.engine.step(float(tspan[n]), mode | STEP_ASYNC)   # the exchange is ordered on the engine's stream
             self.exchange()
             if energy:
                 en[n + 1] = self.engine.energy()[0]
