@@ -26,8 +26,9 @@
 //    border row is always the last row of the march; when a stage has produced it, the row beyond it is
 //    filled with the quadratic extrapolation 3 v[n-1] - 3 v[n-2] + v[n-3], which turns the central
 //    difference of the next stage into the reference's one-sided stencil (v[n-3] - 4 v[n-2] + 3 v[n-1]).
-//  * four variants (template V): interior (sigma == 0 in the warp's window: Psi/Omega pass through), left-right
-//    PML strips (only Psix evolves), top-bottom PML strips (only Psiy evolves), corners (everything).
+//  * five variants (template V): interior (sigma == 0 in the warp's window: Psi/Omega pass through) in a full and a
+//    lean form (the lean one reads the constant P = Psix + Psiy - Omega from a plane of its own), left-right PML strips
+//    (only Psix evolves), top-bottom PML strips (only Psiy evolves), corners (everything).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
