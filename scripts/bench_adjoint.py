@@ -11,9 +11,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import waves_b200 as wb  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 500
+E = int(sys.argv[2]) if len(sys.argv) > 2 else 1   # environments differentiated at once (each stores steps+1 states)
 n = 700
 dim = wb.TwoDim(15.0, n)
-eng = wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 2.0, 20000.0)
+eng = wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 2.0, 20000.0, n_env=E)
 eng.set_source(wb.build_normal(dim, [[-10.0, 0.0]], [0.3], [1.0]), 1000.0)
 rng = np.random.default_rng(0)
 d0 = wb.build_triple_ring_design_space().rand(rng)
@@ -21,7 +22,7 @@ ts = wb.build_tspan(0.0, 1e-5, steps)
 eng.set_design(d0.table(), d0.table(), ts[0], ts[-1])
 w = np.zeros((steps + 1, 3), np.float32)
 w[:, 2] = 1.0   # L = sum_t E_sc(t)
-z0 = np.zeros((1, 12, n, n), np.float32)
+z0 = np.zeros((E, 12, n, n), np.float32)
 res = {}
 for mode, name in ((wb.ADJ_EXACT, "exact"), (wb.ADJ_COMPAT, "compat")):
     for rep in range(2):
@@ -30,9 +31,9 @@ for mode, name in ((wb.ADJ_EXACT, "exact"), (wb.ADJ_COMPAT, "compat")):
         t0 = time.perf_counter()
         loss, gz, gc = eng.adjoint(ts, w, adj_mode=mode)
         dt = time.perf_counter() - t0
-    res[name] = {"seconds": round(dt, 3), "Gcell_updates_per_s_fwd_plus_rev": round(2 * n * n * steps / dt / 1e9, 3),
+    res[name] = {"seconds": round(dt, 3), "Gcell_updates_per_s_fwd_plus_rev": round(2 * E * n * n * steps / dt / 1e9, 3),
                  "launches": eng.launch_count() - l0, "loss": float(loss[0]), "norm_dL_dc": float(np.linalg.norm(gc)),
                  "finite": bool(np.isfinite(gc).all() and np.isfinite(gz).all())}
-print(json.dumps({"workload": f"700^2, triple-ring design frozen, {steps} steps, L = sum_t E_sc(t): forward (fused) + reverse sweep",
+print(json.dumps({"workload": f"{E} x 700^2, triple-ring design frozen, {steps} steps, L = sum_t E_sc(t): forward (fused) + reverse sweep",
                   **res}))
 eng.close()

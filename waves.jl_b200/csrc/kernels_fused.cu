@@ -108,6 +108,8 @@ struct Cfg {
     static constexpr int WARP_F = ((BAR_OFF + RING * 2) + 31) & ~31;  // floats per warp (128-byte multiple)
     static_assert(PF + 4 * SP + 1 <= RING, "ring too shallow");
     static_assert(!(SY && SP != 1), "the sigma_y window and the ghost rows assume SP == 1");
+    // row that holds the ambient kd*c0^2 in windows no cylinder touches (never a TMA target, written once); -1: none
+    static constexpr int ROW_BK0 = SY ? 9 : -1;  // (measured: pays on the top-bottom strips and corners only)
     // row holding kd*c^2 at stage-time index tau
     __host__ __device__ static constexpr int f_bk(int tau) {
         return LEAN ? (tau == 0 ? 4 : 5 + tau) : (INT ? 4 + tau : (tau == 0 ? 6 : 8 + tau));
@@ -276,6 +278,7 @@ struct WarpCtx {
     uint32_t bar0, ring_sa;  // shared-window addresses of mbarrier 0 and of the ring
     int nact;          // culled cylinders (0: none touch this window, -1: list overflow -> slow loop)
     uint32_t tx_bytes; // bytes one row's TMA loads deliver
+    int bko[3];        // float offset of the slot row holding kd*c^2 at stage-time index tau (the ambient row without cylinders)
     float cyl_ylo, cyl_yhi;  // rows with y outside (cyl_ylo, cyl_yhi) are not touched by any culled cylinder
 };
 
@@ -428,7 +431,8 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
     // accumulator outlives the 4-slot window when the stages are 2 rows apart)
     constexpr int ar = C::SP == 1 ? 0 : S - 1, aw = C::SP == 1 ? 0 : S;
     const float sf_next = (S == 1 || S == 2) ? c.sf[1] : c.sf[2];
-    const f2 bk = c.use_bk ? lds2(uri + C::f_bk(tau) * LW) : bc2(A.b0kd);  // kd * c^2 (written on arrival)
+    // kd * c^2: written on arrival in windows a cylinder touches, the ambient row otherwise
+    const f2 bk = C::ROW_BK0 >= 0 ? lds2(uri + c.bko[tau]) : (c.use_bk ? lds2(uri + C::f_bk(tau) * LW) : bc2(A.b0kd));
     const f2 uU = lds2(uri), uVx = lds2(uri + LW), uVy = lds2(uri + 2 * LW);
     const f2 ufC = R.Uf[S - 1][sc];
     const f2 vxC = (S == 1) ? uVx : R.Vx[S - 1][sc];
@@ -776,6 +780,11 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
         __syncwarp();
     }
     c.use_bk = c.nact != 0;
+#pragma unroll
+    for (int tau = 0; tau < 3; ++tau) c.bko[tau] = (c.use_bk ? C::f_bk(tau) : C::ROW_BK0) * LW;
+    if (C::ROW_BK0 >= 0 && !c.use_bk)
+        for (int s = 0; s < C::RING; ++s) sts2(s * C::SLOT_F + C::ROW_BK0 * LW + c.lane2, bc2(A.b0kd));
+    __syncwarp();
 
     Regs R;
     R.e_tot = R.e_inc = R.e_sc = bc2(0.0f);
@@ -1033,15 +1042,20 @@ int fused_prepare(waves_handle *h) {
     }
     p->off[4] = (int)all.size();
     if (p->d_items) cudaFree(p->d_items);
-    cudaMalloc((void **)&p->d_items, sizeof(Item) * (all.size() + 1));
-    cudaMemcpy(p->d_items, all.data(), sizeof(Item) * all.size(), cudaMemcpyHostToDevice);
-    cudaMalloc((void **)&p->d_epart, sizeof(float) * 3 * all.size() * gp.n_env);
-    cudaMalloc((void **)&p->d_bb, sizeof(int) * 4);
-    for (int k = 0; k < 3; ++k) {
-        cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking);
-        cudaEventCreateWithFlags(&p->ev_join[k], cudaEventDisableTiming);
+    cudaError_t ae = cudaMalloc((void **)&p->d_items, sizeof(Item) * (all.size() + 1));
+    if (ae == cudaSuccess) ae = cudaMemcpy(p->d_items, all.data(), sizeof(Item) * all.size(), cudaMemcpyHostToDevice);
+    if (ae == cudaSuccess) ae = cudaMalloc((void **)&p->d_epart, sizeof(float) * 3 * all.size() * gp.n_env);
+    if (ae == cudaSuccess) ae = cudaMalloc((void **)&p->d_bb, sizeof(int) * 4);
+    for (int k = 0; k < 3 && ae == cudaSuccess; ++k) {
+        ae = cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking);
+        if (ae == cudaSuccess) ae = cudaEventCreateWithFlags(&p->ev_join[k], cudaEventDisableTiming);
     }
-    cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+    if (ae == cudaSuccess) ae = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+    if (ae != cudaSuccess) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "fused_prepare: %s", cudaGetErrorString(ae));
+        return waves_set_error(buf);
+    }
 
     p->smem[0] = Cfg<0>::WARP_F * 4;  // (ring depth depends on the variant's stage spacing)
     p->smem[1] = Cfg<1>::WARP_F * 4;
