@@ -471,7 +471,9 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
         // U of the stage state without the source term (differs from U + f only inside the source's columns)
         const float sf_cur = (S == 1) ? c.sf[0] : ((S == 4) ? c.sf[2] : c.sf[1]);
         const f2 uC = (S == 1) ? uU : (c.src_win ? fma2(-sf_cur, lds2(uri + C::ROW_SH * LW), ufC) : ufC);
-        const f2 dUx = SX ? ddx_gen(c, ufC) : ddx_int(ufC), dVx = SX ? ddx_gen(c, vxC) : ddx_int(vxC);
+        // d/dx Vx feeds dU (masked to zero on the domain's edge columns) and, with sigma_y != 0, dPsiy: only then does its
+        // one-sided edge form matter
+        const f2 dUx = SX ? ddx_gen(c, ufC) : ddx_int(ufC), dVx = (SX && SY) ? ddx_gen(c, vxC) : ddx_int(vxC);
         const bool brow = SY && c.border && m == c.nm - 1;  // warp-uniform: this is the domain's first / last row
         const f2 dsum = SY ? fma2(c.dirf, dVy, dVx) : dVx + dVy;
         f2 acc, uPx, uPy, uOm, px, py, om;
