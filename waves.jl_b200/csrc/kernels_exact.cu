@@ -111,7 +111,8 @@ __device__ __forceinline__ float d_y(const GridP &gp, const Plane &pl, long long
 __global__ void __launch_bounds__(256)
 k_rhs_exact(GridP gp, const EnvParams *__restrict__ env, int env0, const float *__restrict__ u, float *__restrict__ kout,
             const float *__restrict__ b2, const float *__restrict__ shape, const float *__restrict__ table, int steps,
-            int step, int stage) {
+            int step, int stage, const float *__restrict__ zadd, float za) {
+    // zadd != nullptr: write the RK stage state zadd + za * k instead of k (used by the reverse pass to re-derive y1..y3)
     int e = env0 + (blockIdx.z >> 1), w = blockIdx.z & 1;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int jl = blockIdx.y * blockDim.y + threadIdx.y;
@@ -138,12 +139,10 @@ k_rhs_exact(GridP gp, const EnvParams *__restrict__ env, int env0, const float *
     float Ux = d_x(gp, pUf, row, i);
     float Uy = d_y(gp, pUf, 0, jl, g, i);
     float dU = ((((b * (Vxx + Vyy)) + Px) + Py) - ((sx + sy) * U)) - Om;
-    k[q] = bc * dU;
-    k[P + q] = Ux - (sx * Vx);
-    k[2 * P + q] = Uy - (sy * Vy);
-    k[3 * P + q] = (b * sx) * Vyy;
-    k[4 * P + q] = (b * sy) * Vxx;
-    k[5 * P + q] = (sx * sy) * U;
+    float r6[6] = {bc * dU, Ux - (sx * Vx), Uy - (sy * Vy), (b * sx) * Vyy, (b * sy) * Vxx, (sx * sy) * U};
+    const float *zb = zadd ? zadd + (long long)e * gp.env_stride + (long long)w * 6 * P : nullptr;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) k[f * P + q] = zb ? zb[f * P + q] + za * r6[f] : r6[f];
 }
 
 // runge_kutta accumulation (src/dynamics.jl:10-15): k1 .+ 2*k2 .+ 2*k3 .+ k4 left to right; y = u .+ (a*k)
@@ -252,10 +251,10 @@ void launch_speed2(waves_handle *h, int env0, int nenv, const float *d_table, in
 }
 
 void launch_rhs_exact(waves_handle *h, int env0, int nenv, const float *u_in, float *k_out, const float *d_table,
-                      int steps, int step, int stage) {
+                      int steps, int step, int stage, const float *zadd, float za) {
     dim3 blk(32, 8), grd((h->gp.nx + 31) / 32, (h->gp.ny_alloc + 7) / 8, nenv * 2);
     k_rhs_exact<<<grd, blk, 0, h->stream>>>(h->gp, h->d_env, env0, u_in, k_out, h->b2, h->shape, d_table, steps, step,
-                                            stage);
+                                            stage, zadd, za);
     h->launches++;
 }
 

@@ -687,6 +687,13 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
 
     // ---- reverse sweep ----
     const bool sp = any_speed_plane(h);
+    // a design that does not move (initial == final cylinders, or a frozen speed plane) has one speed field for every stage
+    bool design_static = true, b2_ready = false;
+    for (int e = 0; e < gp.n_env && design_static; ++e) {
+        const EnvParams &ep = h->h_env[e];
+        if (ep.has_cplane || ep.ncyl == 0) continue;
+        design_static = memcmp(h->h_cyl0 + (size_t)e * h->cyl_cap * 4, h->h_cyl1 + (size_t)e * h->cyl_cap * 4, sizeof(float) * 4 * ep.ncyl) == 0;
+    }
     const float dt = gp.dt, hdt = gp.hdt, s6 = dt / 6.0f, s3 = dt / 3.0f;
     CU_TRY(cudaMemsetAsync(GC, 0, sizeof(float) * planes, h->stream));
     CU_TRY(cudaMemsetAsync(W, 0, sizeof(float) * state, h->stream));
@@ -708,14 +715,14 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
     // W <- W + J_step(z_i, t_i)^T W, dL/dc accumulated: the pullback of one runge_kutta call (src/dynamics.jl:105-107)
     auto step_vjp = [&](int i) {
         const float *z = h->traj + (size_t)i * state;
-        if (sp)
+        if (sp && !(design_static && b2_ready))
             for (int tau = 0; tau < 3; ++tau) launch_speed2(h, 0, gp.n_env, h->d_stage, rows, i, tau == 0 ? 0 : (tau == 1 ? 1 : 3), B2[tau]);
+        b2_ready = true;
         float *saved_b2 = h->b2;
-        // forward stage states y1, y2, y3 (k4 is not needed)
+        // forward stage states y1, y2, y3 (k4 is not needed): y_s = z + a k(y_{s-1}) in one launch each
         for (int s = 0; s < 3; ++s) {
             h->b2 = B2[s == 0 ? 0 : 1];
-            launch_rhs_exact(h, 0, gp.n_env, s == 0 ? z : Y[s - 1], h->k, h->d_stage, rows, i, s);
-            launch_lin3(h, Y[s], 1.0f, z, s == 2 ? dt : hdt, h->k, 0.0f, nullptr);
+            launch_rhs_exact(h, 0, gp.n_env, s == 0 ? z : Y[s - 1], Y[s], h->d_stage, rows, i, s, z, s == 2 ? dt : hdt);
         }
         h->b2 = saved_b2;
         const float *b0 = sp ? B2[0] : nullptr, *b1 = sp ? B2[1] : nullptr, *b2p = sp ? B2[2] : nullptr;

@@ -91,7 +91,7 @@ void launch_stage_table(waves_handle *h, const float *d_tspan, int steps, float 
 void launch_speed2(waves_handle *h, int env0, int nenv, const float *d_table, int steps, int step, int stage,
                    float *b2);
 void launch_rhs_exact(waves_handle *h, int env0, int nenv, const float *u_in, float *k_out, const float *d_table,
-                      int steps, int step, int stage);
+                      int steps, int step, int stage, const float *zadd = nullptr, float za = 0.0f);
 void launch_rk_update(waves_handle *h, int stage, const float *u, const float *k, float *acc, float *ys);
 void launch_rk_final(waves_handle *h, const float *u_in, const float *acc, float *u_out);
 void launch_energy(waves_handle *h, const float *u, float *d_e3, int frame_stride3);
