@@ -140,6 +140,16 @@ int waves_integrate(waves_handle *h, const float *tspan, int steps, int mode, fl
 int waves_adjoint(waves_handle *h, const float *tspan, int steps, int fwd_mode, int adj_mode, const float *w_energy,
                   const float *dL_dzN, float *dL_dz0, float *dL_dc, float *loss);
 
+/*
+ * RLBase.state(env) (src/env.jl:132-137): x = imresize(cat(env.wave[:, :, 1, :], env.source.shape; dims = 3), env.resolution).
+ *   frames   the block waves_integrate filled, (n_env, nsave, 12, ny, nx), host or device: the U_tot plane of every saved frame
+ *            is a channel; the handle's own source shape is the last channel
+ *   out      (n_env, nsave + 1, res_y, res_x), host or device
+ * imresize is Images.jl's (third party, version not pinned by the reference: no Manifest): bilinear sampling at
+ * s (i - 1/2) + 1/2, no prefilter, restated from ImageTransformations.jl; needs res <= grid size like src/env.jl:52.
+ */
+int waves_observe(waves_handle *h, const float *frames, int nsave, int res_x, int res_y, float *out);
+
 /* tot/inc/sc energy of the current state (src/env.jl:104-111): e3 (n_env, 3). */
 int waves_energy(waves_handle *h, float *e3);
 

@@ -706,6 +706,32 @@ class WaveEnv:
         return F32(np.sum(self.signal, dtype=np.float64))
 
 
+def imresize_linear(w: np.ndarray, resolution) -> np.ndarray:
+    """`imresize(w, resolution)` as called by RLBase.state (src/env.jl:132-137) for w (channels, ny, nx).
+
+    THIRD PARTY, PARITY UNPINNED: the reference uses Images.jl's imresize (ImageTransformations.jl; no Manifest, so no
+    version).  Its published algorithm for shrinking: `sf = size(original) ./ size(resized)` (Int/Int -> Float64), output
+    pixel i samples the BSpline(Linear()) interpolant of the original at `sf*(i - 0.5) + 0.5` (1-based; pixel-centre
+    alignment, no prefilter), per axis; trailing dimensions not named in `resolution` keep their size.  Weights and
+    coordinates are Float64, the result is rounded once to the element type.
+    """
+    c, ny, nx = w.shape
+    rx, ry = int(resolution[0]), int(resolution[1])
+
+    def taps(n_in, n_out):
+        pos = (n_in / n_out) * (np.arange(n_out, dtype=np.float64) + 0.5) - 0.5   # 0-based
+        i0 = np.floor(pos).astype(np.int64)
+        f = pos - i0
+        return np.clip(i0, 0, n_in - 1), np.clip(i0 + 1, 0, n_in - 1), f
+
+    x0, x1, fx = taps(nx, rx)
+    y0, y1, fy = taps(ny, ry)
+    wd = w.astype(np.float64)
+    top = (1.0 - fx) * wd[:, y0][:, :, x0] + fx * wd[:, y0][:, :, x1]
+    bot = (1.0 - fx) * wd[:, y1][:, :, x0] + fx * wd[:, y1][:, :, x1]
+    return ((1.0 - fy)[None, :, None] * top + fy[None, :, None] * bot).astype(w.dtype)
+
+
 def flatten_repeated_last_dim(x: np.ndarray) -> np.ndarray:
     """src/utils.jl:20-31 for a list of per-action (frames, k) arrays stacked
     as (actions, frames, k): keep all frames of the first action and frames

@@ -158,7 +158,8 @@ def test_waveenv_mirror_matches_oracle_env():
     rng = np.random.default_rng(2)
     d_init = dsg.rand(rng)
     shape = wb.build_normal(dimg, [[-6.0, 1.0]], [0.8], [1.0])
-    envg = wb.WaveEnv(dimg, design_space=dsg, source=wb.Source(shape, 1000.0), dt=2e-5, integration_steps=30, actions=3)
+    envg = wb.WaveEnv(dimg, design_space=dsg, source=wb.Source(shape, 1000.0), dt=2e-5, integration_steps=30, actions=3,
+                      resolution=(64, 64))   # src/env.jl:52: the resolution must be below the grid size
     envg.design = d_init
     envo = wo.WaveEnv(dimo, dso, wo.Source(shape, F32(1000.0)), dt=2e-5, integration_steps=30, actions=3,
                       design=wo.Cloak(wo.Cylinders(d_init.config.pos, d_init.config.r, d_init.config.c),
@@ -360,3 +361,31 @@ def test_full_size_waveenv_actions_match_c_oracle():
         assert np.abs(env.signal - en).max() / scale < TIGHT
         assert rel(env.wave[-1], u) < TIGHT and rel(env.wave[0], fr[0]) < TIGHT
     assert env.time_step == 300 and en[-1, 2] > 0
+
+
+def test_observation_image_matches_restated_imresize():
+    """RLBase.state(env) (src/env.jl:132-137): device-side imresize of (3 U_tot frames + source shape) vs the NumPy restatement;
+    host and device frame blocks, a batch of environments, and the WaveEnv mirror."""
+    import torch
+    n = 200
+    dim = wb.TwoDim(6.0, n)
+    rng = np.random.default_rng(9)
+    eng = wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 1.0, 20000.0, n_env=2)
+    shapes = [wb.build_normal(dim, [[-2.0, 0.5 * e]], [0.4], [1.0]) for e in range(2)]
+    for e in range(2):
+        eng.set_source(shapes[e], 1000.0, env=e)
+    frames = rng.standard_normal((2, 3, 12, n, n)).astype(F32)
+    for res in ((128, 128), (64, 96)):
+        got = eng.observe(frames, res)
+        for e in range(2):
+            want = wo.imresize_linear(np.concatenate([frames[e, :, 0], shapes[e][None]]), res)
+            assert got[e].shape == want.shape and np.abs(got[e] - want).max() <= 1e-6 * np.abs(want).max()
+        dev = eng.observe(torch.from_numpy(frames).cuda(), res, out=torch.empty((2, 4, res[1], res[0]), device="cuda"))
+        assert np.array_equal(dev.cpu().numpy(), got)
+    eng.close()
+    env = wb.WaveEnv(dim, design_space=wb.build_triple_ring_design_space(), source=wb.Source(shapes[0], 1000.0),
+                     integration_steps=20, actions=2, pml_width=1.0, rng=rng)
+    env(env.action_space().rand(rng))
+    ts, x, design = env.state()
+    want = wo.imresize_linear(np.concatenate([env.wave[:, 0], shapes[0][None]]), (128, 128))
+    assert x.shape == (4, 128, 128) and np.abs(x - want).max() <= 1e-6 * max(np.abs(want).max(), 1e-30)

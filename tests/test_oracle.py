@@ -237,3 +237,16 @@ def test_fp64_variant_error_budget():
         out.append(wo.integrate(dyn, u, ts, (lambda t: dyn.c0, src), dim.x.dtype.type(1e-5), keep=False))
     rel = np.linalg.norm(out[0][0] - out[1][0]) / np.linalg.norm(out[1][0])
     assert out[1].dtype == np.float64 and rel < 1e-5
+
+
+def test_imresize_restatement_properties():
+    """The observation resize (third party, unpinned): constants and linear ramps are reproduced exactly at the sampled
+    coordinates s (i - 1/2) + 1/2, channels are independent, equal sizes are the identity."""
+    n, r = 70, 16
+    yy, xx = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64), indexing="ij")
+    w = np.stack([np.full((n, n), 3.5), 2.0 * xx - 1.0, 0.5 * yy + xx]).astype(np.float32)
+    out = wo.imresize_linear(w, (r, r))
+    pos = (n / r) * (np.arange(r) + 0.5) - 0.5
+    assert np.allclose(out[0], 3.5) and np.allclose(out[1], (2.0 * pos - 1.0)[None, :], rtol=1e-6)
+    assert np.allclose(out[2], 0.5 * pos[:, None] + pos[None, :], rtol=1e-6)
+    assert np.array_equal(wo.imresize_linear(w, (n, n)), w)

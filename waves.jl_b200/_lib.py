@@ -52,6 +52,7 @@ SYMBOLS = {
     "waves_step": (C.c_int, [C.c_void_p, C.c_float, C.c_int]),
     "waves_integrate": (C.c_int, [C.c_void_p, fp, C.c_int, C.c_int, C.c_void_p, ip, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
+    "waves_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "waves_energy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "waves_adjoint": (C.c_int, [C.c_void_p, fp, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),

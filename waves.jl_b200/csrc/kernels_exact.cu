@@ -232,7 +232,40 @@ __global__ void k_halo_copy(GridP gp, float *__restrict__ u, float *__restrict__
     }
 }
 
+// imresize(w, resolution) of Images.jl / ImageTransformations.jl (bilinear, no prefilter) for the observation of
+// RLBase.state(env) (src/env.jl:132-137): output pixel i (1-based) samples the input at s (i - 0.5) + 0.5 with s = n_in / n_out
+// along each axis.  Coordinates and weights in double like the reference (Int / Int scale factors), one rounding to float.
+// in: channel c of environment e is at in + e * env_stride + c * chan_stride (pitch nxp); out: (n_env, n_chan, ry, rx).
+__global__ void k_imresize(int nx, int ny, int in_pitch, const float *__restrict__ in, long long env_stride, long long chan_stride, int n_chan,
+                           const float *__restrict__ last, long long last_env_stride, int last_pitch, int rx, int ry,
+                           float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int e = blockIdx.z / (n_chan + 1), c = blockIdx.z - e * (n_chan + 1);
+    if (i >= rx || j >= ry) return;
+    const float *src = c < n_chan ? in + (long long)e * env_stride + (long long)c * chan_stride : last + (long long)e * last_env_stride;
+    const int nxp = c < n_chan ? in_pitch : last_pitch;
+    const double sx = (double)nx / (double)rx, sy = (double)ny / (double)ry;
+    const double x = sx * ((double)i + 0.5) - 0.5, y = sy * ((double)j + 0.5) - 0.5;  // 0-based source coordinates
+    int x0 = (int)floor(x), y0 = (int)floor(y);
+    const double fx = x - (double)x0, fy = y - (double)y0;
+    const int x1 = min(max(x0 + 1, 0), nx - 1), y1 = min(max(y0 + 1, 0), ny - 1);
+    x0 = min(max(x0, 0), nx - 1);
+    y0 = min(max(y0, 0), ny - 1);
+    const double a = src[(long long)y0 * nxp + x0], b = src[(long long)y0 * nxp + x1];
+    const double cc = src[(long long)y1 * nxp + x0], d = src[(long long)y1 * nxp + x1];
+    const double top = (1.0 - fx) * a + fx * b, bot = (1.0 - fx) * cc + fx * d;
+    out[(((long long)e * (n_chan + 1) + c) * ry + j) * rx + i] = (float)((1.0 - fy) * top + fy * bot);
+}
+
 }  // namespace
+
+void launch_imresize(waves_handle *h, const float *in, long long env_stride, long long chan_stride, int n_chan, int in_pitch,
+                     const float *last, long long last_env_stride, int rx, int ry, float *out) {
+    dim3 blk(32, 8), grd((rx + 31) / 32, (ry + 7) / 8, h->gp.n_env * (n_chan + 1));
+    k_imresize<<<grd, blk, 0, h->stream>>>(h->gp.nx, h->gp.ny_own, in_pitch, in, env_stride, chan_stride, n_chan, last, last_env_stride,
+                                          h->gp.nxp, rx, ry, out);
+    h->launches++;
+}
 
 void launch_stage_table(waves_handle *h, const float *d_tspan, int steps, float *d_table) {
     int n = steps * h->gp.n_env;

@@ -133,6 +133,8 @@ static void free_handle(waves_handle *h) {
         if (h->adj[k]) cudaFree(h->adj[k]);
     if (h->traj) cudaFree(h->traj);
     if (h->pconst) cudaFree(h->pconst);
+    if (h->obs_in) cudaFree(h->obs_in);
+    if (h->obs_out) cudaFree(h->obs_out);
     float **bufs[] = {&h->u[0], &h->u[1], &h->k,      &h->ys,     &h->acc,    &h->b2,     &h->shape,  &h->cplane,
                       &h->d_x,  &h->d_y,  &h->d_sigma, &h->d_cyl0, &h->d_cyl1, &h->d_tspan, &h->d_stage, &h->d_energy};
     for (auto b : bufs)
@@ -527,6 +529,51 @@ extern "C" int waves_step(waves_handle *h, float t, int mode) {
     launch_stage_table(h, h->d_tspan, 1, h->d_stage);
     if (step_any(h, 1, 0, mode & ~WAVES_STEP_ASYNC, nullptr)) return 1;
     if (!(mode & WAVES_STEP_ASYNC)) CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int waves_observe(waves_handle *h, const float *frames, int nsave, int res_x, int res_y, float *out) {
+    CHECK_H(h);
+    const GridP &gp = h->gp;
+    if (!frames || !out || nsave < 0 || res_x < 1 || res_y < 1) return fail("waves_observe: bad arguments");
+    if (res_x > gp.nx || res_y > gp.ny_own) return fail("waves_observe: the resolution must not exceed the grid (src/env.jl:52)");
+    if (gp.ny_own != gp.ny_global) return fail("waves_observe: not available on slab handles");
+    cudaPointerAttributes at;
+    const bool in_dev = cudaPointerGetAttributes(&at, frames) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    const bool out_dev = cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    const size_t plane_e = (size_t)gp.ny_own * gp.nx, frame_e = 12 * plane_e;
+    const float *in = frames;
+    long long env_stride = (long long)nsave * frame_e, chan_stride = (long long)frame_e;
+    if (!in_dev && nsave > 0) {  // only the U_tot planes cross to the device
+        const size_t need = (size_t)gp.n_env * nsave * plane_e;
+        if (h->obs_in_cap < need) {
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            if (h->obs_in) cudaFree(h->obs_in);
+            CU_TRY(cudaMalloc((void **)&h->obs_in, sizeof(float) * need));
+            h->obs_in_cap = need;
+        }
+        CU_TRY(cudaMemcpy2DAsync(h->obs_in, sizeof(float) * plane_e, frames, sizeof(float) * frame_e, sizeof(float) * plane_e,
+                                 (size_t)gp.n_env * nsave, cudaMemcpyHostToDevice, h->stream));
+        in = h->obs_in;
+        env_stride = (long long)nsave * plane_e;
+        chan_stride = (long long)plane_e;
+    }
+    const size_t out_e = (size_t)gp.n_env * (nsave + 1) * res_x * res_y;
+    float *dout = out;
+    if (!out_dev) {
+        if (h->obs_out_cap < out_e) {
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            if (h->obs_out) cudaFree(h->obs_out);
+            CU_TRY(cudaMalloc((void **)&h->obs_out, sizeof(float) * out_e));
+            h->obs_out_cap = out_e;
+        }
+        dout = h->obs_out;
+    }
+    launch_imresize(h, in, env_stride, chan_stride, nsave, gp.nx, h->shape, gp.plane, res_x, res_y, dout);
+    if (!out_dev) CU_TRY(cudaMemcpyAsync(out, dout, sizeof(float) * out_e, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
     CU_TRY(cudaGetLastError());
     return 0;
 }

@@ -52,6 +52,8 @@ struct waves_handle {
     float *cplane;        // [n_env][plane] fixed speed plane, lazily allocated
     float *pconst;        // [n_env][2][plane]: Psix + Psiy - Omega of the interior cells of both wavefields (kernels_fused.cu)
     float *adj[9];        // adjoint scratch: w, wsum, lk, ly, y1, y2, y3 (state-sized), b2 planes x3 (one block), dL/dc
+    float *obs_in, *obs_out;  // observation scratch (waves_observe)
+    size_t obs_in_cap, obs_out_cap;
     float *traj;          // stored forward trajectory [(steps+1)][state]
     long long traj_cap;   // frames
     float *d_x, *d_y, *d_sigma;
@@ -95,6 +97,8 @@ void launch_rhs_exact(waves_handle *h, int env0, int nenv, const float *u_in, fl
 void launch_rk_update(waves_handle *h, int stage, const float *u, const float *k, float *acc, float *ys);
 void launch_rk_final(waves_handle *h, const float *u_in, const float *acc, float *u_out);
 void launch_energy(waves_handle *h, const float *u, float *d_e3, int frame_stride3);
+void launch_imresize(waves_handle *h, const float *in, long long env_stride, long long chan_stride, int n_chan, int in_pitch,
+                     const float *last, long long last_env_stride, int rx, int ry, float *out);
 void launch_pack_halo(waves_handle *h, const float *u, float *lo, float *hi);
 void launch_unpack_halo(waves_handle *h, float *u, const float *lo, const float *hi);
 

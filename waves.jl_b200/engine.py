@@ -132,6 +132,16 @@ class Engine:
                                        _ptr(gz), _ptr(gc), _ptr(loss)))
         return loss, gz, gc
 
+    def observe(self, frames, resolution=(128, 128), out=None):
+        """RLBase.state(env) image (src/env.jl:132-137): imresize(cat(U_tot of the saved frames, source shape), resolution).
+        frames: (n_env, nsave, 12, ny, nx) as filled by integrate (NumPy or CUDA tensor) -> (n_env, nsave + 1, res_y, res_x)."""
+        nsave = int(frames.shape[1])
+        rx, ry = int(resolution[0]), int(resolution[1])
+        if out is None:
+            out = np.empty((self.n_env, nsave + 1, ry, rx), dtype=F32)
+        check(_lib.lib().waves_observe(self._h, _ptr(frames), nsave, rx, ry, _ptr(out)))
+        return out
+
     def energy(self):
         out = np.empty((self.n_env, 3), dtype=F32)
         check(_lib.lib().waves_energy(self._h, _ptr(out)))

@@ -62,12 +62,15 @@ class WaveEnv:
     """WaveEnv(dim; design_space, source, ...) (src/env.jl:14-67) with `env(action)` (src/env.jl:91-121)."""
 
     def __init__(self, dim: TwoDim, design_space=None, source=None, action_speed=250.0, c0=WATER, pml_width=2.0,
-                 pml_scale=20000.0, dt=1e-5, integration_steps=100, actions=10, device=0, mode=MODE_FUSED, rng=None):
+                 pml_scale=20000.0, dt=1e-5, integration_steps=100, actions=10, device=0, mode=MODE_FUSED, rng=None,
+                 resolution=(128, 128)):
         self.dim, self.design_space = dim, design_space
         self.source = source if source is not None else NoSource()
         self.rng = rng or np.random.default_rng()
         self.action_speed, self.dt = F32(action_speed), F32(dt)
         self.integration_steps, self.actions = int(integration_steps), int(actions)
+        self.resolution = tuple(resolution)
+        assert all(n > r for n, r in zip(dim.size(), self.resolution)), "Resolution must be less than finite element grid."
         self.design = design_space.rand(self.rng) if design_space is not None else None
         self.iter = Integrator(AcousticDynamics(dim, c0, pml_width, pml_scale), dt, 1, device, mode)
         nx, ny = dim.size()
@@ -94,6 +97,11 @@ class WaveEnv:
         self.source.reset(self.rng)
         self.iter.engine.set_state(self.wave[-1][None])
         self._source_bound = None
+
+    def state(self):  # src/env.jl:132-137
+        """(tspan, x, design) with x = imresize(cat(u_tot frames, source shape), resolution) as (4, res_y, res_x)."""
+        x = self.iter.engine.observe(np.ascontiguousarray(self.wave[None]), self.resolution)[0]
+        return self.build_tspan(), x, self.design
 
     def action_space(self):  # src/env.jl:143-145
         return build_action_space(self.design, F32(F32(self.action_speed * self.dt) * F32(self.integration_steps)))

@@ -92,6 +92,20 @@ function set_design!(h::Handle, interp::DesignInterpolator, env::Integer = -1)
                        h.ptr, env, size(a, 2), a, b, interp.ti, interp.tf))
 end
 
+"""
+    observe(h, frames, resolution)
+
+The image of `RLBase.state(env)` (src/env.jl:132-137) computed on the device: `imresize(cat(frames[:, :, 1, :], shape; dims = 3),
+resolution)` for the `(nx, ny, 12, nsave)` block `integrate!` returned.  Returns `(res_x, res_y, nsave + 1)`.
+"""
+function observe(h::Handle, frames::Array{Float32, 4}, resolution::Tuple{Int, Int})
+    nsave = size(frames, 4)
+    out = Array{Float32}(undef, resolution[1], resolution[2], nsave + 1)
+    check(h.lib, ccall((:waves_observe, h.lib), Cint, (Ptr{Cvoid}, Ptr{Float32}, Cint, Cint, Cint, Ptr{Float32}),
+                       h.ptr, frames, nsave, resolution[1], resolution[2], out))
+    return out
+end
+
 """One DesignInterpolator per environment of a batch handle over a common [ti, tf]: `a`, `b` are (4, ncyl, n_env) arrays."""
 set_design_batch!(h::Handle, a::Array{Float32, 3}, b::Array{Float32, 3}, ti::Float32, tf::Float32) =
     check(h.lib, ccall((:waves_set_design_batch, h.lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{Float32}, Cfloat, Cfloat),
