@@ -738,3 +738,14 @@ def flatten_repeated_last_dim(x: np.ndarray) -> np.ndarray:
     2..end of every later one."""
     parts = [x[0]] + [xi[1:] for xi in x[1:]]
     return np.concatenate(parts, axis=0)
+
+
+def prepare_data(t_list, y_list, horizon: int):
+    """prepare_data (src/data.jl:35-58) for the tspans (steps+1,) and signals (steps+1, 3) of one episode: windows of `horizon`
+    consecutive actions with the repeated boundary sample dropped (flatten_repeated_last_dim, src/utils.jl:20-31)."""
+    t, y = [], []
+    n = horizon - 1
+    for i in range(len(t_list) - n):
+        t.append(flatten_repeated_last_dim(np.stack(t_list[i:i + horizon])))
+        y.append(flatten_repeated_last_dim(np.stack(y_list[i:i + horizon])))
+    return t, y

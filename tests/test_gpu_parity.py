@@ -389,3 +389,29 @@ def test_observation_image_matches_restated_imresize():
     ts, x, design = env.state()
     want = wo.imresize_linear(np.concatenate([env.wave[:, 0], shapes[0][None]]), (128, 128))
     assert x.shape == (4, 128, 128) and np.abs(x - want).max() <= 1e-6 * max(np.abs(want).max(), 1e-30)
+
+
+def test_batch_env_and_episode_layer():
+    """BatchWaveEnv: environments stepping in lockstep on one handle are bitwise the single-environment WaveEnv; the episode
+    layer (generate_episode!, prepare_data: src/data.jl:12-58) on top of both."""
+    n, steps, actions, E = 128, 20, 4, 3
+    dim = wb.TwoDim(15.0, n)
+    ds = wb.build_triple_ring_design_space()
+    shapes = [wb.build_normal(dim, [[-6.0 + e, 1.0 - e]], [0.8], [1.0]) for e in range(E)]
+    kw = dict(dt=2e-5, integration_steps=steps, actions=actions, resolution=(32, 32))
+    benv = wb.BatchWaveEnv(dim, ds, [wb.Source(s, 1000.0) for s in shapes], rngs=[np.random.default_rng(10 + e) for e in range(E)], **kw)
+    pol_rngs = [np.random.default_rng(100 + e) for e in range(E)]
+    eps = wb.generate_episodes([lambda env, e=e: env.action_spaces()[e].rand(pol_rngs[e]) for e in range(E)], benv)
+    assert benv.is_terminated() and all(len(ep) == actions for ep in eps)
+    for e in range(E):
+        env = wb.WaveEnv(dim, design_space=ds, source=wb.Source(shapes[e], 1000.0), rng=np.random.default_rng(10 + e), **kw)
+        prng = np.random.default_rng(100 + e)
+        ep = wb.generate_episode(lambda env_: env_.action_space().rand(prng), env, reset=False)
+        assert len(ep) == actions
+        for k in range(actions):
+            assert np.array_equal(ep.y[k], eps[e].y[k]) and np.array_equal(ep.t[k], eps[e].t[k])
+            assert np.array_equal(ep.s[k][1], eps[e].s[k][1])                       # observation image
+            assert np.array_equal(ep.a[k].table(), eps[e].a[k].table())
+        assert np.array_equal(env.wave, benv.wave[e])
+        s, a, t, y = wb.prepare_data(ep, 2)
+        assert len(y) == actions - 1 and y[0].shape == (2 * steps + 1, 3) and t[0].shape == (2 * steps + 1,)

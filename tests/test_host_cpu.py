@@ -107,3 +107,29 @@ def test_bench_reference_arm_prints_contract_json():
               "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_prepare_data_mirror_matches_restatement():
+    """prepare_data / flatten_repeated_last_dim (src/data.jl:35-58, src/utils.jl:20-31): host bookkeeping of the episode layer."""
+    rng = np.random.default_rng(0)
+    steps, actions, horizon = 10, 6, 3
+    ep = wb.Episode()
+    t0 = 0.0
+    for k in range(actions):
+        ts = wb.build_tspan(np.float32(t0), 1e-5, steps)
+        t0 = ts[-1]
+        y = rng.standard_normal((steps + 1, 3)).astype(np.float32)
+        if ep.y:
+            y[0] = ep.y[-1][-1]      # consecutive actions share their boundary frame (SURVEY Appendix B-5)
+        ep.s.append((ts, None, None))
+        ep.a.append(k)
+        ep.t.append(ts)
+        ep.y.append(y)
+    s, a, t, y = wb.prepare_data(ep, horizon)
+    to, yo = wo.prepare_data(ep.t, ep.y, horizon)
+    assert len(s) == len(a) == len(t) == len(y) == actions - horizon + 1 == len(to)
+    for i in range(len(t)):
+        assert t[i].shape == (horizon * steps + 1,) and y[i].shape == (horizon * steps + 1, 3)
+        assert np.array_equal(t[i], to[i]) and np.array_equal(y[i], yo[i])
+        assert a[i] == list(range(i, i + horizon)) and s[i] is ep.s[i]
+        assert np.all(np.diff(t[i]) > 0)

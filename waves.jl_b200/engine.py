@@ -63,6 +63,8 @@ class Engine:
 
     # state -------------------------------------------------------------------
     def set_state(self, u12, env=-1):
+        if isinstance(u12, np.ndarray):
+            u12 = np.ascontiguousarray(u12, F32)
         check(_lib.lib().waves_set_state(self._h, env, _ptr(u12)))
 
     def get_state(self, env=-1, out=None):

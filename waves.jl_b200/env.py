@@ -98,8 +98,14 @@ class WaveEnv:
         self.iter.engine.set_state(self.wave[-1][None])
         self._source_bound = None
 
+    def _bind_source(self):
+        if self._source_bound is not self.source.shape:
+            self.iter.engine.set_source(self.source.shape, float(self.source.freq))
+            self._source_bound = self.source.shape
+
     def state(self):  # src/env.jl:132-137
         """(tspan, x, design) with x = imresize(cat(u_tot frames, source shape), resolution) as (4, res_y, res_x)."""
+        self._bind_source()
         x = self.iter.engine.observe(np.ascontiguousarray(self.wave[None]), self.resolution)[0]
         return self.build_tspan(), x, self.design
 
@@ -122,9 +128,7 @@ class WaveEnv:
             nxt = self.design_space(self.design, action)
             interp = DesignInterpolator(self.design, nxt, ti, tspan[-1])
             eng.set_design(self.design.table(), nxt.table(), ti, tspan[-1])
-        if self._source_bound is not self.source.shape:
-            eng.set_source(self.source.shape, float(self.source.freq))
-            self._source_bound = self.source.shape
+        self._bind_source()
         n = self.integration_steps
         ny, nx = self.wave.shape[2:]
         u_tot = np.empty((1, n + 1, ny, nx), F32) if return_frames else None
