@@ -415,3 +415,16 @@ def test_batch_env_and_episode_layer():
         assert np.array_equal(env.wave, benv.wave[e])
         s, a, t, y = wb.prepare_data(ep, 2)
         assert len(y) == actions - 1 and y[0].shape == (2 * steps + 1, 3) and t[0].shape == (2 * steps + 1,)
+
+
+def test_randomized_fused_vs_exact_sweep():
+    """A slice of scripts/fuzz_fused_vs_exact.py (310 random cases were green when this was written): random grid sizes
+    (odd, not multiples of 4, narrower than one window), PML widths, moving designs with up to 40 cylinders, sources,
+    batches -- the fused path against the exact per-stage kernels, which are bit-exact to the oracle."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_fused_vs_exact.py"), "16", "123"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert "FAIL" not in r.stdout and "worst" in r.stdout, r.stdout[-1500:]
+    assert float(r.stdout.strip().splitlines()[-1].split()[1]) < 2e-5
