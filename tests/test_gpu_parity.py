@@ -12,6 +12,7 @@ from oracle import c_oracle as co
 from oracle import waves_oracle as wo
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 F32 = np.float32
 TOL = 1e-4        # stated tolerance
 TIGHT = 2e-5      # what the fused kernel actually delivers (FMA contraction + reassociated stencils)
