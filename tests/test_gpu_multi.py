@@ -19,29 +19,29 @@ import waves_b200 as wb
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-n, steps = 512, 12
-dim = wb.TwoDim(11.0, n)
-rng = np.random.default_rng(0)
-u0 = (rng.standard_normal((12, n, n)) * 1e-3).astype(np.float32)
-shape = wb.build_normal(dim, [[-3.0, 0.4]], [0.3], [1.0])
-ts = wb.build_tspan(0.0, 1e-5, steps)
-slab = wb.SlabEngine(dim.x, dim.y, wb.WATER, 1e-5, 2.0, 20000.0, device=local)
-slab.set_source_global(shape, 1000.0)
 out = {}
-for mode in (wb.MODE_FUSED, wb.MODE_EXACT):
-    slab.set_state_global(u0)
-    en = slab.integrate(ts, mode)
-    full = slab.gather_state()
-    if rank == 0:
-        eng = wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 2.0, 20000.0, device=0)
-        eng.set_state(u0[None]); eng.set_source(shape, 1000.0)
-        ren, _ = eng.integrate(ts, mode)
-        ref = eng.get_state(0)
-        out[mode] = (bool(np.array_equal(full, ref)), float(np.abs(full - ref).max()), float(np.abs(en - ren[0]).max() / ren[0].max()))
-        eng.close()
+for n, steps, gs in ((512, 12, 11.0), (257, 9, 5.5)):   # 257: odd row count, pitch != nx
+    dim = wb.TwoDim(gs, n)
+    rng = np.random.default_rng(n)
+    u0 = (rng.standard_normal((12, n, n)) * 1e-3).astype(np.float32)
+    shape = wb.build_normal(dim, [[-0.3 * gs, 0.04 * gs]], [0.03 * gs], [1.0])
+    ts = wb.build_tspan(0.0, 1e-5, steps)
+    slab = wb.SlabEngine(dim.x, dim.y, wb.WATER, 1e-5, 0.2 * gs, 20000.0, device=local)
+    slab.set_source_global(shape, 1000.0)
+    for mode in (wb.MODE_FUSED, wb.MODE_EXACT):
+        slab.set_state_global(u0)
+        en = slab.integrate(ts, mode)
+        full = slab.gather_state()
+        if rank == 0:
+            eng = wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 0.2 * gs, 20000.0, device=0)
+            eng.set_state(u0[None]); eng.set_source(shape, 1000.0)
+            ren, _ = eng.integrate(ts, mode)
+            ref = eng.get_state(0)
+            out[(n, mode)] = (bool(np.array_equal(full, ref)), float(np.abs(full - ref).max()), float(np.abs(en - ren[0]).max() / ren[0].max()))
+            eng.close()
+    slab.close()
 if rank == 0:
     print("RESULT", out)
-slab.close()
 dist.barrier(); dist.destroy_process_group()
 '''
 
