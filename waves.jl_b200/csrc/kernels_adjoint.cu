@@ -23,8 +23,9 @@ struct Band {
         float acc = 0.0f;
         if (i + 1 <= n - 2) acc += gc[0] * v(i + 1);          // interior row r = i+1 holds gc[0] on column r-1
         if (i - 1 >= 1) acc += gc[1] * v(i - 1);              // interior row r = i-1 holds gc[1] on column r+1
-        if (i <= 2) acc += gf[i] * v(0);                      // first row: columns 0,1,2
-        if (i >= n - 3) acc += gl[i - (n - 3)] * v(n - 1);    // last row: columns n-3,n-2,n-1
+        // (selects instead of gf[i]: dynamic indexing would put the coefficient arrays in local memory)
+        if (i <= 2) acc += (i == 0 ? gf[0] : (i == 1 ? gf[1] : gf[2])) * v(0);                             // first row: columns 0,1,2
+        if (i >= n - 3) acc += (i == n - 3 ? gl[0] : (i == n - 2 ? gl[1] : gl[2])) * v(n - 1);           // last row: columns n-3,n-2,n-1
         return acc;
     }
     template <class F>
