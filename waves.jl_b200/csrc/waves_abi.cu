@@ -142,11 +142,12 @@ static void free_handle(waves_handle *h) {
     if (h->d_env) cudaFree(h->d_env);
     if (h->d_epart) cudaFree(h->d_epart);
     fused_release(h);
-    free(h->h_env);
-    free(h->h_cyl0);
-    free(h->h_cyl1);
+    if (h->h_env) cudaFreeHost(h->h_env);
+    if (h->h_cyl0) cudaFreeHost(h->h_cyl0);
+    if (h->h_cyl1) cudaFreeHost(h->h_cyl1);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_params) cudaEventDestroy(h->ev_params);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -234,9 +235,18 @@ extern "C" int waves_create(const waves_config *cfg, waves_handle **out) {
     h->cyl_cap = 32;
     ALLOC(h->d_cyl0, (size_t)gp.n_env * h->cyl_cap * 4);
     ALLOC(h->d_cyl1, (size_t)gp.n_env * h->cyl_cap * 4);
-    h->h_cyl0 = (float *)calloc((size_t)gp.n_env * h->cyl_cap * 4, sizeof(float));
-    h->h_cyl1 = (float *)calloc((size_t)gp.n_env * h->cyl_cap * 4, sizeof(float));
-    h->h_env = (EnvParams *)calloc(gp.n_env, sizeof(EnvParams));
+    // pinned host staging of the per-environment parameters: their upload is a true asynchronous copy
+    {
+        const size_t cb = sizeof(float) * 4 * (size_t)gp.n_env * h->cyl_cap;
+        if (cudaMallocHost((void **)&h->h_cyl0, cb) != cudaSuccess || cudaMallocHost((void **)&h->h_cyl1, cb) != cudaSuccess ||
+            cudaMallocHost((void **)&h->h_env, sizeof(EnvParams) * gp.n_env) != cudaSuccess) {
+            free_handle(h);
+            return fail("waves_create: cudaMallocHost failed");
+        }
+        memset(h->h_cyl0, 0, cb);
+        memset(h->h_cyl1, 0, cb);
+        memset(h->h_env, 0, sizeof(EnvParams) * gp.n_env);
+    }
     h->epart_blocks = 64;
     ALLOC(h->d_epart, (size_t)gp.n_env * h->epart_blocks * 3);
     cudaMemcpy(h->d_x, cfg->x, sizeof(float) * gp.nx, cudaMemcpyHostToDevice);
@@ -249,6 +259,7 @@ extern "C" int waves_create(const waves_config *cfg, waves_handle **out) {
     h->cyl_dirty = true;
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
+    cudaEventCreateWithFlags(&h->ev_params, cudaEventDisableTiming);
     if (fused_prepare(h)) {
         free_handle(h);
         return 1;  // message set by fused_prepare
@@ -275,7 +286,13 @@ extern "C" int waves_sync(waves_handle *h) {
 
 extern "C" void *waves_stream(waves_handle *h) { return h ? (void *)h->stream : nullptr; }
 
+// host writes to the pinned staging buffers must wait for the last upload that reads them
+static void staging_writable(waves_handle *h) {
+    if (h->ev_params) cudaEventSynchronize(h->ev_params);
+}
+
 static int flush_params(waves_handle *h) {
+    const bool any = h->env_dirty || h->cyl_dirty;
     if (h->env_dirty) {
         CU_TRY(cudaMemcpyAsync(h->d_env, h->h_env, sizeof(EnvParams) * h->gp.n_env, cudaMemcpyHostToDevice, h->stream));
         h->env_dirty = false;
@@ -286,6 +303,7 @@ static int flush_params(waves_handle *h) {
         CU_TRY(cudaMemcpyAsync(h->d_cyl1, h->h_cyl1, n, cudaMemcpyHostToDevice, h->stream));
         h->cyl_dirty = false;
     }
+    if (any) CU_TRY(cudaEventRecord(h->ev_params, h->stream));
     return 0;
 }
 
@@ -360,6 +378,7 @@ extern "C" int waves_set_source(waves_handle *h, int env, const float *shape, fl
     const GridP &gp = h->gp;
     if (env >= gp.n_env) return fail("waves_set_source: env %d out of range", env);
     int e0 = env < 0 ? 0 : env, e1 = env < 0 ? gp.n_env : env + 1;
+    staging_writable(h);
     for (int e = e0; e < e1; ++e) {
         EnvParams &ep = h->h_env[e];
         float *d = h->shape + (size_t)e * gp.plane;
@@ -395,14 +414,18 @@ extern "C" int waves_set_design(waves_handle *h, int env, int ncyl, const float 
     if (ncyl > h->cyl_cap) {
         int cap = h->cyl_cap;
         while (cap < ncyl) cap *= 2;
-        float *n0 = (float *)calloc((size_t)gp.n_env * cap * 4, sizeof(float));
-        float *n1 = (float *)calloc((size_t)gp.n_env * cap * 4, sizeof(float));
+        float *n0 = nullptr, *n1 = nullptr;
+        CU_TRY(cudaStreamSynchronize(h->stream));  // a pending upload may still read the old staging buffers
+        CU_TRY(cudaMallocHost((void **)&n0, sizeof(float) * 4 * (size_t)gp.n_env * cap));
+        CU_TRY(cudaMallocHost((void **)&n1, sizeof(float) * 4 * (size_t)gp.n_env * cap));
+        memset(n0, 0, sizeof(float) * 4 * (size_t)gp.n_env * cap);
+        memset(n1, 0, sizeof(float) * 4 * (size_t)gp.n_env * cap);
         for (int e = 0; e < gp.n_env; ++e) {
             memcpy(n0 + (size_t)e * cap * 4, h->h_cyl0 + (size_t)e * h->cyl_cap * 4, sizeof(float) * 4 * h->cyl_cap);
             memcpy(n1 + (size_t)e * cap * 4, h->h_cyl1 + (size_t)e * h->cyl_cap * 4, sizeof(float) * 4 * h->cyl_cap);
         }
-        free(h->h_cyl0);
-        free(h->h_cyl1);
+        cudaFreeHost(h->h_cyl0);
+        cudaFreeHost(h->h_cyl1);
         h->h_cyl0 = n0;
         h->h_cyl1 = n1;
         CU_TRY(cudaStreamSynchronize(h->stream));
@@ -413,6 +436,7 @@ extern "C" int waves_set_design(waves_handle *h, int env, int ncyl, const float 
         h->cyl_cap = cap;
     }
     int e0 = env < 0 ? 0 : env, e1 = env < 0 ? gp.n_env : env + 1;
+    staging_writable(h);
     for (int e = e0; e < e1; ++e) {
         EnvParams &ep = h->h_env[e];
         ep.ncyl = ncyl;
@@ -446,6 +470,7 @@ extern "C" int waves_set_speed_field(waves_handle *h, int env, const float *c) {
         CU_TRY(cudaMalloc((void **)&h->cplane, sizeof(float) * (size_t)gp.plane * gp.n_env));
         CU_TRY(cudaMemsetAsync(h->cplane, 0, sizeof(float) * (size_t)gp.plane * gp.n_env, h->stream));
     }
+    staging_writable(h);
     for (int e = e0; e < e1; ++e) {
         h->h_env[e].has_cplane = c ? 1 : 0;
         if (c && copy_plane_with_ghosts(h, h->cplane + (size_t)e * gp.plane, c)) return 1;

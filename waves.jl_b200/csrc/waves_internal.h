@@ -83,6 +83,7 @@ struct waves_handle {
     double fused_ms;
     int64_t fused_launches;
     cudaEvent_t ev0, ev1;
+    cudaEvent_t ev_params;  // recorded after every upload of h_env / h_cyl*: the (pinned) staging may be rewritten once it completed
     int fused_smem;
     int sm_count;
     void *plan;  // FusedPlan (kernels_fused.cu)
