@@ -6,6 +6,7 @@ import sys
 import time
 
 import numpy as np
+import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import waves_b200 as wb  # noqa: E402
@@ -23,17 +24,19 @@ eng.set_design(d0.table(), d0.table(), ts[0], ts[-1])
 w = np.zeros((steps + 1, 3), np.float32)
 w[:, 2] = 1.0   # L = sum_t E_sc(t)
 z0 = np.zeros((E, 12, n, n), np.float32)
+gz_d = torch.empty((E, 12, n, n), dtype=torch.float32, device="cuda")   # gradients stay on the device
+gc_d = torch.empty((E, n, n), dtype=torch.float32, device="cuda")
 res = {}
 for mode, name in ((wb.ADJ_EXACT, "exact"), (wb.ADJ_COMPAT, "compat")):
     for rep in range(2):
         eng.set_state(z0)
         l0 = eng.launch_count()
         t0 = time.perf_counter()
-        loss, gz, gc = eng.adjoint(ts, w, adj_mode=mode)
+        loss, gz, gc = eng.adjoint(ts, w, adj_mode=mode, out_dz0=gz_d, out_dc=gc_d)
         dt = time.perf_counter() - t0
     res[name] = {"seconds": round(dt, 3), "Gcell_updates_per_s_fwd_plus_rev": round(2 * E * n * n * steps / dt / 1e9, 3),
-                 "launches": eng.launch_count() - l0, "loss": float(loss[0]), "norm_dL_dc": float(np.linalg.norm(gc)),
-                 "finite": bool(np.isfinite(gc).all() and np.isfinite(gz).all())}
+                 "launches": eng.launch_count() - l0, "loss": float(loss[0]), "norm_dL_dc": float(gc.norm().item()),
+                 "finite": bool(torch.isfinite(gc).all().item() and torch.isfinite(gz).all().item())}
 print(json.dumps({"workload": f"{E} x 700^2, triple-ring design frozen, {steps} steps, L = sum_t E_sc(t): forward (fused) + reverse sweep",
                   **res}))
 eng.close()

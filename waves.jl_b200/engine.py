@@ -119,16 +119,18 @@ class Engine:
                                          _ptr(u_tot), _ptr(u_inc)))
         return en, frames
 
-    def adjoint(self, tspan, w_energy=None, dL_dzN=None, fwd_mode=MODE_FUSED, adj_mode=ADJ_EXACT, want_dc=True):
+    def adjoint(self, tspan, w_energy=None, dL_dzN=None, fwd_mode=MODE_FUSED, adj_mode=ADJ_EXACT, want_dc=True, out_dz0=None,
+                out_dc=None):
         """rrule(::Integrator) + adjoint_sensitivity (src/dynamics.jl:97-128) from the current state.
-        Returns (loss (n_env,), dL/dz0 (n_env,12,ny,nx), dL/dc (n_env,ny,nx) | None)."""
+        Returns (loss (n_env,), dL/dz0 (n_env,12,ny,nx), dL/dc (n_env,ny,nx) | None); out_dz0 / out_dc may be preallocated
+        NumPy arrays or CUDA tensors (the gradients of a large batch are best left on the device)."""
         ts = np.ascontiguousarray(tspan, F32)
         steps = len(ts) - 1
         we = None if w_energy is None else np.ascontiguousarray(w_energy, F32)
         assert we is None or we.shape == (steps + 1, 3)
         an = None if dL_dzN is None else np.ascontiguousarray(dL_dzN, F32)
-        gz = np.empty((self.n_env, 12, self.ny, self.nx), dtype=F32)
-        gc = np.empty((self.n_env, self.ny, self.nx), dtype=F32) if want_dc else None
+        gz = out_dz0 if out_dz0 is not None else np.empty((self.n_env, 12, self.ny, self.nx), dtype=F32)
+        gc = out_dc if out_dc is not None else (np.empty((self.n_env, self.ny, self.nx), dtype=F32) if want_dc else None)
         loss = np.zeros(self.n_env, dtype=F32)
         check(_lib.lib().waves_adjoint(self._h, ts.ctypes.data_as(_lib.fp), steps, fwd_mode, adj_mode, _ptr(we), _ptr(an),
                                        _ptr(gz), _ptr(gc), _ptr(loss)))
