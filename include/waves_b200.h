@@ -171,6 +171,23 @@ int waves_halo_describe(waves_handle *h, waves_halo_desc *out);
  * rank must set its state too): the fused path caches fields that are constant where sigma is zero. */
 int waves_halo_pack(waves_handle *h, float *lo_buf, float *hi_buf);
 int waves_halo_unpack(waves_handle *h, const float *lo_buf, const float *hi_buf);
+/* ---- halo without an exchange step: peer memory over NVLink --------------------------------------------------------
+ * With one process per GPU, every slab handle exports CUDA IPC handles of its two state buffers and of a small flag array
+ * (waves_peer_export); the caller ships that 256-byte record to the neighbouring ranks (any transport) and attaches the
+ * neighbours' records (waves_peer_attach).  From then on the fused step of this rank stores the rows a neighbour needs
+ * straight into that neighbour's ghost rows while it computes them, and consecutive steps of neighbouring ranks are ordered
+ * by stream-ordered flags (a rank starts step n when both neighbours have finished step n-1): no pack, no NCCL call, no
+ * unpack, no host synchronisation.  WAVES_MODE_FUSED only; every rank must take the same sequence of steps.
+ */
+typedef struct waves_peer_info {
+    unsigned char ipc_u0[64], ipc_u1[64], ipc_flags[64]; /* cudaIpcMemHandle_t of u[0], u[1], flags */
+    int32_t ny_alloc, ny_own0, ny_own, device;
+    int32_t reserved[12];
+} waves_peer_info;
+int waves_peer_export(waves_handle *h, waves_peer_info *out);
+/* lo / hi: the records of the ranks owning the rows below / above this slab (NULL at the ends of the grid) */
+int waves_peer_attach(waves_handle *h, const waves_peer_info *lo, const waves_peer_info *hi);
+
 /* CUDA stream (cudaStream_t) the handle launches on, so the caller can order NCCL calls with it. */
 void *waves_stream(waves_handle *h);
 

@@ -13,6 +13,7 @@ import waves_b200 as wb  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+peer = len(sys.argv) > 3 and sys.argv[3] == "peer"   # NVLink peer stores instead of the NCCL halo exchange
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
@@ -30,7 +31,7 @@ sub_y = dim.y[lo:hi]
 xx, yy = dim.x[None, :], sub_y[:, None]
 shape = (np.float32(1.0 / (2 * np.pi * 0.3 ** 2)) * np.exp(-((xx + 10.0) ** 2 + yy ** 2) / np.float32(2 * 0.3 ** 2))).astype(np.float32)
 if world > 1:
-    slab = wb.SlabEngine(dim.x, dim.y, wb.WATER, 1e-5, 2.0, 20000.0, device=local)
+    slab = wb.SlabEngine(dim.x, dim.y, wb.WATER, 1e-5, 2.0, 20000.0, device=local, peer=peer)
     eng = slab.engine
 else:
     eng = wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 2.0, 20000.0, device=local)
@@ -41,7 +42,7 @@ stream = torch.cuda.ExternalStream(eng.stream(), device=local)
 def run(k):
     for i in range(k):
         eng.step(float(ts[i % steps]), wb.MODE_FUSED | wb.STEP_ASYNC)
-        if world > 1:
+        if world > 1 and not peer:
             slab.exchange()
 
 
@@ -65,7 +66,7 @@ if rank == 0:
     v = n * n * steps / (ms.item() * 1e-3) / 1e9
     peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
-    print(json.dumps({"workload": f"single {n}^2 grid with PML, slab-decomposed over {world} B200, halo exchange every RK4 step",
+    print(json.dumps({"workload": f"single {n}^2 grid with PML, slab-decomposed over {world} B200, " + ("edge rows stored into the neighbours' ghost rows over NVLink peer memory" if peer else "NCCL halo exchange every RK4 step"),
                       "n_gpus": world, "steps": steps, "ms_per_step": round(ms.item() / steps, 3), "value": round(v, 2),
                       "unit": "Gcell-updates/s", "frac_of_hbm_roofline": round(v * 96 / (peak * world), 4),
                       "energy_tot_inc_sc": [float(x) for x in et.cpu().numpy()]}))

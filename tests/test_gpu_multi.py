@@ -27,19 +27,32 @@ for n, steps, gs in ((512, 12, 11.0), (257, 9, 5.5)):   # 257: odd row count, pi
     shape = wb.build_normal(dim, [[-0.3 * gs, 0.04 * gs]], [0.03 * gs], [1.0])
     ts = wb.build_tspan(0.0, 1e-5, steps)
     slab = wb.SlabEngine(dim.x, dim.y, wb.WATER, 1e-5, 0.2 * gs, 20000.0, device=local)
+    pslab = wb.SlabEngine(dim.x, dim.y, wb.WATER, 1e-5, 0.2 * gs, 20000.0, device=local, peer=True)   # NVLink peer stores
     slab.set_source_global(shape, 1000.0)
-    for mode in (wb.MODE_FUSED, wb.MODE_EXACT):
-        slab.set_state_global(u0)
-        en = slab.integrate(ts, mode)
-        full = slab.gather_state()
+    pslab.set_source_global(shape, 1000.0)
+    for mode in (wb.MODE_FUSED, wb.MODE_EXACT, "peer"):
+        if mode == "peer":
+            pslab.set_state_global(u0)
+            en = pslab.integrate(ts, wb.MODE_FUSED)
+            pslab.set_state_global(u0)                      # a second run on the same handles (flags keep counting)
+            en = pslab.integrate(ts, wb.MODE_FUSED)
+            full = pslab.gather_state()
+            mode = wb.MODE_FUSED
+            key = (n, "peer")
+        else:
+            slab.set_state_global(u0)
+            en = slab.integrate(ts, mode)
+            full = slab.gather_state()
+            key = (n, mode)
         if rank == 0:
             eng = wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 0.2 * gs, 20000.0, device=0)
             eng.set_state(u0[None]); eng.set_source(shape, 1000.0)
             ren, _ = eng.integrate(ts, mode)
             ref = eng.get_state(0)
-            out[(n, mode)] = (bool(np.array_equal(full, ref)), float(np.abs(full - ref).max()), float(np.abs(en - ren[0]).max() / ren[0].max()))
+            out[key] = (bool(np.array_equal(full, ref)), float(np.abs(full - ref).max()), float(np.abs(en - ren[0]).max() / ren[0].max()))
             eng.close()
     slab.close()
+    pslab.close()
 if rank == 0:
     print("RESULT", out)
 dist.barrier(); dist.destroy_process_group()

@@ -27,6 +27,13 @@ class WavesConfig(C.Structure):
     ]
 
 
+class PeerInfo(C.Structure):
+    """struct waves_peer_info."""
+    _fields_ = [("ipc_u0", C.c_ubyte * 64), ("ipc_u1", C.c_ubyte * 64), ("ipc_flags", C.c_ubyte * 64),
+                ("ny_alloc", C.c_int32), ("ny_own0", C.c_int32), ("ny_own", C.c_int32), ("device", C.c_int32),
+                ("reserved", C.c_int32 * 12)]
+
+
 class HaloDesc(C.Structure):
     """struct waves_halo_desc."""
     _fields_ = [
@@ -59,6 +66,8 @@ SYMBOLS = {
     "waves_halo_describe": (C.c_int, [C.c_void_p, C.POINTER(HaloDesc)]),
     "waves_halo_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "waves_halo_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "waves_peer_export": (C.c_int, [C.c_void_p, C.POINTER(PeerInfo)]),
+    "waves_peer_attach": (C.c_int, [C.c_void_p, C.POINTER(PeerInfo), C.POINTER(PeerInfo)]),
     "waves_stream": (C.c_void_p, [C.c_void_p]),
     "waves_range_f32": (C.c_int, [C.c_float, C.c_float, C.c_int, fp]),
     "waves_build_pml_profile": (C.c_int, [fp, C.c_int, C.c_float, C.c_float, fp]),

@@ -141,6 +141,11 @@ struct FusedArgs {
     int dbg;           // developer bisecting flags (WAVES_DEBUG_FLAGS)
     int cull;          // 0: skip the cylinder cull (no environment has a design)
     float *pconst;     // [n_env][2][plane]: P of the interior cells (written by V = 0 when skip_aux == 0, read by V = 4)
+    // slab decomposition without a halo exchange: rows [peer_j0[s], peer_j0[s] + WAVES_HALO) of this handle are ALSO stored into
+    // the ghost rows of neighbour s (0: lower rows, 1: upper rows) through NVLink peer memory (waves_peer_attach)
+    float *peer_out[2];      // the neighbour's output buffer of this step, nullptr: no neighbour on that side
+    unsigned peer_plane[2];  // floats per field plane over there
+    int peer_j0[2], peer_dj[2];  // my first mirrored local row, and (neighbour's local row) - (my local row)
     int skip_aux;      // 1: the output buffer already holds the auxiliary fields that are constant in a window (see launch_fused_step)
     // host-computed step constants: read straight from the constant bank as FFMA operands
     float kd, b0kd;             // 1/(2Δ) and c0^2/(2Δ)
@@ -271,13 +276,15 @@ struct WarpCtx {
     float *pc_e;       // same position in the P plane of this env / wavefield
     int rowstep;       // dir * nxp: floats between consecutive march rows
     bool xleft, xright, need_w2, first_x, last_x, last_y, is_tot, use_bk, want_e, src_win, in_dom;
-    int w0;
+    int w0, e;
     f2 xs, sx, sxd, bcm;
     float dirf, kdd;   // dir as float, kd * dir
     float sf[3];       // source factor at t, t+dt/2, t+dt
     uint32_t bar0, ring_sa;  // shared-window addresses of mbarrier 0 and of the ring
     int nact;          // culled cylinders (0: none touch this window, -1: list overflow -> slow loop)
     uint32_t tx_bytes; // bytes one row's TMA loads deliver
+    bool peer_any;     // this item owns rows that a neighbouring slab needs as ghost rows (warp-uniform)
+    int col0;          // this lane's first column
     int bko[3];        // float offset of the slot row holding kd*c^2 at stage-time index tau (the ambient row without cylinders)
     float cyl_ylo, cyl_yhi;  // rows with y outside (cyl_ylo, cyl_yhi) are not touched by any culled cylinder
 };
@@ -415,6 +422,20 @@ __device__ __forceinline__ uint32_t bar_of(const Body &b) {
     return q >= 4 ? b.bar[C::NG - 1] + (q - 4) * 8 : (q >= 0 ? b.bar[0] + q * 8 : (q >= -4 ? b.bar[1] + (q + 4) * 8 : b.bar[2] + (q + 8) * 8));
 }
 
+// Mirror freshly stored rows into a neighbouring slab's ghost rows (peer memory over NVLink).  Out of line: only the
+// warps that own one of the first / last WAVES_HALO rows of a slab come here, for those rows.
+// j: local row, col: this lane's first column, plane0: first field plane of the values (relative to the wavefield's U).
+__device__ __noinline__ void peer_store(const FusedArgs &A, int e, int w0, int j, int col, int plane0, int n, f2 v0, f2 v1, f2 v2) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (!A.peer_out[s] || (unsigned)(j - A.peer_j0[s]) >= (unsigned)WAVES_HALO) continue;
+        float *o = A.peer_out[s] + ((size_t)e * 12 + w0 * 6 + plane0) * A.peer_plane[s] + (size_t)(j + A.peer_dj[s]) * A.nxp + col;
+        stg2(o, v0);
+        if (n > 1) stg2(o + A.peer_plane[s], v1);
+        if (n > 2) stg2(o + 2u * A.peer_plane[s], v2);
+    }
+}
+
 // One RK stage S (1..4) on march row m = r - S * SP.  PH = r & 3.  Rows whose inputs are not loaded yet (warm-up)
 // produce values that no stored cell depends on, and stores are predicated.
 // Derivatives are kept un-scaled (differences); the 1/(2Δ) factor is folded into the coefficients.
@@ -458,9 +479,12 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
             }
         } else if (st) {
             float *o = b.po + PH * c.rowstep;
-            stg2(o, fma2(A.dt6, R.aU[ar][sc] + kU, uU));
-            stg2(o + A.plane, fma2(A.dt6kd, R.aVx[ar][sc] + dUx, uVx));
-            stg2(o + 2u * A.plane, fma2(A.dt6kd, R.aVy[ar][sc] + dUy, uVy));
+            const f2 oU = fma2(A.dt6, R.aU[ar][sc] + kU, uU), oVx = fma2(A.dt6kd, R.aVx[ar][sc] + dUx, uVx),
+                     oVy = fma2(A.dt6kd, R.aVy[ar][sc] + dUy, uVy);
+            stg2(o, oU);
+            stg2(o + A.plane, oVx);
+            stg2(o + 2u * A.plane, oVy);
+            if (c.peer_any) peer_store(A, c.e, c.w0, c.jbase + c.dir * m, c.col0, 0, 3, oU, oVx, oVy);
         }
     } else {
         // dU  = bc * [b (Vxx + Vyy) + Psix + Psiy - (sx + sy) U - Omega]      (src/dynamics.jl:169-176)
@@ -528,12 +552,22 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
             }
         } else if (st) {
             float *o = b.po + PH * c.rowstep;
-            stg2(o, fma2(A.dt6, R.aU[ar][sc] + kU, uU));
-            stg2(o + A.plane, fma2(A.dt6, R.aVx[ar][sc] + kVx, uVx));
-            stg2(o + 2u * A.plane, fma2(A.dt6, R.aVy[ar][sc] + kVy, uVy));
-            if (SX) stg2(o + 3u * A.plane, fma2(A.dt6, R.aPx[ar][sc] + kPx, uPx));
-            if (SY) stg2(o + 4u * A.plane, fma2(A.dt6, R.aPy[ar][sc] + kPy, uPy));
-            if (V == 3) stg2(o + 5u * A.plane, fma2(A.dt6, R.aOm[ar][sc] + kOm, uOm));
+            const f2 oU = fma2(A.dt6, R.aU[ar][sc] + kU, uU), oVx = fma2(A.dt6, R.aVx[ar][sc] + kVx, uVx),
+                     oVy = fma2(A.dt6, R.aVy[ar][sc] + kVy, uVy);
+            f2 oPx = bc2(0.f), oPy = bc2(0.f), oOm = bc2(0.f);
+            stg2(o, oU);
+            stg2(o + A.plane, oVx);
+            stg2(o + 2u * A.plane, oVy);
+            if (SX) stg2(o + 3u * A.plane, oPx = fma2(A.dt6, R.aPx[ar][sc] + kPx, uPx));
+            if (SY) stg2(o + 4u * A.plane, oPy = fma2(A.dt6, R.aPy[ar][sc] + kPy, uPy));
+            if (V == 3) stg2(o + 5u * A.plane, oOm = fma2(A.dt6, R.aOm[ar][sc] + kOm, uOm));
+            if (c.peer_any) {
+                const int j = c.jbase + c.dir * m;
+                peer_store(A, c.e, c.w0, j, c.col0, 0, 3, oU, oVx, oVy);
+                if (SX) peer_store(A, c.e, c.w0, j, c.col0, 3, 1, oPx, oPx, oPx);
+                if (SY) peer_store(A, c.e, c.w0, j, c.col0, 4, 1, oPy, oPy, oPy);
+                if (V == 3) peer_store(A, c.e, c.w0, j, c.col0, 5, 1, oOm, oOm, oOm);
+            }
         }
     }
 }
@@ -593,6 +627,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
             if (V == 0) {
                 const f2 px = lds2(uri + 3 * LW), py = lds2(uri + 4 * LW);
                 if (copy_aux) stg2(o + 3u * A.plane, px), stg2(o + 4u * A.plane, py);
+                if (copy_aux && c.peer_any) peer_store(A, c.e, c.w0, c.jbase + c.dir * r, c.col0, 3, 3, px, py, om);
                 P = (px + py) - om;
                 // feeds the lean interior variant of the next steps; halo cells too (they are interior windows' inputs, and
                 // every writer of a cell stores the same value)
@@ -600,10 +635,15 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
             } else if (V == 1) {
                 const f2 py = lds2(uri + 4 * LW);
                 if (copy_aux) stg2(o + 4u * A.plane, py);
+                if (copy_aux && c.peer_any) peer_store(A, c.e, c.w0, c.jbase + c.dir * r, c.col0, 4, 2, py, om, om);
                 P = py - om;
             } else {
                 const f2 px = lds2(uri + 3 * LW);
                 if (copy_aux) stg2(o + 3u * A.plane, px);
+                if (copy_aux && c.peer_any) {
+                    peer_store(A, c.e, c.w0, c.jbase + c.dir * r, c.col0, 3, 1, px, px, px);
+                    peer_store(A, c.e, c.w0, c.jbase + c.dir * r, c.col0, 5, 1, om, om, om);
+                }
                 P = px - om;
             }
             if (copy_aux) stg2(o + 5u * A.plane, om);
@@ -691,6 +731,12 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     c.out_e = A.out + (long long)e * gp.env_stride + (long long)w0 * 6 * gp.plane + min(colA, gp.nxp - 2);
     c.pc_e = A.pconst + ((long long)e * 2 + w0) * gp.plane + min(colA, gp.nxp - 2);
     c.in_dom = colA < gp.nx;
+    c.col0 = colA;
+    c.e = e;
+    c.peer_any = false;
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd)
+        c.peer_any = c.peer_any || (A.peer_out[sd] && item.j0 < A.peer_j0[sd] + WAVES_HALO && item.j1 > A.peer_j0[sd]);
     c.first_x = colA == 0;
     c.last_x = colA == gp.nx - 1;
     c.last_y = colB == gp.nx - 1;
@@ -880,6 +926,13 @@ __global__ void k_energy_reduce(const float *__restrict__ part, int n_items, flo
     }
 }
 
+// peer halo: tell a neighbouring slab that this rank has finished `steps` fused steps (all of this rank's peer stores of
+// those steps were issued by kernels that completed before this one started)
+__global__ void k_peer_signal(int *flag, int steps) {
+    __threadfence_system();
+    *(volatile int *)flag = steps;
+}
+
 __global__ void k_bbox(GridP gp, const float *__restrict__ shape, int *__restrict__ bb) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= gp.nx || j >= gp.ny_alloc) return;
@@ -907,6 +960,7 @@ FusedPlan *plan_of(waves_handle *h, bool create) {
     return static_cast<FusedPlan *>(h->plan);
 }
 
+typedef CUresult (*PFN_waitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1159,9 +1213,30 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     // skipped until something else writes the state (waves_set_state, halo unpack: aux_synced is cleared there).
     A.skip_aux = (h->aux_synced >= 1 && !(dbg_flags & 64)) ? 1 : 0;
     A.pconst = h->pconst;
+    for (int sd = 0; sd < 2; ++sd) {
+        A.peer_out[sd] = h->peer_on ? h->peer_u[sd][h->cur ^ 1] : nullptr;
+        A.peer_plane[sd] = h->peer_plane[sd];
+        A.peer_j0[sd] = h->peer_j0[sd];
+        A.peer_dj[sd] = h->peer_dj[sd];
+    }
     const bool lean = A.skip_aux && !(dbg_flags & 128);
     static const int dbg_skip = getenv("WAVES_DEBUG_SKIP") ? atoi(getenv("WAVES_DEBUG_SKIP")) : 0;  // developer bisecting aid
     if (h->profile) cudaEventRecord(h->ev0, h->stream);
+    if (h->peer_on) {
+        // step n may start once both neighbours have finished step n-1: they no longer read the ghost rows this step's
+        // peer stores overwrite, and their rows of the state this step reads have landed here
+        static PFN_waitValue32 wait32 = nullptr;
+        if (!wait32) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+                return waves_set_error("fused step: cuStreamWaitValue32 entry point not found");
+            wait32 = (PFN_waitValue32)fn;
+        }
+        for (int sd = 0; sd < 2; ++sd)
+            if (h->peer_u[sd][0] && wait32((CUstream)h->stream, (CUdeviceptr)(h->flags + sd), (cuuint32_t)h->peer_steps, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                return waves_set_error("fused step: cuStreamWaitValue32 failed");
+    }
     // two warps (= CTAs) per item and environment: the total and the incident wavefield.  The PML variants are
     // launched on side streams (fork / join with events) so their CTAs fill the tail of the interior kernel.
     A.items = p->d_items;
@@ -1199,6 +1274,11 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     if (d_e3) {
         k_energy_reduce<<<h->gp.n_env, 256, 0, h->stream>>>(p->d_epart, p->off[4], h->d_omega, d_e3, 3 * (steps + 1));
         h->launches++;
+    }
+    if (h->peer_on) {
+        h->peer_steps++;
+        for (int sd = 0; sd < 2; ++sd)
+            if (h->peer_flag[sd]) k_peer_signal<<<1, 1, 0, h->stream>>>(h->peer_flag[sd], h->peer_steps);
     }
     h->cur ^= 1;
     h->aux_synced = 1;

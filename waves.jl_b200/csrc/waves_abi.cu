@@ -133,6 +133,10 @@ static void free_handle(waves_handle *h) {
         if (h->adj[k]) cudaFree(h->adj[k]);
     if (h->traj) cudaFree(h->traj);
     if (h->pconst) cudaFree(h->pconst);
+    for (int sd = 0; sd < 2; ++sd)
+        for (int k = 0; k < 3; ++k)
+            if (h->ipc_ptr[sd][k]) cudaIpcCloseMemHandle(h->ipc_ptr[sd][k]);
+    if (h->flags) cudaFree(h->flags);
     if (h->obs_in) cudaFree(h->obs_in);
     if (h->obs_out) cudaFree(h->obs_out);
     float **bufs[] = {&h->u[0], &h->u[1], &h->k,      &h->ys,     &h->acc,    &h->b2,     &h->shape,  &h->cplane,
@@ -228,6 +232,7 @@ extern "C" int waves_create(const waves_config *cfg, waves_handle **out) {
     ALLOC(h->u[1], state);
     ALLOC(h->shape, (size_t)gp.plane * gp.n_env);
     ALLOC(h->pconst, (size_t)gp.plane * gp.n_env * 2);
+    ALLOC(h->flags, 2);
     ALLOC(h->d_x, gp.nx);
     ALLOC(h->d_y, ny_global);
     ALLOC(h->d_sigma, gp.nx);
@@ -864,6 +869,61 @@ extern "C" int waves_halo_unpack(waves_handle *h, const float *lo_buf, const flo
     // aux_synced is NOT cleared: the auxiliary fields a window treats as constant are constant in the neighbour's rows too
     // (same sigma profile), so every exchange delivers the same ghost values for them; new initial conditions arrive through
     // waves_set_state on every rank, which clears the flag.
+    return 0;
+}
+
+// ---- peer halo (NVLink peer stores instead of an exchange step) -------------------------------------
+extern "C" int waves_peer_export(waves_handle *h, waves_peer_info *out) {
+    CHECK_H(h);
+    if (!out) return fail("waves_peer_export: null");
+    memset(out, 0, sizeof(*out));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU_TRY(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->ipc_u0, h->u[0]));
+    CU_TRY(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->ipc_u1, h->u[1]));
+    CU_TRY(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->ipc_flags, h->flags));
+    out->ny_alloc = h->gp.ny_alloc;
+    out->ny_own0 = h->gp.ny_own0;
+    out->ny_own = h->gp.ny_own;
+    out->device = h->device;
+    return 0;
+}
+
+extern "C" int waves_peer_attach(waves_handle *h, const waves_peer_info *lo, const waves_peer_info *hi) {
+    CHECK_H(h);
+    const GridP &gp = h->gp;
+    if (h->peer_on) return fail("waves_peer_attach: already attached");
+    if ((lo != nullptr) != (gp.ny_own0 > 0) || (hi != nullptr) != (gp.ny_alloc > gp.ny_own0 + gp.ny_own))
+        return fail("waves_peer_attach: a neighbour record is needed exactly on the sides where this slab has ghost rows");
+    const waves_peer_info *nb[2] = {lo, hi};
+    for (int s = 0; s < 2; ++s) {
+        if (!nb[s]) continue;
+        if (s == 0 ? (nb[s]->ny_alloc != nb[s]->ny_own0 + nb[s]->ny_own + WAVES_HALO) : (nb[s]->ny_own0 != WAVES_HALO))
+            return fail("waves_peer_attach: neighbour %d has no ghost rows facing this slab", s);
+        void *p[3] = {nullptr, nullptr, nullptr};
+        const unsigned char *hd[3] = {nb[s]->ipc_u0, nb[s]->ipc_u1, nb[s]->ipc_flags};
+        for (int k = 0; k < 3; ++k) {
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, hd[k], sizeof(mh));
+            CU_TRY(cudaIpcOpenMemHandle(&p[k], mh, cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_ptr[s][k] = p[k];
+        }
+        h->peer_u[s][0] = (float *)p[0];
+        h->peer_u[s][1] = (float *)p[1];
+        h->peer_plane[s] = (unsigned)((size_t)nb[s]->ny_alloc * gp.nxp);
+        if (s == 0) {  // my first owned rows -> the lower neighbour's bottom ghost rows; I am its UPPER neighbour
+            h->peer_j0[0] = gp.ny_own0;
+            h->peer_dj[0] = nb[s]->ny_own0 + nb[s]->ny_own - gp.ny_own0;
+            h->peer_flag[0] = (int *)p[2] + 1;
+        } else {       // my last owned rows -> the upper neighbour's top ghost rows; I am its LOWER neighbour
+            h->peer_j0[1] = gp.ny_own0 + gp.ny_own - WAVES_HALO;
+            h->peer_dj[1] = (nb[s]->ny_own0 - WAVES_HALO) - h->peer_j0[1];
+            h->peer_flag[1] = (int *)p[2] + 0;
+        }
+    }
+    h->peer_steps = 0;
+    CU_TRY(cudaMemsetAsync(h->flags, 0, sizeof(int) * 2, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    h->peer_on = 1;
     return 0;
 }
 

@@ -87,6 +87,15 @@ struct waves_handle {
     int fused_smem;
     int sm_count;
     void *plan;  // FusedPlan (kernels_fused.cu)
+    // ---- peer halo (slabs without an exchange step): neighbours' state buffers mapped through CUDA IPC ----
+    int peer_on;
+    float *peer_u[2][2];      // [side][buffer]: neighbour's u[0], u[1] (nullptr: no neighbour)
+    unsigned peer_plane[2];
+    int peer_j0[2], peer_dj[2];
+    int *flags;               // [2] device ints on THIS GPU: steps completed by the lower / upper neighbour
+    int *peer_flag[2];        // the slot in neighbour s's flags that this rank writes
+    void *ipc_ptr[2][3];      // opened IPC mappings (to close)
+    int peer_steps;           // fused steps taken in peer mode
 };
 
 // ---- kernels_exact.cu ----

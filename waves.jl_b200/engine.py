@@ -166,6 +166,18 @@ class Engine:
     def halo_unpack(self, lo, hi):
         check(_lib.lib().waves_halo_unpack(self._h, _ptr(lo), _ptr(hi)))
 
+    def peer_export(self) -> bytes:
+        """This slab's waves_peer_info record (CUDA IPC handles + geometry) as bytes, to be shipped to the neighbouring ranks."""
+        info = _lib.PeerInfo()
+        check(_lib.lib().waves_peer_export(self._h, C.byref(info)))
+        return bytes(info)
+
+    def peer_attach(self, lo: bytes | None, hi: bytes | None):
+        """Attach the neighbours' records: the fused step then stores its edge rows straight into their ghost rows."""
+        a = _lib.PeerInfo.from_buffer_copy(lo) if lo is not None else None
+        b = _lib.PeerInfo.from_buffer_copy(hi) if hi is not None else None
+        check(_lib.lib().waves_peer_attach(self._h, C.byref(a) if a is not None else None, C.byref(b) if b is not None else None))
+
     def stream(self) -> int:
         return int(_lib.lib().waves_stream(self._h) or 0)
 

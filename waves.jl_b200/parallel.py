@@ -67,7 +67,7 @@ class HaloExchanger:
 class SlabEngine:
     """One rank's slab of a single large grid (BASELINE config 4).  Requires an initialised process group."""
 
-    def __init__(self, x, y, c0, dt, pml_width, pml_scale, device, rank=None, world=None):
+    def __init__(self, x, y, c0, dt, pml_width, pml_scale, device, rank=None, world=None, peer=False):
         import torch
         import torch.distributed as dist
 
@@ -80,6 +80,15 @@ class SlabEngine:
         self.stream = torch.cuda.ExternalStream(self.engine.stream(), device=device)
         self.halo = HaloExchanger(self.rank, self.world, d.n_planes * d.block_floats, torch.device("cuda", device))
         self._torch = torch
+        # peer mode: the fused step stores its edge rows straight into the neighbours' ghost rows over NVLink (CUDA IPC
+        # mappings + stream-ordered flags); the NCCL exchange is only used once after a state was set
+        self.peer = bool(peer) and self.world > 1
+        if self.peer:
+            infos = [None] * self.world
+            dist.all_gather_object(infos, self.engine.peer_export())
+            self.engine.peer_attach(infos[self.rank - 1] if self.rank > 0 else None,
+                                    infos[self.rank + 1] if self.rank < self.world - 1 else None)
+            dist.barrier()
 
     def exchange(self):
         with self._torch.cuda.stream(self.stream):   # NCCL ordered with the engine's own stream
@@ -87,8 +96,15 @@ class SlabEngine:
 
     def set_state_global(self, u12_global):
         """Scatter: every rank takes its rows of a (12, ny_global, nx) array, then ghost rows are exchanged."""
+        import torch.distributed as dist
+        if self.peer:
+            self.engine.sync()
+            dist.barrier()     # nobody may still be storing into this rank's ghost rows
         self.engine.set_state(np.ascontiguousarray(u12_global[:, self.row0:self.row0 + self.ny])[None])
         self.exchange()
+        if self.peer:
+            self.engine.sync()
+            dist.barrier()
 
     def set_source_global(self, shape_global, freq):
         """Every rank takes its rows of the (ny_global, nx) shape INCLUDING the ghost rows of its slab."""
@@ -107,10 +123,12 @@ class SlabEngine:
         en = np.zeros((steps + 1, 3), dtype=np.float64)
         if energy:
             en[0] = self.engine.energy()[0]
-        from .engine import STEP_ASYNC
+        from .engine import MODE_FUSED, STEP_ASYNC
+        peer = self.peer and mode == MODE_FUSED
         for n in range(steps):
             self.engine.step(float(tspan[n]), mode | STEP_ASYNC)   # the exchange is ordered on the engine's stream
-            self.exchange()
+            if not peer:
+                self.exchange()
             if energy:
                 en[n + 1] = self.engine.energy()[0]
         self.engine.sync()
