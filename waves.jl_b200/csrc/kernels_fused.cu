@@ -689,7 +689,9 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
     }
 }
 
-template <int V>
+// PEER: this launch mirrors slab edge rows into the neighbours' ghost rows (a separate instantiation, so that the ordinary
+// kernels carry none of that code: the PML variants are sensitive to their instruction footprint)
+template <int V, bool PEER>
 __global__ void __launch_bounds__(32, V == 3 ? 8 : ((V == 0 || V == 4) ? (WV_SP0 == 1 ? 12 : 8) : WV_OCC_STRIP))
 k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtensorMap map_u7, const __grid_constant__ CUtensorMap map_u6,
              const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_sh) {
@@ -736,7 +738,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     c.peer_any = false;
 #pragma unroll
     for (int sd = 0; sd < 2; ++sd)
-        c.peer_any = c.peer_any || (A.peer_out[sd] && item.j0 < A.peer_j0[sd] + WAVES_HALO && item.j1 > A.peer_j0[sd]);
+        c.peer_any = c.peer_any || (PEER && A.peer_out[sd] && item.j0 < A.peer_j0[sd] + WAVES_HALO && item.j1 > A.peer_j0[sd]);
     c.first_x = colA == 0;
     c.last_x = colA == gp.nx - 1;
     c.last_y = colB == gp.nx - 1;
@@ -1118,11 +1120,12 @@ int fused_prepare(waves_handle *h) {
     p->smem[2] = Cfg<2>::WARP_F * 4;
     p->smem[3] = Cfg<3>::WARP_F * 4;
     p->smem[4] = Cfg<4>::WARP_F * 4;
-    cudaError_t ce = cudaFuncSetAttribute(k_fused_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[0]);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[1]);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[2]);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[3]);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[4]);
+    cudaError_t ce = cudaSuccess;
+#define WV_SET_SMEM(V)                                                                                                           \
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[V]); \
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[V]);
+    WV_SET_SMEM(0) WV_SET_SMEM(1) WV_SET_SMEM(2) WV_SET_SMEM(3) WV_SET_SMEM(4)
+#undef WV_SET_SMEM
     if (ce != cudaSuccess) {
         char buf[256];
         snprintf(buf, sizeof(buf), "fused_prepare: cudaFuncSetAttribute: %s (was the library built for sm_100a?)", cudaGetErrorString(ce));
@@ -1252,11 +1255,19 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
         cudaStream_t st = (v == 0 || !fork) ? h->stream : p->side[v - 1];
         if (st != h->stream) cudaStreamWaitEvent(st, p->ev_fork, 0);
         const CUtensorMap &m7 = h->map_u[h->cur], &m6 = h->map_u6[h->cur];
-        if (v == 0 && lean) k_fused_step<4><<<grid, 32, p->smem[4], st>>>(A, h->map_u3[h->cur], h->map_u1[h->cur], h->map_p, h->map_shape);
-        if (v == 0 && !lean) k_fused_step<0><<<grid, 32, p->smem[0], st>>>(A, m7, m6, h->map_p, h->map_shape);
-        if (v == 1) k_fused_step<1><<<grid, 32, p->smem[1], st>>>(A, m7, m6, h->map_p, h->map_shape);
-        if (v == 2) k_fused_step<2><<<grid, 32, p->smem[2], st>>>(A, m7, m6, h->map_p, h->map_shape);
-        if (v == 3) k_fused_step<3><<<grid, 32, p->smem[3], st>>>(A, m7, m6, h->map_p, h->map_shape);
+#define WV_LAUNCH(V, MA, MB)                                                                                          \
+    do {                                                                                                              \
+        if (h->peer_on)                                                                                               \
+            k_fused_step<V, true><<<grid, 32, p->smem[V], st>>>(A, MA, MB, h->map_p, h->map_shape);                   \
+        else                                                                                                          \
+            k_fused_step<V, false><<<grid, 32, p->smem[V], st>>>(A, MA, MB, h->map_p, h->map_shape);                  \
+    } while (0)
+        if (v == 0 && lean) WV_LAUNCH(4, h->map_u3[h->cur], h->map_u1[h->cur]);
+        if (v == 0 && !lean) WV_LAUNCH(0, m7, m6);
+        if (v == 1) WV_LAUNCH(1, m7, m6);
+        if (v == 2) WV_LAUNCH(2, m7, m6);
+        if (v == 3) WV_LAUNCH(3, m7, m6);
+#undef WV_LAUNCH
         h->launches++;
         if (st != h->stream) {
             cudaEventRecord(p->ev_join[v - 1], st);
