@@ -204,6 +204,54 @@ int waves_build_normal(const float *x, int nx, const float *y, int ny, int n, co
 /* get_dx(dim) = mean(diff(x)), src/dims.jl:126 */
 float waves_mean_diff(const float *x, int n);
 
+/* ---- 1-D latent dynamics: the training-time loop of AcousticEnergyModel -------------------------
+ * Replaces, for AcousticDynamics{OneDim} (src/dynamics.jl:190-222),
+ *     model.iter(z0, t, θ)                with θ = [C, F, PML]   src/model/acoustic_energy_model.jl:86-99
+ *     compute_latent_energy(z, dx)                               src/model/acoustic_energy_model.jl:6-15
+ *     rrule(::Integrator, z0, t, θ) / adjoint_sensitivity        src/dynamics.jl:97-128
+ * One CTA integrates one batch element entirely in shared memory (no launch per step).  Arrays keep the reference's
+ * column-major memory image (host or device pointers):
+ *     z0 (n, 4, batch) fields U_tot, V_tot, U_inc, V_inc      tspan (steps+1, batch)   (one time column per sample)
+ *     X (nseq, batch), Y (n, nseq, batch): C = LinearInterpolation(X, Y) (src/utils.jl:88-98), queried at every RK stage
+ *     shape (n, batch), freq: F = Source(shape, freq) (src/sources.jl:10-23); shape == NULL -> no source
+ *     pml (n, batch): θ[3]; σ = dyn.pml[[1]] .* pml
+ *     z (n, 4, batch, steps+1)     energy (steps+1, 3, batch) {tot, inc, sc}
+ */
+typedef struct waves_latent waves_latent;
+typedef struct waves_latent_config {
+    int32_t n;        /* grid points of the OneDim latent grid (reference: 1024) */
+    int32_t device;   /* CUDA device ordinal */
+    float c0;         /* dyn.c0 */
+    float dt;         /* iter.dt */
+    float pml_width;  /* AcousticDynamics(dim, c0, pml_width, pml_scale): used when pml0 < 0 */
+    float pml_scale;
+    float pml0;       /* >= 0: dyn.pml[1] given directly; < 0: computed with build_pml(::OneDim) (src/pml.jl:6-15) from x */
+    float dx;         /* get_dx(latent_dim) (src/dims.jl:126); <= 0: computed from x */
+    const float *x;     /* HOST, n values: latent_dim.x (src/dims.jl:48-50); may be NULL when grad8, pml0 and dx are given */
+    const float *grad8; /* HOST, optional: rows of dyn.grad first(3) central(2) last(3); NULL -> gradient(x) */
+} waves_latent_config;
+int waves_latent_create(const waves_latent_config *cfg, waves_latent **out);
+int waves_latent_destroy(waves_latent *h);
+/* z = iter(z0, tspan, θ) and/or compute_latent_energy(z, dx); z, energy, z_last (the last state, (n, 4, batch)) are each
+ * nullable: with z == NULL no trajectory ever reaches HBM. */
+int waves_latent_integrate(waves_latent *h, int batch, int steps, int nseq, const float *z0, const float *tspan,
+                           const float *X, const float *Y, const float *shape, float freq, const float *pml, float *z,
+                           float *energy, float *z_last);
+/* adjoint_sensitivity(iter, z, t, θ, ∂L_∂z) (src/dynamics.jl:97-118).  z is the stored solution of waves_latent_integrate.
+ * The cotangent of the solution is  dL_dz (n, 4, batch, steps+1, nullable)  plus, when w_energy (steps+1, 3, batch) is
+ * given, the pullback of compute_latent_energy (so a loss on the energies needs no (n,4,batch,time) cotangent at all).
+ * adj_mode: WAVES_ADJ_EXACT (discrete adjoint) or WAVES_ADJ_COMPAT (the reference loop as written).
+ * Outputs: dL_dz0 (n, 4, batch); nullable dL_dY (n, nseq, batch), dL_dshape (n, batch), dL_dpml (n, batch). */
+int waves_latent_adjoint(waves_latent *h, int batch, int steps, int nseq, const float *z, const float *tspan, const float *X,
+                         const float *Y, const float *shape, float freq, const float *pml, int adj_mode,
+                         const float *w_energy, const float *dL_dz, float *dL_dz0, float *dL_dY, float *dL_dshape,
+                         float *dL_dpml);
+/* build_pml(::OneDim, width, scale), src/pml.jl:6-15: out (n, nullable), *first = its first value (nullable). HOST. */
+int waves_latent_build_pml(const float *x, int n, float width, float scale, float *out, float *first);
+int64_t waves_latent_launch_count(waves_latent *h);
+/* device time (ms, CUDA events on the handle's stream) of the kernel of the last integrate / adjoint call */
+float waves_latent_last_kernel_ms(waves_latent *h);
+
 /* ---- introspection for benchmarks -------------------------------------------------------- */
 /* number of kernel launches issued by this handle so far */
 int64_t waves_launch_count(waves_handle *h);

@@ -1,0 +1,43 @@
+"""Timing of the 1-D latent path on one B200: kernel time from CUDA events inside the library
+(`waves_latent_last_kernel_ms`), host-pointer call time by wall clock.  Prints one JSON line per configuration."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import waves_b200 as wb  # noqa: E402
+from latent_cases import make_case  # noqa: E402
+
+F32 = np.float32
+out = []
+for batch, steps in ((32, 100), (148, 300), (1184, 300), (148, 2000)):
+    cs = make_case(n=1024, batch=batch, steps=steps, nseq=steps // 100 + 1, seed=1)
+    th = cs["theta"]
+    it = wb.LatentIntegrator(wb.LatentDynamics(wb.OneDim(cs["dim"].x), 1531.0, 10.0, 10000.0), cs["dt"])
+    theta = [wb.LinearInterpolation(th.X, th.Y), wb.LatentSource(th.shape, th.freq), th.pml]
+    rec = {"batch": batch, "steps": steps, "n": 1024}
+    for name, kw in (("energy_only", dict(want_z=False, want_energy=True)), ("trajectory", dict(want_z=True, want_energy=True))):
+        if name == "trajectory" and batch * steps > 148 * 300:
+            continue
+        ms = []
+        for _ in range(4):
+            t = time.perf_counter()
+            res = it(cs["z0"], cs["tspan"], theta, **kw)
+            wall = (time.perf_counter() - t) * 1e3
+            ms.append((it.last_kernel_ms(), wall))
+        k, w = min(m[0] for m in ms[1:]), min(m[1] for m in ms[1:])
+        rec[name] = {"kernel_ms": round(k, 4), "call_ms_host_buffers": round(w, 3), "us_per_step": round(1e3 * k / steps, 3),
+                     "Melement_steps_per_s": round(batch * 1024 * steps / k / 1e3, 1)}
+    if batch * steps <= 148 * 300:
+        z = it(cs["z0"], cs["tspan"], theta)
+        wE = np.ones((batch, 3, steps + 1), F32)
+        for _ in range(3):
+            it.adjoint(z, cs["tspan"], theta, w_energy=wE)
+        rec["adjoint"] = {"kernel_ms": round(it.last_kernel_ms(), 4), "us_per_step": round(1e3 * it.last_kernel_ms() / steps, 3)}
+    out.append(rec)
+    print(json.dumps(rec), flush=True)
+    it.close()

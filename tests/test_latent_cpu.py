@@ -1,0 +1,180 @@
+"""CPU tests of the 1-D latent dynamics: the oracle against independent statements of the same
+equations, and the product's kernel source (csrc/latent_core.cuh) executed by the host emulation of the CUDA execution
+model (tests/emu/) against the oracle.  The emulation is test infrastructure: it exists because the build container has
+no GPU; the GPU parity tests proper are in tests/test_gpu_zlatent.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import latent_adjoint_oracle as lao
+from oracle import latent_oracle as lo
+from oracle import waves_oracle as wo
+from latent_cases import make_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+F32 = np.float32
+fp = C.POINTER(C.c_float)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle
+# ---------------------------------------------------------------------------------------------------------------
+def test_pml_1d_matches_reference_constructor_properties():
+    """build_pml(::OneDim) (src/pml.jl:6-15): zero inside, cubic ramp, `scale` at both ends (dyn.pml[[1]] = scale)."""
+    dim = wo.OneDim.make(100.0, 1024)
+    pml = lo.build_pml_1d(dim.x, 10.0, 10000.0)
+    assert pml[0] == F32(10000.0) and pml[-1] == F32(10000.0)
+    inside = np.abs(dim.x) <= 90.0
+    assert np.all(pml[inside] == 0) and np.all(np.diff(pml[: 60]) <= 0)
+    i = 20
+    r = (abs(float(dim.x[i])) - 90.0) / 10.0
+    assert abs(float(pml[i]) - 1e4 * r ** 3) <= 2e-3 * 1e4 * r ** 3
+
+
+def test_linear_interp_restatement():
+    """linear_interp (src/utils.jl:70-86): piecewise linear inside the knots, the last knot included, 0 outside."""
+    rng = np.random.default_rng(1)
+    X = np.array([[0.0, 1.0, 2.0, 4.0], [1.0, 1.5, 2.0, 2.5]], F32)
+    Y = rng.standard_normal((2, 4, 5)).astype(F32)
+    for q in ([0.25, 1.75], [1.0, 2.5], [4.0, 1.0], [3.0, 2.25]):
+        q = np.array(q, F32)
+        got = lo.linear_interp(X, Y, q)
+        for b in range(2):
+            want = np.array([np.interp(float(q[b]), X[b].astype(float), Y[b, :, i].astype(float)) for i in range(5)])
+            np.testing.assert_allclose(got[b], want, rtol=2e-6, atol=2e-6)
+    out = lo.linear_interp(X, Y, np.array([5.0, 0.5], F32))   # outside every segment: masks are all false
+    assert np.all(out == 0)
+
+
+def test_rhs_matches_independent_statement_of_test_pinn():
+    """test/pinn.jl:20-36 (SimpleWave) states the same 1-D right-hand side with a dense-in-form ∇: u_t = c0 c ∇v − σu (× bc),
+    v_t = c0 c ∇(u + f) − σv.  Checked in float64 against the sparse matrix product."""
+    cs = make_case(n=64, batch=2, steps=8, nseq=3)
+    dyn, th = cs["dyn"], cs["theta"]
+    w = cs["z0"]
+    t = np.ascontiguousarray(cs["tspan"][:, 3])
+    got = dyn(w, t, th).astype(np.float64)
+    D = dyn.grad.to_scipy().toarray().astype(np.float64)
+    c = lo.linear_interp(th.X, th.Y, t).astype(np.float64)
+    f = th.shape.astype(np.float64) * np.sin(2 * np.pi * t.astype(np.float64) * 1000.0)[:, None]
+    sig = float(dyn.pml[0]) * th.pml.astype(np.float64)
+    c0 = float(dyn.c0)
+    W = w.astype(np.float64)
+    want = np.stack([(c0 * c * (W[:, 1] @ D.T) - sig * W[:, 0]) * dyn.bc, c0 * c * ((W[:, 0] + f) @ D.T) - sig * W[:, 1],
+                     (c0 * (W[:, 3] @ D.T) - sig * W[:, 2]) * dyn.bc, c0 * ((W[:, 2] + f) @ D.T) - sig * W[:, 3]], 1)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 3e-6 * scale
+
+
+def test_incident_equals_total_when_c_is_one():
+    """With C ≡ 1 the total and the incident field obey the same equation (src/dynamics.jl:210-214)."""
+    cs = make_case(n=64, batch=2, steps=12, nseq=3)
+    th = cs["theta"]
+    th.Y[:] = 1.0
+    z0 = cs["z0"].copy()
+    z0[:, 2:] = z0[:, :2]
+    z = lo.integrate(cs["dyn"], z0, cs["tspan"], th, cs["dt"])
+    np.testing.assert_allclose(z[:, :, 0], z[:, :, 2], rtol=0, atol=2e-6 * np.abs(z).max())
+    e = lo.compute_latent_energy(z, wo.get_dx(cs["dim"]))
+    assert e.shape == (2, 3, 13) and np.all(e[:, 2] <= 1e-9 * e[:, 0].max())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kernel source under the host emulation of the CUDA execution model
+# ---------------------------------------------------------------------------------------------------------------
+class LatentP(C.Structure):
+    """struct LatentP (csrc/latent_core.cuh)."""
+    _fields_ = [("n", C.c_int), ("batch", C.c_int), ("steps", C.c_int), ("nseq", C.c_int),
+                ("c0", C.c_float), ("dt", C.c_float), ("hdt", C.c_float), ("pml_scale", C.c_float), ("freq", C.c_float),
+                ("dx", C.c_float), ("gf", C.c_float * 3), ("gc", C.c_float * 2), ("gl", C.c_float * 3),
+                ("z0", fp), ("tspan", fp), ("X", fp), ("Y", fp), ("shape", fp), ("pml", fp), ("z", fp), ("energy", fp),
+                ("z_last", fp), ("compat", C.c_int), ("zt", fp), ("w_energy", fp), ("dL_dz", fp), ("g_z0", fp), ("g_Y", fp),
+                ("g_shape", fp), ("g_pml", fp)]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(ROOT, "tests", "emu", "latent_emu.cpp")
+    so = os.path.join(ROOT, "tests", "emu", "liblatent_emu.so")
+    core = os.path.join(ROOT, "waves.jl_b200", "csrc", "latent_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off",
+                               "-fno-fast-math", "-o", so, src])
+    L = C.CDLL(so)
+    assert L.emu_sizeof_latentp() == C.sizeof(LatentP)
+    return L
+
+
+def _params(cs, **ptrs):
+    dyn, th = cs["dyn"], cs["theta"]
+    g = dyn.grad
+    p = LatentP(n=cs["n"], batch=cs["batch"], steps=cs["steps"], nseq=cs["nseq"], c0=float(dyn.c0), dt=float(cs["dt"]),
+                hdt=float(F32(0.5) * cs["dt"]), pml_scale=float(dyn.pml[0]), freq=float(th.freq),
+                dx=float(wo.get_dx(cs["dim"])))
+    p.gf[:], p.gc[:], p.gl[:] = list(g.first), list(g.central), list(g.last)
+    keep = []
+    for name, arr in dict(z0=cs["z0"], tspan=cs["tspan"], X=th.X, Y=th.Y, shape=th.shape, pml=th.pml, **ptrs).items():
+        if arr is None:
+            continue
+        assert arr.dtype == np.float32 and arr.flags["C_CONTIGUOUS"]
+        keep.append(arr)
+        setattr(p, name, arr.ctypes.data_as(fp))
+    return p, keep
+
+
+@pytest.mark.parametrize("n,nt,knots", [(96, 96, "actions"), (200, 64, "actions"), (70, 96, "partial")])
+def test_emulated_forward_kernel_is_bit_exact(emu, n, nt, knots):
+    """k_latent_integrate == oracle integrate, bit for bit (fields), energies to 1e-6; threads == elements, a strided
+    ownership (n > threads), idle threads (threads > n), and knots that leave stage times outside every segment."""
+    cs = make_case(n=n, batch=2, steps=12, nseq=4, seed=n, knots=knots)
+    z = np.full((cs["steps"] + 1, cs["batch"], 4, n), np.nan, F32)
+    e = np.full((cs["batch"], 3, cs["steps"] + 1), np.nan, F32)
+    last = np.full((cs["batch"], 4, n), np.nan, F32)
+    p, keep = _params(cs, z=z, energy=e, z_last=last)
+    emu.emu_latent_integrate(C.byref(p), nt)
+    want = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
+    assert np.isfinite(want).all() and np.abs(want[-1] - want[0]).max() > 1e-3      # the case does something
+    assert np.array_equal(z, want)
+    assert np.array_equal(last, want[-1])
+    we = lo.compute_latent_energy(want, wo.get_dx(cs["dim"]))
+    np.testing.assert_allclose(e, we, rtol=1e-6, atol=1e-6 * we.max())
+
+
+def test_emulated_forward_kernel_energy_only(emu):
+    """With z == NULL only the energies and the last state leave the kernel."""
+    cs = make_case(n=64, batch=2, steps=8, nseq=3, seed=5)
+    e = np.full((2, 3, 9), np.nan, F32)
+    last = np.full((2, 4, 64), np.nan, F32)
+    p, keep = _params(cs, energy=e, z_last=last)
+    emu.emu_latent_integrate(C.byref(p), 64)
+    want = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
+    assert np.array_equal(last, want[-1])
+    np.testing.assert_allclose(e, lo.compute_latent_energy(want, wo.get_dx(cs["dim"])), rtol=1e-6)
+
+
+@pytest.mark.parametrize("compat", [0, 1])
+@pytest.mark.parametrize("n,nt", [(48, 64), (80, 32)])
+def test_emulated_adjoint_kernel_matches_autograd(emu, compat, n, nt):
+    """k_latent_adjoint against torch float64 reverse-mode over the unrolled oracle trajectory (exact mode) and a literal
+    transcription of the reference loop (compat mode, src/dynamics.jl:101-115): z0, C.Y, F.shape and PML gradients."""
+    cs = make_case(n=n, batch=2, steps=8, nseq=3, seed=11 + n)
+    rng = np.random.default_rng(3)
+    T = cs["steps"] + 1
+    z = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
+    w_energy = rng.standard_normal((2, 3, T)).astype(F32)
+    dL_dz = (1e-2 * rng.standard_normal(z.shape)).astype(F32)
+    g_z0 = np.full((2, 4, n), np.nan, F32)
+    g_Y = np.zeros((2, cs["nseq"], n), F32)
+    g_shape = np.full((2, n), np.nan, F32)
+    g_pml = np.full((2, n), np.nan, F32)
+    p, keep = _params(cs, zt=z, w_energy=w_energy, dL_dz=dL_dz, g_z0=g_z0, g_Y=g_Y, g_shape=g_shape, g_pml=g_pml)
+    p.compat = compat
+    emu.emu_latent_adjoint(C.byref(p), nt)
+    want = lao.adjoint_truth(cs, w_energy, dL_dz, compat=bool(compat))
+    for name, got in (("z0", g_z0), ("Y", g_Y), ("shape", g_shape), ("pml", g_pml)):
+        ref = want[name]
+        err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        assert err < 1e-4, (name, err)

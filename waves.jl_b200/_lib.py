@@ -42,6 +42,12 @@ class HaloDesc(C.Structure):
     ]
 
 
+class LatentConfig(C.Structure):
+    """struct waves_latent_config."""
+    _fields_ = [("n", C.c_int32), ("device", C.c_int32), ("c0", C.c_float), ("dt", C.c_float), ("pml_width", C.c_float),
+                ("pml_scale", C.c_float), ("pml0", C.c_float), ("dx", C.c_float), ("x", fp), ("grad8", fp)]
+
+
 # every symbol include/waves_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "waves_version": (C.c_int, []),
@@ -74,6 +80,16 @@ SYMBOLS = {
     "waves_build_gradient8": (C.c_int, [fp, C.c_int, fp]),
     "waves_build_normal": (C.c_int, [fp, C.c_int, fp, C.c_int, C.c_int, fp, fp, fp, fp]),
     "waves_mean_diff": (C.c_float, [fp, C.c_int]),
+    "waves_latent_create": (C.c_int, [C.POINTER(LatentConfig), C.POINTER(C.c_void_p)]),
+    "waves_latent_destroy": (C.c_int, [C.c_void_p]),
+    "waves_latent_integrate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "waves_latent_adjoint": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "waves_latent_build_pml": (C.c_int, [fp, C.c_int, C.c_float, C.c_float, fp, fp]),
+    "waves_latent_launch_count": (C.c_int64, [C.c_void_p]),
+    "waves_latent_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "waves_launch_count": (C.c_int64, [C.c_void_p]),
     "waves_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "waves_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -84,7 +100,7 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into libwaves_b200.so (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".h"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     srcs.append(os.path.join(_HERE, "..", "include", "waves_b200.h"))
     stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
     if force or stale:

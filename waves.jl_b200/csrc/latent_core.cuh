@@ -1,0 +1,411 @@
+// 1-D latent dynamics of Waves.jl's AcousticEnergyModel: kernels.
+//
+//   (dyn::AcousticDynamics{OneDim})(x, t, θ)   src/dynamics.jl:190-222      θ = [C, F, PML]
+//   runge_kutta, (iter::Integrator)(ui, tspan::Matrix, θ)   src/dynamics.jl:9-16, :37-49
+//   LinearInterpolation (θ[1])                 src/utils.jl:70-98
+//   Source(shape, freq)(t::Vector) (θ[2])      src/sources.jl:21-23
+//   compute_latent_energy                      src/model/acoustic_energy_model.jl:6-15
+//   adjoint_sensitivity (batchwise OneDim)     src/dynamics.jl:97-118
+//
+// B200 mapping: the reference integrates a batch of ~1 k-element samples with ~100 CUDA.jl kernel launches per RK4
+// step.  Here ONE CTA owns one sample for the whole integration: its state, the four RK4 stage states and the running
+// stage sum live in shared memory (84 KB at n = 1024), neighbours are read from shared memory, each RK4 step costs
+// four block barriers and no launch; HBM sees one 16-byte-per-element frame write per step (when the trajectory is
+// wanted) and nothing else.  The arithmetic is the reference's float32 evaluation order (this file is compiled with
+// -fmad=false), so the forward kernel is bit-exact against oracle/latent_oracle.py.
+//
+// The file contains only thread-index / barrier / shared-memory code so that tests/emu/ can compile the SAME source
+// for the host (threads = pthreads, barrier = pthread barrier) and check indexing and hazards without a GPU.  That
+// host build is a test of this source, never a product path.
+#pragma once
+#include <math.h>
+#include <stddef.h>
+
+#ifndef LAT_EMU
+#define LAT_DEV __device__ __forceinline__
+#define LAT_GLOBAL __global__ __launch_bounds__(1024, 1)  // one 1024-thread CTA per SM: <= 64 registers per thread
+#define LAT_SMEM extern __shared__ __align__(16) unsigned char lat_smem[];
+#define LAT_SYNC() __syncthreads()
+#endif
+
+#define LAT_MAX_WARPS 32
+
+// layouts: C order of the reference's column-major arrays (same memory image)
+struct LatentP {
+    int n, batch, steps, nseq;
+    float c0, dt, hdt, pml_scale, freq, dx;
+    float gf[3], gc[2], gl[3];  // rows of dyn.grad: first(3), central(2), last(3)  (src/operators.jl:10-22)
+    const float *z0;            // (n, 4, batch)          [batch][4][n]
+    const float *tspan;         // (steps+1, batch)       [batch][steps+1]
+    const float *X;             // (nseq, batch)          [batch][nseq]
+    const float *Y;             // (n, nseq, batch)       [batch][nseq][n]
+    const float *shape;         // (n, batch)             [batch][n]      nullptr: NoSource
+    const float *pml;           // (n, batch)             [batch][n]
+    float *z;                   // (n, 4, batch, steps+1) [steps+1][batch][4][n]   nullable
+    float *energy;              // (steps+1, 3, batch)    [batch][3][steps+1]      nullable
+    float *z_last;              // (n, 4, batch)                                   nullable
+    // ---- reverse pass only ----
+    int compat;                 // 0: exact discrete adjoint, 1: the reference loop as written
+    const float *zt;            // stored trajectory [steps+1][batch][4][n]
+    const float *w_energy;      // nullable [batch][3][steps+1]: dL/d(energy)
+    const float *dL_dz;         // nullable [steps+1][batch][4][n]
+    float *g_z0;                // [batch][4][n]
+    float *g_Y;                 // nullable [batch][nseq][n]   (zero-initialised by the caller)
+    float *g_shape;             // nullable [batch][n]
+    float *g_pml;               // nullable [batch][n]
+};
+
+// (∇ * v)[i]: SparseMatrixCSC * dense accumulates nzval*v in increasing column order from 0, no FMA (src/operators.jl:45)
+template <class V>
+LAT_DEV float lat_grad(const LatentP &p, int i, V v) {
+    const int n = p.n;
+    if (i == 0) return ((p.gf[0] * v(0)) + (p.gf[1] * v(1))) + (p.gf[2] * v(2));
+    if (i == n - 1) return ((p.gl[0] * v(n - 3)) + (p.gl[1] * v(n - 2))) + (p.gl[2] * v(n - 1));
+    return (p.gc[0] * v(i - 1)) + (p.gc[1] * v(i + 1));
+}
+
+// (∇' * w)[j] for the reverse pass
+template <class V>
+LAT_DEV float lat_grad_t(const LatentP &p, int j, V w) {
+    const int n = p.n;
+    float r = 0.0f;
+    if (j + 1 >= 1 && j + 1 <= n - 2) r += p.gc[0] * w(j + 1);  // row j+1 holds gc[0] in column j
+    if (j - 1 >= 1 && j - 1 <= n - 2) r += p.gc[1] * w(j - 1);  // row j-1 holds gc[1] in column j
+    if (j <= 2) r += p.gf[j] * w(0);
+    if (j >= n - 3) r += p.gl[j - (n - 3)] * w(n - 1);
+    return r;
+}
+
+// sin(2.0f0 * pi * t * freq) (src/sources.jl:22): ((2f0*π)*t)*freq in Float32; Julia's sin(::Float32) is the rounding
+// of an accurate double evaluation
+LAT_DEV float lat_sin_factor(float t, float freq) {
+    const float two_pi = 2.0f * 3.14159274101257324f;
+    const float arg = (two_pi * t) * freq;
+    return (float)sin((double)arg);
+}
+
+// the reference's segment mask (src/utils.jl:79-80)
+LAT_DEV bool lat_mask(float l, float r, float rend, float t) { return ((l <= t) && (t < r)) || ((r == rend) && (rend == t)); }
+
+// c0 * C(t) for the elements this thread owns (src/utils.jl:70-86, src/dynamics.jl:210): masks and sums as written
+LAT_DEV void lat_speed(const LatentP &p, int b, float t, float *cout, int tid, int nt) {
+    const float *Xb = p.X + (size_t)b * p.nseq;
+    const float *Yb = p.Y + (size_t)b * p.nseq * p.n;
+    const float rend = Xb[p.nseq - 1];
+    float x0 = 0.0f;
+    for (int k = 0; k + 1 < p.nseq; ++k)
+        if (lat_mask(Xb[k], Xb[k + 1], rend, t)) x0 = x0 + Xb[k];
+    const float tx = t - x0;
+    for (int i = tid; i < p.n; i += nt) {
+        float y0 = 0.0f, dydx = 0.0f;
+        for (int k = 0; k + 1 < p.nseq; ++k) {
+            const float l = Xb[k], r = Xb[k + 1];
+            if (lat_mask(l, r, rend, t)) {
+                const float dd = (r - t) - (l - t);  // diff(X .- x): the query is subtracted before the difference
+                const float yk = Yb[(size_t)k * p.n + i], yk1 = Yb[(size_t)(k + 1) * p.n + i];
+                y0 = y0 + yk;
+                dydx = dydx + (yk1 - yk) / dd;
+            }
+        }
+        cout[i] = p.c0 * (y0 + tx * dydx);
+    }
+}
+
+// one right-hand side at element i: S = stage state [4][n] in shared memory, c0c = c0*C(t), fs = source factor
+LAT_DEV void lat_rhs(const LatentP &p, const float *S, const float *c0c, const float *shp, const float *sig, float fs, int i,
+                     float k[4]) {
+    const int n = p.n;
+    const float *Ut = S, *Vt = S + n, *Ui = S + 2 * n, *Vi = S + 3 * n;
+    const float bc = (i == 0 || i == n - 1) ? 0.0f : 1.0f;  // build_dirichlet(::OneDim), src/dims.jl:111-115
+    const float gVt = lat_grad(p, i, [&](int j) { return Vt[j]; });
+    const float gUt = lat_grad(p, i, [&](int j) { return Ut[j] + (shp[j] * fs); });  // ∇ * (U_tot .+ f)
+    const float gVi = lat_grad(p, i, [&](int j) { return Vi[j]; });
+    const float gUi = lat_grad(p, i, [&](int j) { return Ui[j] + (shp[j] * fs); });
+    const float a = c0c[i], s = sig[i];
+    k[0] = ((a * gVt) - (s * Ut[i])) * bc;     // src/dynamics.jl:210, :217
+    k[1] = (a * gUt) - (s * Vt[i]);            // :211
+    k[2] = ((p.c0 * gVi) - (s * Ui[i])) * bc;  // :213, :219
+    k[3] = (gUi * p.c0) - (s * Vi[i]);         // :214
+}
+
+// Σ over the block of three doubles per thread; result valid in out[0..2] (shared) after the NEXT barrier
+LAT_DEV void lat_reduce3_warp(double v[3], double *red, int tid) {
+#ifndef LAT_EMU
+    for (int o = 16; o > 0; o >>= 1)
+        for (int q = 0; q < 3; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+    if ((tid & 31) == 0)
+        for (int q = 0; q < 3; ++q) red[(tid >> 5) * 3 + q] = v[q];
+#else
+    lat_emu_reduce3(v, red, tid);
+#endif
+}
+
+// shared-memory carve-up of the forward kernel: doubles first (alignment), then floats
+#define LAT_FWD_FLOATS(n) (21 * (size_t)(n) + 8)
+#define LAT_FWD_SMEM(n) (sizeof(double) * 3 * LAT_MAX_WARPS + sizeof(float) * LAT_FWD_FLOATS(n))
+
+LAT_GLOBAL void k_latent_integrate(LatentP p) {
+    LAT_SMEM
+    const int n = p.n, tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nw = (nt + 31) >> 5;
+    const int T = p.steps + 1;
+    double *red = (double *)lat_smem;
+    float *u = (float *)(red + 3 * LAT_MAX_WARPS);
+    float *acc = u + 4 * n, *sa = acc + 4 * n, *sb = sa + 4 * n;
+    float *cA = sb + 4 * n, *cB = cA + n, *cC = cB + n, *shp = cC + n, *sig = shp + n;
+    float *fac = sig + n;  // [2][4]: source factors of the three stage times, double-buffered by step parity
+
+    for (int i = tid; i < n; i += nt) {
+        for (int f = 0; f < 4; ++f) {
+            const float v = p.z0[((size_t)b * 4 + f) * n + i];
+            u[f * n + i] = v;
+            if (p.z) p.z[((size_t)b * 4 + f) * n + i] = v;  // frame 0 = ui (src/dynamics.jl:46)
+        }
+        shp[i] = p.shape ? p.shape[(size_t)b * n + i] : 0.0f;
+        sig[i] = p.pml_scale * p.pml[(size_t)b * n + i];  // σ = dyn.pml[[1]] .* PML (src/dynamics.jl:192-193)
+    }
+
+    const float sixth = 1.0f / 6.0f;
+    for (int s = 0; s <= p.steps; ++s) {
+        // ---- phase 0: energy of frame s, parameters of step s (every array written here is owner-only or double-buffered)
+        if (p.energy) {
+            double e[3] = {0.0, 0.0, 0.0};
+            for (int i = tid; i < n; i += nt) {
+                const float a = u[i], c = u[2 * n + i], d = a - c;  // tot .- inc in Float32 first
+                e[0] += (double)a * a;
+                e[1] += (double)c * c;
+                e[2] += (double)d * d;
+            }
+            lat_reduce3_warp(e, red, tid);
+        }
+        float *fc = fac + (s & 1) * 4;
+        if (s < p.steps) {
+            const float t0 = p.tspan[(size_t)b * T + s];
+            const float t1 = t0 + p.hdt, t2 = t0 + p.dt;
+            lat_speed(p, b, t0, cA, tid, nt);
+            lat_speed(p, b, t1, cB, tid, nt);
+            lat_speed(p, b, t2, cC, tid, nt);
+            if (tid < 3) fc[tid] = p.shape ? lat_sin_factor(tid == 0 ? t0 : (tid == 1 ? t1 : t2), p.freq) : 0.0f;
+        }
+        LAT_SYNC();
+        if (p.energy && tid < 3) {
+            double sum = 0.0;
+            for (int w = 0; w < nw; ++w) sum += red[w * 3 + tid];
+            p.energy[((size_t)b * 3 + tid) * T + s] = (float)sum * p.dx;  // sum(tot .^ 2, dims = 1) * dx
+        }
+        if (s == p.steps) break;
+
+        // ---- stage 1: k1 = f(u, t)
+        for (int i = tid; i < n; i += nt) {
+            float k[4];
+            lat_rhs(p, u, cA, shp, sig, fc[0], i, k);
+            for (int f = 0; f < 4; ++f) {
+                acc[f * n + i] = k[f];
+                sa[f * n + i] = u[f * n + i] + (p.hdt * k[f]);
+            }
+        }
+        LAT_SYNC();
+        // ---- stage 2: k2 = f(u + dt/2 k1, t + dt/2)
+        for (int i = tid; i < n; i += nt) {
+            float k[4];
+            lat_rhs(p, sa, cB, shp, sig, fc[1], i, k);
+            for (int f = 0; f < 4; ++f) {
+                acc[f * n + i] = acc[f * n + i] + (2.0f * k[f]);
+                sb[f * n + i] = u[f * n + i] + (p.hdt * k[f]);
+            }
+        }
+        LAT_SYNC();
+        // ---- stage 3: k3 = f(u + dt/2 k2, t + dt/2)
+        for (int i = tid; i < n; i += nt) {
+            float k[4];
+            lat_rhs(p, sb, cB, shp, sig, fc[1], i, k);
+            for (int f = 0; f < 4; ++f) {
+                acc[f * n + i] = acc[f * n + i] + (2.0f * k[f]);
+                sa[f * n + i] = u[f * n + i] + (p.dt * k[f]);
+            }
+        }
+        LAT_SYNC();
+        // ---- stage 4: k4 = f(u + dt k3, t + dt); u <- u + (1/6 (k1 + 2k2 + 2k3 + k4)) dt   (src/dynamics.jl:14-15, :41)
+        for (int i = tid; i < n; i += nt) {
+            float k[4];
+            lat_rhs(p, sa, cC, shp, sig, fc[2], i, k);
+            for (int f = 0; f < 4; ++f) {
+                const float du = (sixth * (acc[f * n + i] + k[f])) * p.dt;
+                const float v = u[f * n + i] + du;
+                u[f * n + i] = v;  // owner-only: stage 4 reads neighbours of sa, never of u
+                if (p.z) p.z[(((size_t)(s + 1) * p.batch + b) * 4 + f) * n + i] = v;
+            }
+        }
+        // no barrier here: phase 0 of the next step touches only this thread's own elements (and the other fac buffer)
+    }
+    if (p.z_last)
+        for (int i = tid; i < n; i += nt)
+            for (int f = 0; f < 4; ++f) p.z_last[((size_t)b * 4 + f) * n + i] = u[f * n + i];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// reverse pass: adjoint_sensitivity (src/dynamics.jl:97-118) for the batchwise OneDim simulation.
+//   exact  : λ_N = a_N;  λ_i = a_i + (I + J_iᵀ) λ_{i+1}
+//   compat : acc = 0; for i = N..0: acc = (I + J_iᵀ)(acc + a_i)          (the loop as written)
+// a_i = dL_dz[i] + d(Σ w_energy · energy)/dz_i.  One CTA per sample; per stored state z_i the three forward stage
+// states are recomputed in shared memory and four transposed right-hand sides are applied; parameter gradients
+// (C.Y through the interpolation weights, F.shape, PML) are accumulated by the owner thread of every element.
+#define LAT_ADJ_FLOATS(n) (39 * (size_t)(n) + 8)
+#define LAT_ADJ_SMEM(n) (sizeof(float) * LAT_ADJ_FLOATS(n))
+
+// vjp of one right-hand side: kb = cotangent of its output (shared, [4][n]), S = the stage state it was evaluated at.
+// Returns the cotangent of the stage state at element j in yb[4] and accumulates the parameter gradients of element j.
+LAT_DEV void lat_rhs_vjp(const LatentP &p, int b, const float *kb, const float *S, const float *c0c, const float *shp,
+                         const float *sig, float fs, float t, int j, float yb[4], float *gshp, float *gsig) {
+    const int n = p.n;
+    const float *Ut = S, *Vt = S + n, *Ui = S + 2 * n, *Vi = S + 3 * n;
+    auto bcf = [&](int i) { return (i == 0 || i == n - 1) ? 0.0f : 1.0f; };
+    const float bj = bcf(j), sj = sig[j];
+    const float tp = lat_grad_t(p, j, [&](int i) { return c0c[i] * kb[n + i]; });           // ∇ᵀ(a ⊙ w_Vtot)
+    const float tq = lat_grad_t(p, j, [&](int i) { return c0c[i] * bcf(i) * kb[i]; });      // ∇ᵀ(a ⊙ bc ⊙ w_Utot)
+    const float tr = lat_grad_t(p, j, [&](int i) { return kb[3 * n + i]; });                // ∇ᵀ(w_Vinc)
+    const float ts = lat_grad_t(p, j, [&](int i) { return bcf(i) * kb[2 * n + i]; });       // ∇ᵀ(bc ⊙ w_Uinc)
+    yb[0] = tp - sj * bj * kb[j];
+    yb[1] = tq - sj * kb[n + j];
+    yb[2] = p.c0 * tr - sj * bj * kb[2 * n + j];
+    yb[3] = p.c0 * ts - sj * kb[3 * n + j];
+    // parameters
+    if (gshp) gshp[j] += (tp + p.c0 * tr) * fs;  // f enters as ∇(U + f) of both wavefields
+    if (gsig) gsig[j] -= bj * kb[j] * Ut[j] + kb[n + j] * Vt[j] + bj * kb[2 * n + j] * Ui[j] + kb[3 * n + j] * Vi[j];
+    if (p.g_Y) {
+        const float gVt = lat_grad(p, j, [&](int i) { return Vt[i]; });
+        const float gUt = lat_grad(p, j, [&](int i) { return Ut[i] + shp[i] * fs; });
+        const float cbar = p.c0 * (bj * kb[j] * gVt + kb[n + j] * gUt);  // dL/dC(t)[j]
+        const float *Xb = p.X + (size_t)b * p.nseq;
+        float *gY = p.g_Y + (size_t)b * p.nseq * n;
+        const float rend = Xb[p.nseq - 1];
+        float x0 = 0.0f;
+        for (int k = 0; k + 1 < p.nseq; ++k)
+            if (lat_mask(Xb[k], Xb[k + 1], rend, t)) x0 = x0 + Xb[k];
+        for (int k = 0; k + 1 < p.nseq; ++k) {
+            const float l = Xb[k], r = Xb[k + 1];
+            if (lat_mask(l, r, rend, t)) {
+                const float wk = (t - x0) / ((r - t) - (l - t));
+                gY[(size_t)k * n + j] += cbar * (1.0f - wk);   // owner-only read-modify-write: no atomics needed
+                gY[(size_t)(k + 1) * n + j] += cbar * wk;
+            }
+        }
+    }
+}
+
+LAT_GLOBAL void k_latent_adjoint(LatentP p) {
+    LAT_SMEM
+    const int n = p.n, tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x;
+    const int T = p.steps + 1, N = p.steps;
+    float *zs = (float *)lat_smem;                       // z_i                        (neighbour reads)
+    float *y2 = zs + 4 * n, *y3 = y2 + 4 * n, *y4 = y3 + 4 * n;
+    float *kbA = y4 + 4 * n, *kbB = kbA + 4 * n;         // stage cotangents, double-buffered (neighbour reads)
+    float *lam = kbB + 4 * n, *zsum = lam + 4 * n;       // owner-only
+    float *cA = zsum + 4 * n, *cB = cA + n, *cC = cB + n, *shp = cC + n, *sig = shp + n;
+    float *gshp = sig + n, *gsig = gshp + n;             // owner-only accumulators
+    float *fac = gsig + n;                               // [2][4]
+
+    for (int i = tid; i < n; i += nt) {
+        shp[i] = p.shape ? p.shape[(size_t)b * n + i] : 0.0f;
+        sig[i] = p.pml_scale * p.pml[(size_t)b * n + i];
+        gshp[i] = 0.0f;
+        gsig[i] = 0.0f;
+        for (int f = 0; f < 4; ++f) lam[f * n + i] = 0.0f;
+    }
+    // a_i at the elements this thread owns, added to lam; zi = state i (global)
+    auto add_cotangent = [&](int i) {
+        const float *zi = p.zt + ((size_t)i * p.batch + b) * 4 * n;
+        float w3[3] = {0.0f, 0.0f, 0.0f};
+        if (p.w_energy)
+            for (int q = 0; q < 3; ++q) w3[q] = p.w_energy[((size_t)b * 3 + q) * T + i];
+        for (int e = tid; e < n; e += nt) {
+            if (p.w_energy) {
+                const float ut = zi[e], ui = zi[2 * n + e], d = ut - ui;
+                lam[e] += 2.0f * p.dx * (w3[0] * ut + w3[2] * d);
+                lam[2 * n + e] += 2.0f * p.dx * (w3[1] * ui - w3[2] * d);
+            }
+            if (p.dL_dz)
+                for (int f = 0; f < 4; ++f) lam[f * n + e] += p.dL_dz[(((size_t)i * p.batch + b) * 4 + f) * n + e];
+        }
+    };
+    if (!p.compat) add_cotangent(N);  // λ_N = a_N
+
+    const float dt = p.dt, hdt = p.hdt, sixth = 1.0f / 6.0f;
+    int it = 0;
+    for (int i = p.compat ? N : N - 1; i >= 0; --i, ++it) {
+        if (p.compat) add_cotangent(i);  // acc += a_i before the step vjp (src/dynamics.jl:110)
+        float *fc = fac + (it & 1) * 4;
+        const float t0 = p.tspan[(size_t)b * T + i];
+        const float t1 = t0 + hdt, t2 = t0 + dt;
+        lat_speed(p, b, t0, cA, tid, nt);
+        lat_speed(p, b, t1, cB, tid, nt);
+        lat_speed(p, b, t2, cC, tid, nt);
+        if (tid < 3) fc[tid] = p.shape ? lat_sin_factor(tid == 0 ? t0 : (tid == 1 ? t1 : t2), p.freq) : 0.0f;
+        const float *zi = p.zt + ((size_t)i * p.batch + b) * 4 * n;
+        for (int e = tid; e < n; e += nt)
+            for (int f = 0; f < 4; ++f) zs[f * n + e] = zi[f * n + e];
+        LAT_SYNC();
+        // ---- forward stage states y2 = z + dt/2 k1(z), y3 = z + dt/2 k2(y2), y4 = z + dt k3(y3)
+        for (int e = tid; e < n; e += nt) {
+            float k[4];
+            lat_rhs(p, zs, cA, shp, sig, fc[0], e, k);
+            for (int f = 0; f < 4; ++f) y2[f * n + e] = zs[f * n + e] + (hdt * k[f]);
+        }
+        LAT_SYNC();
+        for (int e = tid; e < n; e += nt) {
+            float k[4];
+            lat_rhs(p, y2, cB, shp, sig, fc[1], e, k);
+            for (int f = 0; f < 4; ++f) y3[f * n + e] = zs[f * n + e] + (hdt * k[f]);
+        }
+        LAT_SYNC();
+        for (int e = tid; e < n; e += nt) {
+            float k[4];
+            lat_rhs(p, y3, cB, shp, sig, fc[1], e, k);
+            for (int f = 0; f < 4; ++f) {
+                y4[f * n + e] = zs[f * n + e] + (dt * k[f]);
+                kbA[f * n + e] = (sixth * dt) * lam[f * n + e];  // cotangent of k4
+            }
+        }
+        LAT_SYNC();
+        // ---- reverse stages: ȳ4 = J4ᵀ k̄4; k̄3 = dt/3 λ + dt ȳ4; ȳ3 = J3ᵀ k̄3; k̄2 = dt/3 λ + dt/2 ȳ3; ȳ2 = J2ᵀ k̄2;
+        //      k̄1 = dt/6 λ + dt/2 ȳ2; ȳ1 = J1ᵀ k̄1;  δz = ȳ1 + ȳ2 + ȳ3 + ȳ4
+        for (int e = tid; e < n; e += nt) {
+            float yb[4];
+            lat_rhs_vjp(p, b, kbA, y4, cC, shp, sig, fc[2], t2, e, yb, p.g_shape ? gshp : nullptr, p.g_pml ? gsig : nullptr);
+            for (int f = 0; f < 4; ++f) {
+                zsum[f * n + e] = yb[f];
+                kbB[f * n + e] = (2.0f * sixth * dt) * lam[f * n + e] + dt * yb[f];
+            }
+        }
+        LAT_SYNC();
+        for (int e = tid; e < n; e += nt) {
+            float yb[4];
+            lat_rhs_vjp(p, b, kbB, y3, cB, shp, sig, fc[1], t1, e, yb, p.g_shape ? gshp : nullptr, p.g_pml ? gsig : nullptr);
+            for (int f = 0; f < 4; ++f) {
+                zsum[f * n + e] += yb[f];
+                kbA[f * n + e] = (2.0f * sixth * dt) * lam[f * n + e] + hdt * yb[f];
+            }
+        }
+        LAT_SYNC();
+        for (int e = tid; e < n; e += nt) {
+            float yb[4];
+            lat_rhs_vjp(p, b, kbA, y2, cB, shp, sig, fc[1], t1, e, yb, p.g_shape ? gshp : nullptr, p.g_pml ? gsig : nullptr);
+            for (int f = 0; f < 4; ++f) {
+                zsum[f * n + e] += yb[f];
+                kbB[f * n + e] = (sixth * dt) * lam[f * n + e] + hdt * yb[f];
+            }
+        }
+        LAT_SYNC();
+        for (int e = tid; e < n; e += nt) {
+            float yb[4];
+            lat_rhs_vjp(p, b, kbB, zs, cA, shp, sig, fc[0], t0, e, yb, p.g_shape ? gshp : nullptr, p.g_pml ? gsig : nullptr);
+            for (int f = 0; f < 4; ++f) lam[f * n + e] += zsum[f * n + e] + yb[f];  // λ <- λ + δz
+        }
+        if (!p.compat) add_cotangent(i);  // λ_i = a_i + (I + J_iᵀ) λ_{i+1}
+        LAT_SYNC();  // zs, kbB and the stage states are rewritten by the next iteration
+    }
+    for (int e = tid; e < n; e += nt) {
+        for (int f = 0; f < 4; ++f) p.g_z0[((size_t)b * 4 + f) * n + e] = lam[f * n + e];
+        if (p.g_shape) p.g_shape[(size_t)b * n + e] = gshp[e];
+        if (p.g_pml) p.g_pml[(size_t)b * n + e] = p.pml_scale * gsig[e];  // σ = pml_scale .* PML
+    }
+}
