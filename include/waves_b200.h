@@ -249,6 +249,9 @@ int waves_latent_adjoint(waves_latent *h, int batch, int steps, int nseq, const 
 /* build_pml(::OneDim, width, scale), src/pml.jl:6-15: out (n, nullable), *first = its first value (nullable). HOST. */
 int waves_latent_build_pml(const float *x, int n, float width, float scale, float *out, float *first);
 int64_t waves_latent_launch_count(waves_latent *h);
+/* on != 0: always run the generic shared-memory kernels (any n that fits) instead of the register fast path taken for
+ * n <= 1024 and nseq <= 64; both are bit-identical, the switch exists so tests can compare them */
+int waves_latent_set_generic(waves_latent *h, int on);
 /* device time (ms, CUDA events on the handle's stream) of the kernel of the last integrate / adjoint call */
 float waves_latent_last_kernel_ms(waves_latent *h);
 

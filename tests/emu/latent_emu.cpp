@@ -40,6 +40,19 @@ static inline void lat_emu_reduce3(double v[3], double *red, int tid) {
     pthread_barrier_wait(&g_bar);  // g_part is rewritten by the next call
 }
 
+static inline void lat_emu_reduce3f(float v[3], float *red, int tid) {
+    for (int q = 0; q < 3; ++q) g_part[tid * 3 + q] = v[q];
+    pthread_barrier_wait(&g_bar);
+    if ((tid & 31) == 0) {
+        for (int q = 0; q < 3; ++q) {
+            float s = 0.0f;
+            for (int l = 0; l < 32 && tid + l < blockDim.x; ++l) s += (float)g_part[(tid + l) * 3 + q];
+            red[(tid >> 5) * 3 + q] = s;
+        }
+    }
+    pthread_barrier_wait(&g_bar);
+}
+
 #include "../../waves.jl_b200/csrc/latent_core.cuh"
 
 template <class K>
@@ -64,4 +77,5 @@ static void launch(K kernel, const LatentP &p, int nt, size_t smem) {
 
 extern "C" int emu_sizeof_latentp() { return (int)sizeof(LatentP); }
 extern "C" void emu_latent_integrate(const LatentP *p, int nt) { launch(k_latent_integrate, *p, nt, LAT_FWD_SMEM(p->n)); }
+extern "C" void emu_latent_integrate_r1(const LatentP *p, int nt) { launch(k_latent_integrate_r1, *p, nt, LAT_R1_SMEM(p->n)); }
 extern "C" void emu_latent_adjoint(const LatentP *p, int nt) { launch(k_latent_adjoint, *p, nt, LAT_ADJ_SMEM(p->n)); }

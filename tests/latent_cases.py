@@ -20,6 +20,9 @@ def make_case(n=96, batch=3, steps=24, nseq=4, seed=0, gs=100.0, dt=1e-5, c0=153
         stride = steps // (nseq - 1)
         assert stride * (nseq - 1) == steps
         X = np.ascontiguousarray(tspan[:, ::stride])
+    elif knots == "repeated":  # knots that are not increasing: two segment masks are true at once (their terms add up)
+        X = np.ascontiguousarray(tspan[:, [0, steps, steps // 2, steps]])
+        assert nseq == 4
     else:                      # knots that do not cover the whole span: queries outside every segment give C = 0
         X = np.stack([np.linspace(tspan[b, 2], tspan[b, -3], nseq).astype(F32) for b in range(batch)])
     Y = (1.0 + 0.5 * rng.random((batch, nseq, n))).astype(F32)                                        # 2σ(·) ∈ (0, 2)

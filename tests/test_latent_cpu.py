@@ -125,16 +125,21 @@ def _params(cs, **ptrs):
     return p, keep
 
 
-@pytest.mark.parametrize("n,nt,knots", [(96, 96, "actions"), (200, 64, "actions"), (70, 96, "partial")])
-def test_emulated_forward_kernel_is_bit_exact(emu, n, nt, knots):
-    """k_latent_integrate == oracle integrate, bit for bit (fields), energies to 1e-6; threads == elements, a strided
-    ownership (n > threads), idle threads (threads > n), and knots that leave stage times outside every segment."""
-    cs = make_case(n=n, batch=2, steps=12, nseq=4, seed=n, knots=knots)
+@pytest.mark.parametrize("kernel,n,nt,knots,steps", [
+    ("generic", 96, 96, "actions", 12), ("generic", 200, 64, "actions", 12), ("generic", 70, 96, "partial", 12),
+    ("r1", 96, 96, "actions", 12), ("r1", 70, 96, "partial", 12), ("r1", 100, 128, "repeated", 12),
+    ("r1", 33, 64, "actions", 520)])
+def test_emulated_forward_kernel_is_bit_exact(emu, kernel, n, nt, knots, steps):
+    """k_latent_integrate / k_latent_integrate_r1 == oracle integrate, bit for bit (fields), energies to 1e-6; threads ==
+    elements, a strided ownership (n > threads, generic kernel only), idle threads (threads > n), knots that leave stage
+    times outside every segment, repeated knots (two masks true at once: no cursor), and more steps than one table of
+    source factors holds."""
+    cs = make_case(n=n, batch=2, steps=steps, nseq=5 if steps > 100 else 4, seed=n, knots=knots)
     z = np.full((cs["steps"] + 1, cs["batch"], 4, n), np.nan, F32)
     e = np.full((cs["batch"], 3, cs["steps"] + 1), np.nan, F32)
     last = np.full((cs["batch"], 4, n), np.nan, F32)
     p, keep = _params(cs, z=z, energy=e, z_last=last)
-    emu.emu_latent_integrate(C.byref(p), nt)
+    (emu.emu_latent_integrate if kernel == "generic" else emu.emu_latent_integrate_r1)(C.byref(p), nt)
     want = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
     assert np.isfinite(want).all() and np.abs(want[-1] - want[0]).max() > 1e-3      # the case does something
     assert np.array_equal(z, want)
@@ -143,13 +148,14 @@ def test_emulated_forward_kernel_is_bit_exact(emu, n, nt, knots):
     np.testing.assert_allclose(e, we, rtol=1e-6, atol=1e-6 * we.max())
 
 
-def test_emulated_forward_kernel_energy_only(emu):
+@pytest.mark.parametrize("kernel", ["generic", "r1"])
+def test_emulated_forward_kernel_energy_only(emu, kernel):
     """With z == NULL only the energies and the last state leave the kernel."""
     cs = make_case(n=64, batch=2, steps=8, nseq=3, seed=5)
     e = np.full((2, 3, 9), np.nan, F32)
     last = np.full((2, 4, 64), np.nan, F32)
     p, keep = _params(cs, energy=e, z_last=last)
-    emu.emu_latent_integrate(C.byref(p), 64)
+    (emu.emu_latent_integrate if kernel == "generic" else emu.emu_latent_integrate_r1)(C.byref(p), 64)
     want = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
     assert np.array_equal(last, want[-1])
     np.testing.assert_allclose(e, lo.compute_latent_energy(want, wo.get_dx(cs["dim"])), rtol=1e-6)

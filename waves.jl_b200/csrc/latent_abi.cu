@@ -38,6 +38,7 @@ struct waves_latent {
     int64_t launches;
     cudaEvent_t ev0, ev1;  // around the last kernel launch
     float last_ms;
+    int force_generic;  // 1: never use the register fast path (tests compare the two)
 };
 
 static bool on_device(const void *p) {
@@ -225,9 +226,16 @@ extern "C" int waves_latent_integrate(waves_latent *h, int batch, int steps, int
         dev_out(h, 10, z_last, st, &p.z_last))
         return 1;
     // the attribute belongs to the function, not the handle: handles with different n may alternate
-    LCU(cudaFuncSetAttribute(k_latent_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_FWD_SMEM(n)));
+    const bool fast = !h->force_generic && h->n <= 1024 && nseq <= LAT_FAST_NSEQ;  // one element per thread, knots in shared memory
+    if (fast)
+        LCU(cudaFuncSetAttribute(k_latent_integrate_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_R1_SMEM(n)));
+    else
+        LCU(cudaFuncSetAttribute(k_latent_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_FWD_SMEM(n)));
     LCU(cudaEventRecord(h->ev0, h->stream));
-    k_latent_integrate<<<batch, threads_for(h->n), LAT_FWD_SMEM(n), h->stream>>>(p);
+    if (fast)
+        k_latent_integrate_r1<<<batch, threads_for(h->n), LAT_R1_SMEM(n), h->stream>>>(p);
+    else
+        k_latent_integrate<<<batch, threads_for(h->n), LAT_FWD_SMEM(n), h->stream>>>(p);
     h->launches++;
     LCU(cudaGetLastError());
     LCU(cudaEventRecord(h->ev1, h->stream));
@@ -274,6 +282,12 @@ extern "C" int waves_latent_adjoint(waves_latent *h, int batch, int steps, int n
         return 1;
     LCU(cudaStreamSynchronize(h->stream));
     LCU(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    return 0;
+}
+
+extern "C" int waves_latent_set_generic(waves_latent *h, int on) {
+    if (!h) LFAIL("waves_latent_set_generic: null handle");
+    h->force_generic = on != 0;
     return 0;
 }
 

@@ -87,33 +87,33 @@ LAT_DEV float lat_sin_factor(float t, float freq) {
 // the reference's segment mask (src/utils.jl:79-80)
 LAT_DEV bool lat_mask(float l, float r, float rend, float t) { return ((l <= t) && (t < r)) || ((r == rend) && (rend == t)); }
 
-// c0 * C(t) for the elements this thread owns (src/utils.jl:70-86, src/dynamics.jl:210): masks and sums as written
+// c0 * C(t) at element i (src/utils.jl:70-86, src/dynamics.jl:210): masks and sums as written.  Xb: the knots of this
+// sample (global or shared), Yb: its values [nseq][n]
+LAT_DEV float lat_speed_elem(const LatentP &p, const float *Xb, const float *Yb, float t, int i) {
+    const float rend = Xb[p.nseq - 1];
+    float x0 = 0.0f, y0 = 0.0f, dydx = 0.0f;
+    for (int k = 0; k + 1 < p.nseq; ++k) {
+        const float l = Xb[k], r = Xb[k + 1];
+        if (lat_mask(l, r, rend, t)) {
+            const float dd = (r - t) - (l - t);  // diff(X .- x): the query is subtracted before the difference
+            const float yk = Yb[(size_t)k * p.n + i], yk1 = Yb[(size_t)(k + 1) * p.n + i];
+            x0 = x0 + l;
+            y0 = y0 + yk;
+            dydx = dydx + (yk1 - yk) / dd;
+        }
+    }
+    return p.c0 * (y0 + (t - x0) * dydx);
+}
+
+// the same for every element this thread owns (generic kernels)
 LAT_DEV void lat_speed(const LatentP &p, int b, float t, float *cout, int tid, int nt) {
     const float *Xb = p.X + (size_t)b * p.nseq;
     const float *Yb = p.Y + (size_t)b * p.nseq * p.n;
-    const float rend = Xb[p.nseq - 1];
-    float x0 = 0.0f;
-    for (int k = 0; k + 1 < p.nseq; ++k)
-        if (lat_mask(Xb[k], Xb[k + 1], rend, t)) x0 = x0 + Xb[k];
-    const float tx = t - x0;
-    for (int i = tid; i < p.n; i += nt) {
-        float y0 = 0.0f, dydx = 0.0f;
-        for (int k = 0; k + 1 < p.nseq; ++k) {
-            const float l = Xb[k], r = Xb[k + 1];
-            if (lat_mask(l, r, rend, t)) {
-                const float dd = (r - t) - (l - t);  // diff(X .- x): the query is subtracted before the difference
-                const float yk = Yb[(size_t)k * p.n + i], yk1 = Yb[(size_t)(k + 1) * p.n + i];
-                y0 = y0 + yk;
-                dydx = dydx + (yk1 - yk) / dd;
-            }
-        }
-        cout[i] = p.c0 * (y0 + tx * dydx);
-    }
+    for (int i = tid; i < p.n; i += nt) cout[i] = lat_speed_elem(p, Xb, Yb, t, i);
 }
 
 // one right-hand side at element i: S = stage state [4][n] in shared memory, c0c = c0*C(t), fs = source factor
-LAT_DEV void lat_rhs(const LatentP &p, const float *S, const float *c0c, const float *shp, const float *sig, float fs, int i,
-                     float k[4]) {
+LAT_DEV void lat_rhs_s(const LatentP &p, const float *S, float a, const float *shp, float s, float fs, int i, float k[4]) {
     const int n = p.n;
     const float *Ut = S, *Vt = S + n, *Ui = S + 2 * n, *Vi = S + 3 * n;
     const float bc = (i == 0 || i == n - 1) ? 0.0f : 1.0f;  // build_dirichlet(::OneDim), src/dims.jl:111-115
@@ -121,11 +121,15 @@ LAT_DEV void lat_rhs(const LatentP &p, const float *S, const float *c0c, const f
     const float gUt = lat_grad(p, i, [&](int j) { return Ut[j] + (shp[j] * fs); });  // ∇ * (U_tot .+ f)
     const float gVi = lat_grad(p, i, [&](int j) { return Vi[j]; });
     const float gUi = lat_grad(p, i, [&](int j) { return Ui[j] + (shp[j] * fs); });
-    const float a = c0c[i], s = sig[i];
     k[0] = ((a * gVt) - (s * Ut[i])) * bc;     // src/dynamics.jl:210, :217
     k[1] = (a * gUt) - (s * Vt[i]);            // :211
     k[2] = ((p.c0 * gVi) - (s * Ui[i])) * bc;  // :213, :219
     k[3] = (gUi * p.c0) - (s * Vi[i]);         // :214
+}
+
+LAT_DEV void lat_rhs(const LatentP &p, const float *S, const float *c0c, const float *shp, const float *sig, float fs, int i,
+                     float k[4]) {
+    lat_rhs_s(p, S, c0c[i], shp, sig[i], fs, i, k);
 }
 
 // Σ over the block of three doubles per thread; result valid in out[0..2] (shared) after the NEXT barrier
@@ -240,6 +244,171 @@ LAT_GLOBAL void k_latent_integrate(LatentP p) {
     if (p.z_last)
         for (int i = tid; i < n; i += nt)
             for (int f = 0; f < 4; ++f) p.z_last[((size_t)b * 4 + f) * n + i] = u[f * n + i];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Register fast path of the forward kernel: n <= 1024 (the reference's latent grid), one element per thread.
+// ncu on the generic kernel above (profiles/r1_latent_ncu_summary.json): issue-bound, ~1300 warp instructions per warp per
+// RK4 step.  Here the element's state, stage sum, damping and the interpolation operands stay in registers; only the four
+// stage values are exchanged through two ping-pong shared buffers (4 STS + 8 LDS per stage); the knots live in shared
+// memory and, when they increase strictly (then at most one segment mask is true), a cursor replaces the scan; the sine
+// factors of LAT_CH steps are tabulated by all threads at once instead of by three threads on the critical path.
+// Same float32 evaluation order: bit-exact with the generic kernel and the oracle.  Interior threads read i-1 / i+1;
+// the two boundary threads evaluate the three-point rows from shared memory.
+#define LAT_CH 256
+#define LAT_FAST_NSEQ 64
+#define LAT_R1_FLOATS(n) (9 * (size_t)(n) + LAT_FAST_NSEQ + 2 * 3 * LAT_CH + 3 * LAT_MAX_WARPS + 8)
+#define LAT_R1_SMEM(n) (sizeof(float) * LAT_R1_FLOATS(n))
+
+LAT_DEV void lat_reduce3f_warp(float v[3], float *red, int tid) {
+#ifndef LAT_EMU
+    for (int o = 16; o > 0; o >>= 1)
+        for (int q = 0; q < 3; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+    if ((tid & 31) == 0)
+        for (int q = 0; q < 3; ++q) red[(tid >> 5) * 3 + q] = v[q];
+#else
+    lat_emu_reduce3f(v, red, tid);
+#endif
+}
+
+LAT_GLOBAL void k_latent_integrate_r1(LatentP p) {
+    LAT_SMEM
+    const int n = p.n, tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nw = (nt + 31) >> 5;
+    const int T = p.steps + 1, i = tid;
+    float *B0 = (float *)lat_smem, *B1 = B0 + 4 * n;  // ping-pong stage states [4][n]
+    float *shs = B1 + 4 * n;                          // source shape (the boundary rows read three of them)
+    float *Xs = shs + n;                              // knots of this sample
+    float *fcs = Xs + LAT_FAST_NSEQ;                  // [2][LAT_CH][3] source factors, double-buffered by chunk
+    float *red = fcs + 2 * 3 * LAT_CH;                // [warps][3]
+    const bool act = i < n, inner = act && i > 0 && i < n - 1;
+    const float *Yb = p.Y + (size_t)b * p.nseq * n;
+
+    float u[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc[4], ys[4], sg = 0.0f;
+    if (act) {
+        for (int f = 0; f < 4; ++f) {
+            u[f] = p.z0[((size_t)b * 4 + f) * n + i];
+            B0[f * n + i] = u[f];
+            if (p.z) p.z[((size_t)b * 4 + f) * n + i] = u[f];
+        }
+        shs[i] = p.shape ? p.shape[(size_t)b * n + i] : 0.0f;
+        sg = p.pml_scale * p.pml[(size_t)b * n + i];
+    }
+    for (int k = tid; k < p.nseq; k += nt) Xs[k] = p.X[(size_t)b * p.nseq + k];
+    LAT_SYNC();
+    const float shm = inner ? shs[i - 1] : 0.0f, shpp = inner ? shs[i + 1] : 0.0f;
+    bool mono = true;  // strictly increasing knots: the segment masks exclude one another
+    for (int k = 0; k + 1 < p.nseq; ++k) mono = mono && (Xs[k] < Xs[k + 1]);
+    const float rend = Xs[p.nseq - 1];
+    int kcur = 0, kload = -1;
+    float yk = 0.0f, yk1 = 0.0f;
+
+    auto speed = [&](float t) -> float {  // c0 * C(t) at this thread's element
+        if (!act) return 0.0f;
+        if (!mono) return lat_speed_elem(p, Xs, Yb, t, i);
+        while (kcur + 2 < p.nseq && t >= Xs[kcur + 1]) ++kcur;
+        while (kcur > 0 && t < Xs[kcur]) --kcur;
+        const float l = Xs[kcur], r = Xs[kcur + 1];
+        if (!lat_mask(l, r, rend, t)) return p.c0 * (0.0f + (t - 0.0f) * 0.0f);  // no segment: sums of zeros
+        if (kload != kcur) {
+            yk = Yb[(size_t)kcur * n + i];
+            yk1 = Yb[(size_t)(kcur + 1) * n + i];
+            kload = kcur;
+        }
+        const float dd = (r - t) - (l - t);
+        const float x0 = 0.0f + l, y0 = 0.0f + yk, dydx = 0.0f + (yk1 - yk) / dd;
+        return p.c0 * (y0 + (t - x0) * dydx);
+    };
+    auto rhs = [&](const float *S, float a, float fs, const float own[4], float k[4]) {
+        if (inner) {
+            const float *Ut = S, *Vt = S + n, *Ui = S + 2 * n, *Vi = S + 3 * n;
+            const float fm = shm * fs, fq = shpp * fs;
+            const float gVt = (p.gc[0] * Vt[i - 1]) + (p.gc[1] * Vt[i + 1]);
+            const float gUt = (p.gc[0] * (Ut[i - 1] + fm)) + (p.gc[1] * (Ut[i + 1] + fq));
+            const float gVi = (p.gc[0] * Vi[i - 1]) + (p.gc[1] * Vi[i + 1]);
+            const float gUi = (p.gc[0] * (Ui[i - 1] + fm)) + (p.gc[1] * (Ui[i + 1] + fq));
+            k[0] = (a * gVt) - (sg * own[0]);  // bc = 1 inside
+            k[1] = (a * gUt) - (sg * own[1]);
+            k[2] = (p.c0 * gVi) - (sg * own[2]);
+            k[3] = (gUi * p.c0) - (sg * own[3]);
+        } else if (act) {
+            lat_rhs_s(p, S, a, shs, sg, fs, i, k);
+        }
+    };
+
+    const float sixth = 1.0f / 6.0f;
+    float t0 = p.steps > 0 ? p.tspan[(size_t)b * T] : 0.0f;
+    for (int s = 0; s <= p.steps; ++s) {
+        // ---- phase 0 (owner-only data, the red slots and the OTHER factor buffer): energy of frame s, speeds of step s
+        if (p.energy) {
+            const float a = u[0], c = u[2], d = a - c;  // tot .- inc in Float32 first
+            float e[3] = {a * a, c * c, d * d};
+            lat_reduce3f_warp(e, red, tid);
+        }
+        float cA = 0.0f, cB = 0.0f, cC = 0.0f;
+        if (s < p.steps) {
+            if (s % LAT_CH == 0) {  // tabulate the source factors of the next LAT_CH steps
+                float *fw = fcs + ((s / LAT_CH) & 1) * 3 * LAT_CH;
+                for (int q = tid; q < 3 * LAT_CH; q += nt) {
+                    const int st = s + q / 3, w = q - 3 * (q / 3);
+                    if (st < p.steps) {
+                        const float ts = p.tspan[(size_t)b * T + st];
+                        fw[q] = p.shape ? lat_sin_factor(w == 0 ? ts : (w == 1 ? ts + p.hdt : ts + p.dt), p.freq) : 0.0f;
+                    }
+                }
+            }
+            cA = speed(t0);
+            cB = speed(t0 + p.hdt);
+            cC = speed(t0 + p.dt);
+        }
+        LAT_SYNC();
+        if (p.energy && tid < 3) {
+            double sum = 0.0;
+            for (int w = 0; w < nw; ++w) sum += (double)red[w * 3 + tid];
+            p.energy[((size_t)b * 3 + tid) * T + s] = (float)sum * p.dx;
+        }
+        if (s == p.steps) break;
+        const float *fc = fcs + ((s / LAT_CH) & 1) * 3 * LAT_CH + 3 * (s % LAT_CH);
+        const float f0 = fc[0], f1 = fc[1], f2 = fc[2];
+        if (s + 1 < p.steps) t0 = p.tspan[(size_t)b * T + s + 1];  // next step's time, off the critical path
+
+        float k[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        // ---- stage 1: reads B0 (= u), writes y2 to B1
+        rhs(B0, cA, f0, u, k);
+        for (int f = 0; f < 4; ++f) {
+            acc[f] = k[f];
+            ys[f] = u[f] + (p.hdt * k[f]);
+            if (act) B1[f * n + i] = ys[f];
+        }
+        LAT_SYNC();
+        // ---- stage 2: reads B1 (= y2), writes y3 to B0 (u itself lives in registers)
+        rhs(B1, cB, f1, ys, k);
+        for (int f = 0; f < 4; ++f) {
+            acc[f] = acc[f] + (2.0f * k[f]);
+            ys[f] = u[f] + (p.hdt * k[f]);
+            if (act) B0[f * n + i] = ys[f];
+        }
+        LAT_SYNC();
+        // ---- stage 3: reads B0 (= y3), writes y4 to B1
+        rhs(B0, cB, f1, ys, k);
+        for (int f = 0; f < 4; ++f) {
+            acc[f] = acc[f] + (2.0f * k[f]);
+            ys[f] = u[f] + (p.dt * k[f]);
+            if (act) B1[f * n + i] = ys[f];
+        }
+        LAT_SYNC();
+        // ---- stage 4: reads B1 (= y4), writes the new state to B0 (its last readers passed two barriers ago)
+        rhs(B1, cC, f2, ys, k);
+        for (int f = 0; f < 4; ++f) {
+            const float du = (sixth * (acc[f] + k[f])) * p.dt;
+            u[f] = u[f] + du;
+            if (act) {
+                B0[f * n + i] = u[f];
+                if (p.z) p.z[(((size_t)(s + 1) * p.batch + b) * 4 + f) * n + i] = u[f];
+            }
+        }
+    }
+    if (p.z_last && act)
+        for (int f = 0; f < 4; ++f) p.z_last[((size_t)b * 4 + f) * n + i] = u[f];
 }
 
 // ------------------------------------------------------------------------------------------------------------------

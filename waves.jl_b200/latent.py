@@ -140,6 +140,10 @@ class LatentIntegrator:
                                               _ptr(g["pml"])))
         return g
 
+    def set_generic(self, on: bool):
+        """Force the generic shared-memory kernels (the register fast path is the default where it applies)."""
+        check(_lib.lib().waves_latent_set_generic(self._h, int(bool(on))))
+
     def last_kernel_ms(self) -> float:
         """Device time of the kernel of the last call (CUDA events on the handle's stream)."""
         return float(_lib.lib().waves_latent_last_kernel_ms(self._h))
