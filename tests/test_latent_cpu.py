@@ -127,7 +127,7 @@ def _params(cs, **ptrs):
 
 @pytest.mark.parametrize("kernel,n,nt,knots,steps", [
     ("generic", 96, 96, "actions", 12), ("generic", 200, 64, "actions", 12), ("generic", 70, 96, "partial", 12),
-    ("r1", 96, 96, "actions", 12), ("r1", 70, 96, "partial", 12), ("r1", 100, 128, "repeated", 12),
+    ("r1", 96, 96, "actions", 12), ("r1", 70, 96, "partial", 12), ("r1", 100, 128, "repeated", 12), ("r1", 170, 192, "actions", 12),
     ("r1", 33, 64, "actions", 520)])
 def test_emulated_forward_kernel_is_bit_exact(emu, kernel, n, nt, knots, steps):
     """k_latent_integrate / k_latent_integrate_r1 == oracle integrate, bit for bit (fields), energies to 1e-6; threads ==

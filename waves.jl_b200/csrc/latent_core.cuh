@@ -271,6 +271,21 @@ LAT_DEV void lat_reduce3f_warp(float v[3], float *red, int tid) {
 #endif
 }
 
+// Σ of one double per lane, valid in lane 0 (the emulation sums the shared slots directly)
+LAT_DEV double lat_warp_sum(double v, const float *red, int nw, int q, int lane) {
+#ifndef LAT_EMU
+    (void)red; (void)nw; (void)q; (void)lane;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+#else
+    double sum = 0.0;
+    if (lane == 0)
+        for (int w = 0; w < nw; ++w) sum += (double)red[w * 3 + q];
+    (void)v;
+    return sum;
+#endif
+}
+
 LAT_GLOBAL void k_latent_integrate_r1(LatentP p) {
     LAT_SMEM
     const int n = p.n, tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nw = (nt + 31) >> 5;
@@ -318,9 +333,20 @@ LAT_GLOBAL void k_latent_integrate_r1(LatentP p) {
         const float x0 = 0.0f + l, y0 = 0.0f + yk, dydx = 0.0f + (yk1 - yk) / dd;
         return p.c0 * (y0 + (t - x0) * dydx);
     };
+    // The two warps that hold elements 0 and n-1 run a branch-free three-term form of the derivative rows (a per-thread
+    // select keeps the two-term value for their interior lanes), so no warp diverges: ncu/timing showed the barriers
+    // waiting for those two warps when the boundary rows were a divergent out-of-line path.
+    const int wlo = i & ~31;
+    const bool edge_warp = wlo == 0 || (wlo <= n - 1 && n - 1 < wlo + 32);
+    const bool first = act && i == 0, last = act && i == n - 1;
+    const int o0 = first ? 0 : (last ? -2 : -1), o1 = first ? 1 : (last ? -1 : 1), o2 = first ? 2 : 0;
+    const float q0 = first ? p.gf[0] : (last ? p.gl[0] : p.gc[0]), q1 = first ? p.gf[1] : (last ? p.gl[1] : p.gc[1]);
+    const float q2 = first ? p.gf[2] : (last ? p.gl[2] : 0.0f);
+    const float bcv = (first || last) ? 0.0f : 1.0f;
+    const float s0 = act ? shs[i + o0] : 0.0f, s1 = act ? shs[i + o1] : 0.0f, s2 = act ? shs[i + o2] : 0.0f;
     auto rhs = [&](const float *S, float a, float fs, const float own[4], float k[4]) {
-        if (inner) {
-            const float *Ut = S, *Vt = S + n, *Ui = S + 2 * n, *Vi = S + 3 * n;
+        const float *Ut = S, *Vt = S + n, *Ui = S + 2 * n, *Vi = S + 3 * n;
+        if (!edge_warp && inner) {  // every lane of the warp is interior
             const float fm = shm * fs, fq = shpp * fs;
             const float gVt = (p.gc[0] * Vt[i - 1]) + (p.gc[1] * Vt[i + 1]);
             const float gUt = (p.gc[0] * (Ut[i - 1] + fm)) + (p.gc[1] * (Ut[i + 1] + fq));
@@ -331,7 +357,21 @@ LAT_GLOBAL void k_latent_integrate_r1(LatentP p) {
             k[2] = (p.c0 * gVi) - (sg * own[2]);
             k[3] = (gUi * p.c0) - (sg * own[3]);
         } else if (act) {
-            lat_rhs_s(p, S, a, shs, sg, fs, i, k);
+            const bool three = first || last;
+            const float f0 = s0 * fs, f1 = s1 * fs, f2 = s2 * fs;
+            auto row = [&](float v0, float v1, float v2) {
+                const float two = (q0 * v0) + (q1 * v1);
+                const float thr = two + (q2 * v2);
+                return three ? thr : two;
+            };
+            const float gVt = row(Vt[i + o0], Vt[i + o1], Vt[i + o2]);
+            const float gUt = row(Ut[i + o0] + f0, Ut[i + o1] + f1, Ut[i + o2] + f2);
+            const float gVi = row(Vi[i + o0], Vi[i + o1], Vi[i + o2]);
+            const float gUi = row(Ui[i + o0] + f0, Ui[i + o1] + f1, Ui[i + o2] + f2);
+            k[0] = ((a * gVt) - (sg * own[0])) * bcv;  // x * 1 is exact: one instruction stream for all lanes
+            k[1] = (a * gUt) - (sg * own[1]);
+            k[2] = ((p.c0 * gVi) - (sg * own[2])) * bcv;
+            k[3] = (gUi * p.c0) - (sg * own[3]);
         }
     };
 
@@ -361,10 +401,18 @@ LAT_GLOBAL void k_latent_integrate_r1(LatentP p) {
             cC = speed(t0 + p.dt);
         }
         LAT_SYNC();
-        if (p.energy && tid < 3) {
-            double sum = 0.0;
-            for (int w = 0; w < nw; ++w) sum += (double)red[w * 3 + tid];
-            p.energy[((size_t)b * 3 + tid) * T + s] = (float)sum * p.dx;
+        if (p.energy) {  // Σ over the warps, in double: one warp per quantity (warps 1..3, none of them an edge warp)
+            const int w = tid >> 5, lane = tid & 31;
+            if (nw >= 5) {
+                if (w >= 1 && w <= 3) {
+                    const double sum = lat_warp_sum(lane < nw ? (double)red[lane * 3 + (w - 1)] : 0.0, red, nw, w - 1, lane);
+                    if (lane == 0) p.energy[((size_t)b * 3 + (w - 1)) * T + s] = (float)sum * p.dx;
+                }
+            } else if (tid < 3) {
+                double sum = 0.0;
+                for (int ww = 0; ww < nw; ++ww) sum += (double)red[ww * 3 + tid];
+                p.energy[((size_t)b * 3 + tid) * T + s] = (float)sum * p.dx;
+            }
         }
         if (s == p.steps) break;
         const float *fc = fcs + ((s / LAT_CH) & 1) * 3 * LAT_CH + 3 * (s % LAT_CH);
