@@ -17,6 +17,8 @@ it = wb.LatentIntegrator(wb.LatentDynamics(wb.OneDim(cs["dim"].x), 1531.0, 10.0,
 theta = [wb.LinearInterpolation(th.X, th.Y), wb.LatentSource(th.shape, th.freq), th.pml]
 last, e = it(cs["z0"], cs["tspan"], theta, want_z=False, want_energy=True)
 print("fwd ms", it.last_kernel_ms())
+if os.environ.get("LAT_ONLY_FWD"):
+    sys.exit(0)
 z = it(cs["z0"], cs["tspan"], theta)
 it.adjoint(z, cs["tspan"], theta, w_energy=np.ones((148, 3, steps + 1), np.float32))
 print("adj ms", it.last_kernel_ms())

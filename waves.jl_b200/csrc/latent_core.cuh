@@ -310,28 +310,40 @@ LAT_GLOBAL void k_latent_integrate_r1(LatentP p) {
     }
     for (int k = tid; k < p.nseq; k += nt) Xs[k] = p.X[(size_t)b * p.nseq + k];
     LAT_SYNC();
-    const float shm = inner ? shs[i - 1] : 0.0f, shpp = inner ? shs[i + 1] : 0.0f;
     bool mono = true;  // strictly increasing knots: the segment masks exclude one another
     for (int k = 0; k + 1 < p.nseq; ++k) mono = mono && (Xs[k] < Xs[k + 1]);
     const float rend = Xs[p.nseq - 1];
-    int kcur = 0, kload = -1;
+    int kcur = 0;
     float yk = 0.0f, yk1 = 0.0f;
+    float lc = 1.0f, rc = 0.0f;  // knots of the segment whose values yk, yk1 are loaded: empty until the first query
 
-    auto speed = [&](float t) -> float {  // c0 * C(t) at this thread's element
-        if (!act) return 0.0f;
+    // c0 * C(t) at this thread's element.  Common case (ncu: the three queries were 240 of 800 instructions per step):
+    // t lies in the segment of the previous query, whose knots and values are in registers -- then its mask is the only
+    // true one (strictly increasing knots) and the result is the reference's expression for that segment.
+    auto speed_slow = [&](float t) -> float {
         if (!mono) return lat_speed_elem(p, Xs, Yb, t, i);
         while (kcur + 2 < p.nseq && t >= Xs[kcur + 1]) ++kcur;
         while (kcur > 0 && t < Xs[kcur]) --kcur;
         const float l = Xs[kcur], r = Xs[kcur + 1];
         if (!lat_mask(l, r, rend, t)) return p.c0 * (0.0f + (t - 0.0f) * 0.0f);  // no segment: sums of zeros
-        if (kload != kcur) {
+        if (l != lc || r != rc) {
             yk = Yb[(size_t)kcur * n + i];
             yk1 = Yb[(size_t)(kcur + 1) * n + i];
-            kload = kcur;
+            lc = l;
+            rc = r;
         }
         const float dd = (r - t) - (l - t);
         const float x0 = 0.0f + l, y0 = 0.0f + yk, dydx = 0.0f + (yk1 - yk) / dd;
         return p.c0 * (y0 + (t - x0) * dydx);
+    };
+    auto speed = [&](float t) -> float {
+        if (!act) return 0.0f;
+        if (mono && lc <= t && t < rc) {
+            const float dd = (rc - t) - (lc - t);
+            const float x0 = 0.0f + lc, y0 = 0.0f + yk, dydx = 0.0f + (yk1 - yk) / dd;
+            return p.c0 * (y0 + (t - x0) * dydx);
+        }
+        return speed_slow(t);
     };
     // The two warps that hold elements 0 and n-1 run a branch-free three-term form of the derivative rows (a per-thread
     // select keeps the two-term value for their interior lanes), so no warp diverges: ncu/timing showed the barriers
@@ -347,7 +359,7 @@ LAT_GLOBAL void k_latent_integrate_r1(LatentP p) {
     auto rhs = [&](const float *S, float a, float fs, const float own[4], float k[4]) {
         const float *Ut = S, *Vt = S + n, *Ui = S + 2 * n, *Vi = S + 3 * n;
         if (!edge_warp && inner) {  // every lane of the warp is interior
-            const float fm = shm * fs, fq = shpp * fs;
+            const float fm = s0 * fs, fq = s1 * fs;  // interior lanes: s0 = shape[i-1], s1 = shape[i+1]
             const float gVt = (p.gc[0] * Vt[i - 1]) + (p.gc[1] * Vt[i + 1]);
             const float gUt = (p.gc[0] * (Ut[i - 1] + fm)) + (p.gc[1] * (Ut[i + 1] + fq));
             const float gVi = (p.gc[0] * Vi[i - 1]) + (p.gc[1] * Vi[i + 1]);
@@ -377,6 +389,8 @@ LAT_GLOBAL void k_latent_integrate_r1(LatentP p) {
 
     const float sixth = 1.0f / 6.0f;
     float t0 = p.steps > 0 ? p.tspan[(size_t)b * T] : 0.0f;
+    float *zp = (p.z && act) ? p.z + ((size_t)p.batch + b) * 4 * n + i : nullptr;  // this thread's U_tot slot of frame 1
+    const size_t zstep = (size_t)p.batch * 4 * n;
     for (int s = 0; s <= p.steps; ++s) {
         // ---- phase 0 (owner-only data, the red slots and the OTHER factor buffer): energy of frame s, speeds of step s
         if (p.energy) {
@@ -449,10 +463,11 @@ LAT_GLOBAL void k_latent_integrate_r1(LatentP p) {
         for (int f = 0; f < 4; ++f) {
             const float du = (sixth * (acc[f] + k[f])) * p.dt;
             u[f] = u[f] + du;
-            if (act) {
-                B0[f * n + i] = u[f];
-                if (p.z) p.z[(((size_t)(s + 1) * p.batch + b) * 4 + f) * n + i] = u[f];
-            }
+            if (act) B0[f * n + i] = u[f];
+        }
+        if (zp) {
+            for (int f = 0; f < 4; ++f) zp[(size_t)f * n] = u[f];
+            zp += zstep;
         }
     }
     if (p.z_last && act)
