@@ -14,7 +14,7 @@
 module WavesB200
 
 using Waves
-using Waves: TwoDim, WaveEnv, Integrator, AcousticDynamics, DesignInterpolator, AbstractDesign, NoDesign,
+using Waves: OneDim, TwoDim, WaveEnv, Integrator, AcousticDynamics, DesignInterpolator, AbstractDesign, NoDesign,
              Cylinders, Cloak, AbstractScatterers, NoSource, build_tspan, get_dx, get_dy, stack
 using SparseArrays
 
@@ -201,5 +201,83 @@ function sync_reset!(b::B200Env)
     set_state!(b.h, Array{Float32}(b.env.wave[:, :, :, end]))
     set_source!(b.h, b.env.source)
 end
+
+# ---- 1-D latent dynamics: model.iter(z0, t, θ) of AcousticEnergyModel (src/model/acoustic_energy_model.jl:86-106) -------
+# struct waves_latent_config (include/waves_b200.h)
+struct LatentConfig
+    n::Int32; device::Int32
+    c0::Float32; dt::Float32; pml_width::Float32; pml_scale::Float32; pml0::Float32; dx::Float32
+    x::Ptr{Float32}; grad8::Ptr{Float32}
+end
+
+mutable struct LatentHandle
+    ptr::Ptr{Cvoid}
+    lib::String
+    n::Int
+end
+
+"""Handle for `Integrator(runge_kutta, dyn::AcousticDynamics{OneDim}, dt)` (src/dynamics.jl:18-22, :190-222)."""
+function create_latent(iter::Integrator; lib::String, device::Integer = 0)
+    dyn = iter.dynamics
+    x = Vector{Float32}(dyn.dim.x)
+    g8 = grad8(dyn.grad)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve x g8 begin
+        cfg = LatentConfig(length(x), device, dyn.c0, iter.dt, 0f0, 0f0, Array(dyn.pml)[1], get_dx(dyn.dim),
+                           pointer(x), pointer(g8))                       # pml0 = dyn.pml[[1]] (src/dynamics.jl:192)
+        check(lib, ccall((:waves_latent_create, lib), Cint, (Ref{LatentConfig}, Ref{Ptr{Cvoid}}), cfg, out))
+    end
+    return LatentHandle(out[], lib, length(x))
+end
+
+"""
+    latent_integrate(h, z0, t, C, F, PML; want_z = true)
+
+`iter(z0, t, [C, F, PML])` (src/dynamics.jl:37-49) and `compute_latent_energy(z, dx)` (src/model/acoustic_energy_model.jl:6-15)
+in one launch.  z0 (n, 4, batch), t (steps+1, batch), C::LinearInterpolation (X (nseq, batch), Y (n, nseq, batch)),
+F::Source (shape (n, batch)), PML (n, batch): host `Array`s or `CuArray`s (pass `pointer(a)`-compatible arrays).
+Returns `(z (n, 4, batch, steps+1) or nothing, energy (steps+1, 3, batch))`.
+"""
+function latent_integrate(h::LatentHandle, z0, t, C, F, PML; want_z::Bool = true)
+    n, batch, steps, nseq = h.n, size(z0, 3), size(t, 1) - 1, size(C.X, 1)
+    z = want_z ? similar(z0, n, 4, batch, steps + 1) : nothing
+    energy = similar(z0, steps + 1, 3, batch)
+    check(h.lib, ccall((:waves_latent_integrate, h.lib), Cint,
+                       (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
+                        Cfloat, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+                       h.ptr, batch, steps, nseq, z0, t, C.X, C.Y, F.shape, F.freq, PML,
+                       want_z ? z : C_NULL, energy, C_NULL))
+    return z, energy
+end
+
+"""
+    latent_adjoint(h, z, t, C, F, PML; w_energy = C_NULL, dL_dz = C_NULL, adj_mode = 0)
+
+`adjoint_sensitivity(iter, z, t, θ, ∂L_∂z)` (src/dynamics.jl:97-118): returns `(∂L/∂z0, ∂L/∂C.Y, ∂L/∂F.shape, ∂L/∂PML)`.
+`w_energy` (steps+1, 3, batch) is the cotangent of `compute_latent_energy(z, dx)`; `adj_mode = 1` is the reference loop as written.
+"""
+function latent_adjoint(h::LatentHandle, z, t, C, F, PML; w_energy = C_NULL, dL_dz = C_NULL, adj_mode::Integer = 0)
+    n, batch, steps, nseq = h.n, size(z, 3), size(t, 1) - 1, size(C.X, 1)
+    gz0, gY, gS, gP = similar(z, n, 4, batch), similar(C.Y), similar(F.shape), similar(PML)
+    check(h.lib, ccall((:waves_latent_adjoint, h.lib), Cint,
+                       (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
+                        Cfloat, Ptr{Float32}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
+                        Ptr{Float32}),
+                       h.ptr, batch, steps, nseq, z, t, C.X, C.Y, F.shape, F.freq, PML, adj_mode, w_energy, dL_dz,
+                       gz0, gY, gS, gP))
+    return gz0, gY, gS, gP
+end
+
+# What replaces `rrule(iter::Integrator, z0, t, θ)` (src/dynamics.jl:120-128) for the OneDim dynamics:
+#
+#   function Flux.ChainRulesCore.rrule(iter::Integrator, z0::AbstractArray{Float32, 3}, t::AbstractMatrix{Float32}, θ)
+#       C, F, PML = θ
+#       z, _ = WavesB200.latent_integrate(LATENT[], z0, t, C, F, PML)
+#       function Integrator_back(adj)
+#           gz0, gY, gS, gP = WavesB200.latent_adjoint(LATENT[], z, t, C, F, PML; dL_dz = adj, adj_mode = 1)
+#           return nothing, gz0, nothing, [(X = nothing, Y = gY), (shape = gS, freq = nothing), gP]
+#       end
+#       return z, Integrator_back
+#   end
 
 end # module
