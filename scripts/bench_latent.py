@@ -13,6 +13,19 @@ import waves_b200 as wb  # noqa: E402
 from latent_cases import make_case  # noqa: E402
 
 F32 = np.float32
+if "--cpu" in sys.argv:
+    # the oracle (NumPy restatement of the reference's array program, one thread) on the host cores: a bounded sample
+    from oracle import latent_oracle as lo
+    cs = make_case(n=1024, batch=32, steps=100, nseq=2, seed=1)
+    t = time.perf_counter()
+    z = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
+    lo.compute_latent_energy(z, 1.0)
+    dtm = time.perf_counter() - t
+    print(json.dumps({"cpu_oracle": {"batch": 32, "steps": 100, "n": 1024, "seconds": round(dtm, 3),
+                                     "us_per_step": round(1e6 * dtm / 100, 1),
+                                     "Melement_steps_per_s": round(32 * 1024 * 100 / dtm / 1e6, 1), "cores": 1,
+                                     "kind": "port (oracle/latent_oracle.py, NumPy float32)"}}))
+    sys.exit(0)
 out = []
 for batch, steps in ((32, 100), (148, 300), (1184, 300), (148, 2000)):
     cs = make_case(n=1024, batch=batch, steps=steps, nseq=steps // 100 + 1, seed=1)

@@ -81,26 +81,48 @@ def test_no_source_and_c_equal_one_property():
 
 
 @pytest.mark.parametrize("compat", [False, True])
-@pytest.mark.parametrize("n,steps", [(80, 8), (1024, 6)])
-def test_adjoint_matches_autograd(n, steps, compat):
-    cs = make_case(n=n, batch=2, steps=steps, nseq=3, seed=11 + n)
+@pytest.mark.parametrize("n,steps,knots", [(80, 8, "actions"), (65, 8, "partial"), (40, 8, "repeated"), (1024, 6, "actions")])
+def test_adjoint_matches_autograd(n, steps, knots, compat):
+    """Register fast path (default) and generic reverse kernel against float64 autograd / the literal reference loop, and
+    against each other."""
+    cs = make_case(n=n, batch=2, steps=steps, nseq=4 if knots == "repeated" else 3, seed=11 + n, knots=knots)
     rng = np.random.default_rng(3)
     it = _integrator(cs)
     z = it(cs["z0"], cs["tspan"], _theta(cs))
     w_energy = rng.standard_normal((2, 3, steps + 1)).astype(F32)
     dL_dz = (1e-2 * rng.standard_normal(z.shape)).astype(F32)
-    g = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=w_energy, dL_dz=dL_dz, mode=wb.ADJ_COMPAT if compat else wb.ADJ_EXACT)
+    mode = wb.ADJ_COMPAT if compat else wb.ADJ_EXACT
+    g = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=w_energy, dL_dz=dL_dz, mode=mode)
+    it.set_generic(True)
+    gg = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=w_energy, dL_dz=dL_dz, mode=mode)
     want = lao.adjoint_truth(cs, w_energy, dL_dz, compat=compat, z_stored=z)
     for name in ("z0", "Y", "shape", "pml"):
-        err = np.linalg.norm(g[name] - want[name]) / np.linalg.norm(want[name])
-        assert err < 1e-4, (name, err)
+        for got in (g, gg):
+            err = np.linalg.norm(got[name] - want[name]) / np.linalg.norm(want[name])
+            assert err < 1e-4, (name, err)
+        assert np.linalg.norm(g[name] - gg[name]) / np.linalg.norm(gg[name]) < 2e-5, name
+
+
+def test_adjoint_many_steps_energy_cotangent():
+    """300 steps over three action segments (factor-table chunks in reverse order, dL/dY accumulators flushed at every
+    segment change), energy cotangent only: fast path == generic kernel."""
+    cs = make_case(n=1024, batch=3, steps=300, nseq=4, seed=9)
+    it = _integrator(cs)
+    z = it(cs["z0"], cs["tspan"], _theta(cs))
+    wE = np.random.default_rng(1).standard_normal((3, 3, 301)).astype(F32)
+    g = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=wE)
+    it.set_generic(True)
+    gg = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=wE)
+    for name in ("z0", "Y", "shape", "pml"):
+        assert np.linalg.norm(gg[name]) > 0
+        assert np.linalg.norm(g[name] - gg[name]) / np.linalg.norm(gg[name]) < 5e-5, name
 
 
 def test_errors_are_reported_not_thrown():
     cs = make_case(n=1500, batch=1, steps=4, nseq=3)
     it = _integrator(cs)
     z = it(cs["z0"], cs["tspan"], _theta(cs))
-    with pytest.raises(wb.WavesError, match="shared memory"):
+    with pytest.raises(wb.WavesError, match="shared memory"):      # n = 1500: generic reverse kernel, 39 n floats do not fit
         it.adjoint(z, cs["tspan"], _theta(cs), w_energy=np.ones((1, 3, 5), F32))
     with pytest.raises(wb.WavesError, match="shared memory"):
         wb.LatentIntegrator(wb.LatentDynamics(wb.OneDim(100.0, 4096), 1531.0, 10.0, 10000.0), 1e-5)

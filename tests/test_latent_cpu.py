@@ -162,25 +162,79 @@ def test_emulated_forward_kernel_energy_only(emu, kernel):
 
 
 @pytest.mark.parametrize("compat", [0, 1])
-@pytest.mark.parametrize("n,nt", [(48, 64), (80, 32)])
-def test_emulated_adjoint_kernel_matches_autograd(emu, compat, n, nt):
-    """k_latent_adjoint against torch float64 reverse-mode over the unrolled oracle trajectory (exact mode) and a literal
-    transcription of the reference loop (compat mode, src/dynamics.jl:101-115): z0, C.Y, F.shape and PML gradients."""
-    cs = make_case(n=n, batch=2, steps=8, nseq=3, seed=11 + n)
+@pytest.mark.parametrize("kernel,n,nt,knots", [("generic", 48, 64, "actions"), ("generic", 80, 32, "actions"),
+                                               ("r1", 48, 64, "actions"), ("r1", 65, 96, "actions"), ("r1", 130, 160, "actions"),
+                                               ("r1", 70, 96, "partial"), ("r1", 40, 64, "repeated"),
+                                               ("generic", 40, 64, "repeated")])
+def test_emulated_adjoint_kernel_matches_autograd(emu, compat, kernel, n, nt, knots):
+    """k_latent_adjoint / k_latent_adjoint_r1 against torch float64 reverse-mode over the unrolled oracle trajectory (exact
+    mode) and a literal transcription of the reference loop (compat mode, src/dynamics.jl:101-115): z0, C.Y, F.shape and
+    PML gradients; the register kernel also against the generic one."""
+    steps = 8
+    cs = make_case(n=n, batch=2, steps=steps, nseq=4 if knots == "repeated" else 3, seed=11 + n, knots=knots)
     rng = np.random.default_rng(3)
     T = cs["steps"] + 1
     z = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
     w_energy = rng.standard_normal((2, 3, T)).astype(F32)
     dL_dz = (1e-2 * rng.standard_normal(z.shape)).astype(F32)
-    g_z0 = np.full((2, 4, n), np.nan, F32)
-    g_Y = np.zeros((2, cs["nseq"], n), F32)
-    g_shape = np.full((2, n), np.nan, F32)
-    g_pml = np.full((2, n), np.nan, F32)
-    p, keep = _params(cs, zt=z, w_energy=w_energy, dL_dz=dL_dz, g_z0=g_z0, g_Y=g_Y, g_shape=g_shape, g_pml=g_pml)
-    p.compat = compat
-    emu.emu_latent_adjoint(C.byref(p), nt)
+
+    def run(fn):
+        g = dict(z0=np.full((2, 4, n), np.nan, F32), Y=np.zeros((2, cs["nseq"], n), F32), shape=np.full((2, n), np.nan, F32),
+                 pml=np.full((2, n), np.nan, F32))
+        p, keep = _params(cs, zt=z, w_energy=w_energy, dL_dz=dL_dz, g_z0=g["z0"], g_Y=g["Y"], g_shape=g["shape"],
+                          g_pml=g["pml"])
+        p.compat = compat
+        fn(C.byref(p), nt)
+        return g
+
+    got = run(emu.emu_latent_adjoint if kernel == "generic" else emu.emu_latent_adjoint_r1)
     want = lao.adjoint_truth(cs, w_energy, dL_dz, compat=bool(compat))
-    for name, got in (("z0", g_z0), ("Y", g_Y), ("shape", g_shape), ("pml", g_pml)):
-        ref = want[name]
-        err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    for name in ("z0", "Y", "shape", "pml"):
+        err = np.linalg.norm(got[name] - want[name]) / np.linalg.norm(want[name])
         assert err < 1e-4, (name, err)
+    if kernel == "r1":
+        gen = run(emu.emu_latent_adjoint)
+        for name in ("z0", "Y", "shape", "pml"):
+            err = np.linalg.norm(got[name] - gen[name]) / np.linalg.norm(gen[name])
+            assert err < 2e-5, (name, err)
+
+
+@pytest.mark.parametrize("compat", [0, 1])
+def test_emulated_adjoint_r1_many_steps_and_segments(emu, compat):
+    """More steps than one table of source factors holds (chunk switches in reverse order), several segments of C (the
+    register accumulators of dL/dY are flushed at every segment change), energy cotangent only."""
+    n, steps = 33, 520
+    cs = make_case(n=n, batch=1, steps=steps, nseq=5, seed=4)
+    rng = np.random.default_rng(5)
+    z = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
+    w_energy = rng.standard_normal((1, 3, steps + 1)).astype(F32)
+
+    def run(fn):
+        g = dict(z0=np.full((1, 4, n), np.nan, F32), Y=np.zeros((1, 5, n), F32), shape=np.full((1, n), np.nan, F32),
+                 pml=np.full((1, n), np.nan, F32))
+        p, keep = _params(cs, zt=z, w_energy=w_energy, g_z0=g["z0"], g_Y=g["Y"], g_shape=g["shape"], g_pml=g["pml"])
+        p.compat = compat
+        fn(C.byref(p), 64)
+        return g
+
+    got, gen = run(emu.emu_latent_adjoint_r1), run(emu.emu_latent_adjoint)
+    for name in ("z0", "Y", "shape", "pml"):
+        err = np.linalg.norm(got[name] - gen[name]) / np.linalg.norm(gen[name])
+        assert err < 5e-5, (name, err)
+        assert np.linalg.norm(gen[name]) > 0
+
+
+def test_kernels_are_race_free_under_thread_sanitizer():
+    """The four latent kernels under the host emulation, built with -fsanitize=thread: ThreadSanitizer orders accesses by
+    the barriers (vector clocks, independent of timing), so a missing __syncthreads() between a shared-memory write and a
+    neighbour's read is reported even if the interleaving that breaks it never happens in this run."""
+    src = os.path.join(ROOT, "tests", "emu", "latent_tsan_main.cpp")
+    exe = os.path.join(ROOT, "tests", "emu", "latent_tsan")
+    probe = subprocess.run(["g++", "-fsanitize=thread", "-x", "c++", "-", "-o", os.devnull], input=b"int main(){return 0;}")
+    if probe.returncode != 0:
+        pytest.skip("ThreadSanitizer runtime not available")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=thread", "-ffp-contract=off", "-o", exe, src])
+    for args in (["70", "96", "6", "1"], ["65", "96", "5", "0"], ["200", "64", "4", "1"], ["130", "160", "5", "0"],
+                 ["33", "64", "300", "1"]):
+        r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr + r.stdout, (args, (r.stderr + r.stdout)[-2000:])

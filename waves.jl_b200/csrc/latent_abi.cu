@@ -255,7 +255,8 @@ extern "C" int waves_latent_adjoint(waves_latent *h, int batch, int steps, int n
     if (!z || !tspan || !X || !Y || !pml || !dL_dz0) LFAIL("waves_latent_adjoint: z, tspan, X, Y, pml and dL_dz0 are required");
     if (!w_energy && !dL_dz) LFAIL("waves_latent_adjoint: need a cotangent (w_energy and/or dL_dz)");
     if (adj_mode != WAVES_ADJ_EXACT && adj_mode != WAVES_ADJ_COMPAT) LFAIL("waves_latent_adjoint: unknown adjoint mode %d", adj_mode);
-    if (LAT_ADJ_SMEM(h->n) > (size_t)h->max_smem)
+    const bool fast = !h->force_generic && h->n <= 1024 && nseq <= LAT_FAST_NSEQ;  // register fast path, as in the forward pass
+    if (!fast && LAT_ADJ_SMEM(h->n) > (size_t)h->max_smem)
         LFAIL("waves_latent_adjoint: n = %d needs %zu bytes of shared memory per sample (limit %d)", h->n,
               (size_t)LAT_ADJ_SMEM(h->n), h->max_smem);
     const size_t n = h->n, st = 4 * n * (size_t)batch, T = (size_t)steps + 1;
@@ -271,9 +272,15 @@ extern "C" int waves_latent_adjoint(waves_latent *h, int batch, int steps, int n
         dev_out(h, 12, dL_dshape, n * batch, &p.g_shape) || dev_out(h, 13, dL_dpml, n * batch, &p.g_pml))
         return 1;
     if (p.g_Y) LCU(cudaMemsetAsync(p.g_Y, 0, sizeof(float) * n * nseq * batch, h->stream));
-    LCU(cudaFuncSetAttribute(k_latent_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_ADJ_SMEM(n)));
+    if (fast)
+        LCU(cudaFuncSetAttribute(k_latent_adjoint_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_ADJ1_SMEM(n)));
+    else
+        LCU(cudaFuncSetAttribute(k_latent_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_ADJ_SMEM(n)));
     LCU(cudaEventRecord(h->ev0, h->stream));
-    k_latent_adjoint<<<batch, threads_for(h->n), LAT_ADJ_SMEM(n), h->stream>>>(p);
+    if (fast)
+        k_latent_adjoint_r1<<<batch, threads_for(h->n), LAT_ADJ1_SMEM(n), h->stream>>>(p);
+    else
+        k_latent_adjoint<<<batch, threads_for(h->n), LAT_ADJ_SMEM(n), h->stream>>>(p);
     h->launches++;
     LCU(cudaGetLastError());
     LCU(cudaEventRecord(h->ev1, h->stream));

@@ -641,3 +641,308 @@ LAT_GLOBAL void k_latent_adjoint(LatentP p) {
         if (p.g_pml) p.g_pml[(size_t)b * n + e] = p.pml_scale * gsig[e];  // σ = pml_scale .* PML
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Register fast path of the reverse kernel: n <= 1024, one element per thread (the layout of k_latent_integrate_r1).
+// ncu on the generic reverse kernel (profiles/r1_latent_ncu_summary.json): issue-bound, ~3060 warp instructions per warp
+// per step.  Here λ, the step sum, the stage cotangent and the parameter-gradient accumulators are registers; shared memory
+// holds what neighbours read: the stored state (double-buffered by step so no barrier is needed at the end of a step), the
+// three recomputed stage states, and two ping-pong buffers with the PRODUCTS the transposed rows consume
+// (c0·C ⊙ bc ⊙ w_U, c0·C ⊙ w_V, bc ⊙ w_Uinc, w_Vinc) so no speed array has to be shared; ∂L/∂C.Y of the current segment
+// accumulates in two registers and is flushed to HBM only when the stage times move to another segment.
+// Eight barriers per step.  Same mathematics as k_latent_adjoint (float32 accumulation order differs).
+#define LAT_ADJ1_FLOATS(n) (29 * (size_t)(n) + LAT_FAST_NSEQ + 2 * 3 * LAT_CH + 8)
+#define LAT_ADJ1_SMEM(n) (sizeof(float) * LAT_ADJ1_FLOATS(n))
+
+LAT_GLOBAL void k_latent_adjoint_r1(LatentP p) {
+    LAT_SMEM
+    const int n = p.n, tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, i = tid;
+    const int T = p.steps + 1, N = p.steps;
+    float *ZA = (float *)lat_smem, *ZB = ZA + 4 * n;     // stored state z_i, double-buffered by iteration parity
+    float *Y2 = ZB + 4 * n, *Y3 = Y2 + 4 * n, *Y4 = Y3 + 4 * n;
+    float *PA = Y4 + 4 * n, *PB = PA + 4 * n;            // products read by the transposed rows
+    float *shs = PB + 4 * n, *Xs = shs + n, *fcs = Xs + LAT_FAST_NSEQ;
+    const bool act = i < n, inner = act && i > 0 && i < n - 1;
+    const float *Yb = p.Y + (size_t)b * p.nseq * n;
+    float *gY = p.g_Y ? p.g_Y + (size_t)b * p.nseq * n : nullptr;
+
+    float sg = 0.0f;
+    if (act) {
+        shs[i] = p.shape ? p.shape[(size_t)b * n + i] : 0.0f;
+        sg = p.pml_scale * p.pml[(size_t)b * n + i];
+    }
+    for (int k = tid; k < p.nseq; k += nt) Xs[k] = p.X[(size_t)b * p.nseq + k];
+    LAT_SYNC();
+    bool mono = true;
+    for (int k = 0; k + 1 < p.nseq; ++k) mono = mono && (Xs[k] < Xs[k + 1]);
+    const float rend = Xs[p.nseq - 1];
+
+    // per-lane form of the derivative rows, as in k_latent_integrate_r1
+    const int wlo = i & ~31;
+    const bool edge_warp = wlo == 0 || (wlo <= n - 1 && n - 1 < wlo + 32);
+    const bool first = act && i == 0, last = act && i == n - 1, three = first || last;
+    const int o0 = first ? 0 : (last ? -2 : -1), o1 = first ? 1 : (last ? -1 : 1), o2 = first ? 2 : 0;
+    const float q0 = first ? p.gf[0] : (last ? p.gl[0] : p.gc[0]), q1 = first ? p.gf[1] : (last ? p.gl[1] : p.gc[1]);
+    const float q2 = first ? p.gf[2] : (last ? p.gl[2] : 0.0f);
+    const float bcv = three ? 0.0f : 1.0f;
+    // the TRANSPOSED rows differ from the central form at elements 0, 1, 2 and n-3, n-2, n-1 (the one-sided rows reach them)
+    const bool edge_t = wlo == 0 || wlo + 31 >= n - 3;
+    const float s0 = act ? shs[i + o0] : 0.0f, s1 = act ? shs[i + o1] : 0.0f, s2 = act ? shs[i + o2] : 0.0f;
+    auto row = [&](float v0, float v1, float v2) {
+        const float two = (q0 * v0) + (q1 * v1);
+        return three ? two + (q2 * v2) : two;
+    };
+    // forward right-hand side at this thread's element (reference order, as in the forward kernel)
+    auto rhs = [&](const float *S, float a, float fs, const float own[4], float k[4]) {
+        if (!act) return;
+        const float *Ut = S, *Vt = S + n, *Ui = S + 2 * n, *Vi = S + 3 * n;
+        const float f0 = s0 * fs, f1 = s1 * fs, f2 = s2 * fs;
+        float gVt, gUt, gVi, gUi;
+        if (!edge_warp) {
+            gVt = (p.gc[0] * Vt[i - 1]) + (p.gc[1] * Vt[i + 1]);
+            gUt = (p.gc[0] * (Ut[i - 1] + f0)) + (p.gc[1] * (Ut[i + 1] + f1));
+            gVi = (p.gc[0] * Vi[i - 1]) + (p.gc[1] * Vi[i + 1]);
+            gUi = (p.gc[0] * (Ui[i - 1] + f0)) + (p.gc[1] * (Ui[i + 1] + f1));
+        } else {
+            gVt = row(Vt[i + o0], Vt[i + o1], Vt[i + o2]);
+            gUt = row(Ut[i + o0] + f0, Ut[i + o1] + f1, Ut[i + o2] + f2);
+            gVi = row(Vi[i + o0], Vi[i + o1], Vi[i + o2]);
+            gUi = row(Ui[i + o0] + f0, Ui[i + o1] + f1, Ui[i + o2] + f2);
+        }
+        k[0] = ((a * gVt) - (sg * own[0])) * bcv;
+        k[1] = (a * gUt) - (sg * own[1]);
+        k[2] = ((p.c0 * gVi) - (sg * own[2])) * bcv;
+        k[3] = (gUi * p.c0) - (sg * own[3]);
+    };
+
+    // C(t): value c0*C(t)[i], segment index (-1: no segment) and interpolation weight of its right knot
+    int kcur = 0, kreg = -1;  // search cursor; segment whose knots (lc, rc) and values (yk, yk1) are in registers
+    float yk = 0.0f, yk1 = 0.0f, lc = 1.0f, rc = 0.0f;
+    auto query = [&](float t, float &c, int &kseg, float &w) {
+        kseg = -1;
+        w = 0.0f;
+        c = 0.0f;
+        if (!act) return;
+        if (!mono) {
+            c = lat_speed_elem(p, Xs, Yb, t, i);
+            return;
+        }
+        if (!(lc <= t && t < rc)) {
+            while (kcur + 2 < p.nseq && t >= Xs[kcur + 1]) ++kcur;
+            while (kcur > 0 && t < Xs[kcur]) --kcur;
+            const float l = Xs[kcur], r = Xs[kcur + 1];
+            if (!lat_mask(l, r, rend, t)) {
+                c = p.c0 * (0.0f + (t - 0.0f) * 0.0f);
+                return;
+            }
+            if (kreg != kcur) {
+                yk = Yb[(size_t)kcur * n + i];
+                yk1 = Yb[(size_t)(kcur + 1) * n + i];
+                lc = l;
+                rc = r;
+                kreg = kcur;
+            }
+        }
+        const float dd = (rc - t) - (lc - t);
+        const float x0 = 0.0f + lc, y0 = 0.0f + yk, dydx = 0.0f + (yk1 - yk) / dd;
+        c = p.c0 * (y0 + (t - x0) * dydx);
+        kseg = kreg;
+        w = (t - x0) / dd;
+    };
+
+    // ∂L/∂C.Y of segment kacc: coefficients of Y[kacc] and Y[kacc+1] at this element
+    int kacc = -1;
+    float gYa = 0.0f, gYb = 0.0f;
+    auto flush_gy = [&]() {
+        if (gY && act && kacc >= 0) {
+            gY[(size_t)kacc * n + i] += gYa;  // owner-only read-modify-write
+            gY[(size_t)(kacc + 1) * n + i] += gYb;
+        }
+        gYa = 0.0f;
+        gYb = 0.0f;
+    };
+    auto add_gy = [&](float cbar, float t, int kseg, float w) {
+        if (!gY || !act) return;
+        if (!mono) {  // knots that are not increasing: every true mask contributes (as in k_latent_adjoint)
+            float x0 = 0.0f;
+            for (int k = 0; k + 1 < p.nseq; ++k)
+                if (lat_mask(Xs[k], Xs[k + 1], rend, t)) x0 = x0 + Xs[k];
+            for (int k = 0; k + 1 < p.nseq; ++k) {
+                const float l = Xs[k], r = Xs[k + 1];
+                if (lat_mask(l, r, rend, t)) {
+                    const float wk = (t - x0) / ((r - t) - (l - t));
+                    gY[(size_t)k * n + i] += cbar * (1.0f - wk);
+                    gY[(size_t)(k + 1) * n + i] += cbar * wk;
+                }
+            }
+            return;
+        }
+        if (kseg < 0) return;
+        if (kseg != kacc) {
+            flush_gy();
+            kacc = kseg;
+        }
+        gYa += cbar * (1.0f - w);
+        gYb += cbar * w;
+    };
+
+    float lam[4] = {0.0f, 0.0f, 0.0f, 0.0f}, zr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float gshp = 0.0f, gsig = 0.0f;
+    // λ += a_idx at this element; zv = z_idx at this element
+    auto add_cotangent = [&](int idx, const float zv[4]) {
+        if (!act) return;
+        if (p.w_energy) {
+            const float w0 = p.w_energy[((size_t)b * 3 + 0) * T + idx], w1 = p.w_energy[((size_t)b * 3 + 1) * T + idx];
+            const float w2 = p.w_energy[((size_t)b * 3 + 2) * T + idx];
+            const float ut = zv[0], ui = zv[2], d = ut - ui;
+            lam[0] += 2.0f * p.dx * (w0 * ut + w2 * d);
+            lam[2] += 2.0f * p.dx * (w1 * ui - w2 * d);
+        }
+        if (p.dL_dz)
+            for (int f = 0; f < 4; ++f) lam[f] += p.dL_dz[(((size_t)idx * p.batch + b) * 4 + f) * n + i];
+    };
+    auto load_state = [&](int idx) {
+        if (!act) return;
+        const float *zi = p.zt + ((size_t)idx * p.batch + b) * 4 * n;
+        for (int f = 0; f < 4; ++f) zr[f] = zi[(size_t)f * n + i];
+    };
+    // vjp of one right-hand side.  Pin: the products written by the previous stage; S: the stage state; kb: own cotangent
+    auto vjp = [&](const float *S, const float *Pin, float a, float fs, float t, int kseg, float w, const float kb[4],
+                   float yb[4]) {
+        if (!act) return;
+        const float *Q0 = Pin, *Q1 = Pin + n, *Q2 = Pin + 2 * n, *Q3 = Pin + 3 * n;
+        float tp, tq, tr, ts;
+        if (!edge_t) {  // 3 <= i <= n-4 for every lane of this warp: rows i-1 and i+1 are central, no one-sided row reaches i
+            tp = (p.gc[0] * Q1[i + 1]) + (p.gc[1] * Q1[i - 1]);
+            tq = (p.gc[0] * Q0[i + 1]) + (p.gc[1] * Q0[i - 1]);
+            tr = (p.gc[0] * Q3[i + 1]) + (p.gc[1] * Q3[i - 1]);
+            ts = (p.gc[0] * Q2[i + 1]) + (p.gc[1] * Q2[i - 1]);
+        } else {
+            tp = lat_grad_t(p, i, [&](int j) { return Q1[j]; });
+            tq = lat_grad_t(p, i, [&](int j) { return Q0[j]; });
+            tr = lat_grad_t(p, i, [&](int j) { return Q3[j]; });
+            ts = lat_grad_t(p, i, [&](int j) { return Q2[j]; });
+        }
+        yb[0] = tp - sg * bcv * kb[0];
+        yb[1] = tq - sg * kb[1];
+        yb[2] = p.c0 * tr - sg * bcv * kb[2];
+        yb[3] = p.c0 * ts - sg * kb[3];
+        const float *Ut = S, *Vt = S + n, *Ui = S + 2 * n, *Vi = S + 3 * n;
+        if (p.g_shape) gshp += (tp + p.c0 * tr) * fs;
+        if (p.g_pml) gsig -= bcv * kb[0] * Ut[i] + kb[1] * Vt[i] + bcv * kb[2] * Ui[i] + kb[3] * Vi[i];
+        if (gY) {
+            const float f0 = s0 * fs, f1 = s1 * fs, f2 = s2 * fs;
+            float gVt, gUt;
+            if (!edge_warp) {
+                gVt = (p.gc[0] * Vt[i - 1]) + (p.gc[1] * Vt[i + 1]);
+                gUt = (p.gc[0] * (Ut[i - 1] + f0)) + (p.gc[1] * (Ut[i + 1] + f1));
+            } else {
+                gVt = row(Vt[i + o0], Vt[i + o1], Vt[i + o2]);
+                gUt = row(Ut[i + o0] + f0, Ut[i + o1] + f1, Ut[i + o2] + f2);
+            }
+            add_gy(p.c0 * (bcv * kb[0] * gVt + kb[1] * gUt), t, kseg, w);
+        }
+        (void)a;
+    };
+    // the products the NEXT transposed rows read, for the stage whose speed is a
+    auto put_products = [&](float *P, float a, const float kb[4]) {
+        if (!act) return;
+        P[i] = a * bcv * kb[0];
+        P[n + i] = a * kb[1];
+        P[2 * n + i] = bcv * kb[2];
+        P[3 * n + i] = kb[3];
+    };
+
+    if (!p.compat) {  // λ_N = a_N
+        load_state(N);
+        add_cotangent(N, zr);
+    }
+    const float dt = p.dt, hdt = p.hdt, sixth = 1.0f / 6.0f;
+    const int istart = p.compat ? N : N - 1;
+    int it = 0;
+    for (int s = istart; s >= 0; --s, ++it) {
+        float *Z = (it & 1) ? ZB : ZA;
+        // ---- phase 0: state, cotangent (compat), the three speeds, the table of source factors
+        load_state(s);
+        if (p.compat) add_cotangent(s, zr);  // acc += a_i before the step vjp (src/dynamics.jl:110)
+        if (s == istart || (s % LAT_CH) == LAT_CH - 1) {
+            const int c0s = (s / LAT_CH) * LAT_CH;
+            float *fw = fcs + ((s / LAT_CH) & 1) * 3 * LAT_CH;
+            for (int q = tid; q < 3 * LAT_CH; q += nt) {
+                const int st = c0s + q / 3, w = q - 3 * (q / 3);
+                if (st <= s) {
+                    const float ts = p.tspan[(size_t)b * T + st];
+                    fw[q] = p.shape ? lat_sin_factor(w == 0 ? ts : (w == 1 ? ts + hdt : ts + dt), p.freq) : 0.0f;
+                }
+            }
+        }
+        const float t0 = p.tspan[(size_t)b * T + s], t1 = t0 + hdt, t2 = t0 + dt;
+        float cA, cB, cC, wA, wB, wC;
+        int kA, kB, kC;
+        query(t2, cC, kC, wC);  // time-decreasing order, like the sweep
+        query(t1, cB, kB, wB);
+        query(t0, cA, kA, wA);
+        if (act)
+            for (int f = 0; f < 4; ++f) Z[f * n + i] = zr[f];
+        LAT_SYNC();
+        const float *fc = fcs + ((s / LAT_CH) & 1) * 3 * LAT_CH + 3 * (s % LAT_CH);
+        const float f0 = fc[0], f1 = fc[1], f2 = fc[2];
+
+        float k[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ys[4] = {0.0f, 0.0f, 0.0f, 0.0f}, kb[4], yb[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float zsum[4];
+        // ---- forward stage states y2 = z + dt/2 k1(z), y3 = z + dt/2 k2(y2), y4 = z + dt k3(y3)
+        rhs(Z, cA, f0, zr, k);
+        for (int f = 0; f < 4; ++f) {
+            ys[f] = zr[f] + (hdt * k[f]);
+            if (act) Y2[f * n + i] = ys[f];
+        }
+        LAT_SYNC();
+        rhs(Y2, cB, f1, ys, k);
+        for (int f = 0; f < 4; ++f) {
+            ys[f] = zr[f] + (hdt * k[f]);
+            if (act) Y3[f * n + i] = ys[f];
+        }
+        LAT_SYNC();
+        rhs(Y3, cB, f1, ys, k);
+        for (int f = 0; f < 4; ++f) {
+            ys[f] = zr[f] + (dt * k[f]);
+            if (act) Y4[f * n + i] = ys[f];
+            kb[f] = (sixth * dt) * lam[f];  // cotangent of k4
+        }
+        put_products(PA, cC, kb);
+        LAT_SYNC();
+        // ---- reverse stages: ȳ4 = J4ᵀ k̄4; k̄3 = dt/3 λ + dt ȳ4; ȳ3 = J3ᵀ k̄3; k̄2 = dt/3 λ + dt/2 ȳ3; ȳ2 = J2ᵀ k̄2;
+        //      k̄1 = dt/6 λ + dt/2 ȳ2; ȳ1 = J1ᵀ k̄1;  δz = ȳ1 + ȳ2 + ȳ3 + ȳ4
+        vjp(Y4, PA, cC, f2, t2, kC, wC, kb, yb);
+        for (int f = 0; f < 4; ++f) {
+            zsum[f] = yb[f];
+            kb[f] = (2.0f * sixth * dt) * lam[f] + dt * yb[f];
+        }
+        put_products(PB, cB, kb);
+        LAT_SYNC();
+        vjp(Y3, PB, cB, f1, t1, kB, wB, kb, yb);
+        for (int f = 0; f < 4; ++f) {
+            zsum[f] += yb[f];
+            kb[f] = (2.0f * sixth * dt) * lam[f] + hdt * yb[f];
+        }
+        put_products(PA, cB, kb);
+        LAT_SYNC();
+        vjp(Y2, PA, cB, f1, t1, kB, wB, kb, yb);
+        for (int f = 0; f < 4; ++f) {
+            zsum[f] += yb[f];
+            kb[f] = (sixth * dt) * lam[f] + hdt * yb[f];
+        }
+        put_products(PB, cA, kb);
+        LAT_SYNC();
+        vjp(Z, PB, cA, f0, t0, kA, wA, kb, yb);
+        for (int f = 0; f < 4; ++f) lam[f] += zsum[f] + yb[f];  // λ <- λ + δz
+        if (!p.compat) add_cotangent(s, zr);                     // λ_i = a_i + (I + J_iᵀ) λ_{i+1}
+        // no barrier: the next iteration writes the OTHER Z buffer, and every other buffer is rewritten only after barriers
+    }
+    flush_gy();
+    if (act) {
+        for (int f = 0; f < 4; ++f) p.g_z0[((size_t)b * 4 + f) * n + i] = lam[f];
+        if (p.g_shape) p.g_shape[(size_t)b * n + i] = gshp;
+        if (p.g_pml) p.g_pml[(size_t)b * n + i] = p.pml_scale * gsig;
+    }
+}
