@@ -204,12 +204,16 @@ extern "C" int waves_create(const waves_config *cfg, waves_handle **out) {
     std::vector<float> sig(cfg->nx), g8(8);
     if (cfg->sigma)
         memcpy(sig.data(), cfg->sigma, sizeof(float) * cfg->nx);
-    else if (waves_build_pml_profile(cfg->x, cfg->nx, cfg->pml_width, cfg->pml_scale, sig.data()))
+    else if (waves_build_pml_profile(cfg->x, cfg->nx, cfg->pml_width, cfg->pml_scale, sig.data())) {
+        delete h;  // nothing but the struct exists yet
         return 1;
+    }
     if (cfg->grad8)
         memcpy(g8.data(), cfg->grad8, sizeof(float) * 8);
-    else if (waves_build_gradient8(cfg->x, cfg->nx, g8.data()))
+    else if (waves_build_gradient8(cfg->x, cfg->nx, g8.data())) {
+        delete h;
         return 1;
+    }
     memcpy(gp.g_first, g8.data(), 12);
     memcpy(gp.g_central, g8.data() + 3, 8);
     memcpy(gp.g_last, g8.data() + 5, 12);
