@@ -238,3 +238,31 @@ def test_kernels_are_race_free_under_thread_sanitizer():
                  ["33", "64", "300", "1"]):
         r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr + r.stdout, (args, (r.stderr + r.stdout)[-2000:])
+
+
+def test_latent_oracle_matches_reference_vectors():
+    """Pins oracle/latent_oracle.py to the Julia reference; skips while tests/golden/ref_latent_final_and_energy.f32 is absent
+    (tests/golden/make_reference_vectors.jl, part 3, has never been run: no Julia here)."""
+    f = os.path.join(ROOT, "tests", "golden", "ref_latent_final_and_energy.f32")
+    if not os.path.exists(f):
+        pytest.skip("no vectors from the Julia reference (run tests/golden/make_reference_vectors.jl in a Waves.jl checkout)")
+    n, B, steps = 256, 2, 40
+    dim = wo.OneDim.make(100.0, n)
+    dyn = lo.LatentDynamics.make(dim, wo.WATER, 10.0, 10000.0)
+    x = dim.x
+    tspan = np.stack([wo.build_tspan(F32(0.0), 1e-5, steps), wo.build_tspan(F32(1e-3), 1e-5, steps)])
+    X = np.ascontiguousarray(tspan[:, [0, 20, 40]])
+    Y = np.stack([np.stack([(F32(1.0) + F32(0.1) * F32(k) + F32(0.2) * np.sin(F32(0.05) * F32(b) * x)).astype(F32)
+                            for k in (1, 2, 3)]) for b in (1, 2)])
+    shape = np.stack([np.exp(-(x + F32(20)) ** 2 / F32(100)), np.exp(-(x - F32(10)) ** 2 / F32(150))]).astype(F32)
+    pml = np.stack([dyn.pml / dyn.pml.max()] * 2).astype(F32)
+    z0 = np.zeros((B, 4, n), F32)
+    z0[0, 0], z0[0, 2] = np.exp(-x ** 2 / F32(200)), np.exp(-(x - F32(5)) ** 2 / F32(300))
+    z0[1, 0] = np.exp(-(x + F32(30)) ** 2 / F32(250))
+    z0[1, 2] = z0[1, 0]
+    z = lo.integrate(dyn, z0, tspan, lo.LatentTheta(X=X, Y=Y, shape=shape, freq=F32(1000.0), pml=pml), F32(1e-5))
+    e = lo.compute_latent_energy(z, wo.get_dx(dim))
+    ref = np.fromfile(f, F32)
+    ref_z, ref_e = ref[: B * 4 * n].reshape(B, 4, n), ref[B * 4 * n:].reshape(B, 3, steps + 1)
+    rel = lambda a, b: np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64))  # noqa: E731
+    assert rel(z[-1], ref_z) < 1e-4 and rel(e, ref_e) < 1e-4

@@ -250,3 +250,42 @@ def test_imresize_restatement_properties():
     assert np.allclose(out[0], 3.5) and np.allclose(out[1], (2.0 * pos - 1.0)[None, :], rtol=1e-6)
     assert np.allclose(out[2], 0.5 * pos[:, None] + pos[None, :], rtol=1e-6)
     assert np.array_equal(wo.imresize_linear(w, (n, n)), w)
+
+
+# ---- vectors from the real reference (absent until tests/golden/make_reference_vectors.jl has been run) ------------------
+def test_oracle_matches_reference_vectors(golden_dir):
+    """Pins the 2-D oracle to outputs of gladisor/Waves.jl itself.  Skips while the vectors do not exist: the image has no
+    Julia, so the oracle is PARITY UNPINNED until make_reference_vectors.jl is run once elsewhere."""
+    f_en = os.path.join(golden_dir, "ref_config1_energy.f32")
+    f_rows = os.path.join(golden_dir, "ref_config1_final_rows.f32")
+    f_small = os.path.join(golden_dir, "ref_design96_final.f32")
+    if not all(os.path.exists(f) for f in (f_en, f_rows, f_small)):
+        pytest.skip("no vectors from the Julia reference (run tests/golden/make_reference_vectors.jl in a Waves.jl checkout)")
+    rel = lambda a, b: np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64))  # noqa: E731
+    # (1) config 1
+    dim = wo.TwoDim.make(15.0, 700)
+    dyn = wo.AcousticDynamics.make(dim, wo.WATER, 2.0, 20000.0)
+    shape = wo.build_normal(wo.build_grid(dim), np.array([[-10.0, 0.0]]), np.array([0.3]), np.array([1.0]))
+    ts = wo.build_tspan(0.0, 1e-5, 100)
+    dO = F32(wo.get_dx(dim) * wo.get_dy(dim))
+    st, en, _ = co.integrate(dyn, np.zeros((12, 700, 700), F32), ts, 1e-5, dO, shape=shape, freq=1000.0)
+    ref_en = np.fromfile(f_en, F32).reshape(101, 3)
+    assert rel(en[:, :2], ref_en[:, :2]) < 1e-4 and np.all(ref_en[:, 2] <= 1e-12 * ref_en[:, 0].max())
+    ref_rows = np.fromfile(f_rows, F32).reshape(12, 4, 700)          # (700, 4, 12) column-major
+    assert rel(st[:, [0, 23, 349, 698], :], ref_rows) < 1e-4
+    # (2) moving cylinders on 96^2
+    n = 96
+    dim = wo.TwoDim.make(3.0, n)
+    dyn = wo.AcousticDynamics.make(dim, wo.WATER, 0.6, 20000.0)
+    grid = wo.build_grid(dim)
+    pos = np.array([[0.5, 0.0], [0.9, 0.3], [-0.2, -1.1]], dtype=F32)
+    d0 = wo.Cylinders(pos, [0.4, 0.3, 0.5], [1032.0, 1032.0, 2120.0])
+    d1 = wo.Cylinders(pos, [0.6, 0.25, 0.35], [1032.0, 1032.0, 2120.0])
+    ts = wo.build_tspan(F32(3e-4), 1e-5, 40)
+    shape = wo.build_normal(grid, np.array([[-1.0, 0.2]]), np.array([0.15]), np.array([1.0]))
+    u0 = np.zeros((12, n, n), F32)
+    u0[0] = (F32(1e-3) * np.sin(dim.x)[None, :] * np.cos(dim.x)[:, None]).astype(F32)   # 1f-3 .* sin.(x) .* cos.(x') at [j, i]
+    u0[6] = u0[0]
+    st, _, _ = co.integrate(dyn, u0, ts, 1e-5, F32(wo.get_dx(dim) * wo.get_dy(dim)), d0, d1, ts[0], ts[-1], shape=shape,
+                            freq=1000.0)
+    assert rel(st, np.fromfile(f_small, F32).reshape(12, n, n)) < 1e-4
