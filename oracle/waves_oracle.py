@@ -26,7 +26,7 @@ right); set `dtype=np.float64` to get the error-budget variant.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from fractions import Fraction
 
 import numpy as np

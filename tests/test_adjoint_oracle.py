@@ -2,7 +2,6 @@
 autograd over the unrolled trajectory, and the reference-loop-as-written (src/dynamics.jl:97-118) against its
 literal torch transcription."""
 import numpy as np
-import pytest
 
 from oracle import adjoint_oracle as ao
 from oracle import waves_oracle as wo

@@ -25,7 +25,8 @@ from ._lib import check
 from .engine import ADJ_COMPAT, ADJ_EXACT, _ptr
 from .host import F32, _fp, julia_range
 
-__all__ = ["OneDim", "LinearInterpolation", "LatentSource", "LatentDynamics", "LatentIntegrator", "build_pml_1d"]
+__all__ = ["OneDim", "LinearInterpolation", "LatentSource", "LatentDynamics", "LatentIntegrator", "build_pml_1d", "ADJ_EXACT",
+           "ADJ_COMPAT"]
 
 
 @dataclass
@@ -151,5 +152,3 @@ class LatentIntegrator:
     def launch_count(self) -> int:
         return int(_lib.lib().waves_latent_launch_count(self._h))
 
-
-_ = ADJ_COMPAT  # re-exported constant (engine.ADJ_COMPAT) for callers of LatentIntegrator.adjoint
