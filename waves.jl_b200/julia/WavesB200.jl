@@ -230,41 +230,54 @@ function create_latent(iter::Integrator; lib::String, device::Integer = 0)
     return LatentHandle(out[], lib, length(x))
 end
 
+# Raw address of a host `Array` or of a `CuArray` (the library asks the CUDA runtime which kind it got); `nothing` -> NULL.
+# For a CuArray `pointer(a)` is a `CuPtr{Float32}`; its bits are the device address.
+rawptr(::Nothing) = Ptr{Float32}(C_NULL)
+rawptr(a::Array{Float32}) = pointer(a)
+rawptr(a::AbstractArray{Float32}) = reinterpret(Ptr{Float32}, pointer(a))
+
 """
     latent_integrate(h, z0, t, C, F, PML; want_z = true)
 
 `iter(z0, t, [C, F, PML])` (src/dynamics.jl:37-49) and `compute_latent_energy(z, dx)` (src/model/acoustic_energy_model.jl:6-15)
 in one launch.  z0 (n, 4, batch), t (steps+1, batch), C::LinearInterpolation (X (nseq, batch), Y (n, nseq, batch)),
-F::Source (shape (n, batch)), PML (n, batch): host `Array`s or `CuArray`s (pass `pointer(a)`-compatible arrays).
+F::Source (shape (n, batch)), PML (n, batch): all host `Array`s or all `CuArray`s (outputs are `similar` to `z0`).
 Returns `(z (n, 4, batch, steps+1) or nothing, energy (steps+1, 3, batch))`.
 """
 function latent_integrate(h::LatentHandle, z0, t, C, F, PML; want_z::Bool = true)
     n, batch, steps, nseq = h.n, size(z0, 3), size(t, 1) - 1, size(C.X, 1)
     z = want_z ? similar(z0, n, 4, batch, steps + 1) : nothing
     energy = similar(z0, steps + 1, 3, batch)
-    check(h.lib, ccall((:waves_latent_integrate, h.lib), Cint,
-                       (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
-                        Cfloat, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
-                       h.ptr, batch, steps, nseq, z0, t, C.X, C.Y, F.shape, F.freq, PML,
-                       want_z ? z : C_NULL, energy, C_NULL))
+    X, Y, shape = C.X, C.Y, F.shape
+    GC.@preserve z0 t X Y shape PML z energy begin
+        check(h.lib, ccall((:waves_latent_integrate, h.lib), Cint,
+                           (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
+                            Cfloat, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+                           h.ptr, batch, steps, nseq, rawptr(z0), rawptr(t), rawptr(X), rawptr(Y), rawptr(shape), F.freq,
+                           rawptr(PML), rawptr(z), rawptr(energy), C_NULL))
+    end
     return z, energy
 end
 
 """
-    latent_adjoint(h, z, t, C, F, PML; w_energy = C_NULL, dL_dz = C_NULL, adj_mode = 0)
+    latent_adjoint(h, z, t, C, F, PML; w_energy = nothing, dL_dz = nothing, adj_mode = 0)
 
 `adjoint_sensitivity(iter, z, t, θ, ∂L_∂z)` (src/dynamics.jl:97-118): returns `(∂L/∂z0, ∂L/∂C.Y, ∂L/∂F.shape, ∂L/∂PML)`.
 `w_energy` (steps+1, 3, batch) is the cotangent of `compute_latent_energy(z, dx)`; `adj_mode = 1` is the reference loop as written.
 """
-function latent_adjoint(h::LatentHandle, z, t, C, F, PML; w_energy = C_NULL, dL_dz = C_NULL, adj_mode::Integer = 0)
+function latent_adjoint(h::LatentHandle, z, t, C, F, PML; w_energy = nothing, dL_dz = nothing, adj_mode::Integer = 0)
     n, batch, steps, nseq = h.n, size(z, 3), size(t, 1) - 1, size(C.X, 1)
-    gz0, gY, gS, gP = similar(z, n, 4, batch), similar(C.Y), similar(F.shape), similar(PML)
-    check(h.lib, ccall((:waves_latent_adjoint, h.lib), Cint,
-                       (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
-                        Cfloat, Ptr{Float32}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
-                        Ptr{Float32}),
-                       h.ptr, batch, steps, nseq, z, t, C.X, C.Y, F.shape, F.freq, PML, adj_mode, w_energy, dL_dz,
-                       gz0, gY, gS, gP))
+    X, Y, shape = C.X, C.Y, F.shape
+    gz0, gY, gS, gP = similar(z, n, 4, batch), similar(Y), similar(shape), similar(PML)
+    GC.@preserve z t X Y shape PML w_energy dL_dz gz0 gY gS gP begin
+        check(h.lib, ccall((:waves_latent_adjoint, h.lib), Cint,
+                           (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
+                            Cfloat, Ptr{Float32}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
+                            Ptr{Float32}),
+                           h.ptr, batch, steps, nseq, rawptr(z), rawptr(t), rawptr(X), rawptr(Y), rawptr(shape), F.freq,
+                           rawptr(PML), adj_mode, rawptr(w_energy), rawptr(dL_dz), rawptr(gz0), rawptr(gY), rawptr(gS),
+                           rawptr(gP)))
+    end
     return gz0, gY, gS, gP
 end
 
