@@ -33,9 +33,11 @@ for batch, steps in ((32, 100), (148, 300), (1184, 300), (148, 2000)):
     it = wb.LatentIntegrator(wb.LatentDynamics(wb.OneDim(cs["dim"].x), 1531.0, 10.0, 10000.0), cs["dt"])
     theta = [wb.LinearInterpolation(th.X, th.Y), wb.LatentSource(th.shape, th.freq), th.pml]
     rec = {"batch": batch, "steps": steps, "n": 1024}
-    for name, kw in (("energy_only", dict(want_z=False, want_energy=True)), ("trajectory", dict(want_z=True, want_energy=True))):
+    for name, kw in (("energy_only", dict(want_z=False, want_energy=True)), ("trajectory", dict(want_z=True, want_energy=True)),
+                     ("energy_only_pair_variant", dict(want_z=False, want_energy=True))):
         if name == "trajectory" and batch * steps > 148 * 300:
             continue
+        it.set_variant(wb.LATENT_PAIR if name.endswith("pair_variant") else wb.LATENT_AUTO)
         ms = []
         for _ in range(4):
             t = time.perf_counter()
@@ -45,12 +47,16 @@ for batch, steps in ((32, 100), (148, 300), (1184, 300), (148, 2000)):
         k, w = min(m[0] for m in ms[1:]), min(m[1] for m in ms[1:])
         rec[name] = {"kernel_ms": round(k, 4), "call_ms_host_buffers": round(w, 3), "us_per_step": round(1e3 * k / steps, 3),
                      "Melement_steps_per_s": round(batch * 1024 * steps / k / 1e3, 1)}
+    it.set_variant(wb.LATENT_AUTO)
     if batch * steps <= 148 * 300:
         z = it(cs["z0"], cs["tspan"], theta)
         wE = np.ones((batch, 3, steps + 1), F32)
-        for _ in range(3):
-            it.adjoint(z, cs["tspan"], theta, w_energy=wE)
-        rec["adjoint"] = {"kernel_ms": round(it.last_kernel_ms(), 4), "us_per_step": round(1e3 * it.last_kernel_ms() / steps, 3)}
+        for name, variant in (("adjoint", wb.LATENT_AUTO), ("adjoint_generic_kernel", wb.LATENT_GENERIC)):
+            it.set_variant(variant)
+            for _ in range(3):
+                it.adjoint(z, cs["tspan"], theta, w_energy=wE)
+            rec[name] = {"kernel_ms": round(it.last_kernel_ms(), 4), "us_per_step": round(1e3 * it.last_kernel_ms() / steps, 3)}
+        it.set_variant(wb.LATENT_AUTO)
     out.append(rec)
     print(json.dumps(rec), flush=True)
     it.close()

@@ -78,5 +78,6 @@ static void launch(K kernel, const LatentP &p, int nt, size_t smem) {
 extern "C" int emu_sizeof_latentp() { return (int)sizeof(LatentP); }
 extern "C" void emu_latent_integrate(const LatentP *p, int nt) { launch(k_latent_integrate, *p, nt, LAT_FWD_SMEM(p->n)); }
 extern "C" void emu_latent_integrate_r1(const LatentP *p, int nt) { launch(k_latent_integrate_r1, *p, nt, LAT_R1_SMEM(p->n)); }
+extern "C" void emu_latent_integrate_r2(const LatentP *p, int nt) { launch(k_latent_integrate_r2, *p, nt, LAT_R2_SMEM(p->n)); }
 extern "C" void emu_latent_adjoint_r1(const LatentP *p, int nt) { launch(k_latent_adjoint_r1, *p, nt, LAT_ADJ1_SMEM(p->n)); }
 extern "C" void emu_latent_adjoint(const LatentP *p, int nt) { launch(k_latent_adjoint, *p, nt, LAT_ADJ_SMEM(p->n)); }

@@ -39,6 +39,7 @@ int main(int argc, char **argv) {
     p.z = z.data(); p.energy = with_energy ? e.data() : nullptr; p.z_last = last.data();
     emu_latent_integrate(&p, nt);
     if (nt >= n) emu_latent_integrate_r1(&p, nt);
+    if (n % 2 == 0 && nt >= n / 2) emu_latent_integrate_r2(&p, ((n / 2 + 31) / 32) * 32);
     p.zt = z.data(); p.w_energy = wE.data(); p.dL_dz = dz.data(); p.g_z0 = g0.data(); p.g_Y = gY.data(); p.g_shape = gs.data();
     p.g_pml = gp.data();
     for (int compat = 0; compat < 2; ++compat) {

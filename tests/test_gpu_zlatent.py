@@ -31,7 +31,7 @@ def test_host_constructors_match_oracle():
     assert np.array_equal(wb.build_pml_1d(dim, 10.0, 10000.0), cs["dyn"].pml)
 
 
-@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("generic", [0, 1, 2])     # LATENT_AUTO (register fast path), LATENT_GENERIC, LATENT_PAIR
 @pytest.mark.parametrize("n,knots,steps", [(96, "actions", 12), (200, "partial", 12), (100, "repeated", 12), (1500, "actions", 12),
                                            (64, "actions", 600)])
 def test_forward_bit_exact_small(n, knots, steps, generic):
@@ -39,7 +39,7 @@ def test_forward_bit_exact_small(n, knots, steps, generic):
     increasing (no cursor), n > 1024 (strided ownership: always the generic kernel), more steps than one factor table."""
     cs = make_case(n=n, batch=3, steps=steps, nseq=7 if steps > 100 else 4, seed=n, knots=knots)
     it = _integrator(cs)
-    it.set_generic(generic)
+    it.set_variant(generic)
     z, e = it(cs["z0"], cs["tspan"], _theta(cs), want_energy=True)
     want = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
     assert np.array_equal(z, want)
@@ -58,10 +58,11 @@ def test_forward_full_size_batch():
     assert np.array_equal(z, want)
     last, e2 = it(cs["z0"], cs["tspan"], _theta(cs), want_z=False, want_energy=True)
     assert np.array_equal(last, want[-1]) and np.array_equal(e, e2)
-    it.set_generic(True)
-    zg, eg = it(cs["z0"], cs["tspan"], _theta(cs), want_energy=True)
-    assert np.array_equal(zg, z)
-    np.testing.assert_allclose(eg, e, rtol=1e-6)
+    for variant in (wb.LATENT_GENERIC, wb.LATENT_PAIR):
+        it.set_variant(variant)
+        zg, eg = it(cs["z0"], cs["tspan"], _theta(cs), want_energy=True)
+        assert np.array_equal(zg, z)
+        np.testing.assert_allclose(eg, e, rtol=1e-6)
     np.testing.assert_allclose(e, lo.compute_latent_energy(want, wo.get_dx(cs["dim"])), rtol=1e-6)
 
 

@@ -128,7 +128,9 @@ def _params(cs, **ptrs):
 @pytest.mark.parametrize("kernel,n,nt,knots,steps", [
     ("generic", 96, 96, "actions", 12), ("generic", 200, 64, "actions", 12), ("generic", 70, 96, "partial", 12),
     ("r1", 96, 96, "actions", 12), ("r1", 70, 96, "partial", 12), ("r1", 100, 128, "repeated", 12), ("r1", 170, 192, "actions", 12),
-    ("r1", 33, 64, "actions", 520)])
+    ("r1", 33, 64, "actions", 520),
+    ("r2", 96, 64, "actions", 12), ("r2", 70, 64, "partial", 12), ("r2", 100, 64, "repeated", 12), ("r2", 172, 96, "actions", 12),
+    ("r2", 34, 32, "actions", 520), ("r2", 4, 32, "actions", 12), ("r2", 320, 160, "actions", 12)])
 def test_emulated_forward_kernel_is_bit_exact(emu, kernel, n, nt, knots, steps):
     """k_latent_integrate / k_latent_integrate_r1 == oracle integrate, bit for bit (fields), energies to 1e-6; threads ==
     elements, a strided ownership (n > threads, generic kernel only), idle threads (threads > n), knots that leave stage
@@ -139,7 +141,8 @@ def test_emulated_forward_kernel_is_bit_exact(emu, kernel, n, nt, knots, steps):
     e = np.full((cs["batch"], 3, cs["steps"] + 1), np.nan, F32)
     last = np.full((cs["batch"], 4, n), np.nan, F32)
     p, keep = _params(cs, z=z, energy=e, z_last=last)
-    (emu.emu_latent_integrate if kernel == "generic" else emu.emu_latent_integrate_r1)(C.byref(p), nt)
+    {"generic": emu.emu_latent_integrate, "r1": emu.emu_latent_integrate_r1, "r2": emu.emu_latent_integrate_r2}[kernel](
+        C.byref(p), nt)
     want = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
     assert np.isfinite(want).all() and np.abs(want[-1] - want[0]).max() > 1e-3      # the case does something
     assert np.array_equal(z, want)
@@ -148,14 +151,15 @@ def test_emulated_forward_kernel_is_bit_exact(emu, kernel, n, nt, knots, steps):
     np.testing.assert_allclose(e, we, rtol=1e-6, atol=1e-6 * we.max())
 
 
-@pytest.mark.parametrize("kernel", ["generic", "r1"])
+@pytest.mark.parametrize("kernel", ["generic", "r1", "r2"])
 def test_emulated_forward_kernel_energy_only(emu, kernel):
     """With z == NULL only the energies and the last state leave the kernel."""
     cs = make_case(n=64, batch=2, steps=8, nseq=3, seed=5)
     e = np.full((2, 3, 9), np.nan, F32)
     last = np.full((2, 4, 64), np.nan, F32)
     p, keep = _params(cs, energy=e, z_last=last)
-    (emu.emu_latent_integrate if kernel == "generic" else emu.emu_latent_integrate_r1)(C.byref(p), 64)
+    {"generic": emu.emu_latent_integrate, "r1": emu.emu_latent_integrate_r1, "r2": emu.emu_latent_integrate_r2}[kernel](
+        C.byref(p), 64)
     want = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
     assert np.array_equal(last, want[-1])
     np.testing.assert_allclose(e, lo.compute_latent_energy(want, wo.get_dx(cs["dim"])), rtol=1e-6)
@@ -225,7 +229,7 @@ def test_emulated_adjoint_r1_many_steps_and_segments(emu, compat):
 
 
 def test_kernels_are_race_free_under_thread_sanitizer():
-    """The four latent kernels under the host emulation, built with -fsanitize=thread: ThreadSanitizer orders accesses by
+    """The five latent kernels under the host emulation, built with -fsanitize=thread: ThreadSanitizer orders accesses by
     the barriers (vector clocks, independent of timing), so a missing __syncthreads() between a shared-memory write and a
     neighbour's read is reported even if the interleaving that breaks it never happens in this run."""
     src = os.path.join(ROOT, "tests", "emu", "latent_tsan_main.cpp")

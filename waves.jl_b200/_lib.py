@@ -91,6 +91,7 @@ SYMBOLS = {
     "waves_latent_launch_count": (C.c_int64, [C.c_void_p]),
     "waves_latent_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "waves_latent_set_generic": (C.c_int, [C.c_void_p, C.c_int]),
+    "waves_latent_set_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "waves_launch_count": (C.c_int64, [C.c_void_p]),
     "waves_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "waves_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

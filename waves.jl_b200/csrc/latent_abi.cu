@@ -39,6 +39,7 @@ struct waves_latent {
     cudaEvent_t ev0, ev1;  // around the last kernel launch
     float last_ms;
     int force_generic;  // 1: never use the register fast path (tests compare the two)
+    int pair_forward;   // 1: forward pass with the pair kernel where it applies (WAVES_LATENT_PAIR)
 };
 
 static bool on_device(const void *p) {
@@ -227,12 +228,17 @@ extern "C" int waves_latent_integrate(waves_latent *h, int batch, int steps, int
         return 1;
     // the attribute belongs to the function, not the handle: handles with different n may alternate
     const bool fast = !h->force_generic && h->n <= 1024 && nseq <= LAT_FAST_NSEQ;  // one element per thread, knots in shared memory
-    if (fast)
+    const bool pair = fast && h->pair_forward && (h->n % 2) == 0 && h->n >= 4;  // two elements per thread, packed f32x2
+    if (pair)
+        LCU(cudaFuncSetAttribute(k_latent_integrate_r2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_R2_SMEM(n)));
+    else if (fast)
         LCU(cudaFuncSetAttribute(k_latent_integrate_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_R1_SMEM(n)));
     else
         LCU(cudaFuncSetAttribute(k_latent_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_FWD_SMEM(n)));
     LCU(cudaEventRecord(h->ev0, h->stream));
-    if (fast)
+    if (pair)
+        k_latent_integrate_r2<<<batch, threads_for(h->n / 2), LAT_R2_SMEM(n), h->stream>>>(p);
+    else if (fast)
         k_latent_integrate_r1<<<batch, threads_for(h->n), LAT_R1_SMEM(n), h->stream>>>(p);
     else
         k_latent_integrate<<<batch, threads_for(h->n), LAT_FWD_SMEM(n), h->stream>>>(p);
@@ -295,6 +301,15 @@ extern "C" int waves_latent_adjoint(waves_latent *h, int batch, int steps, int n
 extern "C" int waves_latent_set_generic(waves_latent *h, int on) {
     if (!h) LFAIL("waves_latent_set_generic: null handle");
     h->force_generic = on != 0;
+    return 0;
+}
+
+extern "C" int waves_latent_set_variant(waves_latent *h, int variant) {
+    if (!h) LFAIL("waves_latent_set_variant: null handle");
+    if (variant != WAVES_LATENT_AUTO && variant != WAVES_LATENT_GENERIC && variant != WAVES_LATENT_PAIR)
+        LFAIL("waves_latent_set_variant: unknown variant %d", variant);
+    h->force_generic = variant == WAVES_LATENT_GENERIC;
+    h->pair_forward = variant == WAVES_LATENT_PAIR;
     return 0;
 }
 

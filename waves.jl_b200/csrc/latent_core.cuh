@@ -475,6 +475,228 @@ LAT_GLOBAL void k_latent_integrate_r1(LatentP p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Pair variant of the forward fast path (opt-in: waves_latent_set_variant(h, WAVES_LATENT_PAIR)): every thread owns TWO
+// adjacent elements held as float2 and the arithmetic is packed f32x2 (FADD2 / FMUL2: one issue slot per two elements --
+// the forward kernels are issue-bound, profiles/r1_latent_ncu_fastpath_summary.json), neighbours cost 8 LDS per two
+// elements instead of 16, stores are STS.64, and a barrier joins 16 warps instead of 32.  Multiplies and adds stay
+// separately rounded (the packed instructions ptxas emits are FMUL2 and FFMA2 with a unit multiplier or a zero addend,
+// both exact), so it is bit-identical to the other kernels.  127 registers at 512 threads: one sample per SM (at 64
+// registers two samples would share an SM, at the price of spills in the stage loop: to be decided by measurement).
+// n even, 4 <= n <= 1024.  NOT YET RUN ON A B200 (written after the round's GPU budget was spent); checked bit-exact under
+// the host emulation and race-free under ThreadSanitizer.
+#ifndef LAT_EMU
+typedef float2 lf2;
+#define LAT_GLOBAL2 __global__ __launch_bounds__(512, 1)
+LAT_DEV lf2 lf2_mk(float a, float b) { return make_float2(a, b); }
+LAT_DEV lf2 lf2_add(lf2 a, lf2 b) { return __fadd2_rn(a, b); }
+LAT_DEV lf2 lf2_sub(lf2 a, lf2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }  // a + (-b) == a - b in IEEE
+LAT_DEV lf2 lf2_mul(lf2 a, lf2 b) { return __fmul2_rn(a, b); }
+#else
+struct lf2 {
+    float x, y;
+};
+#define LAT_GLOBAL2 static
+LAT_DEV lf2 lf2_mk(float a, float b) { return lf2{a, b}; }
+LAT_DEV lf2 lf2_add(lf2 a, lf2 b) { return lf2{a.x + b.x, a.y + b.y}; }
+LAT_DEV lf2 lf2_sub(lf2 a, lf2 b) { return lf2{a.x - b.x, a.y - b.y}; }
+LAT_DEV lf2 lf2_mul(lf2 a, lf2 b) { return lf2{a.x * b.x, a.y * b.y}; }
+#endif
+LAT_DEV lf2 lf2_bc(float s) { return lf2_mk(s, s); }
+
+#define LAT_R2_FLOATS(n) LAT_R1_FLOATS(n)
+#define LAT_R2_SMEM(n) LAT_R1_SMEM(n)
+
+LAT_GLOBAL2 void k_latent_integrate_r2(LatentP p) {
+    LAT_SMEM
+    const int n = p.n, tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nw = (nt + 31) >> 5;
+    const int T = p.steps + 1, e0 = 2 * tid, half = n >> 1;
+    float *B0 = (float *)lat_smem, *B1 = B0 + 4 * n;
+    float *shs = B1 + 4 * n, *Xs = shs + n, *fcs = Xs + LAT_FAST_NSEQ, *red = fcs + 2 * 3 * LAT_CH;
+    const bool act = tid < half;
+    const float *Yb = p.Y + (size_t)b * p.nseq * n;
+
+    lf2 u[4], acc[4], ys[4], sg = lf2_bc(0.0f), sown = lf2_bc(0.0f);
+    for (int f = 0; f < 4; ++f) u[f] = acc[f] = ys[f] = lf2_bc(0.0f);
+    if (act) {
+        for (int f = 0; f < 4; ++f) {
+            const float *src = p.z0 + ((size_t)b * 4 + f) * n + e0;
+            u[f] = lf2_mk(src[0], src[1]);
+            *(lf2 *)&B0[f * n + e0] = u[f];
+            if (p.z) {
+                float *dst = p.z + ((size_t)b * 4 + f) * n + e0;
+                dst[0] = u[f].x;
+                dst[1] = u[f].y;
+            }
+        }
+        if (p.shape) sown = lf2_mk(p.shape[(size_t)b * n + e0], p.shape[(size_t)b * n + e0 + 1]);
+        *(lf2 *)&shs[e0] = sown;
+        sg = lf2_mul(lf2_bc(p.pml_scale), lf2_mk(p.pml[(size_t)b * n + e0], p.pml[(size_t)b * n + e0 + 1]));
+    }
+    for (int k = tid; k < p.nseq; k += nt) Xs[k] = p.X[(size_t)b * p.nseq + k];
+    LAT_SYNC();
+    bool mono = true;
+    for (int k = 0; k + 1 < p.nseq; ++k) mono = mono && (Xs[k] < Xs[k + 1]);
+    const float rend = Xs[p.nseq - 1];
+
+    // neighbours of the pair: element e0-1 and element e0+2 (clamped for the two boundary threads, whose rows do not use them
+    // in that role)
+    const bool first = act && tid == 0, last = act && tid == half - 1;
+    const int iL = e0 > 0 ? e0 - 1 : 0, iR = e0 + 2 < n ? e0 + 2 : n - 1;
+    const lf2 sN = act ? lf2_mk(shs[iL], shs[iR]) : lf2_bc(0.0f);
+    const int wlo = tid & ~31;
+    const bool edge_warp = wlo == 0 || (wlo <= half - 1 && half - 1 < wlo + 32);
+    // rows of dyn.grad for the two elements: coefficients of the operands (X0, X1, X2) chosen in grad() below
+    const lf2 A0 = lf2_mk(first ? p.gf[0] : p.gc[0], last ? p.gl[0] : p.gc[0]);
+    const lf2 A1 = lf2_mk(first ? p.gf[1] : p.gc[1], last ? p.gl[1] : p.gc[1]);
+    const lf2 A2 = lf2_mk(first ? p.gf[2] : 0.0f, last ? p.gl[2] : 0.0f);
+    const lf2 bcv = lf2_mk(first ? 0.0f : 1.0f, last ? 0.0f : 1.0f);
+    const lf2 g0 = lf2_bc(p.gc[0]), g1 = lf2_bc(p.gc[1]), c02 = lf2_bc(p.c0);
+    // (∇ * v) at the two elements: N = (v[e0-1], v[e0+2]), O = (v[e0], v[e0+1])
+    auto grad = [&](lf2 N, lf2 O) -> lf2 {
+        if (!edge_warp) return lf2_add(lf2_mul(g0, lf2_mk(N.x, O.x)), lf2_mul(g1, lf2_mk(O.y, N.y)));
+        const lf2 X0 = lf2_mk(first ? O.x : N.x, last ? N.x : O.x);
+        const lf2 X1 = lf2_mk(O.y, last ? O.x : N.y);
+        const lf2 X2 = lf2_mk(N.y, O.y);
+        const lf2 two = lf2_add(lf2_mul(A0, X0), lf2_mul(A1, X1));
+        const lf2 thr = lf2_add(two, lf2_mul(A2, X2));
+        return lf2_mk(first ? thr.x : two.x, last ? thr.y : two.y);
+    };
+    auto rhs = [&](const float *S, lf2 a, float fs, const lf2 own[4], lf2 k[4]) {
+        if (!act) return;
+        const float *Ut = S, *Vt = S + n, *Ui = S + 2 * n, *Vi = S + 3 * n;
+        const lf2 fs2 = lf2_bc(fs);
+        const lf2 fN = lf2_mul(sN, fs2), fO = lf2_mul(sown, fs2);
+        const lf2 gVt = grad(lf2_mk(Vt[iL], Vt[iR]), own[1]);
+        const lf2 gUt = grad(lf2_add(lf2_mk(Ut[iL], Ut[iR]), fN), lf2_add(own[0], fO));  // ∇ * (U_tot .+ f)
+        const lf2 gVi = grad(lf2_mk(Vi[iL], Vi[iR]), own[3]);
+        const lf2 gUi = grad(lf2_add(lf2_mk(Ui[iL], Ui[iR]), fN), lf2_add(own[2], fO));
+        k[0] = lf2_sub(lf2_mul(a, gVt), lf2_mul(sg, own[0]));
+        k[1] = lf2_sub(lf2_mul(a, gUt), lf2_mul(sg, own[1]));
+        k[2] = lf2_sub(lf2_mul(c02, gVi), lf2_mul(sg, own[2]));
+        k[3] = lf2_sub(lf2_mul(gUi, c02), lf2_mul(sg, own[3]));
+        if (edge_warp) {  // bc: x * 1 is exact for the interior lanes
+            k[0] = lf2_mul(k[0], bcv);
+            k[2] = lf2_mul(k[2], bcv);
+        }
+    };
+
+    // c0 * C(t) at the two elements, as in k_latent_integrate_r1
+    int kcur = 0;
+    lf2 yk = lf2_bc(0.0f), yk1 = lf2_bc(0.0f);
+    float lc = 1.0f, rc = 0.0f;
+    auto speed = [&](float t) -> lf2 {
+        if (!act) return lf2_bc(0.0f);
+        if (!mono) return lf2_mk(lat_speed_elem(p, Xs, Yb, t, e0), lat_speed_elem(p, Xs, Yb, t, e0 + 1));
+        if (!(lc <= t && t < rc)) {
+            while (kcur + 2 < p.nseq && t >= Xs[kcur + 1]) ++kcur;
+            while (kcur > 0 && t < Xs[kcur]) --kcur;
+            const float l = Xs[kcur], r = Xs[kcur + 1];
+            if (!lat_mask(l, r, rend, t)) return lf2_bc(p.c0 * (0.0f + (t - 0.0f) * 0.0f));
+            if (l != lc || r != rc) {
+                yk = lf2_mk(Yb[(size_t)kcur * n + e0], Yb[(size_t)kcur * n + e0 + 1]);
+                yk1 = lf2_mk(Yb[(size_t)(kcur + 1) * n + e0], Yb[(size_t)(kcur + 1) * n + e0 + 1]);
+                lc = l;
+                rc = r;
+            }
+        }
+        const float dd = (rc - t) - (lc - t), x0 = 0.0f + lc;
+        const lf2 dy = lf2_sub(yk1, yk);
+        const lf2 dydx = lf2_add(lf2_bc(0.0f), lf2_mk(dy.x / dd, dy.y / dd));
+        const lf2 y0 = lf2_add(lf2_bc(0.0f), yk);
+        return lf2_mul(c02, lf2_add(y0, lf2_mul(lf2_bc(t - x0), dydx)));
+    };
+
+    const lf2 hdt2 = lf2_bc(p.hdt), dt2 = lf2_bc(p.dt), two2 = lf2_bc(2.0f), sixth2 = lf2_bc(1.0f / 6.0f);
+    float t0 = p.steps > 0 ? p.tspan[(size_t)b * T] : 0.0f;
+    float *zp = (p.z && act) ? p.z + ((size_t)p.batch + b) * 4 * n + e0 : nullptr;
+    const size_t zstep = (size_t)p.batch * 4 * n;
+    for (int s = 0; s <= p.steps; ++s) {
+        if (p.energy) {
+            const lf2 d = lf2_sub(u[0], u[2]);  // tot .- inc in Float32 first
+            const lf2 ea = lf2_mul(u[0], u[0]), ec = lf2_mul(u[2], u[2]), ed = lf2_mul(d, d);
+            float e[3] = {ea.x + ea.y, ec.x + ec.y, ed.x + ed.y};
+            lat_reduce3f_warp(e, red, tid);
+        }
+        lf2 cA = lf2_bc(0.0f), cB = cA, cC = cA;
+        if (s < p.steps) {
+            if (s % LAT_CH == 0) {
+                float *fw = fcs + ((s / LAT_CH) & 1) * 3 * LAT_CH;
+                for (int q = tid; q < 3 * LAT_CH; q += nt) {
+                    const int st = s + q / 3, w = q - 3 * (q / 3);
+                    if (st < p.steps) {
+                        const float ts = p.tspan[(size_t)b * T + st];
+                        fw[q] = p.shape ? lat_sin_factor(w == 0 ? ts : (w == 1 ? ts + p.hdt : ts + p.dt), p.freq) : 0.0f;
+                    }
+                }
+            }
+            cA = speed(t0);
+            cB = speed(t0 + p.hdt);
+            cC = speed(t0 + p.dt);
+        }
+        LAT_SYNC();
+        if (p.energy) {
+            const int w = tid >> 5, lane = tid & 31;
+            if (nw >= 5) {
+                if (w >= 1 && w <= 3) {
+                    const double sum = lat_warp_sum(lane < nw ? (double)red[lane * 3 + (w - 1)] : 0.0, red, nw, w - 1, lane);
+                    if (lane == 0) p.energy[((size_t)b * 3 + (w - 1)) * T + s] = (float)sum * p.dx;
+                }
+            } else if (tid < 3) {
+                double sum = 0.0;
+                for (int ww = 0; ww < nw; ++ww) sum += (double)red[ww * 3 + tid];
+                p.energy[((size_t)b * 3 + tid) * T + s] = (float)sum * p.dx;
+            }
+        }
+        if (s == p.steps) break;
+        const float *fc = fcs + ((s / LAT_CH) & 1) * 3 * LAT_CH + 3 * (s % LAT_CH);
+        const float f0 = fc[0], f1 = fc[1], f2 = fc[2];
+        if (s + 1 < p.steps) t0 = p.tspan[(size_t)b * T + s + 1];
+
+        lf2 k[4];
+        for (int f = 0; f < 4; ++f) k[f] = lf2_bc(0.0f);
+        rhs(B0, cA, f0, u, k);  // stage 1: reads B0 (= u), writes y2 to B1
+        for (int f = 0; f < 4; ++f) {
+            acc[f] = k[f];
+            ys[f] = lf2_add(u[f], lf2_mul(hdt2, k[f]));
+            if (act) *(lf2 *)&B1[f * n + e0] = ys[f];
+        }
+        LAT_SYNC();
+        rhs(B1, cB, f1, ys, k);  // stage 2: reads B1 (= y2), writes y3 to B0
+        for (int f = 0; f < 4; ++f) {
+            acc[f] = lf2_add(acc[f], lf2_mul(two2, k[f]));
+            ys[f] = lf2_add(u[f], lf2_mul(hdt2, k[f]));
+            if (act) *(lf2 *)&B0[f * n + e0] = ys[f];
+        }
+        LAT_SYNC();
+        rhs(B0, cB, f1, ys, k);  // stage 3: reads B0 (= y3), writes y4 to B1
+        for (int f = 0; f < 4; ++f) {
+            acc[f] = lf2_add(acc[f], lf2_mul(two2, k[f]));
+            ys[f] = lf2_add(u[f], lf2_mul(dt2, k[f]));
+            if (act) *(lf2 *)&B1[f * n + e0] = ys[f];
+        }
+        LAT_SYNC();
+        rhs(B1, cC, f2, ys, k);  // stage 4: reads B1 (= y4), writes the new state to B0
+        for (int f = 0; f < 4; ++f) {
+            const lf2 du = lf2_mul(lf2_mul(sixth2, lf2_add(acc[f], k[f])), dt2);
+            u[f] = lf2_add(u[f], du);
+            if (act) *(lf2 *)&B0[f * n + e0] = u[f];
+        }
+        if (zp) {
+            for (int f = 0; f < 4; ++f) {
+                zp[(size_t)f * n] = u[f].x;
+                zp[(size_t)f * n + 1] = u[f].y;
+            }
+            zp += zstep;
+        }
+    }
+    if (p.z_last && act)
+        for (int f = 0; f < 4; ++f) {
+            p.z_last[((size_t)b * 4 + f) * n + e0] = u[f].x;
+            p.z_last[((size_t)b * 4 + f) * n + e0 + 1] = u[f].y;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // reverse pass: adjoint_sensitivity (src/dynamics.jl:97-118) for the batchwise OneDim simulation.
 //   exact  : λ_N = a_N;  λ_i = a_i + (I + J_iᵀ) λ_{i+1}
 //   compat : acc = 0; for i = N..0: acc = (I + J_iᵀ)(acc + a_i)          (the loop as written)

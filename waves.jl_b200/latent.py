@@ -25,7 +25,9 @@ from ._lib import check
 from .engine import ADJ_COMPAT, ADJ_EXACT, _ptr
 from .host import F32, _fp, julia_range
 
-__all__ = ["OneDim", "LinearInterpolation", "LatentSource", "LatentDynamics", "LatentIntegrator", "build_pml_1d", "ADJ_EXACT",
+LATENT_AUTO, LATENT_GENERIC, LATENT_PAIR = 0, 1, 2
+
+__all__ = ["LATENT_AUTO", "LATENT_GENERIC", "LATENT_PAIR", "OneDim", "LinearInterpolation", "LatentSource", "LatentDynamics", "LatentIntegrator", "build_pml_1d", "ADJ_EXACT",
            "ADJ_COMPAT"]
 
 
@@ -144,6 +146,10 @@ class LatentIntegrator:
     def set_generic(self, on: bool):
         """Force the generic shared-memory kernels (the register fast path is the default where it applies)."""
         check(_lib.lib().waves_latent_set_generic(self._h, int(bool(on))))
+
+    def set_variant(self, variant: int):
+        """LATENT_AUTO (default), LATENT_GENERIC or LATENT_PAIR (experimental forward kernel: two elements per thread)."""
+        check(_lib.lib().waves_latent_set_variant(self._h, int(variant)))
 
     def last_kernel_ms(self) -> float:
         """Device time of the kernel of the last call (CUDA events on the handle's stream)."""
