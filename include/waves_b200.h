@@ -252,12 +252,16 @@ int64_t waves_latent_launch_count(waves_latent *h);
 /* on != 0: always run the generic shared-memory kernels (any n that fits) instead of the register fast path taken for
  * n <= 1024 and nseq <= 64; both are bit-identical, the switch exists so tests can compare them */
 int waves_latent_set_generic(waves_latent *h, int on);
-/* Kernel variant of the latent path.  AUTO: register fast paths where they apply (n <= 1024, nseq <= 64), else the generic
- * kernels.  GENERIC: as waves_latent_set_generic(h, 1).  PAIR: forward pass with two elements per thread and packed f32x2
- * arithmetic (n even, 4 <= n <= 1024; otherwise AUTO) -- experimental: bit-identical under emulation, not yet timed. */
+/* Kernel variants of the latent path (flags, OR-ed).  The default (AUTO) is what has been measured on a B200: the register
+ * fast path of the forward pass where it applies (n <= 1024, nseq <= 64), the generic kernels otherwise and for the reverse
+ * pass.  GENERIC (exclusive): as waves_latent_set_generic(h, 1).  PAIR: forward pass with two elements per thread and packed
+ * f32x2 arithmetic (n even, 4 <= n <= 1024).  ADJ_R1: reverse pass with the register kernel (n <= 1024, nseq <= 64).
+ * PAIR and ADJ_R1 are bit-identical / equal to rounding under the host emulation of the kernels but were written after the
+ * round's GPU budget was spent: opt-in until timed. */
 #define WAVES_LATENT_AUTO 0
 #define WAVES_LATENT_GENERIC 1
 #define WAVES_LATENT_PAIR 2
+#define WAVES_LATENT_ADJ_R1 4
 int waves_latent_set_variant(waves_latent *h, int variant);
 /* device time (ms, CUDA events on the handle's stream) of the kernel of the last integrate / adjoint call */
 float waves_latent_last_kernel_ms(waves_latent *h);

@@ -31,7 +31,7 @@ def test_host_constructors_match_oracle():
     assert np.array_equal(wb.build_pml_1d(dim, 10.0, 10000.0), cs["dyn"].pml)
 
 
-@pytest.mark.parametrize("generic", [0, 1, 2])     # LATENT_AUTO (register fast path), LATENT_GENERIC, LATENT_PAIR
+@pytest.mark.parametrize("generic", [0, 1])     # LATENT_AUTO (register fast path), LATENT_GENERIC
 @pytest.mark.parametrize("n,knots,steps", [(96, "actions", 12), (200, "partial", 12), (100, "repeated", 12), (1500, "actions", 12),
                                            (64, "actions", 600)])
 def test_forward_bit_exact_small(n, knots, steps, generic):
@@ -58,11 +58,10 @@ def test_forward_full_size_batch():
     assert np.array_equal(z, want)
     last, e2 = it(cs["z0"], cs["tspan"], _theta(cs), want_z=False, want_energy=True)
     assert np.array_equal(last, want[-1]) and np.array_equal(e, e2)
-    for variant in (wb.LATENT_GENERIC, wb.LATENT_PAIR):
-        it.set_variant(variant)
-        zg, eg = it(cs["z0"], cs["tspan"], _theta(cs), want_energy=True)
-        assert np.array_equal(zg, z)
-        np.testing.assert_allclose(eg, e, rtol=1e-6)
+    it.set_variant(wb.LATENT_GENERIC)
+    zg, eg = it(cs["z0"], cs["tspan"], _theta(cs), want_energy=True)
+    assert np.array_equal(zg, z)
+    np.testing.assert_allclose(eg, e, rtol=1e-6)
     np.testing.assert_allclose(e, lo.compute_latent_energy(want, wo.get_dx(cs["dim"])), rtol=1e-6)
 
 
@@ -82,9 +81,55 @@ def test_no_source_and_c_equal_one_property():
 
 
 @pytest.mark.parametrize("compat", [False, True])
+@pytest.mark.parametrize("n,steps,knots", [(80, 8, "actions"), (40, 8, "repeated"), (1024, 6, "actions")])
+def test_adjoint_generic_kernel_matches_autograd(n, steps, knots, compat):
+    """The generic reverse kernel against float64 autograd (exact mode) / the literal reference loop (compat mode)."""
+    cs = make_case(n=n, batch=2, steps=steps, nseq=4 if knots == "repeated" else 3, seed=11 + n, knots=knots)
+    rng = np.random.default_rng(3)
+    it = _integrator(cs)
+    it.set_variant(wb.LATENT_GENERIC)
+    z = it(cs["z0"], cs["tspan"], _theta(cs))
+    w_energy = rng.standard_normal((2, 3, steps + 1)).astype(F32)
+    dL_dz = (1e-2 * rng.standard_normal(z.shape)).astype(F32)
+    g = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=w_energy, dL_dz=dL_dz, mode=wb.ADJ_COMPAT if compat else wb.ADJ_EXACT)
+    want = lao.adjoint_truth(cs, w_energy, dL_dz, compat=compat, z_stored=z)
+    for name in ("z0", "Y", "shape", "pml"):
+        err = np.linalg.norm(g[name] - want[name]) / np.linalg.norm(want[name])
+        assert err < 1e-4, (name, err)
+
+
+def test_errors_are_reported_not_thrown():
+    cs = make_case(n=1500, batch=1, steps=4, nseq=3)
+    it = _integrator(cs)
+    z = it(cs["z0"], cs["tspan"], _theta(cs))
+    with pytest.raises(wb.WavesError, match="shared memory"):      # n = 1500: generic reverse kernel, 39 n floats do not fit
+        it.adjoint(z, cs["tspan"], _theta(cs), w_energy=np.ones((1, 3, 5), F32))
+    with pytest.raises(wb.WavesError, match="shared memory"):
+        wb.LatentIntegrator(wb.LatentDynamics(wb.OneDim(100.0, 4096), 1531.0, 10.0, 10000.0), 1e-5)
+
+
+# ---- kernels written after the round's GPU budget was spent (checked under the host emulation and ThreadSanitizer, first run
+# ---- on a B200 is this file): kept last so that a failure here cannot hide the results above ---------------------------------
+@pytest.mark.parametrize("n,knots,steps", [(96, "actions", 12), (70, "partial", 12), (100, "repeated", 12), (64, "actions", 600),
+                                           (1024, "actions", 100)])
+def test_pair_variant_forward_bit_exact(n, knots, steps):
+    """LATENT_PAIR (two elements per thread, packed f32x2) == oracle, bit for bit."""
+    cs = make_case(n=n, batch=3, steps=steps, nseq=7 if steps == 600 else (3 if steps == 100 else 4), seed=n, knots=knots)
+    it = _integrator(cs)
+    it.set_variant(wb.LATENT_PAIR)
+    z, e = it(cs["z0"], cs["tspan"], _theta(cs), want_energy=True)
+    want = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
+    assert np.array_equal(z, want)
+    we = lo.compute_latent_energy(want, wo.get_dx(cs["dim"]))
+    np.testing.assert_allclose(e, we, rtol=1e-6, atol=1e-6 * we.max())
+    last, e2 = it(cs["z0"], cs["tspan"], _theta(cs), want_z=False, want_energy=True)
+    assert np.array_equal(last, want[-1]) and np.array_equal(e, e2)
+
+
+@pytest.mark.parametrize("compat", [False, True])
 @pytest.mark.parametrize("n,steps,knots", [(80, 8, "actions"), (65, 8, "partial"), (40, 8, "repeated"), (1024, 6, "actions")])
-def test_adjoint_matches_autograd(n, steps, knots, compat):
-    """Register fast path (default) and generic reverse kernel against float64 autograd / the literal reference loop, and
+def test_adjoint_fast_path_matches_autograd(n, steps, knots, compat):
+    """Register reverse kernel (LATENT_ADJ_R1) and generic reverse kernel against float64 autograd / the literal reference loop, and
     against each other."""
     cs = make_case(n=n, batch=2, steps=steps, nseq=4 if knots == "repeated" else 3, seed=11 + n, knots=knots)
     rng = np.random.default_rng(3)
@@ -93,6 +138,7 @@ def test_adjoint_matches_autograd(n, steps, knots, compat):
     w_energy = rng.standard_normal((2, 3, steps + 1)).astype(F32)
     dL_dz = (1e-2 * rng.standard_normal(z.shape)).astype(F32)
     mode = wb.ADJ_COMPAT if compat else wb.ADJ_EXACT
+    it.set_variant(wb.LATENT_ADJ_R1)
     g = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=w_energy, dL_dz=dL_dz, mode=mode)
     it.set_generic(True)
     gg = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=w_energy, dL_dz=dL_dz, mode=mode)
@@ -104,13 +150,14 @@ def test_adjoint_matches_autograd(n, steps, knots, compat):
         assert np.linalg.norm(g[name] - gg[name]) / np.linalg.norm(gg[name]) < 2e-5, name
 
 
-def test_adjoint_many_steps_energy_cotangent():
+def test_adjoint_fast_path_many_steps_energy_cotangent():
     """300 steps over three action segments (factor-table chunks in reverse order, dL/dY accumulators flushed at every
     segment change), energy cotangent only: fast path == generic kernel."""
     cs = make_case(n=1024, batch=3, steps=300, nseq=4, seed=9)
     it = _integrator(cs)
     z = it(cs["z0"], cs["tspan"], _theta(cs))
     wE = np.random.default_rng(1).standard_normal((3, 3, 301)).astype(F32)
+    it.set_variant(wb.LATENT_ADJ_R1)
     g = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=wE)
     it.set_generic(True)
     gg = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=wE)
@@ -119,11 +166,3 @@ def test_adjoint_many_steps_energy_cotangent():
         assert np.linalg.norm(g[name] - gg[name]) / np.linalg.norm(gg[name]) < 5e-5, name
 
 
-def test_errors_are_reported_not_thrown():
-    cs = make_case(n=1500, batch=1, steps=4, nseq=3)
-    it = _integrator(cs)
-    z = it(cs["z0"], cs["tspan"], _theta(cs))
-    with pytest.raises(wb.WavesError, match="shared memory"):      # n = 1500: generic reverse kernel, 39 n floats do not fit
-        it.adjoint(z, cs["tspan"], _theta(cs), w_energy=np.ones((1, 3, 5), F32))
-    with pytest.raises(wb.WavesError, match="shared memory"):
-        wb.LatentIntegrator(wb.LatentDynamics(wb.OneDim(100.0, 4096), 1531.0, 10.0, 10000.0), 1e-5)

@@ -25,9 +25,9 @@ from ._lib import check
 from .engine import ADJ_COMPAT, ADJ_EXACT, _ptr
 from .host import F32, _fp, julia_range
 
-LATENT_AUTO, LATENT_GENERIC, LATENT_PAIR = 0, 1, 2
+LATENT_AUTO, LATENT_GENERIC, LATENT_PAIR, LATENT_ADJ_R1 = 0, 1, 2, 4
 
-__all__ = ["LATENT_AUTO", "LATENT_GENERIC", "LATENT_PAIR", "OneDim", "LinearInterpolation", "LatentSource", "LatentDynamics", "LatentIntegrator", "build_pml_1d", "ADJ_EXACT",
+__all__ = ["LATENT_AUTO", "LATENT_GENERIC", "LATENT_PAIR", "LATENT_ADJ_R1", "OneDim", "LinearInterpolation", "LatentSource", "LatentDynamics", "LatentIntegrator", "build_pml_1d", "ADJ_EXACT",
            "ADJ_COMPAT"]
 
 
@@ -148,7 +148,8 @@ class LatentIntegrator:
         check(_lib.lib().waves_latent_set_generic(self._h, int(bool(on))))
 
     def set_variant(self, variant: int):
-        """LATENT_AUTO (default), LATENT_GENERIC or LATENT_PAIR (experimental forward kernel: two elements per thread)."""
+        """Flags: LATENT_AUTO (default: the kernels measured on a B200), LATENT_GENERIC, or any of LATENT_PAIR (forward kernel
+        with two elements per thread) | LATENT_ADJ_R1 (register reverse kernel) -- both opt-in until timed."""
         check(_lib.lib().waves_latent_set_variant(self._h, int(variant)))
 
     def last_kernel_ms(self) -> float:
