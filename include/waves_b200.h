@@ -255,7 +255,8 @@ int waves_latent_set_generic(waves_latent *h, int on);
 /* Kernel variants of the latent path (flags, OR-ed).  The default (AUTO) is what has been measured on a B200: the register
  * fast path of the forward pass where it applies (n <= 1024, nseq <= 64), the generic kernels otherwise and for the reverse
  * pass.  GENERIC (exclusive): as waves_latent_set_generic(h, 1).  PAIR: forward pass with two elements per thread and packed
- * f32x2 arithmetic (n even, 4 <= n <= 1024).  ADJ_R1: reverse pass with the register kernel (n <= 1024, nseq <= 64).
+ * f32x2 arithmetic (n even, 4 <= n <= 1024).  ADJ_R1: reverse pass with the register kernel (n <= 1024, nseq <= 64);
+ * PAIR | ADJ_R1: its two-elements-per-thread form.
  * PAIR and ADJ_R1 are bit-identical / equal to rounding under the host emulation of the kernels but were written after the
  * round's GPU budget was spent: opt-in until timed. */
 #define WAVES_LATENT_AUTO 0

@@ -80,4 +80,5 @@ extern "C" void emu_latent_integrate(const LatentP *p, int nt) { launch(k_latent
 extern "C" void emu_latent_integrate_r1(const LatentP *p, int nt) { launch(k_latent_integrate_r1, *p, nt, LAT_R1_SMEM(p->n)); }
 extern "C" void emu_latent_integrate_r2(const LatentP *p, int nt) { launch(k_latent_integrate_r2, *p, nt, LAT_R2_SMEM(p->n)); }
 extern "C" void emu_latent_adjoint_r1(const LatentP *p, int nt) { launch(k_latent_adjoint_r1, *p, nt, LAT_ADJ1_SMEM(p->n)); }
+extern "C" void emu_latent_adjoint_r2(const LatentP *p, int nt) { launch(k_latent_adjoint_r2, *p, nt, LAT_ADJ1_SMEM(p->n)); }
 extern "C" void emu_latent_adjoint(const LatentP *p, int nt) { launch(k_latent_adjoint, *p, nt, LAT_ADJ_SMEM(p->n)); }

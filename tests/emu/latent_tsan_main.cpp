@@ -46,6 +46,7 @@ int main(int argc, char **argv) {
         p.compat = compat;
         emu_latent_adjoint(&p, nt);
         if (nt >= n) emu_latent_adjoint_r1(&p, nt);
+        if (n % 2 == 0 && nt >= n / 2) emu_latent_adjoint_r2(&p, ((n / 2 + 31) / 32) * 32);
     }
     double chk = 0;
     for (float v : g0) chk += v;

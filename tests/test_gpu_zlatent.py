@@ -140,14 +140,17 @@ def test_adjoint_fast_path_matches_autograd(n, steps, knots, compat):
     mode = wb.ADJ_COMPAT if compat else wb.ADJ_EXACT
     it.set_variant(wb.LATENT_ADJ_R1)
     g = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=w_energy, dL_dz=dL_dz, mode=mode)
+    it.set_variant(wb.LATENT_ADJ_R1 | wb.LATENT_PAIR)      # pair form where n is even, else the register kernel again
+    gp = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=w_energy, dL_dz=dL_dz, mode=mode)
     it.set_generic(True)
     gg = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=w_energy, dL_dz=dL_dz, mode=mode)
     want = lao.adjoint_truth(cs, w_energy, dL_dz, compat=compat, z_stored=z)
     for name in ("z0", "Y", "shape", "pml"):
-        for got in (g, gg):
+        for got in (g, gp, gg):
             err = np.linalg.norm(got[name] - want[name]) / np.linalg.norm(want[name])
             assert err < 1e-4, (name, err)
-        assert np.linalg.norm(g[name] - gg[name]) / np.linalg.norm(gg[name]) < 2e-5, name
+        for got in (g, gp):
+            assert np.linalg.norm(got[name] - gg[name]) / np.linalg.norm(gg[name]) < 2e-5, name
 
 
 def test_adjoint_fast_path_many_steps_energy_cotangent():
@@ -159,10 +162,13 @@ def test_adjoint_fast_path_many_steps_energy_cotangent():
     wE = np.random.default_rng(1).standard_normal((3, 3, 301)).astype(F32)
     it.set_variant(wb.LATENT_ADJ_R1)
     g = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=wE)
+    it.set_variant(wb.LATENT_ADJ_R1 | wb.LATENT_PAIR)
+    gp = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=wE)
     it.set_generic(True)
     gg = it.adjoint(z, cs["tspan"], _theta(cs), w_energy=wE)
     for name in ("z0", "Y", "shape", "pml"):
         assert np.linalg.norm(gg[name]) > 0
-        assert np.linalg.norm(g[name] - gg[name]) / np.linalg.norm(gg[name]) < 5e-5, name
+        for got in (g, gp):
+            assert np.linalg.norm(got[name] - gg[name]) / np.linalg.norm(gg[name]) < 5e-5, name
 
 

@@ -169,7 +169,10 @@ def test_emulated_forward_kernel_energy_only(emu, kernel):
 @pytest.mark.parametrize("kernel,n,nt,knots", [("generic", 48, 64, "actions"), ("generic", 80, 32, "actions"),
                                                ("r1", 48, 64, "actions"), ("r1", 65, 96, "actions"), ("r1", 130, 160, "actions"),
                                                ("r1", 70, 96, "partial"), ("r1", 40, 64, "repeated"),
-                                               ("generic", 40, 64, "repeated")])
+                                               ("generic", 40, 64, "repeated"),
+                                               ("r2", 48, 32, "actions"), ("r2", 66, 64, "actions"), ("r2", 132, 96, "actions"),
+                                               ("r2", 70, 64, "partial"), ("r2", 40, 32, "repeated"), ("r2", 4, 32, "actions"),
+                                               ("r2", 8, 32, "actions"), ("r2", 260, 160, "actions"), ("r2", 130, 96, "actions")])
 def test_emulated_adjoint_kernel_matches_autograd(emu, compat, kernel, n, nt, knots):
     """k_latent_adjoint / k_latent_adjoint_r1 against torch float64 reverse-mode over the unrolled oracle trajectory (exact
     mode) and a literal transcription of the reference loop (compat mode, src/dynamics.jl:101-115): z0, C.Y, F.shape and
@@ -191,12 +194,12 @@ def test_emulated_adjoint_kernel_matches_autograd(emu, compat, kernel, n, nt, kn
         fn(C.byref(p), nt)
         return g
 
-    got = run(emu.emu_latent_adjoint if kernel == "generic" else emu.emu_latent_adjoint_r1)
+    got = run({"generic": emu.emu_latent_adjoint, "r1": emu.emu_latent_adjoint_r1, "r2": emu.emu_latent_adjoint_r2}[kernel])
     want = lao.adjoint_truth(cs, w_energy, dL_dz, compat=bool(compat))
     for name in ("z0", "Y", "shape", "pml"):
         err = np.linalg.norm(got[name] - want[name]) / np.linalg.norm(want[name])
         assert err < 1e-4, (name, err)
-    if kernel == "r1":
+    if kernel != "generic":
         gen = run(emu.emu_latent_adjoint)
         for name in ("z0", "Y", "shape", "pml"):
             err = np.linalg.norm(got[name] - gen[name]) / np.linalg.norm(gen[name])
@@ -207,7 +210,7 @@ def test_emulated_adjoint_kernel_matches_autograd(emu, compat, kernel, n, nt, kn
 def test_emulated_adjoint_r1_many_steps_and_segments(emu, compat):
     """More steps than one table of source factors holds (chunk switches in reverse order), several segments of C (the
     register accumulators of dL/dY are flushed at every segment change), energy cotangent only."""
-    n, steps = 33, 520
+    n, steps = 34, 520
     cs = make_case(n=n, batch=1, steps=steps, nseq=5, seed=4)
     rng = np.random.default_rng(5)
     z = lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"])
@@ -221,15 +224,17 @@ def test_emulated_adjoint_r1_many_steps_and_segments(emu, compat):
         fn(C.byref(p), 64)
         return g
 
-    got, gen = run(emu.emu_latent_adjoint_r1), run(emu.emu_latent_adjoint)
-    for name in ("z0", "Y", "shape", "pml"):
-        err = np.linalg.norm(got[name] - gen[name]) / np.linalg.norm(gen[name])
-        assert err < 5e-5, (name, err)
-        assert np.linalg.norm(gen[name]) > 0
+    gen = run(emu.emu_latent_adjoint)
+    for fn in (emu.emu_latent_adjoint_r1, emu.emu_latent_adjoint_r2):
+        got = run(fn)
+        for name in ("z0", "Y", "shape", "pml"):
+            err = np.linalg.norm(got[name] - gen[name]) / np.linalg.norm(gen[name])
+            assert err < 5e-5, (name, err)
+            assert np.linalg.norm(gen[name]) > 0
 
 
 def test_kernels_are_race_free_under_thread_sanitizer():
-    """The five latent kernels under the host emulation, built with -fsanitize=thread: ThreadSanitizer orders accesses by
+    """The six latent kernels under the host emulation, built with -fsanitize=thread: ThreadSanitizer orders accesses by
     the barriers (vector clocks, independent of timing), so a missing __syncthreads() between a shared-memory write and a
     neighbour's read is reported even if the interleaving that breaks it never happens in this run."""
     src = os.path.join(ROOT, "tests", "emu", "latent_tsan_main.cpp")

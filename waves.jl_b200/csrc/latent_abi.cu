@@ -279,12 +279,17 @@ extern "C" int waves_latent_adjoint(waves_latent *h, int batch, int steps, int n
         dev_out(h, 12, dL_dshape, n * batch, &p.g_shape) || dev_out(h, 13, dL_dpml, n * batch, &p.g_pml))
         return 1;
     if (p.g_Y) LCU(cudaMemsetAsync(p.g_Y, 0, sizeof(float) * n * nseq * batch, h->stream));
-    if (fast)
+    const bool pair = fast && h->pair_forward && (h->n % 2) == 0 && h->n >= 4;  // PAIR | ADJ_R1: two elements per thread
+    if (pair)
+        LCU(cudaFuncSetAttribute(k_latent_adjoint_r2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_ADJ1_SMEM(n)));
+    else if (fast)
         LCU(cudaFuncSetAttribute(k_latent_adjoint_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_ADJ1_SMEM(n)));
     else
         LCU(cudaFuncSetAttribute(k_latent_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAT_ADJ_SMEM(n)));
     LCU(cudaEventRecord(h->ev0, h->stream));
-    if (fast)
+    if (pair)
+        k_latent_adjoint_r2<<<batch, threads_for(h->n / 2), LAT_ADJ1_SMEM(n), h->stream>>>(p);
+    else if (fast)
         k_latent_adjoint_r1<<<batch, threads_for(h->n), LAT_ADJ1_SMEM(n), h->stream>>>(p);
     else
         k_latent_adjoint<<<batch, threads_for(h->n), LAT_ADJ_SMEM(n), h->stream>>>(p);

@@ -1168,3 +1168,323 @@ LAT_GLOBAL void k_latent_adjoint_r1(LatentP p) {
         if (p.g_pml) p.g_pml[(size_t)b * n + i] = p.pml_scale * gsig;
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Pair variant of the register reverse kernel (opt-in: WAVES_LATENT_PAIR | WAVES_LATENT_ADJ_R1): k_latent_adjoint_r1 with
+// two adjacent elements per thread as float2 and packed f32x2 arithmetic, as k_latent_integrate_r2 does for the forward
+// pass.  n even, 4 <= n <= 1024.  NOT YET RUN ON A B200; equal to the generic reverse kernel (to float32 rounding) under the
+// host emulation, race-free under ThreadSanitizer.
+LAT_GLOBAL2 void k_latent_adjoint_r2(LatentP p) {
+    LAT_SMEM
+    const int n = p.n, tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, e0 = 2 * tid, half = n >> 1;
+    const int T = p.steps + 1, N = p.steps;
+    float *ZA = (float *)lat_smem, *ZB = ZA + 4 * n;
+    float *Y2 = ZB + 4 * n, *Y3 = Y2 + 4 * n, *Y4 = Y3 + 4 * n;
+    float *PA = Y4 + 4 * n, *PB = PA + 4 * n;
+    float *shs = PB + 4 * n, *Xs = shs + n, *fcs = Xs + LAT_FAST_NSEQ;
+    const bool act = tid < half;
+    const float *Yb = p.Y + (size_t)b * p.nseq * n;
+    float *gY = p.g_Y ? p.g_Y + (size_t)b * p.nseq * n : nullptr;
+    const lf2 zero2 = lf2_bc(0.0f);
+
+    lf2 sg = zero2, sown = zero2;
+    if (act) {
+        if (p.shape) sown = lf2_mk(p.shape[(size_t)b * n + e0], p.shape[(size_t)b * n + e0 + 1]);
+        *(lf2 *)&shs[e0] = sown;
+        sg = lf2_mul(lf2_bc(p.pml_scale), lf2_mk(p.pml[(size_t)b * n + e0], p.pml[(size_t)b * n + e0 + 1]));
+    }
+    for (int k = tid; k < p.nseq; k += nt) Xs[k] = p.X[(size_t)b * p.nseq + k];
+    LAT_SYNC();
+    bool mono = true;
+    for (int k = 0; k + 1 < p.nseq; ++k) mono = mono && (Xs[k] < Xs[k + 1]);
+    const float rend = Xs[p.nseq - 1];
+
+    const bool first = act && tid == 0, last = act && tid == half - 1;
+    const int iL = e0 > 0 ? e0 - 1 : 0, iR = e0 + 2 < n ? e0 + 2 : n - 1;
+    const lf2 sN = act ? lf2_mk(shs[iL], shs[iR]) : zero2;
+    const int wlo = tid & ~31;
+    const bool edge_warp = wlo == 0 || (wlo <= half - 1 && half - 1 < wlo + 32);
+    const lf2 A0 = lf2_mk(first ? p.gf[0] : p.gc[0], last ? p.gl[0] : p.gc[0]);
+    const lf2 A1 = lf2_mk(first ? p.gf[1] : p.gc[1], last ? p.gl[1] : p.gc[1]);
+    const lf2 A2 = lf2_mk(first ? p.gf[2] : 0.0f, last ? p.gl[2] : 0.0f);
+    const lf2 bcv = lf2_mk(first ? 0.0f : 1.0f, last ? 0.0f : 1.0f);
+    const lf2 g0 = lf2_bc(p.gc[0]), g1 = lf2_bc(p.gc[1]), c02 = lf2_bc(p.c0);
+    auto grad = [&](lf2 Nn, lf2 O) -> lf2 {  // (∇ * v) at the two elements, as in k_latent_integrate_r2
+        if (!edge_warp) return lf2_add(lf2_mul(g0, lf2_mk(Nn.x, O.x)), lf2_mul(g1, lf2_mk(O.y, Nn.y)));
+        const lf2 X0 = lf2_mk(first ? O.x : Nn.x, last ? Nn.x : O.x);
+        const lf2 X1 = lf2_mk(O.y, last ? O.x : Nn.y);
+        const lf2 X2 = lf2_mk(Nn.y, O.y);
+        const lf2 two = lf2_add(lf2_mul(A0, X0), lf2_mul(A1, X1));
+        const lf2 thr = lf2_add(two, lf2_mul(A2, X2));
+        return lf2_mk(first ? thr.x : two.x, last ? thr.y : two.y);
+    };
+    auto rhs = [&](const float *S, lf2 a, float fs, const lf2 own[4], lf2 k[4]) {
+        if (!act) return;
+        const float *Ut = S, *Vt = S + n, *Ui = S + 2 * n, *Vi = S + 3 * n;
+        const lf2 fs2 = lf2_bc(fs);
+        const lf2 fN = lf2_mul(sN, fs2), fO = lf2_mul(sown, fs2);
+        const lf2 gVt = grad(lf2_mk(Vt[iL], Vt[iR]), own[1]);
+        const lf2 gUt = grad(lf2_add(lf2_mk(Ut[iL], Ut[iR]), fN), lf2_add(own[0], fO));
+        const lf2 gVi = grad(lf2_mk(Vi[iL], Vi[iR]), own[3]);
+        const lf2 gUi = grad(lf2_add(lf2_mk(Ui[iL], Ui[iR]), fN), lf2_add(own[2], fO));
+        k[0] = lf2_mul(lf2_sub(lf2_mul(a, gVt), lf2_mul(sg, own[0])), bcv);
+        k[1] = lf2_sub(lf2_mul(a, gUt), lf2_mul(sg, own[1]));
+        k[2] = lf2_mul(lf2_sub(lf2_mul(c02, gVi), lf2_mul(sg, own[2])), bcv);
+        k[3] = lf2_sub(lf2_mul(gUi, c02), lf2_mul(sg, own[3]));
+    };
+    // transposed rows: (∇ᵀ w)[j] = gc0 w[j+1] (row j+1 central) + gc1 w[j-1] (row j-1 central) + gf[j] w[0] (j <= 2)
+    //                              + gl[j-(n-3)] w[n-1] (j >= n-3); per-thread coefficient pairs make the edge form branch-free
+    auto tcoef = [&](int j, float &ta, float &tb, float &tf, float &tl) {
+        ta = (j + 1 >= 1 && j + 1 <= n - 2) ? p.gc[0] : 0.0f;
+        tb = (j - 1 >= 1 && j - 1 <= n - 2) ? p.gc[1] : 0.0f;
+        tf = (j >= 0 && j <= 2) ? p.gf[j] : 0.0f;
+        tl = (j >= n - 3 && j <= n - 1) ? p.gl[j - (n - 3)] : 0.0f;
+    };
+    float ta0, tb0, tf0, tl0, ta1, tb1, tf1, tl1;
+    tcoef(act ? e0 : 3, ta0, tb0, tf0, tl0);
+    tcoef(act ? e0 + 1 : 3, ta1, tb1, tf1, tl1);
+    const lf2 TA = lf2_mk(ta0, ta1), TB = lf2_mk(tb0, tb1), TF = lf2_mk(tf0, tf1), TL = lf2_mk(tl0, tl1);
+    const bool edge_t = wlo == 0 || wlo + 31 >= half - 2;  // warps holding elements 0,1,2 or n-3,n-2,n-1
+    auto gradT = [&](const float *Q, lf2 O) -> lf2 {       // O = this thread's own pair of Q
+        const lf2 Nn = lf2_mk(Q[iL], Q[iR]);
+        if (!edge_t) return lf2_add(lf2_mul(g0, lf2_mk(O.y, Nn.y)), lf2_mul(g1, lf2_mk(Nn.x, O.x)));
+        const lf2 inner2 = lf2_add(lf2_mul(TA, lf2_mk(O.y, Nn.y)), lf2_mul(TB, lf2_mk(Nn.x, O.x)));
+        return lf2_add(inner2, lf2_add(lf2_mul(TF, lf2_bc(Q[0])), lf2_mul(TL, lf2_bc(Q[n - 1]))));
+    };
+
+    int kcur = 0, kreg = -1;
+    lf2 yk = zero2, yk1 = zero2;
+    float lc = 1.0f, rc = 0.0f;
+    auto query = [&](float t, lf2 &c, int &kseg, float &w) {
+        kseg = -1;
+        w = 0.0f;
+        c = zero2;
+        if (!act) return;
+        if (!mono) {
+            c = lf2_mk(lat_speed_elem(p, Xs, Yb, t, e0), lat_speed_elem(p, Xs, Yb, t, e0 + 1));
+            return;
+        }
+        if (!(lc <= t && t < rc)) {
+            while (kcur + 2 < p.nseq && t >= Xs[kcur + 1]) ++kcur;
+            while (kcur > 0 && t < Xs[kcur]) --kcur;
+            const float l = Xs[kcur], r = Xs[kcur + 1];
+            if (!lat_mask(l, r, rend, t)) {
+                c = lf2_bc(p.c0 * (0.0f + (t - 0.0f) * 0.0f));
+                return;
+            }
+            if (kreg != kcur) {
+                yk = lf2_mk(Yb[(size_t)kcur * n + e0], Yb[(size_t)kcur * n + e0 + 1]);
+                yk1 = lf2_mk(Yb[(size_t)(kcur + 1) * n + e0], Yb[(size_t)(kcur + 1) * n + e0 + 1]);
+                lc = l;
+                rc = r;
+                kreg = kcur;
+            }
+        }
+        const float dd = (rc - t) - (lc - t), x0 = 0.0f + lc;
+        const lf2 dy = lf2_sub(yk1, yk);
+        const lf2 dydx = lf2_add(zero2, lf2_mk(dy.x / dd, dy.y / dd));
+        c = lf2_mul(c02, lf2_add(lf2_add(zero2, yk), lf2_mul(lf2_bc(t - x0), dydx)));
+        kseg = kreg;
+        w = (t - x0) / dd;
+    };
+
+    int kacc = -1;
+    lf2 gYa = zero2, gYb = zero2;
+    auto flush_gy = [&]() {
+        if (gY && act && kacc >= 0) {
+            gY[(size_t)kacc * n + e0] += gYa.x;
+            gY[(size_t)kacc * n + e0 + 1] += gYa.y;
+            gY[(size_t)(kacc + 1) * n + e0] += gYb.x;
+            gY[(size_t)(kacc + 1) * n + e0 + 1] += gYb.y;
+        }
+        gYa = zero2;
+        gYb = zero2;
+    };
+    auto add_gy = [&](lf2 cbar, float t, int kseg, float w) {
+        if (!gY || !act) return;
+        if (!mono) {
+            float x0 = 0.0f;
+            for (int k = 0; k + 1 < p.nseq; ++k)
+                if (lat_mask(Xs[k], Xs[k + 1], rend, t)) x0 = x0 + Xs[k];
+            for (int k = 0; k + 1 < p.nseq; ++k) {
+                const float l = Xs[k], r = Xs[k + 1];
+                if (lat_mask(l, r, rend, t)) {
+                    const float wk = (t - x0) / ((r - t) - (l - t));
+                    gY[(size_t)k * n + e0] += cbar.x * (1.0f - wk);
+                    gY[(size_t)k * n + e0 + 1] += cbar.y * (1.0f - wk);
+                    gY[(size_t)(k + 1) * n + e0] += cbar.x * wk;
+                    gY[(size_t)(k + 1) * n + e0 + 1] += cbar.y * wk;
+                }
+            }
+            return;
+        }
+        if (kseg < 0) return;
+        if (kseg != kacc) {
+            flush_gy();
+            kacc = kseg;
+        }
+        gYa = lf2_add(gYa, lf2_mul(cbar, lf2_bc(1.0f - w)));
+        gYb = lf2_add(gYb, lf2_mul(cbar, lf2_bc(w)));
+    };
+
+    lf2 lam[4], zr[4];
+    for (int f = 0; f < 4; ++f) lam[f] = zr[f] = zero2;
+    lf2 gshp = zero2, gsig = zero2;
+    auto add_cotangent = [&](int idx, const lf2 zv[4]) {
+        if (!act) return;
+        if (p.w_energy) {
+            const float w0 = p.w_energy[((size_t)b * 3 + 0) * T + idx], w1 = p.w_energy[((size_t)b * 3 + 1) * T + idx];
+            const float w2 = p.w_energy[((size_t)b * 3 + 2) * T + idx];
+            const lf2 d = lf2_sub(zv[0], zv[2]), k2 = lf2_bc(2.0f * p.dx);
+            lam[0] = lf2_add(lam[0], lf2_mul(k2, lf2_add(lf2_mul(lf2_bc(w0), zv[0]), lf2_mul(lf2_bc(w2), d))));
+            lam[2] = lf2_add(lam[2], lf2_mul(k2, lf2_sub(lf2_mul(lf2_bc(w1), zv[2]), lf2_mul(lf2_bc(w2), d))));
+        }
+        if (p.dL_dz)
+            for (int f = 0; f < 4; ++f) {
+                const float *src = p.dL_dz + (((size_t)idx * p.batch + b) * 4 + f) * n + e0;
+                lam[f] = lf2_add(lam[f], lf2_mk(src[0], src[1]));
+            }
+    };
+    auto load_state = [&](int idx) {
+        if (!act) return;
+        const float *zi = p.zt + ((size_t)idx * p.batch + b) * 4 * n + e0;
+        for (int f = 0; f < 4; ++f) zr[f] = lf2_mk(zi[(size_t)f * n], zi[(size_t)f * n + 1]);
+    };
+    lf2 po[4];  // this thread's own pairs of the products last written by put_products
+    for (int f = 0; f < 4; ++f) po[f] = zero2;
+    auto put_products = [&](float *P, lf2 a, const lf2 kb[4]) {
+        if (!act) return;
+        po[0] = lf2_mul(lf2_mul(a, bcv), kb[0]);
+        po[1] = lf2_mul(a, kb[1]);
+        po[2] = lf2_mul(bcv, kb[2]);
+        po[3] = kb[3];
+        for (int f = 0; f < 4; ++f) *(lf2 *)&P[f * n + e0] = po[f];
+    };
+    auto vjp = [&](const float *S, const float *Pin, float fs, float t, int kseg, float w, const lf2 kb[4], lf2 yb[4]) {
+        if (!act) return;
+        const lf2 tq = gradT(Pin, po[0]);          // ∇ᵀ(a ⊙ bc ⊙ w_Utot)
+        const lf2 tp = gradT(Pin + n, po[1]);      // ∇ᵀ(a ⊙ w_Vtot)
+        const lf2 ts = gradT(Pin + 2 * n, po[2]);  // ∇ᵀ(bc ⊙ w_Uinc)
+        const lf2 tr = gradT(Pin + 3 * n, po[3]);  // ∇ᵀ(w_Vinc)
+        yb[0] = lf2_sub(tp, lf2_mul(lf2_mul(sg, bcv), kb[0]));
+        yb[1] = lf2_sub(tq, lf2_mul(sg, kb[1]));
+        yb[2] = lf2_sub(lf2_mul(c02, tr), lf2_mul(lf2_mul(sg, bcv), kb[2]));
+        yb[3] = lf2_sub(lf2_mul(c02, ts), lf2_mul(sg, kb[3]));
+        const lf2 Ut = *(const lf2 *)&S[e0], Vt = *(const lf2 *)&S[n + e0], Ui = *(const lf2 *)&S[2 * n + e0],
+                  Vi = *(const lf2 *)&S[3 * n + e0];
+        const lf2 fs2 = lf2_bc(fs);
+        if (p.g_shape) gshp = lf2_add(gshp, lf2_mul(lf2_add(tp, lf2_mul(c02, tr)), fs2));
+        if (p.g_pml) {
+            const lf2 a0 = lf2_mul(lf2_mul(bcv, kb[0]), Ut), a1 = lf2_mul(kb[1], Vt);
+            const lf2 a2 = lf2_mul(lf2_mul(bcv, kb[2]), Ui), a3 = lf2_mul(kb[3], Vi);
+            gsig = lf2_sub(gsig, lf2_add(lf2_add(a0, a1), lf2_add(a2, a3)));
+        }
+        if (gY) {
+            const lf2 fN = lf2_mul(sN, fs2), fO = lf2_mul(sown, fs2);
+            const lf2 gVt = grad(lf2_mk(S[n + iL], S[n + iR]), Vt);
+            const lf2 gUt = grad(lf2_add(lf2_mk(S[iL], S[iR]), fN), lf2_add(Ut, fO));
+            const lf2 cbar = lf2_mul(c02, lf2_add(lf2_mul(lf2_mul(bcv, kb[0]), gVt), lf2_mul(kb[1], gUt)));
+            add_gy(cbar, t, kseg, w);
+        }
+    };
+
+    if (!p.compat) {
+        load_state(N);
+        add_cotangent(N, zr);
+    }
+    const float dt = p.dt, hdt = p.hdt, sixth = 1.0f / 6.0f;
+    const lf2 hdt2 = lf2_bc(hdt), dt2 = lf2_bc(dt);
+    const lf2 w4 = lf2_bc(sixth * dt), w23 = lf2_bc(2.0f * sixth * dt);
+    const int istart = p.compat ? N : N - 1;
+    int it = 0;
+    for (int s = istart; s >= 0; --s, ++it) {
+        float *Z = (it & 1) ? ZB : ZA;
+        load_state(s);
+        if (p.compat) add_cotangent(s, zr);
+        if (s == istart || (s % LAT_CH) == LAT_CH - 1) {
+            const int c0s = (s / LAT_CH) * LAT_CH;
+            float *fw = fcs + ((s / LAT_CH) & 1) * 3 * LAT_CH;
+            for (int q = tid; q < 3 * LAT_CH; q += nt) {
+                const int st = c0s + q / 3, w = q - 3 * (q / 3);
+                if (st <= s) {
+                    const float ts = p.tspan[(size_t)b * T + st];
+                    fw[q] = p.shape ? lat_sin_factor(w == 0 ? ts : (w == 1 ? ts + hdt : ts + dt), p.freq) : 0.0f;
+                }
+            }
+        }
+        const float t0 = p.tspan[(size_t)b * T + s], t1 = t0 + hdt, t2 = t0 + dt;
+        lf2 cA, cB, cC;
+        float wA, wB, wC;
+        int kA, kB, kC;
+        query(t2, cC, kC, wC);
+        query(t1, cB, kB, wB);
+        query(t0, cA, kA, wA);
+        if (act)
+            for (int f = 0; f < 4; ++f) *(lf2 *)&Z[f * n + e0] = zr[f];
+        LAT_SYNC();
+        const float *fc = fcs + ((s / LAT_CH) & 1) * 3 * LAT_CH + 3 * (s % LAT_CH);
+        const float f0 = fc[0], f1 = fc[1], f2 = fc[2];
+
+        lf2 k[4], ys[4], kb[4], yb[4], zsum[4];
+        for (int f = 0; f < 4; ++f) k[f] = ys[f] = kb[f] = yb[f] = zsum[f] = zero2;
+        rhs(Z, cA, f0, zr, k);
+        for (int f = 0; f < 4; ++f) {
+            ys[f] = lf2_add(zr[f], lf2_mul(hdt2, k[f]));
+            if (act) *(lf2 *)&Y2[f * n + e0] = ys[f];
+        }
+        LAT_SYNC();
+        rhs(Y2, cB, f1, ys, k);
+        for (int f = 0; f < 4; ++f) {
+            ys[f] = lf2_add(zr[f], lf2_mul(hdt2, k[f]));
+            if (act) *(lf2 *)&Y3[f * n + e0] = ys[f];
+        }
+        LAT_SYNC();
+        rhs(Y3, cB, f1, ys, k);
+        for (int f = 0; f < 4; ++f) {
+            ys[f] = lf2_add(zr[f], lf2_mul(dt2, k[f]));
+            if (act) *(lf2 *)&Y4[f * n + e0] = ys[f];
+            kb[f] = lf2_mul(w4, lam[f]);
+        }
+        put_products(PA, cC, kb);
+        LAT_SYNC();
+        vjp(Y4, PA, f2, t2, kC, wC, kb, yb);
+        for (int f = 0; f < 4; ++f) {
+            zsum[f] = yb[f];
+            kb[f] = lf2_add(lf2_mul(w23, lam[f]), lf2_mul(dt2, yb[f]));
+        }
+        put_products(PB, cB, kb);
+        LAT_SYNC();
+        vjp(Y3, PB, f1, t1, kB, wB, kb, yb);
+        for (int f = 0; f < 4; ++f) {
+            zsum[f] = lf2_add(zsum[f], yb[f]);
+            kb[f] = lf2_add(lf2_mul(w23, lam[f]), lf2_mul(hdt2, yb[f]));
+        }
+        put_products(PA, cB, kb);
+        LAT_SYNC();
+        vjp(Y2, PA, f1, t1, kB, wB, kb, yb);
+        for (int f = 0; f < 4; ++f) {
+            zsum[f] = lf2_add(zsum[f], yb[f]);
+            kb[f] = lf2_add(lf2_mul(w4, lam[f]), lf2_mul(hdt2, yb[f]));
+        }
+        put_products(PB, cA, kb);
+        LAT_SYNC();
+        vjp(Z, PB, f0, t0, kA, wA, kb, yb);
+        for (int f = 0; f < 4; ++f) lam[f] = lf2_add(lam[f], lf2_add(zsum[f], yb[f]));
+        if (!p.compat) add_cotangent(s, zr);
+    }
+    flush_gy();
+    if (act) {
+        for (int f = 0; f < 4; ++f) {
+            p.g_z0[((size_t)b * 4 + f) * n + e0] = lam[f].x;
+            p.g_z0[((size_t)b * 4 + f) * n + e0 + 1] = lam[f].y;
+        }
+        if (p.g_shape) {
+            p.g_shape[(size_t)b * n + e0] = gshp.x;
+            p.g_shape[(size_t)b * n + e0 + 1] = gshp.y;
+        }
+        if (p.g_pml) {
+            p.g_pml[(size_t)b * n + e0] = p.pml_scale * gsig.x;
+            p.g_pml[(size_t)b * n + e0 + 1] = p.pml_scale * gsig.y;
+        }
+    }
+}
