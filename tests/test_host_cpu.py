@@ -133,3 +133,73 @@ def test_prepare_data_mirror_matches_restatement():
         assert np.array_equal(t[i], to[i]) and np.array_equal(y[i], yo[i])
         assert a[i] == list(range(i, i + horizon)) and s[i] is ep.s[i]
         assert np.all(np.diff(t[i]) > 0)
+
+
+# ---- static check of the (never executed) Julia shim against the ctypes binding that IS exercised -------------------------
+_JL_TYPES = {"Int32": C.c_int32, "UInt32": C.c_uint32, "Float32": C.c_float, "Ptr{Float32}": C.POINTER(C.c_float)}
+
+
+def _julia_struct(src, name):
+    body = re.search(r"struct %s\n(.*?)\nend" % name, src, re.S).group(1)
+    fields = []
+    for decl in re.split(r"[;\n]", body):
+        decl = decl.split("#")[0].strip()
+        if decl:
+            fname, ftype = [x.strip() for x in decl.split("::")]
+            fields.append((fname, _JL_TYPES[ftype]))
+    return fields
+
+
+def _split_top(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "({":
+            depth += 1
+        elif ch in ")}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_shim_matches_the_ctypes_binding():
+    """waves.jl_b200/julia/WavesB200.jl cannot run here (no Julia).  Its struct layouts and every ccall signature are
+    compared with waves.jl_b200/_lib.py, whose structures and argument lists are exercised by the GPU tests."""
+    from waves_b200 import _lib
+    src = open(os.path.join(ROOT, "waves.jl_b200", "julia", "WavesB200.jl")).read()
+    for jl_name, ct in (("WavesConfig", _lib.WavesConfig), ("LatentConfig", _lib.LatentConfig)):
+        got = _julia_struct(src, jl_name)
+        want = [(n, t) for n, t in ct._fields_]
+        assert [n for n, _ in got] == [n for n, _ in want], jl_name
+        for (n, tj), (_, tc) in zip(got, want):
+            assert C.sizeof(tj) == C.sizeof(tc) and (tj is tc or issubclass(tj, C._Pointer) == issubclass(tc, C._Pointer)), (jl_name, n)
+
+    kinds = {"Cint": "i32", "Cfloat": "f32", "Cstring": "str", "Ptr{Cvoid}": "ptr", "Ptr{Float32}": "ptr", "Ptr{Int32}": "ptr",
+             "Ref{Ptr{Cvoid}}": "ptr", "Ref{WavesConfig}": "ptr", "Ref{LatentConfig}": "ptr", "Int64": "i64"}
+
+    def ckind(t):
+        if t in (C.c_int, C.c_int32):
+            return "i32"
+        if t is C.c_float:
+            return "f32"
+        if t is C.c_int64:
+            return "i64"
+        if t is C.c_char_p:
+            return "str"
+        return "ptr"      # c_void_p and POINTER(...)
+
+    calls = re.findall(r"ccall\(\(:(waves_[a-z0-9_]+),\s*[\w.]+\),\s*(\w+),\s*\((.*?)\),?\s*\n?\s*(?:h\.ptr|h_lib|cfg|\))", src, re.S)
+    seen = set()
+    for name, ret, args in calls:
+        res, argtypes = _lib.SYMBOLS[name]
+        jl_args = [a for a in _split_top(args.replace("\n", " ")) if a]
+        assert [kinds[a] for a in jl_args] == [ckind(t) for t in argtypes], (name, jl_args)
+        assert kinds[ret] == ckind(res), name
+        seen.add(name)
+    assert {"waves_create", "waves_integrate", "waves_adjoint", "waves_set_design", "waves_observe", "waves_latent_create",
+            "waves_latent_integrate", "waves_latent_adjoint"} <= seen, seen
