@@ -275,3 +275,11 @@ def test_latent_oracle_matches_reference_vectors():
     ref_z, ref_e = ref[: B * 4 * n].reshape(B, 4, n), ref[B * 4 * n:].reshape(B, 3, steps + 1)
     rel = lambda a, b: np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64))  # noqa: E731
     assert rel(z[-1], ref_z) < 1e-4 and rel(e, ref_e) < 1e-4
+
+
+def test_randomized_agreement_of_all_kernels(emu):
+    """A slice of scripts/fuzz_latent_emu.py: random sizes, thread counts, knot layouts, modes -- the three forward kernels
+    equal the oracle bit for bit, the register reverse kernels equal the generic one to float32 rounding."""
+    r = subprocess.run([os.sys.executable, os.path.join(ROOT, "scripts", "fuzz_latent_emu.py"), "7", "16"], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
