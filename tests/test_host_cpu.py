@@ -203,3 +203,34 @@ def test_julia_shim_matches_the_ctypes_binding():
         seen.add(name)
     assert {"waves_create", "waves_integrate", "waves_adjoint", "waves_set_design", "waves_observe", "waves_latent_create",
             "waves_latent_integrate", "waves_latent_adjoint"} <= seen, seen
+
+
+def test_header_is_c99_and_the_library_links_from_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/waves_b200.h must compile as C99 (cgo / ccall / JNI hosts) and a plain C
+    program must link against the library and get error codes -- not exceptions -- back."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "waves_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = tmp_path / "abi_link.c"
+    src.write_text(r'''
+#include "waves_b200.h"
+#include <stdio.h>
+#include <string.h>
+int main(void) {
+    waves_latent_config lc; waves_latent *lh = 0; waves_config c; waves_handle *h = 0; int rc1, rc2;
+    memset(&lc, 0, sizeof lc); memset(&c, 0, sizeof c);
+    lc.n = 16;
+    rc1 = waves_latent_create(&lc, &lh);
+    printf("%d|%s\n", rc1, waves_last_error());
+    rc2 = waves_create(&c, &h);
+    printf("%d|%s\n", rc2, waves_last_error());
+    return (waves_version() == WAVES_B200_VERSION && rc1 != 0 && rc2 != 0 && !lh && !h) ? 0 : 1;
+}
+''')
+    exe = tmp_path / "abi_link"
+    libdir = os.path.join(ROOT, "waves.jl_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), "-o", str(exe), str(src), "-L" + libdir,
+                           "-lwaves_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "waves_latent_create" in out.stdout and "waves_create" in out.stdout
