@@ -15,6 +15,7 @@ cs = make_case(n=1024, batch=148, steps=steps, nseq=steps // 100 + 1, seed=1)
 th = cs["theta"]
 it = wb.LatentIntegrator(wb.LatentDynamics(wb.OneDim(cs["dim"].x), 1531.0, 10.0, 10000.0), cs["dt"])
 theta = [wb.LinearInterpolation(th.X, th.Y), wb.LatentSource(th.shape, th.freq), th.pml]
+it.set_variant(int(os.environ.get("LAT_VARIANT", 0)))   # 0 defaults, 2 pair forward, 4 register reverse, 6 pair reverse
 last, e = it(cs["z0"], cs["tspan"], theta, want_z=False, want_energy=True)
 print("fwd ms", it.last_kernel_ms())
 if os.environ.get("LAT_ONLY_FWD"):
