@@ -216,6 +216,8 @@ float waves_mean_diff(const float *x, int n);
  *     shape (n, batch), freq: F = Source(shape, freq) (src/sources.jl:10-23); shape == NULL -> no source
  *     pml (n, batch): θ[3]; σ = dyn.pml[[1]] .* pml
  *     z (n, 4, batch, steps+1)     energy (steps+1, 3, batch) {tot, inc, sc}
+ * Same conventions as above: 0 / non-zero return codes with waves_last_error(), no CPU path, a handle is not thread-safe,
+ * every call synchronises the handle's stream before it returns (all outputs are complete on return).
  */
 typedef struct waves_latent waves_latent;
 typedef struct waves_latent_config {

@@ -126,7 +126,6 @@ class LatentIntegrator:
         last = None if want_z else np.empty((batch, 4, self.n), F32)
         check(_lib.lib().waves_latent_integrate(self._h, batch, steps, nseq, _ptr(z0), _ptr(tspan), _ptr(X), _ptr(Y),
                                                 _ptr(shape), C.c_float(freq), _ptr(pml), _ptr(z), _ptr(e), _ptr(last)))
-        self._keep = (z0, tspan, X, Y, shape, pml)
         out = z if want_z else last
         return (out, e) if (want_energy or out_energy is not None) else out
 
