@@ -244,7 +244,7 @@ def test_kernels_are_race_free_under_thread_sanitizer():
         pytest.skip("ThreadSanitizer runtime not available")
     subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=thread", "-ffp-contract=off", "-o", exe, src])
     for args in (["70", "96", "6", "1"], ["65", "96", "5", "0"], ["200", "64", "4", "1"], ["130", "160", "5", "0"],
-                 ["33", "64", "300", "1"]):
+                 ["33", "64", "300", "1"], ["34", "64", "300", "1"]):
         r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr + r.stdout, (args, (r.stderr + r.stdout)[-2000:])
 
