@@ -118,6 +118,8 @@ class LatentIntegrator:
         compute_latent_energy(z, dx) [batch][3][time] (src/model/acoustic_energy_model.jl:6-15).  With want_z=False the
         trajectory never reaches HBM and only the energies (and the last state) come back."""
         z0, tspan = self._f32(z0), self._f32(tspan)
+        if getattr(tspan, "ndim", 2) == 1:   # iter(ui, tspan::AbstractVector, θ) = iter(ui, tspan[:, :], θ), src/dynamics.jl:51-53
+            tspan = np.ascontiguousarray(np.broadcast_to(np.asarray(tspan, F32)[None, :], (int(z0.shape[0]), len(tspan))))
         X, Y, shape, freq, pml = self._theta(theta)
         batch, steps, nseq = int(z0.shape[0]), int(tspan.shape[1]) - 1, int(X.shape[1])
         assert tuple(z0.shape) == (batch, 4, self.n) and tuple(Y.shape) == (batch, nseq, self.n)
