@@ -133,6 +133,7 @@ int waves_integrate(waves_handle *h, const float *tspan, int steps, int mode, fl
  *   dL_dz0     out, (n_env, 12, ny, nx)               dL_dc    out, nullable, (n_env, ny, nx): sensitivity to the speed
  *              plane of the total field (a time-constant perturbation, accumulated over every RK stage; the hard cylinder
  *              mask of src/designs.jl:99-104 has no derivative, so no design-parameter gradient exists in the reference)
+ *              With dL_dc == NULL the forward stage states are not recomputed: 4 instead of 7 launches per reverse step.
  *   loss       out, nullable, HOST (n_env): the energy part of L
  *   fwd_mode   WAVES_MODE_FUSED / WAVES_MODE_EXACT for the forward pass;  adj_mode  WAVES_ADJ_EXACT / WAVES_ADJ_COMPAT
  * Not available on slab handles.

@@ -799,15 +799,20 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
         if (sp && !(design_static && b2_ready))
             for (int tau = 0; tau < 3; ++tau) launch_speed2(h, 0, gp.n_env, h->d_stage, rows, i, tau == 0 ? 0 : (tau == 1 ? 1 : 3), B2[tau]);
         b2_ready = true;
-        float *saved_b2 = h->b2;
-        // forward stage states y1, y2, y3 (k4 is not needed): y_s = z + a k(y_{s-1}) in one launch each
-        for (int s = 0; s < 3; ++s) {
-            h->b2 = B2[s == 0 ? 0 : 1];
-            launch_rhs_exact(h, 0, gp.n_env, s == 0 ? z : Y[s - 1], Y[s], h->d_stage, rows, i, s, z, s == 2 ? dt : hdt);
-        }
-        h->b2 = saved_b2;
-        const float *b0 = sp ? B2[0] : nullptr, *b1 = sp ? B2[1] : nullptr, *b2p = sp ? B2[2] : nullptr;
         float *gc = dL_dc ? GC : nullptr;
+        // forward stage states y1, y2, y3 (k4 is not needed): y_s = z + a k(y_{s-1}) in one launch each.  The dynamics are
+        // linear in the state, so J^T does not depend on them: only the dL/dc term reads them (k_rhs_transposed touches `y`
+        // under `gcacc` only).  Without dL/dc -- the gradient the reference itself can produce, its mask has no derivative --
+        // a reverse step is the four transposed right-hand sides alone.
+        if (gc) {
+            float *saved_b2 = h->b2;
+            for (int s = 0; s < 3; ++s) {
+                h->b2 = B2[s == 0 ? 0 : 1];
+                launch_rhs_exact(h, 0, gp.n_env, s == 0 ? z : Y[s - 1], Y[s], h->d_stage, rows, i, s, z, s == 2 ? dt : hdt);
+            }
+            h->b2 = saved_b2;
+        }
+        const float *b0 = sp ? B2[0] : nullptr, *b1 = sp ? B2[1] : nullptr, *b2p = sp ? B2[2] : nullptr;
         // each launch forms its cotangent on the fly (a w + b λ_y of the previous stage), returns λ_y = J^T(.) and keeps the
         // running sum WS = w + λ_y3 + λ_y2 + λ_y1 + λ_z; LK / LY alternate as the λ_y buffers
         launch_rhs_transposed(h, s6, W, 0.0f, nullptr, Y[2], b2p, LY, WS, 1, gc);  // λ_k4 = dt/6 w           -> λ_y3 = J4^T λ_k4
