@@ -37,6 +37,15 @@ for mode, name in ((wb.ADJ_EXACT, "exact"), (wb.ADJ_COMPAT, "compat")):
     res[name] = {"seconds": round(dt, 3), "Gcell_updates_per_s_fwd_plus_rev": round(2 * E * n * n * steps / dt / 1e9, 3),
                  "launches": eng.launch_count() - l0, "loss": float(loss[0]), "norm_dL_dc": float(gc.norm().item()),
                  "finite": bool(torch.isfinite(gc).all().item() and torch.isfinite(gz).all().item())}
+# dL/dz0 only (the reference-equivalent gradient): no forward-stage recomputation, 4 launches per reverse step
+for rep in range(2):
+    eng.set_state(z0)
+    l0 = eng.launch_count()
+    t0 = time.perf_counter()
+    loss, gz, _ = eng.adjoint(ts, w, adj_mode=wb.ADJ_EXACT, out_dz0=gz_d, want_dc=False)
+    dt = time.perf_counter() - t0
+res["exact_z0_only"] = {"seconds": round(dt, 3), "Gcell_updates_per_s_fwd_plus_rev": round(2 * E * n * n * steps / dt / 1e9, 3),
+                        "launches": eng.launch_count() - l0, "finite": bool(torch.isfinite(gz).all().item())}
 print(json.dumps({"workload": f"{E} x 700^2, triple-ring design frozen, {steps} steps, L = sum_t E_sc(t): forward (fused) + reverse sweep",
                   **res}))
 eng.close()
