@@ -73,6 +73,11 @@ typedef struct waves_config {
 } waves_config;
 
 int waves_version(void);
+/* 0 for the release library.  WAVES_BUILD_DEV: a developer build (-DWAVES_DEV) that honours the WAVES_DEBUG_* environment
+ * switches (tile sizes, launch order, skipped kernel variants); benchmarks must refuse it.  The release build reads no
+ * environment variable at all. */
+#define WAVES_BUILD_DEV 1
+int waves_build_flags(void);
 const char *waves_last_error(void);
 
 /* AcousticDynamics + Integrator + WaveEnv state allocation (src/dynamics.jl:141-149, src/env.jl:52-66). */
@@ -255,17 +260,19 @@ int64_t waves_latent_launch_count(waves_latent *h);
 /* on != 0: always run the generic shared-memory kernels (any n that fits) instead of the register fast path taken for
  * n <= 1024 and nseq <= 64; both are bit-identical, the switch exists so tests can compare them */
 int waves_latent_set_generic(waves_latent *h, int on);
-/* Kernel variants of the latent path (flags, OR-ed).  The default (AUTO) is what has been measured on a B200: the register
- * fast path of the forward pass where it applies (n <= 1024, nseq <= 64), the generic kernels otherwise and for the reverse
- * pass.  GENERIC (exclusive): as waves_latent_set_generic(h, 1).  PAIR: forward pass with two elements per thread and packed
- * f32x2 arithmetic (n even, 4 <= n <= 1024).  ADJ_R1: reverse pass with the register kernel (n <= 1024, nseq <= 64);
- * PAIR | ADJ_R1: its two-elements-per-thread form.
- * PAIR and ADJ_R1 are bit-identical / equal to rounding under the host emulation of the kernels but were written after the
- * round's GPU budget was spent: opt-in until timed. */
+/* Kernel variants of the latent path (flags, OR-ed).  Every variant is green on the B200 (tests/test_gpu_zlatent.py) and timed
+ * (profiles/r2_latent_bench.jsonl).  AUTO, the default, takes the fastest measured kernel that applies:
+ *   forward  n <= 1024, nseq <= 64: two elements per thread, packed f32x2 (n even; 2.9 us per RK4 step at 148 x 1024), else one
+ *            element per thread (3.0 us); otherwise the generic shared-memory kernel.  All three are bit-identical.
+ *   reverse  same conditions: the register kernels (pair form 7.6 us per step, single 9.4 us); otherwise the generic kernel (15.5).
+ * GENERIC (exclusive): as waves_latent_set_generic(h, 1).  The other flags select kernels explicitly (tests, benchmarks):
+ * SINGLE: one element per thread in the forward pass, generic reverse kernel unless ADJ_R1 is also given;
+ * PAIR: forward pair kernel; ADJ_R1: register reverse kernel, in its pair form with PAIR | ADJ_R1. */
 #define WAVES_LATENT_AUTO 0
 #define WAVES_LATENT_GENERIC 1
 #define WAVES_LATENT_PAIR 2
 #define WAVES_LATENT_ADJ_R1 4
+#define WAVES_LATENT_SINGLE 8
 int waves_latent_set_variant(waves_latent *h, int variant);
 /* device time (ms, CUDA events on the handle's stream) of the kernel of the last integrate / adjoint call */
 float waves_latent_last_kernel_ms(waves_latent *h);

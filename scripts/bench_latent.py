@@ -37,7 +37,7 @@ for batch, steps in ((32, 100), (148, 300), (1184, 300), (148, 2000)):
                      ("energy_only_pair_variant", dict(want_z=False, want_energy=True))):
         if name == "trajectory" and batch * steps > 148 * 300:
             continue
-        it.set_variant(wb.LATENT_PAIR if name.endswith("pair_variant") else wb.LATENT_AUTO)
+        it.set_variant(wb.LATENT_PAIR if name.endswith("pair_variant") else wb.LATENT_SINGLE)
         ms = []
         for _ in range(4):
             t = time.perf_counter()
@@ -51,7 +51,7 @@ for batch, steps in ((32, 100), (148, 300), (1184, 300), (148, 2000)):
     if batch * steps <= 148 * 300:
         z = it(cs["z0"], cs["tspan"], theta)
         wE = np.ones((batch, 3, steps + 1), F32)
-        for name, variant in (("adjoint", wb.LATENT_AUTO), ("adjoint_register_variant", wb.LATENT_ADJ_R1),
+        for name, variant in (("adjoint", wb.LATENT_SINGLE), ("adjoint_register_variant", wb.LATENT_SINGLE | wb.LATENT_ADJ_R1),
                               ("adjoint_register_pair_variant", wb.LATENT_ADJ_R1 | wb.LATENT_PAIR)):
             it.set_variant(variant)
             for _ in range(3):

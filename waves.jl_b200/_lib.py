@@ -51,6 +51,7 @@ class LatentConfig(C.Structure):
 # every symbol include/waves_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "waves_version": (C.c_int, []),
+    "waves_build_flags": (C.c_int, []),
     "waves_last_error": (C.c_char_p, []),
     "waves_create": (C.c_int, [C.POINTER(WavesConfig), C.POINTER(C.c_void_p)]),
     "waves_destroy": (C.c_int, [C.c_void_p]),

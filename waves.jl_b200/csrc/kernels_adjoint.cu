@@ -177,7 +177,7 @@ __global__ void k_energy_cotangent(GridP gp, const float *__restrict__ z, float 
 
 void launch_rhs_transposed(waves_handle *h, float a, const float *w, float b, const float *lyp, const float *y, const float *b2,
                            float *out, float *ws, int first, float *gcacc) {
-    static const int bx = getenv("WAVES_DEBUG_ADJ_BX") ? atoi(getenv("WAVES_DEBUG_ADJ_BX")) : 64;  // developer tuning aid (measured: 64 x 4 tiles)
+    static const int bx = waves_dev_env("WAVES_DEBUG_ADJ_BX", 64);  // developer tuning aid (measured: 64 x 4 tiles)
     dim3 blk(bx, 256 / bx), grd((h->gp.nx + bx - 1) / bx, (h->gp.ny_own + blk.y - 1) / blk.y, h->gp.n_env * 2);
     k_rhs_transposed<<<grd, blk, 0, h->stream>>>(h->gp, a, w, b, lyp, y, b2, out, ws, first, gcacc);
     h->launches++;

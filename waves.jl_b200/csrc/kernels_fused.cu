@@ -1054,8 +1054,8 @@ int fused_prepare(waves_handle *h) {
     if (ri1 > own1) ri1 = own1;
     // rows per slab: tall slabs amortise the 8 halo + 8 fill/drain rows, but keep >= ~8 waves of warps in flight; a single
     // environment is latency-bound by the march length, so short slabs (more, redundant, warps) win there
-    static const int seg_cap = getenv("WAVES_DEBUG_SEGCAP") ? atoi(getenv("WAVES_DEBUG_SEGCAP")) : 192;  // developer tuning aid
-    static const int seg_div = getenv("WAVES_DEBUG_SEGDIV") ? atoi(getenv("WAVES_DEBUG_SEGDIV")) : 14000;
+    static const int seg_cap = waves_dev_env("WAVES_DEBUG_SEGCAP", 192);  // developer tuning aid
+    static const int seg_div = waves_dev_env("WAVES_DEBUG_SEGDIV", 14000);
     const int SEG = std::max(16, std::min(seg_cap, (int)(2LL * gp.ny_own * (long long)cols.size() * gp.n_env / seg_div)));
     auto add_rows = [&](int a, int b, bool interior) {
         if (b <= a) return;
@@ -1208,7 +1208,7 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     A.dt6kd = A.dt6 * A.kd;
     A.plane = (unsigned)h->gp.plane;
     A.nxp = (unsigned)h->gp.nxp;
-    static const int dbg_flags = getenv("WAVES_DEBUG_FLAGS") ? atoi(getenv("WAVES_DEBUG_FLAGS")) : 0;
+    static const int dbg_flags = waves_dev_env("WAVES_DEBUG_FLAGS", 0);
     A.dbg = dbg_flags;
     A.cull = (dbg_flags & 4) ? 0 : 1;
     // Where sigma_x (sigma_y) is zero, Psix/Psiy/Omega (the fields whose RHS carries that factor, src/dynamics.jl:172-174) never
@@ -1223,7 +1223,7 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
         A.peer_dj[sd] = h->peer_dj[sd];
     }
     const bool lean = A.skip_aux && !(dbg_flags & 128);
-    static const int dbg_skip = getenv("WAVES_DEBUG_SKIP") ? atoi(getenv("WAVES_DEBUG_SKIP")) : 0;  // developer bisecting aid
+    static const int dbg_skip = waves_dev_env("WAVES_DEBUG_SKIP", 0);  // developer bisecting aid
     if (h->profile) cudaEventRecord(h->ev0, h->stream);
     if (h->peer_on) {
         // step n may start once both neighbours have finished step n-1: they no longer read the ghost rows this step's
@@ -1247,7 +1247,7 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     if (fork) cudaEventRecord(p->ev_fork, h->stream);
     // the interior kernel goes first: the CTAs of the (forked) PML kernels then fill its tail (measured: 1201 -> 1124 us per
     // step against launching the small kernels first)
-    static const int order_flag = getenv("WAVES_DEBUG_ORDER") ? atoi(getenv("WAVES_DEBUG_ORDER")) : 1;  // developer tuning aid
+    static const int order_flag = waves_dev_env("WAVES_DEBUG_ORDER", 1);  // developer tuning aid
     for (int vi = 0; vi < 4; ++vi) {
         const int v = order_flag ? vi : 3 - vi;
         const int n = p->off[v + 1] - p->off[v];

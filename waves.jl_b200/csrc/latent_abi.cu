@@ -116,6 +116,7 @@ extern "C" int waves_latent_create(const waves_latent_config *cfg, waves_latent 
 
     waves_latent *h = new waves_latent();
     memset(h, 0, sizeof(*h));
+    h->pair_forward = h->fast_adjoint = 1;  // WAVES_LATENT_AUTO
     h->device = cfg->device;
     h->n = cfg->n;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
@@ -262,7 +263,7 @@ extern "C" int waves_latent_adjoint(waves_latent *h, int batch, int steps, int n
     if (!z || !tspan || !X || !Y || !pml || !dL_dz0) LFAIL("waves_latent_adjoint: z, tspan, X, Y, pml and dL_dz0 are required");
     if (!w_energy && !dL_dz) LFAIL("waves_latent_adjoint: need a cotangent (w_energy and/or dL_dz)");
     if (adj_mode != WAVES_ADJ_EXACT && adj_mode != WAVES_ADJ_COMPAT) LFAIL("waves_latent_adjoint: unknown adjoint mode %d", adj_mode);
-    const bool fast = h->fast_adjoint && !h->force_generic && h->n <= 1024 && nseq <= LAT_FAST_NSEQ;  // opt-in register kernel
+    const bool fast = h->fast_adjoint && !h->force_generic && h->n <= 1024 && nseq <= LAT_FAST_NSEQ;  // register kernels
     if (!fast && LAT_ADJ_SMEM(h->n) > (size_t)h->max_smem)
         LFAIL("waves_latent_adjoint: n = %d needs %zu bytes of shared memory per sample (limit %d)", h->n,
               (size_t)LAT_ADJ_SMEM(h->n), h->max_smem);
@@ -307,18 +308,20 @@ extern "C" int waves_latent_adjoint(waves_latent *h, int batch, int steps, int n
 extern "C" int waves_latent_set_generic(waves_latent *h, int on) {
     if (!h) LFAIL("waves_latent_set_generic: null handle");
     h->force_generic = on != 0;
-    if (on) h->pair_forward = h->fast_adjoint = 0;
+    h->pair_forward = h->fast_adjoint = on ? 0 : 1;  // off: back to WAVES_LATENT_AUTO
     return 0;
 }
 
 extern "C" int waves_latent_set_variant(waves_latent *h, int variant) {
     if (!h) LFAIL("waves_latent_set_variant: null handle");
-    const int known = WAVES_LATENT_GENERIC | WAVES_LATENT_PAIR | WAVES_LATENT_ADJ_R1;
-    if (variant < 0 || (variant & ~known) || ((variant & WAVES_LATENT_GENERIC) && variant != WAVES_LATENT_GENERIC))
+    const int known = WAVES_LATENT_GENERIC | WAVES_LATENT_PAIR | WAVES_LATENT_ADJ_R1 | WAVES_LATENT_SINGLE;
+    if (variant < 0 || (variant & ~known) || ((variant & WAVES_LATENT_GENERIC) && variant != WAVES_LATENT_GENERIC) ||
+        ((variant & WAVES_LATENT_SINGLE) && (variant & WAVES_LATENT_PAIR)))
         LFAIL("waves_latent_set_variant: bad variant flags %d", variant);
     h->force_generic = (variant & WAVES_LATENT_GENERIC) != 0;
-    h->pair_forward = (variant & WAVES_LATENT_PAIR) != 0;
-    h->fast_adjoint = (variant & WAVES_LATENT_ADJ_R1) != 0;
+    // AUTO = the fastest kernels measured on a B200 (profiles/r2_latent_bench.jsonl): the pair forms of both passes
+    h->pair_forward = variant == WAVES_LATENT_AUTO || (variant & WAVES_LATENT_PAIR) != 0;
+    h->fast_adjoint = variant == WAVES_LATENT_AUTO || (variant & WAVES_LATENT_ADJ_R1) != 0;
     return 0;
 }
 

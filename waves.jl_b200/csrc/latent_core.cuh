@@ -475,22 +475,25 @@ LAT_GLOBAL void k_latent_integrate_r1(LatentP p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Pair variant of the forward fast path (opt-in: waves_latent_set_variant(h, WAVES_LATENT_PAIR)): every thread owns TWO
-// adjacent elements held as float2 and the arithmetic is packed f32x2 (FADD2 / FMUL2: one issue slot per two elements --
+// Pair variant of the forward fast path (what WAVES_LATENT_AUTO selects for even n <= 1024): every thread owns TWO
+// adjacent elements held as float2 and the arithmetic is packed f32x2 (FADD2 / FFMA2: one issue slot per two elements --
 // the forward kernels are issue-bound, profiles/r1_latent_ncu_fastpath_summary.json), neighbours cost 8 LDS per two
 // elements instead of 16, stores are STS.64, and a barrier joins 16 warps instead of 32.  Multiplies and adds stay
-// separately rounded (the packed instructions ptxas emits are FMUL2 and FFMA2 with a unit multiplier or a zero addend,
-// both exact), so it is bit-identical to the other kernels.  127 registers at 512 threads: one sample per SM (at 64
-// registers two samples would share an SM, at the price of spills in the stage loop: to be decided by measurement).
-// n even, 4 <= n <= 1024.  NOT YET RUN ON A B200 (written after the round's GPU budget was spent); checked bit-exact under
-// the host emulation and race-free under ThreadSanitizer.
+// separately rounded (see lf2_mul below), so it is bit-identical to the other kernels: green on the B200
+// (tests/test_gpu_zlatent.py::test_pair_variant_forward_bit_exact), 2.89 against 3.01 us per RK4 step at 148 x 1024
+// (profiles/r2_latent_bench.jsonl), static SASS check in profiles/r2_latent_pair_sass_digest.json (scripts/sass_check_latent.py).
+// 127 registers at 512 threads: one sample per SM.  n even, 4 <= n <= 1024.
 #ifndef LAT_EMU
 typedef float2 lf2;
 #define LAT_GLOBAL2 __global__ __launch_bounds__(512, 1)
 LAT_DEV lf2 lf2_mk(float a, float b) { return make_float2(a, b); }
 LAT_DEV lf2 lf2_add(lf2 a, lf2 b) { return __fadd2_rn(a, b); }
 LAT_DEV lf2 lf2_sub(lf2 a, lf2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }  // a + (-b) == a - b in IEEE
-LAT_DEV lf2 lf2_mul(lf2 a, lf2 b) { return __fmul2_rn(a, b); }
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under --fmad=false (inline PTX included; seen on the
+// B200 as a 1-ulp difference).  The product is therefore formed as fma(a, b, -0.0) with the -0.0 read from constant memory:
+// exact (x + -0 == x for every x), opaque to ptxas, and an FFMA2 followed by an FADD2 cannot be contracted.
+__constant__ float2 lat_negzero = {-0.0f, -0.0f};
+LAT_DEV lf2 lf2_mul(lf2 a, lf2 b) { return __ffma2_rn(a, b, lat_negzero); }
 #else
 struct lf2 {
     float x, y;

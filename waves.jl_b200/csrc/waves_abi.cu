@@ -37,6 +37,13 @@ static int fail(const char *fmt, ...) {
 int waves_set_error(const char *msg) { return fail("%s", msg); }
 
 extern "C" int waves_version(void) { return WAVES_B200_VERSION; }
+extern "C" int waves_build_flags(void) {
+#ifdef WAVES_DEV
+    return WAVES_BUILD_DEV;
+#else
+    return 0;
+#endif
+}
 extern "C" const char *waves_last_error(void) { return g_err; }
 
 // ---------------------------------------------------------------------------------------------

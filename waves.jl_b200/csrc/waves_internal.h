@@ -6,6 +6,18 @@
 
 #include "../../include/waves_b200.h"
 
+// Developer tuning / bisecting switches exist only in -DWAVES_DEV builds (scripts/tune_build.sh).  The release library reads no
+// environment variable: a benchmarked .so cannot be made to skip work from outside (waves_build_flags() reports which build it is).
+#ifdef WAVES_DEV
+#include <stdlib.h>
+static inline int waves_dev_env(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+#else
+#define waves_dev_env(name, dflt) (dflt)
+#endif
+
 // Per-environment parameters of θ = [C, F] (src/env.jl:96-102), device-resident.
 struct EnvParams {
     int ncyl;        // 0 -> NoDesign

@@ -25,9 +25,9 @@ from ._lib import check
 from .engine import ADJ_COMPAT, ADJ_EXACT, _ptr
 from .host import F32, _fp, julia_range
 
-LATENT_AUTO, LATENT_GENERIC, LATENT_PAIR, LATENT_ADJ_R1 = 0, 1, 2, 4
+LATENT_AUTO, LATENT_GENERIC, LATENT_PAIR, LATENT_ADJ_R1, LATENT_SINGLE = 0, 1, 2, 4, 8
 
-__all__ = ["LATENT_AUTO", "LATENT_GENERIC", "LATENT_PAIR", "LATENT_ADJ_R1", "OneDim", "LinearInterpolation", "LatentSource", "LatentDynamics", "LatentIntegrator", "build_pml_1d", "ADJ_EXACT",
+__all__ = ["LATENT_AUTO", "LATENT_GENERIC", "LATENT_PAIR", "LATENT_ADJ_R1", "LATENT_SINGLE", "OneDim", "LinearInterpolation", "LatentSource", "LatentDynamics", "LatentIntegrator", "build_pml_1d", "ADJ_EXACT",
            "ADJ_COMPAT"]
 
 
@@ -106,6 +106,16 @@ class LatentIntegrator:
     def _f32(a):
         return a if (a is None or hasattr(a, "data_ptr")) else np.ascontiguousarray(a, F32)
 
+    def _tspan(self, tspan, batch):
+        """tspan [batch][time]; a vector is iter(ui, tspan::AbstractVector, θ) = iter(ui, tspan[:, :], θ) (src/dynamics.jl:51-53):
+        the same times for every batch element.  Host arrays and CUDA tensors alike."""
+        tspan = self._f32(tspan)
+        if tspan.ndim == 1:
+            if hasattr(tspan, "data_ptr"):
+                return tspan[None, :].expand(batch, -1).contiguous()
+            return np.ascontiguousarray(np.broadcast_to(tspan[None, :], (batch, len(tspan))))
+        return tspan
+
     def _theta(self, theta):
         Cint, Fsrc, pml = theta
         X, Y = self._f32(Cint.X), self._f32(Cint.Y)
@@ -117,9 +127,8 @@ class LatentIntegrator:
         """iter(z0, tspan, θ) (src/dynamics.jl:37-49) -> z [time][batch][4][n]; with want_energy also
         compute_latent_energy(z, dx) [batch][3][time] (src/model/acoustic_energy_model.jl:6-15).  With want_z=False the
         trajectory never reaches HBM and only the energies (and the last state) come back."""
-        z0, tspan = self._f32(z0), self._f32(tspan)
-        if getattr(tspan, "ndim", 2) == 1:   # iter(ui, tspan::AbstractVector, θ) = iter(ui, tspan[:, :], θ), src/dynamics.jl:51-53
-            tspan = np.ascontiguousarray(np.broadcast_to(np.asarray(tspan, F32)[None, :], (int(z0.shape[0]), len(tspan))))
+        z0 = self._f32(z0)
+        tspan = self._tspan(tspan, int(z0.shape[0]))
         X, Y, shape, freq, pml = self._theta(theta)
         batch, steps, nseq = int(z0.shape[0]), int(tspan.shape[1]) - 1, int(X.shape[1])
         assert tuple(z0.shape) == (batch, 4, self.n) and tuple(Y.shape) == (batch, nseq, self.n)
@@ -133,24 +142,27 @@ class LatentIntegrator:
 
     def adjoint(self, z, tspan, theta, w_energy=None, dL_dz=None, mode=ADJ_EXACT):
         """adjoint_sensitivity(iter, z, t, θ, ∂L_∂z) (src/dynamics.jl:97-118) -> dict(z0, Y, shape, pml)."""
-        z, tspan = self._f32(z), self._f32(tspan)
+        z = self._f32(z)
+        tspan = self._tspan(tspan, int(z.shape[1]))
         X, Y, shape, freq, pml = self._theta(theta)
         batch, steps, nseq = int(z.shape[1]), int(tspan.shape[1]) - 1, int(X.shape[1])
+        we, gz = self._f32(w_energy), self._f32(dL_dz)   # keep the converted copies alive across the call
         g = {"z0": np.empty((batch, 4, self.n), F32), "Y": np.empty((batch, nseq, self.n), F32),
              "shape": np.empty((batch, self.n), F32) if shape is not None else None, "pml": np.empty((batch, self.n), F32)}
         check(_lib.lib().waves_latent_adjoint(self._h, batch, steps, nseq, _ptr(z), _ptr(tspan), _ptr(X), _ptr(Y), _ptr(shape),
-                                              C.c_float(freq), _ptr(pml), int(mode), _ptr(self._f32(w_energy)),
-                                              _ptr(self._f32(dL_dz)), _ptr(g["z0"]), _ptr(g["Y"]), _ptr(g["shape"]),
+                                              C.c_float(freq), _ptr(pml), int(mode), _ptr(we),
+                                              _ptr(gz), _ptr(g["z0"]), _ptr(g["Y"]), _ptr(g["shape"]),
                                               _ptr(g["pml"])))
         return g
 
     def set_generic(self, on: bool):
-        """Force the generic shared-memory kernels (the register fast path is the default where it applies)."""
+        """Force the generic shared-memory kernels (the register fast paths are the default where they apply)."""
         check(_lib.lib().waves_latent_set_generic(self._h, int(bool(on))))
 
     def set_variant(self, variant: int):
-        """Flags: LATENT_AUTO (default: the kernels measured on a B200), LATENT_GENERIC, or any of LATENT_PAIR (forward kernel
-        with two elements per thread) | LATENT_ADJ_R1 (register reverse kernel) -- both opt-in until timed."""
+        """Flags: LATENT_AUTO (default: the fastest kernels measured on a B200 -- the pair forms of both passes), LATENT_GENERIC,
+        or an explicit choice: LATENT_SINGLE (one element per thread) / LATENT_PAIR (two) for the forward pass, | LATENT_ADJ_R1
+        for the register reverse kernel (otherwise the generic one)."""
         check(_lib.lib().waves_latent_set_variant(self._h, int(variant)))
 
     def last_kernel_ms(self) -> float:
