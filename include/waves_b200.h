@@ -46,6 +46,7 @@ typedef struct waves_handle waves_handle;
 /* adjoint modes (src/dynamics.jl:97-118) */
 #define WAVES_ADJ_EXACT 0  /* exact discrete adjoint  lambda_i = a_i + (I+J_i^T) lambda_{i+1} */
 #define WAVES_ADJ_COMPAT 1 /* the reference loop as written (one extra step-vjp) */
+#define WAVES_ADJ_STAGEWISE 0x100 /* OR into adj_mode: reverse sweep with the per-stage kernels even without dL_dc (cross-check) */
 
 /*
  * Mirrors AcousticDynamics(dim, c0, pml_width, pml_scale) (src/dynamics.jl:141-149)
@@ -124,27 +125,42 @@ int waves_step(waves_handle *h, float t, int mode);
  *                (env.wave = frames 80,90,100: src/env.jl:116)
  *   u_tot_traj / u_inc_traj  nullable (n_env, steps+1, ny, nx): the full U trajectories that
  *                (env::WaveEnv)(action) returns for rendering (src/env.jl:120, src/plot.jl:25)
+ *                With waves_set_traj_stride(h, k) they hold every k-th frame only: (n_env, steps / k + 1, ny, nx), frame 0 first
+ *                (what a renderer that shows a few frames per action needs, instead of 2 x 198 MB per action at 700^2).
  * The state of the handle is left at the last step.
+ * Fused mode replays the whole integration from a CUDA graph captured by the first call of the same shape (same steps, save
+ * steps, output buffers); frames / trajectories in pageable host memory disable that (use device or pinned buffers).
  */
 int waves_integrate(waves_handle *h, const float *tspan, int steps, int mode, float *energy, const int32_t *save_steps,
                     int nsave, float *frames, float *u_tot_traj, float *u_inc_traj);
+/* Decimation of the U trajectories of waves_integrate (stride >= 1, default 1: every frame; src/plot.jl:25 consumers). */
+int waves_set_traj_stride(waves_handle *h, int stride);
+/* on == 0: launch every kernel of waves_integrate directly instead of replaying a captured CUDA graph (default: on). */
+int waves_set_graph(waves_handle *h, int on);
 
 /*
  * rrule(::Integrator, z0, t, θ) + adjoint_sensitivity (src/dynamics.jl:97-128) for the 2-D dynamics: runs the forward
- * integration from the handle's current state (storing all steps+1 states on the device, like the reference), then the
- * reverse sweep.  The loss is
+ * integration from the handle's current state, then the reverse sweep.  The loss is
  *     L = sum_i sum_k w_energy[i][k] * E_k(z_i)  +  <dL_dzN, z_N>          E = {tot, inc, sc} of src/env.jl:104-111
  *   w_energy   HOST, nullable, (steps+1, 3)           dL_dzN   nullable, (n_env, 12, ny, nx) extra cotangent of the last state
  *   dL_dz0     out, (n_env, 12, ny, nx)               dL_dc    out, nullable, (n_env, ny, nx): sensitivity to the speed
  *              plane of the total field (a time-constant perturbation, accumulated over every RK stage; the hard cylinder
  *              mask of src/designs.jl:99-104 has no derivative, so no design-parameter gradient exists in the reference)
- *              With dL_dc == NULL the forward stage states are not recomputed: 4 instead of 7 launches per reverse step.
  *   loss       out, nullable, HOST (n_env): the energy part of L
  *   fwd_mode   WAVES_MODE_FUSED / WAVES_MODE_EXACT for the forward pass;  adj_mode  WAVES_ADJ_EXACT / WAVES_ADJ_COMPAT
+ * With dL_dc == NULL (the gradient the reference itself can produce) every reverse step is ONE fused launch set -- the
+ * dynamics are affine in the state, so the reverse step is an RK4 step of the transposed operator and needs no forward stage
+ * state -- and only the two U planes of each state are stored (for the energy cotangent).  With dL_dc the per-stage kernels
+ * run on fully stored states.  Storage: the reference keeps all steps+1 states; here the forward pass keeps a checkpoint per
+ * segment and the reverse sweep re-runs one segment at a time when steps+1 stored states do not fit in free device memory
+ * (waves_set_adjoint_checkpoint forces a segment length).  The handle is left at the last state z_N.
  * Not available on slab handles.
  */
 int waves_adjoint(waves_handle *h, const float *tspan, int steps, int fwd_mode, int adj_mode, const float *w_energy,
                   const float *dL_dzN, float *dL_dz0, float *dL_dc, float *loss);
+/* Segment length of the reverse pass: a checkpoint every `every` steps, the steps of one segment re-run and stored while the
+ * sweep crosses it.  0 (default): one segment when everything fits in free device memory, else about sqrt(steps * 6). */
+int waves_set_adjoint_checkpoint(waves_handle *h, int every);
 
 /*
  * RLBase.state(env) (src/env.jl:132-137): x = imresize(cat(env.wave[:, :, 1, :], env.source.shape; dims = 3), env.resolution).
@@ -156,7 +172,8 @@ int waves_adjoint(waves_handle *h, const float *tspan, int steps, int fwd_mode, 
  */
 int waves_observe(waves_handle *h, const float *frames, int nsave, int res_x, int res_y, float *out);
 
-/* tot/inc/sc energy of the current state (src/env.jl:104-111): e3 (n_env, 3). */
+/* tot/inc/sc energy of the current state (src/env.jl:104-111): e3 (n_env, 3).  A DEVICE e3 is written asynchronously on the
+ * handle's stream (no synchronisation: per-step energies of a slab run stay on the device until the end). */
 int waves_energy(waves_handle *h, float *e3);
 
 /* ---- slab decomposition (one process per GPU) ----------------------------------- */
@@ -280,6 +297,8 @@ float waves_latent_last_kernel_ms(waves_latent *h);
 /* ---- introspection for benchmarks -------------------------------------------------------- */
 /* number of kernel launches issued by this handle so far */
 int64_t waves_launch_count(waves_handle *h);
+/* number of waves_integrate calls that ran as ONE CUDA graph launch (capture + first launch included) */
+int64_t waves_graph_replays(waves_handle *h);
 /* average device time (ms) of the fused step kernel launches since the last reset, measured with
  * CUDA events on the handle's stream when profiling is on (waves_profile(h, 1)). */
 int waves_profile(waves_handle *h, int on);

@@ -95,3 +95,9 @@ def integrate(dyn, state, tspan, dt, dOmega, design0=None, design1=None, ti=0.0,
 
 def num_threads() -> int:
     return int(lib().wo_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the C restatement (torchrun exports OMP_NUM_THREADS=1: the reference arm of bench.py overrides it)."""
+    lib().wo_set_num_threads(C.c_int(int(n)))
+    return num_threads()

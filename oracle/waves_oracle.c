@@ -249,3 +249,12 @@ int wo_num_threads(void) {
     return 1;
 #endif
 }
+
+/* bench.py --impl reference: use every host core even when the launcher exported OMP_NUM_THREADS=1 (torchrun does) */
+void wo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

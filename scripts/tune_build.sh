@@ -12,6 +12,6 @@ while [ $# -ge 2 ]; do
   tag=$1; flags=$2; shift 2
   $NV $flags -Xptxas -v -c -o $OUT/fused_$tag.o kernels_fused.cu 2> $OUT/fused_$tag.ptxas.log
   $NV -c -o $OUT/abi_dev.o waves_abi.cu
-  $NV -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libwaves_b200_$tag.so kernels_exact.o kernels_adjoint.o $OUT/fused_$tag.o $OUT/abi_dev.o latent_abi.o -lcudart_static -lpthread -ldl -lrt
+  $NV -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libwaves_b200_$tag.so kernels_exact.o kernels_adjoint.o kernels_adjoint_fused.o $OUT/fused_$tag.o $OUT/abi_dev.o latent_abi.o -lcudart_static -lpthread -ldl -lrt
   echo "$tag: $(grep -E 'Used [0-9]+ registers' $OUT/fused_$tag.ptxas.log | head -4 | sed 's/ptxas info    : Used //; s/ registers.*//' | tr '\n' ' ')"
 done

@@ -16,9 +16,9 @@ def rel(a, b):
     return np.linalg.norm(np.asarray(a, np.float64) - b) / np.linalg.norm(b)
 
 
-def setup(n=48, steps=6, moving=True):
+def setup(n=48, steps=6, moving=True, pml_width=0.5):
     dim = wo.TwoDim.make(2.0, n)
-    dyn = wo.AcousticDynamics.make(dim, wo.WATER, 0.5, 20000.0)
+    dyn = wo.AcousticDynamics.make(dim, wo.WATER, pml_width, 20000.0)
     grid = wo.build_grid(dim)
     shape = wo.build_normal(grid, np.array([[-0.8, 0.2]]), np.array([0.2]), np.array([1.0]))
     pos = np.array([[0.4, 0.0], [-0.2, -0.7]], np.float32)

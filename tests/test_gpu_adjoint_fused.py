@@ -1,0 +1,145 @@
+"""Fused reverse step (kernels_adjoint_fused.cu) and checkpointed storage of waves_adjoint.
+
+Without dL/dc -- the gradient the reference itself can produce, its cylinder mask has no derivative -- a reverse step is one
+fused launch set: an RK4 step of the transposed operator on shared-memory tiles.  Checked against float64 autograd over the
+unrolled trajectory / the reference loop as written (oracle/adjoint_oracle.py), against the per-stage reverse kernels, by
+central finite differences of the loss computed on the GPU, and with every segment length of the checkpointed storage."""
+import numpy as np
+import pytest
+
+import waves_b200 as wb
+from oracle import adjoint_oracle as ao
+from test_gpu_adjoint import TOL, rel, setup
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+# n = 48: general tiles only (the zero-sigma zone is narrower than a tile); n = 200 with a thin PML: interior tiles, general
+# tiles and the seam between the two launches; n = 131: odd size, row pitch != nx, partial tiles
+@pytest.mark.parametrize("n,pml_width", [(48, 0.5), (200, 0.25), (131, 0.2)])
+@pytest.mark.parametrize("adj_mode", [wb.ADJ_EXACT, wb.ADJ_COMPAT])
+def test_fused_reverse_matches_autograd_and_per_stage_kernels(n, pml_width, adj_mode):
+    steps = 6 if adj_mode == wb.ADJ_EXACT else 5
+    p, eng, ts, z0, w, aN = setup(n=n, steps=steps, pml_width=pml_width)
+    L, gz, _, traj = ao.autograd_truth(p, z0, w, aN)
+    want = gz if adj_mode == wb.ADJ_EXACT else ao.reference_loop_torch(p, traj, w, aN)[0]
+    for fwd in (wb.MODE_EXACT, wb.MODE_FUSED):
+        eng.set_state(z0[None])
+        n0 = eng.launch_count()
+        loss, dz0, none = eng.adjoint(ts, w, aN[None], fwd_mode=fwd, adj_mode=adj_mode, want_dc=False)
+        assert none is None and rel(dz0[0], want) < TOL, (fwd, rel(dz0[0], want))
+        for f in range(12):
+            assert rel(dz0[0, f], want[f]) < 5 * TOL, f"field {f}"
+        assert abs(loss[0] - (L - float(np.sum(traj[-1] * aN)))) < 1e-4 * abs(L)
+        assert rel(eng.get_state(0), traj[-1]) < TOL
+    eng.set_state(z0[None])
+    _, dz_s, _ = eng.adjoint(ts, w, aN[None], fwd_mode=wb.MODE_FUSED, adj_mode=adj_mode, want_dc=False, fused_reverse=False)
+    assert rel(dz0[0], np.float64(dz_s[0])) < 1e-5
+    eng.close()
+
+
+@pytest.mark.parametrize("every", [1, 2, 3, 7])
+@pytest.mark.parametrize("want_dc", [False, True])
+def test_checkpointed_storage_gives_the_same_gradients(every, want_dc):
+    """7 steps in segments of 1, 2, 3 (uneven last segment) and 7 (one segment): checkpoints + re-run segments vs everything
+    stored.  The re-run starts from a restored state (full interior variant instead of the lean one), so equality is to
+    rounding, not bitwise."""
+    p, eng, ts, z0, w, aN = setup(n=200, steps=7, pml_width=0.25)
+    outs = []
+    for k in (0, every):
+        eng.set_adjoint_checkpoint(k)
+        eng.set_state(z0[None])
+        outs.append(eng.adjoint(ts, w, aN[None], fwd_mode=wb.MODE_FUSED, adj_mode=wb.ADJ_EXACT, want_dc=want_dc) + (eng.get_state(0),))
+    (l0, g0, c0, s0), (l1, g1, c1, s1) = outs
+    assert rel(g1[0], np.float64(g0[0])) < 2e-6 and abs(l1[0] - l0[0]) <= 1e-6 * abs(l0[0]) and np.array_equal(s0, s1)
+    if want_dc:
+        assert rel(c1[0], np.float64(c0[0])) < 2e-6
+    eng.close()
+
+
+def _env700(n_env=1, steps=500, src=(-3.5, 2.5)):
+    dim = wb.TwoDim(15.0, 700)
+    eng = wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 2.0, 20000.0, n_env=n_env)
+    eng.set_source(wb.build_normal(dim, [list(src)], [0.3], [1.0]), 1000.0)   # 4 m from the ring: scattering within the run
+    d0 = wb.build_triple_ring_design_space().rand(np.random.default_rng(0))
+    ts = wb.build_tspan(0.0, 1e-5, steps)
+    eng.set_design(d0.table(), d0.table(), ts[0], ts[-1])
+    return eng, ts
+
+
+def test_config5_full_size_fused_reverse_vs_per_stage_and_finite_differences():
+    """BASELINE configs[4]: 700^2, triple-ring design frozen, 500 steps, L = sum_t E_sc(t).
+    (i) dL/dz0 of the fused reverse sweep against the per-stage kernels in the reference's exact float32 order (forward and
+    reverse), relative L2 <= 1e-4; (ii) central finite differences of L along 10 random directions, L evaluated by the fused
+    forward pass on the GPU (L is quadratic in z0, so the central difference is exact up to float32 rounding of the energies)."""
+    import torch
+    steps = 500
+    eng, ts = _env700(steps=steps)
+    w = np.zeros((steps + 1, 3), F32)
+    w[:, 2] = 1.0
+    rng = np.random.default_rng(1)
+    z0 = np.zeros((1, 12, 700, 700), F32)
+    eng.set_state(z0)
+    loss, gz, _ = eng.adjoint(ts, w, want_dc=False)
+    eng.set_state(z0)
+    _, gz_e, _ = eng.adjoint(ts, w, fwd_mode=wb.MODE_EXACT, want_dc=False, fused_reverse=False)
+    err = rel(gz[0], np.float64(gz_e[0]))
+    print(f"config 5: dL/dz0 fused vs exact-order per-stage kernels: rel-L2 {err:.2e}, |g| = {np.linalg.norm(np.float64(gz[0])):.3e}, loss {loss[0]:.4e}")
+    assert loss[0] > 0 and np.isfinite(gz).all() and err < TOL
+
+    def L_of(z):
+        eng.set_state(z)
+        en, _ = eng.integrate(ts, wb.MODE_FUSED, energy=True)
+        return float(np.sum(np.float64(en[0]) * w))
+
+    g64 = np.float64(gz[0])
+    L0, u = float(loss[0]), 1e-6     # u: relative rounding of a float32 energy (per-warp float32 partial sums, float64 above)
+    yy, xx = np.mgrid[0:700, 0:700]
+    for k in range(10):
+        # smooth random direction in every field (a few random Gaussian bumps)
+        d = np.zeros((12, 700, 700), F32)
+        for f in range(12):
+            for _ in range(3):
+                cx, cy, s = rng.uniform(80, 620), rng.uniform(80, 620), rng.uniform(8, 40)
+                d[f] += rng.standard_normal() * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s)).astype(F32)
+        gd = float(np.sum(g64 * d))
+        # L(z0 + e d) = L0 + e <g, d> + e^2 q: a trial pair gives q, and e* = sqrt(L0 / q) balances the rounding of the two
+        # terms (error of the central difference ~ u (L0 + e^2 q) / e)
+        e1 = 1e-2
+        q = max((L_of((z0[0] + F32(e1) * d)[None]) + L_of((z0[0] - F32(e1) * d)[None]) - 2 * L0) / (2 * e1 * e1), 1e-30)
+        eps = float(np.sqrt(L0 / q))
+        fd = (L_of((z0[0] + F32(eps) * d)[None]) - L_of((z0[0] - F32(eps) * d)[None])) / (2.0 * float(F32(eps)))
+        bound = 1e-3 * abs(gd) + 4 * u * (L0 + eps * eps * q) / eps
+        print(f"  direction {k}: <g, d> = {gd:.6e}, central difference = {fd:.6e}, eps = {eps:.2e}, |diff| = {abs(fd - gd):.2e} (bound {bound:.2e})")
+        assert abs(fd - gd) < bound, (k, fd, gd, bound)
+    eng.close()
+
+
+def test_batched_gradients_with_checkpoints_at_full_size():
+    """8 x 700^2 x 120 steps with a checkpoint every 16 steps: every environment of the batch gets the gradient of the
+    single-environment run (environment 3 has its own design and source position)."""
+    steps = 120
+    eng, ts = _env700(n_env=8, steps=steps)
+    dim = wb.TwoDim(15.0, 700)
+    d3 = wb.build_triple_ring_design_space().rand(np.random.default_rng(3))
+    eng.set_design(d3.table(), d3.table(), ts[0], ts[-1], env=3)
+    eng.set_source(wb.build_normal(dim, [[-2.0, -3.0]], [0.3], [1.0]), 1000.0, env=3)
+    w = np.zeros((steps + 1, 3), F32)
+    w[:, 2] = 1.0
+    w[-1, 0] = 0.5
+    z0 = (np.random.default_rng(2).standard_normal((1, 12, 700, 700)) * 1e-4).astype(F32)
+    import torch
+    gz_d = torch.empty((8, 12, 700, 700), dtype=torch.float32, device="cuda:0")
+    eng.set_adjoint_checkpoint(16)
+    eng.set_state(np.repeat(z0, 8, 0))
+    loss, _, _ = eng.adjoint(ts, w, want_dc=False, out_dz0=gz_d)
+    g = gz_d.cpu().numpy()
+    one, ts1 = _env700(steps=steps)
+    one.set_state(z0)
+    l1, g1, _ = one.adjoint(ts1, w, want_dc=False)
+    for e in (0, 1, 2, 4, 5, 6, 7):
+        assert rel(g[e], np.float64(g1[0])) < 2e-6 and abs(loss[e] - l1[0]) <= 2e-6 * abs(l1[0]), e
+    assert rel(g[3], np.float64(g1[0])) > 1e-2 and np.isfinite(g).all()
+    one.close()
+    eng.close()

@@ -429,3 +429,84 @@ def test_randomized_fused_vs_exact_sweep():
     assert r.returncode == 0, r.stderr[-1500:]
     assert "FAIL" not in r.stdout and "worst" in r.stdout, r.stdout[-1500:]
     assert float(r.stdout.strip().splitlines()[-1].split()[1]) < 2e-5
+
+
+def test_graph_replay_equals_direct_launches(golden_dir):
+    """waves_integrate replays a captured CUDA graph on calls of the same shape: three consecutive env(action)-like calls
+    (moving design, shifting tspan, frames into a device buffer) must equal the directly launched run bit for bit, including
+    the first call after a state write (full interior variant) and a change of shape (re-capture)."""
+    import torch
+    g, dim, dyn = load_small(golden_dir)
+    outs = []
+    for graph in (True, False):
+        eng = make_engine(dim, dyn, dO=g["dOmega"])
+        eng.set_graph(graph)
+        eng.set_state(g["u0"][None])
+        eng.set_source(g["shape"], float(g["freq"]))
+        frames = torch.zeros((1, 2, 12, len(dim.y), len(dim.x)), dtype=torch.float32, device="cuda:0")
+        rec = []
+        for k, steps in enumerate((12, 12, 12, 8, 12)):
+            t0 = F32(12 * k) * F32(1e-5)
+            ts = wb.build_tspan(t0, 1e-5, steps)
+            eng.set_design(g["cyl0"] if k % 2 == 0 else g["cyl1"], g["cyl1"] if k % 2 == 0 else g["cyl0"], ts[0], ts[-1])
+            en, _ = eng.integrate(ts, wb.MODE_FUSED, energy=True, save_steps=[steps - 4, steps], frames=frames)
+            rec.append((en.copy(), frames.cpu().numpy().copy(), eng.get_state(0).copy()))
+            if k == 2:
+                eng.set_state(rec[0][2][None])   # a state write invalidates the constant-field shortcut (and the graph key)
+        outs.append((rec, eng.launch_count()))
+        eng.close()
+    for (ea, fa, ua), (eb, fb, ub) in zip(outs[0][0], outs[1][0]):
+        assert np.array_equal(ea, eb) and np.array_equal(fa, fb) and np.array_equal(ua, ub)
+    assert outs[0][1] == outs[1][1], "a replay must account for the launches it stands for"
+
+
+def test_decimated_trajectory_capture(golden_dir):
+    """U-only trajectories for renderers (src/plot.jl:25) with waves_set_traj_stride: every k-th frame, batch of 2 envs."""
+    g, dim, dyn = load_small(golden_dir)
+    ny, nx = len(dim.y), len(dim.x)
+    eng = make_engine(dim, dyn, n_env=2, dO=g["dOmega"])
+    eng.set_source(g["shape"], float(g["freq"]))
+    eng.set_design(g["cyl0"], g["cyl1"], g["tspan"][0], g["tspan"][-1], env=0)
+    ts = wb.build_tspan(0.0, 1e-5, 20)
+    u0 = np.stack([g["u0"], 0.5 * g["u0"]])
+    eng.set_state(u0)
+    full_t, full_i = np.empty((2, 21, ny, nx), F32), np.empty((2, 21, ny, nx), F32)
+    eng.integrate(ts, wb.MODE_FUSED, energy=False, u_tot=full_t, u_inc=full_i)
+    eng.set_state(u0)
+    eng.set_traj_stride(5)
+    dec_t, dec_i = np.empty((2, 5, ny, nx), F32), np.empty((2, 5, ny, nx), F32)
+    eng.integrate(ts, wb.MODE_FUSED, energy=False, u_tot=dec_t, u_inc=dec_i)
+    assert np.array_equal(dec_t, full_t[:, ::5]) and np.array_equal(dec_i, full_i[:, ::5])
+    assert np.array_equal(full_t[:, 0], u0[:, 0]) and np.array_equal(full_i[:, 0], u0[:, 6])
+    eng.close()
+
+
+def test_config2_twenty_actions_energy_trace():
+    """BASELINE configs[1] as written (scripts/data.jl:48-55): WaveEnv with the triple-ring design space and
+    RandomPosGaussianSource(x = -10, y ~ U[-10, 10]), 20 actions x 100 RK4 steps; the concatenated 2001 x 3 energy trace
+    (flatten_repeated_last_dim, src/utils.jl:20-31) and the final fields against the C restatement chained the same way.
+    Tolerance: the north star's 1e-4 relative L2 after all 2000 steps."""
+    n, steps, actions = 700, 100, 20
+    dimg, dimo = wb.TwoDim(15.0, n), wo.TwoDim.make(15.0, n)
+    dyn = wo.AcousticDynamics.make(dimo, wo.WATER, 2.0, 20000.0)
+    dO = F32(wo.get_dx(dimo) * wo.get_dy(dimo))
+    rng = np.random.default_rng(0)
+    ds = wb.build_triple_ring_design_space()
+    src = wb.RandomPosGaussianSource(dimg, [-10.0, -10.0], [-10.0, 10.0], [0.3], [1.0], 1000.0, rng=rng)
+    env = wb.WaveEnv(dimg, design_space=ds, source=src, integration_steps=steps, actions=actions, rng=rng)
+    as_cyl = lambda d: wo.Cylinders(d.table()[:, :2], d.table()[:, 2], d.table()[:, 3])
+    u = np.zeros((12, n, n), F32)
+    sig_g, sig_o = [], []
+    while not env.is_terminated():
+        d0 = env.design
+        ts, _, _, _ = env(env.action_space().rand(rng))
+        u, en, _ = co.integrate(dyn, u, ts, 1e-5, dO, as_cyl(d0), as_cyl(env.design), ts[0], ts[-1], shape=src.shape, freq=1000.0)
+        sig_g.append(env.signal)
+        sig_o.append(en)
+    sg, so = wo.flatten_repeated_last_dim(np.stack(sig_g)), wo.flatten_repeated_last_dim(np.stack(sig_o))
+    assert sg.shape == (actions * steps + 1, 3) and env.time_step == actions * steps
+    errs = [rel(sg[:, k], so[:, k]) for k in range(3)]
+    ferr = rel(env.wave[-1], u)
+    print(f"config 2: energy trace rel-L2 tot/inc/sc = {errs}, final fields {ferr:.2e}, replays {env.iter.engine.graph_replays()}")
+    assert so[-1, 2] > 0 and max(errs) < TOL and ferr < TOL
+    assert env.iter.engine.graph_replays() == actions, "every env(action) must run as one CUDA graph launch"

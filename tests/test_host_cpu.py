@@ -193,7 +193,9 @@ def test_julia_shim_matches_the_ctypes_binding():
             return "str"
         return "ptr"      # c_void_p and POINTER(...)
 
-    calls = re.findall(r"ccall\(\(:(waves_[a-z0-9_]+),\s*[\w.]+\),\s*(\w+),\s*\((.*?)\),?\s*\n?\s*(?:h\.ptr|h_lib|cfg|\))", src, re.S)
+    assert "ccall((:" not in src.split("module WavesB200")[1].replace("`ccall((:name, lib), ...)`", ""), \
+        "entry points are resolved with Libdl.dlsym (a (name, lib) pair must be a constant expression)"
+    calls = re.findall(r"ccall\(sym\(:(waves_[a-z0-9_]+)\),\s*(\w+),\s*\((.*?)\),?\s*\n?\s*(?:h\.ptr|h_lib|cfg|\))", src, re.S)
     seen = set()
     for name, ret, args in calls:
         res, argtypes = _lib.SYMBOLS[name]

@@ -289,3 +289,59 @@ def test_oracle_matches_reference_vectors(golden_dir):
     st, _, _ = co.integrate(dyn, u0, ts, 1e-5, F32(wo.get_dx(dim) * wo.get_dy(dim)), d0, d1, ts[0], ts[-1], shape=shape,
                             freq=1000.0)
     assert rel(st, np.fromfile(f_small, F32).reshape(12, n, n)) < 1e-4
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - b) / (np.linalg.norm(np.asarray(b, np.float64)) + 1e-300))
+
+
+# ---- second, structurally independent statement of the path (oracle/sparse_oracle.py): SciPy CSC matrix products and unfused
+# ---- float32 broadcasts in the reference's own (nx, ny, field) layout ---------------------------------------------------------
+def test_sparse_statement_small_design_matches_oracle(golden_dir):
+    """96^2, three cylinders (two overlapping) with moving radii, source, PML, random initial state, 40 steps: all 12 fields, the
+    right-hand side and the energy trace of the two independent statements agree to float32 accumulation-order noise."""
+    from oracle import sparse_oracle as so
+    g = np.load(os.path.join(golden_dir, "small_design_96.npz"))
+    dyn = so.Dynamics(g["grid_size"], int(g["n"]), g["c0"], g["pml_width"], g["pml_scale"])
+    assert np.array_equal(dyn.x, g["x"]) and np.array_equal(dyn.pml[:, 0], g["sigma"])
+    G = dyn.grad.toarray()
+    assert np.array_equal(np.concatenate([G[0, :3], G[5, [4, 6]], G[-1, -3:]]), g["grad8"])
+    shape = so.build_normal(dyn.grid, np.array([[-1.0, 0.2]]), [0.15], [1.0])
+    np.testing.assert_allclose(shape.T, g["shape"], rtol=2e-6, atol=1e-30)
+    ts, c0, c1 = g["tspan"], g["cyl0"], g["cyl1"]
+
+    def C(t):
+        d = so.design_at(t, c0, c1, ts[0], ts[-1])
+        return so.speed(d[:, :2], d[:, 2], d[:, 3], dyn.grid, dyn.c0)
+
+    theta = (C, so.source(np.ascontiguousarray(g["shape"].T), g["freq"]))
+    u0 = so.to_julia(g["u0"])
+    k = so.from_julia(dyn(u0, g["rhs_t"], theta))
+    assert rel(k, g["rhs"]) < 1e-6
+    sol = so.integrate(dyn, u0, ts, theta, g["dt"])
+    final, step1 = so.from_julia(sol[-1]), so.from_julia(sol[1])
+    assert rel(step1, g["step1"]) < 1e-6 and rel(final, g["final"]) < 1e-6
+    for f in range(12):
+        assert rel(final[f], g["final"][f]) < 2e-6, f
+    en = so.energies(sol, F32(np.mean(np.diff(dyn.x))), F32(np.mean(np.diff(dyn.y))))
+    assert np.abs(en - g["energy"]).max() / g["energy"].max() < 1e-6
+
+
+def test_sparse_statement_config1_matches_golden(golden_dir):
+    """BASELINE config 1 (TwoDim(15, 700), Gaussian source at (-10, 0), no design, 100 RK4 steps): the sparse-matrix statement
+    against the committed fixture of the stencil statement -- all 12 fields at 512 probe points after 1, 10 and 100 steps and
+    the 101 x 3 energy trace, <= 1e-6."""
+    from oracle import sparse_oracle as so
+    g = np.load(os.path.join(golden_dir, "config1_700.npz"))
+    dyn = so.Dynamics(15.0, 700, 1531.0, 2.0, 20000.0)
+    assert np.array_equal(dyn.x, g["x"])
+    shape = so.build_normal(dyn.grid, np.array([[-10.0, 0.0]]), [0.3], [1.0])
+    np.testing.assert_allclose(shape[:, 350], g["shape_row350"], rtol=2e-6, atol=1e-30)
+    theta = (lambda t: dyn.c0, so.source(shape, 1000.0))
+    sol = so.integrate(dyn, np.zeros((700, 700, 12), F32), g["tspan"], theta, 1e-5)
+    for s in (1, 10, 100):
+        got = so.from_julia(sol[s])[:, g["probe_j"], g["probe_i"]]
+        assert rel(got, g[f"probes_{s}"]) < 1e-6, s
+    en = so.energies(sol, F32(np.mean(np.diff(dyn.x))), F32(np.mean(np.diff(dyn.y))))
+    assert rel(en[:, 0], g["energy"][:, 0]) < 1e-6 and rel(en[:, 1], g["energy"][:, 1]) < 1e-6
+    assert np.all(en[:, 2] == 0)   # no design: both wavefields see identical inputs

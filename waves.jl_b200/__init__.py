@@ -10,7 +10,7 @@ from .env import AcousticDynamics, Integrator, WaveEnv
 from .data import (BatchWaveEnv, Episode, RandomDesignPolicy, flatten_repeated_last_dim, generate_episode, generate_episodes,
                    prepare_data)
 from .latent import LATENT_ADJ_R1, LATENT_AUTO, LATENT_GENERIC, LATENT_PAIR, LATENT_SINGLE, LatentDynamics, LatentIntegrator, LatentSource, LinearInterpolation, OneDim, build_pml_1d
-from .parallel import HaloExchanger, SlabEngine, shard_envs, slab_rows
+from .parallel import HaloExchanger, LocalSlabGroup, SlabEngine, shard_envs, slab_rows
 from .host import (AIR, WATER, Cloak, Cylinders, DesignInterpolator, DesignSpace, NoSource, RandomPosGaussianSource,
                    Source, TwoDim, build_action_space, build_gradient, build_grid, build_normal, build_pml,
                    build_radii_design_space, build_triple_ring_design_space, build_tspan, build_wave, get_dx, get_dy,

@@ -66,10 +66,13 @@ SYMBOLS = {
     "waves_step": (C.c_int, [C.c_void_p, C.c_float, C.c_int]),
     "waves_integrate": (C.c_int, [C.c_void_p, fp, C.c_int, C.c_int, C.c_void_p, ip, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
+    "waves_set_traj_stride": (C.c_int, [C.c_void_p, C.c_int]),
+    "waves_set_graph": (C.c_int, [C.c_void_p, C.c_int]),
     "waves_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "waves_energy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "waves_adjoint": (C.c_int, [C.c_void_p, fp, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    "waves_set_adjoint_checkpoint": (C.c_int, [C.c_void_p, C.c_int]),
     "waves_halo_describe": (C.c_int, [C.c_void_p, C.POINTER(HaloDesc)]),
     "waves_halo_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "waves_halo_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -94,6 +97,7 @@ SYMBOLS = {
     "waves_latent_set_generic": (C.c_int, [C.c_void_p, C.c_int]),
     "waves_latent_set_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "waves_launch_count": (C.c_int64, [C.c_void_p]),
+    "waves_graph_replays": (C.c_int64, [C.c_void_p]),
     "waves_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "waves_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }

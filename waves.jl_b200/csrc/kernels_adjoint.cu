@@ -160,14 +160,16 @@ __global__ void k_lin3(long long n, float *__restrict__ out, float a, const floa
     out[q] = v;
 }
 
-// w += dL/dz_i of the energy-weighted loss sum_k w3[k] E_k (src/env.jl:104-111): only the two U planes are touched
-__global__ void k_energy_cotangent(GridP gp, const float *__restrict__ z, float *__restrict__ w, float w_tot, float w_inc, float w_sc,
-                                   float d_omega) {
+// w += dL/dz_i of the energy-weighted loss sum_k w3[k] E_k (src/env.jl:104-111): only the two U planes are touched.
+// z: U_tot of environment e at z + e * z_env + q, U_inc at + z_inc (a full state, or the two gathered U planes).
+__global__ void k_energy_cotangent(GridP gp, const float *__restrict__ z, long long z_env, long long z_inc, float *__restrict__ w,
+                                   float w_tot, float w_inc, float w_sc, float d_omega) {
     const int e = blockIdx.z;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= gp.nx || j >= gp.ny_own) return;
+    const long long qz = (long long)e * z_env + (long long)j * gp.nxp + i;
     const long long q = (long long)e * gp.env_stride + (long long)j * gp.nxp + i;
-    const float ut = z[q], ui = z[q + 6 * gp.plane], d = ut - ui;
+    const float ut = z[qz], ui = z[qz + z_inc], d = ut - ui;
     const float two = 2.0f * d_omega;
     w[q] += two * (w_tot * ut + w_sc * d);
     w[q + 6 * gp.plane] += two * (w_inc * ui - w_sc * d);
@@ -189,8 +191,8 @@ void launch_lin3(waves_handle *h, float *out, float a, const float *x, float b, 
     h->launches++;
 }
 
-void launch_energy_cotangent(waves_handle *h, const float *z, float *w, const float *w3) {
+void launch_energy_cotangent(waves_handle *h, const float *z, long long z_env, long long z_inc, float *w, const float *w3) {
     dim3 blk(32, 8), grd((h->gp.nx + 31) / 32, (h->gp.ny_own + 7) / 8, h->gp.n_env);
-    k_energy_cotangent<<<grd, blk, 0, h->stream>>>(h->gp, z, w, w3[0], w3[1], w3[2], h->d_omega);
+    k_energy_cotangent<<<grd, blk, 0, h->stream>>>(h->gp, z, z_env, z_inc, w, w3[0], w3[1], w3[2], h->d_omega);
     h->launches++;
 }

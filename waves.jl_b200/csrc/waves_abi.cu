@@ -132,13 +132,20 @@ extern "C" float waves_mean_diff(const float *x, int n) {
 // ---------------------------------------------------------------------------------------------
 // Handle
 // ---------------------------------------------------------------------------------------------
+static void graph_drop(waves_handle *h) {
+    if (h->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
+    h->graph_exec = nullptr;
+}
+
 static void free_handle(waves_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int k = 0; k < 9; ++k)
         if (h->adj[k]) cudaFree(h->adj[k]);
+    graph_drop(h);
     if (h->traj) cudaFree(h->traj);
+    if (h->ckpt) cudaFree(h->ckpt);
     if (h->pconst) cudaFree(h->pconst);
     for (int sd = 0; sd < 2; ++sd)
         for (int k = 0; k < 3; ++k)
@@ -538,14 +545,14 @@ static int step_exact(waves_handle *h, int steps, int step) {
     return 0;
 }
 
-static int step_any(waves_handle *h, int steps, int step, int mode, float *d_e3) {
+static int step_any(waves_handle *h, int steps, int step, int mode, float *d_e3, int defer_slot = -1) {
     if (mode == WAVES_MODE_EXACT) {
         if (step_exact(h, steps, step)) return 1;
         if (d_e3) launch_energy(h, h->u[h->cur], d_e3, 3 * (steps + 1));
         return 0;
     }
     if (mode != WAVES_MODE_FUSED) return fail("unknown mode %d", mode);
-    return launch_fused_step(h, h->d_stage, steps, step, d_e3);
+    return launch_fused_step(h, h->d_stage, steps, step, d_e3, defer_slot);
 }
 
 extern "C" int waves_rhs(waves_handle *h, int env, float t, float *du12) {
@@ -626,10 +633,40 @@ extern "C" int waves_energy(waves_handle *h, float *e3) {
         CU_TRY(cudaMalloc((void **)&h->d_energy, sizeof(float) * 3 * 128 * (size_t)h->gp.n_env));
         h->energy_cap = 128;
     }
-    launch_energy(h, h->u[h->cur], h->d_energy, 3);
-    CU_TRY(cudaMemcpyAsync(e3, h->d_energy, sizeof(float) * 3 * h->gp.n_env, cudaMemcpyDefault, h->stream));
-    CU_TRY(cudaStreamSynchronize(h->stream));
+    cudaPointerAttributes at;
+    const bool out_dev = cudaPointerGetAttributes(&at, e3) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (out_dev) {  // device output: written by the kernel itself, asynchronous on the handle's stream (no host round trip)
+        launch_energy(h, h->u[h->cur], e3, 3);
+    } else {
+        launch_energy(h, h->u[h->cur], h->d_energy, 3);
+        CU_TRY(cudaMemcpyAsync(e3, h->d_energy, sizeof(float) * 3 * h->gp.n_env, cudaMemcpyDefault, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+    }
     CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Is `p` memory a captured CUDA graph may copy to / from asynchronously (device, managed or pinned host memory)?
+static bool graph_safe_ptr(const void *p) {
+    if (!p) return true;
+    cudaPointerAttributes at;
+    const bool ok = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    return ok;
+}
+
+extern "C" int waves_set_traj_stride(waves_handle *h, int stride) {
+    CHECK_H(h);
+    if (stride < 1) return fail("waves_set_traj_stride: stride must be >= 1");
+    h->traj_stride = stride;
+    return 0;
+}
+
+extern "C" int waves_set_graph(waves_handle *h, int on) {
+    CHECK_H(h);
+    h->graph_off = on ? 0 : 1;
+    if (!on) graph_drop(h);
     return 0;
 }
 
@@ -646,19 +683,25 @@ extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, i
     if (ensure_stage(h, steps) || flush_params(h)) return 1;
     if (energy && h->energy_cap < steps + 1) {
         CU_TRY(cudaStreamSynchronize(h->stream));
+        graph_drop(h);
         if (h->d_energy) cudaFree(h->d_energy);
         h->energy_cap = steps + 1 < 128 ? 128 : steps + 1;
         CU_TRY(cudaMalloc((void **)&h->d_energy, sizeof(float) * 3 * (size_t)h->energy_cap * gp.n_env));
     }
+    const bool fused = mode == WAVES_MODE_FUSED;
+    if (!fused && ensure_exact_scratch(h)) return 1;  // (allocations must not happen inside a stream capture)
     CU_TRY(cudaMemcpyAsync(h->d_tspan, tspan, sizeof(float) * (steps + 1), cudaMemcpyDefault, h->stream));
     launch_stage_table(h, h->d_tspan, steps, h->d_stage);
 
     const size_t frame_elems = (size_t)12 * gp.ny_own * gp.nx, plane_elems = (size_t)gp.ny_own * gp.nx;
+    const int stride = h->traj_stride > 0 ? h->traj_stride : 1;
+    const size_t traj_frames = (size_t)steps / stride + 1;
+    const bool dense = gp.nxp == gp.nx && gp.ny_alloc == gp.ny_own;
     int isave = 0;
     auto emit = [&](int frame) -> int {
         const float *u = h->u[h->cur];
         if (isave < nsave && save_steps[isave] == frame) {
-            if (gp.nxp == gp.nx && gp.ny_alloc == gp.ny_own) {
+            if (dense) {
                 // dense planes: one strided copy moves this frame of every environment
                 CU_TRY(cudaMemcpy2DAsync(frames + (size_t)isave * frame_elems, sizeof(float) * frame_elems * nsave, u,
                                          sizeof(float) * gp.env_stride, sizeof(float) * frame_elems, gp.n_env, cudaMemcpyDefault, h->stream));
@@ -670,13 +713,23 @@ extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, i
             }
             ++isave;
         }
-        for (int e = 0; e < gp.n_env; ++e) {
-            float *base = const_cast<float *>(u) + (size_t)e * gp.env_stride;
-            if (u_tot_traj && copy_plane(h, base, nullptr, u_tot_traj + ((size_t)e * (steps + 1) + frame) * plane_elems, 1))
-                return 1;
-            if (u_inc_traj &&
-                copy_plane(h, base + 6 * gp.plane, nullptr, u_inc_traj + ((size_t)e * (steps + 1) + frame) * plane_elems, 1))
-                return 1;
+        // U trajectories for renderers (src/plot.jl:25): every `stride`-th frame, one strided copy per field for all environments
+        if ((u_tot_traj || u_inc_traj) && frame % stride == 0) {
+            const size_t slot = (size_t)(frame / stride);
+            for (int f = 0; f < 2; ++f) {
+                float *dst = f == 0 ? u_tot_traj : u_inc_traj;
+                if (!dst) continue;
+                const float *src = u + (size_t)f * 6 * gp.plane;
+                if (dense) {
+                    CU_TRY(cudaMemcpy2DAsync(dst + slot * plane_elems, sizeof(float) * plane_elems * traj_frames, src,
+                                             sizeof(float) * gp.env_stride, sizeof(float) * plane_elems, gp.n_env, cudaMemcpyDefault, h->stream));
+                } else {
+                    for (int e = 0; e < gp.n_env; ++e)
+                        if (copy_plane(h, const_cast<float *>(src) + (size_t)e * gp.env_stride, nullptr,
+                                       dst + ((size_t)e * traj_frames + slot) * plane_elems, 1))
+                            return 1;
+                }
+            }
         }
         return 0;
     };
@@ -684,15 +737,78 @@ extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, i
     // The fused kernel reports the energies of the frame it READS (they ride on the row arrival), so frame n
     // comes out of step n and the last frame needs one stand-alone reduction; the exact path reports the frame
     // it wrote.
-    const bool fused = mode == WAVES_MODE_FUSED;
-    if (energy && !fused) launch_energy(h, h->u[h->cur], h->d_energy, 3 * (steps + 1));
-    if (emit(0)) return 1;
-    for (int n = 0; n < steps; ++n) {
-        float *d_e3 = energy ? h->d_energy + 3 * (size_t)(fused ? n : n + 1) : nullptr;
-        if (step_any(h, steps, n, mode, d_e3)) return 1;
-        if (emit(n + 1)) return 1;
-    }
-    if (energy && fused) launch_energy(h, h->u[h->cur], h->d_energy + 3 * (size_t)steps, 3 * (steps + 1));
+    auto run_steps = [&]() -> int {
+        isave = 0;
+        if (energy && !fused) launch_energy(h, h->u[h->cur], h->d_energy, 3 * (steps + 1));
+        if (emit(0)) return 1;
+        // short integrations of small batches keep the per-warp energy partials of every step and reduce them in ONE launch at
+        // the end: a single environment is latency-bound, and a reduction kernel between consecutive steps sits on its critical path
+        const bool defer = energy && fused && steps <= fused_epart_slots(h);
+        for (int n = 0; n < steps; ++n) {
+            float *d_e3 = energy ? h->d_energy + 3 * (size_t)(fused ? n : n + 1) : nullptr;
+            if (step_any(h, steps, n, mode, d_e3, defer ? n : -1)) return 1;
+            if (emit(n + 1)) return 1;
+        }
+        if (defer) fused_reduce_deferred(h, steps, h->d_energy, 3 * (steps + 1));
+        if (energy && fused) launch_energy(h, h->u[h->cur], h->d_energy + 3 * (size_t)steps, 3 * (steps + 1));
+        return 0;
+    };
+
+    // The whole integration (every kernel of every step, the forks to the side streams, the frame copies) is captured ONCE
+    // into a CUDA graph and replayed by later calls with the same shape: a single environment is launch-bound (a 700^2 step
+    // is ~10 us of device work behind 5 launches and 6 event operations), and replaying removes the per-launch host cost.
+    // The graph bakes in buffer addresses and which ping-pong buffer is current, so the key below holds all of them.
+    const bool want_graph = fused && !h->graph_off && !h->profile && !h->peer_on && graph_safe_ptr(frames) && graph_safe_ptr(u_tot_traj) &&
+                            graph_safe_ptr(u_inc_traj) && steps >= 4;
+    if (want_graph) {
+        uint64_t key[12] = {(uint64_t)steps, (uint64_t)mode, (uint64_t)h->cur, (uint64_t)h->aux_synced, (uint64_t)(energy != nullptr),
+                            (uint64_t)nsave, (uint64_t)(uintptr_t)frames, (uint64_t)(uintptr_t)u_tot_traj, (uint64_t)(uintptr_t)u_inc_traj,
+                            (uint64_t)stride, (uint64_t)(uintptr_t)h->d_stage, (uint64_t)(uintptr_t)h->d_energy};
+        uint64_t hs = 1469598103934665603ull;
+        for (int i = 0; i < nsave; ++i) hs = (hs ^ (uint64_t)save_steps[i]) * 1099511628211ull;
+        const uint64_t more[5] = {(uint64_t)(uintptr_t)h->d_cyl0, (uint64_t)(uintptr_t)h->d_cyl1, (uint64_t)(uintptr_t)h->d_env,
+                                  (uint64_t)h->cyl_cap, (uint64_t)(uintptr_t)h->d_tspan};
+        for (uint64_t v : more) hs = (hs ^ v) * 1099511628211ull;
+        key[5] ^= hs << 8;
+        if (!h->graph_exec || memcmp(key, h->graph_key, sizeof(key)) != 0) {
+            graph_drop(h);
+            const int cur0 = h->cur, aux0 = h->aux_synced;
+            const int64_t l0 = h->launches;
+            cudaGraph_t g = nullptr;
+            CU_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = run_steps();
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+            if (rc || ce != cudaSuccess || !g) {
+                if (g) cudaGraphDestroy(g);
+                cudaGetLastError();
+                h->cur = cur0;
+                h->aux_synced = aux0;
+                h->launches = l0;
+                if (rc) return 1;
+                return fail("waves_integrate: stream capture failed: %s", cudaGetErrorString(ce));
+            }
+            cudaGraphExec_t ge = nullptr;
+            ce = cudaGraphInstantiate(&ge, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) {
+                h->cur = cur0;
+                h->aux_synced = aux0;
+                h->launches = l0;
+                return fail("waves_integrate: cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+            }
+            h->graph_exec = ge;
+            memcpy(h->graph_key, key, sizeof(key));
+            h->graph_launches = h->launches - l0;
+            h->graph_cur_after = h->cur;
+        } else {  // the replay leaves the handle as the captured run left it
+            h->cur = h->graph_cur_after;
+            h->aux_synced = 1;
+            h->launches += h->graph_launches;
+        }
+        CU_TRY(cudaGraphLaunch((cudaGraphExec_t)h->graph_exec, h->stream));
+        h->graph_replays++;
+    } else if (run_steps())
+        return 1;
     if (energy)
         CU_TRY(cudaMemcpyAsync(energy, h->d_energy, sizeof(float) * 3 * (size_t)(steps + 1) * gp.n_env, cudaMemcpyDefault,
                                h->stream));
@@ -703,74 +819,131 @@ extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, i
 
 
 // ---- reverse pass -----------------------------------------------------------------------------
+extern "C" int waves_set_adjoint_checkpoint(waves_handle *h, int every) {
+    CHECK_H(h);
+    if (every < 0) return fail("waves_set_adjoint_checkpoint: need every >= 0 (0: chosen from the free device memory)");
+    h->adj_ckpt = every;
+    return 0;
+}
+
+static int grow_floats(waves_handle *h, float **buf, size_t *cap, size_t need, const char *what) {
+    if (*cap >= need) return 0;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    cudaError_t ce = cudaMalloc((void **)buf, sizeof(float) * need);
+    if (ce != cudaSuccess) return fail("waves_adjoint: cannot allocate %.1f MB for %s (%s)", need * 4e-6, what, cudaGetErrorString(ce));
+    *cap = need;
+    return 0;
+}
+
 extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int fwd_mode, int adj_mode,
                              const float *w_energy, const float *dL_dzN, float *dL_dz0, float *dL_dc, float *loss) {
     CHECK_H(h);
     const GridP &gp = h->gp;
     if (!tspan || steps < 1 || !dL_dz0) return fail("waves_adjoint: need tspan, steps >= 1 and dL_dz0");
     if (gp.ny_own != gp.ny_global) return fail("waves_adjoint: not available on slab handles");
+    const bool stagewise = (adj_mode & WAVES_ADJ_STAGEWISE) != 0;
+    adj_mode &= ~WAVES_ADJ_STAGEWISE;
     if (adj_mode != WAVES_ADJ_EXACT && adj_mode != WAVES_ADJ_COMPAT) return fail("waves_adjoint: unknown adjoint mode %d", adj_mode);
+    if (fwd_mode != WAVES_MODE_FUSED && fwd_mode != WAVES_MODE_EXACT) return fail("waves_adjoint: unknown forward mode %d", fwd_mode);
     const size_t state = (size_t)gp.env_stride * gp.n_env, planes = (size_t)gp.plane * gp.n_env;
-    // scratch: 0 w, 1 wsum, 2 lk, 3 ly, 4 y1, 5 y2, 6 y3 (state-sized); 7: three b^2 planes; 8: dL/dc
-    for (int k = 0; k < 7; ++k)
+    // Without the speed-plane gradient the reverse step is one fused launch set (kernels_adjoint_fused.cu) and needs only the
+    // two U planes of every stored state (for the energy cotangent); dL/dc needs the forward stage states and runs the
+    // per-stage kernels of kernels_adjoint.cu on full stored states.
+    const bool fused_rev = !stagewise && dL_dc == nullptr;
+    const size_t slot = fused_rev ? 2 * planes : state;
+
+    // scratch: 0 w, 1 wsum (both paths); stagewise: 2 lk, 3 ly, 4 y1, 5 y2, 6 y3 (state-sized); 7: three b^2 planes; 8: dL/dc
+    const int nstate = fused_rev ? (dL_dzN ? 3 : 2) : 7;
+    for (int k = 0; k < nstate; ++k)
         if (!h->adj[k]) CU_TRY(cudaMalloc((void **)&h->adj[k], sizeof(float) * state));
     if (!h->adj[7]) CU_TRY(cudaMalloc((void **)&h->adj[7], sizeof(float) * 3 * planes));
-    if (!h->adj[8]) CU_TRY(cudaMalloc((void **)&h->adj[8], sizeof(float) * planes));
-    if (h->traj_cap < steps + 1) {
-        CU_TRY(cudaStreamSynchronize(h->stream));
-        if (h->traj) cudaFree(h->traj);
-        h->traj = nullptr;
-        h->traj_cap = 0;
-        cudaError_t ce = cudaMalloc((void **)&h->traj, sizeof(float) * state * (size_t)(steps + 1));
-        if (ce != cudaSuccess)
-            return fail("waves_adjoint: cannot store %d states of %.1f MB on the device (%s)", steps + 1, state * 4e-6,
-                        cudaGetErrorString(ce));
-        h->traj_cap = steps + 1;
+    if (dL_dc && !h->adj[8]) CU_TRY(cudaMalloc((void **)&h->adj[8], sizeof(float) * planes));
+    if (fwd_mode == WAVES_MODE_EXACT || !fused_rev)
+        if (ensure_exact_scratch(h)) return 1;
+
+    // ---- storage plan: every state of the LAST segment is kept while the forward pass runs; earlier segments keep only the
+    // state at their start (checkpoint) and are re-run during the reverse sweep.  One segment (no
+    // recomputation) when everything fits.
+    int K = steps;
+    {
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const double have = 0.8 * ((double)free_b + 4.0 * ((double)h->traj_cap + (double)h->ckpt_cap));
+        auto bytes = [&](int k) { return 4.0 * ((double)(k + 1) * slot + (k < steps ? (double)((steps + k - 1) / k) * state : 0.0)); };
+        if (h->adj_ckpt > 0)
+            K = h->adj_ckpt < steps ? h->adj_ckpt : steps;
+        else if (bytes(steps) > have) {
+            K = (int)ceil(sqrt((double)steps * (double)state / (double)slot));
+            K = K < 1 ? 1 : (K > steps ? steps : K);
+            if (bytes(K) > have)
+                return fail("waves_adjoint: %d steps of %d environments need %.1f GB even with checkpoints every %d steps (%.1f GB free)",
+                            steps, gp.n_env, bytes(K) * 1e-9, K, free_b * 1e-9);
+        }
     }
-    float *W = h->adj[0], *WS = h->adj[1], *LK = h->adj[2], *LY = h->adj[3];  // W / WS swap roles after every step
+    const int nseg = (steps + K - 1) / K;
+    if (grow_floats(h, &h->traj, &h->traj_cap, (size_t)(K + 1) * slot, "the stored states of one segment")) return 1;
+    if (nseg > 1 && grow_floats(h, &h->ckpt, &h->ckpt_cap, (size_t)nseg * state, "checkpoints")) return 1;
+    h->adj_last_K = K;
+
+    float *W = h->adj[0], *WS = h->adj[1];  // W / WS swap roles after every step
+    float *LK = h->adj[2], *LY = h->adj[3];
     float *Y[3] = {h->adj[4], h->adj[5], h->adj[6]};
     float *B2[3] = {h->adj[7], h->adj[7] + planes, h->adj[7] + 2 * planes};
     float *GC = h->adj[8];
-    if (ensure_exact_scratch(h)) return 1;
 
-    // ---- forward: (iter::Integrator)(z0, t, θ), every state kept (src/dynamics.jl:121) ----
+    // ---- forward: (iter::Integrator)(z0, t, θ) (src/dynamics.jl:121) ----
     // the stage table gets steps+1 rows: the reference's loop also pulls back through a step taken at t_N
     const int rows = steps + 1;
+    const int erows = rows + 1;  // the step kernels lay the energy trace out for a `rows`-step integration: rows + 1 frames per env
     if (ensure_stage(h, rows + 1) || flush_params(h)) return 1;
-    if (h->energy_cap < rows) {
+    if (h->energy_cap < erows) {
         CU_TRY(cudaStreamSynchronize(h->stream));
+        graph_drop(h);
         if (h->d_energy) cudaFree(h->d_energy);
-        h->energy_cap = rows < 128 ? 128 : rows;
+        h->energy_cap = erows < 128 ? 128 : erows;
         CU_TRY(cudaMalloc((void **)&h->d_energy, sizeof(float) * 3 * (size_t)h->energy_cap * gp.n_env));
     }
-    {
-        std::vector<float> ts(rows + 1);
-        memcpy(ts.data(), tspan, sizeof(float) * rows);
-        ts[rows] = tspan[steps];
-        CU_TRY(cudaMemcpyAsync(h->d_tspan, ts.data(), sizeof(float) * rows, cudaMemcpyHostToDevice, h->stream));
-        CU_TRY(cudaStreamSynchronize(h->stream));
-    }
+    CU_TRY(cudaMemcpyAsync(h->d_tspan, tspan, sizeof(float) * rows, cudaMemcpyDefault, h->stream));
     launch_stage_table(h, h->d_tspan, rows, h->d_stage);
-    CU_TRY(cudaMemcpyAsync(h->traj, h->u[h->cur], sizeof(float) * state, cudaMemcpyDeviceToDevice, h->stream));
+    auto record = [&](int slot_idx) -> int {  // the state a reverse step needs: its U planes, or all of it
+        float *dst = h->traj + (size_t)slot_idx * slot;
+        if (fused_rev)
+            launch_gather_u(h, h->u[h->cur], dst);
+        else
+            CU_TRY(cudaMemcpyAsync(dst, h->u[h->cur], sizeof(float) * state, cudaMemcpyDeviceToDevice, h->stream));
+        return 0;
+    };
+    const bool want_loss = loss != nullptr && w_energy != nullptr;
+    const bool fused_fwd = fwd_mode == WAVES_MODE_FUSED;
+    if (want_loss && !fused_fwd) launch_energy(h, h->u[h->cur], h->d_energy, 3 * erows);
     for (int n = 0; n < steps; ++n) {
-        if (step_any(h, rows, n, fwd_mode, nullptr)) return 1;
-        CU_TRY(cudaMemcpyAsync(h->traj + (size_t)(n + 1) * state, h->u[h->cur], sizeof(float) * state, cudaMemcpyDeviceToDevice,
-                               h->stream));
+        const int seg = n / K, j = n - seg * K;
+        if (j == 0 && seg < nseg - 1)
+            CU_TRY(cudaMemcpyAsync(h->ckpt + (size_t)seg * state, h->u[h->cur], sizeof(float) * state, cudaMemcpyDeviceToDevice, h->stream));
+        if (seg == nseg - 1 && record(j)) return 1;
+        float *d_e3 = want_loss ? h->d_energy + 3 * (size_t)(fused_fwd ? n : n + 1) : nullptr;
+        if (step_any(h, rows, n, fwd_mode, d_e3)) return 1;
     }
+    if (record(steps - (nseg - 1) * K)) return 1;
+    if (want_loss && fused_fwd) launch_energy(h, h->u[h->cur], h->d_energy + 3 * (size_t)steps, 3 * erows);
+    if (nseg > 1)  // z_N: the handle is left at the last state, like waves_integrate
+        CU_TRY(cudaMemcpyAsync(h->ckpt + (size_t)(nseg - 1) * state, h->u[h->cur], sizeof(float) * state, cudaMemcpyDeviceToDevice, h->stream));
     if (loss) {
-        std::vector<float> e3((size_t)3 * gp.n_env);
         for (int e = 0; e < gp.n_env; ++e) loss[e] = 0.0f;
-        std::vector<double> acc(gp.n_env, 0.0);
-        for (int i = 0; i <= steps && w_energy; ++i) {
-            const float *w3 = w_energy + 3 * i;
-            if (w3[0] == 0.0f && w3[1] == 0.0f && w3[2] == 0.0f) continue;
-            launch_energy(h, h->traj + (size_t)i * state, h->d_energy, 3);
-            CU_TRY(cudaMemcpyAsync(e3.data(), h->d_energy, sizeof(float) * 3 * gp.n_env, cudaMemcpyDeviceToHost, h->stream));
+        if (want_loss) {
+            std::vector<float> en((size_t)3 * erows * gp.n_env);
+            CU_TRY(cudaMemcpyAsync(en.data(), h->d_energy, sizeof(float) * en.size(), cudaMemcpyDeviceToHost, h->stream));
             CU_TRY(cudaStreamSynchronize(h->stream));
-            for (int e = 0; e < gp.n_env; ++e)
-                acc[e] += (double)w3[0] * e3[3 * e] + (double)w3[1] * e3[3 * e + 1] + (double)w3[2] * e3[3 * e + 2];
+            for (int e = 0; e < gp.n_env; ++e) {
+                double acc = 0.0;
+                for (int i = 0; i <= steps; ++i)
+                    for (int k = 0; k < 3; ++k) acc += (double)w_energy[3 * i + k] * (double)en[((size_t)e * erows + i) * 3 + k];
+                loss[e] = (float)acc;
+            }
         }
-        for (int e = 0; e < gp.n_env; ++e) loss[e] = (float)acc[e];
     }
 
     // ---- reverse sweep ----
@@ -783,34 +956,45 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
         design_static = memcmp(h->h_cyl0 + (size_t)e * h->cyl_cap * 4, h->h_cyl1 + (size_t)e * h->cyl_cap * 4, sizeof(float) * 4 * ep.ncyl) == 0;
     }
     const float dt = gp.dt, hdt = gp.hdt, s6 = dt / 6.0f, s3 = dt / 3.0f;
-    CU_TRY(cudaMemsetAsync(GC, 0, sizeof(float) * planes, h->stream));
-    CU_TRY(cudaMemsetAsync(W, 0, sizeof(float) * state, h->stream));
-    auto add_cotangent = [&](int i) -> int {  // W += a_i
-        if (w_energy) {
-            const float *w3 = w_energy + 3 * i;
-            if (w3[0] != 0.0f || w3[1] != 0.0f || w3[2] != 0.0f) launch_energy_cotangent(h, h->traj + (size_t)i * state, W, w3);
-        }
-        if (i == steps && dL_dzN) {
-            // LK <- the caller's cotangent in the pitched layout, W += LK
-            CU_TRY(cudaMemsetAsync(LK, 0, sizeof(float) * state, h->stream));
-            for (int e = 0; e < gp.n_env; ++e)
-                if (copy_planes_fast(h, LK + (size_t)e * gp.env_stride, dL_dzN + (size_t)e * 12 * gp.ny_own * gp.nx, nullptr, 12))
-                    return 1;
-            launch_lin3(h, W, 1.0f, W, 1.0f, LK, 0.0f, nullptr);
-        }
-        return 0;
+    static const float zero3[3] = {0.0f, 0.0f, 0.0f};
+    auto w3_of = [&](int i) -> const float * {
+        if (!w_energy) return nullptr;
+        const float *w3 = w_energy + 3 * i;
+        return (w3[0] != 0.0f || w3[1] != 0.0f || w3[2] != 0.0f) ? w3 : nullptr;
     };
-    // W <- W + J_step(z_i, t_i)^T W, dL/dc accumulated: the pullback of one runge_kutta call (src/dynamics.jl:105-107)
-    auto step_vjp = [&](int i) {
-        const float *z = h->traj + (size_t)i * state;
+    if (dL_dc) CU_TRY(cudaMemsetAsync(GC, 0, sizeof(float) * planes, h->stream));
+    CU_TRY(cudaMemsetAsync(W, 0, sizeof(float) * state, h->stream));
+    auto speeds = [&](int i) {
         if (sp && !(design_static && b2_ready))
             for (int tau = 0; tau < 3; ++tau) launch_speed2(h, 0, gp.n_env, h->d_stage, rows, i, tau == 0 ? 0 : (tau == 1 ? 1 : 3), B2[tau]);
         b2_ready = true;
+    };
+    // W += a_i, the energy cotangent of the stored state z_i at `zslot`
+    auto add_energy = [&](int i, const float *zslot) {
+        if (const float *w3 = w3_of(i)) {
+            if (fused_rev)
+                launch_energy_cotangent(h, zslot, 2 * gp.plane, gp.plane, W, w3);
+            else
+                launch_energy_cotangent(h, zslot, gp.env_stride, 6 * gp.plane, W, w3);
+        }
+    };
+    // W += the caller's cotangent of the last state
+    auto add_final = [&]() -> int {
+        float *T = h->adj[2];  // the caller's cotangent in the pitched layout
+        CU_TRY(cudaMemsetAsync(T, 0, sizeof(float) * state, h->stream));
+        for (int e = 0; e < gp.n_env; ++e)
+            if (copy_planes_fast(h, T + (size_t)e * gp.env_stride, dL_dzN + (size_t)e * 12 * gp.ny_own * gp.nx, nullptr, 12))
+                return 1;
+        launch_lin3(h, W, 1.0f, W, 1.0f, T, 0.0f, nullptr);
+        return 0;
+    };
+    // W <- W + J_step(z_i, t_i)^T W with the per-stage kernels, dL/dc accumulated: the pullback of one runge_kutta call
+    // (src/dynamics.jl:105-107)
+    auto step_vjp_stagewise = [&](int i, const float *z) {
+        speeds(i);
         float *gc = dL_dc ? GC : nullptr;
         // forward stage states y1, y2, y3 (k4 is not needed): y_s = z + a k(y_{s-1}) in one launch each.  The dynamics are
-        // linear in the state, so J^T does not depend on them: only the dL/dc term reads them (k_rhs_transposed touches `y`
-        // under `gcacc` only).  Without dL/dc -- the gradient the reference itself can produce, its mask has no derivative --
-        // a reverse step is the four transposed right-hand sides alone.
+        // linear in the state, so J^T does not depend on them: only the dL/dc term reads them.
         if (gc) {
             float *saved_b2 = h->b2;
             for (int s = 0; s < 3; ++s) {
@@ -828,17 +1012,46 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
         launch_rhs_transposed(h, s6, W, hdt, LY, z, b0, LK, WS, 0, gc);            // λ_k1 = dt/6 w + dt/2 λ_y1 -> λ_z
         std::swap(W, WS);                                                          // w <- w + J_step^T w
     };
-    if (adj_mode == WAVES_ADJ_EXACT) {
-        if (add_cotangent(steps)) return 1;            // λ_N = a_N
-        for (int i = steps - 1; i >= 0; --i) {         // λ_i = a_i + (I + J_i^T) λ_{i+1}
-            step_vjp(i);
-            if (add_cotangent(i)) return 1;
+    // one reverse step i with the stored state at `zslot`: exact  W <- a_i + (I + J_i^T) W ; compat  W <- (I + J_i^T)(W + a_i)
+    auto reverse_step = [&](int i, const float *zslot) -> int {
+        const float *w3 = w3_of(i);
+        if (fused_rev) {
+            speeds(i);
+            const float *b2v[3] = {sp ? B2[0] : nullptr, sp ? B2[1] : nullptr, sp ? B2[2] : nullptr};
+            const bool pre = adj_mode == WAVES_ADJ_COMPAT && w3, post = adj_mode == WAVES_ADJ_EXACT && w3;
+            if (launch_adjoint_step_fused(h, W, WS, b2v, pre ? zslot : nullptr, pre ? w3 : zero3, post ? zslot : nullptr, post ? w3 : zero3))
+                return 1;
+            std::swap(W, WS);
+            return 0;
         }
-    } else {
-        for (int i = steps; i >= 0; --i) {             // the loop as written: acc = (I + J_i^T)(acc + a_i), i = N..0
-            if (add_cotangent(i)) return 1;
-            step_vjp(i);
+        if (adj_mode == WAVES_ADJ_COMPAT) add_energy(i, zslot);
+        step_vjp_stagewise(i, zslot);
+        if (adj_mode == WAVES_ADJ_EXACT) add_energy(i, zslot);
+        return 0;
+    };
+    for (int seg = nseg - 1; seg >= 0; --seg) {
+        const int s0 = seg * K, len = (steps - s0) < K ? (steps - s0) : K;
+        if (seg < nseg - 1) {  // re-run the segment from its checkpoint, storing what its reverse steps need
+            CU_TRY(cudaMemcpyAsync(h->u[h->cur], h->ckpt + (size_t)seg * state, sizeof(float) * state, cudaMemcpyDeviceToDevice, h->stream));
+            h->aux_synced = 0;
+            for (int j = 0; j < len; ++j) {
+                if (record(j)) return 1;
+                if (step_any(h, rows, s0 + j, fwd_mode, nullptr)) return 1;
+            }
+        } else {  // the last state: lambda_N = a_N (exact), or the extra step-vjp of the loop as written (compat)
+            const float *zN = h->traj + (size_t)len * slot;
+            if (dL_dzN && add_final()) return 1;
+            if (adj_mode == WAVES_ADJ_EXACT)
+                add_energy(steps, zN);
+            else if (reverse_step(steps, zN))
+                return 1;
         }
+        for (int j = len - 1; j >= 0; --j)
+            if (reverse_step(s0 + j, h->traj + (size_t)j * slot)) return 1;
+    }
+    if (nseg > 1) {
+        CU_TRY(cudaMemcpyAsync(h->u[h->cur], h->ckpt + (size_t)(nseg - 1) * state, sizeof(float) * state, cudaMemcpyDeviceToDevice, h->stream));
+        h->aux_synced = 0;
     }
     for (int e = 0; e < gp.n_env; ++e) {
         if (copy_planes_fast(h, W + (size_t)e * gp.env_stride, nullptr, dL_dz0 + (size_t)e * 12 * gp.ny_own * gp.nx, 12)) return 1;
@@ -945,6 +1158,7 @@ extern "C" int waves_peer_attach(waves_handle *h, const waves_peer_info *lo, con
 
 // ---- introspection ---------------------------------------------------------------------------
 extern "C" int64_t waves_launch_count(waves_handle *h) { return h ? h->launches : 0; }
+extern "C" int64_t waves_graph_replays(waves_handle *h) { return h ? h->graph_replays : 0; }
 
 extern "C" int waves_profile(waves_handle *h, int on) {
     CHECK_H(h);

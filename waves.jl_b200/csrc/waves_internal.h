@@ -66,8 +66,13 @@ struct waves_handle {
     float *adj[9];        // adjoint scratch: w, wsum, lk, ly, y1, y2, y3 (state-sized), b2 planes x3 (one block), dL/dc
     float *obs_in, *obs_out;  // observation scratch (waves_observe)
     size_t obs_in_cap, obs_out_cap;
-    float *traj;          // stored forward trajectory [(steps+1)][state]
-    long long traj_cap;   // frames
+    float *traj;          // reverse pass: what the reverse steps of one segment need of the stored states (waves_adjoint)
+    size_t traj_cap;      // floats
+    float *ckpt;          // reverse pass: the state at the start of every segment + the last state
+    size_t ckpt_cap;      // floats
+    int adj_ckpt;         // steps per segment requested by the caller (0: automatic)
+    int adj_last_K;       // steps per segment the last waves_adjoint call used
+    int adj_z0, adj_z1;   // zero-sigma zone of the profile (fused reverse step), 0/0: not computed yet
     float *d_x, *d_y, *d_sigma;
     EnvParams *h_env, *d_env;
     bool env_dirty;
@@ -108,6 +113,14 @@ struct waves_handle {
     int *peer_flag[2];        // the slot in neighbour s's flags that this rank writes
     void *ipc_ptr[2][3];      // opened IPC mappings (to close)
     int peer_steps;           // fused steps taken in peer mode
+    // ---- CUDA graph of a whole waves_integrate call (waves_abi.cu) ----
+    void *graph_exec;         // cudaGraphExec_t of the last captured integration, nullptr: none
+    uint64_t graph_key[12];   // what the captured graph depends on (shape of the call, buffer addresses, ping-pong parity)
+    int64_t graph_launches;   // kernel launches one replay stands for
+    int64_t graph_replays;
+    int graph_cur_after;      // h->cur after the captured run
+    int graph_off;            // 1: launch every kernel directly (waves_set_graph)
+    int traj_stride;          // U trajectories keep every traj_stride-th frame (waves_set_traj_stride); 0 == 1
 };
 
 // ---- kernels_exact.cu ----
@@ -128,7 +141,12 @@ void launch_unpack_halo(waves_handle *h, float *u, const float *lo, const float 
 void launch_rhs_transposed(waves_handle *h, float a, const float *w, float b, const float *lyp, const float *y, const float *b2,
                            float *out, float *ws, int first, float *gcacc);
 void launch_lin3(waves_handle *h, float *out, float a, const float *x, float b, const float *y, float c, const float *z);
-void launch_energy_cotangent(waves_handle *h, const float *z, float *w, const float *w3 /*host, 3 weights*/);
+void launch_energy_cotangent(waves_handle *h, const float *z, long long z_env, long long z_inc, float *w, const float *w3 /*host, 3 weights*/);
+
+// ---- kernels_adjoint_fused.cu ----
+int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, const float *const b2[3], const float *pre_u,
+                              const float *pre_w3, const float *post_u, const float *post_w3);
+void launch_gather_u(waves_handle *h, const float *u, float *out);
 
 // ---- kernels_fused.cu ----
 int fused_prepare(waves_handle *h);  // work items, tensor maps, smem attribute; 0 on success
@@ -136,4 +154,6 @@ void fused_release(waves_handle *h);
 int fused_item_counts(waves_handle *h, int *n_int, int *n_gen);
 int source_bbox(waves_handle *h, int env, int *bbox4);
 int waves_set_error(const char *msg);  // sets the thread-local message, returns 1
-int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step, float *d_e3 /*nullable*/);
+int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step, float *d_e3 /*nullable*/, int defer_slot = -1);
+int fused_epart_slots(waves_handle *h);
+void fused_reduce_deferred(waves_handle *h, int count, float *d_e3, int env_stride3);

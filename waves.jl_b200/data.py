@@ -93,12 +93,22 @@ class BatchWaveEnv:
         self.engine = Engine(dim.x, dim.y, c0, dt, pml_width, pml_scale, n_env=self.n_env, device=device)
         nx, ny = dim.size()
         self.designs = [design_space.rand(r) for r in self.rngs]
-        self.wave = np.zeros((self.n_env, 3, 12, ny, nx), dtype=F32)
+        # env.wave of every environment stays on the device (src/env.jl:116 under gpu(env)); `.wave` copies it out on demand
+        import torch
+        self._wave_dev = torch.zeros((self.n_env, 3, 12, ny, nx), dtype=torch.float32, device=f"cuda:{device}")
+        self._wave_host = None
         self.signal = np.zeros((self.n_env, self.integration_steps + 1, 3), dtype=F32)
         self.time_step = 0
-        self.engine.set_state(self.wave[:, -1])
+        self.engine.set_state(self._wave_dev[:, -1].contiguous())
         for e, src in enumerate(self.sources):
             self.engine.set_source(src.shape, float(src.freq), env=e)
+
+    @property
+    def wave(self):
+        """(n_env, 3, 12, ny, nx) host copy of the kept frames, made on first use after an action."""
+        if self._wave_host is None:
+            self._wave_host = self._wave_dev.cpu().numpy()
+        return self._wave_host
 
     def time(self):
         return F32(F32(self.time_step) * self.dt)
@@ -115,7 +125,7 @@ class BatchWaveEnv:
 
     def state(self):
         """Per environment (tspan, image (4, res_y, res_x), design): RLBase.state (src/env.jl:132-137)."""
-        x = self.engine.observe(self.wave, self.resolution)
+        x = self.engine.observe(self._wave_dev, self.resolution)   # device frames in, (n_env, 4, res_y, res_x) floats out
         ts = self.build_tspan()
         return [(ts, x[e], self.designs[e]) for e in range(self.n_env)]
 
@@ -128,7 +138,9 @@ class BatchWaveEnv:
         nxt = [self.design_space(d, a) for d, a in zip(self.designs, actions)]
         self.engine.set_design_batch(np.stack([d.table() for d in self.designs]), np.stack([d.table() for d in nxt]), ti, tspan[-1])
         n = self.integration_steps
-        self.signal, self.wave = self.engine.integrate(tspan, self.mode, energy=True, save_steps=[n - 2 * FRAMESKIP, n - FRAMESKIP, n])
+        self.signal, _ = self.engine.integrate(tspan, self.mode, energy=True, save_steps=[n - 2 * FRAMESKIP, n - FRAMESKIP, n],
+                                               frames=self._wave_dev)
+        self._wave_host = None
         interps = [DesignInterpolator(d, x, ti, tspan[-1]) for d, x in zip(self.designs, nxt)]
         self.designs = nxt
         self.time_step += n

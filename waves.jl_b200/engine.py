@@ -11,7 +11,7 @@ from ._lib import check
 F32 = np.float32
 MODE_FUSED, MODE_EXACT = 0, 1
 STEP_ASYNC = 0x100
-ADJ_EXACT, ADJ_COMPAT = 0, 1
+ADJ_EXACT, ADJ_COMPAT, ADJ_STAGEWISE = 0, 1, 0x100
 
 
 def _ptr(a):
@@ -119,8 +119,20 @@ class Engine:
                                          _ptr(u_tot), _ptr(u_inc)))
         return en, frames
 
+    def set_traj_stride(self, stride: int):
+        """u_tot / u_inc trajectories of integrate keep every `stride`-th frame: (n_env, steps // stride + 1, ny, nx)."""
+        check(_lib.lib().waves_set_traj_stride(self._h, int(stride)))
+
+    def set_graph(self, on: bool):
+        """Replay integrate() from a captured CUDA graph (default) or launch every kernel directly."""
+        check(_lib.lib().waves_set_graph(self._h, int(bool(on))))
+
+    def set_adjoint_checkpoint(self, every: int):
+        """Reverse pass: checkpoint every `every` steps and re-run one segment at a time (0: automatic, from free memory)."""
+        check(_lib.lib().waves_set_adjoint_checkpoint(self._h, int(every)))
+
     def adjoint(self, tspan, w_energy=None, dL_dzN=None, fwd_mode=MODE_FUSED, adj_mode=ADJ_EXACT, want_dc=True, out_dz0=None,
-                out_dc=None):
+                out_dc=None, fused_reverse=True):
         """rrule(::Integrator) + adjoint_sensitivity (src/dynamics.jl:97-128) from the current state.
         Returns (loss (n_env,), dL/dz0 (n_env,12,ny,nx), dL/dc (n_env,ny,nx) | None); out_dz0 / out_dc may be preallocated
         NumPy arrays or CUDA tensors (the gradients of a large batch are best left on the device)."""
@@ -132,6 +144,8 @@ class Engine:
         gz = out_dz0 if out_dz0 is not None else np.empty((self.n_env, 12, self.ny, self.nx), dtype=F32)
         gc = out_dc if out_dc is not None else (np.empty((self.n_env, self.ny, self.nx), dtype=F32) if want_dc else None)
         loss = np.zeros(self.n_env, dtype=F32)
+        if not fused_reverse:
+            adj_mode |= ADJ_STAGEWISE   # per-stage reverse kernels even without dL/dc (cross-check of the fused reverse step)
         check(_lib.lib().waves_adjoint(self._h, ts.ctypes.data_as(_lib.fp), steps, fwd_mode, adj_mode, _ptr(we), _ptr(an),
                                        _ptr(gz), _ptr(gc), _ptr(loss)))
         return loss, gz, gc
@@ -146,8 +160,10 @@ class Engine:
         check(_lib.lib().waves_observe(self._h, _ptr(frames), nsave, rx, ry, _ptr(out)))
         return out
 
-    def energy(self):
-        out = np.empty((self.n_env, 3), dtype=F32)
+    def energy(self, out=None):
+        """(n_env, 3) energies of the current state; a CUDA tensor `out` is filled asynchronously on the engine's stream."""
+        if out is None:
+            out = np.empty((self.n_env, 3), dtype=F32)
         check(_lib.lib().waves_energy(self._h, _ptr(out)))
         return out
 
@@ -184,6 +200,9 @@ class Engine:
     # introspection -----------------------------------------------------------
     def launch_count(self) -> int:
         return int(_lib.lib().waves_launch_count(self._h))
+
+    def graph_replays(self) -> int:
+        return int(_lib.lib().waves_graph_replays(self._h))
 
     def profile(self, on: bool):
         check(_lib.lib().waves_profile(self._h, int(on)))

@@ -74,11 +74,22 @@ class WaveEnv:
         self.design = design_space.rand(self.rng) if design_space is not None else None
         self.iter = Integrator(AcousticDynamics(dim, c0, pml_width, pml_scale), dt, 1, device, mode)
         nx, ny = dim.size()
-        self.wave = np.zeros((3, 12, ny, nx), dtype=F32)            # (nx,ny,12,3) in the reference
+        # env.wave = the frames 80, 90, 100 of the last action, (nx,ny,12,3) in the reference, kept ON THE DEVICE like the
+        # reference's gpu(env) does (src/env.jl:116); `env.wave` hands out a host copy on demand
+        import torch
+        self._wave_dev = torch.zeros((1, 3, 12, ny, nx), dtype=torch.float32, device=f"cuda:{device}")
+        self._wave_host = None
         self.signal = np.zeros((self.integration_steps + 1, 3), dtype=F32)
         self.time_step = 0
-        self.iter.engine.set_state(self.wave[-1][None])
+        self.iter.engine.set_state(self._wave_dev[0, -1])
         self._source_bound = None
+
+    @property
+    def wave(self):
+        """(3, 12, ny, nx) host copy of the kept frames (one device->host copy per action, made on first use)."""
+        if self._wave_host is None:
+            self._wave_host = self._wave_dev[0].cpu().numpy()
+        return self._wave_host
 
     def time(self):  # src/env.jl:69-71
         return F32(F32(self.time_step) * self.dt)
@@ -91,11 +102,12 @@ class WaveEnv:
 
     def reset(self):  # src/env.jl:81-88
         self.time_step = 0
-        self.wave[:] = 0
+        self._wave_dev.zero_()
+        self._wave_host = None
         self.design = self.design_space.rand(self.rng) if self.design_space is not None else None
-        self.signal[:] = 0
+        self.signal = np.zeros_like(self.signal)
         self.source.reset(self.rng)
-        self.iter.engine.set_state(self.wave[-1][None])
+        self.iter.engine.set_state(self._wave_dev[0, -1])
         self._source_bound = None
 
     def _bind_source(self):
@@ -106,7 +118,7 @@ class WaveEnv:
     def state(self):  # src/env.jl:132-137
         """(tspan, x, design) with x = imresize(cat(u_tot frames, source shape), resolution) as (4, res_y, res_x)."""
         self._bind_source()
-        x = self.iter.engine.observe(np.ascontiguousarray(self.wave[None]), self.resolution)[0]
+        x = self.iter.engine.observe(self._wave_dev, self.resolution)[0]   # only (4, res_y, res_x) floats leave the GPU
         return self.build_tspan(), x, self.design
 
     def action_space(self):  # src/env.jl:143-145
@@ -115,9 +127,10 @@ class WaveEnv:
     def reward(self):  # src/env.jl:147-149
         return F32(np.sum(self.signal, dtype=np.float64))
 
-    def __call__(self, action, return_frames=False):
-        """One environment step.  The device state carries over between calls, so only the design table,
-        the tspan and (optionally) frames cross the host-device boundary."""
+    def __call__(self, action, return_frames=False, frame_stride=1):
+        """One environment step.  The device state and env.wave carry over between calls on the device, so only the design
+        table, the tspan and the energy signal cross the host-device boundary (and the whole call replays one CUDA graph);
+        return_frames adds the U trajectories a renderer wants (src/env.jl:120), every `frame_stride`-th frame."""
         eng = self.iter.engine
         tspan = self.build_tspan()
         ti = self.time()
@@ -130,13 +143,15 @@ class WaveEnv:
             eng.set_design(self.design.table(), nxt.table(), ti, tspan[-1])
         self._bind_source()
         n = self.integration_steps
-        ny, nx = self.wave.shape[2:]
-        u_tot = np.empty((1, n + 1, ny, nx), F32) if return_frames else None
-        u_inc = np.empty((1, n + 1, ny, nx), F32) if return_frames else None
-        en, frames = eng.integrate(tspan, self.iter.mode, energy=True, save_steps=[n - 2 * FRAMESKIP, n - FRAMESKIP, n],
-                                   u_tot=u_tot, u_inc=u_inc)
+        ny, nx = self._wave_dev.shape[3:]
+        nf = n // int(frame_stride) + 1
+        u_tot = np.empty((1, nf, ny, nx), F32) if return_frames else None
+        u_inc = np.empty((1, nf, ny, nx), F32) if return_frames else None
+        eng.set_traj_stride(frame_stride if return_frames else 1)
+        en, _ = eng.integrate(tspan, self.iter.mode, energy=True, save_steps=[n - 2 * FRAMESKIP, n - FRAMESKIP, n],
+                              frames=self._wave_dev, u_tot=u_tot, u_inc=u_inc)
         self.signal = en[0]
         self.design = nxt
-        self.wave = frames[0]
+        self._wave_host = None
         self.time_step += n
         return tspan, interp, (u_tot[0] if return_frames else None), (u_inc[0] if return_frames else None)

@@ -17,6 +17,21 @@ using Waves
 using Waves: OneDim, TwoDim, WaveEnv, Integrator, AcousticDynamics, DesignInterpolator, AbstractDesign, NoDesign,
              Cylinders, Cloak, AbstractScatterers, NoSource, build_tspan, get_dx, get_dy, stack
 using SparseArrays
+using Libdl
+
+# The library is opened once with Libdl and every entry point is resolved with dlsym: `ccall((:name, lib), ...)` needs `lib` to
+# be a constant or global expression, so a path held in a local variable or a struct field cannot be used there.
+const LIBH = Ref{Ptr{Cvoid}}(C_NULL)
+const LIBPATH = Ref{String}("")
+"""    load!(path)  -- open libwaves_b200.so (idempotent); every handle of this session uses it"""
+function load!(path::AbstractString)
+    if LIBH[] == C_NULL || LIBPATH[] != path
+        LIBH[] = Libdl.dlopen(path)
+        LIBPATH[] = String(path)
+    end
+    return LIBH[]
+end
+sym(name::Symbol) = (LIBH[] == C_NULL && error("waves_b200: call WavesB200.load!(\"/path/to/libwaves_b200.so\") first"); Libdl.dlsym(LIBH[], name))
 
 const MODE_FUSED = Cint(0)
 const MODE_EXACT = Cint(1)
@@ -36,7 +51,7 @@ end
 
 function check(h_lib::String, rc::Cint)
     rc == 0 && return nothing
-    msg = unsafe_string(ccall((:waves_last_error, h_lib), Cstring, ()))
+    msg = unsafe_string(ccall(sym(:waves_last_error), Cstring, ()))
     error("waves_b200: " * msg)
 end
 
@@ -62,33 +77,33 @@ function create(dyn::AcousticDynamics{TwoDim}, dt::Float32; lib::String, device:
         cfg = Ref(WavesConfig(length(x), length(y), n_env, device, dyn.c0, dt, 0f0, 0f0,
                               pointer(x), pointer(y), pointer(sigma), pointer(g8),
                               get_dx(dim) * get_dy(dim), length(y), 0, 0))
-        check(lib, ccall((:waves_create, lib), Cint, (Ref{WavesConfig}, Ref{Ptr{Cvoid}}), cfg, out))
+        check(lib, ccall(sym(:waves_create), Cint, (Ref{WavesConfig}, Ref{Ptr{Cvoid}}), cfg, out))
     end
     h = Handle(out[], lib)
-    finalizer(h -> (h.ptr != C_NULL && ccall((:waves_destroy, h.lib), Cint, (Ptr{Cvoid},), h.ptr); h.ptr = C_NULL), h)
+    finalizer(h -> (h.ptr != C_NULL && ccall(sym(:waves_destroy), Cint, (Ptr{Cvoid},), h.ptr); h.ptr = C_NULL), h)
     return h
 end
 
 set_state!(h::Handle, u12::Array{Float32, 3}, env::Integer = -1) =
-    check(h.lib, ccall((:waves_set_state, h.lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), h.ptr, env, u12))
+    check(h.lib, ccall(sym(:waves_set_state), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), h.ptr, env, u12))
 
 function get_state(h::Handle, nx, ny, env::Integer = 0)
     u = Array{Float32}(undef, nx, ny, 12)
-    check(h.lib, ccall((:waves_get_state, h.lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), h.ptr, env, u))
+    check(h.lib, ccall(sym(:waves_get_state), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), h.ptr, env, u))
     return u
 end
 
 set_source!(h::Handle, ::NoSource, env::Integer = -1) =
-    check(h.lib, ccall((:waves_set_source, h.lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Cfloat), h.ptr, env, C_NULL, 0f0))
+    check(h.lib, ccall(sym(:waves_set_source), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Cfloat), h.ptr, env, C_NULL, 0f0))
 set_source!(h::Handle, src, env::Integer = -1) =   # Source / RandomPosGaussianSource: fields shape, freq
-    check(h.lib, ccall((:waves_set_source, h.lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Cfloat), h.ptr, env, Array{Float32}(src.shape), src.freq))
+    check(h.lib, ccall(sym(:waves_set_source), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Cfloat), h.ptr, env, Array{Float32}(src.shape), src.freq))
 
 set_design!(h::Handle, ::Nothing, env::Integer = -1) =
-    check(h.lib, ccall((:waves_set_design, h.lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Cfloat, Cfloat), h.ptr, env, 0, C_NULL, C_NULL, 0f0, 0f0))
+    check(h.lib, ccall(sym(:waves_set_design), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Cfloat, Cfloat), h.ptr, env, 0, C_NULL, C_NULL, 0f0, 0f0))
 function set_design!(h::Handle, interp::DesignInterpolator, env::Integer = -1)
     interp.initial isa NoDesign && return set_design!(h, nothing, env)
     a, b = cyl_table(interp.initial), cyl_table(interp.final)
-    check(h.lib, ccall((:waves_set_design, h.lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Cfloat, Cfloat),
+    check(h.lib, ccall(sym(:waves_set_design), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Cfloat, Cfloat),
                        h.ptr, env, size(a, 2), a, b, interp.ti, interp.tf))
 end
 
@@ -101,14 +116,14 @@ resolution)` for the `(nx, ny, 12, nsave)` block `integrate!` returned.  Returns
 function observe(h::Handle, frames::Array{Float32, 4}, resolution::Tuple{Int, Int})
     nsave = size(frames, 4)
     out = Array{Float32}(undef, resolution[1], resolution[2], nsave + 1)
-    check(h.lib, ccall((:waves_observe, h.lib), Cint, (Ptr{Cvoid}, Ptr{Float32}, Cint, Cint, Cint, Ptr{Float32}),
+    check(h.lib, ccall(sym(:waves_observe), Cint, (Ptr{Cvoid}, Ptr{Float32}, Cint, Cint, Cint, Ptr{Float32}),
                        h.ptr, frames, nsave, resolution[1], resolution[2], out))
     return out
 end
 
 """One DesignInterpolator per environment of a batch handle over a common [ti, tf]: `a`, `b` are (4, ncyl, n_env) arrays."""
 set_design_batch!(h::Handle, a::Array{Float32, 3}, b::Array{Float32, 3}, ti::Float32, tf::Float32) =
-    check(h.lib, ccall((:waves_set_design_batch, h.lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{Float32}, Cfloat, Cfloat),
+    check(h.lib, ccall(sym(:waves_set_design_batch), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{Float32}, Cfloat, Cfloat),
                        h.ptr, size(a, 2), a, b, ti, tf))
 
 """
@@ -123,7 +138,7 @@ function integrate!(h::Handle, tspan::Vector{Float32}, nx::Int, ny::Int; save_st
     steps = length(tspan) - 1
     energy = Array{Float32}(undef, 3, steps + 1)                  # column-major (3, steps+1) == C (steps+1, 3)
     frames = Array{Float32}(undef, nx, ny, 12, length(save_steps))
-    check(h.lib, ccall((:waves_integrate, h.lib), Cint,
+    check(h.lib, ccall(sym(:waves_integrate), Cint,
                        (Ptr{Cvoid}, Ptr{Float32}, Cint, Cint, Ptr{Float32}, Ptr{Int32}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
                        h.ptr, tspan, steps, mode, energy, save_steps, length(save_steps), frames, u_tot, u_inc))
     return energy, frames
@@ -142,7 +157,7 @@ function adjoint!(h::Handle, tspan::Vector{Float32}, nx::Int, ny::Int; w_energy 
     gz = Array{Float32}(undef, nx, ny, 12)
     gc = Array{Float32}(undef, nx, ny)
     loss = zeros(Float32, 1)
-    check(h.lib, ccall((:waves_adjoint, h.lib), Cint,
+    check(h.lib, ccall(sym(:waves_adjoint), Cint,
                        (Ptr{Cvoid}, Ptr{Float32}, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
                        h.ptr, tspan, steps, fwd_mode, adj_mode, w_energy, dL_dzN, gz, gc, loss))   # w_energy: (3, steps+1) column-major
     return loss[1], gz, gc
@@ -225,7 +240,7 @@ function create_latent(iter::Integrator; lib::String, device::Integer = 0)
     GC.@preserve x g8 begin
         cfg = LatentConfig(length(x), device, dyn.c0, iter.dt, 0f0, 0f0, Array(dyn.pml)[1], get_dx(dyn.dim),
                            pointer(x), pointer(g8))                       # pml0 = dyn.pml[[1]] (src/dynamics.jl:192)
-        check(lib, ccall((:waves_latent_create, lib), Cint, (Ref{LatentConfig}, Ref{Ptr{Cvoid}}), cfg, out))
+        check(lib, ccall(sym(:waves_latent_create), Cint, (Ref{LatentConfig}, Ref{Ptr{Cvoid}}), cfg, out))
     end
     return LatentHandle(out[], lib, length(x))
 end
@@ -250,7 +265,7 @@ function latent_integrate(h::LatentHandle, z0, t, C, F, PML; want_z::Bool = true
     energy = similar(z0, steps + 1, 3, batch)
     X, Y, shape = C.X, C.Y, F.shape
     GC.@preserve z0 t X Y shape PML z energy begin
-        check(h.lib, ccall((:waves_latent_integrate, h.lib), Cint,
+        check(h.lib, ccall(sym(:waves_latent_integrate), Cint,
                            (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
                             Cfloat, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
                            h.ptr, batch, steps, nseq, rawptr(z0), rawptr(t), rawptr(X), rawptr(Y), rawptr(shape), F.freq,
@@ -270,7 +285,7 @@ function latent_adjoint(h::LatentHandle, z, t, C, F, PML; w_energy = nothing, dL
     X, Y, shape = C.X, C.Y, F.shape
     gz0, gY, gS, gP = similar(z, n, 4, batch), similar(Y), similar(shape), similar(PML)
     GC.@preserve z t X Y shape PML w_energy dL_dz gz0 gY gS gP begin
-        check(h.lib, ccall((:waves_latent_adjoint, h.lib), Cint,
+        check(h.lib, ccall(sym(:waves_latent_adjoint), Cint,
                            (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
                             Cfloat, Ptr{Float32}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
                             Ptr{Float32}),
@@ -292,5 +307,40 @@ end
 #       end
 #       return z, Integrator_back
 #   end
+
+
+# ---- episodes written by the Python mirror (waves.jl_b200/data.py: Episode.save -> .npz) as reference Episodes ----------------
+# The reference stores episodes as BSON of Julia structs (src/data.jl:60-71: s::Vector{WaveEnvState}, a::Vector{<:AbstractDesign},
+# t::Vector{Vector{Float32}}, y::Vector{Matrix{Float32}}), which only Julia can write faithfully.  The batched generator writes
+# plain arrays; this turns one file into the reference's Episode (NPZ.jl is the only extra dependency) and
+#     FileIO.save(WavesB200.episode_from_npz("episode1.npz", env), "episode1.bson")
+# produces exactly what scripts/main.jl:144-150 loads with Episode(path = ...).
+"""
+    episode_from_npz(path, env::WaveEnv; npzread) -> Waves.Episode
+
+`images` (A, C, res_y, res_x), `t` (A, steps+1), `y` (A, steps+1, 3), `designs` / `actions` (A, ncyl, 4) rows {x, y, r, c} of the
+stacked cylinders; `env` supplies `dim` and a design of the right type (the cylinder tables are poured into copies of it).
+Pass `npzread = NPZ.npzread` (NPZ.jl keeps NumPy's logical shapes).
+"""
+function episode_from_npz(path::AbstractString, env::WaveEnv; npzread)
+    f = npzread(path)
+    A = size(f["t"], 1)
+    rows(tab, k0, n) = (Matrix{Float32}(tab[k0:k0+n-1, 1:2]), Vector{Float32}(tab[k0:k0+n-1, 3]), Vector{Float32}(tab[k0:k0+n-1, 4]))
+    fill_design(proto::Cylinders, tab, k0 = 1) = Cylinders(rows(tab, k0, length(proto))...)
+    fill_design(proto::AbstractScatterers, tab, k0 = 1) = typeof(proto)(fill_design(proto.cylinders, tab, k0))
+    fill_design(proto::Cloak, tab, k0 = 1) = Cloak(fill_design(proto.config, tab, 1), fill_design(proto.core, tab, length(proto.config.cylinders) + 1))
+    s = Waves.WaveEnvState[]
+    a = AbstractDesign[]
+    t = Vector{Float32}[]
+    y = Matrix{Float32}[]
+    for i in 1:A
+        img = permutedims(f["images"][i, :, :, :], (3, 2, 1))          # (C, res_y, res_x) -> (res_x, res_y, C), src/env.jl:134-135
+        push!(s, Waves.WaveEnvState(env.dim, Vector{Float32}(f["t"][i, :]), Array{Float32}(img), fill_design(env.design, f["designs"][i, :, :])))
+        push!(a, fill_design(env.design, f["actions"][i, :, :]))
+        push!(t, Vector{Float32}(f["t"][i, :]))
+        push!(y, Matrix{Float32}(f["y"][i, :, :]))                      # (steps+1, 3) like env.signal, src/env.jl:114
+    end
+    return Waves.Episode(s, a, t, y)
+end
 
 end # module

@@ -120,23 +120,24 @@ class SlabEngine:
         import torch.distributed as dist
         torch = self._torch
         steps = len(tspan) - 1
-        en = np.zeros((steps + 1, 3), dtype=np.float64)
-        if energy:
-            en[0] = self.engine.energy()[0]
         from .engine import MODE_FUSED, STEP_ASYNC
         peer = self.peer and mode == MODE_FUSED
+        # per-step energies stay on the device (written on the engine's stream): one all-reduce at the end, no host sync per step
+        d_en = torch.zeros((steps + 1, 3), dtype=torch.float32, device=f"cuda:{self.engine.device}") if energy else None
+        if energy:
+            self.engine.energy(out=d_en[0:1])
         for n in range(steps):
             self.engine.step(float(tspan[n]), mode | STEP_ASYNC)   # the exchange is ordered on the engine's stream
             if not peer:
                 self.exchange()
             if energy:
-                en[n + 1] = self.engine.energy()[0]
+                self.engine.energy(out=d_en[n + 1:n + 2])
         self.engine.sync()
-        if energy:
-            t = torch.from_numpy(en).to(f"cuda:{self.engine.device}")
-            dist.all_reduce(t)
-            en = t.cpu().numpy()
-        return en.astype(np.float32) if energy else None
+        if not energy:
+            return None
+        t = d_en.double()
+        dist.all_reduce(t)
+        return t.cpu().numpy().astype(np.float32)
 
     def gather_state(self):
         """All ranks receive the full (12, ny_global, nx) state (test/diagnostic helper)."""
@@ -148,3 +149,76 @@ class SlabEngine:
 
     def close(self):
         self.engine.close()
+
+
+class LocalSlabGroup:
+    """All slabs of one large grid driven by ONE process: `world` slab handles on the given devices (repeat a device ordinal to
+    put several slabs on one GPU), ghost rows moved with waves_halo_pack -> device copy -> waves_halo_unpack.  No process group.
+    This is the single-process form of SlabEngine (same slab geometry, same kernels), and what lets the slab path be checked
+    bit for bit against the single-handle run on a box with one GPU."""
+
+    def __init__(self, x, y, c0, dt, pml_width, pml_scale, devices):
+        import torch
+
+        from .engine import Engine
+        self._torch, self.world = torch, len(devices)
+        self.devices = [int(d) for d in devices]
+        self.rows = [slab_rows(len(y), r, self.world) for r in range(self.world)]
+        self.engines = [Engine(x, y, c0, dt, pml_width, pml_scale, n_env=1, device=d, ny_local=ny, row0=row0)
+                        for d, (row0, ny) in zip(self.devices, self.rows)]
+        self.buf = []
+        for r, eng in enumerate(self.engines):
+            d = eng.halo_describe()
+            mk = lambda on: torch.empty(d.n_planes * d.block_floats if on else 0, dtype=torch.float32, device=f"cuda:{self.devices[r]}")
+            # send_lo, send_hi, recv_lo, recv_hi
+            self.buf.append([mk(r > 0), mk(r < self.world - 1), mk(r > 0), mk(r < self.world - 1)])
+
+    def sync(self):
+        for eng in self.engines:
+            eng.sync()
+
+    def exchange(self):
+        W = self.world
+        for r, eng in enumerate(self.engines):
+            eng.halo_pack(self.buf[r][0] if r > 0 else None, self.buf[r][1] if r < W - 1 else None)
+        self.sync()
+        for r in range(W):  # my first rows -> the lower neighbour's upper ghost rows, my last rows -> the upper neighbour's lower ones
+            if r > 0:
+                self.buf[r - 1][3].copy_(self.buf[r][0])
+            if r < W - 1:
+                self.buf[r + 1][2].copy_(self.buf[r][1])
+        self._torch.cuda.synchronize()
+        for r, eng in enumerate(self.engines):
+            eng.halo_unpack(self.buf[r][2] if r > 0 else None, self.buf[r][3] if r < W - 1 else None)
+        self.sync()
+
+    def set_state_global(self, u12_global):
+        for eng, (row0, ny) in zip(self.engines, self.rows):
+            eng.set_state(np.ascontiguousarray(u12_global[:, row0:row0 + ny])[None])
+        self.exchange()
+
+    def set_source_global(self, shape_global, freq):
+        for r, (eng, (row0, ny)) in enumerate(zip(self.engines, self.rows)):
+            lo = row0 - (HALO if r > 0 else 0)
+            hi = row0 + ny + (HALO if r < self.world - 1 else 0)
+            eng.set_source(None if shape_global is None else np.ascontiguousarray(shape_global[lo:hi]), freq)
+
+    def integrate(self, tspan, mode=0):
+        """RK4 steps with one exchange per step -> global (steps+1, 3) energy trace (float64 sum of the slabs' energies)."""
+        from .engine import STEP_ASYNC
+        steps = len(tspan) - 1
+        en = np.zeros((steps + 1, 3), dtype=np.float64)
+        en[0] = sum(eng.energy()[0].astype(np.float64) for eng in self.engines)
+        for n in range(steps):
+            for eng in self.engines:
+                eng.step(float(tspan[n]), mode | STEP_ASYNC)
+            self.exchange()
+            en[n + 1] = sum(eng.energy()[0].astype(np.float64) for eng in self.engines)
+        return en.astype(np.float32)
+
+    def gather_state(self):
+        return np.concatenate([eng.get_state(0) for eng in self.engines], axis=1)
+
+    def close(self):
+        for eng in self.engines:
+            eng.close()
