@@ -260,7 +260,7 @@ def run_ours(args):
                 import bench_single_env
                 se = bench_single_env.measure(actions=10, device=local)
                 extras["single_env"] = {"workload": "BASELINE configs[1]: one 700^2 WaveEnv, env(action) = 100 RK4 steps + energy trace",
-                                        "single_env_us_per_step": se["graph"]["us_per_rk4_step"], **se}
+                                        "single_env_us_per_step": se["default"]["us_per_rk4_step"], **se}
             except Exception as ex:  # a sub-record must never take the headline down
                 extras["single_env"] = {"error": repr(ex)[:300]}
             try:

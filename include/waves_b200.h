@@ -128,14 +128,21 @@ int waves_step(waves_handle *h, float t, int mode);
  *                With waves_set_traj_stride(h, k) they hold every k-th frame only: (n_env, steps / k + 1, ny, nx), frame 0 first
  *                (what a renderer that shows a few frames per action needs, instead of 2 x 198 MB per action at 700^2).
  * The state of the handle is left at the last step.
- * Fused mode replays the whole integration from a CUDA graph captured by the first call of the same shape (same steps, save
- * steps, output buffers); frames / trajectories in pageable host memory disable that (use device or pinned buffers).
+ * Fused mode amortises launches (waves_set_graph): a batch that fits into one wave of warps (e.g. a single 700^2 environment,
+ * which is latency-bound) takes one launch per step and one energy reduction per call; larger batches replay the whole
+ * integration from a CUDA graph captured by the first call of the same shape (same steps, save steps, output buffers; frames /
+ * trajectories in pageable host memory disable the graph: use device or pinned buffers).
  */
 int waves_integrate(waves_handle *h, const float *tspan, int steps, int mode, float *energy, const int32_t *save_steps,
                     int nsave, float *frames, float *u_tot_traj, float *u_inc_traj);
 /* Decimation of the U trajectories of waves_integrate (stride >= 1, default 1: every frame; src/plot.jl:25 consumers). */
 int waves_set_traj_stride(waves_handle *h, int stride);
-/* on == 0: launch every kernel of waves_integrate directly instead of replaying a captured CUDA graph (default: on). */
+/* How waves_integrate issues the kernels of a fused integration (results are bitwise the same in every mode):
+ *   0  every kernel of every step launched directly;
+ *   1  (default) large batches replay the whole integration from a CUDA graph captured by the first call of a shape; a batch
+ *      that fits into one wave of warps (a single 700^2 environment) takes ONE launch per step (all variants in one kernel);
+ *   2  like 1, but such a small batch advances all steps between two saved frames in one COOPERATIVE launch with a grid
+ *      barrier between steps (fewest launches; measured slower per step than mode 1 on a B200). */
 int waves_set_graph(waves_handle *h, int on);
 
 /*

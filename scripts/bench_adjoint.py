@@ -44,8 +44,18 @@ def measure(steps=500, E=1, device=0, with_dc=True, check_exact=True, n=700):
                      "loss": float(loss[0]), "finite": bool(torch.isfinite(gz).all().item())}
         return gz, gc
 
+    # forward pass alone (same steps, energy trace), to split the sweep times below
+    for _ in range(2):
+        eng.set_state(z0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.integrate(ts, wb.MODE_FUSED, energy=True)
+        torch.cuda.synchronize()
+        fwd = time.perf_counter() - t0
+    res["forward_only_seconds"] = round(fwd, 4)
     # dL/dz0 only: the gradient the reference itself can produce (its hard cylinder mask has no derivative)
     gz, _ = run("z0_only", adj_mode=wb.ADJ_EXACT, want_dc=False)
+    res["reverse_Gcell_per_s"] = round(E * n * n * steps / max(res["z0_only"]["seconds"] - fwd, 1e-9) / 1e9, 3)
     res["seconds"], res["value"] = res["z0_only"]["seconds"], res["z0_only"]["value"]
     g_fused = gz.clone()
     run("z0_only_compat", adj_mode=wb.ADJ_COMPAT, want_dc=False)

@@ -1,5 +1,5 @@
 """BASELINE configs[1] latency: ONE 700^2 WaveEnv (triple-ring design + Gaussian source), env(action) = 100 RK4 steps + energy
-trace, replayed from the captured CUDA graph vs launched kernel by kernel.  Prints one JSON line.
+trace, in the three launch modes of waves_set_graph (default: one launch per step for a small batch).  Prints one JSON line.
   python scripts/bench_single_env.py [actions]"""
 import json
 import os
@@ -17,7 +17,7 @@ def measure(actions=20, steps=100, n=700, device=0):
     dim = wb.TwoDim(15.0, n)
     rng = np.random.default_rng(0)
     out = {}
-    for name, graph in (("graph", True), ("direct", False)):
+    for name, graph in (("default", 1), ("cooperative_multi_step", 2), ("direct", 0)):
         src = wb.RandomPosGaussianSource(dim, [-10.0, -10.0], [-10.0, 10.0], [0.3], [1.0], 1000.0, rng=np.random.default_rng(1))
         env = wb.WaveEnv(dim, design_space=wb.build_triple_ring_design_space(), source=src, integration_steps=steps,
                          actions=actions + 3, rng=np.random.default_rng(2), device=device)

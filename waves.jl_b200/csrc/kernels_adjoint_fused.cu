@@ -14,13 +14,15 @@
 // and D^T the transpose of the 3-band matrix of src/operators.jl:10-22 (its one-sided first / last rows couple the three
 // outermost cells to the edge cell).
 //
-// Temporal blocking in shared memory: a CTA owns a TX x TY tile of ONE wavefield of one environment, loads it with a 4-cell
-// halo (one cell per RK stage), runs the four transposed stages on the tile in shared memory (the stage cotangent's
-// differentiated quantities are exchanged through four shared planes, everything else lives in registers of the thread that
-// owns the cell) and writes the tile once: 12 planes read + 12 written per reverse step instead of 30 per STAGE for the
-// per-stage kernels of kernels_adjoint.cu.  The halo is recomputed redundantly; halo cells go stale one ring per stage and
-// never feed an owned cell.  Two variants: INTERIOR tiles (sigma == 0 in the whole tile region, away from the domain border:
-// mask 1, central stencils only, the three auxiliary cotangents never feed back and are only accumulated) and general tiles.
+// Temporal blocking in shared memory: a CTA owns a 64 x TY tile of ONE wavefield of one environment, loads it with a 4-cell
+// halo (one cell per RK stage), runs the four transposed stages on the tile in shared memory and writes the tile once: 12
+// planes read + 12 written per reverse step instead of 30 per STAGE for the per-stage kernels of kernels_adjoint.cu.  The halo
+// is recomputed redundantly; halo cells go stale one ring per stage and never feed an owned cell.  A thread owns four
+// consecutive cells of a row (float4 global and shared accesses, its own exchanged values in registers between the two phases
+// of a stage).  Shared memory per CTA: 6 planes of w, 3 or 4 exchanged planes of the stage cotangent, 0 / 1 / 3 planes of c^2,
+// each 4 * 512 floats, pitched to the region width so that consecutive threads touch consecutive banks.  Two variants:
+// INTERIOR tiles (sigma == 0 in the whole tile region, away from the domain border: mask 1, central stencils only, the three
+// auxiliary cotangents never feed back and are only accumulated) and general tiles.
 #include <algorithm>
 #include <vector>
 
@@ -28,26 +30,24 @@
 
 namespace {
 
-constexpr int ATX = 64;        // tile width (owned columns)
-constexpr int ASWP = ATX + 12;  // shared row pitch; a tile region is at most ATX + 10 columns wide
-#ifndef WV_ADJ_NT_INT
-#define WV_ADJ_NT_INT 1024
+constexpr int ATX = 64;             // tile width (owned columns)
+constexpr int AWMAX = ATX + 10;     // a tile region is at most ATX + 10 columns wide (4 halo columns per side, + 2 at a domain edge)
+#ifndef WV_ADJ_TY_INT
+#define WV_ADJ_TY_INT 17
 #endif
-#ifndef WV_ADJ_NT_GEN
-#define WV_ADJ_NT_GEN 512
+#ifndef WV_ADJ_TY_GEN
+#define WV_ADJ_TY_GEN 16
 #endif
-#ifndef WV_ADJ_MINB_GEN
-#define WV_ADJ_MINB_GEN 2
-#endif
-constexpr int ATY_INT = 28, ANT_INT = WV_ADJ_NT_INT;  // interior tiles: owned rows, threads (1024: 3 cells per thread, <= 64 registers)
-constexpr int ATY_GEN = 12, ANT_GEN = WV_ADJ_NT_GEN;  // general tiles
-constexpr int AGUARD = 2 * ASWP + 4;        // floats in front of / behind the planes: stencil reads of edge cells stay in bounds
+constexpr int ATY_INT = WV_ADJ_TY_INT, ATY_GEN = WV_ADJ_TY_GEN;  // owned rows of interior / general tiles
+constexpr int ANT = 512;            // threads per CTA; two CTAs per SM (<= 64 registers, <= 113 KB of shared memory each)
+constexpr int AGUARD = 2 * AWMAX + 4;  // floats in front of / behind the planes: stencil reads of edge cells stay in bounds
 
 struct AdjFArgs {
     GridP gp;
     const float *w_in;   // [n_env][12][plane] cotangent before the step
     float *w_out;        // same layout, after it (must not alias w_in: neighbouring tiles read the halo)
     const float *b2[3];  // c^2 planes of the total field at t, t + dt/2, t + dt: [n_env][plane]; nullptr: ambient c0^2
+    int nb;              // distinct planes among b2[0..2]: 0 (none), 1 (a design that does not move) or 3
     // energy cotangent a = dL/dz of sum_k w3[k] E_k(z) (src/env.jl:104-111), z given by its two U planes [n_env][2][plane]:
     const float *pre_u;  // added to w_in BEFORE the step (the reference loop as written), nullptr: none
     const float *post_u; // added to w_out AFTER the step (exact discrete adjoint), nullptr: none
@@ -76,12 +76,122 @@ __device__ __forceinline__ float dT_gen(const float *__restrict__ v, int o, int 
     return acc;
 }
 
-template <bool INTERIOR, int TY, int NT>
-__global__ void __launch_bounds__(NT, INTERIOR ? 1 : WV_ADJ_MINB_GEN) k_adjoint_step(const __grid_constant__ AdjFArgs A) {
-    constexpr int SH = TY + 10, PL = SH * ASWP;            // rows / floats of one shared plane
-    constexpr int NW = INTERIOR ? 3 : 6;                   // planes of w kept in shared memory
-    constexpr int NL = INTERIOR ? 3 : 4;                   // exchanged planes of the stage cotangent
-    constexpr int CPT = ((ATX + 10) * SH + NT - 1) / NT;   // cells per thread
+// (D^T v) of the four cells c0 .. c0+3 of a group with the one-sided rows: along x (di = 1: coordinates i0 .. i0+3, cells behind
+// the domain give 0) or along y (di = 0: the four cells share the row i0).  Out of line: only groups / rows on the domain
+// border come here, and the callers stay within their register budget.
+__device__ __noinline__ float4 dT4_edge(const float *__restrict__ v, int c0, int st, int i0, int di, int n, const GridP &gp) {
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * di;
+        r[j] = i < n ? dT_gen(v, c0 + j, st, i, n, gp) : 0.f;
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
+
+// Interior tiles, vectorised along x: the region of an interior tile is always 72 columns wide (full halos) and starts on a
+// multiple of 4 columns, so a thread owns FOUR consecutive cells of one row: global memory moves as float4, its own cells'
+// exchanged values stay in registers between the two phases of a stage, the y neighbours arrive as two LDS.128 per plane and
+// the x neighbours as two scalar loads -- a quarter of the shared-memory and address instructions of the scalar form.
+// 512 threads x 4 cells cover up to 27 rows of 72 (TY <= 17).
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ float4 operator*(float s, float4 v) { return make_float4(s * v.x, s * v.y, s * v.z, s * v.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 fma4(float s, float4 a, float4 b) { return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w)); }
+
+template <int TY>
+__global__ void __launch_bounds__(ANT, 2) k_adjoint_step_int4(const __grid_constant__ AdjFArgs A) {
+    constexpr int WR = ATX + 8, GPR = WR / 4;     // region width, 4-cell groups per row
+    constexpr int PLF = 4 * ANT;                   // floats per plane
+    static_assert((TY + 10) * GPR <= ANT + GPR * 2 && (TY + 8) * GPR <= ANT, "an interior region must fit one group per thread");
+    const GridP &gp = A.gp;
+    const int nxp = gp.nxp;
+    const long long P = gp.plane;
+    const int tx = blockIdx.x % A.tiles_x, ty = blockIdx.x / A.tiles_x;
+    const int e = blockIdx.y >> 1, wf = blockIdx.y & 1;
+    const int x0 = A.x_org + tx * ATX, y0 = A.y_org + ty * TY;
+    if (y0 >= A.y_end) return;
+    const int y1 = min(y0 + TY, A.y_end);
+    const int L = x0 - 4, T0 = y0 - 4, Hr = y1 + 4 - T0;   // interior tiles keep full halos inside the domain
+    const int ngrp = Hr * GPR;
+    float *Wt = adj_sm + AGUARD, *Lx = Wt + 6 * PLF, *Bt = Lx + 3 * PLF;
+    const float *win = A.w_in + ((long long)e * 12 + wf * 6) * P;
+    float *wout = A.w_out + ((long long)e * 12 + wf * 6) * P;
+    const int nb = wf == 0 ? A.nb : 0;
+
+    const int t = threadIdx.x, c0 = 4 * t;            // first of this thread's four cells: float c0 of every plane
+    const bool act = t < ngrp;
+    const int lr = act ? t / GPR : 0, lc = act ? 4 * (t - lr * GPR) : 0;
+    const int q = (T0 + lr) * nxp + L + lc;           // first cell in a global plane (16-byte aligned)
+#pragma unroll
+    for (int f = 0; f < 6; ++f) st4(Wt + f * PLF + c0, ld4(win + f * P + q));
+    if (A.pre_u) {
+        const float *up = A.pre_u + (long long)e * 2 * P + q;
+        const float4 ut = ld4(up), ui = ld4(up + P), d = ut - ui;
+        const float4 a4 = wf == 0 ? A.two_dO * (A.pre_w[0] * ut + A.pre_w[2] * d) : A.two_dO * (A.pre_w[1] * ui - A.pre_w[2] * d);
+        st4(Wt + c0, ld4(Wt + c0) + a4);
+    }
+    for (int tb = 0; tb < nb; ++tb) st4(Bt + tb * PLF + c0, ld4(A.b2[tb] + (long long)e * P + q));
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 oU = z4, oVx = z4, oVy = z4, sU = z4, sVx = z4, sVy = z4, sg = z4;
+    __syncthreads();
+
+    const float dt = gp.dt, cp = gp.g_central[1];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {   // stages 4, 3, 2, 1 of the forward step
+        const float a = (s == 0 || s == 3) ? dt * (1.0f / 6.0f) : dt * (1.0f / 3.0f);
+        const float be = s == 0 ? 0.0f : (s == 1 ? dt : 0.5f * dt);
+        const int tau = s == 0 ? 2 : (s == 3 ? 0 : 1);
+        // phase A: l = a w + be l_prev; exchange b lU, lVx, lVy
+        const float4 lU = fma4(be, oU, a * ld4(Wt + c0));
+        const float4 b4 = nb == 0 ? make_float4(gp.b0, gp.b0, gp.b0, gp.b0) : ld4(Bt + (nb == 1 ? 0 : tau) * PLF + c0);
+        const float4 qc = b4 * lU;
+        const float4 vx = fma4(be, oVx, a * ld4(Wt + PLF + c0)), vy = fma4(be, oVy, a * ld4(Wt + 2 * PLF + c0));
+        st4(Lx + c0, qc);
+        st4(Lx + PLF + c0, vx);
+        st4(Lx + 2 * PLF + c0, vy);
+        __syncthreads();
+        // phase B: l_new = J^T l with central rows only (D^T = -D)
+        const float ql = Lx[c0 - 1], qr = Lx[c0 + 4], vl = Lx[PLF + c0 - 1], vr = Lx[PLF + c0 + 4];
+        const float4 qu = ld4(Lx + c0 - WR), qd = ld4(Lx + c0 + WR), yu = ld4(Lx + 2 * PLF + c0 - WR), yd = ld4(Lx + 2 * PLF + c0 + WR);
+        const float4 dxv = make_float4(vl - vx.y, vx.x - vx.z, vx.y - vx.w, vx.z - vr);
+        const float4 dxq = make_float4(ql - qc.y, qc.x - qc.z, qc.y - qc.w, qc.z - qr);
+        oU = cp * (dxv + (yu - yd));
+        oVx = cp * dxq;
+        oVy = cp * (qu - qd);
+        sg = sg + lU;
+        sU = sU + oU;
+        sVx = sVx + oVx;
+        sVy = sVy + oVy;
+        __syncthreads();
+    }
+    const int y = T0 + lr;
+    if (!act || lc < 4 || lc >= WR - 4 || y < y0 || y >= y1) return;   // whole groups are owned or not (x0 = L + 4)
+    float4 vU = ld4(Wt + c0) + sU;
+    if (A.post_u) {
+        const float *up = A.post_u + (long long)e * 2 * P + q;
+        const float4 ut = ld4(up), ui = ld4(up + P), d = ut - ui;
+        vU = vU + (wf == 0 ? A.two_dO * (A.post_w[0] * ut + A.post_w[2] * d) : A.two_dO * (A.post_w[1] * ui - A.post_w[2] * d));
+    }
+    st4(wout + q, vU);
+    st4(wout + P + q, ld4(Wt + PLF + c0) + sVx);
+    st4(wout + 2 * P + q, ld4(Wt + 2 * PLF + c0) + sVy);
+    st4(wout + 3 * P + q, ld4(Wt + 3 * PLF + c0) + sg);
+    st4(wout + 4 * P + q, ld4(Wt + 4 * PLF + c0) + sg);
+    st4(wout + 5 * P + q, ld4(Wt + 5 * PLF + c0) - sg);
+}
+
+// General tiles (PML strips, corners, domain border), vectorised along x like the interior form: four consecutive cells of a row
+// per thread, planes pitched to a multiple of 4 columns.  The one-sided rows of D^T (the three outermost cells of the domain in
+// each direction) are taken by a scalar path that only the groups / rows holding such cells enter.  Columns behind the domain's
+// last one (the pad of a pitched row) are carried along as cells nobody reads.
+template <int TY>
+__global__ void __launch_bounds__(ANT, 2) k_adjoint_step_gen4(const __grid_constant__ AdjFArgs A) {
+    constexpr int PLF = 4 * ANT;
+    static_assert((TY + 10) * ((AWMAX + 3) / 4) <= ANT, "a general region must fit one group per thread");
     const GridP &gp = A.gp;
     const int nx = gp.nx, ny = gp.ny_global, nxp = gp.nxp;
     const long long P = gp.plane;
@@ -89,140 +199,136 @@ __global__ void __launch_bounds__(NT, INTERIOR ? 1 : WV_ADJ_MINB_GEN) k_adjoint_
     const int e = blockIdx.y >> 1, wf = blockIdx.y & 1;
     const int x0 = A.x_org + tx * ATX, y0 = A.y_org + ty * TY;
     if (x0 >= nx || y0 >= A.y_end) return;
-    if (!INTERIOR && x0 >= A.skip_x0 && x0 + ATX <= A.skip_x1 && y0 >= A.skip_y0 && y0 + TY <= A.skip_y1) return;
+    if (x0 >= A.skip_x0 && x0 + ATX <= A.skip_x1 && y0 >= A.skip_y0 && y0 + TY <= A.skip_y1) return;
     const int x1 = min(x0 + ATX, nx), y1 = min(y0 + TY, A.y_end);
-    // tile region [L, R) x [T0, B): 4 halo cells per side, clipped to the domain; a region that would end 1 or 2 cells short of
-    // the domain edge is extended to it (the transposed one-sided rows couple the edge cell to its two inner neighbours)
     const int L = max(x0 - 4, 0), T0 = max(y0 - 4, 0);
     int R = min(x1 + 4, nx), B = min(y1 + 4, ny);
     if (nx - R <= 2) R = nx;
     if (ny - B <= 2) B = ny;
-    const int Wr = R - L, ncell = Wr * (B - T0);
-
-    float *Wt = adj_sm + AGUARD;        // NW planes: w of this tile (U, Vx, Vy[, Psix, Psiy, Omega])
-    float *Lx = Wt + NW * PL;           // NL planes: INTERIOR {b lU, lVx, lVy}; general {qx, qy, lVx, lVy}
+    const int Wp = (R - L + 3) & ~3, gpr = Wp >> 2, ngrp = gpr * (B - T0);   // pitch (floats), groups per row, groups
+    float *Wt = adj_sm + AGUARD, *Lx = Wt + 6 * PLF, *Bt = Lx + 4 * PLF;
     const float *win = A.w_in + ((long long)e * 12 + wf * 6) * P;
     float *wout = A.w_out + ((long long)e * 12 + wf * 6) * P;
+    const int nb = wf == 0 ? A.nb : 0;
 
-    // ---- ownership: cell c = tid + k NT of the region, row-major ----
-    int off[CPT];
+    const int t = threadIdx.x, c0 = 4 * t;
+    const bool act = t < ngrp;
+    const int lr = act ? t / gpr : 0, lc = act ? 4 * (t - lr * gpr) : 0;
+    const int xg = L + lc, y = T0 + lr;               // first column of the group, its row
+    const int q = y * nxp + xg;
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-        const int c = threadIdx.x + k * NT;
-        if (c < ncell) {
-            const int lr = c / Wr, lc = c - lr * Wr;
-            off[k] = lr * ASWP + lc;
-        } else
-            off[k] = -1;
+    for (int f = 0; f < 6; ++f) st4(Wt + f * PLF + c0, ld4(win + f * P + q));
+    if (A.pre_u) {
+        const float *up = A.pre_u + (long long)e * 2 * P + q;
+        const float4 ut = ld4(up), ui = ld4(up + P), d = ut - ui;
+        const float4 a4 = wf == 0 ? A.two_dO * (A.pre_w[0] * ut + A.pre_w[2] * d) : A.two_dO * (A.pre_w[1] * ui - A.pre_w[2] * d);
+        st4(Wt + c0, ld4(Wt + c0) + a4);
     }
-    const int gq0 = T0 * nxp + L;
-    auto gq_of = [&](int o) { const int lr = o / ASWP; return gq0 + lr * nxp + (o - lr * ASWP); };  // global offset in a plane
-    // ---- load w (+ the cotangent injected before the step) ----
-#pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-        if (off[k] < 0) continue;
-        const int q = gq_of(off[k]);
-#pragma unroll
-        for (int f = 0; f < NW; ++f) Wt[f * PL + off[k]] = win[f * P + q];
-        if (A.pre_u) Wt[off[k]] += energy_cot(A.pre_u + (long long)e * 2 * P + q, P, wf, A.pre_w, A.two_dO);
-    }
-    float oU[CPT], oVx[CPT], oVy[CPT], og[CPT], sU[CPT], sVx[CPT], sVy[CPT], sg[CPT];
-#pragma unroll
-    for (int k = 0; k < CPT; ++k) oU[k] = oVx[k] = oVy[k] = og[k] = sU[k] = sVx[k] = sVy[k] = sg[k] = 0.0f;
+    for (int tb = 0; tb < nb; ++tb) st4(Bt + tb * PLF + c0, ld4(A.b2[tb] + (long long)e * P + q));
+    const float sy = __ldg(gp.sigma + y);
+    const bool yedge = y == 0 || y == ny - 1;
+    // Dirichlet mask of the four cells as bits (1: the cell is on the domain border, its lU is masked to zero)
+    const unsigned mb = (yedge ? 15u : 0u) | ((xg == 0 || xg == nx - 1) ? 1u : 0u) | (xg + 1 == nx - 1 ? 2u : 0u) |
+                        (xg + 2 == nx - 1 ? 4u : 0u) | (xg + 3 == nx - 1 ? 8u : 0u);
+    // groups / rows that hold one of the three outermost cells of the domain (or pad columns) take the scalar one-sided path
+    const bool xspecial = xg <= 2 || xg + 3 >= nx - 3, yspecial = y <= 2 || y >= ny - 3;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 oU = z4, oVx = z4, oVy = z4, og = z4, sU = z4, sVx = z4, sVy = z4, sg = z4;
     __syncthreads();
 
-    const float dt = gp.dt;
-    const float cm = gp.g_central[0], cp = gp.g_central[1];
+    const float dt = gp.dt, cm = gp.g_central[0], cp = gp.g_central[1];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {   // stages 4, 3, 2, 1 of the forward step
         const float a = (s == 0 || s == 3) ? dt * (1.0f / 6.0f) : dt * (1.0f / 3.0f);
         const float be = s == 0 ? 0.0f : (s == 1 ? dt : 0.5f * dt);
         const int tau = s == 0 ? 2 : (s == 3 ? 0 : 1);
-        const float *b2p = (wf == 0 && A.b2[tau]) ? A.b2[tau] + (long long)e * P : nullptr;
-        // phase A: the differentiated quantities of the stage cotangent l = a w + be l_prev
-#pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            if (off[k] < 0) continue;
-            const int o = off[k];
-            const float b = b2p ? __ldg(b2p + gq_of(o)) : gp.b0;
-            const float lU = a * Wt[o] + be * oU[k];
-            if (INTERIOR) {
-                Lx[o] = b * lU;
-                Lx[PL + o] = a * Wt[PL + o] + be * oVx[k];
-                Lx[2 * PL + o] = a * Wt[2 * PL + o] + be * oVy[k];
-            } else {
-                const int lr = o / ASWP, lc = o - lr * ASWP, x = L + lc, y = T0 + lr;
-                const float sx = __ldg(gp.sigma + x), sy = __ldg(gp.sigma + y);
-                const float m = (x == 0 || x == nx - 1 || y == 0 || y == ny - 1) ? 0.0f : 1.0f;
-                const float lPx = a * Wt[3 * PL + o] + be * og[k], lPy = a * Wt[4 * PL + o] + be * og[k];
-                const float mU = m * lU;
-                Lx[o] = b * (mU + sy * lPy);
-                Lx[PL + o] = b * (mU + sx * lPx);
-                Lx[2 * PL + o] = a * Wt[PL + o] + be * oVx[k];
-                Lx[3 * PL + o] = a * Wt[2 * PL + o] + be * oVy[k];
-            }
+        // phase A: l = a w + be l_prev; exchange qx = b (m lU + sy lPsiy), qy = b (m lU + sx lPsix), lVx, lVy
+        float4 lU = fma4(be, oU, a * ld4(Wt + c0));
+        if (mb) {   // (rare: border rows / columns only)
+            lU.x = (mb & 1u) ? 0.f : lU.x;
+            lU.y = (mb & 2u) ? 0.f : lU.y;
+            lU.z = (mb & 4u) ? 0.f : lU.z;
+            lU.w = (mb & 8u) ? 0.f : lU.w;
+        }
+        {
+            const float4 sx = ld4(gp.sigma + xg);   // (L1-resident; the profile is allocated with 4 floats of padding)
+            const float4 b4 = nb == 0 ? make_float4(gp.b0, gp.b0, gp.b0, gp.b0) : ld4(Bt + (nb == 1 ? 0 : tau) * PLF + c0);
+            const float4 lPx = fma4(be, og, a * ld4(Wt + 3 * PLF + c0)), lPy = fma4(be, og, a * ld4(Wt + 4 * PLF + c0));
+            st4(Lx + c0, b4 * (lU + sy * lPy));
+            st4(Lx + PLF + c0, b4 * (lU + sx * lPx));
+            st4(Lx + 2 * PLF + c0, fma4(be, oVx, a * ld4(Wt + PLF + c0)));
+            st4(Lx + 3 * PLF + c0, fma4(be, oVy, a * ld4(Wt + 2 * PLF + c0)));
         }
         __syncthreads();
         // phase B: l_new = J^T l
-#pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            if (off[k] < 0) continue;
-            const int o = off[k];
-            const float lU = a * Wt[o] + be * oU[k];
-            if (INTERIOR) {
-                const float *q = Lx, *lvx = Lx + PL, *lvy = Lx + 2 * PL;
-                oU[k] = (cm * lvx[o + 1] + cp * lvx[o - 1]) + (cm * lvy[o + ASWP] + cp * lvy[o - ASWP]);
-                oVx[k] = cm * q[o + 1] + cp * q[o - 1];
-                oVy[k] = cm * q[o + ASWP] + cp * q[o - ASWP];
-                sg[k] += lU;
-            } else {
-                const int lr = o / ASWP, lc = o - lr * ASWP, x = L + lc, y = T0 + lr;
-                const float sx = __ldg(gp.sigma + x), sy = __ldg(gp.sigma + y);
-                const float m = (x == 0 || x == nx - 1 || y == 0 || y == ny - 1) ? 0.0f : 1.0f;
-                const float lOm = a * Wt[5 * PL + o] - be * og[k];
-                const float mU = m * lU;
-                const float *qx = Lx, *qy = Lx + PL, *lvx = Lx + 2 * PL, *lvy = Lx + 3 * PL;
-                oU[k] = -(sx + sy) * mU + dT_gen(lvx, o, 1, x, nx, gp) + dT_gen(lvy, o, ASWP, y, ny, gp) + (sx * sy) * lOm;
-                oVx[k] = dT_gen(qx, o, 1, x, nx, gp) - sx * lvx[o];
-                oVy[k] = dT_gen(qy, o, ASWP, y, ny, gp) - sy * lvy[o];
-                og[k] = mU;
-                sg[k] += mU;
+        {
+            const float *qx = Lx, *qy = Lx + PLF, *lvx = Lx + 2 * PLF, *lvy = Lx + 3 * PLF;
+            const float4 sx = ld4(gp.sigma + xg);
+            // (one derivative at a time, each result folded into its output at once: the live set stays within 64 registers)
+            {   // new lVx = Dx^T qx - sx lVx
+                const float4 vx = ld4(lvx + c0);
+                float4 d;
+                if (xspecial)
+                    d = dT4_edge(qx, c0, 1, xg, 1, nx, gp);
+                else {
+                    const float4 qc = ld4(qx + c0);
+                    d = cp * make_float4(qx[c0 - 1] - qc.y, qc.x - qc.z, qc.y - qc.w, qc.z - qx[c0 + 4]);   // central rows: cm = -cp
+                }
+                oVx = d - sx * vx;
+                sVx = sVx + oVx;
+                // Dx^T lVx, first part of the new lU
+                if (xspecial)
+                    oU = dT4_edge(lvx, c0, 1, xg, 1, nx, gp);
+                else
+                    oU = cp * make_float4(lvx[c0 - 1] - vx.y, vx.x - vx.z, vx.y - vx.w, vx.z - lvx[c0 + 4]);
             }
-            sU[k] += oU[k];
-            sVx[k] += oVx[k];
-            sVy[k] += oVy[k];
+            {   // new lVy = Dy^T qy - sy lVy
+                const float4 d = yspecial ? dT4_edge(qy, c0, Wp, y, 0, ny, gp) : cp * (ld4(qy + c0 - Wp) - ld4(qy + c0 + Wp));
+                oVy = d - sy * ld4(lvy + c0);
+                sVy = sVy + oVy;
+            }
+            oU = oU + (yspecial ? dT4_edge(lvy, c0, Wp, y, 0, ny, gp) : cp * (ld4(lvy + c0 - Wp) - ld4(lvy + c0 + Wp)));
+            {
+                const float4 lOm = a * ld4(Wt + 5 * PLF + c0) - be * og;
+                oU = oU + (sy * sx) * lOm - (sx + make_float4(sy, sy, sy, sy)) * lU;
+            }
+            sU = sU + oU;
+            og = lU;
+            sg = sg + lU;
+            (void)cm;
         }
         __syncthreads();
     }
-
-    // ---- w' = w + sum of the four stage results (+ the cotangent injected after the step), owned cells only ----
+    if (!act || y < y0 || y >= y1) return;
+    // owned columns: [x0, x1); a group may straddle x1 (pad columns / a domain whose width is not a multiple of 4)
+    float4 vU = ld4(Wt + c0) + sU;
+    if (A.post_u) {
+        const float *up = A.post_u + (long long)e * 2 * P + q;
+        const float4 ut = ld4(up), ui = ld4(up + P), d = ut - ui;
+        vU = vU + (wf == 0 ? A.two_dO * (A.post_w[0] * ut + A.post_w[2] * d) : A.two_dO * (A.post_w[1] * ui - A.post_w[2] * d));
+    }
+    const float4 r1 = ld4(Wt + PLF + c0) + sVx, r2 = ld4(Wt + 2 * PLF + c0) + sVy, r3 = ld4(Wt + 3 * PLF + c0) + sg,
+                 r4 = ld4(Wt + 4 * PLF + c0) + sg, r5 = ld4(Wt + 5 * PLF + c0) - sg;
+    if (xg >= x0 && xg + 3 < x1) {
+        st4(wout + q, vU);
+        st4(wout + P + q, r1);
+        st4(wout + 2 * P + q, r2);
+        st4(wout + 3 * P + q, r3);
+        st4(wout + 4 * P + q, r4);
+        st4(wout + 5 * P + q, r5);
+    } else {
+        const float v[6][4] = {{vU.x, vU.y, vU.z, vU.w}, {r1.x, r1.y, r1.z, r1.w}, {r2.x, r2.y, r2.z, r2.w},
+                               {r3.x, r3.y, r3.z, r3.w}, {r4.x, r4.y, r4.z, r4.w}, {r5.x, r5.y, r5.z, r5.w}};
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-        if (off[k] < 0) continue;
-        const int o = off[k], lr = o / ASWP, lc = o - lr * ASWP, x = L + lc, y = T0 + lr;
-        if (x < x0 || x >= x1 || y < y0 || y >= y1) continue;
-        const int q = gq0 + lr * nxp + lc;
-        float vU = Wt[o] + sU[k];
-        if (A.post_u) vU += energy_cot(A.post_u + (long long)e * 2 * P + q, P, wf, A.post_w, A.two_dO);
-        wout[q] = vU;
-        wout[P + q] = Wt[PL + o] + sVx[k];
-        wout[2 * P + q] = Wt[2 * PL + o] + sVy[k];
-        if (INTERIOR) {
-            wout[3 * P + q] = win[3 * P + q] + sg[k];
-            wout[4 * P + q] = win[4 * P + q] + sg[k];
-            wout[5 * P + q] = win[5 * P + q] - sg[k];
-        } else {
-            wout[3 * P + q] = Wt[3 * PL + o] + sg[k];
-            wout[4 * P + q] = Wt[4 * PL + o] + sg[k];
-            wout[5 * P + q] = Wt[5 * PL + o] - sg[k];
-        }
+        for (int j = 0; j < 4; ++j)
+            if (xg + j >= x0 && xg + j < x1)
+#pragma unroll
+                for (int f = 0; f < 6; ++f) wout[f * P + q + j] = v[f][j];
     }
 }
 
-template <bool INTERIOR, int TY>
-constexpr size_t adj_smem() {
-    return sizeof(float) * ((size_t)(INTERIOR ? 6 : 10) * (TY + 10) * ASWP + 2 * AGUARD);
-}
+size_t adj_smem_int4(int nb) { return sizeof(float) * ((size_t)(9 + nb) * 4 * ANT + 2 * AGUARD); }
+size_t adj_smem_gen4(int nb) { return sizeof(float) * ((size_t)(10 + nb) * 4 * ANT + 2 * AGUARD); }
 
 // gather the two U planes of every environment of a state: [n_env][12][plane] -> [n_env][2][plane]
 __global__ void k_gather_u(GridP gp, const float *__restrict__ u, float *__restrict__ out) {
@@ -241,11 +347,10 @@ int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, 
     if (gp.ny_own != gp.ny_global) return waves_set_error("fused reverse step: not available on slab handles");
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t ce = cudaFuncSetAttribute(k_adjoint_step<true, ATY_INT, ANT_INT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)adj_smem<true, ATY_INT>());
+        cudaError_t ce = cudaFuncSetAttribute(k_adjoint_step_int4<ATY_INT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)adj_smem_int4(3));
         if (ce == cudaSuccess)
-            ce = cudaFuncSetAttribute(k_adjoint_step<false, ATY_GEN, ANT_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)adj_smem<false, ATY_GEN>());
+            ce = cudaFuncSetAttribute(k_adjoint_step_gen4<ATY_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem_gen4(3));
         if (ce != cudaSuccess) return waves_set_error("fused reverse step: cudaFuncSetAttribute failed (was the library built for sm_100a?)");
         attr_done = true;
     }
@@ -274,6 +379,7 @@ int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, 
     A.w_in = w_in;
     A.w_out = w_out;
     for (int t = 0; t < 3; ++t) A.b2[t] = b2 ? b2[t] : nullptr;
+    A.nb = (!b2 || !b2[0]) ? 0 : ((b2[0] == b2[1] && b2[1] == b2[2]) ? 1 : 3);
     A.pre_u = pre_u;
     A.post_u = post_u;
     for (int k = 0; k < 3; ++k) {
@@ -289,7 +395,7 @@ int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, 
         A.skip_x0 = A.skip_x1 = A.skip_y0 = A.skip_y1 = 0;
         const int tiles_y = (yi1 - yi0 + ATY_INT - 1) / ATY_INT;
         dim3 grd(A.tiles_x * tiles_y, gp.n_env * 2);
-        k_adjoint_step<true, ATY_INT, ANT_INT><<<grd, ANT_INT, adj_smem<true, ATY_INT>(), h->stream>>>(A);
+        k_adjoint_step_int4<ATY_INT><<<grd, ANT, adj_smem_int4(A.nb), h->stream>>>(A);
         h->launches++;
     }
     A.tiles_x = (gp.nx + ATX - 1) / ATX;
@@ -303,7 +409,7 @@ int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, 
     {
         const int tiles_y = (gp.ny_global + ATY_GEN - 1) / ATY_GEN;
         dim3 grd(A.tiles_x * tiles_y, gp.n_env * 2);
-        k_adjoint_step<false, ATY_GEN, ANT_GEN><<<grd, ANT_GEN, adj_smem<false, ATY_GEN>(), h->stream>>>(A);
+        k_adjoint_step_gen4<ATY_GEN><<<grd, ANT, adj_smem_gen4(A.nb), h->stream>>>(A);
         h->launches++;
     }
     return 0;

@@ -66,7 +66,7 @@ namespace {
 #define WV_OCC_INT 12   // resident warps per SM the interior variants are compiled for (12: 168 registers available)
 #endif
 #ifndef WV_MBAR_FAST
-#define WV_MBAR_FAST 0  // 1: the bounded-spin trap of mbar_wait lives in an out-of-line slow path (first try_wait inline)
+#define WV_MBAR_FAST 1  // 1 (measured +2.5%): the bounded-spin trap of mbar_wait lives in an out-of-line slow path (first try_wait inline)
 #endif
 constexpr int PF = 3;        // TMA prefetch distance in rows
 constexpr int PFL2 = WV_PFL2;  // L2 prefetch distance in rows (cp.async.bulk.prefetch.tensor)
@@ -305,15 +305,16 @@ struct WarpCtx {
     int col0;          // this lane's first column
     int bko[3];        // float offset of the slot row holding kd*c^2 at stage-time index tau (the ambient row without cylinders)
     float cyl_ylo, cyl_yhi;  // rows with y outside (cyl_ylo, cyl_yhi) are not touched by any culled cylinder
+    const float *table;      // stage-table row of this step (environment 0)
 };
 
 // c(x,y,t)^2 with every cylinder (list overflow), exact order of src/designs.jl:99-116
-__device__ __noinline__ float speed2_slow(const FusedArgs &A, int e, int tau, float xs, float yv) {
+__device__ __noinline__ float speed2_slow(const FusedArgs &A, const float *table, int e, int tau, float xs, float yv) {
     const EnvParams ep = A.env[e];
     const float *cyl0 = A.cyl0 + (size_t)e * A.cyl_cap * 4, *cyl1 = A.cyl1 + (size_t)e * A.cyl_cap * 4;
     const int ncyl = ep.ncyl;
     const float ti = ep.ti, tf = ep.tf, c0 = A.gp.c0;
-    const float t = A.table[((size_t)e * A.steps + A.step) * STAGE_ROW + tau];
+    const float t = table[(size_t)e * A.steps * STAGE_ROW + tau];
     int cnt = 0;
     float cd = 0.0f;
     for (int k = 0; k < ncyl; ++k) {
@@ -368,11 +369,11 @@ __device__ __noinline__ void speed_row(int uri, int nact, f2 xs, float yv, float
 }
 // same with every cylinder of the design (the culled list overflowed)
 template <int V>
-__device__ __noinline__ void speed_row_slow(const FusedArgs &A, int e, int uri, f2 xs, float yv) {
+__device__ __noinline__ void speed_row_slow(const FusedArgs &A, const float *table, int e, int uri, f2 xs, float yv) {
     using C = Cfg<V>;
     for (int tau = 0; tau < 3; ++tau)
         sts2(uri + (tau == 0 ? C::f_bk(0) : (tau == 1 ? C::f_bk(1) : C::f_bk(2))) * LW,
-             A.kd * mk2(speed2_slow(A, e, tau, xs.x, yv), speed2_slow(A, e, tau, xs.y, yv)));
+             A.kd * mk2(speed2_slow(A, table, e, tau, xs.x, yv), speed2_slow(A, table, e, tau, xs.y, yv)));
 }
 
 // Register state of one warp: rotating windows indexed [stage][march row & 3], one column pair per lane
@@ -677,7 +678,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
         if (c.use_bk) {
             const float yv = A.gp.y[min(max(A.gp.grow0 + c.jbase + c.dir * r, 0), A.gp.ny_global - 1)];
             if (c.nact < 0) {
-                speed_row_slow<V>(A, e, uri, c.xs, yv);
+                speed_row_slow<V>(A, c.table, e, uri, c.xs, yv);
             } else if (yv > c.cyl_ylo && yv < c.cyl_yhi) {
                 speed_row<V>(uri, c.nact, c.xs, yv, A.gp.c0, A.kd);
             } else {  // ambient speed on the whole row
@@ -707,25 +708,29 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
     }
 }
 
+// Body of one work item: blocks 2 k, 2 k + 1 of a variant's range are the total / incident wavefield of item k % n_items of
+// environment k / n_items.  `items` / `n_items` / `epart_off` describe the variant's slice of the work list.
 // PEER: this launch mirrors slab edge rows into the neighbours' ghost rows (a separate instantiation, so that the ordinary
 // kernels carry none of that code: the PML variants are sensitive to their instruction footprint)
 template <int V, bool PEER>
-__global__ void __launch_bounds__(32, V == 3 ? 8 : ((V == 0 || V == 4) ? (WV_SP0 == 1 ? WV_OCC_INT : 8) : WV_OCC_STRIP))
-k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtensorMap map_u7, const __grid_constant__ CUtensorMap map_u6,
-             const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_sh) {
+__device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw, const Item *__restrict__ items, int n_items, int epart_off,
+                                                const CUtensorMap &map_u7, const CUtensorMap &map_u6, const CUtensorMap &map_c,
+                                                const CUtensorMap &map_sh, const float *__restrict__ table, float *__restrict__ out,
+                                                float *__restrict__ epart) {
+    // table: stage-table row of THIS step for environment 0 (environment e: + e * A.steps rows); out: the buffer this step
+    // writes; epart: this step's energy partials (nullptr: none).  The single-step kernels pass A's own values.
     // full variants: map_u7 / map_u6 = boxes of 7 / 6 state planes; lean interior: map_u7 = box of 3 planes, map_u6 = box of 1 plane,
     // map_c = the P planes
     using C = Cfg<V>;
     constexpr bool SX = C::SX, SY = C::SY;
     const int lane = threadIdx.x & 31;
     // one warp per CTA: every item-derived value below is provably CTA-uniform (uniform datapath)
-    long long gw = blockIdx.x;
     const int w0 = (int)(gw & 1);  // two warps (tot, inc) per item, adjacent block indices -> co-scheduled
     gw >>= 1;
-    const int e = (int)(gw / A.n_items), it = (int)(gw - (long long)e * A.n_items);
+    const int e = (int)(gw / n_items), it = (int)(gw - (long long)e * n_items);
     if (e >= A.gp.n_env) return;
     const GridP &gp = A.gp;
-    const Item item = A.items[it];
+    const Item item = items[it];
     const EnvParams ep = A.env[e];
 
     WarpCtx c;
@@ -734,7 +739,8 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     c.bar0 = smem_u32(&smf[C::BAR_OFF]);
     c.w0 = w0;
     c.is_tot = w0 == 0;
-    c.want_e = c.is_tot && A.epart != nullptr;
+    c.want_e = c.is_tot && epart != nullptr;
+    c.table = table;
     c.x0 = item.x0;
     c.nm = item.lb - item.la;
     c.dir = (SY && item.top) ? -1 : 1;
@@ -748,7 +754,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     const bool valid_lane = 2 * lane >= item.vlo && 2 * lane < item.vhi;
     c.mo0 = c.dir > 0 ? item.j0 - item.la : item.lb - item.j1;
     c.mon = valid_lane ? (unsigned)(item.j1 - item.j0) : 0u;
-    c.out_e = A.out + (long long)e * gp.env_stride + (long long)w0 * 6 * gp.plane + min(colA, gp.nxp - 2);
+    c.out_e = out + (long long)e * gp.env_stride + (long long)w0 * 6 * gp.plane + min(colA, gp.nxp - 2);
     c.pc_e = A.pconst + ((long long)e * 2 + w0) * gp.plane + min(colA, gp.nxp - 2);
     c.in_dom = colA < gp.nx;
     c.col0 = colA;
@@ -767,7 +773,7 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
     c.xs = mk2(gp.x[min(colA, gp.nx - 1)], gp.x[min(colB, gp.nx - 1)]);  // columns past nx are never owned
     c.sx = SX ? mk2(gp.sigma[min(colA, gp.nx - 1)], gp.sigma[min(colB, gp.nx - 1)]) : bc2(0.0f);
     c.sxd = c.dirf * c.sx;
-    const float *trow = A.table + ((size_t)e * A.steps + A.step) * STAGE_ROW;
+    const float *trow = table + (size_t)e * A.steps * STAGE_ROW;
     c.sf[0] = trow[3];
     c.sf[1] = trow[4];
     c.sf[2] = trow[5];
@@ -915,11 +921,94 @@ k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtens
             es += __shfl_down_sync(0xffffffffu, es, o);
         }
         if (lane == 0) {
-            float *p = A.epart + ((size_t)e * A.epart_stride + A.epart_off + it) * 3;
+            float *p = epart + ((size_t)e * A.epart_stride + epart_off + it) * 3;
             p[0] = et;
             p[1] = ei;
             p[2] = es;
         }
+    }
+}
+
+template <int V, bool PEER>
+__global__ void __launch_bounds__(32, V == 3 ? 8 : ((V == 0 || V == 4) ? (WV_SP0 == 1 ? WV_OCC_INT : 8) : WV_OCC_STRIP))
+k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtensorMap map_u7, const __grid_constant__ CUtensorMap map_u6,
+             const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_sh) {
+    fused_step_body<V, PEER>(A, blockIdx.x, A.items, A.n_items, A.epart_off, map_u7, map_u6, map_c, map_sh, A.table, A.out, A.epart);
+}
+
+// Small batches (everything resident in one wave at 8 warps per SM): ALL variants of a step in ONE launch, and -- launched
+// cooperatively -- SEVERAL consecutive steps in one launch with a grid-wide barrier between them.  A single 700^2 environment
+// is latency-bound: its step lasts as long as its slowest march, and four launches on forked streams, their joins and the
+// drain / ramp-up between consecutive steps cost more than the marches themselves.  Blocks are ordered slowest variant first
+// (corners, top-bottom strips, left-right strips, interior).
+struct MergedInfo {
+    int blk0[5];      // first block of the corner / top-bottom / left-right / interior ranges, and the grid size
+    int item_off[4];  // first item of variant v in the work list (also its energy-partial offset)
+    int n_items[4];
+    int lean;         // interior range runs the lean variant (V = 4)
+    int nsm;          // SMs of the device; the grid is a multiple of it (see the work permutation in the kernel)
+    int grid;
+    // multi-step (cooperative) launches:
+    int nsteps;            // steps taken by this launch (1: plain launch, no barrier)
+    int cur0;              // buffer index the first step reads
+    float *buf[2];         // the two state buffers
+    float *epart0;         // energy partials of the first step (nullptr: none); step k: + k * epart_step
+    size_t epart_step;
+    unsigned *bar;         // grid barrier counter, zero at launch
+};
+
+// All CTAs of a cooperative launch meet here between two steps.  Every lane publishes its global stores of the step
+// (__threadfence), lane 0 arrives and waits for everybody (bounded spin: a barrier that never completes traps instead of
+// hanging the GPU), and the async proxy is fenced so that the next step's TMA loads see the other CTAs' generic-proxy stores.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target) {
+    __threadfence();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(bar, 1u);
+        unsigned v, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if (v < target && ++spins > (1u << 24)) __trap();
+        } while (v < target);
+    }
+    __syncwarp();
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// MULTI = false: one step, the maps of the buffer it reads in the `a` slots (compile-time addresses, no step loop: the form
+// that costs no registers); MULTI = true: M.nsteps steps with a grid barrier between them, maps selected per step.
+template <bool MULTI>
+__global__ void __launch_bounds__(32, 8)
+k_fused_step_all(const __grid_constant__ FusedArgs A, const __grid_constant__ MergedInfo M, const __grid_constant__ CUtensorMap m7a,
+                 const __grid_constant__ CUtensorMap m6a, const __grid_constant__ CUtensorMap u3a, const __grid_constant__ CUtensorMap u1a,
+                 const __grid_constant__ CUtensorMap m7b, const __grid_constant__ CUtensorMap m6b, const __grid_constant__ CUtensorMap u3b,
+                 const __grid_constant__ CUtensorMap u1b, const __grid_constant__ CUtensorMap mp, const __grid_constant__ CUtensorMap msh) {
+    // Work permutation: the block scheduler deals consecutive blocks round-robin over the SMs, so block i lands on SM i % nsm.
+    // Work item (i % nsm) * per + i / nsm gives every SM `per` CONSECUTIVE items of the variant-sorted list: the warps of an SM
+    // then run the same variant.  A small batch is bound by instruction fetch (each variant's row loop is ~64 KB of code; ncu:
+    // 63 % of the stall samples were `no_instruction` with the variants mixed on every SM), so sharing one loop per SM matters.
+    const int per = gridDim.x / M.nsm;
+    const int b = ((int)blockIdx.x % M.nsm) * per + (int)blockIdx.x / M.nsm;
+#pragma unroll 1
+    for (int k = 0; k < (MULTI ? M.nsteps : 1); ++k) {
+        const int cur = MULTI ? ((M.cur0 + k) & 1) : 0;   // MULTI: the buffer this step reads
+        const CUtensorMap *m7 = cur ? &m7b : &m7a, *m6 = cur ? &m6b : &m6a, *u3 = cur ? &u3b : &u3a, *u1 = cur ? &u1b : &u1a;
+        const float *table = MULTI ? A.table + (size_t)k * STAGE_ROW : A.table;
+        float *out = MULTI ? M.buf[cur ^ 1] : A.out;
+        float *epart = MULTI ? (M.epart0 ? M.epart0 + (size_t)k * M.epart_step : nullptr) : A.epart;
+        if (b >= M.blk0[4]) {
+            // (padding block of the permuted grid: no work, but it takes part in the barriers)
+        } else if (b < M.blk0[1])
+            fused_step_body<3, false>(A, b, A.items + M.item_off[3], M.n_items[3], M.item_off[3], *m7, *m6, mp, msh, table, out, epart);
+        else if (b < M.blk0[2])
+            fused_step_body<2, false>(A, b - M.blk0[1], A.items + M.item_off[2], M.n_items[2], M.item_off[2], *m7, *m6, mp, msh, table, out, epart);
+        else if (b < M.blk0[3])
+            fused_step_body<1, false>(A, b - M.blk0[2], A.items + M.item_off[1], M.n_items[1], M.item_off[1], *m7, *m6, mp, msh, table, out, epart);
+        else if (M.lean)
+            fused_step_body<4, false>(A, b - M.blk0[3], A.items + M.item_off[0], M.n_items[0], M.item_off[0], *u3, *u1, mp, msh, table, out, epart);
+        else
+            fused_step_body<0, false>(A, b - M.blk0[3], A.items + M.item_off[0], M.n_items[0], M.item_off[0], *m7, *m6, mp, msh, table, out, epart);
+        if (MULTI && k + 1 < M.nsteps) grid_barrier(M.bar, (unsigned)(k + 1) * gridDim.x);
     }
 }
 
@@ -977,6 +1066,9 @@ struct FusedPlan {
     int epart_slots = 1;      // steps whose partials d_epart can hold (deferred reduction of short integrations of small batches)
     int *d_bb = nullptr;
     int smem[5] = {0, 0, 0, 0, 0};
+    int smem_all = 0;         // k_fused_step_all: the largest of them
+    unsigned *d_bar = nullptr;  // grid barrier counter of the multi-step launches
+    bool coop_ok = true;      // cooperative launches work on this device / grid
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // the PML variants run beside the interior kernel
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 };
@@ -1080,27 +1172,43 @@ int fused_prepare(waves_handle *h) {
     // environment is latency-bound by the march length, so short slabs (more, redundant, warps) win there
     static const int seg_cap = waves_dev_env("WAVES_DEBUG_SEGCAP", 192);  // developer tuning aid
     static const int seg_div = waves_dev_env("WAVES_DEBUG_SEGDIV", 14000);
-    const int SEG = std::max(16, std::min(seg_cap, (int)(2LL * gp.ny_own * (long long)cols.size() * gp.n_env / seg_div)));
+    int SEG = std::max(16, std::min(seg_cap, (int)(2LL * gp.ny_own * (long long)cols.size() * gp.n_env / seg_div)));
     // the PML rows hold few cells but their variants are the slowest per row: half-length marches there keep the corner kernel
     // off the critical path of a latency-bound (small) batch; no effect on large batches (SEG covers the whole PML width)
-    const int SEG_PML = std::max(8, SEG / 2);
-    auto add_rows = [&](int a, int b, bool interior) {
-        if (b <= a) return;
-        const int seg = interior ? SEG : SEG_PML;
-        int n = (b - a + seg - 1) / seg;
-        // an item may touch only ONE of the domain's first / last rows (it marches towards it)
-        if (gp.grow0 + a < 4 && gp.grow0 + b > gp.ny_global - 4 && n < 2) n = 2;
-        for (int k = 0; k < n; ++k) {
-            int lo = a + (int)((long long)(b - a) * k / n), hi = a + (int)((long long)(b - a) * (k + 1) / n);
-            rows.push_back({lo, hi, interior});
+    auto build_rows = [&](int seg_int) {
+        rows.clear();
+        const int seg_pml = std::max(8, seg_int / 2);
+        auto add_rows = [&](int a, int b, bool interior) {
+            if (b <= a) return;
+            const int seg = interior ? seg_int : seg_pml;
+            int n = (b - a + seg - 1) / seg;
+            // an item may touch only ONE of the domain's first / last rows (it marches towards it)
+            if (gp.grow0 + a < 4 && gp.grow0 + b > gp.ny_global - 4 && n < 2) n = 2;
+            for (int k = 0; k < n; ++k) {
+                int lo = a + (int)((long long)(b - a) * k / n), hi = a + (int)((long long)(b - a) * (k + 1) / n);
+                rows.push_back({lo, hi, interior});
+            }
+        };
+        if (ri1 - ri0 < 16) {
+            add_rows(own0, own1, false);
+        } else {
+            add_rows(own0, ri0, false);
+            add_rows(ri0, ri1, true);
+            add_rows(ri1, own1, false);
         }
     };
-    if (ri1 - ri0 < 16) {
-        add_rows(own0, own1, false);
-    } else {
-        add_rows(own0, ri0, false);
-        add_rows(ri0, ri1, true);
-        add_rows(ri1, own1, false);
+    build_rows(SEG);
+    // a batch that nearly fits into one wave of the single-launch kernel (k_fused_step_all: 8 warps per SM) gets the shortest
+    // marches that still fit: it is latency-bound, and a second, nearly empty wave would double its step time
+    {
+        const long long cap = 8LL * h->sm_count;
+        auto warps = [&]() { return 2LL * (long long)rows.size() * (long long)cols.size() * gp.n_env; };
+        if (SEG == 16 && warps() <= 2 * cap) {
+            int seg = 8;
+            build_rows(seg);
+            while (warps() > cap && seg < 64) build_rows(++seg);
+            if (warps() > cap) build_rows(SEG);
+        }
     }
 
     std::vector<Item> cls[4];
@@ -1136,6 +1244,7 @@ int fused_prepare(waves_handle *h) {
         if (ae == cudaSuccess) ae = cudaMalloc((void **)&p->d_epart, per_step * p->epart_slots);
     }
     if (ae == cudaSuccess) ae = cudaMalloc((void **)&p->d_bb, sizeof(int) * 4);
+    if (ae == cudaSuccess) ae = cudaMalloc((void **)&p->d_bar, sizeof(unsigned));
     for (int k = 0; k < 3 && ae == cudaSuccess; ++k) {
         ae = cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking);
         if (ae == cudaSuccess) ae = cudaEventCreateWithFlags(&p->ev_join[k], cudaEventDisableTiming);
@@ -1158,6 +1267,9 @@ int fused_prepare(waves_handle *h) {
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[V]);
     WV_SET_SMEM(0) WV_SET_SMEM(1) WV_SET_SMEM(2) WV_SET_SMEM(3) WV_SET_SMEM(4)
 #undef WV_SET_SMEM
+    p->smem_all = *std::max_element(p->smem, p->smem + 5);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step_all<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_all);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step_all<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_all);
     if (ce != cudaSuccess) {
         char buf[256];
         snprintf(buf, sizeof(buf), "fused_prepare: cudaFuncSetAttribute: %s (was the library built for sm_100a?)", cudaGetErrorString(ce));
@@ -1194,6 +1306,7 @@ void fused_release(waves_handle *h) {
     if (p->d_items) cudaFree(p->d_items);
     if (p->d_epart) cudaFree(p->d_epart);
     if (p->d_bb) cudaFree(p->d_bb);
+    if (p->d_bar) cudaFree(p->d_bar);
     for (int k = 0; k < 3; ++k) {
         if (p->side[k]) cudaStreamDestroy(p->side[k]);
         if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]);
@@ -1211,6 +1324,12 @@ int fused_item_counts(waves_handle *h, int *n_int, int *n_gen) {
     return 0;
 }
 
+// a batch small enough for the single-launch step kernel (and its multi-step cooperative form)
+bool fused_is_small_batch(waves_handle *h) {
+    FusedPlan *p = plan_of(h, false);
+    return p && !h->peer_on && 2LL * p->off[4] * h->gp.n_env <= 8LL * h->sm_count;
+}
+
 int fused_epart_slots(waves_handle *h) {
     FusedPlan *p = plan_of(h, false);
     return p ? p->epart_slots : 1;
@@ -1224,25 +1343,24 @@ void fused_reduce_deferred(waves_handle *h, int count, float *d_e3, int env_stri
     h->launches++;
 }
 
-// d_e3 (nullable) receives the energies of the state the step READS (frame `step`), not of the one it writes.
-// defer_slot >= 0: keep the partials in slot `defer_slot` instead of reducing them now (fused_reduce_deferred later).
-int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step, float *d_e3, int defer_slot) {
-    FusedPlan *p = plan_of(h, false);
-    if (!p || !h->maps_ready) return waves_set_error("fused step: handle not prepared");
-    for (int e = 0; e < h->gp.n_env; ++e)
-        if (h->h_env[e].has_cplane)
-            return waves_set_error("fused step: a fixed speed plane (waves_set_speed_field) needs WAVES_MODE_EXACT");
-    FusedArgs A;
+static int fused_dbg_flags() {
+    static const int dbg_flags = waves_dev_env("WAVES_DEBUG_FLAGS", 0);
+    return dbg_flags;
+}
+
+// kernel arguments of the step that reads table row `step` and h->u[h->cur]
+static void fused_fill_args(waves_handle *h, FusedPlan *p, FusedArgs &A, const float *d_table, int steps, int step, bool energy, int defer_slot) {
+    const int dbg_flags = fused_dbg_flags();
     A.gp = h->gp;
     A.env = h->d_env;
     A.cyl0 = h->d_cyl0;
     A.cyl1 = h->d_cyl1;
     A.cyl_cap = h->cyl_cap;
-    A.table = d_table;
+    A.table = d_table + (size_t)step * STAGE_ROW;   // row of this step for environment 0 (environment e: + e * steps rows)
     A.steps = steps;
     A.step = step;
     A.out = h->u[h->cur ^ 1];
-    A.epart = d_e3 ? p->d_epart + (defer_slot > 0 ? (size_t)defer_slot * 3 * p->off[4] * h->gp.n_env : 0) : nullptr;
+    A.epart = energy ? p->d_epart + (defer_slot > 0 ? (size_t)defer_slot * 3 * p->off[4] * h->gp.n_env : 0) : nullptr;
     A.epart_stride = p->off[4];
     A.kd = h->gp.g_central[1];
     A.b0kd = h->gp.b0 * A.kd;
@@ -1254,7 +1372,6 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     A.dt6kd = A.dt6 * A.kd;
     A.plane = (unsigned)h->gp.plane;
     A.nxp = (unsigned)h->gp.nxp;
-    static const int dbg_flags = waves_dev_env("WAVES_DEBUG_FLAGS", 0);
     A.dbg = dbg_flags;
     A.cull = (dbg_flags & 4) ? 0 : 1;
     // Where sigma_x (sigma_y) is zero, Psix/Psiy/Omega (the fields whose RHS carries that factor, src/dynamics.jl:172-174) never
@@ -1268,6 +1385,79 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
         A.peer_j0[sd] = h->peer_j0[sd];
         A.peer_dj[sd] = h->peer_dj[sd];
     }
+    A.items = p->d_items;
+    A.n_items = 0;
+    A.epart_off = 0;
+}
+
+static bool fused_small_batch(waves_handle *h, FusedPlan *p) {
+    return !h->peer_on && !(fused_dbg_flags() & 256) && 2LL * p->off[4] * h->gp.n_env <= 8LL * h->sm_count;
+}
+
+static void fused_fill_merged(waves_handle *h, FusedPlan *p, MergedInfo &M, bool lean) {
+    const int order[4] = {3, 2, 1, 0};
+    int blk = 0;
+    for (int k = 0; k < 4; ++k) {
+        const int v = order[k];
+        M.blk0[k] = blk;
+        M.item_off[v] = p->off[v];
+        M.n_items[v] = p->off[v + 1] - p->off[v];
+        blk += 2 * M.n_items[v] * h->gp.n_env;
+    }
+    M.blk0[4] = blk;
+    M.lean = lean ? 1 : 0;
+    M.nsm = h->sm_count;
+    M.grid = ((blk + M.nsm - 1) / M.nsm) * M.nsm;
+    M.nsteps = 1;
+    M.cur0 = h->cur;
+    M.buf[0] = h->u[0];
+    M.buf[1] = h->u[1];
+    M.epart0 = nullptr;
+    M.epart_step = (size_t)3 * p->off[4] * h->gp.n_env;
+    M.bar = p->d_bar;
+}
+
+// `count` consecutive steps (table rows step0 ..) of a small batch in ONE cooperative launch (k_fused_step_all with a grid
+// barrier between steps).  Needs the steady state (lean interior variant) and, with energies, one partials slot per step
+// (slots step0 .. step0 + count - 1).  Returns 0: done; -1: not applicable here (take single steps instead); 1: error.
+int launch_fused_multi(waves_handle *h, const float *d_table, int steps, int step0, int count, bool energy) {
+    FusedPlan *p = plan_of(h, false);
+    if (!p || !h->maps_ready) return waves_set_error("fused step: handle not prepared");
+    if (count < 2 || !p->coop_ok || h->profile || !fused_small_batch(h, p) || h->aux_synced < 1 || (fused_dbg_flags() & (64 | 128 | 512))) return -1;
+    if (energy && step0 + count > p->epart_slots) return -1;
+    for (int e = 0; e < h->gp.n_env; ++e)
+        if (h->h_env[e].has_cplane) return -1;
+    FusedArgs A;
+    fused_fill_args(h, p, A, d_table, steps, step0, energy, 0);
+    MergedInfo M;
+    fused_fill_merged(h, p, M, true);
+    M.nsteps = count;
+    M.epart0 = energy ? p->d_epart + (size_t)step0 * M.epart_step : nullptr;
+    cudaMemsetAsync(p->d_bar, 0, sizeof(unsigned), h->stream);
+    void *args[] = {&A, &M, &h->map_u[0], &h->map_u6[0], &h->map_u3[0], &h->map_u1[0], &h->map_u[1], &h->map_u6[1], &h->map_u3[1], &h->map_u1[1],
+                    &h->map_p, &h->map_shape};
+    cudaError_t ce = cudaLaunchCooperativeKernel((const void *)k_fused_step_all<true>, dim3((unsigned)M.grid), dim3(32), args, (size_t)p->smem_all, h->stream);
+    if (ce != cudaSuccess) {   // e.g. the grid is not co-resident on this device: never try again on this handle
+        cudaGetLastError();
+        p->coop_ok = false;
+        return -1;
+    }
+    h->launches++;
+    h->cur ^= count & 1;
+    return 0;
+}
+
+// d_e3 (nullable) receives the energies of the state the step READS (frame `step`), not of the one it writes.
+// defer_slot >= 0: keep the partials in slot `defer_slot` instead of reducing them now (fused_reduce_deferred later).
+int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step, float *d_e3, int defer_slot) {
+    FusedPlan *p = plan_of(h, false);
+    if (!p || !h->maps_ready) return waves_set_error("fused step: handle not prepared");
+    for (int e = 0; e < h->gp.n_env; ++e)
+        if (h->h_env[e].has_cplane)
+            return waves_set_error("fused step: a fixed speed plane (waves_set_speed_field) needs WAVES_MODE_EXACT");
+    FusedArgs A;
+    fused_fill_args(h, p, A, d_table, steps, step, d_e3 != nullptr, defer_slot);
+    const int dbg_flags = fused_dbg_flags();
     const bool lean = A.skip_aux && !(dbg_flags & 128);
     static const int dbg_skip = waves_dev_env("WAVES_DEBUG_SKIP", 0);  // developer bisecting aid
     if (h->profile) cudaEventRecord(h->ev0, h->stream);
@@ -1286,9 +1476,19 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
             if (h->peer_u[sd][0] && wait32((CUstream)h->stream, (CUdeviceptr)(h->flags + sd), (cuuint32_t)h->peer_steps, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
                 return waves_set_error("fused step: cuStreamWaitValue32 failed");
     }
-    // two warps (= CTAs) per item and environment: the total and the incident wavefield.  The PML variants are
-    // launched on side streams (fork / join with events) so their CTAs fill the tail of the interior kernel.
-    A.items = p->d_items;
+    // two warps (= CTAs) per item and environment: the total and the incident wavefield.
+    // small batch (one wave at 8 warps per SM): every variant in one launch (k_fused_step_all)
+    if (fused_small_batch(h, p)) {
+        MergedInfo M;
+        fused_fill_merged(h, p, M, lean);
+        M.epart0 = A.epart;
+        const int c0 = h->cur, c1 = h->cur ^ 1;
+        k_fused_step_all<false><<<(unsigned)M.grid, 32, p->smem_all, h->stream>>>(A, M, h->map_u[c0], h->map_u6[c0], h->map_u3[c0], h->map_u1[c0],
+                                                                                     h->map_u[c1], h->map_u6[c1], h->map_u3[c1], h->map_u1[c1],
+                                                                                     h->map_p, h->map_shape);
+        h->launches++;
+    } else {
+    // The PML variants are launched on side streams (fork / join with events) so their CTAs fill the tail of the interior kernel.
     const bool fork = !(dbg_flags & 16);
     if (fork) cudaEventRecord(p->ev_fork, h->stream);
     // the interior kernel goes first: the CTAs of the (forked) PML kernels then fill its tail (measured: 1201 -> 1124 us per
@@ -1323,6 +1523,7 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
             cudaEventRecord(p->ev_join[v - 1], st);
             cudaStreamWaitEvent(h->stream, p->ev_join[v - 1], 0);
         }
+    }
     }
     if (h->profile) {
         cudaEventRecord(h->ev1, h->stream);

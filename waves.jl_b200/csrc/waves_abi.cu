@@ -253,7 +253,7 @@ extern "C" int waves_create(const waves_config *cfg, waves_handle **out) {
     ALLOC(h->flags, 2);
     ALLOC(h->d_x, gp.nx);
     ALLOC(h->d_y, ny_global);
-    ALLOC(h->d_sigma, gp.nx);
+    ALLOC(h->d_sigma, gp.nx + 4);  // (+4: the vectorised reverse kernel reads the profile four columns at a time)
     ALLOC(h->d_env, gp.n_env);
     h->cyl_cap = 32;
     ALLOC(h->d_cyl0, (size_t)gp.n_env * h->cyl_cap * 4);
@@ -665,7 +665,9 @@ extern "C" int waves_set_traj_stride(waves_handle *h, int stride) {
 
 extern "C" int waves_set_graph(waves_handle *h, int on) {
     CHECK_H(h);
+    if (on < 0 || on > 2) return fail("waves_set_graph: mode must be 0, 1 or 2");
     h->graph_off = on ? 0 : 1;
+    h->coop_on = on == 2;
     if (!on) graph_drop(h);
     return 0;
 }
@@ -744,10 +746,28 @@ extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, i
         // short integrations of small batches keep the per-warp energy partials of every step and reduce them in ONE launch at
         // the end: a single environment is latency-bound, and a reduction kernel between consecutive steps sits on its critical path
         const bool defer = energy && fused && steps <= fused_epart_slots(h);
-        for (int n = 0; n < steps; ++n) {
+        auto needs_emit = [&](int frame) {
+            return (isave < nsave && save_steps[isave] == frame) || ((u_tot_traj || u_inc_traj) && frame % stride == 0);
+        };
+        for (int n = 0; n < steps;) {
+            // small batches: every step up to the next frame that has to be copied out in ONE cooperative launch
+            if (fused && h->coop_on && (defer || !energy)) {
+                int stop = n + 1;
+                while (stop < steps && !needs_emit(stop)) ++stop;
+                if (stop - n >= 2) {
+                    const int rc = launch_fused_multi(h, h->d_stage, steps, n, stop - n, energy != nullptr);
+                    if (rc == 1) return 1;
+                    if (rc == 0) {
+                        n = stop;
+                        if (emit(n)) return 1;
+                        continue;
+                    }
+                }
+            }
             float *d_e3 = energy ? h->d_energy + 3 * (size_t)(fused ? n : n + 1) : nullptr;
             if (step_any(h, steps, n, mode, d_e3, defer ? n : -1)) return 1;
             if (emit(n + 1)) return 1;
+            ++n;
         }
         if (defer) fused_reduce_deferred(h, steps, h->d_energy, 3 * (steps + 1));
         if (energy && fused) launch_energy(h, h->u[h->cur], h->d_energy + 3 * (size_t)steps, 3 * (steps + 1));
@@ -758,7 +778,8 @@ extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, i
     // into a CUDA graph and replayed by later calls with the same shape: a single environment is launch-bound (a 700^2 step
     // is ~10 us of device work behind 5 launches and 6 event operations), and replaying removes the per-launch host cost.
     // The graph bakes in buffer addresses and which ping-pong buffer is current, so the key below holds all of them.
-    const bool want_graph = fused && !h->graph_off && !h->profile && !h->peer_on && graph_safe_ptr(frames) && graph_safe_ptr(u_tot_traj) &&
+    // (a batch small enough for the multi-step cooperative launches needs no graph: a handful of launches per call)
+    const bool want_graph = fused && !h->graph_off && !h->profile && !h->peer_on && !fused_is_small_batch(h) && graph_safe_ptr(frames) && graph_safe_ptr(u_tot_traj) &&
                             graph_safe_ptr(u_inc_traj) && steps >= 4;
     if (want_graph) {
         uint64_t key[12] = {(uint64_t)steps, (uint64_t)mode, (uint64_t)h->cur, (uint64_t)h->aux_synced, (uint64_t)(energy != nullptr),
@@ -1017,7 +1038,8 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
         const float *w3 = w3_of(i);
         if (fused_rev) {
             speeds(i);
-            const float *b2v[3] = {sp ? B2[0] : nullptr, sp ? B2[1] : nullptr, sp ? B2[2] : nullptr};
+            // (a design that does not move has ONE speed plane: the kernel then stages a single plane in shared memory)
+            const float *b2v[3] = {sp ? B2[0] : nullptr, sp ? B2[design_static ? 0 : 1] : nullptr, sp ? B2[design_static ? 0 : 2] : nullptr};
             const bool pre = adj_mode == WAVES_ADJ_COMPAT && w3, post = adj_mode == WAVES_ADJ_EXACT && w3;
             if (launch_adjoint_step_fused(h, W, WS, b2v, pre ? zslot : nullptr, pre ? w3 : zero3, post ? zslot : nullptr, post ? w3 : zero3))
                 return 1;

@@ -120,6 +120,7 @@ struct waves_handle {
     int64_t graph_replays;
     int graph_cur_after;      // h->cur after the captured run
     int graph_off;            // 1: launch every kernel directly (waves_set_graph)
+    int coop_on;              // 1: small batches take several steps per cooperative launch (waves_set_graph(h, 2))
     int traj_stride;          // U trajectories keep every traj_stride-th frame (waves_set_traj_stride); 0 == 1
 };
 
@@ -155,5 +156,7 @@ int fused_item_counts(waves_handle *h, int *n_int, int *n_gen);
 int source_bbox(waves_handle *h, int env, int *bbox4);
 int waves_set_error(const char *msg);  // sets the thread-local message, returns 1
 int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step, float *d_e3 /*nullable*/, int defer_slot = -1);
+int launch_fused_multi(waves_handle *h, const float *d_table, int steps, int step0, int count, bool energy);  // 0 done, -1 n/a, 1 error
+bool fused_is_small_batch(waves_handle *h);
 int fused_epart_slots(waves_handle *h);
 void fused_reduce_deferred(waves_handle *h, int count, float *d_e3, int env_stride3);

@@ -123,9 +123,10 @@ class Engine:
         """u_tot / u_inc trajectories of integrate keep every `stride`-th frame: (n_env, steps // stride + 1, ny, nx)."""
         check(_lib.lib().waves_set_traj_stride(self._h, int(stride)))
 
-    def set_graph(self, on: bool):
-        """Replay integrate() from a captured CUDA graph (default) or launch every kernel directly."""
-        check(_lib.lib().waves_set_graph(self._h, int(bool(on))))
+    def set_graph(self, mode):
+        """How integrate() issues kernels: 0 / False every kernel directly; 1 / True (default) CUDA graph replay for large
+        batches, one launch per step for small ones; 2 additionally several steps per cooperative launch for small batches."""
+        check(_lib.lib().waves_set_graph(self._h, int(mode)))
 
     def set_adjoint_checkpoint(self, every: int):
         """Reverse pass: checkpoint every `every` steps and re-run one segment at a time (0: automatic, from free memory)."""
