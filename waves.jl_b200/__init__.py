@@ -3,7 +3,7 @@
 The computation lives in csrc/ (hand-written sm_100a CUDA behind the C ABI of include/waves_b200.h);
 this package is the host-side mirror of the reference's call surface for that path.
 """
-from . import _lib
+from . import _lib, bson
 from ._lib import WavesError, build
 from .engine import ADJ_COMPAT, ADJ_EXACT, MODE_EXACT, MODE_FUSED, STEP_ASYNC, Engine
 from .env import AcousticDynamics, Integrator, WaveEnv

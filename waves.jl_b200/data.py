@@ -2,7 +2,7 @@
 form the reference lacks: many WaveEnv stepping in lockstep on one handle.
 
 Only bookkeeping lives here; the integration, the energy signal and the observation image run in the CUDA library.
-Episodes are saved as .npz (the reference writes BSON, src/data.jl:60-71; BSON.jl is not part of this path).
+Episodes are saved as .npz or, with `Episode.save_bson`, in the reference's own BSON layout (src/data.jl:60-71; see bson.py).
 """
 from __future__ import annotations
 
@@ -48,6 +48,11 @@ class Episode:
     def save(self, path: str):
         np.savez_compressed(path, images=np.stack([s[1] for s in self.s]), t=np.stack(self.t), y=np.stack(self.y),
                             designs=np.stack([s[2].table() for s in self.s]), actions=np.stack([a.table() for a in self.a]))
+
+    def save_bson(self, path: str, dim, scatterers: str = "AdjustableRadiiScatterers"):
+        """FileIO.save(episode, path) (src/data.jl:60-62): the (s, a, t, y) document `Episode(path = ...)` loads."""
+        from . import bson
+        bson.save_episode(self, dim, path, scatterers)
 
 
 def generate_episode(policy, env: WaveEnv, reset: bool = True) -> Episode:
