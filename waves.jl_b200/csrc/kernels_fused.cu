@@ -71,6 +71,7 @@ namespace {
 constexpr int PF = 3;        // TMA prefetch distance in rows
 constexpr int PFL2 = WV_PFL2;  // L2 prefetch distance in rows (cp.async.bulk.prefetch.tensor)
 constexpr int CYL_CAP = 12;  // culled cylinders kept per warp
+constexpr int ROWMASK_CAP = 224;  // march rows with a precomputed cylinder mask (16 bits each); rows beyond test every culled cylinder
 constexpr int LW = 64;       // columns per warp window (two per lane)
 constexpr int OWN_W = LW - 8;  // owned columns of a full window (4-column halo per side)
 
@@ -111,7 +112,9 @@ struct Cfg {
     static constexpr int RING_F = RING * SLOT_F;
     static constexpr int CYL_OFF = RING_F;
     static constexpr int BAR_OFF = CYL_OFF + CYL_CAP * 16;  // per culled cylinder: (px, py, r^2, c) x 3 stage times + (y_mid, reach^2, -, -)
-    static constexpr int WARP_F = ((BAR_OFF + RING * 2) + 31) & ~31;  // floats per warp (128-byte multiple)
+    // per march row: bit a set <=> culled cylinder a can touch the row at one of the three stage times (built once per march)
+    static constexpr int MASK_OFF = BAR_OFF + RING * 2;
+    static constexpr int WARP_F = ((MASK_OFF + ROWMASK_CAP / 2) + 31) & ~31;  // floats per warp (128-byte multiple)
     static_assert(PF + 4 * SP + 1 <= RING, "ring too shallow");
     static_assert(!(SY && SP != 1), "the sigma_y window and the ghost rows assume SP == 1");
     // row that holds the ambient kd*c0^2 in windows no cylinder touches (never a TMA target, written once); -1: none
@@ -304,7 +307,6 @@ struct WarpCtx {
     bool peer_any;     // this item owns rows that a neighbouring slab needs as ghost rows (warp-uniform)
     int col0;          // this lane's first column
     int bko[3];        // float offset of the slot row holding kd*c^2 at stage-time index tau (the ambient row without cylinders)
-    float cyl_ylo, cyl_yhi;  // rows with y outside (cyl_ylo, cyl_yhi) are not touched by any culled cylinder
     const float *table;      // stage-table row of this step (environment 0)
 };
 
@@ -338,16 +340,16 @@ __device__ __noinline__ float speed2_slow(const FusedArgs &A, const float *table
 // operand comes by value so no kernel parameter is re-read through a generic pointer.
 // uri = float index of this lane's pair in row 0 of the slot.
 template <int V>
-__device__ __noinline__ void speed_row(int uri, int nact, f2 xs, float yv, float c0, float kd) {
+__device__ __noinline__ void speed_row(int uri, unsigned mask, f2 xs, float yv, float c0, float kd) {
     using C = Cfg<V>;
     int cnt0[3] = {0, 0, 0}, cnt1[3] = {0, 0, 0};
     float cd0[3] = {0.f, 0.f, 0.f}, cd1[3] = {0.f, 0.f, 0.f};
+    // mask (warp-uniform): the culled cylinders whose reach in y covers this row, in list order (the order of the design, so the
+    // speeds of overlapping cylinders add up in the reference's order)
 #pragma unroll 1
-    for (int a = 0; a < nact; ++a) {
-        // meta: (y_mid, reach^2): rows farther than `reach` from y_mid miss the cylinder at all three stage times
-        const float2 meta = *reinterpret_cast<const float2 *>(&smf[C::CYL_OFF + a * 16 + 12]);
-        const float dm = yv - meta.x;
-        if (dm * dm >= meta.y) continue;  // warp-uniform
+    while (mask) {
+        const int a = __ffs(mask) - 1;
+        mask &= mask - 1;
 #pragma unroll
         for (int tau = 0; tau < 3; ++tau) {
             const float4 p = *reinterpret_cast<const float4 *>(&smf[C::CYL_OFF + a * 16 + tau * 4]);  // px, py, r^2, c
@@ -591,6 +593,22 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
     }
 }
 
+// Issue the TMA loads of march row rp (state planes, and where needed U of the incident field and the source shape row) into the
+// ring slot at shared address dst, completing on mbarrier bar.  Warp-uniform operands; the whole warp executes this.
+template <int V>
+__device__ __forceinline__ void issue_row(const WarpCtx &c, int e, uint32_t bar, uint32_t dst, int rp, const CUtensorMap *map_u,
+                                          const CUtensorMap *map_b, const CUtensorMap *map_c, const CUtensorMap *map_sh) {
+    using C = Cfg<V>;
+    const int jp = c.jbase + c.dir * rp;
+    if (C::LEAN) {
+        tma_issue_row_lean(bar, c.tx_bytes, dst, map_u, map_c, c.x0, jp, e * 12 + c.w0 * 6, e * 2 + c.w0, LW * 4);
+        if (c.want_e) tma_issue_one(bar, dst + C::ROW_UI * (LW * 4), map_b, c.x0, jp, e * 12 + 6);
+        if (c.src_win) tma_issue_one(bar, dst + C::ROW_SH * (LW * 4), map_sh, c.x0, jp, e);
+    } else {
+        tma_issue_row(bar, c.tx_bytes, dst, map_u, c.x0, jp, e * 12 + c.w0 * 6, c.src_win, dst + C::ROW_SH * (LW * 4), map_sh, e);
+    }
+}
+
 template <int V, int PH>
 __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, int e, const Body &b, Regs &R, int r,
                                          const CUtensorMap *map_u, const CUtensorMap *map_b, const CUtensorMap *map_c,
@@ -601,19 +619,8 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
     __syncwarp();
     {
         const int rp = r + PF;
-        if (rp >= 0 && rp < c.nm) {  // warp-uniform
-            const uint32_t bar = bar_of<V, PH, PF>(b);
-            const uint32_t dst = c.ring_sa + 4u * (uint32_t)(slot_of<V, PH, PF>(b) - c.lane2);
-            if (C::LEAN) {
-                const int jp = c.jbase + c.dir * rp;
-                tma_issue_row_lean(bar, c.tx_bytes, dst, map_u, map_c, c.x0, jp, e * 12 + c.w0 * 6, e * 2 + c.w0, LW * 4);
-                if (c.want_e) tma_issue_one(bar, dst + C::ROW_UI * (LW * 4), map_b, c.x0, jp, e * 12 + 6);
-                if (c.src_win) tma_issue_one(bar, dst + C::ROW_SH * (LW * 4), map_sh, c.x0, jp, e);
-            }
-            else
-                tma_issue_row(bar, c.tx_bytes, dst, map_u, c.x0, c.jbase + c.dir * rp, e * 12 + c.w0 * 6, c.src_win,
-                              dst + C::ROW_SH * (LW * 4), map_sh, e);
-        }
+        if (rp < c.nm)  // warp-uniform
+            issue_row<V>(c, e, bar_of<V, PH, PF>(b), c.ring_sa + 4u * (uint32_t)(slot_of<V, PH, PF>(b) - c.lane2), rp, map_u, map_b, map_c, map_sh);
         if (PFL2 > 0) {
             const int rl = r + PFL2;
             if (c.lane2 == 0 && rl < c.nm) tma_prefetch_l2_3d(map_u, c.x0, c.jbase + c.dir * rl, e * 12 + c.w0 * 6);
@@ -621,7 +628,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
     }
     // 2. arrival of march row r: stage-0 windows, energy of the owned rows, pass-through of the constant
     //    auxiliary fields, speed field of the row
-    if (r >= 0 && r < c.nm) {
+    if (r < c.nm) {
         mbar_wait(b.bar[0] + PH * 8, b.par);
         const int uri = b.g[0] + PH * C::SLOT_F;
         constexpr int s0 = PH & 3, sm = (s0 + 3) & 3, s2 = (s0 + 2) & 3, sp = (s0 + 1) & 3;
@@ -676,15 +683,18 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
             R.Vy[0][sp] = ghost_row(R.Vy[0][s0], R.Vy[0][sm], R.Vy[0][s2]);
         }
         if (c.use_bk) {
-            const float yv = A.gp.y[min(max(A.gp.grow0 + c.jbase + c.dir * r, 0), A.gp.ny_global - 1)];
+            const int jg = min(max(A.gp.grow0 + c.jbase + c.dir * r, 0), A.gp.ny_global - 1);
             if (c.nact < 0) {
-                speed_row_slow<V>(A, c.table, e, uri, c.xs, yv);
-            } else if (yv > c.cyl_ylo && yv < c.cyl_yhi) {
-                speed_row<V>(uri, c.nact, c.xs, yv, A.gp.c0, A.kd);
-            } else {  // ambient speed on the whole row
-                sts2(uri + C::f_bk(0) * LW, bc2(A.b0kd));
-                sts2(uri + C::f_bk(1) * LW, bc2(A.b0kd));
-                sts2(uri + C::f_bk(2) * LW, bc2(A.b0kd));
+                speed_row_slow<V>(A, c.table, e, uri, c.xs, A.gp.y[jg]);
+            } else {
+                const unsigned mask = r < ROWMASK_CAP ? reinterpret_cast<const unsigned short *>(&smf[C::MASK_OFF])[r] : (1u << c.nact) - 1u;
+                if (mask) {
+                    speed_row<V>(uri, mask, c.xs, A.gp.y[jg], A.gp.c0, A.kd);
+                } else {  // ambient speed on the whole row
+                    sts2(uri + C::f_bk(0) * LW, bc2(A.b0kd));
+                    sts2(uri + C::f_bk(1) * LW, bc2(A.b0kd));
+                    sts2(uri + C::f_bk(2) * LW, bc2(A.b0kd));
+                }
             }
         }
         // the rows rewritten above are TMA targets again RING rows later: order the generic writes before it
@@ -799,7 +809,6 @@ __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw
         const float yb = gp.y[min(max(gp.grow0 + item.lb - 1, 0), gp.ny_global - 1)];
         const float ylo = fminf(ya, yb), yhi = fmaxf(ya, yb);
         int n = 0;
-        float ylo_all = 1e30f, yhi_all = -1e30f;
         for (int k0 = 0; k0 < ep.ncyl; k0 += 32) {
             const int k = k0 + lane;
             float P[3][4];
@@ -837,21 +846,27 @@ __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw
                 const float reach = 0.5f * (pymax_ - pymin_) + mrg;
                 *reinterpret_cast<float4 *>(&smf[C::CYL_OFF + pos * 16 + 12]) = make_float4(0.5f * (pymax_ + pymin_), reach * reach, 0.f, 0.f);
             }
-            if (hit) {
-                ylo_all = fminf(ylo_all, pymin_ - mrg);
-                yhi_all = fmaxf(yhi_all, pymax_ + mrg);
-            }
             n += __popc(bal);
         }
         c.nact = n <= CYL_CAP ? n : -1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            ylo_all = fminf(ylo_all, __shfl_xor_sync(0xffffffffu, ylo_all, o));
-            yhi_all = fmaxf(yhi_all, __shfl_xor_sync(0xffffffffu, yhi_all, o));
-        }
-        c.cyl_ylo = ylo_all;
-        c.cyl_yhi = yhi_all;
         __syncwarp();
+        // which culled cylinders can touch which march row: one 16-bit mask per row, built once (a lane takes every 32nd row),
+        // so the march tests nothing on the rows no cylinder reaches and only the reaching ones elsewhere
+        if (c.nact > 0) {
+            unsigned short *rowmask = reinterpret_cast<unsigned short *>(&smf[C::MASK_OFF]);
+            for (int m = lane; m < c.nm && m < ROWMASK_CAP; m += 32) {
+                const float yv = gp.y[min(max(gp.grow0 + c.jbase + c.dir * m, 0), gp.ny_global - 1)];
+                unsigned bits = 0;
+                for (int a = 0; a < c.nact; ++a) {
+                    // meta: (y_mid, reach^2): rows farther than `reach` from y_mid miss the cylinder at all three stage times
+                    const float2 meta = *reinterpret_cast<const float2 *>(&smf[C::CYL_OFF + a * 16 + 12]);
+                    const float dm = yv - meta.x;
+                    bits |= (dm * dm < meta.y) ? (1u << a) : 0u;
+                }
+                rowmask[m] = (unsigned short)bits;
+            }
+            __syncwarp();
+        }
     }
     c.use_bk = c.nact != 0;
 #pragma unroll
@@ -884,16 +899,23 @@ __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw
     }
 
     const CUtensorMap *map_u = (C::LEAN || c.is_tot) ? &map_u7 : &map_u6;
-    // march rows rb .. rb+3 per loop body; the body starting at -4 only prefetches and warms up.  March row m
-    // lives in ring slot m mod RING, so a body's rows fill one group of the ring.
+    // march rows rb .. rb+3 per loop body.  March row m lives in ring slot m mod RING, so a body's rows fill one group of the
+    // ring.  The first PF rows are requested before the loop; the loop ends with the iteration in which stage 4 produces the last
+    // OWNED row (march row mo0 + rows - 1, at r = that row + 4 SP): a march that does not end on a domain border row owns
+    // nothing in its last 4 rows, so their stages are never run (fused_prepare makes the slab heights multiples of 4, which
+    // makes r_end one too).
     Body b;
-    const int nbody = (c.nm + 4 * C::SP + 4 + 3) / 4;  // bodies -4, 0, 4, ... covering arrivals up to nm-1 and the 4 SP drain rows
-    b.po = c.out_e + (long long)(c.jbase - (4 + 4 * C::SP) * c.dir) * (int)A.nxp;  // the body at -4 stores rows that are never owned
-    int grp = C::NG - 1;  // group of body k = (k - 1) mod NG
-    b.par = 1;            // rows of body k are use number (k - 1) div NG of their slots
+    const int r_end = c.mo0 + (item.j1 - item.j0) + 4 * C::SP;
+    const int nbody = (r_end + 3) / 4;
+#pragma unroll
+    for (int rp = 0; rp < PF; ++rp)
+        if (rp < c.nm) issue_row<V>(c, e, c.bar0 + rp * 8, c.ring_sa + 4u * (uint32_t)(rp * C::SLOT_F), rp, map_u, &map_u6, &map_c, &map_sh);
+    b.po = c.out_e + (long long)(c.jbase - 4 * C::SP * c.dir) * (int)A.nxp;  // stage 4 of body row rb works on march row rb - 4 SP
+    int grp = 0;  // group of body k = k mod NG
+    b.par = 0;    // rows of body k are use number k div NG of their slots
 #pragma unroll 1
     for (int k = 0; k < nbody; ++k) {
-        const int rb = 4 * k - 4;
+        const int rb = 4 * k;
 #pragma unroll
         for (int d = 0; d < C::NG; ++d) {
             int gd = grp - d;
@@ -1071,7 +1093,11 @@ struct FusedPlan {
     bool coop_ok = true;      // cooperative launches work on this device / grid
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // the PML variants run beside the interior kernel
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    // waves_profile: event pairs around the launch sets, read back without a host synchronisation between steps
+    std::vector<cudaEvent_t> pev;
+    int pev_used = 0;
 };
+constexpr int PROFILE_PAIRS = 256;
 
 FusedPlan *plan_of(waves_handle *h, bool create) {
     if (!h->plan && create) h->plan = new FusedPlan();
@@ -1184,10 +1210,11 @@ int fused_prepare(waves_handle *h) {
             int n = (b - a + seg - 1) / seg;
             // an item may touch only ONE of the domain's first / last rows (it marches towards it)
             if (gp.grow0 + a < 4 && gp.grow0 + b > gp.ny_global - 4 && n < 2) n = 2;
-            for (int k = 0; k < n; ++k) {
-                int lo = a + (int)((long long)(b - a) * k / n), hi = a + (int)((long long)(b - a) * (k + 1) / n);
-                rows.push_back({lo, hi, interior});
-            }
+            // slab heights are multiples of 4 rows (the last one takes the remainder): the march loop runs in bodies of 4 rows
+            // and ends with the last owned row, so an aligned slab wastes no iteration
+            const int q = (b - a) / 4;
+            auto cut = [&](int k) { return k >= n ? b : (q >= n ? a + 4 * (int)((long long)q * k / n) : a + (int)((long long)(b - a) * k / n)); };
+            for (int k = 0; k < n; ++k) rows.push_back({cut(k), cut(k + 1), interior});
         };
         if (ri1 - ri0 < 16) {
             add_rows(own0, own1, false);
@@ -1312,8 +1339,24 @@ void fused_release(waves_handle *h) {
         if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]);
     }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    for (cudaEvent_t ev : p->pev) cudaEventDestroy(ev);
     delete p;
     h->plan = nullptr;
+}
+
+// waves_profile: add the durations of the launch sets recorded since the last call to h->fused_ms (synchronises the stream)
+void fused_profile_drain(waves_handle *h) {
+    FusedPlan *p = plan_of(h, false);
+    if (!p || p->pev_used == 0) return;
+    cudaEventSynchronize(p->pev[2 * p->pev_used - 1]);
+    for (int i = 0; i < p->pev_used; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p->pev[2 * i], p->pev[2 * i + 1]) == cudaSuccess) {
+            h->fused_ms += ms;
+            h->fused_launches++;
+        }
+    }
+    p->pev_used = 0;
 }
 
 int fused_item_counts(waves_handle *h, int *n_int, int *n_gen) {
@@ -1460,7 +1503,17 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
     const int dbg_flags = fused_dbg_flags();
     const bool lean = A.skip_aux && !(dbg_flags & 128);
     static const int dbg_skip = waves_dev_env("WAVES_DEBUG_SKIP", 0);  // developer bisecting aid
-    if (h->profile) cudaEventRecord(h->ev0, h->stream);
+    int prof_slot = -1;
+    if (h->profile) {   // event pair of this launch set; no host synchronisation here, so consecutive steps run back to back
+        if (p->pev_used == PROFILE_PAIRS) fused_profile_drain(h);
+        while ((int)p->pev.size() < 2 * (p->pev_used + 1)) {
+            cudaEvent_t ev;
+            if (cudaEventCreate(&ev) != cudaSuccess) return waves_set_error("fused step: cudaEventCreate failed");
+            p->pev.push_back(ev);
+        }
+        prof_slot = p->pev_used++;
+        cudaEventRecord(p->pev[2 * prof_slot], h->stream);
+    }
     if (h->peer_on) {
         // step n may start once both neighbours have finished step n-1: they no longer read the ghost rows this step's
         // peer stores overwrite, and their rows of the state this step reads have landed here
@@ -1525,14 +1578,7 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
         }
     }
     }
-    if (h->profile) {
-        cudaEventRecord(h->ev1, h->stream);
-        cudaEventSynchronize(h->ev1);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-        h->fused_ms += ms;
-        h->fused_launches++;
-    }
+    if (prof_slot >= 0) cudaEventRecord(p->pev[2 * prof_slot + 1], h->stream);
     if (d_e3 && defer_slot < 0) {
         k_energy_reduce<<<h->gp.n_env, 256, 0, h->stream>>>(p->d_epart, p->off[4], h->d_omega, d_e3, 3 * (steps + 1), 0);
         h->launches++;

@@ -1184,6 +1184,7 @@ extern "C" int64_t waves_graph_replays(waves_handle *h) { return h ? h->graph_re
 
 extern "C" int waves_profile(waves_handle *h, int on) {
     CHECK_H(h);
+    fused_profile_drain(h);
     h->profile = on;
     h->fused_ms = 0;
     h->fused_launches = 0;
@@ -1193,6 +1194,7 @@ extern "C" int waves_profile(waves_handle *h, int on) {
 extern "C" int waves_profile_read(waves_handle *h, double *ms, int64_t *n) {
     CHECK_H(h);
     CU_TRY(cudaStreamSynchronize(h->stream));
+    fused_profile_drain(h);
     if (ms) *ms = h->fused_ms;
     if (n) *n = h->fused_launches;
     return 0;

@@ -153,6 +153,7 @@ void launch_gather_u(waves_handle *h, const float *u, float *out);
 int fused_prepare(waves_handle *h);  // work items, tensor maps, smem attribute; 0 on success
 void fused_release(waves_handle *h);
 int fused_item_counts(waves_handle *h, int *n_int, int *n_gen);
+void fused_profile_drain(waves_handle *h);   // waves_profile: collect the recorded launch-set durations (synchronises)
 int source_bbox(waves_handle *h, int env, int *bbox4);
 int waves_set_error(const char *msg);  // sets the thread-local message, returns 1
 int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step, float *d_e3 /*nullable*/, int defer_slot = -1);
