@@ -487,6 +487,19 @@ def test_decimated_trajectory_capture(golden_dir):
     eng.integrate(ts, wb.MODE_FUSED, energy=False, u_tot=dec_t, u_inc=dec_i)
     assert np.array_equal(dec_t, full_t[:, ::5]) and np.array_equal(dec_i, full_i[:, ::5])
     assert np.array_equal(full_t[:, 0], u0[:, 0]) and np.array_equal(full_i[:, 0], u0[:, 6])
+    # device destinations take the SM copy kernel (k_copy_blocks) instead of pitched memcpys: same bytes, saved frames included
+    import torch
+    eng.set_state(u0)
+    dev_t, dev_i = (torch.full((2, 5, ny, nx), -1.0, dtype=torch.float32, device="cuda:0") for _ in range(2))
+    dev_f = torch.full((2, 3, 12, ny, nx), -1.0, dtype=torch.float32, device="cuda:0")
+    eng.integrate(ts, wb.MODE_FUSED, energy=False, save_steps=[0, 7, 20], frames=dev_f, u_tot=dev_t, u_inc=dev_i)
+    state_dev = eng.get_state()
+    eng.set_state(u0)
+    _, host_f = eng.integrate(ts, wb.MODE_FUSED, energy=False, save_steps=[0, 7, 20])
+    assert np.array_equal(dev_t.cpu().numpy(), dec_t) and np.array_equal(dev_i.cpu().numpy(), dec_i)
+    assert np.array_equal(dev_f.cpu().numpy(), host_f)
+    assert np.array_equal(host_f[:, 0], u0) and np.array_equal(host_f[:, 2], state_dev)
+    assert np.array_equal(host_f[:, 1, 0], full_t[:, 7]) and np.array_equal(host_f[:, 1, 6], full_i[:, 7])
     eng.close()
 
 

@@ -656,6 +656,14 @@ static bool graph_safe_ptr(const void *p) {
     return ok;
 }
 
+static bool device_ptr_aligned16(const void *p, int device) {
+    if (!p || ((uintptr_t)p & 15u)) return false;
+    cudaPointerAttributes at;
+    const bool ok = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device == device;
+    cudaGetLastError();
+    return ok;
+}
+
 extern "C" int waves_set_traj_stride(waves_handle *h, int stride) {
     CHECK_H(h);
     if (stride < 1) return fail("waves_set_traj_stride: stride must be >= 1");
@@ -699,11 +707,19 @@ extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, i
     const int stride = h->traj_stride > 0 ? h->traj_stride : 1;
     const size_t traj_frames = (size_t)steps / stride + 1;
     const bool dense = gp.nxp == gp.nx && gp.ny_alloc == gp.ny_own;
+    // destinations in device memory whose layout keeps every block 16-byte aligned are written by a copy kernel
+    const bool al4 = dense && plane_elems % 4 == 0 && gp.env_stride % 4 == 0 && gp.plane % 4 == 0;
+    const bool frames_dev = al4 && device_ptr_aligned16(frames, h->device);
+    const bool traj_dev[2] = {al4 && device_ptr_aligned16(u_tot_traj, h->device), al4 && device_ptr_aligned16(u_inc_traj, h->device)};
     int isave = 0;
     auto emit = [&](int frame) -> int {
         const float *u = h->u[h->cur];
         if (isave < nsave && save_steps[isave] == frame) {
-            if (dense) {
+            if (dense && frames_dev) {
+                // device destination: an SM copy kernel moves this frame of every environment at the HBM copy rate
+                launch_copy_blocks(h, u, frames + (size_t)isave * frame_elems, (long long)frame_elems, (long long)gp.env_stride,
+                                   (long long)(frame_elems * nsave), gp.n_env);
+            } else if (dense) {
                 // dense planes: one strided copy moves this frame of every environment
                 CU_TRY(cudaMemcpy2DAsync(frames + (size_t)isave * frame_elems, sizeof(float) * frame_elems * nsave, u,
                                          sizeof(float) * gp.env_stride, sizeof(float) * frame_elems, gp.n_env, cudaMemcpyDefault, h->stream));
@@ -722,7 +738,10 @@ extern "C" int waves_integrate(waves_handle *h, const float *tspan, int steps, i
                 float *dst = f == 0 ? u_tot_traj : u_inc_traj;
                 if (!dst) continue;
                 const float *src = u + (size_t)f * 6 * gp.plane;
-                if (dense) {
+                if (dense && (f == 0 ? traj_dev[0] : traj_dev[1])) {
+                    launch_copy_blocks(h, src, dst + slot * plane_elems, (long long)plane_elems, (long long)gp.env_stride,
+                                       (long long)(plane_elems * traj_frames), gp.n_env);
+                } else if (dense) {
                     CU_TRY(cudaMemcpy2DAsync(dst + slot * plane_elems, sizeof(float) * plane_elems * traj_frames, src,
                                              sizeof(float) * gp.env_stride, sizeof(float) * plane_elems, gp.n_env, cudaMemcpyDefault, h->stream));
                 } else {

@@ -136,6 +136,8 @@ void launch_energy(waves_handle *h, const float *u, float *d_e3, int frame_strid
 void launch_imresize(waves_handle *h, const float *in, long long env_stride, long long chan_stride, int n_chan, int in_pitch,
                      const float *last, long long last_env_stride, int rx, int ry, float *out);
 void launch_pack_halo(waves_handle *h, const float *u, float *lo, float *hi);
+void launch_copy_blocks(waves_handle *h, const float *src, float *dst, long long elems, long long src_stride, long long dst_stride,
+                        int n_blocks);  // device -> device, everything a multiple of 4 floats
 void launch_unpack_halo(waves_handle *h, float *u, const float *lo, const float *hi);
 
 // ---- kernels_adjoint.cu ----
