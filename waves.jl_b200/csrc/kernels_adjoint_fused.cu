@@ -66,29 +66,6 @@ __device__ __forceinline__ float energy_cot(const float *__restrict__ up, long l
     return wf == 0 ? two_dO * (w3[0] * ut + w3[2] * d) : two_dO * (w3[1] * ui - w3[2] * d);
 }
 
-// (D^T v)[i] along one axis for a cell at coordinate i of n, v read from shared memory at stride `st` around offset o
-__device__ __forceinline__ float dT_gen(const float *__restrict__ v, int o, int st, int i, int n, const GridP &gp) {
-    float acc = 0.0f;
-    if (i + 1 <= n - 2) acc += gp.g_central[0] * v[o + st];   // interior row r = i+1 holds g_central[0] on column r-1
-    if (i - 1 >= 1) acc += gp.g_central[1] * v[o - st];       // interior row r = i-1 holds g_central[1] on column r+1
-    if (i <= 2) acc += (i == 0 ? gp.g_first[0] : (i == 1 ? gp.g_first[1] : gp.g_first[2])) * v[o - i * st];
-    if (i >= n - 3) acc += (i == n - 3 ? gp.g_last[0] : (i == n - 2 ? gp.g_last[1] : gp.g_last[2])) * v[o + (n - 1 - i) * st];
-    return acc;
-}
-
-// (D^T v) of the four cells c0 .. c0+3 of a group with the one-sided rows: along x (di = 1: coordinates i0 .. i0+3, cells behind
-// the domain give 0) or along y (di = 0: the four cells share the row i0).  Out of line: only groups / rows on the domain
-// border come here, and the callers stay within their register budget.
-__device__ __noinline__ float4 dT4_edge(const float *__restrict__ v, int c0, int st, int i0, int di, int n, const GridP &gp) {
-    float r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int i = i0 + j * di;
-        r[j] = i < n ? dT_gen(v, c0 + j, st, i, n, gp) : 0.f;
-    }
-    return make_float4(r[0], r[1], r[2], r[3]);
-}
-
 // Interior tiles, vectorised along x: the region of an interior tile is always 72 columns wide (full halos) and starts on a
 // multiple of 4 columns, so a thread owns FOUR consecutive cells of one row: global memory moves as float4, its own cells'
 // exchanged values stay in registers between the two phases of a stage, the y neighbours arrive as two LDS.128 per plane and
@@ -117,7 +94,9 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_int4(const __grid_const
     const int y1 = min(y0 + TY, A.y_end);
     const int L = x0 - 4, T0 = y0 - 4, Hr = y1 + 4 - T0;   // interior tiles keep full halos inside the domain
     const int ngrp = Hr * GPR;
-    float *Wt = adj_sm + AGUARD, *Lx = Wt + 6 * PLF, *Bt = Lx + 3 * PLF;
+    // (the three auxiliary cotangents of an interior tile feed nothing -- sigma == 0 -- and only receive the sum of the stage
+    // cotangents of their own cell: they are not staged in shared memory, the owned cells read and write them at the end)
+    float *Wt = adj_sm + AGUARD, *Lx = Wt + 3 * PLF, *Bt = Lx + 3 * PLF;
     const float *win = A.w_in + ((long long)e * 12 + wf * 6) * P;
     float *wout = A.w_out + ((long long)e * 12 + wf * 6) * P;
     const int nb = wf == 0 ? A.nb : 0;
@@ -127,7 +106,7 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_int4(const __grid_const
     const int lr = act ? t / GPR : 0, lc = act ? 4 * (t - lr * GPR) : 0;
     const int q = (T0 + lr) * nxp + L + lc;           // first cell in a global plane (16-byte aligned)
 #pragma unroll
-    for (int f = 0; f < 6; ++f) st4(Wt + f * PLF + c0, ld4(win + f * P + q));
+    for (int f = 0; f < 3; ++f) st4(Wt + f * PLF + c0, ld4(win + f * P + q));
     if (A.pre_u) {
         const float *up = A.pre_u + (long long)e * 2 * P + q;
         const float4 ut = ld4(up), ui = ld4(up + P), d = ut - ui;
@@ -179,15 +158,22 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_int4(const __grid_const
     st4(wout + q, vU);
     st4(wout + P + q, ld4(Wt + PLF + c0) + sVx);
     st4(wout + 2 * P + q, ld4(Wt + 2 * PLF + c0) + sVy);
-    st4(wout + 3 * P + q, ld4(Wt + 3 * PLF + c0) + sg);
-    st4(wout + 4 * P + q, ld4(Wt + 4 * PLF + c0) + sg);
-    st4(wout + 5 * P + q, ld4(Wt + 5 * PLF + c0) - sg);
+    st4(wout + 3 * P + q, ld4(win + 3 * P + q) + sg);
+    st4(wout + 4 * P + q, ld4(win + 4 * P + q) + sg);
+    st4(wout + 5 * P + q, ld4(win + 5 * P + q) - sg);
 }
 
 // General tiles (PML strips, corners, domain border), vectorised along x like the interior form: four consecutive cells of a row
-// per thread, planes pitched to a multiple of 4 columns.  The one-sided rows of D^T (the three outermost cells of the domain in
-// each direction) are taken by a scalar path that only the groups / rows holding such cells enter.  Columns behind the domain's
-// last one (the pad of a pitched row) are carried along as cells nobody reads.
+// per thread, planes pitched to a multiple of 4 columns.  The transposed derivative with its one-sided first / last rows
+// (src/operators.jl:3-4) is the CENTRAL transposed stencil with zeros behind the domain plus a rank-one correction on the three
+// outermost cells of each side,
+//     (D^T v)[i] = cp (v[i-1] - v[i+1])  +  (gf0, gf1 - cp, gf2)[i] v[0]        for i = 0, 1, 2
+//                                         +  (gl0, gl1 - cm, gl2)[i-(n-3)] v[n-1]  for i = n-3, n-2, n-1
+// (needs n >= 8 so that the two sides do not meet; waves_adjoint takes the per-stage kernels on smaller grids).  v[0] of a row is
+// the first component of the thread that holds columns 0..3, v[n-1] is read from the exchanged plane; along y the corrections
+// are one extra row read with a per-thread scalar coefficient.  Every thread runs the same few instructions: the border costs
+// two selects and short predicated blocks instead of a divergent out-of-line routine.  Columns behind the domain's last one
+// (the pad of a pitched row) are kept at zero in the exchanged planes.
 template <int TY>
 __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_gen4(const __grid_constant__ AdjFArgs A) {
     constexpr int PLF = 4 * ANT;
@@ -226,17 +212,62 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_gen4(const __grid_const
     }
     for (int tb = 0; tb < nb; ++tb) st4(Bt + tb * PLF + c0, ld4(A.b2[tb] + (long long)e * P + q));
     const float sy = __ldg(gp.sigma + y);
-    const bool yedge = y == 0 || y == ny - 1;
+    const bool ytop = y == 0, ybot = y == ny - 1;
     // Dirichlet mask of the four cells as bits (1: the cell is on the domain border, its lU is masked to zero)
-    const unsigned mb = (yedge ? 15u : 0u) | ((xg == 0 || xg == nx - 1) ? 1u : 0u) | (xg + 1 == nx - 1 ? 2u : 0u) |
+    const unsigned mb = ((ytop || ybot) ? 15u : 0u) | ((xg == 0 || xg == nx - 1) ? 1u : 0u) | (xg + 1 == nx - 1 ? 2u : 0u) |
                         (xg + 2 == nx - 1 ? 4u : 0u) | (xg + 3 == nx - 1 ? 8u : 0u);
-    // groups / rows that hold one of the three outermost cells of the domain (or pad columns) take the scalar one-sided path
-    const bool xspecial = xg <= 2 || xg + 3 >= nx - 3, yspecial = y <= 2 || y >= ny - 3;
+    // pad columns of this group (bits), kept at zero in the exchanged planes: they are the "v[n] = 0" of the last column
+    const unsigned pad = (xg + 1 >= nx ? 2u : 0u) | (xg + 2 >= nx ? 4u : 0u) | (xg + 3 >= nx ? 8u : 0u) | (xg >= nx ? 1u : 0u);
+    const bool xl0 = xg == 0;                                        // columns 0..3: nothing to the left, left one-sided corrections
+    const bool xr0 = xg + 4 >= nx;                                   // nothing inside the domain to the right of this group
+    const bool xrs = R == nx && xg + 3 >= nx - 3 && xg < nx;         // holds one of the three last columns
+    const int oN = (nx - 1 - L) - lc;                                // from this group's first float to column nx-1 of its row
+    const float cm = gp.g_central[0], cp = gp.g_central[1];
+    // coefficient of v[row 0] / v[row ny-1] in (Dy^T v) of this thread's row, and where those rows are (region rows 0 / B-1-T0)
+    const float kyT = y == 0 ? gp.g_first[0] : (y == 1 ? gp.g_first[1] - cp : (y == 2 ? gp.g_first[2] : 0.0f));
+    const float kyB = y == ny - 3 ? gp.g_last[0] : (y == ny - 2 ? gp.g_last[1] - cm : (y == ny - 1 ? gp.g_last[2] : 0.0f));
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // (D^T v) along x of this thread's four cells; own: its values of the plane (registers or re-read)
+    auto dxT = [&](const float *__restrict__ pl, const float4 own) -> float4 {
+        const float l = xl0 ? 0.0f : pl[c0 - 1], r = xr0 ? 0.0f : pl[c0 + 4];
+        float4 d = cp * make_float4(l - own.y, own.x - own.z, own.y - own.w, own.z - r);   // central rows: cm = -cp
+        if (xl0) {
+            d.x = fmaf(gp.g_first[0], own.x, d.x);
+            d.y = fmaf(gp.g_first[1] - cp, own.x, d.y);
+            d.z = fmaf(gp.g_first[2], own.x, d.z);
+        }
+        if (xrs) {
+            const float vN = pl[c0 + oN];
+            const int k0 = xg - (nx - 3);   // cell j of the group is column nx-3 + (k0 + j)
+            const float g0 = gp.g_last[0], g1 = gp.g_last[1] - cm, g2 = gp.g_last[2];
+            auto kr = [&](int k) { return k == 0 ? g0 : (k == 1 ? g1 : (k == 2 ? g2 : 0.0f)); };
+            d.x = fmaf(kr(k0), vN, d.x);
+            d.y = fmaf(kr(k0 + 1), vN, d.y);
+            d.z = fmaf(kr(k0 + 2), vN, d.z);
+            d.w = fmaf(kr(k0 + 3), vN, d.w);
+        }
+        return d;
+    };
+    auto dyT = [&](const float *__restrict__ pl) -> float4 {
+        const float4 u = ytop ? z4 : ld4(pl + c0 - Wp), dn = ybot ? z4 : ld4(pl + c0 + Wp);
+        float4 d = cp * (u - dn);
+        if (kyT != 0.0f) d = fma4(kyT, ld4(pl + c0 - lr * Wp), d);                  // (y <= 2: the region starts at row 0)
+        if (kyB != 0.0f) d = fma4(kyB, ld4(pl + c0 + (ny - 1 - y) * Wp), d);        // (y >= ny-3: the region ends at row ny-1)
+        return d;
+    };
+    auto zero_pad = [&](float4 v) -> float4 {
+        if (pad) {
+            v.x = (pad & 1u) ? 0.f : v.x;
+            v.y = (pad & 2u) ? 0.f : v.y;
+            v.z = (pad & 4u) ? 0.f : v.z;
+            v.w = (pad & 8u) ? 0.f : v.w;
+        }
+        return v;
+    };
     float4 oU = z4, oVx = z4, oVy = z4, og = z4, sU = z4, sVx = z4, sVy = z4, sg = z4;
     __syncthreads();
 
-    const float dt = gp.dt, cm = gp.g_central[0], cp = gp.g_central[1];
+    const float dt = gp.dt;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {   // stages 4, 3, 2, 1 of the forward step
         const float a = (s == 0 || s == 3) ? dt * (1.0f / 6.0f) : dt * (1.0f / 3.0f);
@@ -254,10 +285,10 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_gen4(const __grid_const
             const float4 sx = ld4(gp.sigma + xg);   // (L1-resident; the profile is allocated with 4 floats of padding)
             const float4 b4 = nb == 0 ? make_float4(gp.b0, gp.b0, gp.b0, gp.b0) : ld4(Bt + (nb == 1 ? 0 : tau) * PLF + c0);
             const float4 lPx = fma4(be, og, a * ld4(Wt + 3 * PLF + c0)), lPy = fma4(be, og, a * ld4(Wt + 4 * PLF + c0));
-            st4(Lx + c0, b4 * (lU + sy * lPy));
-            st4(Lx + PLF + c0, b4 * (lU + sx * lPx));
-            st4(Lx + 2 * PLF + c0, fma4(be, oVx, a * ld4(Wt + PLF + c0)));
-            st4(Lx + 3 * PLF + c0, fma4(be, oVy, a * ld4(Wt + 2 * PLF + c0)));
+            st4(Lx + c0, zero_pad(b4 * (lU + sy * lPy)));
+            st4(Lx + PLF + c0, zero_pad(b4 * (lU + sx * lPx)));
+            st4(Lx + 2 * PLF + c0, zero_pad(fma4(be, oVx, a * ld4(Wt + PLF + c0))));
+            st4(Lx + 3 * PLF + c0, zero_pad(fma4(be, oVy, a * ld4(Wt + 2 * PLF + c0))));
         }
         __syncthreads();
         // phase B: l_new = J^T l
@@ -265,29 +296,17 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_gen4(const __grid_const
             const float *qx = Lx, *qy = Lx + PLF, *lvx = Lx + 2 * PLF, *lvy = Lx + 3 * PLF;
             const float4 sx = ld4(gp.sigma + xg);
             // (one derivative at a time, each result folded into its output at once: the live set stays within 64 registers)
-            {   // new lVx = Dx^T qx - sx lVx
+            {   // new lVx = Dx^T qx - sx lVx ; Dx^T lVx is the first part of the new lU
                 const float4 vx = ld4(lvx + c0);
-                float4 d;
-                if (xspecial)
-                    d = dT4_edge(qx, c0, 1, xg, 1, nx, gp);
-                else {
-                    const float4 qc = ld4(qx + c0);
-                    d = cp * make_float4(qx[c0 - 1] - qc.y, qc.x - qc.z, qc.y - qc.w, qc.z - qx[c0 + 4]);   // central rows: cm = -cp
-                }
-                oVx = d - sx * vx;
+                oVx = dxT(qx, ld4(qx + c0)) - sx * vx;
                 sVx = sVx + oVx;
-                // Dx^T lVx, first part of the new lU
-                if (xspecial)
-                    oU = dT4_edge(lvx, c0, 1, xg, 1, nx, gp);
-                else
-                    oU = cp * make_float4(lvx[c0 - 1] - vx.y, vx.x - vx.z, vx.y - vx.w, vx.z - lvx[c0 + 4]);
+                oU = dxT(lvx, vx);
             }
             {   // new lVy = Dy^T qy - sy lVy
-                const float4 d = yspecial ? dT4_edge(qy, c0, Wp, y, 0, ny, gp) : cp * (ld4(qy + c0 - Wp) - ld4(qy + c0 + Wp));
-                oVy = d - sy * ld4(lvy + c0);
+                oVy = dyT(qy) - sy * ld4(lvy + c0);
                 sVy = sVy + oVy;
             }
-            oU = oU + (yspecial ? dT4_edge(lvy, c0, Wp, y, 0, ny, gp) : cp * (ld4(lvy + c0 - Wp) - ld4(lvy + c0 + Wp)));
+            oU = oU + dyT(lvy);
             {
                 const float4 lOm = a * ld4(Wt + 5 * PLF + c0) - be * og;
                 oU = oU + (sy * sx) * lOm - (sx + make_float4(sy, sy, sy, sy)) * lU;
@@ -295,7 +314,6 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_gen4(const __grid_const
             sU = sU + oU;
             og = lU;
             sg = sg + lU;
-            (void)cm;
         }
         __syncthreads();
     }
@@ -327,7 +345,7 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_gen4(const __grid_const
     }
 }
 
-size_t adj_smem_int4(int nb) { return sizeof(float) * ((size_t)(9 + nb) * 4 * ANT + 2 * AGUARD); }
+size_t adj_smem_int4(int nb) { return sizeof(float) * ((size_t)(6 + nb) * 4 * ANT + 2 * AGUARD); }
 size_t adj_smem_gen4(int nb) { return sizeof(float) * ((size_t)(10 + nb) * 4 * ANT + 2 * AGUARD); }
 
 // gather the two U planes of every environment of a state: [n_env][12][plane] -> [n_env][2][plane]

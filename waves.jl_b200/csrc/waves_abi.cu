@@ -892,7 +892,7 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
     // Without the speed-plane gradient the reverse step is one fused launch set (kernels_adjoint_fused.cu) and needs only the
     // two U planes of every stored state (for the energy cotangent); dL/dc needs the forward stage states and runs the
     // per-stage kernels of kernels_adjoint.cu on full stored states.
-    const bool fused_rev = !stagewise && dL_dc == nullptr;
+    const bool fused_rev = !stagewise && dL_dc == nullptr && gp.nx >= 8 && gp.ny_global >= 8;   // (the fused kernel's border form needs 8 cells)
     const size_t slot = fused_rev ? 2 * planes : state;
 
     // scratch: 0 w, 1 wsum (both paths); stagewise: 2 lk, 3 ly, 4 y1, 5 y2, 6 y3 (state-sized); 7: three b^2 planes; 8: dL/dc
