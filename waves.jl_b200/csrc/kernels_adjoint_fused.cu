@@ -38,7 +38,17 @@ constexpr int AWMAX = ATX + 10;     // a tile region is at most ATX + 10 columns
 #ifndef WV_ADJ_TY_GEN
 #define WV_ADJ_TY_GEN 16
 #endif
+#ifndef WV_ADJ_TX_INT
+#define WV_ADJ_TX_INT 64   // owned columns of an interior tile (64 or 32)
+#endif
+#ifndef WV_ADJ_NT_INT
+#define WV_ADJ_NT_INT 512  // threads of an interior CTA (512: two CTAs per SM, 256: four)
+#endif
+#ifndef WV_ADJ_SHFL
+#define WV_ADJ_SHFL 1      // x neighbours of a 4-cell group by warp shuffle (the scalar shared-memory reads are 4-way bank conflicts)
+#endif
 constexpr int ATY_INT = WV_ADJ_TY_INT, ATY_GEN = WV_ADJ_TY_GEN;  // owned rows of interior / general tiles
+constexpr int ATX_INT = WV_ADJ_TX_INT, ANT_INT = WV_ADJ_NT_INT;
 constexpr int ANT = 512;            // threads per CTA; two CTAs per SM (<= 64 registers, <= 113 KB of shared memory each)
 constexpr int AGUARD = 2 * AWMAX + 4;  // floats in front of / behind the planes: stencil reads of edge cells stay in bounds
 
@@ -79,17 +89,17 @@ __device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_fl
 __device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 __device__ __forceinline__ float4 fma4(float s, float4 a, float4 b) { return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w)); }
 
-template <int TY>
-__global__ void __launch_bounds__(ANT, 2) k_adjoint_step_int4(const __grid_constant__ AdjFArgs A) {
-    constexpr int WR = ATX + 8, GPR = WR / 4;     // region width, 4-cell groups per row
-    constexpr int PLF = 4 * ANT;                   // floats per plane
-    static_assert((TY + 10) * GPR <= ANT + GPR * 2 && (TY + 8) * GPR <= ANT, "an interior region must fit one group per thread");
+template <int TY, int TX, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) k_adjoint_step_int4(const __grid_constant__ AdjFArgs A) {
+    constexpr int WR = TX + 8, GPR = WR / 4;      // region width, 4-cell groups per row
+    constexpr int PLF = 4 * NT;                    // floats per plane
+    static_assert((TY + 8) * GPR <= NT, "an interior region must fit one group per thread");
     const GridP &gp = A.gp;
     const int nxp = gp.nxp;
     const long long P = gp.plane;
     const int tx = blockIdx.x % A.tiles_x, ty = blockIdx.x / A.tiles_x;
     const int e = blockIdx.y >> 1, wf = blockIdx.y & 1;
-    const int x0 = A.x_org + tx * ATX, y0 = A.y_org + ty * TY;
+    const int x0 = A.x_org + tx * TX, y0 = A.y_org + ty * TY;
     if (y0 >= A.y_end) return;
     const int y1 = min(y0 + TY, A.y_end);
     const int L = x0 - 4, T0 = y0 - 4, Hr = y1 + 4 - T0;   // interior tiles keep full halos inside the domain
@@ -132,9 +142,26 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_int4(const __grid_const
         st4(Lx + c0, qc);
         st4(Lx + PLF + c0, vx);
         st4(Lx + 2 * PLF + c0, vy);
+#if WV_ADJ_SHFL
+        float ql = __shfl_up_sync(0xffffffffu, qc.w, 1), qr = __shfl_down_sync(0xffffffffu, qc.x, 1);
+        float vl = __shfl_up_sync(0xffffffffu, vx.w, 1), vr = __shfl_down_sync(0xffffffffu, vx.x, 1);
+#endif
         __syncthreads();
         // phase B: l_new = J^T l with central rows only (D^T = -D)
+#if WV_ADJ_SHFL
+        // the x neighbours sit in the neighbouring lanes' registers (a group that starts / ends a row gets a value of another row:
+        // those are the outermost halo columns, stale by construction); lanes 0 and 31 read theirs from shared memory
+        if ((t & 31) == 0) {
+            ql = Lx[c0 - 1];
+            vl = Lx[PLF + c0 - 1];
+        }
+        if ((t & 31) == 31) {
+            qr = Lx[c0 + 4];
+            vr = Lx[PLF + c0 + 4];
+        }
+#else
         const float ql = Lx[c0 - 1], qr = Lx[c0 + 4], vl = Lx[PLF + c0 - 1], vr = Lx[PLF + c0 + 4];
+#endif
         const float4 qu = ld4(Lx + c0 - WR), qd = ld4(Lx + c0 + WR), yu = ld4(Lx + 2 * PLF + c0 - WR), yd = ld4(Lx + 2 * PLF + c0 + WR);
         const float4 dxv = make_float4(vl - vx.y, vx.x - vx.z, vx.y - vx.w, vx.z - vr);
         const float4 dxq = make_float4(ql - qc.y, qc.x - qc.z, qc.y - qc.w, qc.z - qr);
@@ -345,7 +372,7 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_gen4(const __grid_const
     }
 }
 
-size_t adj_smem_int4(int nb) { return sizeof(float) * ((size_t)(6 + nb) * 4 * ANT + 2 * AGUARD); }
+size_t adj_smem_int4(int nb) { return sizeof(float) * ((size_t)(6 + nb) * 4 * ANT_INT + 2 * AGUARD); }
 size_t adj_smem_gen4(int nb) { return sizeof(float) * ((size_t)(10 + nb) * 4 * ANT + 2 * AGUARD); }
 
 // gather the two U planes of every environment of a state: [n_env][12][plane] -> [n_env][2][plane]
@@ -365,7 +392,7 @@ int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, 
     if (gp.ny_own != gp.ny_global) return waves_set_error("fused reverse step: not available on slab handles");
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t ce = cudaFuncSetAttribute(k_adjoint_step_int4<ATY_INT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t ce = cudaFuncSetAttribute(k_adjoint_step_int4<ATY_INT, ATX_INT, ANT_INT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)adj_smem_int4(3));
         if (ce == cudaSuccess)
             ce = cudaFuncSetAttribute(k_adjoint_step_gen4<ATY_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem_gen4(3));
@@ -406,14 +433,14 @@ int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, 
     }
     A.two_dO = 2.0f * h->d_omega;
     if (has_int) {
-        A.tiles_x = (xi1 - xi0) / ATX;
+        A.tiles_x = (xi1 - xi0) / ATX_INT;
         A.x_org = xi0;
         A.y_org = yi0;
         A.y_end = yi1;
         A.skip_x0 = A.skip_x1 = A.skip_y0 = A.skip_y1 = 0;
         const int tiles_y = (yi1 - yi0 + ATY_INT - 1) / ATY_INT;
         dim3 grd(A.tiles_x * tiles_y, gp.n_env * 2);
-        k_adjoint_step_int4<ATY_INT><<<grd, ANT, adj_smem_int4(A.nb), h->stream>>>(A);
+        k_adjoint_step_int4<ATY_INT, ATX_INT, ANT_INT><<<grd, ANT_INT, adj_smem_int4(A.nb), h->stream>>>(A);
         h->launches++;
     }
     A.tiles_x = (gp.nx + ATX - 1) / ATX;
