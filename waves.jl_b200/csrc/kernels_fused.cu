@@ -65,6 +65,11 @@ namespace {
 #ifndef WV_OCC_INT
 #define WV_OCC_INT 12   // resident warps per SM the interior variants are compiled for (12: 168 registers available)
 #endif
+#ifndef WV_SMALL_SP2
+#define WV_SMALL_SP2 0  // small batches (k_fused_step_all): 1 = lean interior with the stages two rows apart (V = 5); measured on a
+                        // single 700^2 environment: 35.8 us per step against 31.5 (the step is bound by instruction fetch, not by the
+                        // dependent chain: ncu 52 % of the stall samples no_instruction, and V = 5 is more code)
+#endif
 #ifndef WV_MBAR_FAST
 #define WV_MBAR_FAST 1  // 1 (measured +2.5%): the bounded-spin trap of mbar_wait lives in an out-of-line slow path (first try_wait inline)
 #endif
@@ -81,6 +86,9 @@ constexpr int OWN_W = LW - 8;  // owned columns of a full window (4-column halo 
 // V = 0 is the interior (sigma == 0 in the whole window: Psix, Psiy, Omega never change and only pass through);
 // V = 4 is the LEAN interior: once a V = 0 step has stored P = Psix + Psiy - Omega of every interior cell in its own
 // plane and both state buffers hold the (constant) auxiliary fields, only U, Vx, Vy and P are read and U, Vx, Vy written;
+// V = 5 is the lean interior with the RK stages TWO rows apart (four independent chains per warp instead of one dependent
+// chain): it needs ~220 registers, so it only pays where the occupancy is 8 warps per SM anyway -- the single-launch kernel of
+// small, latency-bound batches (k_fused_step_all);
 // V = 1 / 2 are the left-right / top-bottom PML strips (only Psix / Psiy evolves besides U, Vx, Vy; the other
 // two auxiliary fields pass through); V = 3 are the corners (all six fields evolve).
 //
@@ -94,11 +102,11 @@ constexpr int OWN_W = LW - 8;  // owned columns of a full window (4-column halo 
 template <int V>
 struct Cfg {
     static constexpr bool SX = (V & 1) != 0, SY = (V & 2) != 0;
-    static constexpr bool INT = (V == 0 || V == 4), LEAN = (V == 4);
+    static constexpr bool INT = (V == 0 || V == 4 || V == 5), LEAN = (V == 4 || V == 5);
     // Stage spacing: stage s works SP rows behind stage s-1.  With SP = 1 the stages of one loop iteration form a
     // dependent chain (stage s needs the row stage s-1 just produced); with SP = 2 they are independent, which
     // gives each warp four interleavable chains at the price of a deeper ring and more live registers.
-    static constexpr int SP = INT ? WV_SP0 : (V == 1 ? WV_SP1 : 1);
+    static constexpr int SP = V == 5 ? 2 : (INT ? WV_SP0 : (V == 1 ? WV_SP1 : 1));
     static constexpr int NG = SP == 1 ? 2 : 3;   // ring groups of 4 rows: rows r + PF .. r - 4 SP must stay resident
     static constexpr int RING = 4 * NG;
     static constexpr bool P_REGS = INT && WV_P_REGS && SP == 1;
@@ -1027,7 +1035,7 @@ k_fused_step_all(const __grid_constant__ FusedArgs A, const __grid_constant__ Me
         else if (b < M.blk0[3])
             fused_step_body<1, false>(A, b - M.blk0[2], A.items + M.item_off[1], M.n_items[1], M.item_off[1], *m7, *m6, mp, msh, table, out, epart);
         else if (M.lean)
-            fused_step_body<4, false>(A, b - M.blk0[3], A.items + M.item_off[0], M.n_items[0], M.item_off[0], *u3, *u1, mp, msh, table, out, epart);
+            fused_step_body<WV_SMALL_SP2 ? 5 : 4, false>(A, b - M.blk0[3], A.items + M.item_off[0], M.n_items[0], M.item_off[0], *u3, *u1, mp, msh, table, out, epart);
         else
             fused_step_body<0, false>(A, b - M.blk0[3], A.items + M.item_off[0], M.n_items[0], M.item_off[0], *m7, *m6, mp, msh, table, out, epart);
         if (MULTI && k + 1 < M.nsteps) grid_barrier(M.bar, (unsigned)(k + 1) * gridDim.x);
@@ -1294,7 +1302,7 @@ int fused_prepare(waves_handle *h) {
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem[V]);
     WV_SET_SMEM(0) WV_SET_SMEM(1) WV_SET_SMEM(2) WV_SET_SMEM(3) WV_SET_SMEM(4)
 #undef WV_SET_SMEM
-    p->smem_all = *std::max_element(p->smem, p->smem + 5);
+    p->smem_all = std::max(*std::max_element(p->smem, p->smem + 5), (int)(Cfg<WV_SMALL_SP2 ? 5 : 4>::WARP_F * 4));
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step_all<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_all);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step_all<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_all);
     if (ce != cudaSuccess) {
