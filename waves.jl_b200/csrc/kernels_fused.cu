@@ -70,6 +70,11 @@ namespace {
                         // single 700^2 environment: 35.8 us per step against 31.5 (the step is bound by instruction fetch, not by the
                         // dependent chain: ncu 52 % of the stall samples no_instruction, and V = 5 is more code)
 #endif
+#ifndef WV_SMALL_PDL
+#define WV_SMALL_PDL 0  // small batches: 1 = consecutive single-launch steps overlap by programmatic dependent launch.  Measured on a
+                        // single 700^2 environment: 31.5 -> 45.7 us per step -- CTAs that become resident as slots free up no longer land
+                        // round-robin on the SMs, which breaks the per-SM grouping by variant (k_fused_step_all) the step's speed rests on
+#endif
 #ifndef WV_MBAR_FAST
 #define WV_MBAR_FAST 1  // 1 (measured +2.5%): the bounded-spin trap of mbar_wait lives in an out-of-line slow path (first try_wait inline)
 #endif
@@ -730,7 +735,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
 // environment k / n_items.  `items` / `n_items` / `epart_off` describe the variant's slice of the work list.
 // PEER: this launch mirrors slab edge rows into the neighbours' ghost rows (a separate instantiation, so that the ordinary
 // kernels carry none of that code: the PML variants are sensitive to their instruction footprint)
-template <int V, bool PEER>
+template <int V, bool PEER, bool PDL = false>
 __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw, const Item *__restrict__ items, int n_items, int epart_off,
                                                 const CUtensorMap &map_u7, const CUtensorMap &map_u6, const CUtensorMap &map_c,
                                                 const CUtensorMap &map_sh, const float *__restrict__ table, float *__restrict__ out,
@@ -915,6 +920,13 @@ __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw
     Body b;
     const int r_end = c.mo0 + (item.j1 - item.j0) + 4 * C::SP;
     const int nbody = (r_end + 3) / 4;
+    // Programmatic dependent launch (small batches): everything above -- the cull, the row masks, the mbarriers -- reads nothing
+    // the previous step wrote, so this CTA may run it while the last CTAs of the previous step are still marching; the state is
+    // only touched (TMA loads below, stores in the march) once that grid has completed and its writes are visible.
+    if (PDL) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
 #pragma unroll
     for (int rp = 0; rp < PF; ++rp)
         if (rp < c.nm) issue_row<V>(c, e, c.bar0 + rp * 8, c.ring_sa + 4u * (uint32_t)(rp * C::SLOT_F), rp, map_u, &map_u6, &map_c, &map_sh);
@@ -1019,6 +1031,9 @@ k_fused_step_all(const __grid_constant__ FusedArgs A, const __grid_constant__ Me
     // 63 % of the stall samples were `no_instruction` with the variants mixed on every SM), so sharing one loop per SM matters.
     const int per = gridDim.x / M.nsm;
     const int b = ((int)blockIdx.x % M.nsm) * per + (int)blockIdx.x / M.nsm;
+    // single-step form: let the next step's grid become resident as soon as this one's CTAs retire (see fused_step_body)
+    constexpr bool PDL = !MULTI && WV_SMALL_PDL;
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #pragma unroll 1
     for (int k = 0; k < (MULTI ? M.nsteps : 1); ++k) {
         const int cur = MULTI ? ((M.cur0 + k) & 1) : 0;   // MULTI: the buffer this step reads
@@ -1029,15 +1044,15 @@ k_fused_step_all(const __grid_constant__ FusedArgs A, const __grid_constant__ Me
         if (b >= M.blk0[4]) {
             // (padding block of the permuted grid: no work, but it takes part in the barriers)
         } else if (b < M.blk0[1])
-            fused_step_body<3, false>(A, b, A.items + M.item_off[3], M.n_items[3], M.item_off[3], *m7, *m6, mp, msh, table, out, epart);
+            fused_step_body<3, false, PDL>(A, b, A.items + M.item_off[3], M.n_items[3], M.item_off[3], *m7, *m6, mp, msh, table, out, epart);
         else if (b < M.blk0[2])
-            fused_step_body<2, false>(A, b - M.blk0[1], A.items + M.item_off[2], M.n_items[2], M.item_off[2], *m7, *m6, mp, msh, table, out, epart);
+            fused_step_body<2, false, PDL>(A, b - M.blk0[1], A.items + M.item_off[2], M.n_items[2], M.item_off[2], *m7, *m6, mp, msh, table, out, epart);
         else if (b < M.blk0[3])
-            fused_step_body<1, false>(A, b - M.blk0[2], A.items + M.item_off[1], M.n_items[1], M.item_off[1], *m7, *m6, mp, msh, table, out, epart);
+            fused_step_body<1, false, PDL>(A, b - M.blk0[2], A.items + M.item_off[1], M.n_items[1], M.item_off[1], *m7, *m6, mp, msh, table, out, epart);
         else if (M.lean)
-            fused_step_body<WV_SMALL_SP2 ? 5 : 4, false>(A, b - M.blk0[3], A.items + M.item_off[0], M.n_items[0], M.item_off[0], *u3, *u1, mp, msh, table, out, epart);
+            fused_step_body<WV_SMALL_SP2 ? 5 : 4, false, PDL>(A, b - M.blk0[3], A.items + M.item_off[0], M.n_items[0], M.item_off[0], *u3, *u1, mp, msh, table, out, epart);
         else
-            fused_step_body<0, false>(A, b - M.blk0[3], A.items + M.item_off[0], M.n_items[0], M.item_off[0], *m7, *m6, mp, msh, table, out, epart);
+            fused_step_body<0, false, PDL>(A, b - M.blk0[3], A.items + M.item_off[0], M.n_items[0], M.item_off[0], *m7, *m6, mp, msh, table, out, epart);
         if (MULTI && k + 1 < M.nsteps) grid_barrier(M.bar, (unsigned)(k + 1) * gridDim.x);
     }
 }
@@ -1544,9 +1559,18 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
         fused_fill_merged(h, p, M, lean);
         M.epart0 = A.epart;
         const int c0 = h->cur, c1 = h->cur ^ 1;
-        k_fused_step_all<false><<<(unsigned)M.grid, 32, p->smem_all, h->stream>>>(A, M, h->map_u[c0], h->map_u6[c0], h->map_u3[c0], h->map_u1[c0],
-                                                                                     h->map_u[c1], h->map_u6[c1], h->map_u3[c1], h->map_u1[c1],
-                                                                                     h->map_p, h->map_shape);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)M.grid);
+        cfg.blockDim = dim3(32);
+        cfg.dynamicSmemBytes = (size_t)p->smem_all;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = (WV_SMALL_PDL && !(dbg_flags & 1024)) ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, k_fused_step_all<false>, A, M, h->map_u[c0], h->map_u6[c0], h->map_u3[c0], h->map_u1[c0], h->map_u[c1],
+                           h->map_u6[c1], h->map_u3[c1], h->map_u1[c1], h->map_p, h->map_shape);
         h->launches++;
     } else {
     // The PML variants are launched on side streams (fork / join with events) so their CTAs fill the tail of the interior kernel.
