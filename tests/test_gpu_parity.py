@@ -533,3 +533,65 @@ def test_config2_twenty_actions_energy_trace():
     print(f"config 2: energy trace rel-L2 tot/inc/sc = {errs}, final fields {ferr:.2e}, {per_action:.1f} launches per env(action)")
     assert so[-1, 2] > 0 and max(errs) < TOL and ferr < TOL
     assert per_action < 112, "a single environment takes one launch per step and one energy reduction per action"
+
+
+def test_config3_full_batch_1024_envs_properties():
+    """BASELINE configs[2] at its full size on ONE GPU: 1024 independent 700^2 environments (52 GB of state).  The oracle cannot
+    run this, so size-independent properties carry the check: (i) environments with identical inputs, 12 apart in the batch and
+    therefore on different warps / work items, end bitwise identical; (ii) the first 12 environments equal a 12-environment handle
+    (a different work plan): fields bit for bit, energy trace to 1e-6; (iii) an environment without design has E_sc == 0 exactly and
+    E_tot == E_inc; (iv) the energies are finite and the source has put energy in."""
+    import torch
+    if torch.cuda.mem_get_info(0)[0] < 70e9:
+        pytest.skip("needs 70 GB of free device memory")
+    n, E, period, steps = 700, 1024, 12, 12
+    dim = wb.TwoDim(15.0, n)
+    ds = wb.build_triple_ring_design_space()
+    rng = np.random.default_rng(7)
+    designs = []
+    for k in range(4):
+        d0 = ds.rand(rng)
+        d1 = ds(d0, wb.build_action_space(d0, 0.25).rand(rng))
+        designs.append(None if k == 3 else (d0.table(), d1.table()))
+    shapes = [wb.build_normal(dim, [[-10.0, y]], [0.3], [1.0]) for y in (-6.0, 0.5, 7.0)]
+    ts = wb.build_tspan(0.0, 1e-5, steps)
+    # initial states: smooth random fields, incident == total (so that an environment without design keeps them equal); the wave
+    # of a source at x = -10 would need ~400 steps to reach the rings, a field that is everywhere meets them at once
+    u0s = []
+    for k in range(3):
+        a = rng.standard_normal((6, n // 20, n // 20)).astype(F32)
+        f = np.kron(a, np.ones((20, 20), F32))
+        for _ in range(3):   # a few smoothing passes
+            f = (f + np.roll(f, 3, 1) + np.roll(f, -3, 1) + np.roll(f, 3, 2) + np.roll(f, -3, 2)) * F32(0.2)
+        u0s.append(np.ascontiguousarray(np.concatenate([f, f]) * F32(1e-3))[None])
+
+    def run(n_env):
+        eng = wb.Engine(dim.x, dim.y, wb.WATER, 1e-5, 2.0, 20000.0, n_env=n_env, device=0)
+        for e in range(n_env):
+            eng.set_source(shapes[e % 3], 1000.0, env=e)
+            eng.set_state(u0s[e % 3], env=e)
+            d = designs[e % 4]
+            if d is None:
+                eng.set_design(None, None, 0, 0, env=e)
+            else:
+                eng.set_design(d[0], d[1], ts[0], ts[-1], env=e)
+        for _ in range(2):   # two env(action)-like calls: the first runs the full interior variant, the second the lean one
+            en, _ = eng.integrate(ts, wb.MODE_FUSED)
+        picks = {e: eng.get_state(e).copy() for e in (0, 3, 5, 11, 12, 15, 515, 1020, 1023) if e < n_env}
+        eng.close()
+        return en, picks
+
+    en, st = run(E)
+    assert np.isfinite(en).all() and en[:, -1, 1].min() > 0
+    for e in range(period, E):
+        assert np.array_equal(en[e], en[e % period]), f"env {e} differs from env {e % period}"
+    assert np.array_equal(st[12], st[0]) and np.array_equal(st[15], st[3]) and np.array_equal(st[515], st[11])
+    assert np.array_equal(st[1020], st[0]) and np.array_equal(st[1023], st[3])
+    assert np.array_equal(st[3][:6], st[3][6:]), "no design: total field == incident field"
+    assert np.all(en[3, :, 2] == 0.0) and np.array_equal(en[3, :, 0], en[3, :, 1])
+    assert en[0, -1, 2] > 0 and not np.array_equal(st[0][0], st[0][6]), "a design scatters"
+    en12, st12 = run(period)
+    # (fields are independent of the work plan; the energy sums are taken per work item, so their last bits follow the plan)
+    assert np.abs(en12 - en[:period]).max() <= 1e-6 * np.abs(en12).max()
+    for e in (0, 3, 5, 11):
+        assert np.array_equal(st12[e], st[e])
