@@ -359,9 +359,16 @@ def main():
     ap.add_argument("--ref-rk4-steps", type=int, default=20, help="RK4 steps per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record: anything else that writes to file descriptor 1 (the NCCL version banner
+    # of the first communicator, library chatter) is sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
+    os.close(json_fd)
 
 
 if __name__ == "__main__":
