@@ -163,6 +163,18 @@ function adjoint!(h::Handle, tspan::Vector{Float32}, nx::Int, ny::Int; w_energy 
     return loss[1], gz, gc
 end
 
+# ---- controls of the two calls above ----------------------------------------------------------------------
+"""u_tot / u_inc trajectories of `integrate!` keep every `stride`-th frame only (what a renderer needs, src/plot.jl:25)"""
+set_traj_stride!(h::Handle, stride::Integer) =
+    check(h.lib, ccall(sym(:waves_set_traj_stride), Cint, (Ptr{Cvoid}, Cint), h.ptr, stride))
+"""how `integrate!` issues kernels: 0 every kernel directly, 1 (default) CUDA-graph replay / one launch per step, 2 cooperative multi-step launches"""
+set_graph!(h::Handle, mode::Integer) = check(h.lib, ccall(sym(:waves_set_graph), Cint, (Ptr{Cvoid}, Cint), h.ptr, mode))
+"""`adjoint!` stores a checkpoint every `every` steps and re-runs one segment at a time (0: chosen from the free device memory)"""
+set_adjoint_checkpoint!(h::Handle, every::Integer) =
+    check(h.lib, ccall(sym(:waves_set_adjoint_checkpoint), Cint, (Ptr{Cvoid}, Cint), h.ptr, every))
+"""wait for everything queued on the handle's stream"""
+sync!(h::Handle) = check(h.lib, ccall(sym(:waves_sync), Cint, (Ptr{Cvoid},), h.ptr))
+
 # ---- seam B2: (iter::Integrator)(ui, tspan, θ) for the parameterised θ the environment builds -------------
 """Drop-in for `iter(ui, tspan, [C, F])` when C is the design interpolation of `(env::WaveEnv)(action)`
 (src/env.jl:96-99): pass the DesignInterpolator (or `nothing` for a constant c0) instead of the closure."""
