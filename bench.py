@@ -165,7 +165,11 @@ def measure_batch(wb, torch, dist, rank, world, local, E, env0, total_envs, S, s
     clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
     replays0 = eng.graph_replays()
     one_step(True)
+    sampler2 = ClockSampler(local)
+    if rank == 0 and sample_clocks:
+        sampler2.start()
     ms_e2e, _ = timed(steps, True)
+    clocks_e2e = sampler2.stop() if (rank == 0 and sample_clocks) else None
     graph_replays = eng.graph_replays() - replays0
 
     # dominant-kernel duration, measured live with CUDA events on the launching stream (separate pass, kernels launched
@@ -183,7 +187,7 @@ def measure_batch(wb, torch, dist, rank, world, local, E, env0, total_envs, S, s
     return {"value": cells_step * steps / (ms_total * 1e-3) / 1e9, "e2e": cells_step * steps / (ms_e2e * 1e-3) / 1e9,
             "ms_per_step": ms_total / steps, "launches": int(launches), "per_launch_s": per_launch_s, "clocks": clocks,
             "h2d": int(world * (h_design.numel() * 4 + (S + 1) * 4)), "d2h": int(world * h_energy.numel() * 4),
-            "frames_kept": nkeep, "graph_replays_per_e2e_step": graph_replays / (steps + 1)}
+            "frames_kept": nkeep, "graph_replays_per_e2e_step": graph_replays / (steps + 1), "clocks_e2e": clocks_e2e}
 
 
 def run_ours(args):
@@ -234,7 +238,10 @@ def run_ours(args):
                        "l2": f"inputs larger than L2: {E * 12 * n * n * 4 / 1e9:.2f} GB of state per GPU streamed every RK4 step"},
             "e2e": {"value": round(m["e2e"], 3), "unit": UNIT, "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
                     "note": f"per env(action): design tables + tspan from host, energy signal to pinned host, env.wave ({m['frames_kept']} "
-                            f"frame(s) x 12 fields) kept on the device; {m['graph_replays_per_e2e_step']:.2f} CUDA graph launches per step"},
+                            f"frame(s) x 12 fields) kept on the device; {m['graph_replays_per_e2e_step']:.2f} CUDA graph launches per step; "
+                            "measured after the value window in the same process (the GPU is at its sustained, power-capped clock by then: "
+                            "clocks_sm_mhz below against clocks.sm_mhz)",
+                    "clocks_sm_mhz": None if not m.get("clocks_e2e") else m["clocks_e2e"]["sm_mhz"]},
             "gpu_launches": m["launches"],
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
