@@ -31,15 +31,20 @@ def measure(steps=500, E=1, device=0, with_dc=True, check_exact=True, n=700):
     res = {"workload": f"{E} x 700^2, triple-ring design frozen, {steps} steps, L = sum_t E_sc(t): forward (fused) + reverse sweep",
            "steps": steps, "envs": E, "unit": "Gcell-updates/s (forward + reverse)"}
 
-    def run(name, reps=2, **kw):
-        for _ in range(reps):
+    def run(name, reps=4, **kw):
+        # the first repetition allocates the stored-state buffers; the best of the others is reported (a 50 ms workload after
+        # an allocation pause is sensitive to the clock ramp of an idle GPU: single repetitions varied 0.05 .. 0.13 s)
+        best = None
+        for rep in range(reps):
             eng.set_state(z0)
             l0 = eng.launch_count()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             loss, gz, gc = eng.adjoint(ts, w, out_dz0=gz_d, **kw)
             torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
+            if rep > 0:
+                best = min(best or 1e30, time.perf_counter() - t0)
+        dt = best
         res[name] = {"seconds": round(dt, 4), "value": round(2 * E * n * n * steps / dt / 1e9, 3), "launches": eng.launch_count() - l0,
                      "loss": float(loss[0]), "finite": bool(torch.isfinite(gz).all().item())}
         return gz, gc

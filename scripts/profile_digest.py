@@ -61,7 +61,7 @@ def gb(s):
 cells = 128 * 700 * 700
 dram = sum(gb(k["dram__bytes_read.sum"]) + gb(k["dram__bytes_write.sum"]) for k in kern)
 summary = {"source": f"gpurun_out/prof_{tag}.ncu-rep (ncu --set full --clock-control none; 128 x 700^2 environments, one RK4 step; "
-                     "the four k_fused_step variants serialised with WAVES_DEBUG_FLAGS=16)",
+                     "ncu serialises the four k_fused_step variants of the launch set)",
            "cells_per_launch_set": cells, "dram_bytes_per_launch_set": dram, "dram_bytes_per_cell_update": dram / cells,
            "algorithmic_bytes_per_cell_update": 96, "kernels": kern}
 json.dump(summary, open(os.path.join(P, f"{tag}_ncu_full_summary.json"), "w"), indent=1)

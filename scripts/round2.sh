@@ -12,6 +12,9 @@ tail -5 gpurun_out/gputest_$TAG.log
 timeout 600 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 echo "bench rc=$?"
 head -c 1500 gpurun_out/bench_$TAG.json
+# the driver's own settings (20 timed steps after 5 warm-up steps: ~20 s of sustained load before the e2e window)
+timeout 600 python bench.py --steps 20 --warmup 5 --no-extras --no-cpu-baseline > gpurun_out/bench20_$TAG.json 2> gpurun_out/bench20_$TAG.err
+head -c 600 gpurun_out/bench20_$TAG.json; echo
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err
 # launch list of the same command (direct launches: kernel nodes of a replayed graph are listed too)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_$TAG.csv \
