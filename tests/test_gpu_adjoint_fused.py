@@ -143,3 +143,26 @@ def test_batched_gradients_with_checkpoints_at_full_size():
     assert rel(g[3], np.float64(g1[0])) > 1e-2 and np.isfinite(g).all()
     one.close()
     eng.close()
+
+
+@pytest.mark.parametrize("n,pml_width", [(200, 0.25), (131, 0.2)])
+@pytest.mark.parametrize("adj_mode", [wb.ADJ_EXACT, wb.ADJ_COMPAT])
+def test_march_interior_equals_tile_kernels(n, pml_width, adj_mode):
+    """The interior of the fused reverse step runs on the forward kernel's march (TMA ring, transposed operator, auxiliary
+    cotangents accumulated in one plane) with the shared-memory tiles on the frame around it; `march=False` takes the tiles
+    everywhere.  Same gradient to float32 rounding, with a moving design, energy weights on every frame and a cotangent of
+    the last state in all 12 fields (the auxiliary ones included)."""
+    steps = 7
+    p, eng, ts, z0, w, aN = setup(n=n, steps=steps, pml_width=pml_width)
+    outs = []
+    for march in (True, False):
+        eng.set_state(z0[None])
+        l0 = eng.launch_count()
+        loss, dz0, _ = eng.adjoint(ts, w, aN[None], adj_mode=adj_mode, want_dc=False, march=march)
+        outs.append((loss.copy(), dz0.copy(), eng.launch_count() - l0))
+    (la, ga, na), (lb, gb, nb) = outs
+    assert na != nb, "the two forms must not launch the same kernels"
+    assert la[0] == lb[0]
+    for f in range(12):
+        assert rel(ga[0, f], np.float64(gb[0, f])) < 2e-6, f"field {f}: {rel(ga[0, f], np.float64(gb[0, f]))}"
+    eng.close()

@@ -67,6 +67,10 @@ struct AdjFArgs {
     int x_org, y_org;    // first owned column / row of tile (0, 0)
     int y_end;           // owned rows stop here (exclusive)
     int skip_x0, skip_x1, skip_y0, skip_y1;  // general launch: tiles inside this rectangle belong to the interior launch
+    // general launch over up to four rectangular bands (the frame around the rectangle the march kernel owns): band k holds the
+    // blocks [bstart[k], bstart[k+1]) as tiles of ATX x TY from (bx0, by0), clipped to (bx1, by1); nband == 0: one band = the domain
+    int nband;
+    int bx0[4], bx1[4], by0[4], by1[4], btx[4], bstart[5];
 };
 
 extern __shared__ __align__(16) float adj_sm[];
@@ -208,12 +212,23 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_gen4(const __grid_const
     const GridP &gp = A.gp;
     const int nx = gp.nx, ny = gp.ny_global, nxp = gp.nxp;
     const long long P = gp.plane;
-    const int tx = blockIdx.x % A.tiles_x, ty = blockIdx.x / A.tiles_x;
     const int e = blockIdx.y >> 1, wf = blockIdx.y & 1;
-    const int x0 = A.x_org + tx * ATX, y0 = A.y_org + ty * TY;
-    if (x0 >= nx || y0 >= A.y_end) return;
-    if (x0 >= A.skip_x0 && x0 + ATX <= A.skip_x1 && y0 >= A.skip_y0 && y0 + TY <= A.skip_y1) return;
-    const int x1 = min(x0 + ATX, nx), y1 = min(y0 + TY, A.y_end);
+    int x0, y0, xe, ye;
+    if (A.nband > 0) {
+        int k = 0;
+        while (k + 1 < A.nband && (int)blockIdx.x >= A.bstart[k + 1]) ++k;
+        const int bi = (int)blockIdx.x - A.bstart[k];
+        const int tx = bi % A.btx[k], ty = bi / A.btx[k];
+        x0 = A.bx0[k] + tx * ATX, y0 = A.by0[k] + ty * TY;
+        xe = A.bx1[k], ye = A.by1[k];
+    } else {
+        const int tx = blockIdx.x % A.tiles_x, ty = blockIdx.x / A.tiles_x;
+        x0 = A.x_org + tx * ATX, y0 = A.y_org + ty * TY;
+        xe = nx, ye = A.y_end;
+        if (x0 >= A.skip_x0 && x0 + ATX <= A.skip_x1 && y0 >= A.skip_y0 && y0 + TY <= A.skip_y1) return;
+    }
+    if (x0 >= xe || y0 >= ye) return;
+    const int x1 = min(x0 + ATX, xe), y1 = min(y0 + TY, ye);
     const int L = max(x0 - 4, 0), T0 = max(y0 - 4, 0);
     int R = min(x1 + 4, nx), B = min(y1 + 4, ny);
     if (nx - R <= 2) R = nx;
@@ -382,7 +397,85 @@ __global__ void k_gather_u(GridP gp, const float *__restrict__ u, float *__restr
     if (q < n) out[((long long)e * 2 + f) * n + q] = u[((long long)e * 12 + f * 6) * n + q];
 }
 
+// After a sweep whose interior ran on the march (kernels_fused.cu, stage_T): the three auxiliary cotangents of the cells of the
+// rectangle [x0, x1) x [y0, y1) receive the accumulated G = sum over the steps of dt/6 (y0 + 2 y1 + 2 y2 + y3)_U.
+__global__ void k_apply_aux_cotangent(GridP gp, float *__restrict__ w, const float *__restrict__ G, int x0, int x1, int y0, int y1) {
+    const int x = x0 + 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = y0 + blockIdx.y;
+    const int e = blockIdx.z >> 1, wf = blockIdx.z & 1;
+    if (x >= x1 || y >= y1) return;
+    const long long q = (long long)y * gp.nxp + x;
+    const float4 g = ld4(G + ((long long)e * 2 + wf) * gp.plane + q);
+    float *wp = w + ((long long)e * 12 + wf * 6) * gp.plane + q;
+    st4(wp + 3 * gp.plane, ld4(wp + 3 * gp.plane) + g);
+    st4(wp + 4 * gp.plane, ld4(wp + 4 * gp.plane) + g);
+    st4(wp + 5 * gp.plane, ld4(wp + 5 * gp.plane) - g);
+}
+
 }  // namespace
+
+void launch_apply_aux_cotangent(waves_handle *h, float *w, const float *G, const int rect[4]) {
+    const int groups = (rect[1] - rect[0] + 3) / 4;
+    dim3 grd((groups + 63) / 64, rect[3] - rect[2], h->gp.n_env * 2);
+    k_apply_aux_cotangent<<<grd, 64, 0, h->stream>>>(h->gp, w, G, rect[0], rect[1], rect[2], rect[3]);
+    h->launches++;
+}
+
+static int adj_attr_once() {
+    static bool attr_done = false;
+    if (attr_done) return 0;
+    cudaError_t ce = cudaFuncSetAttribute(k_adjoint_step_int4<ATY_INT, ATX_INT, ANT_INT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)adj_smem_int4(3));
+    if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(k_adjoint_step_gen4<ATY_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem_gen4(3));
+    if (ce != cudaSuccess) return waves_set_error("fused reverse step: cudaFuncSetAttribute failed (was the library built for sm_100a?)");
+    attr_done = true;
+    return 0;
+}
+
+// The general tiles of one fused reverse step on the frame around `rect` (whose cells another kernel advances): four bands.
+int launch_adjoint_step_frame(waves_handle *h, const float *w_in, float *w_out, const float *const b2[3], const float *pre_u,
+                              const float *pre_w3, const float *post_u, const float *post_w3, const int rect[4]) {
+    const GridP &gp = h->gp;
+    if (adj_attr_once()) return 1;
+    AdjFArgs A;
+    A.gp = gp;
+    A.w_in = w_in;
+    A.w_out = w_out;
+    for (int t = 0; t < 3; ++t) A.b2[t] = b2 ? b2[t] : nullptr;
+    A.nb = (!b2 || !b2[0]) ? 0 : ((b2[0] == b2[1] && b2[1] == b2[2]) ? 1 : 3);
+    A.pre_u = pre_u;
+    A.post_u = post_u;
+    for (int k = 0; k < 3; ++k) {
+        A.pre_w[k] = pre_w3 ? pre_w3[k] : 0.0f;
+        A.post_w[k] = post_w3 ? post_w3[k] : 0.0f;
+    }
+    A.two_dO = 2.0f * h->d_omega;
+    A.tiles_x = 1;
+    A.x_org = A.y_org = 0;
+    A.y_end = gp.ny_global;
+    A.skip_x0 = A.skip_x1 = A.skip_y0 = A.skip_y1 = 0;
+    // left and right bands over the full height, top and bottom bands between them
+    const int bx0[4] = {0, rect[1], rect[0], rect[0]}, bx1[4] = {rect[0], gp.nx, rect[1], rect[1]};
+    const int by0[4] = {0, 0, 0, rect[3]}, by1[4] = {gp.ny_global, gp.ny_global, rect[2], gp.ny_global};
+    int nb = 0, blocks = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (bx1[k] <= bx0[k] || by1[k] <= by0[k]) continue;
+        A.bx0[nb] = bx0[k], A.bx1[nb] = bx1[k], A.by0[nb] = by0[k], A.by1[nb] = by1[k];
+        A.btx[nb] = (bx1[k] - bx0[k] + ATX - 1) / ATX;
+        A.bstart[nb] = blocks;
+        blocks += A.btx[nb] * ((by1[k] - by0[k] + ATY_GEN - 1) / ATY_GEN);
+        ++nb;
+    }
+    for (int k = nb; k < 4; ++k) A.bx0[k] = A.bx1[k] = A.by0[k] = A.by1[k] = 0, A.btx[k] = 1, A.bstart[k] = blocks;
+    A.bstart[4] = blocks;
+    if (nb < 4) A.bstart[nb] = blocks;
+    A.nband = nb;
+    if (nb == 0) return 0;
+    dim3 grd(blocks, gp.n_env * 2);
+    k_adjoint_step_gen4<ATY_GEN><<<grd, ANT, adj_smem_gen4(A.nb), h->stream>>>(A);
+    h->launches++;
+    return 0;
+}
 
 // One fused reverse step for every environment: w_out = [pre-injection] (I + J_step^T) w_in [+ post-injection].
 // b2[tau]: c^2 planes of the total field at the three stage times (nullptr: no design anywhere).
@@ -390,15 +483,7 @@ int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, 
                               const float *pre_w3, const float *post_u, const float *post_w3) {
     const GridP &gp = h->gp;
     if (gp.ny_own != gp.ny_global) return waves_set_error("fused reverse step: not available on slab handles");
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t ce = cudaFuncSetAttribute(k_adjoint_step_int4<ATY_INT, ATX_INT, ANT_INT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)adj_smem_int4(3));
-        if (ce == cudaSuccess)
-            ce = cudaFuncSetAttribute(k_adjoint_step_gen4<ATY_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem_gen4(3));
-        if (ce != cudaSuccess) return waves_set_error("fused reverse step: cudaFuncSetAttribute failed (was the library built for sm_100a?)");
-        attr_done = true;
-    }
+    if (adj_attr_once()) return 1;
     // zero-sigma zone [z0, z1) of the profile, cached per handle
     if (h->adj_z1 == 0 && h->adj_z0 == 0) {
         std::vector<float> sig(gp.nx);
@@ -432,6 +517,9 @@ int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, 
         A.post_w[k] = post_w3 ? post_w3[k] : 0.0f;
     }
     A.two_dO = 2.0f * h->d_omega;
+    A.nband = 0;
+    for (int k = 0; k < 4; ++k) A.bx0[k] = A.bx1[k] = A.by0[k] = A.by1[k] = 0, A.btx[k] = 1, A.bstart[k] = 0;
+    A.bstart[4] = 0;
     if (has_int) {
         A.tiles_x = (xi1 - xi0) / ATX_INT;
         A.x_org = xi0;

@@ -107,20 +107,23 @@ constexpr int OWN_W = LW - 8;  // owned columns of a full window (4-column halo 
 template <int V>
 struct Cfg {
     static constexpr bool SX = (V & 1) != 0, SY = (V & 2) != 0;
-    static constexpr bool INT = (V == 0 || V == 4 || V == 5), LEAN = (V == 4 || V == 5);
+    static constexpr bool TR = (V == 6);   // transposed (reverse-pass) interior step, see stage_T
+    static constexpr bool INT = (V == 0 || V == 4 || V == 5 || V == 6), LEAN = (V == 4 || V == 5 || V == 6);
     // Stage spacing: stage s works SP rows behind stage s-1.  With SP = 1 the stages of one loop iteration form a
     // dependent chain (stage s needs the row stage s-1 just produced); with SP = 2 they are independent, which
     // gives each warp four interleavable chains at the price of a deeper ring and more live registers.
-    static constexpr int SP = V == 5 ? 2 : (INT ? WV_SP0 : (V == 1 ? WV_SP1 : 1));
+    static constexpr int SP = V == 5 ? 2 : (V == 6 ? 1 : (INT ? WV_SP0 : (V == 1 ? WV_SP1 : 1)));
     static constexpr int NG = SP == 1 ? 2 : 3;   // ring groups of 4 rows: rows r + PF .. r - 4 SP must stay resident
     static constexpr int RING = 4 * NG;
-    static constexpr bool P_REGS = INT && WV_P_REGS && SP == 1;
+    static constexpr bool P_REGS = INT && WV_P_REGS && SP == 1 && !TR;
     static constexpr int ROW_UI = LEAN ? 4 : 6;
     static constexpr int ROW_SH = LEAN ? 5 : 7;
     // V = 0: the Psix row (only when P is not kept in registers); V = 4: the TMA-loaded P row; V = 1, 2: a row no TMA load
     // ever writes, so storing P needs no cross-proxy fence
     static constexpr int ROW_P = INT ? 3 : 8;
-    static constexpr int SLOT_ROWS = INT ? 8 : 11;
+    // V = 6 slot rows: 0..2 the cotangents of U, Vx, Vy (TMA), 3 the accumulated auxiliary cotangent G (TMA), 4, 5 U of the total /
+    // incident field of the stored forward state (TMA; energy cotangent), 6..8 c^2 at the three stage times (never a TMA target)
+    static constexpr int SLOT_ROWS = TR ? 9 : (INT ? 8 : 11);
     static constexpr int SLOT_F = SLOT_ROWS * LW;
     static constexpr int RING_F = RING * SLOT_F;
     static constexpr int CYL_OFF = RING_F;
@@ -134,7 +137,7 @@ struct Cfg {
     static constexpr int ROW_BK0 = SY ? 9 : -1;  // (measured: pays on the top-bottom strips and corners only)
     // row holding kd*c^2 at stage-time index tau
     __host__ __device__ static constexpr int f_bk(int tau) {
-        return LEAN ? (tau == 0 ? 4 : 5 + tau) : (INT ? 4 + tau : (tau == 0 ? 6 : 8 + tau));
+        return TR ? 6 + tau : (LEAN ? (tau == 0 ? 4 : 5 + tau) : (INT ? 4 + tau : (tau == 0 ? 6 : 8 + tau)));
     }
 };
 
@@ -174,6 +177,13 @@ struct FusedArgs {
     float akd_h, akd_f, dt6kd;  // (dt/2)kd, dt*kd, (dt/6)kd
     float hdt, dt, dt6;
     unsigned plane, nxp;
+    // V = 6 (reverse pass): energy cotangent a = dL/dz of sum_k inj_w[k] E_k(z) (src/env.jl:104-111) of the stored state whose two U
+    // planes are planes zplane0 + 2 e, + 1 of the Z tensor map: added to the incoming cotangent (tr_inj == 1, the reference loop as
+    // written) or to the outgoing one (tr_inj == 2, exact discrete adjoint); 0: none
+    int tr_inj;
+    float inj_w[3];
+    float two_dO;
+    int zplane0;
 };
 
 extern __shared__ __align__(128) float smf[];  // all shared memory, indexed with 32-bit arithmetic
@@ -321,6 +331,7 @@ struct WarpCtx {
     int col0;          // this lane's first column
     int bko[3];        // float offset of the slot row holding kd*c^2 at stage-time index tau (the ambient row without cylinders)
     const float *table;      // stage-table row of this step (environment 0)
+    int zplane;              // V = 6: first of this environment's two stored U planes in the Z tensor map
 };
 
 // c(x,y,t)^2 with every cylinder (list overflow), exact order of src/designs.jl:99-116
@@ -384,11 +395,11 @@ __device__ __noinline__ void speed_row(int uri, unsigned mask, f2 xs, float yv, 
 }
 // same with every cylinder of the design (the culled list overflowed)
 template <int V>
-__device__ __noinline__ void speed_row_slow(const FusedArgs &A, const float *table, int e, int uri, f2 xs, float yv) {
+__device__ __noinline__ void speed_row_slow(const FusedArgs &A, const float *table, int e, int uri, f2 xs, float yv, float kd) {
     using C = Cfg<V>;
     for (int tau = 0; tau < 3; ++tau)
         sts2(uri + (tau == 0 ? C::f_bk(0) : (tau == 1 ? C::f_bk(1) : C::f_bk(2))) * LW,
-             A.kd * mk2(speed2_slow(A, table, e, tau, xs.x, yv), speed2_slow(A, table, e, tau, xs.y, yv)));
+             kd * mk2(speed2_slow(A, table, e, tau, xs.x, yv), speed2_slow(A, table, e, tau, xs.y, yv)));
 }
 
 // Register state of one warp: rotating windows indexed [stage][march row & 3], one column pair per lane
@@ -606,6 +617,72 @@ __device__ __forceinline__ void stage(const WarpCtx &c, const FusedArgs &A, cons
     }
 }
 
+// ---- reverse pass, interior windows (V = 6) --------------------------------------------------------------------------------
+// The right-hand side is affine in the state, so the reverse of one runge_kutta call (src/dynamics.jl:9-16 under
+// adjoint_sensitivity, src/dynamics.jl:97-118) is an RK4 step of the TRANSPOSED operator with the stage times reversed:
+//     k1 = J(t+dt)^T w,  k2 = J(t+dt/2)^T (w + dt/2 k1),  k3 = J(t+dt/2)^T (w + dt/2 k2),  k4 = J(t)^T (w + dt k3),
+//     w' = w + dt/6 (k1 + 2 k2 + 2 k3 + k4)
+// (kernels_adjoint_fused.cu states the same step stage cotangent by stage cotangent).  Where sigma == 0 and away from the border
+//     (J^T y)_U = -(Dx yVx + Dy yVy),   (J^T y)_Vx = -Dx (c^2 yU),   (J^T y)_Vy = -Dy (c^2 yU),
+//     (J^T y)_Psix = (J^T y)_Psiy = yU,  (J^T y)_Omega = -yU
+// -- the forward interior step with c^2 INSIDE the derivative and the signs flipped -- so the march, the TMA ring and the
+// software pipeline of the forward kernel carry over: the U window holds c^2(t_next stage) * yU instead of U + f, the constants
+// kd, a kd, dt/6 kd arrive negated, and there is no source and no P.  The three auxiliary cotangents feed nothing where sigma == 0;
+// they all receive dt/6 (y0 + 2 y1 + 2 y2 + y3)_U, which is accumulated in ONE plane G (slot row 3) and added to them after the
+// sweep (k_apply_aux_cotangent).
+template <int V, int S, int PH>
+__device__ __forceinline__ void stage_T(const WarpCtx &c, const FusedArgs &A, const Body &b, Regs &R, int m) {
+    using C = Cfg<V>;
+    constexpr int sc = (PH - S + 16) & 3, sm = (sc + 3) & 3, sp = (sc + 1) & 3;  // rows m, m-1, m+1
+    const int uri = slot_of<V, PH, -S>(b);
+    const float a = (S == 3) ? A.dt : A.hdt;
+    const float akd = (S == 3) ? A.akd_f : A.akd_h;            // a * (-kd)
+    constexpr int tau_next = (S == 1 || S == 2) ? 1 : 0;       // stage S + 1 applies J^T at t+dt/2, t+dt/2, t
+    const f2 uU = lds2(uri), uVx = lds2(uri + LW), uVy = lds2(uri + 2 * LW);
+    const f2 zC = R.Uf[S - 1][sc];                             // c^2 * yU of the stage input
+    const f2 vxC = (S == 1) ? uVx : R.Vx[S - 1][sc];
+    const f2 dZy = R.Uf[S - 1][sp] - R.Uf[S - 1][sm];
+    const f2 dVy = R.Vy[S - 1][sp] - R.Vy[S - 1][sm];
+    const f2 dZx = ddx_int(zC), dVx = ddx_int(vxC);
+    const f2 dsum = dVx + dVy;                                 // kU = -kd * dsum
+    const bool st = (unsigned)(m - c.mo0) < c.mon;
+    if (S < 4) {
+        const f2 yU = fma2(akd, dsum, uU);
+        const f2 c2n = c.use_bk ? lds2(uri + C::f_bk(tau_next) * LW) : bc2(A.gp.b0);
+        R.Uf[S][sc] = c2n * yU;
+        R.Vx[S][sc] = fma2(akd, dZx, uVx);
+        R.Vy[S][sc] = fma2(akd, dZy, uVy);
+        if (S == 1) {
+            R.aU[0][sc] = dsum;
+            R.aVx[0][sc] = dZx;
+            R.aVy[0][sc] = dZy;
+            R.aPx[0][sc] = fma2(2.0f, yU, uU);                 // y0 + 2 y1
+        } else {
+            R.aU[0][sc] = fma2(2.0f, dsum, R.aU[0][sc]);
+            R.aVx[0][sc] = fma2(2.0f, dZx, R.aVx[0][sc]);
+            R.aVy[0][sc] = fma2(2.0f, dZy, R.aVy[0][sc]);
+            R.aPx[0][sc] = (S == 2) ? fma2(2.0f, yU, R.aPx[0][sc]) : R.aPx[0][sc] + yU;
+        }
+    } else if (st) {
+        float *o = b.po + PH * c.rowstep;
+        f2 oU = fma2(A.dt6kd, R.aU[0][sc] + dsum, uU);
+        const f2 oVx = fma2(A.dt6kd, R.aVx[0][sc] + dZx, uVx), oVy = fma2(A.dt6kd, R.aVy[0][sc] + dZy, uVy);
+        if (A.tr_inj == 2) {   // exact discrete adjoint: the energy cotangent of the stored state joins the outgoing cotangent
+            const f2 ut = lds2(uri + 4 * LW), ui = lds2(uri + 5 * LW), d = ut - ui;
+            oU = oU + (c.is_tot ? A.two_dO * (A.inj_w[0] * ut + A.inj_w[2] * d) : A.two_dO * (A.inj_w[1] * ui - A.inj_w[2] * d));
+        }
+        stg2(o, oU);
+        stg2(o + A.plane, oVx);
+        stg2(o + 2u * A.plane, oVy);
+        stg2(c.pc_e + (o - c.out_e), fma2(A.dt6, R.aPx[0][sc], lds2(uri + C::ROW_P * LW)));
+    }
+}
+
+template <int V, int PH>
+__device__ __forceinline__ void row_step_T(const WarpCtx &c, const FusedArgs &A, int e, const Body &b, Regs &R, int r,
+                                           const CUtensorMap *map_u, const CUtensorMap *map_b, const CUtensorMap *map_c,
+                                           const CUtensorMap *map_sh);
+
 // Issue the TMA loads of march row rp (state planes, and where needed U of the incident field and the source shape row) into the
 // ring slot at shared address dst, completing on mbarrier bar.  Warp-uniform operands; the whole warp executes this.
 template <int V>
@@ -613,7 +690,10 @@ __device__ __forceinline__ void issue_row(const WarpCtx &c, int e, uint32_t bar,
                                           const CUtensorMap *map_b, const CUtensorMap *map_c, const CUtensorMap *map_sh) {
     using C = Cfg<V>;
     const int jp = c.jbase + c.dir * rp;
-    if (C::LEAN) {
+    if (C::TR) {   // map_u: the incoming cotangent (box of 3 planes), map_c: the G planes, map_sh: the stored U planes (box of 2)
+        tma_issue_row_lean(bar, c.tx_bytes, dst, map_u, map_c, c.x0, jp, e * 12 + c.w0 * 6, e * 2 + c.w0, LW * 4);
+        tma_issue_one(bar, dst + 4 * (LW * 4), map_sh, c.x0, jp, c.zplane);
+    } else if (C::LEAN) {
         tma_issue_row_lean(bar, c.tx_bytes, dst, map_u, map_c, c.x0, jp, e * 12 + c.w0 * 6, e * 2 + c.w0, LW * 4);
         if (c.want_e) tma_issue_one(bar, dst + C::ROW_UI * (LW * 4), map_b, c.x0, jp, e * 12 + 6);
         if (c.src_win) tma_issue_one(bar, dst + C::ROW_SH * (LW * 4), map_sh, c.x0, jp, e);
@@ -628,6 +708,10 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
                                          const CUtensorMap *map_sh) {
     using C = Cfg<V>;
     constexpr bool SX = C::SX, SY = C::SY;
+    if (C::TR) {
+        row_step_T<V, PH>(c, A, e, b, R, r, map_u, map_b, map_c, map_sh);
+        return;
+    }
     // 1. prefetch march row r + PF into the slot that row r + PF - RING vacated (all its readers finished >= 1 step ago)
     __syncwarp();
     {
@@ -698,7 +782,7 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
         if (c.use_bk) {
             const int jg = min(max(A.gp.grow0 + c.jbase + c.dir * r, 0), A.gp.ny_global - 1);
             if (c.nact < 0) {
-                speed_row_slow<V>(A, c.table, e, uri, c.xs, A.gp.y[jg]);
+                speed_row_slow<V>(A, c.table, e, uri, c.xs, A.gp.y[jg], A.kd);
             } else {
                 const unsigned mask = r < ROWMASK_CAP ? reinterpret_cast<const unsigned short *>(&smf[C::MASK_OFF])[r] : (1u << c.nact) - 1u;
                 if (mask) {
@@ -729,6 +813,53 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
         stage<V, 3, PH>(c, A, b, R, r - 3 * C::SP);
         stage<V, 4, PH>(c, A, b, R, r - 4 * C::SP);
     }
+}
+
+template <int V, int PH>
+__device__ __forceinline__ void row_step_T(const WarpCtx &c, const FusedArgs &A, int e, const Body &b, Regs &R, int r,
+                                           const CUtensorMap *map_u, const CUtensorMap *map_b, const CUtensorMap *map_c,
+                                           const CUtensorMap *map_sh) {
+    using C = Cfg<V>;
+    __syncwarp();
+    {
+        const int rp = r + PF;
+        if (rp < c.nm)  // warp-uniform
+            issue_row<V>(c, e, bar_of<V, PH, PF>(b), c.ring_sa + 4u * (uint32_t)(slot_of<V, PH, PF>(b) - c.lane2), rp, map_u, map_b, map_c, map_sh);
+    }
+    if (r < c.nm) {
+        mbar_wait(b.bar[0] + PH * 8, b.par);
+        const int uri = b.g[0] + PH * C::SLOT_F;
+        constexpr int s0 = PH & 3;
+        f2 U = lds2(uri);
+        if (A.tr_inj == 1) {   // the reference loop as written: the energy cotangent joins the incoming cotangent (halo cells too)
+            const f2 ut = lds2(uri + 4 * LW), ui = lds2(uri + 5 * LW), d = ut - ui;
+            U = U + (c.is_tot ? A.two_dO * (A.inj_w[0] * ut + A.inj_w[2] * d) : A.two_dO * (A.inj_w[1] * ui - A.inj_w[2] * d));
+            sts2(uri, U);   // (a TMA target: fenced below)
+        }
+        if (c.use_bk) {   // c^2 of the row at the three stage times (rows 6..8: no TMA load ever writes them)
+            const int jg = min(max(A.gp.grow0 + c.jbase + c.dir * r, 0), A.gp.ny_global - 1);
+            if (c.nact < 0) {
+                speed_row_slow<V>(A, c.table, e, uri, c.xs, A.gp.y[jg], 1.0f);
+            } else {
+                const unsigned mask = r < ROWMASK_CAP ? reinterpret_cast<const unsigned short *>(&smf[C::MASK_OFF])[r] : (1u << c.nact) - 1u;
+                if (mask) {
+                    speed_row<V>(uri, mask, c.xs, A.gp.y[jg], A.gp.c0, 1.0f);
+                } else {
+                    sts2(uri + C::f_bk(0) * LW, bc2(A.gp.b0));
+                    sts2(uri + C::f_bk(1) * LW, bc2(A.gp.b0));
+                    sts2(uri + C::f_bk(2) * LW, bc2(A.gp.b0));
+                }
+            }
+        }
+        // stage 1 applies J^T at t + dt: its U window holds c^2(t + dt) * wU
+        R.Uf[0][s0] = (c.use_bk ? lds2(uri + C::f_bk(2) * LW) : bc2(A.gp.b0)) * U;
+        R.Vy[0][s0] = lds2(uri + 2 * LW);
+        if (A.tr_inj == 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    stage_T<V, 1, PH>(c, A, b, R, r - 1);
+    stage_T<V, 2, PH>(c, A, b, R, r - 2);
+    stage_T<V, 3, PH>(c, A, b, R, r - 3);
+    stage_T<V, 4, PH>(c, A, b, R, r - 4);
 }
 
 // Body of one work item: blocks 2 k, 2 k + 1 of a variant's range are the total / incident wavefield of item k % n_items of
@@ -802,14 +933,15 @@ __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw
     c.sf[2] = trow[5];
     // the source shape row rides along for every row of the windows that overlap the source's columns; the
     // other windows keep a zero row
-    c.src_win = ep.has_source && item.x0 < ep.src_i1 && item.x0 + LW > ep.src_i0 && ep.src_j1 > ep.src_j0;
+    c.src_win = !C::TR && ep.has_source && item.x0 < ep.src_i1 && item.x0 + LW > ep.src_i0 && ep.src_j1 > ep.src_j0;
+    c.zplane = C::TR ? A.zplane0 + 2 * e : 0;
 
-    c.tx_bytes = (C::LEAN ? (4 + (c.want_e ? 1 : 0) + (c.src_win ? 1 : 0)) : ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0))) * (LW * 4);
+    c.tx_bytes = C::TR ? 6 * (LW * 4) : (C::LEAN ? (4 + (c.want_e ? 1 : 0) + (c.src_win ? 1 : 0)) : ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0))) * (LW * 4);
     if (lane == 0) {
         for (int s = 0; s < C::RING; ++s) mbar_init(c.bar0 + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (!c.src_win)
+    if (!c.src_win && !C::TR)
         for (int s = 0; s < C::RING; ++s) sts2(s * C::SLOT_F + C::ROW_SH * LW + c.lane2, bc2(0.0f));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
@@ -972,7 +1104,7 @@ __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw
 }
 
 template <int V, bool PEER>
-__global__ void __launch_bounds__(32, V == 3 ? 8 : ((V == 0 || V == 4) ? (WV_SP0 == 1 ? WV_OCC_INT : 8) : WV_OCC_STRIP))
+__global__ void __launch_bounds__(32, V == 3 ? 8 : ((V == 0 || V == 4) ? (WV_SP0 == 1 ? WV_OCC_INT : 8) : (V == 6 ? 11 : WV_OCC_STRIP)))
 k_fused_step(const __grid_constant__ FusedArgs A, const __grid_constant__ CUtensorMap map_u7, const __grid_constant__ CUtensorMap map_u6,
              const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_sh) {
     fused_step_body<V, PEER>(A, blockIdx.x, A.items, A.n_items, A.epart_off, map_u7, map_u6, map_c, map_sh, A.table, A.out, A.epart);
@@ -1119,6 +1251,15 @@ struct FusedPlan {
     // waves_profile: event pairs around the launch sets, read back without a host synchronisation between steps
     std::vector<cudaEvent_t> pev;
     int pev_used = 0;
+    // reverse pass on the march (launch_adjoint_interior_march): tensor maps over the cotangent buffers, the G planes and the stored
+    // U planes, re-encoded when a buffer moves; the rectangle the interior items tile (-1: they do not tile one)
+    void *enc = nullptr;
+    CUtensorMap map_w[2], map_g, map_z;
+    const float *map_w_base[2] = {nullptr, nullptr}, *map_g_base = nullptr, *map_z_base = nullptr;
+    size_t map_z_planes = 0;
+    int rect[4] = {0, 0, 0, 0};
+    int rect_state = 0;   // 0: not computed, 1: valid, -1: no rectangle
+    int smem_tr = 0;
 };
 constexpr int PROFILE_PAIRS = 256;
 
@@ -1285,6 +1426,20 @@ int fused_prepare(waves_handle *h) {
         all.insert(all.end(), cls[v].begin(), cls[v].end());
     }
     p->off[4] = (int)all.size();
+    {   // do the interior items tile a rectangle?  (the reverse pass runs the march there and shared-memory tiles around it)
+        int x0 = 1 << 30, x1 = 0, y0 = 1 << 30, y1 = 0;
+        long long area = 0;
+        for (const Item &it : cls[0]) {
+            x0 = std::min(x0, it.x0 + it.vlo);
+            x1 = std::max(x1, it.x0 + it.vhi);
+            y0 = std::min(y0, it.j0);
+            y1 = std::max(y1, it.j1);
+            area += (long long)(it.vhi - it.vlo) * (it.j1 - it.j0);
+        }
+        const bool ok = !cls[0].empty() && gp.ny_own == gp.ny_global && area == (long long)(x1 - x0) * (y1 - y0) && (x0 & 3) == 0 && (x1 & 3) == 0;
+        p->rect_state = ok ? 1 : -1;
+        p->rect[0] = x0, p->rect[1] = x1, p->rect[2] = y0, p->rect[3] = y1;
+    }
     if (p->d_items) cudaFree(p->d_items);
     cudaError_t ae = cudaMalloc((void **)&p->d_items, sizeof(Item) * (all.size() + 1));
     if (ae == cudaSuccess) ae = cudaMemcpy(p->d_items, all.data(), sizeof(Item) * all.size(), cudaMemcpyHostToDevice);
@@ -1318,6 +1473,8 @@ int fused_prepare(waves_handle *h) {
     WV_SET_SMEM(0) WV_SET_SMEM(1) WV_SET_SMEM(2) WV_SET_SMEM(3) WV_SET_SMEM(4)
 #undef WV_SET_SMEM
     p->smem_all = std::max(*std::max_element(p->smem, p->smem + 5), (int)(Cfg<WV_SMALL_SP2 ? 5 : 4>::WARP_F * 4));
+    p->smem_tr = Cfg<6>::WARP_F * 4;
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_tr);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step_all<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_all);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step_all<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_all);
     if (ce != cudaSuccess) {
@@ -1333,6 +1490,7 @@ int fused_prepare(waves_handle *h) {
     ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (ce != cudaSuccess || !fn) return waves_set_error("fused_prepare: cuTensorMapEncodeTiled entry point not found");
     PFN_encodeTiled enc = (PFN_encodeTiled)fn;
+    p->enc = fn;
     int r0 = make_map(enc, &h->map_u[0], h->u[0], gp, 12 * gp.n_env, 7);  // total field + U of the incident field
     int r1 = make_map(enc, &h->map_u[1], h->u[1], gp, 12 * gp.n_env, 7);
     int r2 = make_map(enc, &h->map_shape, h->shape, gp, gp.n_env, 1);
@@ -1454,6 +1612,10 @@ static void fused_fill_args(waves_handle *h, FusedPlan *p, FusedArgs &A, const f
     A.items = p->d_items;
     A.n_items = 0;
     A.epart_off = 0;
+    A.tr_inj = 0;
+    A.inj_w[0] = A.inj_w[1] = A.inj_w[2] = 0.0f;
+    A.two_dO = 0.0f;
+    A.zplane0 = 0;
 }
 
 static bool fused_small_batch(waves_handle *h, FusedPlan *p) {
@@ -1628,5 +1790,63 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
         snprintf(buf, sizeof(buf), "fused step launch: %s", cudaGetErrorString(ce));
         return waves_set_error(buf);
     }
+    return 0;
+}
+
+// ---- reverse pass: the interior of one fused reverse step on the march (V = 6, see stage_T) ----------------------------------------
+// w_in / w_out: cotangent before / after the step, state layout [n_env][12][plane]; G: [n_env][2][plane] accumulated auxiliary
+// cotangent of the interior cells; z: the two U planes [n_env][2][plane] of the stored forward state the step passes, inside the
+// buffer zbase of zfloats floats (one tensor map covers the whole buffer); w3 (host, nullable) its energy weights, inj: 1 = added
+// to the incoming cotangent, 2 = to the outgoing one.  rect receives the rectangle [x0, x1) x [y0, y1) this launch owns.
+// Returns 0: launched; -1: not applicable on this handle (the caller takes the shared-memory tiles everywhere); 1: error.
+int launch_adjoint_interior_march(waves_handle *h, const float *w_in, float *w_out, float *G, const float *zbase, size_t zfloats,
+                                  const float *z, const float *w3, int inj, const float *d_table, int steps, int step, int rect[4]) {
+    FusedPlan *p = plan_of(h, false);
+    if (!p || !h->maps_ready || !p->enc || p->rect_state != 1 || h->peer_on) return -1;
+    const GridP &gp = h->gp;
+    for (int e = 0; e < gp.n_env; ++e)
+        if (h->h_env[e].has_cplane) return -1;   // a frozen speed plane has no cylinder table to evaluate on the march
+    const int n0 = p->off[1] - p->off[0];
+    if (n0 <= 0) return -1;
+    PFN_encodeTiled enc = (PFN_encodeTiled)p->enc;
+    int wi = -1;
+    for (int k = 0; k < 2; ++k)
+        if (p->map_w_base[k] == w_in) wi = k;
+    if (wi < 0) {   // (two cotangent buffers alternate: slot by first use)
+        wi = p->map_w_base[0] == nullptr ? 0 : (p->map_w_base[1] == nullptr ? 1 : 0);
+        if (make_map(enc, &p->map_w[wi], const_cast<float *>(w_in), gp, 12 * gp.n_env, 3)) return waves_set_error("reverse march: tensor map (cotangent) failed");
+        p->map_w_base[wi] = w_in;
+    }
+    if (p->map_g_base != G) {
+        if (make_map(enc, &p->map_g, G, gp, 2 * gp.n_env, 1)) return waves_set_error("reverse march: tensor map (G) failed");
+        p->map_g_base = G;
+    }
+    const size_t zplanes = zfloats / gp.plane;
+    if (p->map_z_base != zbase || p->map_z_planes != zplanes) {
+        if (make_map(enc, &p->map_z, const_cast<float *>(zbase), gp, (int)zplanes, 2)) return waves_set_error("reverse march: tensor map (stored states) failed");
+        p->map_z_base = zbase;
+        p->map_z_planes = zplanes;
+    }
+    FusedArgs A;
+    fused_fill_args(h, p, A, d_table, steps, step, false, -1);
+    A.out = w_out;
+    A.pconst = G;
+    A.skip_aux = 1;
+    A.epart = nullptr;
+    A.kd = -A.kd;   // the transposed interior operator is the forward one with the signs flipped (stage_T)
+    A.akd_h = -A.akd_h;
+    A.akd_f = -A.akd_f;
+    A.dt6kd = -A.dt6kd;
+    A.tr_inj = w3 ? inj : 0;
+    for (int k = 0; k < 3; ++k) A.inj_w[k] = w3 ? w3[k] : 0.0f;
+    A.two_dO = 2.0f * h->d_omega;
+    A.zplane0 = (int)((z - zbase) / (ptrdiff_t)gp.plane);
+    A.items = p->d_items + p->off[0];
+    A.n_items = n0;
+    A.epart_off = 0;
+    const unsigned grid = (unsigned)(2LL * n0 * gp.n_env);
+    k_fused_step<6, false><<<grid, 32, p->smem_tr, h->stream>>>(A, p->map_w[wi], p->map_w[wi], p->map_g, p->map_z);
+    h->launches++;
+    for (int k = 0; k < 4; ++k) rect[k] = p->rect[k];
     return 0;
 }

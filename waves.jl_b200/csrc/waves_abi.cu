@@ -143,6 +143,7 @@ static void free_handle(waves_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int k = 0; k < 9; ++k)
         if (h->adj[k]) cudaFree(h->adj[k]);
+    if (h->adj_g) cudaFree(h->adj_g);
     graph_drop(h);
     if (h->traj) cudaFree(h->traj);
     if (h->ckpt) cudaFree(h->ckpt);
@@ -884,8 +885,8 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
     const GridP &gp = h->gp;
     if (!tspan || steps < 1 || !dL_dz0) return fail("waves_adjoint: need tspan, steps >= 1 and dL_dz0");
     if (gp.ny_own != gp.ny_global) return fail("waves_adjoint: not available on slab handles");
-    const bool stagewise = (adj_mode & WAVES_ADJ_STAGEWISE) != 0;
-    adj_mode &= ~WAVES_ADJ_STAGEWISE;
+    const bool stagewise = (adj_mode & WAVES_ADJ_STAGEWISE) != 0, tiles_only = (adj_mode & WAVES_ADJ_TILES) != 0;
+    adj_mode &= ~(WAVES_ADJ_STAGEWISE | WAVES_ADJ_TILES);
     if (adj_mode != WAVES_ADJ_EXACT && adj_mode != WAVES_ADJ_COMPAT) return fail("waves_adjoint: unknown adjoint mode %d", adj_mode);
     if (fwd_mode != WAVES_MODE_FUSED && fwd_mode != WAVES_MODE_EXACT) return fail("waves_adjoint: unknown forward mode %d", fwd_mode);
     const size_t state = (size_t)gp.env_stride * gp.n_env, planes = (size_t)gp.plane * gp.n_env;
@@ -900,6 +901,7 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
     for (int k = 0; k < nstate; ++k)
         if (!h->adj[k]) CU_TRY(cudaMalloc((void **)&h->adj[k], sizeof(float) * state));
     if (!h->adj[7]) CU_TRY(cudaMalloc((void **)&h->adj[7], sizeof(float) * 3 * planes));
+    if (fused_rev && !tiles_only && !h->adj_g) CU_TRY(cudaMalloc((void **)&h->adj_g, sizeof(float) * 2 * planes));
     if (dL_dc && !h->adj[8]) CU_TRY(cudaMalloc((void **)&h->adj[8], sizeof(float) * planes));
     if (fwd_mode == WAVES_MODE_EXACT || !fused_rev)
         if (ensure_exact_scratch(h)) return 1;
@@ -1004,6 +1006,16 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
     };
     if (dL_dc) CU_TRY(cudaMemsetAsync(GC, 0, sizeof(float) * planes, h->stream));
     CU_TRY(cudaMemsetAsync(W, 0, sizeof(float) * state, h->stream));
+    // Fused reverse step: its interior runs on the march kernel (kernels_fused.cu, stage_T) and keeps the auxiliary cotangents of
+    // those cells as ONE accumulated plane G, added to them after the sweep; the frame around it takes the shared-memory tiles.
+    // march: -1 not decided yet (the first step tells whether the handle's work plan allows it), 0 tiles everywhere, 1 march.
+    int march = (fused_rev && !tiles_only) ? -1 : 0;
+    int rect[4] = {0, 0, 0, 0};
+    if (march) {
+        // the march never writes the auxiliary cotangents of its cells: both ping-pong buffers must hold the same (initial) values there
+        CU_TRY(cudaMemsetAsync(h->adj_g, 0, sizeof(float) * 2 * planes, h->stream));
+        CU_TRY(cudaMemsetAsync(WS, 0, sizeof(float) * state, h->stream));
+    }
     auto speeds = [&](int i) {
         if (sp && !(design_static && b2_ready))
             for (int tau = 0; tau < 3; ++tau) launch_speed2(h, 0, gp.n_env, h->d_stage, rows, i, tau == 0 ? 0 : (tau == 1 ? 1 : 3), B2[tau]);
@@ -1026,6 +1038,7 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
             if (copy_planes_fast(h, T + (size_t)e * gp.env_stride, dL_dzN + (size_t)e * 12 * gp.ny_own * gp.nx, nullptr, 12))
                 return 1;
         launch_lin3(h, W, 1.0f, W, 1.0f, T, 0.0f, nullptr);
+        if (march) CU_TRY(cudaMemcpyAsync(WS, W, sizeof(float) * state, cudaMemcpyDeviceToDevice, h->stream));
         return 0;
     };
     // W <- W + J_step(z_i, t_i)^T W with the per-stage kernels, dL/dc accumulated: the pullback of one runge_kutta call
@@ -1060,7 +1073,16 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
             // (a design that does not move has ONE speed plane: the kernel then stages a single plane in shared memory)
             const float *b2v[3] = {sp ? B2[0] : nullptr, sp ? B2[design_static ? 0 : 1] : nullptr, sp ? B2[design_static ? 0 : 2] : nullptr};
             const bool pre = adj_mode == WAVES_ADJ_COMPAT && w3, post = adj_mode == WAVES_ADJ_EXACT && w3;
-            if (launch_adjoint_step_fused(h, W, WS, b2v, pre ? zslot : nullptr, pre ? w3 : zero3, post ? zslot : nullptr, post ? w3 : zero3))
+            if (march) {
+                const int rc = launch_adjoint_interior_march(h, W, WS, h->adj_g, h->traj, h->traj_cap, zslot, w3, pre ? 1 : 2, h->d_stage, rows, i, rect);
+                if (rc == 1) return 1;
+                if (rc < 0 && march > 0) return fail("waves_adjoint: the march kernel became unavailable in the middle of a sweep");
+                march = rc == 0 ? 1 : 0;
+            }
+            if (march) {
+                if (launch_adjoint_step_frame(h, W, WS, b2v, pre ? zslot : nullptr, pre ? w3 : zero3, post ? zslot : nullptr, post ? w3 : zero3, rect))
+                    return 1;
+            } else if (launch_adjoint_step_fused(h, W, WS, b2v, pre ? zslot : nullptr, pre ? w3 : zero3, post ? zslot : nullptr, post ? w3 : zero3))
                 return 1;
             std::swap(W, WS);
             return 0;
@@ -1094,6 +1116,7 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
         CU_TRY(cudaMemcpyAsync(h->u[h->cur], h->ckpt + (size_t)(nseg - 1) * state, sizeof(float) * state, cudaMemcpyDeviceToDevice, h->stream));
         h->aux_synced = 0;
     }
+    if (march > 0) launch_apply_aux_cotangent(h, W, h->adj_g, rect);
     for (int e = 0; e < gp.n_env; ++e) {
         if (copy_planes_fast(h, W + (size_t)e * gp.env_stride, nullptr, dL_dz0 + (size_t)e * 12 * gp.ny_own * gp.nx, 12)) return 1;
         if (dL_dc && copy_planes_fast(h, GC + (size_t)e * gp.plane, nullptr, dL_dc + (size_t)e * gp.ny_own * gp.nx, 1)) return 1;

@@ -73,6 +73,8 @@ struct waves_handle {
     int adj_ckpt;         // steps per segment requested by the caller (0: automatic)
     int adj_last_K;       // steps per segment the last waves_adjoint call used
     int adj_z0, adj_z1;   // zero-sigma zone of the profile (fused reverse step), 0/0: not computed yet
+    float *adj_g;         // [n_env][2][plane] accumulated auxiliary cotangent of the interior cells (reverse pass on the march)
+    int adj_march;        // waves_set_adjoint_march: 1 (default) the interior of the fused reverse step runs on the march kernel
     float *d_x, *d_y, *d_sigma;
     EnvParams *h_env, *d_env;
     bool env_dirty;
@@ -150,6 +152,9 @@ void launch_energy_cotangent(waves_handle *h, const float *z, long long z_env, l
 int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, const float *const b2[3], const float *pre_u,
                               const float *pre_w3, const float *post_u, const float *post_w3);
 void launch_gather_u(waves_handle *h, const float *u, float *out);
+int launch_adjoint_step_frame(waves_handle *h, const float *w_in, float *w_out, const float *const b2[3], const float *pre_u,
+                              const float *pre_w3, const float *post_u, const float *post_w3, const int rect[4]);
+void launch_apply_aux_cotangent(waves_handle *h, float *w, const float *G, const int rect[4]);
 
 // ---- kernels_fused.cu ----
 int fused_prepare(waves_handle *h);  // work items, tensor maps, smem attribute; 0 on success
@@ -160,6 +165,8 @@ int source_bbox(waves_handle *h, int env, int *bbox4);
 int waves_set_error(const char *msg);  // sets the thread-local message, returns 1
 int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step, float *d_e3 /*nullable*/, int defer_slot = -1);
 int launch_fused_multi(waves_handle *h, const float *d_table, int steps, int step0, int count, bool energy);  // 0 done, -1 n/a, 1 error
+int launch_adjoint_interior_march(waves_handle *h, const float *w_in, float *w_out, float *G, const float *zbase, size_t zfloats,
+                                  const float *z, const float *w3, int inj, const float *d_table, int steps, int step, int rect[4]);
 bool fused_is_small_batch(waves_handle *h);
 int fused_epart_slots(waves_handle *h);
 void fused_reduce_deferred(waves_handle *h, int count, float *d_e3, int env_stride3);
