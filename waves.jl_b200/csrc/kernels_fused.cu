@@ -75,6 +75,12 @@ namespace {
                         // single 700^2 environment: 31.5 -> 45.7 us per step -- CTAs that become resident as slots free up no longer land
                         // round-robin on the SMs, which breaks the per-SM grouping by variant (k_fused_step_all) the step's speed rests on
 #endif
+#ifndef WV_ADJ_CONCURRENT
+#define WV_ADJ_CONCURRENT 0  // reverse pass: 1 = the march kernel of the interior runs beside the tile kernel of the frame (side stream,
+                             // event fork / join).  Measured: single environment 0.043 -> 0.038 s per 500-step gradient, 32 environments
+                             // unchanged -- but intermittently wrong gradients on freshly created handles (2 of 3 runs of the GPU suite;
+                             // never with the two kernels on one stream, 3 of 3), not root-caused: off
+#endif
 #ifndef WV_MBAR_FAST
 #define WV_MBAR_FAST 1  // 1 (measured +2.5%): the bounded-spin trap of mbar_wait lives in an out-of-line slow path (first try_wait inline)
 #endif
@@ -1845,8 +1851,26 @@ int launch_adjoint_interior_march(waves_handle *h, const float *w_in, float *w_o
     A.n_items = n0;
     A.epart_off = 0;
     const unsigned grid = (unsigned)(2LL * n0 * gp.n_env);
+    // on a side stream: the tiles of the frame (launched by the caller on the handle's stream) read the same cotangent and write
+    // other cells, so the two kernels of a reverse step run side by side; adjoint_march_join() orders the next step after both
+#if WV_ADJ_CONCURRENT
+    cudaEventRecord(p->ev_fork, h->stream);
+    cudaStreamWaitEvent(p->side[0], p->ev_fork, 0);
+    k_fused_step<6, false><<<grid, 32, p->smem_tr, p->side[0]>>>(A, p->map_w[wi], p->map_w[wi], p->map_g, p->map_z);
+    cudaEventRecord(p->ev_join[0], p->side[0]);
+#else
     k_fused_step<6, false><<<grid, 32, p->smem_tr, h->stream>>>(A, p->map_w[wi], p->map_w[wi], p->map_g, p->map_z);
+#endif
     h->launches++;
     for (int k = 0; k < 4; ++k) rect[k] = p->rect[k];
     return 0;
+}
+
+void adjoint_march_join(waves_handle *h) {
+    FusedPlan *p = plan_of(h, false);
+#if WV_ADJ_CONCURRENT
+    if (p) cudaStreamWaitEvent(h->stream, p->ev_join[0], 0);
+#else
+    (void)p;
+#endif
 }

@@ -1082,6 +1082,7 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
             if (march) {
                 if (launch_adjoint_step_frame(h, W, WS, b2v, pre ? zslot : nullptr, pre ? w3 : zero3, post ? zslot : nullptr, post ? w3 : zero3, rect))
                     return 1;
+                adjoint_march_join(h);
             } else if (launch_adjoint_step_fused(h, W, WS, b2v, pre ? zslot : nullptr, pre ? w3 : zero3, post ? zslot : nullptr, post ? w3 : zero3))
                 return 1;
             std::swap(W, WS);
