@@ -70,7 +70,7 @@ struct AdjFArgs {
     // general launch over up to four rectangular bands (the frame around the rectangle the march kernel owns): band k holds the
     // blocks [bstart[k], bstart[k+1]) as tiles of ATX x TY from (bx0, by0), clipped to (bx1, by1); nband == 0: one band = the domain
     int nband;
-    int bx0[4], bx1[4], by0[4], by1[4], btx[4], bstart[5];
+    int bx0[4], bx1[4], by0[4], by1[4], btx[4], bty[4], bstart[5];   // bty: owned rows per tile of the band (as many as its width lets 512 threads hold)
 };
 
 extern __shared__ __align__(16) float adj_sm[];
@@ -213,13 +213,14 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_gen4(const __grid_const
     const int nx = gp.nx, ny = gp.ny_global, nxp = gp.nxp;
     const long long P = gp.plane;
     const int e = blockIdx.y >> 1, wf = blockIdx.y & 1;
-    int x0, y0, xe, ye;
+    int x0, y0, xe, ye, tyr = TY;
     if (A.nband > 0) {
         int k = 0;
         while (k + 1 < A.nband && (int)blockIdx.x >= A.bstart[k + 1]) ++k;
         const int bi = (int)blockIdx.x - A.bstart[k];
         const int tx = bi % A.btx[k], ty = bi / A.btx[k];
-        x0 = A.bx0[k] + tx * ATX, y0 = A.by0[k] + ty * TY;
+        tyr = A.bty[k];
+        x0 = A.bx0[k] + tx * ATX, y0 = A.by0[k] + ty * tyr;
         xe = A.bx1[k], ye = A.by1[k];
     } else {
         const int tx = blockIdx.x % A.tiles_x, ty = blockIdx.x / A.tiles_x;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(ANT, 2) k_adjoint_step_gen4(const __grid_const
         if (x0 >= A.skip_x0 && x0 + ATX <= A.skip_x1 && y0 >= A.skip_y0 && y0 + TY <= A.skip_y1) return;
     }
     if (x0 >= xe || y0 >= ye) return;
-    const int x1 = min(x0 + ATX, xe), y1 = min(y0 + TY, ye);
+    const int x1 = min(x0 + ATX, xe), y1 = min(y0 + tyr, ye);
     const int L = max(x0 - 4, 0), T0 = max(y0 - 4, 0);
     int R = min(x1 + 4, nx), B = min(y1 + 4, ny);
     if (nx - R <= 2) R = nx;
@@ -462,11 +463,23 @@ int launch_adjoint_step_frame(waves_handle *h, const float *w_in, float *w_out, 
         if (bx1[k] <= bx0[k] || by1[k] <= by0[k]) continue;
         A.bx0[nb] = bx0[k], A.bx1[nb] = bx1[k], A.by0[nb] = by0[k], A.by1[nb] = by1[k];
         A.btx[nb] = (bx1[k] - bx0[k] + ATX - 1) / ATX;
+        // rows per tile: a region of W columns (tile + halos, + 2 where it is extended to a domain edge) is W/4 groups wide, and
+        // (rows + 8 halo rows + 2 of an extension) x groups must fit the CTA's 512 threads; the band's height is split evenly
+        int gprmax = 1;
+        for (int tx = 0; tx < A.btx[nb]; ++tx) {   // (the kernel's own region arithmetic)
+            const int x0 = bx0[k] + tx * ATX, x1 = std::min(x0 + ATX, bx1[k]), L = std::max(x0 - 4, 0);
+            int R = std::min(x1 + 4, gp.nx);
+            if (gp.nx - R <= 2) R = gp.nx;
+            gprmax = std::max(gprmax, ((R - L + 3) & ~3) >> 2);
+        }
+        const int tymax = std::max(4, ANT / gprmax - 10), H = by1[k] - by0[k];
+        const int nt = (H + tymax - 1) / tymax;
+        A.bty[nb] = (H + nt - 1) / nt;
         A.bstart[nb] = blocks;
-        blocks += A.btx[nb] * ((by1[k] - by0[k] + ATY_GEN - 1) / ATY_GEN);
+        blocks += A.btx[nb] * nt;
         ++nb;
     }
-    for (int k = nb; k < 4; ++k) A.bx0[k] = A.bx1[k] = A.by0[k] = A.by1[k] = 0, A.btx[k] = 1, A.bstart[k] = blocks;
+    for (int k = nb; k < 4; ++k) A.bx0[k] = A.bx1[k] = A.by0[k] = A.by1[k] = 0, A.btx[k] = 1, A.bty[k] = ATY_GEN, A.bstart[k] = blocks;
     A.bstart[4] = blocks;
     if (nb < 4) A.bstart[nb] = blocks;
     A.nband = nb;
@@ -518,7 +531,7 @@ int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, 
     }
     A.two_dO = 2.0f * h->d_omega;
     A.nband = 0;
-    for (int k = 0; k < 4; ++k) A.bx0[k] = A.bx1[k] = A.by0[k] = A.by1[k] = 0, A.btx[k] = 1, A.bstart[k] = 0;
+    for (int k = 0; k < 4; ++k) A.bx0[k] = A.bx1[k] = A.by0[k] = A.by1[k] = 0, A.btx[k] = 1, A.bty[k] = ATY_GEN, A.bstart[k] = 0;
     A.bstart[4] = 0;
     if (has_int) {
         A.tiles_x = (xi1 - xi0) / ATX_INT;
