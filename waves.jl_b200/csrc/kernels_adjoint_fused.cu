@@ -14,6 +14,10 @@
 // and D^T the transpose of the 3-band matrix of src/operators.jl:10-22 (its one-sided first / last rows couple the three
 // outermost cells to the edge cell).
 //
+// Since round 2 the INTERIOR of the step runs on the forward kernel's march (kernels_fused.cu: stage_T, k_fused_step<6>); the kernels
+// of this file advance the frame around it (k_adjoint_step_gen4 on four bands, launch_adjoint_step_frame) or, with
+// WAVES_ADJ_TILES or where the march does not apply, everything (launch_adjoint_step_fused).
+//
 // Temporal blocking in shared memory: a CTA owns a 64 x TY tile of ONE wavefield of one environment, loads it with a 4-cell
 // halo (one cell per RK stage), runs the four transposed stages on the tile in shared memory and writes the tile once: 12
 // planes read + 12 written per reverse step instead of 30 per STAGE for the per-stage kernels of kernels_adjoint.cu.  The halo
