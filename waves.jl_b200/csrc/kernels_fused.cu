@@ -76,10 +76,10 @@ namespace {
                         // round-robin on the SMs, which breaks the per-SM grouping by variant (k_fused_step_all) the step's speed rests on
 #endif
 #ifndef WV_ADJ_CONCURRENT
-#define WV_ADJ_CONCURRENT 0  // reverse pass: 1 = the march kernel of the interior runs beside the tile kernel of the frame (side stream,
-                             // event fork / join).  Measured: single environment 0.043 -> 0.038 s per 500-step gradient, 32 environments
-                             // unchanged -- but intermittently wrong gradients on freshly created handles (2 of 3 runs of the GPU suite;
-                             // never with the two kernels on one stream, 3 of 3), not root-caused: off
+#define WV_ADJ_CONCURRENT 1  // reverse pass: the march kernel of the interior runs beside the tile kernel of the frame (side stream,
+                             // event fork / join; the two touch disjoint cells).  (Its first form gave intermittently wrong gradients:
+                             // V = 6 had inherited SY from the variant bits, so the ambient-speed row landed on the first row of the
+                             // next ring slot -- a TMA target -- without a proxy fence; harmless by timing on one stream.)
 #endif
 #ifndef WV_MBAR_FAST
 #define WV_MBAR_FAST 1  // 1 (measured +2.5%): the bounded-spin trap of mbar_wait lives in an out-of-line slow path (first try_wait inline)
@@ -112,7 +112,7 @@ constexpr int OWN_W = LW - 8;  // owned columns of a full window (4-column halo 
 //   rows f_bk(0..2): kd*c^2 at the three stage times (only where a cylinder is near).
 template <int V>
 struct Cfg {
-    static constexpr bool SX = (V & 1) != 0, SY = (V & 2) != 0;
+    static constexpr bool SX = V < 4 && (V & 1) != 0, SY = V < 4 && (V & 2) != 0;   // (V >= 4 are interior forms: no sigma)
     static constexpr bool TR = (V == 6);   // transposed (reverse-pass) interior step, see stage_T
     static constexpr bool INT = (V == 0 || V == 4 || V == 5 || V == 6), LEAN = (V == 4 || V == 5 || V == 6);
     // Stage spacing: stage s works SP rows behind stage s-1.  With SP = 1 the stages of one loop iteration form a
