@@ -47,6 +47,7 @@ typedef struct waves_handle waves_handle;
 #define WAVES_ADJ_EXACT 0  /* exact discrete adjoint  lambda_i = a_i + (I+J_i^T) lambda_{i+1} */
 #define WAVES_ADJ_COMPAT 1 /* the reference loop as written (one extra step-vjp) */
 #define WAVES_ADJ_STAGEWISE 0x100 /* OR into adj_mode: reverse sweep with the per-stage kernels even without dL_dc (cross-check) */
+#define WAVES_ADJ_NO_RING 0x400   /* OR into adj_mode: the marching kernel takes the interior only, the whole PML frame stays on tiles */
 #define WAVES_ADJ_TILES 0x200     /* OR into adj_mode: the fused reverse step takes the shared-memory tile kernels everywhere instead of
                                      the marching kernel in the interior (cross-check of the two) */
 

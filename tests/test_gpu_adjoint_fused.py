@@ -17,7 +17,8 @@ F32 = np.float32
 
 # n = 48: general tiles only (the zero-sigma zone is narrower than a tile); n = 200 with a thin PML: interior tiles, general
 # tiles and the seam between the two launches; n = 131: odd size, row pitch != nx, partial tiles
-@pytest.mark.parametrize("n,pml_width", [(48, 0.5), (200, 0.25), (131, 0.2)])
+# n = 200 with a 25-cell PML: the PML ring runs on the march as well (variants 7, 8, 9), tiles only on the outer 8 cells
+@pytest.mark.parametrize("n,pml_width", [(48, 0.5), (200, 0.25), (131, 0.2), (200, 0.5)])
 @pytest.mark.parametrize("adj_mode", [wb.ADJ_EXACT, wb.ADJ_COMPAT])
 def test_fused_reverse_matches_autograd_and_per_stage_kernels(n, pml_width, adj_mode):
     steps = 6 if adj_mode == wb.ADJ_EXACT else 5
@@ -165,4 +166,27 @@ def test_march_interior_equals_tile_kernels(n, pml_width, adj_mode):
     assert la[0] == lb[0]
     for f in range(12):
         assert rel(ga[0, f], np.float64(gb[0, f])) < 2e-6, f"field {f}: {rel(ga[0, f], np.float64(gb[0, f]))}"
+    eng.close()
+
+
+@pytest.mark.parametrize("n,pml_width", [(200, 0.5), (256, 0.6)])
+@pytest.mark.parametrize("adj_mode", [wb.ADJ_EXACT, wb.ADJ_COMPAT])
+def test_march_pml_ring_equals_tile_kernels(n, pml_width, adj_mode):
+    """With a PML of >= 16 cells the ring between the outer 8 cells of the domain and the interior rectangle runs on the march
+    too (left / right strips, top / bottom strips, corners: stage_TP), the tiles keep the outer 8 cells.  Three forms of the
+    same gradient: ring + interior on the march, interior only, tiles everywhere."""
+    steps = 7
+    p, eng, ts, z0, w, aN = setup(n=n, steps=steps, pml_width=pml_width)
+    outs = []
+    for kw in (dict(), dict(ring=False), dict(march=False)):
+        eng.set_state(z0[None])
+        l0 = eng.launch_count()
+        loss, dz0, _ = eng.adjoint(ts, w, aN[None], adj_mode=adj_mode, want_dc=False, **kw)
+        outs.append((loss.copy(), dz0.copy(), eng.launch_count() - l0))
+    assert outs[0][2] > outs[1][2] > outs[2][2] - 2, [o[2] for o in outs]   # 5 / 2 / 2 launches per reverse step (+ the G pass)
+    assert outs[0][2] != outs[1][2], "the ring variants must have been launched"
+    for k in (0, 1):
+        assert outs[k][0][0] == outs[2][0][0]
+        for f in range(12):
+            assert rel(outs[k][1][0, f], np.float64(outs[2][1][0, f])) < 2e-6, f"form {k} field {f}: {rel(outs[k][1][0, f], np.float64(outs[2][1][0, f]))}"
     eng.close()

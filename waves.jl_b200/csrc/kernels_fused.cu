@@ -114,6 +114,9 @@ template <int V>
 struct Cfg {
     static constexpr bool SX = V < 4 && (V & 1) != 0, SY = V < 4 && (V & 2) != 0;   // (V >= 4 are interior forms: no sigma)
     static constexpr bool TR = (V == 6);   // transposed (reverse-pass) interior step, see stage_T
+    // transposed step in the PML ring (away from the border: central stencils, mask 1), see stage_TP: V = 7 columns with sigma_x,
+    // V = 8 rows with sigma_y, V = 9 both
+    static constexpr bool TP = (V >= 7 && V <= 9), TSX = (V == 7 || V == 9), TSY = (V == 8 || V == 9);
     static constexpr bool INT = (V == 0 || V == 4 || V == 5 || V == 6), LEAN = (V == 4 || V == 5 || V == 6);
     // Stage spacing: stage s works SP rows behind stage s-1.  With SP = 1 the stages of one loop iteration form a
     // dependent chain (stage s needs the row stage s-1 just produced); with SP = 2 they are independent, which
@@ -129,6 +132,7 @@ struct Cfg {
     static constexpr int ROW_P = INT ? 3 : 8;
     // V = 6 slot rows: 0..2 the cotangents of U, Vx, Vy (TMA), 3 the accumulated auxiliary cotangent G (TMA), 4, 5 U of the total /
     // incident field of the stored forward state (TMA; energy cotangent), 6..8 c^2 at the three stage times (never a TMA target)
+    // V = 7..9 slot rows: 0..5 the six cotangents (TMA), 6, 7 U of the total / incident field of the stored state (TMA), 8..10 c^2
     static constexpr int SLOT_ROWS = TR ? 9 : (INT ? 8 : 11);
     static constexpr int SLOT_F = SLOT_ROWS * LW;
     static constexpr int RING_F = RING * SLOT_F;
@@ -143,7 +147,7 @@ struct Cfg {
     static constexpr int ROW_BK0 = SY ? 9 : -1;  // (measured: pays on the top-bottom strips and corners only)
     // row holding kd*c^2 at stage-time index tau
     __host__ __device__ static constexpr int f_bk(int tau) {
-        return TR ? 6 + tau : (LEAN ? (tau == 0 ? 4 : 5 + tau) : (INT ? 4 + tau : (tau == 0 ? 6 : 8 + tau)));
+        return TR ? 6 + tau : TP ? 8 + tau : (LEAN ? (tau == 0 ? 4 : 5 + tau) : (INT ? 4 + tau : (tau == 0 ? 6 : 8 + tau)));
     }
 };
 
@@ -688,6 +692,10 @@ template <int V, int PH>
 __device__ __forceinline__ void row_step_T(const WarpCtx &c, const FusedArgs &A, int e, const Body &b, Regs &R, int r,
                                            const CUtensorMap *map_u, const CUtensorMap *map_b, const CUtensorMap *map_c,
                                            const CUtensorMap *map_sh);
+template <int V, int PH>
+__device__ __forceinline__ void row_step_TP(const WarpCtx &c, const FusedArgs &A, int e, const Body &b, Regs &R, int r,
+                                            const CUtensorMap *map_u, const CUtensorMap *map_b, const CUtensorMap *map_c,
+                                            const CUtensorMap *map_sh);
 
 // Issue the TMA loads of march row rp (state planes, and where needed U of the incident field and the source shape row) into the
 // ring slot at shared address dst, completing on mbarrier bar.  Warp-uniform operands; the whole warp executes this.
@@ -696,7 +704,9 @@ __device__ __forceinline__ void issue_row(const WarpCtx &c, int e, uint32_t bar,
                                           const CUtensorMap *map_b, const CUtensorMap *map_c, const CUtensorMap *map_sh) {
     using C = Cfg<V>;
     const int jp = c.jbase + c.dir * rp;
-    if (C::TR) {   // map_u: the incoming cotangent (box of 3 planes), map_c: the G planes, map_sh: the stored U planes (box of 2)
+    if (C::TP) {   // map_u: the incoming cotangent (box of 6 planes), map_sh: the stored U planes (box of 2) into rows 6, 7
+        tma_issue_row(bar, c.tx_bytes, dst, map_u, c.x0, jp, e * 12 + c.w0 * 6, true, dst + 6 * (LW * 4), map_sh, c.zplane);
+    } else if (C::TR) {   // map_u: the incoming cotangent (box of 3 planes), map_c: the G planes, map_sh: the stored U planes (box of 2)
         tma_issue_row_lean(bar, c.tx_bytes, dst, map_u, map_c, c.x0, jp, e * 12 + c.w0 * 6, e * 2 + c.w0, LW * 4);
         tma_issue_one(bar, dst + 4 * (LW * 4), map_sh, c.x0, jp, c.zplane);
     } else if (C::LEAN) {
@@ -716,6 +726,10 @@ __device__ __forceinline__ void row_step(const WarpCtx &c, const FusedArgs &A, i
     constexpr bool SX = C::SX, SY = C::SY;
     if (C::TR) {
         row_step_T<V, PH>(c, A, e, b, R, r, map_u, map_b, map_c, map_sh);
+        return;
+    }
+    if (C::TP) {
+        row_step_TP<V, PH>(c, A, e, b, R, r, map_u, map_b, map_c, map_sh);
         return;
     }
     // 1. prefetch march row r + PF into the slot that row r + PF - RING vacated (all its readers finished >= 1 step ago)
@@ -868,6 +882,141 @@ __device__ __forceinline__ void row_step_T(const WarpCtx &c, const FusedArgs &A,
     stage_T<V, 4, PH>(c, A, b, R, r - 4);
 }
 
+// ---- reverse pass, PML ring (V = 7, 8, 9) ---------------------------------------------------------------------------------------
+// The transposed right-hand side with sigma != 0, at least 8 cells from the domain border (central stencils D^T = -D, mask 1; the
+// outer 8 cells stay on the shared-memory tiles, which hold all the border logic):
+//     (J^T y)_U    = -(sx + sy) yU - Dx yVx - Dy yVy + sx sy yOm
+//     (J^T y)_Vx   = -Dx [c^2 (yU + sy yPsiy)] - sx yVx
+//     (J^T y)_Vy   = -Dy [c^2 (yU + sx yPsix)] - sy yVy
+//     (J^T y)_Psix = (J^T y)_Psiy = yU,   (J^T y)_Om = -yU
+// Windows: Uf = Qy = c^2 (yU + sx yPsix) (rows m-1, m+1), Px = Qx = c^2 (yU + sy yPsiy) (row m), Py = yU, Om = yOm (row m), Vx, Vy; the
+// three auxiliary cotangents all move by dt/6 (y0 + 2 y1 + 2 y2 + y3)_U (accumulated in aPx) and are stored to their planes.
+template <int V, int S, int PH>
+__device__ __forceinline__ void stage_TP(const WarpCtx &c, const FusedArgs &A, const Body &b, Regs &R, int m) {
+    using C = Cfg<V>;
+    constexpr bool TSX = C::TSX, TSY = C::TSY;
+    constexpr int sc = (PH - S + 16) & 3, sm = (sc + 3) & 3, sp = (sc + 1) & 3;  // rows m, m-1, m+1
+    const int uri = slot_of<V, PH, -S>(b);
+    const float a = (S == 3) ? A.dt : A.hdt;
+    const float akd = (S == 3) ? A.akd_f : A.akd_h;            // a * (-kd)
+    constexpr int tau_next = (S == 1 || S == 2) ? 1 : 0;       // stage S + 1 applies J^T at t+dt/2, t+dt/2, t
+    const f2 uU = lds2(uri), uVx = lds2(uri + LW), uVy = lds2(uri + 2 * LW);
+    const f2 sx = c.sx;
+    const float sy = TSY ? R.sy[sc] : 0.0f;
+    const f2 yU = (S == 1) ? uU : R.Py[S - 1][sc];
+    const f2 vxC = (S == 1) ? uVx : R.Vx[S - 1][sc];
+    const f2 vyC = R.Vy[S - 1][sc];
+    const f2 dQx = ddx_int(R.Px[S - 1][sc]), dVx = ddx_int(vxC);
+    const f2 dQy = R.Uf[S - 1][sp] - R.Uf[S - 1][sm];
+    const f2 dVy = R.Vy[S - 1][sp] - R.Vy[S - 1][sm];
+    // kU without the derivative part; kd-scaled differences are added with the (negated) a kd / dt/6 kd constants
+    f2 kU0 = TSX ? bc2(0.0f) - (sx + bc2(sy)) * yU : bc2(-sy) * yU;
+    if (TSX && TSY) kU0 = fma2(bc2(sy) * sx, (S == 1) ? lds2(uri + 5 * LW) : R.Om[S - 1][sc], kU0);
+    const f2 dsum = dVx + dVy;
+    const bool st = (unsigned)(m - c.mo0) < c.mon;
+    if (S < 4) {
+        const f2 yUn = fma2(akd, dsum, fma2(a, kU0, uU));
+        f2 yVx = fma2(akd, dQx, uVx), yVy = fma2(akd, dQy, uVy);
+        if (TSX) yVx = yVx - (a * sx) * vxC;
+        if (TSY) yVy = fma2(-a * sy, vyC, yVy);
+        const f2 c2n = c.use_bk ? lds2(uri + C::f_bk(tau_next) * LW) : bc2(A.gp.b0);
+        R.Py[S][sc] = yUn;
+        R.Vx[S][sc] = yVx;
+        R.Vy[S][sc] = yVy;
+        // y_S of the auxiliary cotangents: w + a (J^T y_{S-1}) = w +- a yU
+        R.Uf[S][sc] = TSX ? c2n * fma2(sx, fma2(a, yU, lds2(uri + 3 * LW)), yUn) : c2n * yUn;
+        R.Px[S][sc] = TSY ? c2n * fma2(sy, fma2(a, yU, lds2(uri + 4 * LW)), yUn) : c2n * yUn;
+        if (TSX && TSY) R.Om[S][sc] = fma2(-a, yU, lds2(uri + 5 * LW));
+        if (S == 1) {
+            R.aU[0][sc] = kU0;
+            R.aOm[0][sc] = dsum;
+            R.aVx[0][sc] = dQx;
+            R.aVy[0][sc] = dQy;
+            if (TSX) R.aPy[0][sc] = sx * vxC;
+            if (TSY) R.aVy[1][sc] = sy * vyC;
+            R.aPx[0][sc] = fma2(2.0f, yUn, uU);                // y0 + 2 y1
+        } else {
+            R.aU[0][sc] = fma2(2.0f, kU0, R.aU[0][sc]);
+            R.aOm[0][sc] = fma2(2.0f, dsum, R.aOm[0][sc]);
+            R.aVx[0][sc] = fma2(2.0f, dQx, R.aVx[0][sc]);
+            R.aVy[0][sc] = fma2(2.0f, dQy, R.aVy[0][sc]);
+            if (TSX) R.aPy[0][sc] = fma2(2.0f, sx * vxC, R.aPy[0][sc]);
+            if (TSY) R.aVy[1][sc] = fma2(2.0f, sy * vyC, R.aVy[1][sc]);
+            R.aPx[0][sc] = (S == 2) ? fma2(2.0f, yUn, R.aPx[0][sc]) : R.aPx[0][sc] + yUn;
+        }
+    } else if (st) {
+        float *o = b.po + PH * c.rowstep;
+        // w' = w + dt/6 (k1 + 2 k2 + 2 k3 + k4); kd-scaled parts and plain parts are accumulated separately
+        f2 oU = fma2(A.dt6kd, R.aOm[0][sc] + dsum, fma2(A.dt6, R.aU[0][sc] + kU0, uU));
+        f2 oVx = fma2(A.dt6kd, R.aVx[0][sc] + dQx, uVx), oVy = fma2(A.dt6kd, R.aVy[0][sc] + dQy, uVy);
+        if (TSX) oVx = fma2(-A.dt6, R.aPy[0][sc] + sx * vxC, oVx);
+        if (TSY) oVy = fma2(-A.dt6, R.aVy[1][sc] + sy * vyC, oVy);
+        if (A.tr_inj == 2) {   // exact discrete adjoint: the energy cotangent of the stored state joins the outgoing cotangent
+            const f2 ut = lds2(uri + 6 * LW), ui = lds2(uri + 7 * LW), d = ut - ui;
+            oU = oU + (c.is_tot ? A.two_dO * (A.inj_w[0] * ut + A.inj_w[2] * d) : A.two_dO * (A.inj_w[1] * ui - A.inj_w[2] * d));
+        }
+        const f2 g = A.dt6 * R.aPx[0][sc];
+        stg2(o, oU);
+        stg2(o + A.plane, oVx);
+        stg2(o + 2u * A.plane, oVy);
+        stg2(o + 3u * A.plane, lds2(uri + 3 * LW) + g);
+        stg2(o + 4u * A.plane, lds2(uri + 4 * LW) + g);
+        stg2(o + 5u * A.plane, lds2(uri + 5 * LW) - g);
+    }
+}
+
+template <int V, int PH>
+__device__ __forceinline__ void row_step_TP(const WarpCtx &c, const FusedArgs &A, int e, const Body &b, Regs &R, int r,
+                                            const CUtensorMap *map_u, const CUtensorMap *map_b, const CUtensorMap *map_c,
+                                            const CUtensorMap *map_sh) {
+    using C = Cfg<V>;
+    __syncwarp();
+    {
+        const int rp = r + PF;
+        if (rp < c.nm)  // warp-uniform
+            issue_row<V>(c, e, bar_of<V, PH, PF>(b), c.ring_sa + 4u * (uint32_t)(slot_of<V, PH, PF>(b) - c.lane2), rp, map_u, map_b, map_c, map_sh);
+    }
+    const int jg = min(max(A.gp.grow0 + c.jbase + c.dir * r, 0), A.gp.ny_global - 1);
+    const float syr = C::TSY ? A.gp.sigma[jg] : 0.0f;   // (issued before the wait: its latency hides behind the row's arrival)
+    if (r < c.nm) {
+        mbar_wait(b.bar[0] + PH * 8, b.par);
+        const int uri = b.g[0] + PH * C::SLOT_F;
+        constexpr int s0 = PH & 3;
+        f2 U = lds2(uri);
+        if (A.tr_inj == 1) {   // the reference loop as written: the energy cotangent joins the incoming cotangent (halo cells too)
+            const f2 ut = lds2(uri + 6 * LW), ui = lds2(uri + 7 * LW), d = ut - ui;
+            U = U + (c.is_tot ? A.two_dO * (A.inj_w[0] * ut + A.inj_w[2] * d) : A.two_dO * (A.inj_w[1] * ui - A.inj_w[2] * d));
+            sts2(uri, U);   // (a TMA target: fenced below)
+        }
+        if (c.use_bk) {   // c^2 of the row at the three stage times (rows 8..10: no TMA load ever writes them)
+            if (c.nact < 0) {
+                speed_row_slow<V>(A, c.table, e, uri, c.xs, A.gp.y[jg], 1.0f);
+            } else {
+                const unsigned mask = r < ROWMASK_CAP ? reinterpret_cast<const unsigned short *>(&smf[C::MASK_OFF])[r] : (1u << c.nact) - 1u;
+                if (mask) {
+                    speed_row<V>(uri, mask, c.xs, A.gp.y[jg], A.gp.c0, 1.0f);
+                } else {
+                    sts2(uri + C::f_bk(0) * LW, bc2(A.gp.b0));
+                    sts2(uri + C::f_bk(1) * LW, bc2(A.gp.b0));
+                    sts2(uri + C::f_bk(2) * LW, bc2(A.gp.b0));
+                }
+            }
+        }
+        // stage 1 applies J^T at t + dt
+        const f2 c2 = c.use_bk ? lds2(uri + C::f_bk(2) * LW) : bc2(A.gp.b0);
+        R.Uf[0][s0] = C::TSX ? c2 * fma2(c.sx, lds2(uri + 3 * LW), U) : c2 * U;
+        R.Px[0][s0] = C::TSY ? c2 * fma2(syr, lds2(uri + 4 * LW), U) : c2 * U;
+        R.Vy[0][s0] = lds2(uri + 2 * LW);
+        if (A.tr_inj == 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    stage_TP<V, 1, PH>(c, A, b, R, r - 1);
+    stage_TP<V, 2, PH>(c, A, b, R, r - 2);
+    stage_TP<V, 3, PH>(c, A, b, R, r - 3);
+    stage_TP<V, 4, PH>(c, A, b, R, r - 4);
+    // sigma_y of march row r: first used by stage 1 in the next iteration (its window entry was row r - 4's until now)
+    if (C::TSY) R.sy[PH & 3] = syr;
+}
+
 // Body of one work item: blocks 2 k, 2 k + 1 of a variant's range are the total / incident wavefield of item k % n_items of
 // environment k / n_items.  `items` / `n_items` / `epart_off` describe the variant's slice of the work list.
 // PEER: this launch mirrors slab edge rows into the neighbours' ghost rows (a separate instantiation, so that the ordinary
@@ -931,7 +1080,7 @@ __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw
     c.need_w2 = ((gp.nx - 1 - item.x0) & 1) == 0;
     c.bcm = mk2((c.first_x || c.last_x) ? 0.0f : 1.0f, c.last_y ? 0.0f : 1.0f);
     c.xs = mk2(gp.x[min(colA, gp.nx - 1)], gp.x[min(colB, gp.nx - 1)]);  // columns past nx are never owned
-    c.sx = SX ? mk2(gp.sigma[min(colA, gp.nx - 1)], gp.sigma[min(colB, gp.nx - 1)]) : bc2(0.0f);
+    c.sx = (SX || C::TSX) ? mk2(gp.sigma[min(colA, gp.nx - 1)], gp.sigma[min(colB, gp.nx - 1)]) : bc2(0.0f);
     c.sxd = c.dirf * c.sx;
     const float *trow = table + (size_t)e * A.steps * STAGE_ROW;
     c.sf[0] = trow[3];
@@ -939,15 +1088,15 @@ __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw
     c.sf[2] = trow[5];
     // the source shape row rides along for every row of the windows that overlap the source's columns; the
     // other windows keep a zero row
-    c.src_win = !C::TR && ep.has_source && item.x0 < ep.src_i1 && item.x0 + LW > ep.src_i0 && ep.src_j1 > ep.src_j0;
-    c.zplane = C::TR ? A.zplane0 + 2 * e : 0;
+    c.src_win = !C::TR && !C::TP && ep.has_source && item.x0 < ep.src_i1 && item.x0 + LW > ep.src_i0 && ep.src_j1 > ep.src_j0;
+    c.zplane = (C::TR || C::TP) ? A.zplane0 + 2 * e : 0;
 
-    c.tx_bytes = C::TR ? 6 * (LW * 4) : (C::LEAN ? (4 + (c.want_e ? 1 : 0) + (c.src_win ? 1 : 0)) : ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0))) * (LW * 4);
+    c.tx_bytes = C::TR ? 6 * (LW * 4) : C::TP ? 8 * (LW * 4) : (C::LEAN ? (4 + (c.want_e ? 1 : 0) + (c.src_win ? 1 : 0)) : ((c.is_tot ? 7 : 6) + (c.src_win ? 1 : 0))) * (LW * 4);
     if (lane == 0) {
         for (int s = 0; s < C::RING; ++s) mbar_init(c.bar0 + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (!c.src_win && !C::TR)
+    if (!c.src_win && !C::TR && !C::TP)
         for (int s = 0; s < C::RING; ++s) sts2(s * C::SLOT_F + C::ROW_SH * LW + c.lane2, bc2(0.0f));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
@@ -1266,8 +1415,17 @@ struct FusedPlan {
     int rect[4] = {0, 0, 0, 0};
     int rect_state = 0;   // 0: not computed, 1: valid, -1: no rectangle
     int smem_tr = 0;
+    // the PML ring between the outer TP_OW cells of the domain and that rectangle, as work items of the variants 7 (left / right
+    // strips), 8 (top / bottom strips), 9 (corners): tp_off[k] .. tp_off[k+1] in d_tp_items; tp_ok: the ring exists
+    Item *d_tp_items = nullptr;
+    int tp_off[4] = {0, 0, 0, 0};
+    bool tp_ok = false;
+    int smem_tp = 0;
+    CUtensorMap map_w6[2];
+    const float *map_w6_base[2] = {nullptr, nullptr};
 };
 constexpr int PROFILE_PAIRS = 256;
+constexpr int TP_OW = 8;   // reverse pass: the outer cells of the domain that stay on the shared-memory tiles (all border logic lives there)
 
 FusedPlan *plan_of(waves_handle *h, bool create) {
     if (!h->plan && create) h->plan = new FusedPlan();
@@ -1446,6 +1604,64 @@ int fused_prepare(waves_handle *h) {
         p->rect_state = ok ? 1 : -1;
         p->rect[0] = x0, p->rect[1] = x1, p->rect[2] = y0, p->rect[3] = y1;
     }
+    std::vector<Item> tp[3];
+    p->tp_ok = false;
+    if (p->rect_state == 1 && (gp.nx & 3) == 0 && p->rect[0] - TP_OW >= 8 && gp.nx - TP_OW - p->rect[1] >= 8 && p->rect[2] - TP_OW >= 8 &&
+        gp.ny_global - TP_OW - p->rect[3] >= 8) {
+        // column windows of the side strips (56 owned columns at most, 4 halo columns each side inside the domain) and the column
+        // windows / row slabs of the interior items; row slabs of the top / bottom strips
+        struct Span { int x0, lo, hi; };
+        std::vector<Span> side, mid;
+        auto add_side = [&](int a, int b) {
+            for (int o = a; o < b; o += OWN_W) side.push_back({o - 4, o, std::min(o + OWN_W, b)});
+        };
+        add_side(TP_OW, p->rect[0]);
+        add_side(p->rect[1], gp.nx - TP_OW);
+        for (auto &cc : cols)
+            if (cc.interior) mid.push_back({cc.x0, cc.olo, cc.ohi});
+        std::vector<std::pair<int, int>> rmid, rtb;
+        for (auto &rr : rows)
+            if (rr.interior) rmid.push_back({rr.j0, rr.j1});
+        auto add_tb = [&](int a, int b) {
+            const int n = (b - a + SEG - 1) / SEG;
+            for (int k = 0; k < n; ++k) rtb.push_back({a + (int)((long long)(b - a) * k / n), a + (int)((long long)(b - a) * (k + 1) / n)});
+        };
+        add_tb(TP_OW, p->rect[2]);
+        add_tb(p->rect[3], gp.ny_global - TP_OW);
+        auto emit = [&](std::vector<Item> &dst, const std::vector<Span> &cs, const std::vector<std::pair<int, int>> &rs, int cls_id) {
+            for (auto &r2 : rs)
+                for (auto &c2 : cs) {
+                    Item it;
+                    it.x0 = c2.x0;
+                    it.vlo = c2.lo - c2.x0;
+                    it.vhi = c2.hi - c2.x0;
+                    it.j0 = r2.first;
+                    it.j1 = r2.second;
+                    it.la = r2.first - 4;
+                    it.lb = r2.second + 4;
+                    it.top = it.bot = 0;
+                    it.cls = cls_id;
+                    dst.push_back(it);
+                }
+        };
+        emit(tp[0], side, rmid, 7);
+        emit(tp[1], mid, rtb, 8);
+        emit(tp[2], side, rtb, 9);
+        p->tp_ok = !tp[0].empty() && !tp[1].empty() && !tp[2].empty();
+    }
+    if (p->d_tp_items) cudaFree(p->d_tp_items);
+    p->d_tp_items = nullptr;
+    if (p->tp_ok) {
+        std::vector<Item> tall;
+        for (int k = 0; k < 3; ++k) {
+            p->tp_off[k] = (int)tall.size();
+            tall.insert(tall.end(), tp[k].begin(), tp[k].end());
+        }
+        p->tp_off[3] = (int)tall.size();
+        if (cudaMalloc((void **)&p->d_tp_items, sizeof(Item) * tall.size()) != cudaSuccess ||
+            cudaMemcpy(p->d_tp_items, tall.data(), sizeof(Item) * tall.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+            p->tp_ok = false;
+    }
     if (p->d_items) cudaFree(p->d_items);
     cudaError_t ae = cudaMalloc((void **)&p->d_items, sizeof(Item) * (all.size() + 1));
     if (ae == cudaSuccess) ae = cudaMemcpy(p->d_items, all.data(), sizeof(Item) * all.size(), cudaMemcpyHostToDevice);
@@ -1481,6 +1697,10 @@ int fused_prepare(waves_handle *h) {
     p->smem_all = std::max(*std::max_element(p->smem, p->smem + 5), (int)(Cfg<WV_SMALL_SP2 ? 5 : 4>::WARP_F * 4));
     p->smem_tr = Cfg<6>::WARP_F * 4;
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_tr);
+    p->smem_tp = Cfg<9>::WARP_F * 4;
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_tp);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_tp);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_tp);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step_all<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_all);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_fused_step_all<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_all);
     if (ce != cudaSuccess) {
@@ -1518,6 +1738,7 @@ void fused_release(waves_handle *h) {
     FusedPlan *p = static_cast<FusedPlan *>(h->plan);
     if (!p) return;
     if (p->d_items) cudaFree(p->d_items);
+    if (p->d_tp_items) cudaFree(p->d_tp_items);
     if (p->d_epart) cudaFree(p->d_epart);
     if (p->d_bb) cudaFree(p->d_bb);
     if (p->d_bar) cudaFree(p->d_bar);
@@ -1866,11 +2087,70 @@ int launch_adjoint_interior_march(waves_handle *h, const float *w_in, float *w_o
     return 0;
 }
 
-void adjoint_march_join(waves_handle *h) {
+void adjoint_march_join(waves_handle *h, int ring) {
     FusedPlan *p = plan_of(h, false);
 #if WV_ADJ_CONCURRENT
     if (p) cudaStreamWaitEvent(h->stream, p->ev_join[0], 0);
+    if (p && ring) cudaStreamWaitEvent(h->stream, p->ev_join[1], 0);
 #else
     (void)p;
 #endif
+}
+
+// The PML ring of one fused reverse step on the march (V = 7, 8, 9, see stage_TP): everything between the outer TP_OW cells of the
+// domain and the rectangle launch_adjoint_interior_march owns.  Arguments as there; outer receives the rectangle
+// [TP_OW, nx - TP_OW) x [TP_OW, ny - TP_OW) the two march launches own together.  Runs on a side stream (adjoint_march_join orders
+// the next step after it).  Returns 0: launched; -1: no ring on this handle; 1: error.
+int launch_adjoint_ring_march(waves_handle *h, const float *w_in, float *w_out, const float *zbase, size_t zfloats, const float *z,
+                              const float *w3, int inj, const float *d_table, int steps, int step, int outer[4]) {
+    FusedPlan *p = plan_of(h, false);
+    if (!p || !p->tp_ok || !p->enc || h->peer_on) return -1;
+    const GridP &gp = h->gp;
+    PFN_encodeTiled enc = (PFN_encodeTiled)p->enc;
+    int wi = -1;
+    for (int k = 0; k < 2; ++k)
+        if (p->map_w6_base[k] == w_in) wi = k;
+    if (wi < 0) {
+        wi = p->map_w6_base[0] == nullptr ? 0 : (p->map_w6_base[1] == nullptr ? 1 : 0);
+        if (make_map(enc, &p->map_w6[wi], const_cast<float *>(w_in), gp, 12 * gp.n_env, 6)) return waves_set_error("reverse march: tensor map (cotangent, 6 planes) failed");
+        p->map_w6_base[wi] = w_in;
+    }
+    if (p->map_z_base != zbase || p->map_z_planes != zfloats / gp.plane) return waves_set_error("reverse march: the ring launch follows the interior launch of the same step");
+    FusedArgs A;
+    fused_fill_args(h, p, A, d_table, steps, step, false, -1);
+    A.out = w_out;
+    A.pconst = nullptr;
+    A.skip_aux = 1;
+    A.epart = nullptr;
+    A.kd = -A.kd;
+    A.akd_h = -A.akd_h;
+    A.akd_f = -A.akd_f;
+    A.dt6kd = -A.dt6kd;
+    A.tr_inj = w3 ? inj : 0;
+    for (int k = 0; k < 3; ++k) A.inj_w[k] = w3 ? w3[k] : 0.0f;
+    A.two_dO = 2.0f * h->d_omega;
+    A.zplane0 = (int)((z - zbase) / (ptrdiff_t)gp.plane);
+    A.epart_off = 0;
+#if WV_ADJ_CONCURRENT
+    cudaStream_t st = p->side[1];
+    cudaStreamWaitEvent(st, p->ev_fork, 0);   // (recorded by the interior launch of this step)
+#else
+    cudaStream_t st = h->stream;
+#endif
+    for (int k = 0; k < 3; ++k) {
+        const int n = p->tp_off[k + 1] - p->tp_off[k];
+        if (n <= 0) continue;
+        A.items = p->d_tp_items + p->tp_off[k];
+        A.n_items = n;
+        const unsigned grid = (unsigned)(2LL * n * gp.n_env);
+        if (k == 0) k_fused_step<7, false><<<grid, 32, p->smem_tp, st>>>(A, p->map_w6[wi], p->map_w6[wi], p->map_g, p->map_z);
+        if (k == 1) k_fused_step<8, false><<<grid, 32, p->smem_tp, st>>>(A, p->map_w6[wi], p->map_w6[wi], p->map_g, p->map_z);
+        if (k == 2) k_fused_step<9, false><<<grid, 32, p->smem_tp, st>>>(A, p->map_w6[wi], p->map_w6[wi], p->map_g, p->map_z);
+        h->launches++;
+    }
+#if WV_ADJ_CONCURRENT
+    cudaEventRecord(p->ev_join[1], st);
+#endif
+    outer[0] = TP_OW, outer[1] = gp.nx - TP_OW, outer[2] = TP_OW, outer[3] = gp.ny_global - TP_OW;
+    return 0;
 }

@@ -885,8 +885,9 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
     const GridP &gp = h->gp;
     if (!tspan || steps < 1 || !dL_dz0) return fail("waves_adjoint: need tspan, steps >= 1 and dL_dz0");
     if (gp.ny_own != gp.ny_global) return fail("waves_adjoint: not available on slab handles");
+    const int adj_flags = adj_mode;
     const bool stagewise = (adj_mode & WAVES_ADJ_STAGEWISE) != 0, tiles_only = (adj_mode & WAVES_ADJ_TILES) != 0;
-    adj_mode &= ~(WAVES_ADJ_STAGEWISE | WAVES_ADJ_TILES);
+    adj_mode &= ~(WAVES_ADJ_STAGEWISE | WAVES_ADJ_TILES | WAVES_ADJ_NO_RING);
     if (adj_mode != WAVES_ADJ_EXACT && adj_mode != WAVES_ADJ_COMPAT) return fail("waves_adjoint: unknown adjoint mode %d", adj_mode);
     if (fwd_mode != WAVES_MODE_FUSED && fwd_mode != WAVES_MODE_EXACT) return fail("waves_adjoint: unknown forward mode %d", fwd_mode);
     const size_t state = (size_t)gp.env_stride * gp.n_env, planes = (size_t)gp.plane * gp.n_env;
@@ -1010,6 +1011,7 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
     // those cells as ONE accumulated plane G, added to them after the sweep; the frame around it takes the shared-memory tiles.
     // march: -1 not decided yet (the first step tells whether the handle's work plan allows it), 0 tiles everywhere, 1 march.
     int march = (fused_rev && !tiles_only) ? -1 : 0;
+    int ring = (march && !(adj_flags & WAVES_ADJ_NO_RING)) ? -1 : 0;   // same convention, for the PML ring around the interior
     int rect[4] = {0, 0, 0, 0};
     if (march) {
         // the march never writes the auxiliary cotangents of its cells: both ping-pong buffers must hold the same (initial) values there
@@ -1080,9 +1082,18 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
                 march = rc == 0 ? 1 : 0;
             }
             if (march) {
-                if (launch_adjoint_step_frame(h, W, WS, b2v, pre ? zslot : nullptr, pre ? w3 : zero3, post ? zslot : nullptr, post ? w3 : zero3, rect))
+                // the PML ring on the march too where the handle has one: the tiles then keep the outer 8 cells of the domain
+                int frame[4] = {rect[0], rect[1], rect[2], rect[3]};
+                int rc2 = -1;
+                if (ring) {
+                    rc2 = launch_adjoint_ring_march(h, W, WS, h->traj, h->traj_cap, zslot, w3, pre ? 1 : 2, h->d_stage, rows, i, frame);
+                    if (rc2 == 1) return 1;
+                    if (rc2 < 0 && ring > 0) return fail("waves_adjoint: the ring march became unavailable in the middle of a sweep");
+                    ring = rc2 == 0 ? 1 : 0;
+                }
+                if (launch_adjoint_step_frame(h, W, WS, b2v, pre ? zslot : nullptr, pre ? w3 : zero3, post ? zslot : nullptr, post ? w3 : zero3, frame))
                     return 1;
-                adjoint_march_join(h);
+                adjoint_march_join(h, ring);
             } else if (launch_adjoint_step_fused(h, W, WS, b2v, pre ? zslot : nullptr, pre ? w3 : zero3, post ? zslot : nullptr, post ? w3 : zero3))
                 return 1;
             std::swap(W, WS);

@@ -167,7 +167,9 @@ int launch_fused_step(waves_handle *h, const float *d_table, int steps, int step
 int launch_fused_multi(waves_handle *h, const float *d_table, int steps, int step0, int count, bool energy);  // 0 done, -1 n/a, 1 error
 int launch_adjoint_interior_march(waves_handle *h, const float *w_in, float *w_out, float *G, const float *zbase, size_t zfloats,
                                   const float *z, const float *w3, int inj, const float *d_table, int steps, int step, int rect[4]);
-void adjoint_march_join(waves_handle *h);   // the handle's stream waits for the march kernel of the current reverse step
+int launch_adjoint_ring_march(waves_handle *h, const float *w_in, float *w_out, const float *zbase, size_t zfloats, const float *z,
+                              const float *w3, int inj, const float *d_table, int steps, int step, int outer[4]);
+void adjoint_march_join(waves_handle *h, int ring);   // the handle's stream waits for the march kernels of the current reverse step
 bool fused_is_small_batch(waves_handle *h);
 int fused_epart_slots(waves_handle *h);
 void fused_reduce_deferred(waves_handle *h, int count, float *d_e3, int env_stride3);

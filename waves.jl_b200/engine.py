@@ -11,7 +11,7 @@ from ._lib import check
 F32 = np.float32
 MODE_FUSED, MODE_EXACT = 0, 1
 STEP_ASYNC = 0x100
-ADJ_EXACT, ADJ_COMPAT, ADJ_STAGEWISE, ADJ_TILES = 0, 1, 0x100, 0x200
+ADJ_EXACT, ADJ_COMPAT, ADJ_STAGEWISE, ADJ_TILES, ADJ_NO_RING = 0, 1, 0x100, 0x200, 0x400
 
 
 def _ptr(a):
@@ -133,7 +133,7 @@ class Engine:
         check(_lib.lib().waves_set_adjoint_checkpoint(self._h, int(every)))
 
     def adjoint(self, tspan, w_energy=None, dL_dzN=None, fwd_mode=MODE_FUSED, adj_mode=ADJ_EXACT, want_dc=True, out_dz0=None,
-                out_dc=None, fused_reverse=True, march=True):
+                out_dc=None, fused_reverse=True, march=True, ring=True):
         """rrule(::Integrator) + adjoint_sensitivity (src/dynamics.jl:97-128) from the current state.
         Returns (loss (n_env,), dL/dz0 (n_env,12,ny,nx), dL/dc (n_env,ny,nx) | None); out_dz0 / out_dc may be preallocated
         NumPy arrays or CUDA tensors (the gradients of a large batch are best left on the device)."""
@@ -147,6 +147,8 @@ class Engine:
         loss = np.zeros(self.n_env, dtype=F32)
         if not fused_reverse:
             adj_mode |= ADJ_STAGEWISE   # per-stage reverse kernels even without dL/dc (cross-check of the fused reverse step)
+        if not ring:
+            adj_mode |= ADJ_NO_RING     # the march kernel takes the interior only (cross-check of the PML-ring variants)
         if not march:
             adj_mode |= ADJ_TILES       # fused reverse step on the shared-memory tiles everywhere (cross-check of the march kernel)
         check(_lib.lib().waves_adjoint(self._h, ts.ctypes.data_as(_lib.fp), steps, fwd_mode, adj_mode, _ptr(we), _ptr(an),
