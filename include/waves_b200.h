@@ -48,6 +48,8 @@ typedef struct waves_handle waves_handle;
 #define WAVES_ADJ_COMPAT 1 /* the reference loop as written (one extra step-vjp) */
 #define WAVES_ADJ_STAGEWISE 0x100 /* OR into adj_mode: reverse sweep with the per-stage kernels even without dL_dc (cross-check) */
 #define WAVES_ADJ_NO_RING 0x400   /* OR into adj_mode: the marching kernel takes the interior only, the whole PML frame stays on tiles */
+#define WAVES_ADJ_RING 0x800      /* OR into adj_mode: the PML ring on the marching kernel even for a small batch (default: batches of
+                                     >= 2 M cells; a single environment is latency-bound and better off with fewer launches) */
 #define WAVES_ADJ_TILES 0x200     /* OR into adj_mode: the fused reverse step takes the shared-memory tile kernels everywhere instead of
                                      the marching kernel in the interior (cross-check of the two) */
 

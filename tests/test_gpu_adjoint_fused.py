@@ -28,7 +28,7 @@ def test_fused_reverse_matches_autograd_and_per_stage_kernels(n, pml_width, adj_
     for fwd in (wb.MODE_EXACT, wb.MODE_FUSED):
         eng.set_state(z0[None])
         n0 = eng.launch_count()
-        loss, dz0, none = eng.adjoint(ts, w, aN[None], fwd_mode=fwd, adj_mode=adj_mode, want_dc=False)
+        loss, dz0, none = eng.adjoint(ts, w, aN[None], fwd_mode=fwd, adj_mode=adj_mode, want_dc=False, ring="always")
         assert none is None and rel(dz0[0], want) < TOL, (fwd, rel(dz0[0], want))
         for f in range(12):
             assert rel(dz0[0, f], want[f]) < 5 * TOL, f"field {f}"
@@ -178,7 +178,7 @@ def test_march_pml_ring_equals_tile_kernels(n, pml_width, adj_mode):
     steps = 7
     p, eng, ts, z0, w, aN = setup(n=n, steps=steps, pml_width=pml_width)
     outs = []
-    for kw in (dict(), dict(ring=False), dict(march=False)):
+    for kw in (dict(ring="always"), dict(ring=False), dict(march=False)):   # (a single small environment skips the ring by default)
         eng.set_state(z0[None])
         l0 = eng.launch_count()
         loss, dz0, _ = eng.adjoint(ts, w, aN[None], adj_mode=adj_mode, want_dc=False, **kw)

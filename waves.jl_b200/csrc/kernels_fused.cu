@@ -2091,7 +2091,10 @@ void adjoint_march_join(waves_handle *h, int ring) {
     FusedPlan *p = plan_of(h, false);
 #if WV_ADJ_CONCURRENT
     if (p) cudaStreamWaitEvent(h->stream, p->ev_join[0], 0);
-    if (p && ring) cudaStreamWaitEvent(h->stream, p->ev_join[1], 0);
+    if (p && ring) {
+        cudaStreamWaitEvent(h->stream, p->ev_join[1], 0);
+        cudaStreamWaitEvent(h->stream, p->ev_join[2], 0);
+    }
 #else
     (void)p;
 #endif
@@ -2132,14 +2135,18 @@ int launch_adjoint_ring_march(waves_handle *h, const float *w_in, float *w_out, 
     A.zplane0 = (int)((z - zbase) / (ptrdiff_t)gp.plane);
     A.epart_off = 0;
 #if WV_ADJ_CONCURRENT
-    cudaStream_t st = p->side[1];
-    cudaStreamWaitEvent(st, p->ev_fork, 0);   // (recorded by the interior launch of this step)
-#else
-    cudaStream_t st = h->stream;
+    // side strips on one side stream, top / bottom strips and corners on another (ev_fork: recorded by the interior launch of this step)
+    cudaStreamWaitEvent(p->side[1], p->ev_fork, 0);
+    cudaStreamWaitEvent(p->side[2], p->ev_fork, 0);
 #endif
     for (int k = 0; k < 3; ++k) {
         const int n = p->tp_off[k + 1] - p->tp_off[k];
         if (n <= 0) continue;
+#if WV_ADJ_CONCURRENT
+        cudaStream_t st = k == 0 ? p->side[1] : p->side[2];
+#else
+        cudaStream_t st = h->stream;
+#endif
         A.items = p->d_tp_items + p->tp_off[k];
         A.n_items = n;
         const unsigned grid = (unsigned)(2LL * n * gp.n_env);
@@ -2149,7 +2156,8 @@ int launch_adjoint_ring_march(waves_handle *h, const float *w_in, float *w_out, 
         h->launches++;
     }
 #if WV_ADJ_CONCURRENT
-    cudaEventRecord(p->ev_join[1], st);
+    cudaEventRecord(p->ev_join[1], p->side[1]);
+    cudaEventRecord(p->ev_join[2], p->side[2]);
 #endif
     outer[0] = TP_OW, outer[1] = gp.nx - TP_OW, outer[2] = TP_OW, outer[3] = gp.ny_global - TP_OW;
     return 0;

@@ -887,7 +887,7 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
     if (gp.ny_own != gp.ny_global) return fail("waves_adjoint: not available on slab handles");
     const int adj_flags = adj_mode;
     const bool stagewise = (adj_mode & WAVES_ADJ_STAGEWISE) != 0, tiles_only = (adj_mode & WAVES_ADJ_TILES) != 0;
-    adj_mode &= ~(WAVES_ADJ_STAGEWISE | WAVES_ADJ_TILES | WAVES_ADJ_NO_RING);
+    adj_mode &= ~(WAVES_ADJ_STAGEWISE | WAVES_ADJ_TILES | WAVES_ADJ_NO_RING | WAVES_ADJ_RING);
     if (adj_mode != WAVES_ADJ_EXACT && adj_mode != WAVES_ADJ_COMPAT) return fail("waves_adjoint: unknown adjoint mode %d", adj_mode);
     if (fwd_mode != WAVES_MODE_FUSED && fwd_mode != WAVES_MODE_EXACT) return fail("waves_adjoint: unknown forward mode %d", fwd_mode);
     const size_t state = (size_t)gp.env_stride * gp.n_env, planes = (size_t)gp.plane * gp.n_env;
@@ -1011,7 +1011,10 @@ extern "C" int waves_adjoint(waves_handle *h, const float *tspan, int steps, int
     // those cells as ONE accumulated plane G, added to them after the sweep; the frame around it takes the shared-memory tiles.
     // march: -1 not decided yet (the first step tells whether the handle's work plan allows it), 0 tiles everywhere, 1 march.
     int march = (fused_rev && !tiles_only) ? -1 : 0;
-    int ring = (march && !(adj_flags & WAVES_ADJ_NO_RING)) ? -1 : 0;   // same convention, for the PML ring around the interior
+    // same convention, for the PML ring around the interior: three more launches per step, which pay once the batch is
+    // throughput-bound (measured: 32 x 700^2 32.0 -> 36.2 Gcell-updates/s, one 700^2 environment 0.036 -> 0.040 s)
+    const bool ring_pays = (long long)gp.n_env * gp.nx * gp.ny_global >= 2000000LL || (adj_flags & WAVES_ADJ_RING);
+    int ring = (march && ring_pays && !(adj_flags & WAVES_ADJ_NO_RING)) ? -1 : 0;
     int rect[4] = {0, 0, 0, 0};
     if (march) {
         // the march never writes the auxiliary cotangents of its cells: both ping-pong buffers must hold the same (initial) values there

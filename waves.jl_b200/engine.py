@@ -11,7 +11,7 @@ from ._lib import check
 F32 = np.float32
 MODE_FUSED, MODE_EXACT = 0, 1
 STEP_ASYNC = 0x100
-ADJ_EXACT, ADJ_COMPAT, ADJ_STAGEWISE, ADJ_TILES, ADJ_NO_RING = 0, 1, 0x100, 0x200, 0x400
+ADJ_EXACT, ADJ_COMPAT, ADJ_STAGEWISE, ADJ_TILES, ADJ_NO_RING, ADJ_RING = 0, 1, 0x100, 0x200, 0x400, 0x800
 
 
 def _ptr(a):
@@ -147,8 +147,10 @@ class Engine:
         loss = np.zeros(self.n_env, dtype=F32)
         if not fused_reverse:
             adj_mode |= ADJ_STAGEWISE   # per-stage reverse kernels even without dL/dc (cross-check of the fused reverse step)
-        if not ring:
+        if ring is False:
             adj_mode |= ADJ_NO_RING     # the march kernel takes the interior only (cross-check of the PML-ring variants)
+        elif ring == "always":
+            adj_mode |= ADJ_RING        # ... and the PML ring on the march even for a small (latency-bound) batch
         if not march:
             adj_mode |= ADJ_TILES       # fused reverse step on the shared-memory tiles everywhere (cross-check of the march kernel)
         check(_lib.lib().waves_adjoint(self._h, ts.ctypes.data_as(_lib.fp), steps, fwd_mode, adj_mode, _ptr(we), _ptr(an),
