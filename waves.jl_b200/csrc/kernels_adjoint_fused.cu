@@ -27,6 +27,8 @@
 // each 4 * 512 floats, pitched to the region width so that consecutive threads touch consecutive banks.  Two variants:
 // INTERIOR tiles (sigma == 0 in the whole tile region, away from the domain border: mask 1, central stencils only, the three
 // auxiliary cotangents never feed back and are only accumulated) and general tiles.
+#include <stdint.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -566,7 +568,14 @@ int launch_adjoint_step_fused(waves_handle *h, const float *w_in, float *w_out, 
 }
 
 void launch_gather_u(waves_handle *h, const float *u, float *out) {
-    dim3 grd((unsigned)((h->gp.plane + 255) / 256), h->gp.n_env * 2);
-    k_gather_u<<<grd, 256, 0, h->stream>>>(h->gp, u, out);
+    const GridP &gp = h->gp;
+    if ((gp.plane & 3) == 0 && (((uintptr_t)u | (uintptr_t)out) & 15u) == 0) {
+        // two strided block copies (U of the total field, U of the incident field) at the HBM copy rate (float4, streaming)
+        launch_copy_blocks(h, u, out, (long long)gp.plane, (long long)gp.env_stride, 2LL * gp.plane, gp.n_env);
+        launch_copy_blocks(h, u + 6 * gp.plane, out + gp.plane, (long long)gp.plane, (long long)gp.env_stride, 2LL * gp.plane, gp.n_env);
+        return;
+    }
+    dim3 grd((unsigned)((gp.plane + 255) / 256), gp.n_env * 2);
+    k_gather_u<<<grd, 256, 0, h->stream>>>(gp, u, out);
     h->launches++;
 }
