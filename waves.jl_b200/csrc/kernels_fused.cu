@@ -26,9 +26,12 @@
 //    border row is always the last row of the march; when a stage has produced it, the row beyond it is
 //    filled with the quadratic extrapolation 3 v[n-1] - 3 v[n-2] + v[n-3], which turns the central
 //    difference of the next stage into the reference's one-sided stencil (v[n-3] - 4 v[n-2] + 3 v[n-1]).
-//  * five variants (template V): interior (sigma == 0 in the warp's window: Psi/Omega pass through) in a full and a
+//  * five forward variants (template V): interior (sigma == 0 in the warp's window: Psi/Omega pass through) in a full and a
 //    lean form (the lean one reads the constant P = Psix + Psiy - Omega from a plane of its own), left-right PML strips
-//    (only Psix evolves), top-bottom PML strips (only Psiy evolves), corners (everything).
+//    (only Psix evolves), top-bottom PML strips (only Psiy evolves), corners (everything);
+//  * the REVERSE pass runs on the same march (stage_T / stage_TP further down): V = 6 is the transposed step of the interior,
+//    V = 7, 8, 9 of the PML ring (left-right strips, top-bottom strips, corners) at least 8 cells away from the domain border.
+//    V = 5 is the lean interior with the stages two rows apart (built, measured, off).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
