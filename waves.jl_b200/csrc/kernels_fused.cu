@@ -78,6 +78,9 @@ namespace {
                         // single 700^2 environment: 31.5 -> 45.7 us per step -- CTAs that become resident as slots free up no longer land
                         // round-robin on the SMs, which breaks the per-SM grouping by variant (k_fused_step_all) the step's speed rests on
 #endif
+#ifndef WV_SIDE_PRIO
+#define WV_SIDE_PRIO 0   // stream priority of the side streams (PML variants): 0 default, 1 highest, -1 lowest
+#endif
 #ifndef WV_ADJ_CONCURRENT
 #define WV_ADJ_CONCURRENT 1  // reverse pass: the march kernel of the interior runs beside the tile kernel of the frame (side stream,
                              // event fork / join; the two touch disjoint cells).  (Its first form gave intermittently wrong gradients:
@@ -1676,7 +1679,15 @@ int fused_prepare(waves_handle *h) {
     if (ae == cudaSuccess) ae = cudaMalloc((void **)&p->d_bb, sizeof(int) * 4);
     if (ae == cudaSuccess) ae = cudaMalloc((void **)&p->d_bar, sizeof(unsigned));
     for (int k = 0; k < 3 && ae == cudaSuccess; ++k) {
+#if WV_SIDE_PRIO
+        {   // side streams at the lowest / highest priority: their CTAs go last / first when slots free up
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            ae = cudaStreamCreateWithPriority(&p->side[k], cudaStreamNonBlocking, WV_SIDE_PRIO > 0 ? hi : lo);
+        }
+#else
         ae = cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking);
+#endif
         if (ae == cudaSuccess) ae = cudaEventCreateWithFlags(&p->ev_join[k], cudaEventDisableTiming);
     }
     if (ae == cudaSuccess) ae = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
