@@ -13,7 +13,8 @@ eight ("scaling": "strong").  `--envs-per-gpu E` fixes the per-GPU batch instead
 Sub-records after the headline (each bounded to a few seconds; --no-extras skips them):
   "weak"        the 128-environments-per-GPU shard at N = 1 (the round-1 headline, for continuity)
   "single_env"  BASELINE configs[1]: one 700^2 WaveEnv, us per RK4 step of env(action) (N = 1)
-  "adjoint"     BASELINE configs[4]: gradient of the scattered energy through 500 steps, forward + reverse (N = 1)
+  "adjoint"     BASELINE configs[4]: gradient of the scattered energy through 500 steps, forward + reverse, one environment and a
+                batch of 32 x 100 steps (N = 1)
   "slab"        BASELINE configs[3]: one 16384^2 grid slab-decomposed over the N GPUs, NVLink peer-memory halo (N > 1)
 """
 import argparse
@@ -273,8 +274,10 @@ def run_ours(args):
             try:
                 import bench_adjoint
                 extras["adjoint"] = bench_adjoint.measure(steps=500, E=1, device=local)
+                b32 = bench_adjoint.measure(steps=100, E=32, device=local, with_dc=False, check_exact=False)
+                extras["adjoint"]["batch_32_envs_100_steps"] = {k: b32[k] for k in ("forward_only_seconds", "seconds", "value", "reverse_Gcell_per_s")}
             except Exception as ex:
-                extras["adjoint"] = {"error": repr(ex)[:300]}
+                extras.setdefault("adjoint", {})["error"] = repr(ex)[:300]
             out.update(extras)
             out["single_env_us_per_step"] = extras.get("single_env", {}).get("single_env_us_per_step")
         else:
