@@ -190,3 +190,44 @@ def test_march_pml_ring_equals_tile_kernels(n, pml_width, adj_mode):
         for f in range(12):
             assert rel(outs[k][1][0, f], np.float64(outs[2][1][0, f])) < 2e-6, f"form {k} field {f}: {rel(outs[k][1][0, f], np.float64(outs[2][1][0, f]))}"
     eng.close()
+
+
+def test_march_pml_ring_with_cylinders_in_the_ring_and_a_batch():
+    """The ring variants evaluate c^2 from the culled cylinders like the forward speed field: a moving cylinder that reaches into
+    the PML ring (but not into the outer 8 cells), three environments with different designs on one handle, ring + interior on
+    the march against the tiles everywhere, and every environment of the batch against its own single-environment run."""
+    n, steps, dt = 256, 6, 4e-6
+    dim = wb.TwoDim(2.0, n)
+    ts = wb.build_tspan(2e-4, dt, steps)
+    rng = np.random.default_rng(11)
+    z0 = (rng.standard_normal((3, 12, n, n)) * 1e-3).astype(F32)
+    w = rng.uniform(0.2, 1.0, (steps + 1, 3)).astype(F32)
+    shape = wb.build_normal(dim, [[-0.8, 0.2]], [0.2], [1.0])
+    designs = [(np.array([[1.30, 0.20, 0.40, 1032.0], [-0.2, -1.35, 0.30, 2100.0]], F32), np.array([[1.35, 0.15, 0.45, 1032.0], [-0.2, -1.40, 0.35, 2100.0]], F32)),
+               (np.array([[0.40, 0.00, 0.45, 1032.0], [-1.3, 1.30, 0.35, 900.0]], F32), np.array([[0.45, 0.05, 0.50, 1032.0], [-1.35, 1.35, 0.30, 900.0]], F32)),
+               None]
+
+    def make(n_env, which):
+        eng = wb.Engine(dim.x, dim.y, wb.WATER, dt, 0.6, 20000.0, n_env=n_env)
+        for e, k in enumerate(which):
+            eng.set_source(shape, 1000.0, env=e)
+            if designs[k] is None:
+                eng.set_design(None, None, 0, 0, env=e)
+            else:
+                eng.set_design(designs[k][0], designs[k][1], ts[0], ts[-1], env=e)
+        return eng
+
+    eng = make(3, (0, 1, 2))
+    outs = []
+    for kw in (dict(ring="always"), dict(march=False)):
+        eng.set_state(z0)
+        outs.append(eng.adjoint(ts, w, want_dc=False, **kw)[:2])
+    for e in range(3):
+        assert rel(outs[0][1][e], np.float64(outs[1][1][e])) < 2e-6 and outs[0][0][e] == outs[1][0][e], e
+    eng.close()
+    for e in range(3):
+        one = make(1, (e,))
+        one.set_state(z0[e:e + 1])
+        l1, g1, _ = one.adjoint(ts, w, want_dc=False, ring="always")
+        assert np.array_equal(g1[0], outs[0][1][e]) and l1[0] == outs[0][0][e], e
+        one.close()
