@@ -78,6 +78,10 @@ namespace {
                         // single 700^2 environment: 31.5 -> 45.7 us per step -- CTAs that become resident as slots free up no longer land
                         // round-robin on the SMs, which breaks the per-SM grouping by variant (k_fused_step_all) the step's speed rests on
 #endif
+#ifndef WV_EARLY_TMA
+#define WV_EARLY_TMA 1   // the TMA loads of the first PF rows are issued before the cylinder cull instead of after it (measured:
+                         // 128 x 700^2 1036 -> 1030 us per launch set, 1024 x 700^2 7714 -> 7693, one environment 33.7 -> 33.1 us per step)
+#endif
 #ifndef WV_SIDE_PRIO
 #define WV_SIDE_PRIO 0   // stream priority of the side streams (PML variants): 0 default, 1 highest, -1 lowest
 #endif
@@ -1106,6 +1110,19 @@ __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw
         for (int s = 0; s < C::RING; ++s) sts2(s * C::SLOT_F + C::ROW_SH * LW + c.lane2, bc2(0.0f));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
+#if WV_EARLY_TMA
+    // the first PF rows are requested before the cull: their flight time hides behind it (nothing below touches a TMA row)
+    {
+        const CUtensorMap *map_e = (C::LEAN || c.is_tot) ? &map_u7 : &map_u6;
+        if (PDL) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+#pragma unroll
+        for (int rp = 0; rp < PF; ++rp)
+            if (rp < c.nm) issue_row<V>(c, e, c.bar0 + rp * 8, c.ring_sa + 4u * (uint32_t)(rp * C::SLOT_F), rp, map_e, &map_u6, &map_c, &map_sh);
+    }
+#endif
 
     // cull the design's cylinders against this warp's window, at the three stage times (src/designs.jl:287-292)
     c.nact = 0;
@@ -1216,6 +1233,7 @@ __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw
     // Programmatic dependent launch (small batches): everything above -- the cull, the row masks, the mbarriers -- reads nothing
     // the previous step wrote, so this CTA may run it while the last CTAs of the previous step are still marching; the state is
     // only touched (TMA loads below, stores in the march) once that grid has completed and its writes are visible.
+#if !WV_EARLY_TMA
     if (PDL) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
@@ -1223,6 +1241,7 @@ __device__ __forceinline__ void fused_step_body(const FusedArgs &A, long long gw
 #pragma unroll
     for (int rp = 0; rp < PF; ++rp)
         if (rp < c.nm) issue_row<V>(c, e, c.bar0 + rp * 8, c.ring_sa + 4u * (uint32_t)(rp * C::SLOT_F), rp, map_u, &map_u6, &map_c, &map_sh);
+#endif
     b.po = c.out_e + (long long)(c.jbase - 4 * C::SP * c.dir) * (int)A.nxp;  // stage 4 of body row rb works on march row rb - 4 SP
     int grp = 0;  // group of body k = k mod NG
     b.par = 0;    // rows of body k are use number k div NG of their slots
