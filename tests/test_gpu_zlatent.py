@@ -188,3 +188,37 @@ def test_adjoint_accepts_float64_cotangents_and_vector_tspan():
     got = it.adjoint(z, cs["tspan"][0], _theta(cs), w_energy=wE, dL_dz=np.asfortranarray(gz))
     for name in ("z0", "Y", "shape", "pml"):
         assert np.array_equal(got[name], want[name]), name
+
+
+def test_reference_adjoint_sensitivity_script():
+    """scripts/adjoint_sensitivity.jl as written: OneDim(15, 1024), AcousticDynamics(dim, WATER, 5, 10000), dt = 1e-5, N = 300 steps,
+    one sample, C = LinearInterpolation(t[[1, end], :], ones), F = Source(zeros, 1), PML = dyn.pml / maximum(dyn.pml), loss =
+    mse(z[:, 1, 1, end], target): the gradient with respect to z0 (what `back(one(loss))` pulls through the Integrator rrule)
+    against float64 autograd, with the default kernels and the generic ones."""
+    n, steps = 1024, 300
+    cs = make_case(n=n, batch=1, steps=steps, nseq=2, seed=3, gs=15.0, dt=1e-5, c0=wo.WATER, pml_width=5.0, pml_scale=10000.0, freq=1.0)
+    th = cs["theta"]
+    pml = (cs["dyn"].pml / cs["dyn"].pml.max())[None, :].astype(F32)
+    cs["theta"] = lo.LatentTheta(X=np.ascontiguousarray(cs["tspan"][:, [0, -1]]), Y=np.ones_like(th.Y), shape=np.zeros_like(th.shape),
+                                 freq=F32(1.0), pml=pml)
+    x = cs["dim"].x.astype(np.float64)
+    rng = np.random.default_rng(0)
+    # z0 = emb(freq_coefs): a smooth, small superposition of sines per field (SinWaveEmbedder), 50 frequencies
+    k = np.arange(1, 51)[:, None]
+    z0 = (0.01 * rng.standard_normal((4, 50)) @ np.sin(np.pi * k * (x[None, :] - x[0]) / (x[-1] - x[0]))).astype(F32)
+    cs["z0"] = z0[None]
+    target = np.exp(-0.5 * (x / 0.3) ** 2).astype(F32)   # build_normal(x, [0], [0.3], [1])
+    it = _integrator(cs, pml_width=5.0, pml_scale=10000.0)
+    z = it(cs["z0"], cs["tspan"], _theta(cs))
+    assert np.array_equal(z, lo.integrate(cs["dyn"], cs["z0"], cs["tspan"], cs["theta"], cs["dt"]))
+    dL_dz = np.zeros_like(z)
+    dL_dz[-1, 0, 0] = (2.0 / n) * (z[-1, 0, 0] - target)   # d mse(z[:, 1, 1, end], target) / dz
+    want = lao.adjoint_truth(cs, None, dL_dz, compat=False, z_stored=z)
+    g = it.adjoint(z, cs["tspan"], _theta(cs), dL_dz=dL_dz)
+    it.set_generic(True)
+    gg = it.adjoint(z, cs["tspan"], _theta(cs), dL_dz=dL_dz)
+    for got in (g, gg):
+        err = np.linalg.norm(got["z0"] - want["z0"]) / np.linalg.norm(want["z0"])
+        assert err < 1e-4, err
+    assert np.linalg.norm(want["z0"]) > 0
+    it.close()
