@@ -55,6 +55,10 @@ def test_create_fails_loudly_without_gpu():
 
 @pytest.mark.parametrize("gs,n", [(15.0, 700), (5.0, 512), (3.0, 96), (2.0, 33)])
 def test_host_builders_match_oracle(gs, n):
+    """Self-consistency, not an independent pin: the product's host builders (C ABI) and the oracle's are the same derivation of
+    the reference's formulas typed twice (Float32 ranges evaluated in Float64, src/dims.jl:56-60; PML profile src/pml.jl:21-29;
+    gradient rows src/operators.jl:10-22).  What this catches is drift between the two; what pins either is Julia
+    (tests/golden/make_reference_vectors.jl).  The GPU parity tests at 700^2 run the product's OWN builders against the oracle."""
     d = wb.TwoDim(gs, n)
     o = wo.TwoDim.make(gs, n)
     assert np.array_equal(d.x, o.x) and np.array_equal(d.y, o.y)
@@ -66,6 +70,7 @@ def test_host_builders_match_oracle(gs, n):
 
 
 def test_tspan_matches_oracle():
+    """Self-consistency of the two statements of build_tspan (src/dynamics.jl:5-7), see test_host_builders_match_oracle."""
     for ts, steps in [(0, 100), (100, 100), (1900, 100), (37, 13)]:
         ti = F32(F32(ts) * F32(1e-5))
         assert np.array_equal(wb.build_tspan(ti, 1e-5, steps), wo.build_tspan(ti, 1e-5, steps))
